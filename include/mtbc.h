@@ -1,0 +1,267 @@
+/*
+ * mtbc.h -- C ABI of the B200-native (sm_100a) kernels behind the multi-task encoder-decoder hot path of
+ * caumente/multi_task_breast_cancer.
+ *
+ * The reference has no FFI layer of its own: its operator API is torch.nn modules.  Each entry
+ * point below names the reference call site (file:line under /root/reference) whose ATen/cuDNN work it replaces.
+ * Everything is plain C: raw device pointers, sizes, a cudaStream_t passed as void*.  All launches are asynchronous
+ * and stream ordered; functions return 0 on success or a negative mtbc_status (never abort, never synchronise).
+ *
+ * Activation layout everywhere: bf16, NHWC, channel count padded to a multiple of 32 ("Cp"); pad lanes are kept 0.
+ */
+#ifndef MTBC_H_
+#define MTBC_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum mtbc_status {
+  MTBC_OK = 0,
+  MTBC_ERR_INVALID = -1, /* bad argument / unsupported shape        */
+  MTBC_ERR_CUDA = -2,    /* CUDA runtime or driver call failed       */
+  MTBC_ERR_NO_DEVICE = -3 /* no sm_100 device / driver entry missing */
+};
+
+/* Human readable text for the last error raised on the calling thread. */
+const char* mtbc_last_error(void);
+/* Library ABI version (bumped on any struct change). */
+int mtbc_abi_version(void);
+/* 0 if the current device is sm_100 and the tensor-map driver entry point resolves. */
+int mtbc_device_check(void);
+
+/* ------------------------------------------------------------------------------------------------------------- */
+/* Strided NHWC view of a bf16 activation (channel stride 1).  Strides in elements.                               */
+typedef struct {
+  const void* ptr;
+  int32_t C, W, H, N;
+  int64_t sW, sH, sN;
+} mtbc_act_view;
+
+/* One K-segment of the implicit GEMM: a (tap, source) pair.  The A box of a 128-pixel tile is read from
+ * views[view] shifted by (dh, dw) (out-of-range pixels read as 0 = the conv's zero padding); the matching B rows
+ * are wpack[wtap][n][wk0 + c]. */
+typedef struct {
+  int32_t view, dh, dw, wk0, wtap;
+} mtbc_gemm_seg;
+
+#define MTBC_MAX_VIEWS 8
+#define MTBC_MAX_SEGS 48
+
+/* Implicit-GEMM forward/data-gradient op on tcgen05 tensor cores (TMA-fed, TMEM accumulators):
+ *   D[pixel (n,h,w)][col] = sum_seg sum_c  A_seg[pixel + (dh,dw)][c] * wpack[wtap][col][wk0 + c]
+ * Replaces: nn.Conv2d 3x3 forward  (MTnnUNet.py:12-16,34; MONAI Convolution via MTUNetPlusPlus.py:47-71) with the
+ * skip concatenation (MTUNetPlusPlus.py:107-118, MTnnUNet.py:161-169) folded in as extra segments; its data gradient
+ * (aten::convolution_backward); nn.ConvTranspose2d k=s forward and data gradient (MTnnUNet.py:96-100, MONAI UpCat).
+ * epi_mode 0: out[n,h,w,col] (bf16, channel stride out_C);  1: pixel shuffle, col = q*up_cp + co, q = i*up_k + j,
+ * out[n, up_k*h+i, up_k*w+j, co].  bias (fp32[ncols or up_cp]) optional.  stat_sum/stat_sq (fp32 [N][stat_C]) optional:
+ * per-(n,channel) sum and sum of squares of the fp32 result = InstanceNorm statistics (MTnnUNet.py:35).
+ * accumulate != 0: out += D (gradient accumulation for tensors with several consumers). */
+typedef struct {
+  int32_t nviews;
+  mtbc_act_view views[MTBC_MAX_VIEWS];
+  int32_t nseg;
+  mtbc_gemm_seg seg[MTBC_MAX_SEGS];
+  const void* wpack; /* bf16 [w_ntaps][ncols][w_ktot] */
+  int32_t w_ntaps, w_ktot;
+  int32_t ncols;   /* GEMM N (padded)           */
+  int32_t W, H, N; /* GEMM row space = pixels   */
+  int32_t epi_mode;
+  void* out;
+  int32_t out_C;
+  int32_t up_k, up_cp;
+  const float* bias;
+  float* stat_sum;
+  float* stat_sq;
+  int32_t stat_C;
+  int32_t accumulate;
+} mtbc_conv_gemm_desc;
+
+/* One tap of a weight-gradient GEMM: dW[tap][co][k0 + ci] += sum_pixels A[a_view][pixel + (a_dh,a_dw)][ci] *
+ * B[b_view][pixel][co]. */
+typedef struct {
+  int32_t a_view, a_dh, a_dw, b_view;
+} mtbc_wgrad_tap;
+
+/* Weight gradient on tcgen05 (both operands MN-major, reduction over pixels, split over CTAs, fp32 atomics into a
+ * zeroed accumulator laid out like wpack: dw_acc[tap][row][ld_k]).
+ * Replaces: aten::convolution_backward weight path for Conv2d 3x3 and ConvTranspose2d k=s. */
+typedef struct {
+  int32_t a_nviews;
+  mtbc_act_view a_views[4];
+  int32_t b_nviews;
+  mtbc_act_view b_views[4];
+  int32_t ntaps;
+  mtbc_wgrad_tap taps[9];
+  int32_t W, H, N; /* pixel grid reduced over */
+  float* dw_acc;
+  int32_t n_rows; /* rows per tap plane of dw_acc (>= b C) */
+  int32_t ld_k;   /* row length of dw_acc                   */
+  int32_t k0;     /* column offset of this source           */
+  int32_t splits; /* 0 = auto */
+} mtbc_wgrad_desc;
+
+typedef struct mtbc_op mtbc_op; /* opaque: encoded tensor maps + launch geometry */
+
+int mtbc_conv_gemm_create(const mtbc_conv_gemm_desc* d, mtbc_op** out);
+int mtbc_wgrad_create(const mtbc_wgrad_desc* d, mtbc_op** out);
+int mtbc_op_launch(mtbc_op* op, void* stream);
+int mtbc_ops_launch(mtbc_op* const* ops, int32_t n, void* stream);
+void mtbc_op_destroy(mtbc_op* op);
+/* Algorithmic FLOPs (2*M*N*K over padded dims) of one launch of the op, for roofline accounting. */
+double mtbc_op_flops(const mtbc_op* op);
+
+/* ------------------------------------------------------------------------------------------------------------- */
+/* Weight packing.  fp32 parameters in PyTorch layout -> bf16 GEMM operands (run once per optimizer step).        */
+
+/* Conv2d weight [Cout][Cin][kh][kw] (fp32) -> forward pack  wf[tap][co (rows=ncols)][ld_k] at column k0.. (tap =
+ * r*kw+s) and, if wd != NULL, data-gradient pack wd[tap'][ci (rows=wd_rows)][wd_ld] with tap' = flipped tap,
+ * for the channel slice [c_begin, c_begin+c_count) of Cin (one concat source). */
+int mtbc_pack_conv_weight(const float* w, int32_t Cout, int32_t Cin, int32_t ksz, int32_t c_begin, int32_t c_count,
+                          void* wf, int32_t wf_rows, int32_t wf_ld, int32_t wf_k0, void* wd, int32_t wd_rows,
+                          int32_t wd_ld, void* stream);
+/* ConvTranspose2d weight [Cin][Cout][k][k] (fp32) -> forward pack wf[0][q*cp + co][ci] (q = i*k+j, rows = k*k*cp,
+ * ld = wf_ld) and data-gradient pack wd[q][ci][co] (rows = wd_rows, ld = wd_ld). */
+int mtbc_pack_convT_weight(const float* w, int32_t Cin, int32_t Cout, int32_t k, int32_t cp, void* wf, int32_t wf_ld,
+                           void* wd, int32_t wd_rows, int32_t wd_ld, void* stream);
+/* dw_acc[tap][row][ld] (fp32) -> Conv2d grad [Cout][Cin][kh][kw] slice; add != 0 accumulates into grad. */
+int mtbc_unpack_conv_wgrad(const float* acc, int32_t rows, int32_t ld, int32_t k0, float* grad, int32_t Cout,
+                           int32_t Cin, int32_t ksz, int32_t c_begin, int32_t c_count, int32_t add, void* stream);
+/* dw_acc[q][co][ld] -> ConvTranspose2d grad [Cin][Cout][k][k]. */
+int mtbc_unpack_convT_wgrad(const float* acc, int32_t rows, int32_t ld, float* grad, int32_t Cin, int32_t Cout,
+                            int32_t k, int32_t add, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------- */
+/* First layer: Conv2d 3x3 with Cin <= 4 on the fp32 NCHW input image (K = 9*Cin is too small for a tensor tile).  */
+/* Replaces conv_0_0.conv_0 / encoder1.ConvInNormLRelu1.Conv forward + weight gradient (no data gradient: the image
+ * needs none, training_multitask.py:82-90). */
+int mtbc_conv_first_fwd(const float* x, int32_t N, int32_t Cin, int32_t H, int32_t W, const float* w, const float* bias,
+                        int32_t Cout, void* y, int32_t Cp, float* stat_sum, float* stat_sq, void* stream);
+int mtbc_conv_first_wgrad(const float* x, int32_t N, int32_t Cin, int32_t H, int32_t W, const void* dy, int32_t Cp,
+                          int32_t Cout, float* dw, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------- */
+/* InstanceNorm2d (+affine) + LeakyReLU (+ optional 2x2 max-pool output), memory bound, 128-bit accesses.          */
+/* Replaces nn.InstanceNorm2d / nn.LeakyReLU / nn.MaxPool2d (MTnnUNet.py:35-36,103; MONAI ADN + Down).             */
+
+/* Per-(n,c) sum / sum of squares of a bf16 NHWC tensor (used when the producing GEMM could not fuse them). */
+int mtbc_in_stats(const void* y, int32_t N, int32_t HW, int32_t Cp, float* stat_sum, float* stat_sq, void* stream);
+/* a = lrelu(((y-mean)*rstd)*gamma+beta); mean/rstd (fp32 [N][Cp]) are written for the backward pass.
+ * gamma/beta may be NULL (affine=False).  pooled (bf16 [N][H/2][W/2][Cp]) optional. */
+int mtbc_in_apply(const void* y, int32_t N, int32_t H, int32_t W, int32_t Cp, const float* stat_sum,
+                  const float* stat_sq, const float* gamma, const float* beta, int32_t C_true, float eps, float slope,
+                  void* a, void* pooled, float* mean, float* rstd, void* stream);
+/* Backward pass 1: s1[n][c] = sum g, s2[n][c] = sum g*xhat with g = dA * lrelu'(.)  (s1,s2 zeroed by the caller). */
+int mtbc_in_bwd_reduce(const void* dA, const void* y, int32_t N, int32_t HW, int32_t Cp, const float* mean,
+                       const float* rstd, const float* gamma, const float* beta, float slope, float* s1, float* s2,
+                       void* stream);
+/* Backward pass 2: dy = rstd*gamma*(g - s1/HW - xhat*s2/HW)  (bf16).  dgamma[c] += sum_n s2, dbeta[c] += sum_n s1. */
+int mtbc_in_bwd_apply(const void* dA, const void* y, int32_t N, int32_t HW, int32_t Cp, const float* mean,
+                      const float* rstd, const float* gamma, const float* beta, float slope, const float* s1,
+                      const float* s2, void* dy, float* dgamma, float* dbeta, int32_t C_true, void* stream);
+/* Stand-alone 2x2/2 max-pool backward: dA (+)= route(dP) to the first maximum of each window of a. */
+int mtbc_maxpool2_bwd(const void* a, const void* dP, int32_t N, int32_t H, int32_t W, int32_t Cp, void* dA,
+                      int32_t accumulate, void* stream);
+/* Nearest x2 upsample forward / backward (Multi_BTS_UNet.py:100,154-158). */
+int mtbc_upsample2_fwd(const void* x, int32_t N, int32_t H, int32_t W, int32_t Cp, void* y, void* stream);
+int mtbc_upsample2_bwd(const void* dy, int32_t N, int32_t H, int32_t W, int32_t Cp, void* dx, int32_t accumulate,
+                       void* stream);
+/* Per-channel sum over all pixels of a bf16 NHWC tensor -> fp32 [C_true] (ConvTranspose2d bias gradient). */
+int mtbc_channel_sum(const void* t, int64_t npix, int32_t Cp, int32_t C_true, float* out, int32_t add, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------- */
+/* Mask heads: Conv2d 1x1 C -> 1 (MTnnUNet.py:6-9,118; MTUNetPlusPlus.py:73-76,120-123), optionally preceded by a
+ * ConvTranspose2d k=s (deep-supervision heads MTnnUNet.py:106-117, Multi_BTS_UNet.py:118-127) which is composed
+ * algebraically with the 1x1 projection so the k*k*C intermediate is never materialised. */
+int mtbc_head1x1_fwd(const void* a, int64_t npix, int32_t Cp, int32_t C, const float* w, const float* b,
+                     float* logits, void* stream);
+int mtbc_head1x1_bwd(const void* a, const float* dlogits, int64_t npix, int32_t Cp, int32_t C, const float* w,
+                     void* dA, int32_t accumulate, float* dw, float* db, void* stream);
+/* Composed head: Wc[ci][q] = sum_co Wt[ci][co][q]*w1[co], bc = sum_co bt[co]*w1[co] + b1. */
+int mtbc_dshead_compose(const float* wt, const float* bt, const float* w1, const float* b1, int32_t C, int32_t k,
+                        float* wc, float* bc, void* stream);
+int mtbc_dshead_fwd(const void* a, int32_t N, int32_t H, int32_t W, int32_t Cp, int32_t C, int32_t k, const float* wc,
+                    const float* bc, float* logits, void* stream);
+/* dA (+)= ..., dwc[ci][q] += ..., dbc += ...  (dwc/dbc zeroed by caller). */
+int mtbc_dshead_bwd(const void* a, const float* dlogits, int32_t N, int32_t H, int32_t W, int32_t Cp, int32_t C,
+                    int32_t k, const float* wc, void* dA, int32_t accumulate, float* dwc, float* dbc, void* stream);
+/* Chain rule back to the two original parameter sets (state_dict layout stays the reference's). */
+int mtbc_dshead_decompose(const float* dwc, const float* dbc, const float* wt, const float* bt, const float* w1,
+                          int32_t C, int32_t k, float* dwt, float* dbt, float* dw1, float* db1, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------- */
+/* Classification head: AdaptiveAvgPool2d(1) -> Flatten -> Linear(F,Hd) -> ReLU -> Linear(Hd,K)
+ * (MTnnUNet.py:125-132, MTUNetPlusPlus.py:80-87).  hidden (fp32 [N][Hd]) and gap (fp32 [N][F]) are saved by the
+ * forward; the backward overwrites hidden with d(hidden).  dw1/db1/dw2/db2 accumulate (zeroed by the caller). */
+int mtbc_gap_fc_fwd(const void* a, int32_t N, int32_t HW, int32_t Cp, int32_t F, const float* w1, const float* b1,
+                    int32_t Hd, const float* w2, const float* b2, int32_t K, float* gap, float* hidden, float* logits,
+                    void* stream);
+int mtbc_gap_fc_bwd(const float* dlogits, int32_t N, int32_t HW, int32_t Cp, int32_t F, const float* w1, int32_t Hd,
+                    const float* w2, int32_t K, const float* gap, float* hidden, void* dA, int32_t accumulate,
+                    float* dw1, float* db1, float* dw2, float* db2, void* stream);
+/* Flatten -> Linear(C*HW, Hd) -> ReLU -> Linear(Hd,K) head of Multi_BTS_UNet (Multi_BTS_UNet.py:107-115); the
+ * weight columns are indexed in NCHW flatten order (c*HW + hw) as in the reference. */
+int mtbc_flat_fc_fwd(const void* a, int32_t N, int32_t HW, int32_t Cp, int32_t C, const float* w1, const float* b1,
+                     int32_t Hd, const float* w2, const float* b2, int32_t K, float* hidden, float* logits,
+                     void* stream);
+int mtbc_flat_fc_bwd(const void* a, const float* dlogits, int32_t N, int32_t HW, int32_t Cp, int32_t C,
+                     const float* w1, int32_t Hd, const float* w2, int32_t K, const float* hidden, void* dA,
+                     int32_t accumulate, float* dw1, float* db1, float* dw2, float* db2, float* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------- */
+/* Losses.  Dice = monai.losses.DiceLoss(sigmoid=True, squared_pred=True, smooth_nr=1, smooth_dr=1)
+ * (experiment_init.py:209-211); focal = FocalLoss(alpha, gamma=2) on soft targets (criterions.py:6-24). */
+
+/* sums[n][3] = (sum t*p, sum t*t, sum p*p) with p = sigmoid(logit); zeroed by the caller. */
+int mtbc_dice_sums(const float* logits, const float* target, int32_t N, int64_t HW, float* sums, void* stream);
+/* loss = mean_n 1 - (2I+1)/(G+P+1)  -> *loss (fp32 scalar, overwritten). */
+int mtbc_dice_finalize(const float* sums, int32_t N, float* loss, void* stream);
+/* dlogits = gscale[0] * dLoss/dlogit   (gscale: device fp32 scalar = upstream gradient * head weight). */
+int mtbc_dice_bwd(const float* logits, const float* target, int32_t N, int64_t HW, const float* sums,
+                  const float* gscale, float gmul, float* dlogits, void* stream);
+int mtbc_focal_fwd(const float* logits, const float* target, int32_t N, int32_t K, float alpha, float gamma,
+                   float* loss, void* stream);
+int mtbc_focal_bwd(const float* logits, const float* target, int32_t N, int32_t K, float alpha, float gamma,
+                   const float* gscale, float gmul, float* dlogits, void* stream);
+/* Fused multi-task objective (criterions.py:52-76 + training_multitask.py:98): given per-head dice sums (head 0 =
+ * full decoder, weight 1/(j+1) if inversely_weighted) and the focal loss, writes out[0..3] = total, seg, cls, nan
+ * flag (1.0 if any is NaN) -- the NaN guard is a device flag, not a host sync. */
+int mtbc_multitask_loss(const float* dice_losses, int32_t nheads, int32_t inversely_weighted, const float* focal,
+                        float alpha_mix, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------- */
+/* Prediction-refining module (utils/models.py:316-332,366-386) + hard Dice inputs (training_multitask.py:65-71):
+ * mask = logit > 0; cnt[n] = #mask; cls[n] = argmax(class logits); refined mask = 0 if cls==normal_id (when
+ * seg_by_class); refined cls = normal_id if cnt <= threshold... (when class_by_seg, cnt == 0).  Both refinements read
+ * the initial predictions. */
+int mtbc_refine_predictions(const float* mask_logits, const float* class_logits, int32_t N, int64_t HW, int32_t K,
+                            int32_t normal_id, int32_t seg_by_class, int32_t class_by_seg, int32_t pixel_threshold,
+                            uint8_t* mask_out, int32_t* class_out, int32_t* count_out, void* stream);
+/* tp/fp/fn of (logit > 0) against a {0,1} mask over the whole batch -> int64 out[3] (zeroed by caller). */
+int mtbc_hard_dice_counts(const float* logits, const float* target, int64_t n, long long* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------- */
+/* Optimizer (next-row f1): torch.optim.Adam(lr, betas, eps) semantics (experiment_init.py:186-187), fused with the
+ * 1/world gradient scaling of the data-parallel all-reduce.  step is the 1-based step count. */
+int mtbc_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                   float beta1, float beta2, float eps, float grad_scale, int32_t step, void* stream);
+
+/* Same, with the step count and learning rate read from device memory (valid inside a captured CUDA graph). */
+int mtbc_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                       const float* lr_dev, float beta1, float beta2, float eps, float grad_scale,
+                       const int32_t* step_dev, void* stream);
+int mtbc_increment_i32(int32_t* p, void* stream);
+
+/* Utilities. */
+int mtbc_fill_f32(float* p, int64_t n, float v, void* stream);
+int mtbc_zero_bytes(void* p, int64_t nbytes, void* stream);
+int mtbc_f32_to_bf16_nhwc(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, void* y, int32_t Cp,
+                          void* stream);
+int mtbc_bf16_nhwc_to_f32(const void* x, int32_t N, int32_t C, int32_t H, int32_t W, int32_t Cp, float* y,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MTBC_H_ */

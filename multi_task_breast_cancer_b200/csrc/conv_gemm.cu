@@ -1,0 +1,595 @@
+// Implicit-GEMM convolution kernels for sm_100a: TMA (tiled mode, zero OOB fill = conv padding) -> swizzled smem ->
+// tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) -> tcgen05.ld epilogue.
+//
+//  * conv_gemm_kernel : forward / data-gradient.  A = 128 output pixels x KC channels per (tap, source, chunk)
+//    K-block (K-major, 64B/128B swizzle), B = BN x KC slice of the packed weights (K-major).  A skip concatenation is
+//    just more (tap, source) segments: the concat tensor is never materialised (MTUNetPlusPlus.py:107-118).
+//  * wgrad_kernel     : weight gradient.  Reduction runs over pixels, so both operands are MN-major views of the very
+//    same NHWC boxes; accumulators for up to 9 taps live side by side in TMEM; split over pixel ranges with fp32 atomics.
+#include "ptx.cuh"
+#include "internal.h"
+#include <cuda.h>
+#include <vector>
+#include <string.h>
+
+namespace mtbc {
+
+// ------------------------------------------------------------------------------------------------ kernel params
+struct SegDev {
+  int16_t view, dh, dw, wtap;
+  int32_t wk0;
+  int16_t nchunk, kc;
+};  // 16 B
+
+struct ConvGemmParams {
+  CUtensorMap amap[MTBC_MAX_VIEWS];
+  CUtensorMap wmap[2];  // [0]: 32-channel boxes / 64B swizzle, [1]: 64-channel boxes / 128B swizzle
+  SegDev seg[MTBC_MAX_SEGS];
+  int32_t nseg;
+  int32_t TW, TH, TN, tiles_w, tiles_h;
+  int32_t W, H, N;
+  int32_t BN, tmem_cols, stages, a_stage_bytes, stage_bytes;
+  int32_t epi_mode, out_C, up_k, up_cp, accumulate, stat_C;
+  __nv_bfloat16* out;
+  const float* bias;
+  float* stat_sum;
+  float* stat_sq;
+};
+
+constexpr int kMaxStages = 8;
+
+__global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t s_full[kMaxStages];
+  __shared__ uint64_t s_empty[kMaxStages];
+  __shared__ uint64_t s_accum;
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_stat[2][256];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  // tile coordinates
+  const int bx = blockIdx.x;
+  const int w0 = (bx % p.tiles_w) * p.TW;
+  const int h0 = ((bx / p.tiles_w) % p.tiles_h) * p.TH;
+  const int n0 = (bx / (p.tiles_w * p.tiles_h)) * p.TN;
+  const int ntile = blockIdx.y;
+  const int BN = p.BN;
+
+  for (int i = tid; i < 512; i += 128) (&s_stat[0][0])[i] = 0.f;
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 1);
+    }
+    mbar_init(&s_accum, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&s_tmem, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+
+  if (warp == 0 && lane == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int s = 0; s < p.nseg; ++s) {
+      const SegDev sg = p.seg[s];
+      const CUtensorMap* am = &p.amap[sg.view];
+      const CUtensorMap* wm = &p.wmap[sg.kc == 64 ? 1 : 0];
+      const uint32_t bytes = static_cast<uint32_t>((128 + BN) * sg.kc * 2);
+      for (int ch = 0; ch < sg.nchunk; ++ch) {
+        mbar_wait(&s_empty[stage], phase ^ 1u);
+        uint8_t* a_dst = smem + stage * p.stage_bytes;
+        uint8_t* b_dst = a_dst + p.a_stage_bytes;
+        mbar_arrive_expect_tx(&s_full[stage], bytes);
+        tma_load_4d(a_dst, am, &s_full[stage], ch * sg.kc, w0 + sg.dw, h0 + sg.dh, n0);
+        tma_load_3d(b_dst, wm, &s_full[stage], sg.wk0 + ch * sg.kc, ntile * BN, sg.wtap);
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---------------------------------------------------------------- MMA issuer (one thread)
+    const uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t accumulate = 0;
+    for (int s = 0; s < p.nseg; ++s) {
+      const SegDev sg = p.seg[s];
+      const uint32_t sbo = 8u * sg.kc * 2u;
+      const uint32_t layout = sg.kc == 64 ? 2u : 4u;
+      for (int ch = 0; ch < sg.nchunk; ++ch) {
+        mbar_wait(&s_full[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + stage * p.stage_bytes);
+        const uint32_t b_addr = a_addr + p.a_stage_bytes;
+        for (int k = 0; k < sg.kc / 16; ++k) {
+          const uint64_t da = umma_smem_desc(a_addr + k * 32, 16, sbo, layout);
+          const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, sbo, layout);
+          umma_bf16(tmem_base, da, db, idesc, accumulate);
+          accumulate = 1;
+        }
+        umma_commit(&s_empty[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+    umma_commit(&s_accum);
+  }
+  __syncwarp();
+
+  // ------------------------------------------------------------------ epilogue (all 4 warps, thread <-> TMEM lane)
+  mbar_wait(&s_accum, 0);
+  tc_fence_after();
+  __syncwarp();
+
+  const int row = warp * 32 + lane;
+  const int tw = row % p.TW, th = (row / p.TW) % p.TH, tn = row / (p.TW * p.TH);
+  const int n = n0 + tn, h = h0 + th, w = w0 + tw;
+  const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
+  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  const bool do_stats = (p.stat_sum != nullptr);
+
+  for (int c = 0; c < BN; c += 16) {
+    float v[16];
+    tmem_ld16(taddr + c, v);
+    const int col = ntile * BN + c;
+    __nv_bfloat16* dst;
+    int bcol;
+    if (p.epi_mode == 0) {
+      bcol = col;
+      dst = p.out + ((static_cast<int64_t>(n) * p.H + h) * p.W + w) * p.out_C + col;
+    } else {
+      const int q = col / p.up_cp;
+      bcol = col - q * p.up_cp;
+      const int i = q / p.up_k, j = q - i * p.up_k;
+      const int64_t Ho = static_cast<int64_t>(p.H) * p.up_k, Wo = static_cast<int64_t>(p.W) * p.up_k;
+      dst = p.out + ((n * Ho + static_cast<int64_t>(h) * p.up_k + i) * Wo + static_cast<int64_t>(w) * p.up_k + j) * p.out_C + bcol;
+    }
+    if (p.bias != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + bcol + i);
+    }
+    if (do_stats) {
+      float sv[16], sq[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        sv[i] = valid ? v[i] : 0.f;
+        sq[i] = sv[i] * sv[i];
+      }
+      const float cs = warp_colsum16(sv, lane);
+      const float cq = warp_colsum16(sq, lane);
+      if ((lane & 1) == 0) {
+        const int cc = c + col16_of_lane(lane);
+        atomicAdd(&s_stat[0][cc], cs);
+        atomicAdd(&s_stat[1][cc], cq);
+      }
+    }
+    if (valid) {
+      uint4* d4 = reinterpret_cast<uint4*>(dst);
+      if (p.accumulate) {
+        uint4 o0 = d4[0], o1 = d4[1];
+        const uint32_t ou[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float2 f = unpack_bf16x2(ou[i]);
+          v[2 * i] += f.x;
+          v[2 * i + 1] += f.y;
+        }
+      }
+      uint4 r0, r1;
+      r0.x = pack_bf16x2(v[0], v[1]);
+      r0.y = pack_bf16x2(v[2], v[3]);
+      r0.z = pack_bf16x2(v[4], v[5]);
+      r0.w = pack_bf16x2(v[6], v[7]);
+      r1.x = pack_bf16x2(v[8], v[9]);
+      r1.y = pack_bf16x2(v[10], v[11]);
+      r1.z = pack_bf16x2(v[12], v[13]);
+      r1.w = pack_bf16x2(v[14], v[15]);
+      d4[0] = r0;
+      d4[1] = r1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (do_stats) {
+    // TN == 1 is enforced by the host when statistics are fused: the whole tile belongs to sample n0.
+    for (int i = tid; i < BN; i += 128) {
+      const int64_t o = static_cast<int64_t>(n0) * p.stat_C + ntile * BN + i;
+      atomicAdd(p.stat_sum + o, s_stat[0][i]);
+      atomicAdd(p.stat_sq + o, s_stat[1][i]);
+    }
+  }
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ weight gradient
+struct WgradParams {
+  CUtensorMap amap[4];
+  CUtensorMap bmap[4];
+  int16_t t_aview[9], t_adh[9], t_adw[9], t_bview[9];
+  int32_t ntaps, T;       // taps in total / per CTA
+  int32_t a_C, a_kc, a_boxes;  // channels of A source, channels per box, boxes per 128-channel M block
+  int32_t b_kc, b_boxes;  // boxes per BN tile
+  int32_t BN, n_tiles, tmem_cols;
+  int32_t TW, TH, TN, tiles_w, tiles_h, n_ptiles, splits;
+  int32_t a_stage_bytes, b_stage_bytes, a_box_bytes, b_box_bytes;
+  int32_t n_rows, ld_k, k0;
+  float* dw_acc;
+};
+
+constexpr int kWgAStages = 3;
+constexpr int kWgBStages = 2;
+
+__global__ void __launch_bounds__(128) wgrad_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t s_afull[kWgAStages], s_aempty[kWgAStages];
+  __shared__ uint64_t s_bfull[kWgBStages], s_bempty[kWgBStages];
+  __shared__ uint64_t s_accum;
+  __shared__ uint32_t s_tmem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kWgAStages * p.a_stage_bytes;
+
+  const int split = blockIdx.x;
+  const int mblk = blockIdx.y;
+  const int tapgroup = blockIdx.z / p.n_tiles;
+  const int ntile = blockIdx.z % p.n_tiles;
+  const int BN = p.BN;
+  const int T = p.T;
+
+  // pixel tiles of this split
+  const int per = (p.n_ptiles + p.splits - 1) / p.splits;
+  const int pt_begin = split * per;
+  const int pt_end = min(p.n_ptiles, pt_begin + per);
+  const int n_my = max(0, pt_end - pt_begin);
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kWgAStages; ++s) { mbar_init(&s_afull[s], 1); mbar_init(&s_aempty[s], 1); }
+    for (int s = 0; s < kWgBStages; ++s) { mbar_init(&s_bfull[s], 1); mbar_init(&s_bempty[s], 1); }
+    mbar_init(&s_accum, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&s_tmem, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+
+  // number of A boxes that actually exist for this M block
+  const int a_c0 = mblk * 128;
+  const int a_nbox = min(p.a_boxes, (p.a_C - a_c0 + p.a_kc - 1) / p.a_kc);
+
+  if (n_my > 0) {
+    if (warp == 0 && lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int pt = pt_begin; pt < pt_end; ++pt) {
+        const int w0 = (pt % p.tiles_w) * p.TW;
+        const int h0 = ((pt / p.tiles_w) % p.tiles_h) * p.TH;
+        const int n0 = (pt / (p.tiles_w * p.tiles_h)) * p.TN;
+        // B tile(s) of this pixel tile.  A tap group shares one b_view only if all its taps do; otherwise (convT)
+        // the host sets T so that each CTA's taps are loaded as separate B stages (see below).
+        for (int t = 0; t < T; ++t) {
+          const int tap = tapgroup * T + t;
+          const bool need_b = (t == 0) || (p.t_bview[tap] != p.t_bview[tap - 1]);
+          if (need_b) {
+            mbar_wait(&s_bempty[sb], pb ^ 1u);
+            mbar_arrive_expect_tx(&s_bfull[sb], static_cast<uint32_t>(p.b_boxes * p.b_box_bytes));
+            const CUtensorMap* bm = &p.bmap[p.t_bview[tap]];
+            for (int b = 0; b < p.b_boxes; ++b)
+              tma_load_4d(smem_b + sb * p.b_stage_bytes + b * p.b_box_bytes, bm, &s_bfull[sb],
+                          ntile * BN + b * p.b_kc, w0, h0, n0);
+            if (++sb == kWgBStages) { sb = 0; pb ^= 1u; }
+          }
+          mbar_wait(&s_aempty[sa], pa ^ 1u);
+          mbar_arrive_expect_tx(&s_afull[sa], static_cast<uint32_t>(a_nbox * p.a_box_bytes));
+          const CUtensorMap* am = &p.amap[p.t_aview[tap]];
+          for (int b = 0; b < a_nbox; ++b)
+            tma_load_4d(smem_a + sa * p.a_stage_bytes + b * p.a_box_bytes, am, &s_afull[sa], a_c0 + b * p.a_kc,
+                        w0 + p.t_adw[tap], h0 + p.t_adh[tap], n0);
+          if (++sa == kWgAStages) { sa = 0; pa ^= 1u; }
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
+      const uint32_t a_sbo = 8u * p.a_kc * 2u, b_sbo = 8u * p.b_kc * 2u;
+      const uint32_t a_layout = p.a_kc == 64 ? 2u : 4u, b_layout = p.b_kc == 64 ? 2u : 4u;
+      const uint32_t a_kstep = 16u * p.a_kc * 2u, b_kstep = 16u * p.b_kc * 2u;  // 16 pixel rows
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int cur_b = -1;
+      for (int pt = pt_begin; pt < pt_end; ++pt) {
+        for (int t = 0; t < T; ++t) {
+          const int tap = tapgroup * T + t;
+          const bool need_b = (t == 0) || (p.t_bview[tap] != p.t_bview[tap - 1]);
+          if (need_b) {
+            if (cur_b >= 0) {  // release the previous B stage: all MMAs reading it have been issued
+              umma_commit(&s_bempty[cur_b]);
+            }
+            mbar_wait(&s_bfull[sb], pb);
+            cur_b = sb;
+            if (++sb == kWgBStages) { sb = 0; pb ^= 1u; }
+          }
+          mbar_wait(&s_afull[sa], pa);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + sa * p.a_stage_bytes);
+          const uint32_t b_addr = smem_u32(smem_b + cur_b * p.b_stage_bytes);
+          const uint32_t d_addr = tmem_base + static_cast<uint32_t>(t * BN);
+          for (int k = 0; k < 8; ++k) {  // 128 pixels / 16
+            const uint64_t da = umma_smem_desc(a_addr + k * a_kstep, p.a_box_bytes, a_sbo, a_layout);
+            const uint64_t db = umma_smem_desc(b_addr + k * b_kstep, p.b_box_bytes, b_sbo, b_layout);
+            umma_bf16(d_addr, da, db, idesc, (pt > pt_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&s_aempty[sa]);
+          if (++sa == kWgAStages) { sa = 0; pa ^= 1u; }
+        }
+      }
+      umma_commit(&s_accum);
+    }
+    __syncwarp();
+    mbar_wait(&s_accum, 0);
+    tc_fence_after();
+    __syncwarp();
+
+    const int m = warp * 32 + lane;
+    const int ci = a_c0 + m;
+    const bool valid = ci < p.a_C;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    for (int t = 0; t < T; ++t) {
+      const int tap = tapgroup * T + t;
+      for (int c = 0; c < BN; c += 16) {
+        float v[16];
+        tmem_ld16(taddr + t * BN + c, v);
+        if (valid) {
+          float* dst = p.dw_acc + (static_cast<int64_t>(tap) * p.n_rows + ntile * BN + c) * p.ld_k + p.k0 + ci;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) atomicAdd(dst + static_cast<int64_t>(i) * p.ld_k, v[i]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_encode() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmapEncodeTiled>(f);
+  }
+  return fn;
+}
+bool tensor_map_available() { return get_encode() != nullptr; }
+
+// bf16 NHWC view -> 4D tensor map with box (kc, TW, TH, TN)
+static int encode_act(CUtensorMap* m, const mtbc_act_view& v, int kc, int TW, int TH, int TN) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  if (!enc) return set_error(MTBC_ERR_NO_DEVICE, "cuTensorMapEncodeTiled not available");
+  if (v.C % 32 != 0 || (reinterpret_cast<uintptr_t>(v.ptr) & 15) != 0)
+    return set_error(MTBC_ERR_INVALID, "activation view: C %% 32 != 0 or pointer not 16B aligned");
+  cuuint64_t gdim[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N};
+  cuuint64_t gstr[3] = {(cuuint64_t)v.sW * 2, (cuuint64_t)v.sH * 2, (cuuint64_t)v.sN * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(v.ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(MTBC_ERR_CUDA, "cuTensorMapEncodeTiled(act) failed: %d", (int)r);
+  return 0;
+}
+static int encode_w(CUtensorMap* m, const void* w, int ktot, int nrows, int ntaps, int kc, int BN) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  if (!enc) return set_error(MTBC_ERR_NO_DEVICE, "cuTensorMapEncodeTiled not available");
+  cuuint64_t gdim[3] = {(cuuint64_t)ktot, (cuuint64_t)nrows, (cuuint64_t)ntaps};
+  cuuint64_t gstr[2] = {(cuuint64_t)ktot * 2, (cuuint64_t)ktot * 2 * nrows};
+  cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)BN, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(MTBC_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+  return 0;
+}
+
+// 128-pixel tile shape for an (N, H, W) row space
+static void pick_tile(int W, int H, int N, int* TW, int* TH, int* TN) {
+  int tw = W >= 16 ? 16 : W;
+  int th = 128 / tw;
+  if (th > H) th = H;
+  int tn = 128 / (tw * th);
+  *TW = tw; *TH = th; *TN = tn;
+}
+static bool pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+static int tmem_cols_for(int n) { int c = 32; while (c < n) c <<= 1; return c; }
+static int pick_bn(int ncols, int maxbn, int multiple) {
+  int best = 0;
+  for (int bn = multiple; bn <= maxbn && bn <= ncols; bn += multiple)
+    if (ncols % bn == 0 && bn % 16 == 0) best = bn;
+  return best;
+}
+
+struct ConvGemmOp : public OpBase {
+  ConvGemmParams p;
+  dim3 grid;
+  int smem_bytes;
+  double flops;
+  int launch(cudaStream_t st) override {
+    conv_gemm_kernel<<<grid, 128, smem_bytes, st>>>(p);
+    return check_launch("conv_gemm_kernel");
+  }
+  double op_flops() const override { return flops; }
+};
+
+struct WgradOp : public OpBase {
+  WgradParams p;
+  dim3 grid;
+  int smem_bytes;
+  double flops;
+  int launch(cudaStream_t st) override {
+    wgrad_kernel<<<grid, 128, smem_bytes, st>>>(p);
+    return check_launch("wgrad_kernel");
+  }
+  double op_flops() const override { return flops; }
+};
+
+int conv_gemm_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
+  if (!d || !out) return set_error(MTBC_ERR_INVALID, "null argument");
+  if (d->nviews < 1 || d->nviews > MTBC_MAX_VIEWS || d->nseg < 1 || d->nseg > MTBC_MAX_SEGS)
+    return set_error(MTBC_ERR_INVALID, "conv_gemm: bad nviews/nseg (%d, %d)", d->nviews, d->nseg);
+  if (d->ncols % 32 != 0) return set_error(MTBC_ERR_INVALID, "conv_gemm: ncols %% 32 != 0");
+  ConvGemmOp* op = new ConvGemmOp();
+  ConvGemmParams& p = op->p;
+  memset(&p, 0, sizeof(p));
+  int TW, TH, TN;
+  pick_tile(d->W, d->H, d->N, &TW, &TH, &TN);
+  if (!pow2(d->W) && (d->W % TW)) { delete op; return set_error(MTBC_ERR_INVALID, "conv_gemm: W=%d not tileable", d->W); }
+  if (d->W % TW || d->H % TH) { delete op; return set_error(MTBC_ERR_INVALID, "conv_gemm: H,W (%d,%d) not multiples of the tile (%d,%d)", d->H, d->W, TH, TW); }
+  p.TW = TW; p.TH = TH; p.TN = TN;
+  p.tiles_w = d->W / TW; p.tiles_h = d->H / TH;
+  const int tiles_n = (d->N + TN - 1) / TN;
+  p.W = d->W; p.H = d->H; p.N = d->N;
+  const int BN = pick_bn(d->ncols, 256, 16);
+  if (BN == 0) { delete op; return set_error(MTBC_ERR_INVALID, "conv_gemm: no N tile for ncols=%d", d->ncols); }
+  p.BN = BN;
+  p.tmem_cols = tmem_cols_for(BN);
+  int kcmax = 32;
+  int kc_of_view[MTBC_MAX_VIEWS];
+  for (int i = 0; i < d->nviews; ++i) {
+    const mtbc_act_view& v = d->views[i];
+    if (v.W != d->W || v.H != d->H || v.N != d->N) { delete op; return set_error(MTBC_ERR_INVALID, "conv_gemm: view %d geometry mismatch", i); }
+    kc_of_view[i] = (v.C % 64 == 0) ? 64 : 32;
+    if (kc_of_view[i] > kcmax) kcmax = kc_of_view[i];
+    int rc = encode_act(&p.amap[i], v, kc_of_view[i], TW, TH, TN);
+    if (rc) { delete op; return rc; }
+  }
+  bool use32 = false, use64 = false;
+  double ksum = 0;
+  for (int s = 0; s < d->nseg; ++s) {
+    const mtbc_gemm_seg& g = d->seg[s];
+    if (g.view < 0 || g.view >= d->nviews || g.wtap < 0 || g.wtap >= d->w_ntaps) { delete op; return set_error(MTBC_ERR_INVALID, "conv_gemm: segment %d out of range", s); }
+    const int kc = kc_of_view[g.view];
+    const int C = d->views[g.view].C;
+    if (g.wk0 % 32 != 0 || g.wk0 + C > d->w_ktot) { delete op; return set_error(MTBC_ERR_INVALID, "conv_gemm: segment %d weight columns out of range", s); }
+    if (kc == 64 && g.wk0 % 64 != 0) { delete op; return set_error(MTBC_ERR_INVALID, "conv_gemm: 64-wide source at a non-64-aligned K offset"); }
+    p.seg[s].view = (int16_t)g.view; p.seg[s].dh = (int16_t)g.dh; p.seg[s].dw = (int16_t)g.dw;
+    p.seg[s].wtap = (int16_t)g.wtap; p.seg[s].wk0 = g.wk0; p.seg[s].kc = (int16_t)kc; p.seg[s].nchunk = (int16_t)(C / kc);
+    (kc == 64 ? use64 : use32) = true;
+    ksum += C;
+  }
+  p.nseg = d->nseg;
+  if (use32) { int rc = encode_w(&p.wmap[0], d->wpack, d->w_ktot, d->ncols, d->w_ntaps, 32, BN); if (rc) { delete op; return rc; } }
+  if (use64) { int rc = encode_w(&p.wmap[1], d->wpack, d->w_ktot, d->ncols, d->w_ntaps, 64, BN); if (rc) { delete op; return rc; } }
+  p.a_stage_bytes = 128 * kcmax * 2;
+  p.stage_bytes = (128 + BN) * kcmax * 2;
+  p.stage_bytes = (p.stage_bytes + 1023) & ~1023;
+  const int budget = (p.stage_bytes * 3 <= 100 * 1024) ? 100 * 1024 : 200 * 1024;
+  int stages = budget / p.stage_bytes;
+  if (stages > 6) stages = 6;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  op->smem_bytes = stages * p.stage_bytes + 1024;
+  p.epi_mode = d->epi_mode; p.out_C = d->out_C; p.up_k = d->up_k > 0 ? d->up_k : 1; p.up_cp = d->up_cp > 0 ? d->up_cp : d->ncols;
+  p.accumulate = d->accumulate; p.stat_C = d->stat_C;
+  p.out = reinterpret_cast<__nv_bfloat16*>(d->out);
+  p.bias = d->bias; p.stat_sum = d->stat_sum; p.stat_sq = d->stat_sq;
+  if (d->stat_sum && TN != 1) { delete op; return set_error(MTBC_ERR_INVALID, "conv_gemm: fused statistics need >= 128 pixels per sample (TN=%d)", TN); }
+  if (d->epi_mode == 1 && (p.up_cp % 16 != 0)) { delete op; return set_error(MTBC_ERR_INVALID, "conv_gemm: up_cp %% 16"); }
+  op->grid = dim3(p.tiles_w * p.tiles_h * tiles_n, d->ncols / BN, 1);
+  op->flops = 2.0 * double(d->N) * d->H * d->W * double(d->ncols) * ksum;
+  cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  if (e != cudaSuccess) { delete op; return set_error(MTBC_ERR_CUDA, "cudaFuncSetAttribute(conv_gemm): %s", cudaGetErrorString(e)); }
+  *out = op;
+  return 0;
+}
+
+int wgrad_create(const mtbc_wgrad_desc* d, OpBase** out) {
+  if (!d || !out) return set_error(MTBC_ERR_INVALID, "null argument");
+  if (d->a_nviews < 1 || d->a_nviews > 4 || d->b_nviews < 1 || d->b_nviews > 4 || d->ntaps < 1 || d->ntaps > 9)
+    return set_error(MTBC_ERR_INVALID, "wgrad: bad view/tap counts");
+  WgradOp* op = new WgradOp();
+  WgradParams& p = op->p;
+  memset(&p, 0, sizeof(p));
+  int TW, TH, TN;
+  pick_tile(d->W, d->H, d->N, &TW, &TH, &TN);
+  if (d->W % TW || d->H % TH) { delete op; return set_error(MTBC_ERR_INVALID, "wgrad: H,W not multiples of the tile"); }
+  p.TW = TW; p.TH = TH; p.TN = TN; p.tiles_w = d->W / TW; p.tiles_h = d->H / TH;
+  const int tiles_n = (d->N + TN - 1) / TN;
+  p.n_ptiles = p.tiles_w * p.tiles_h * tiles_n;
+  const int aC = d->a_views[0].C, bC = d->b_views[0].C;
+  for (int i = 0; i < d->a_nviews; ++i) if (d->a_views[i].C != aC) { delete op; return set_error(MTBC_ERR_INVALID, "wgrad: A views differ in C"); }
+  for (int i = 0; i < d->b_nviews; ++i) if (d->b_views[i].C != bC) { delete op; return set_error(MTBC_ERR_INVALID, "wgrad: B views differ in C"); }
+  p.a_C = aC;
+  p.a_kc = (aC % 64 == 0) ? 64 : 32;
+  p.b_kc = (bC % 64 == 0) ? 64 : 32;
+  p.a_boxes = 128 / p.a_kc;
+  const int BN = pick_bn(bC, 128, p.b_kc);
+  if (BN == 0) { delete op; return set_error(MTBC_ERR_INVALID, "wgrad: no N tile for C=%d", bC); }
+  p.BN = BN; p.n_tiles = bC / BN; p.b_boxes = BN / p.b_kc;
+  int T = 1;
+  for (int t = 1; t <= d->ntaps; ++t) if (d->ntaps % t == 0 && t * BN <= 512) T = t;
+  p.T = T; p.ntaps = d->ntaps;
+  p.tmem_cols = tmem_cols_for(T * BN);
+  for (int i = 0; i < d->a_nviews; ++i) { int rc = encode_act(&p.amap[i], d->a_views[i], p.a_kc, TW, TH, TN); if (rc) { delete op; return rc; } }
+  for (int i = 0; i < d->b_nviews; ++i) { int rc = encode_act(&p.bmap[i], d->b_views[i], p.b_kc, TW, TH, TN); if (rc) { delete op; return rc; } }
+  for (int t = 0; t < d->ntaps; ++t) {
+    const mtbc_wgrad_tap& tp = d->taps[t];
+    if (tp.a_view < 0 || tp.a_view >= d->a_nviews || tp.b_view < 0 || tp.b_view >= d->b_nviews) { delete op; return set_error(MTBC_ERR_INVALID, "wgrad: tap %d view out of range", t); }
+    p.t_aview[t] = (int16_t)tp.a_view; p.t_adh[t] = (int16_t)tp.a_dh; p.t_adw[t] = (int16_t)tp.a_dw; p.t_bview[t] = (int16_t)tp.b_view;
+  }
+  p.a_box_bytes = 128 * p.a_kc * 2; p.b_box_bytes = 128 * p.b_kc * 2;
+  p.a_stage_bytes = 128 * 128 * 2;               // always room for a full 128-channel M block
+  p.b_stage_bytes = p.b_boxes * p.b_box_bytes;   // BN * 256 B
+  op->smem_bytes = kWgAStages * p.a_stage_bytes + kWgBStages * p.b_stage_bytes + 1024;
+  p.n_rows = d->n_rows; p.ld_k = d->ld_k; p.k0 = d->k0; p.dw_acc = d->dw_acc;
+  const int mblocks = (aC + 127) / 128;
+  const int base_ctas = mblocks * (d->ntaps / T) * p.n_tiles;
+  int splits = d->splits;
+  if (splits <= 0) {
+    splits = (2 * 148 + base_ctas - 1) / base_ctas;
+    // keep at least 4 pixel tiles per split so the TMEM/setup cost amortises
+    int maxs = (p.n_ptiles + 3) / 4; if (maxs < 1) maxs = 1;
+    if (splits > maxs) splits = maxs;
+  }
+  if (splits > p.n_ptiles) splits = p.n_ptiles;
+  if (splits < 1) splits = 1;
+  p.splits = splits;
+  op->grid = dim3(splits, mblocks, (d->ntaps / T) * p.n_tiles);
+  op->flops = 2.0 * double(d->N) * d->H * d->W * double(aC) * double(bC) * d->ntaps;
+  cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  if (e != cudaSuccess) { delete op; return set_error(MTBC_ERR_CUDA, "cudaFuncSetAttribute(wgrad): %s", cudaGetErrorString(e)); }
+  *out = op;
+  return 0;
+}
+
+}  // namespace mtbc

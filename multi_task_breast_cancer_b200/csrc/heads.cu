@@ -1,0 +1,588 @@
+// Mask heads (1x1 projection, algebraically composed deep-supervision heads) and classification heads
+// (global-average-pool + 2 FC, flatten + 2 FC).  All CUDA-core: M = batch is far below a tensor tile and the 1x1
+// projections are pure HBM streams.
+#include "ptx.cuh"
+#include "internal.h"
+
+namespace mtbc {
+
+// ------------------------------------------------------------------------------------------------ 1x1 head
+__global__ void __launch_bounds__(256) head1x1_fwd_kernel(const __nv_bfloat16* __restrict__ a, int64_t npix, int Cp,
+                                                          int C, const float* __restrict__ w,
+                                                          const float* __restrict__ b, float* __restrict__ logits) {
+  extern __shared__ float s_w[];  // [Cp]
+  for (int i = threadIdx.x; i < Cp; i += 256) s_w[i] = i < C ? w[i] : 0.f;
+  __syncthreads();
+  const float bias = b ? b[0] : 0.f;
+  const int cvec = Cp / 8;
+  for (int64_t pix = blockIdx.x * 256ll + threadIdx.x; pix < npix; pix += gridDim.x * 256ll) {
+    const uint4* src = reinterpret_cast<const uint4*>(a + pix * Cp);
+    float acc = bias;
+    for (int v = 0; v < cvec; ++v) {
+      const uint4 u = src[v];
+      const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16x2(uu[k]);
+        acc = fmaf(f.x, s_w[v * 8 + 2 * k], acc);
+        acc = fmaf(f.y, s_w[v * 8 + 2 * k + 1], acc);
+      }
+    }
+    logits[pix] = acc;
+  }
+}
+
+// dA[pix][c] (+)= dl[pix]*w[c];  dw[c] += sum_pix dl[pix]*a[pix][c];  db += sum_pix dl[pix]
+__global__ void __launch_bounds__(256) head1x1_bwd_kernel(const __nv_bfloat16* __restrict__ a,
+                                                          const float* __restrict__ dl, int64_t npix, int Cp, int C,
+                                                          const float* __restrict__ w, __nv_bfloat16* __restrict__ dA,
+                                                          int accumulate, float* __restrict__ dw,
+                                                          float* __restrict__ db) {
+  extern __shared__ float s_acc[];  // [Cp + 1]
+  const int cvec = Cp / 8;
+  for (int i = threadIdx.x; i <= Cp; i += 256) s_acc[i] = 0.f;
+  __syncthreads();
+  const int64_t total = npix * cvec;
+  const int64_t start = blockIdx.x * 256ll + threadIdx.x, stride = gridDim.x * 256ll;
+  const int v = static_cast<int>(start % cvec);
+  float wv[8], acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, accb = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) wv[k] = (v * 8 + k) < C ? w[v * 8 + k] : 0.f;
+  for (int64_t i = start; i < total; i += stride) {
+    const int64_t pix = i / cvec;
+    const float g = dl[pix];
+    const uint4 u = *reinterpret_cast<const uint4*>(a + i * 8);
+    const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack_bf16x2(uu[k]);
+      acc[2 * k] = fmaf(g, f.x, acc[2 * k]);
+      acc[2 * k + 1] = fmaf(g, f.y, acc[2 * k + 1]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = g * wv[k];
+    if (accumulate) {
+      const uint4 q = *reinterpret_cast<const uint4*>(dA + i * 8);
+      const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16x2(qq[k]);
+        o[2 * k] += f.x;
+        o[2 * k + 1] += f.y;
+      }
+    }
+    uint4 r;
+    r.x = pack_bf16x2(o[0], o[1]); r.y = pack_bf16x2(o[2], o[3]); r.z = pack_bf16x2(o[4], o[5]); r.w = pack_bf16x2(o[6], o[7]);
+    *reinterpret_cast<uint4*>(dA + i * 8) = r;
+    if (v == 0) accb += g;
+  }
+  if (start < total) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&s_acc[v * 8 + k], acc[k]);
+    if (v == 0) atomicAdd(&s_acc[Cp], accb);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += 256) atomicAdd(dw + i, s_acc[i]);
+  if (threadIdx.x == 0) atomicAdd(db, s_acc[Cp]);
+}
+
+// ------------------------------------------------------------------------------------------------ composed DS head
+__global__ void dshead_compose_kernel(const float* __restrict__ wt, const float* __restrict__ bt,
+                                      const float* __restrict__ w1, const float* __restrict__ b1, int C, int kk,
+                                      float* __restrict__ wc, float* __restrict__ bc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C * kk) {
+    const int ci = i / kk, q = i % kk;
+    float a = 0.f;
+    for (int co = 0; co < C; ++co) a = fmaf(wt[(static_cast<int64_t>(ci) * C + co) * kk + q], w1[co], a);
+    wc[i] = a;
+  }
+  if (i == 0) {
+    float a = b1[0];
+    for (int co = 0; co < C; ++co) a = fmaf(bt[co], w1[co], a);
+    bc[0] = a;
+  }
+}
+
+// logits[n, k*h+i, k*w+j] = sum_ci a[n,h,w,ci]*wc[ci][q] + bc ; block = 256 threads = (256/kk pixels) x kk outputs
+__global__ void __launch_bounds__(256) dshead_fwd_kernel(const __nv_bfloat16* __restrict__ a, int N, int H, int W,
+                                                         int Cp, int C, int k, const float* __restrict__ wc,
+                                                         const float* __restrict__ bc, float* __restrict__ logits) {
+  extern __shared__ float sm[];
+  const int kk = k * k;
+  const int PB = 256 / kk;
+  float* s_wc = sm;            // [C][kk]
+  float* s_a = sm + C * kk;    // [PB][C]
+  for (int i = threadIdx.x; i < C * kk; i += 256) s_wc[i] = wc[i];
+  const float bias = bc[0];
+  const int64_t npix = static_cast<int64_t>(N) * H * W;
+  const int pl = threadIdx.x / kk, q = threadIdx.x % kk;
+  const int qi = q / k, qj = q % k;
+  for (int64_t p0 = blockIdx.x * static_cast<int64_t>(PB); p0 < npix; p0 += static_cast<int64_t>(gridDim.x) * PB) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < PB * C; i += 256) {
+      const int64_t pix = p0 + i / C;
+      s_a[i] = pix < npix ? __bfloat162float(a[pix * Cp + (i % C)]) : 0.f;
+    }
+    __syncthreads();
+    const int64_t pix = p0 + pl;
+    if (pl < PB && pix < npix) {
+      float acc = bias;
+      const float* ar = s_a + pl * C;
+      for (int ci = 0; ci < C; ++ci) acc = fmaf(ar[ci], s_wc[ci * kk + q], acc);
+      const int w = static_cast<int>(pix % W);
+      const int h = static_cast<int>((pix / W) % H);
+      const int64_t n = pix / (static_cast<int64_t>(W) * H);
+      logits[(n * H * k + static_cast<int64_t>(h) * k + qi) * (static_cast<int64_t>(W) * k) + static_cast<int64_t>(w) * k + qj] = acc;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) dshead_bwd_kernel(const __nv_bfloat16* __restrict__ a,
+                                                         const float* __restrict__ dl, int N, int H, int W, int Cp,
+                                                         int C, int k, const float* __restrict__ wc,
+                                                         __nv_bfloat16* __restrict__ dA, int accumulate,
+                                                         float* __restrict__ dwc, float* __restrict__ dbc) {
+  extern __shared__ float sm[];
+  const int kk = k * k;
+  const int PB = 256 / kk;
+  float* s_wc = sm;                 // [C][kk]
+  float* s_a = s_wc + C * kk;       // [PB][C]
+  float* s_dl = s_a + PB * C;       // [PB][kk]
+  __shared__ float s_db;
+  for (int i = threadIdx.x; i < C * kk; i += 256) s_wc[i] = wc[i];
+  if (threadIdx.x == 0) s_db = 0.f;
+  const int64_t npix = static_cast<int64_t>(N) * H * W;
+  const int q = threadIdx.x % kk, cl = threadIdx.x / kk;  // this thread owns dwc[(cl + j*PB)][q]
+  const int nacc = (C + PB - 1) / PB;                      // <= 32
+  float acc[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+  float accb = 0.f;
+  for (int64_t p0 = blockIdx.x * static_cast<int64_t>(PB); p0 < npix; p0 += static_cast<int64_t>(gridDim.x) * PB) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < PB * C; i += 256) {
+      const int64_t pix = p0 + i / C;
+      s_a[i] = pix < npix ? __bfloat162float(a[pix * Cp + (i % C)]) : 0.f;
+    }
+    {
+      const int pl = threadIdx.x / kk;
+      const int64_t pix = p0 + pl;
+      float g = 0.f;
+      if (pl < PB && pix < npix) {
+        const int w = static_cast<int>(pix % W);
+        const int h = static_cast<int>((pix / W) % H);
+        const int64_t n = pix / (static_cast<int64_t>(W) * H);
+        g = dl[(n * H * k + static_cast<int64_t>(h) * k + q / k) * (static_cast<int64_t>(W) * k) + static_cast<int64_t>(w) * k + q % k];
+      }
+      if (pl < PB) s_dl[pl * kk + q] = g;
+      accb += g;
+    }
+    __syncthreads();
+    // weight gradient partials
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < nacc) {
+        const int ci = cl + j * PB;
+        if (ci < C) {
+          float s = acc[j];
+          for (int pl = 0; pl < PB; ++pl) s = fmaf(s_a[pl * C + ci], s_dl[pl * kk + q], s);
+          acc[j] = s;
+        }
+      }
+    }
+    // data gradient: PB*Cp outputs
+    for (int i = threadIdx.x; i < PB * Cp; i += 256) {
+      const int pl = i / Cp, ci = i % Cp;
+      const int64_t pix = p0 + pl;
+      if (pix < npix) {
+        float s = 0.f;
+        if (ci < C) {
+          const float* wr = s_wc + ci * kk;
+          const float* gr = s_dl + pl * kk;
+          for (int qq = 0; qq < kk; ++qq) s = fmaf(gr[qq], wr[qq], s);
+        }
+        __nv_bfloat16* d = dA + pix * Cp + ci;
+        if (accumulate) s += __bfloat162float(*d);
+        *d = __float2bfloat16(s);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (j < nacc) {
+      const int ci = cl + j * PB;
+      if (ci < C && cl < PB) atomicAdd(dwc + ci * kk + q, acc[j]);
+    }
+  }
+  accb = warp_sum(accb);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&s_db, accb);
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(dbc, s_db);
+}
+
+__global__ void dshead_decompose_kernel(const float* __restrict__ dwc, const float* __restrict__ dbc,
+                                        const float* __restrict__ wt, const float* __restrict__ bt,
+                                        const float* __restrict__ w1, int C, int kk, float* __restrict__ dwt,
+                                        float* __restrict__ dbt, float* __restrict__ dw1, float* __restrict__ db1) {
+  // grid-stride over dwt entries; block 0 additionally does the small vectors
+  const int64_t total = static_cast<int64_t>(C) * C * kk;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int q = static_cast<int>(i % kk);
+    const int co = static_cast<int>((i / kk) % C);
+    const int ci = static_cast<int>(i / (static_cast<int64_t>(kk) * C));
+    dwt[i] += dwc[ci * kk + q] * w1[co];
+  }
+  if (blockIdx.x == 0) {
+    const float gb = dbc[0];
+    for (int co = threadIdx.x; co < C; co += blockDim.x) {
+      float s = gb * bt[co];
+      for (int ci = 0; ci < C; ++ci)
+        for (int q = 0; q < kk; ++q) s = fmaf(dwc[ci * kk + q], wt[(static_cast<int64_t>(ci) * C + co) * kk + q], s);
+      dw1[co] += s;
+      dbt[co] += gb * w1[co];
+    }
+    if (threadIdx.x == 0) db1[0] += gb;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ GAP + FC head
+__global__ void __launch_bounds__(256) gap_fc_fwd_kernel(const __nv_bfloat16* __restrict__ a, int HW, int Cp, int F,
+                                                         const float* __restrict__ w1, const float* __restrict__ b1,
+                                                         int Hd, const float* __restrict__ w2,
+                                                         const float* __restrict__ b2, int K, float* __restrict__ gap,
+                                                         float* __restrict__ hidden, float* __restrict__ logits) {
+  extern __shared__ float sm[];
+  float* s_gap = sm;       // [F]
+  float* s_h = sm + F;     // [Hd]
+  const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const __nv_bfloat16* src = a + static_cast<int64_t>(n) * HW * Cp;
+  const float inv = 1.f / static_cast<float>(HW);
+  for (int c = threadIdx.x; c < F; c += 256) {
+    float s = 0.f;
+    for (int p = 0; p < HW; ++p) s += __bfloat162float(src[static_cast<int64_t>(p) * Cp + c]);
+    s *= inv;
+    s_gap[c] = s;
+    gap[static_cast<int64_t>(n) * F + c] = s;
+  }
+  __syncthreads();
+  for (int j = warp; j < Hd; j += 8) {
+    const float* wr = w1 + static_cast<int64_t>(j) * F;
+    float s = 0.f;
+    for (int c = lane; c < F; c += 32) s = fmaf(wr[c], s_gap[c], s);
+    s = warp_sum(s);
+    if (lane == 0) {
+      s = fmaxf(s + b1[j], 0.f);
+      s_h[j] = s;
+      hidden[static_cast<int64_t>(n) * Hd + j] = s;
+    }
+  }
+  __syncthreads();
+  for (int k = warp; k < K; k += 8) {
+    const float* wr = w2 + static_cast<int64_t>(k) * Hd;
+    float s = 0.f;
+    for (int j = lane; j < Hd; j += 32) s = fmaf(wr[j], s_h[j], s);
+    s = warp_sum(s);
+    if (lane == 0) logits[static_cast<int64_t>(n) * K + k] = s + b2[k];
+  }
+}
+
+// per sample: dh (written over hidden), dgap -> dA broadcast, dw2/db2 via atomics
+__global__ void __launch_bounds__(256) gap_fc_bwd_sample_kernel(const float* __restrict__ dl, int HW, int Cp, int F,
+                                                                const float* __restrict__ w1, int Hd,
+                                                                const float* __restrict__ w2, int K,
+                                                                float* __restrict__ hidden,
+                                                                __nv_bfloat16* __restrict__ dA, int accumulate,
+                                                                float* __restrict__ dw2, float* __restrict__ db2) {
+  extern __shared__ float sm[];
+  float* s_dh = sm;        // [Hd]
+  float* s_dl = sm + Hd;   // [K]
+  const int n = blockIdx.x;
+  for (int k = threadIdx.x; k < K; k += 256) {
+    const float g = dl[static_cast<int64_t>(n) * K + k];
+    s_dl[k] = g;
+    atomicAdd(db2 + k, g);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < Hd; j += 256) {
+    const float h = hidden[static_cast<int64_t>(n) * Hd + j];
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) {
+      s = fmaf(w2[static_cast<int64_t>(k) * Hd + j], s_dl[k], s);
+      atomicAdd(dw2 + static_cast<int64_t>(k) * Hd + j, s_dl[k] * h);
+    }
+    s = h > 0.f ? s : 0.f;
+    s_dh[j] = s;
+    hidden[static_cast<int64_t>(n) * Hd + j] = s;
+  }
+  __syncthreads();
+  const float inv = 1.f / static_cast<float>(HW);
+  __nv_bfloat16* dst = dA + static_cast<int64_t>(n) * HW * Cp;
+  for (int c = threadIdx.x; c < Cp; c += 256) {
+    float s = 0.f;
+    if (c < F)
+      for (int j = 0; j < Hd; ++j) s = fmaf(w1[static_cast<int64_t>(j) * F + c], s_dh[j], s);
+    s *= inv;
+    for (int p = 0; p < HW; ++p) {
+      __nv_bfloat16* d = dst + static_cast<int64_t>(p) * Cp + c;
+      float o = s;
+      if (accumulate) o += __bfloat162float(*d);
+      *d = __float2bfloat16(o);
+    }
+  }
+}
+// dw1[j][c] += sum_n dh[n][j]*gap[n][c] ; db1[j] += sum_n dh[n][j]
+__global__ void __launch_bounds__(256) fc1_wgrad_kernel(const float* __restrict__ dh, const float* __restrict__ x,
+                                                        int N, int Hd, int F, float* __restrict__ dw1,
+                                                        float* __restrict__ db1) {
+  const int64_t total = static_cast<int64_t>(Hd) * F;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+    const int j = static_cast<int>(i / F), c = static_cast<int>(i % F);
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s = fmaf(dh[static_cast<int64_t>(n) * Hd + j], x[static_cast<int64_t>(n) * F + c], s);
+    dw1[i] += s;
+    if (c == 0) {
+      float b = 0.f;
+      for (int n = 0; n < N; ++n) b += dh[static_cast<int64_t>(n) * Hd + j];
+      db1[j] += b;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ flatten + FC head
+// hidden_pre[n][j] += sum_{k in slice} w1[j][k]*a[n][k]   with k = c*HW + hw (NCHW flatten order of the reference)
+__global__ void __launch_bounds__(256) flat_fc1_kernel(const __nv_bfloat16* __restrict__ a, int N, int HW, int Cp,
+                                                       int C, const float* __restrict__ w1, int Hd, int slices,
+                                                       float* __restrict__ hidden_pre) {
+  const int j = blockIdx.x, sl = blockIdx.y;
+  const int64_t F = static_cast<int64_t>(C) * HW;
+  const int64_t k0 = F * sl / slices, k1 = F * (sl + 1) / slices;
+  __shared__ float s_red[8];
+  for (int n0 = 0; n0 < N; n0 += 8) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t k = k0 + threadIdx.x; k < k1; k += 256) {
+      const float wv = w1[static_cast<int64_t>(j) * F + k];
+      const int c = static_cast<int>(k / HW), hw = static_cast<int>(k % HW);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (n0 + i < N) acc[i] = fmaf(wv, __bfloat162float(a[(static_cast<int64_t>(n0 + i) * HW + hw) * Cp + c]), acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float s = warp_sum(acc[i]);
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
+      __syncthreads();
+      if (threadIdx.x == 0 && n0 + i < N) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += s_red[w];
+        atomicAdd(hidden_pre + static_cast<int64_t>(n0 + i) * Hd + j, t);
+      }
+    }
+  }
+}
+__global__ void flat_fc2_kernel(float* __restrict__ hidden, const float* __restrict__ b1, int N, int Hd,
+                                const float* __restrict__ w2, const float* __restrict__ b2, int K,
+                                float* __restrict__ logits) {
+  extern __shared__ float s_h[];  // [Hd]
+  const int n = blockIdx.x;
+  for (int j = threadIdx.x; j < Hd; j += blockDim.x) {
+    const float h = fmaxf(hidden[static_cast<int64_t>(n) * Hd + j] + b1[j], 0.f);
+    hidden[static_cast<int64_t>(n) * Hd + j] = h;
+    s_h[j] = h;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = warp; k < K; k += blockDim.x / 32) {
+    float s = 0.f;
+    for (int j = lane; j < Hd; j += 32) s = fmaf(w2[static_cast<int64_t>(k) * Hd + j], s_h[j], s);
+    s = warp_sum(s);
+    if (lane == 0) logits[static_cast<int64_t>(n) * K + k] = s + b2[k];
+  }
+}
+// dh[n][j] = relu'(hidden) * sum_k w2[k][j]*dl[n][k] ; dw2, db2, db1 accumulate
+__global__ void flat_fc_bwd_small_kernel(const float* __restrict__ dl, int N, int Hd, const float* __restrict__ w2,
+                                         int K, const float* __restrict__ hidden, float* __restrict__ dh,
+                                         float* __restrict__ db1, float* __restrict__ dw2, float* __restrict__ db2) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < Hd) {
+    float bsum = 0.f;
+    for (int n = 0; n < N; ++n) {
+      const float h = hidden[static_cast<int64_t>(n) * Hd + j];
+      float s = 0.f;
+      for (int k = 0; k < K; ++k) s = fmaf(w2[static_cast<int64_t>(k) * Hd + j], dl[static_cast<int64_t>(n) * K + k], s);
+      s = h > 0.f ? s : 0.f;
+      dh[static_cast<int64_t>(n) * Hd + j] = s;
+      bsum += s;
+    }
+    db1[j] += bsum;
+    for (int k = 0; k < K; ++k) {
+      float s = 0.f;
+      for (int n = 0; n < N; ++n) s = fmaf(dl[static_cast<int64_t>(n) * K + k], hidden[static_cast<int64_t>(n) * Hd + j], s);
+      dw2[static_cast<int64_t>(k) * Hd + j] += s;
+    }
+  }
+  if (j < K) {
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += dl[static_cast<int64_t>(n) * K + j];
+    db2[j] += s;
+  }
+}
+// one thread per flattened column k: single pass over w1 (read) and dw1 (write)
+__global__ void __launch_bounds__(256) flat_fc_bwd_big_kernel(const __nv_bfloat16* __restrict__ a, int N, int HW,
+                                                              int Cp, int C, const float* __restrict__ w1, int Hd,
+                                                              const float* __restrict__ dh,
+                                                              __nv_bfloat16* __restrict__ dA, int accumulate,
+                                                              float* __restrict__ dw1) {
+  extern __shared__ float s_dh[];  // [N][Hd]
+  for (int i = threadIdx.x; i < N * Hd; i += 256) s_dh[i] = dh[i];
+  __syncthreads();
+  const int64_t F = static_cast<int64_t>(C) * HW;
+  const int64_t k = blockIdx.x * 256ll + threadIdx.x;
+  if (k >= F) return;
+  const int c = static_cast<int>(k / HW), hw = static_cast<int>(k % HW);
+  for (int n0 = 0; n0 < N; n0 += 8) {
+    float av[8], da[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      av[i] = (n0 + i < N) ? __bfloat162float(a[(static_cast<int64_t>(n0 + i) * HW + hw) * Cp + c]) : 0.f;
+      da[i] = 0.f;
+    }
+    for (int j = 0; j < Hd; ++j) {
+      const float wv = w1[static_cast<int64_t>(j) * F + k];
+      float g = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (n0 + i < N) {
+          const float d = s_dh[(n0 + i) * Hd + j];
+          da[i] = fmaf(d, wv, da[i]);
+          g = fmaf(d, av[i], g);
+        }
+      }
+      dw1[static_cast<int64_t>(j) * F + k] += g;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (n0 + i < N) {
+        __nv_bfloat16* d = dA + (static_cast<int64_t>(n0 + i) * HW + hw) * Cp + c;
+        float o = da[i];
+        if (accumulate) o += __bfloat162float(*d);
+        *d = __float2bfloat16(o);
+      }
+    }
+  }
+}
+
+}  // namespace mtbc
+
+using namespace mtbc;
+#define ST(s) static_cast<cudaStream_t>(s)
+#define BF(p) static_cast<__nv_bfloat16*>(p)
+#define CBF(p) static_cast<const __nv_bfloat16*>(p)
+
+extern "C" {
+
+int mtbc_head1x1_fwd(const void* a, int64_t npix, int32_t Cp, int32_t C, const float* w, const float* b,
+                     float* logits, void* stream) {
+  int g = cdiv(npix, 256); if (g > 148 * 8) g = 148 * 8;
+  head1x1_fwd_kernel<<<g, 256, Cp * sizeof(float), ST(stream)>>>(CBF(a), npix, Cp, C, w, b, logits);
+  return check_launch("head1x1_fwd");
+}
+int mtbc_head1x1_bwd(const void* a, const float* dlogits, int64_t npix, int32_t Cp, int32_t C, const float* w,
+                     void* dA, int32_t accumulate, float* dw, float* db, void* stream) {
+  const int cvec = Cp / 8;
+  if (256 % cvec != 0) return set_error(MTBC_ERR_INVALID, "head1x1_bwd: Cp/8 must divide 256");
+  int g = cdiv(npix * cvec, 256 * 8); if (g > 148 * 8) g = 148 * 8; if (g < 1) g = 1;
+  head1x1_bwd_kernel<<<g, 256, (Cp + 1) * sizeof(float), ST(stream)>>>(CBF(a), dlogits, npix, Cp, C, w, BF(dA),
+                                                                      accumulate, dw, db);
+  return check_launch("head1x1_bwd");
+}
+int mtbc_dshead_compose(const float* wt, const float* bt, const float* w1, const float* b1, int32_t C, int32_t k,
+                        float* wc, float* bc, void* stream) {
+  const int kk = k * k;
+  dshead_compose_kernel<<<cdiv(C * kk, 128), 128, 0, ST(stream)>>>(wt, bt, w1, b1, C, kk, wc, bc);
+  return check_launch("dshead_compose");
+}
+int mtbc_dshead_fwd(const void* a, int32_t N, int32_t H, int32_t W, int32_t Cp, int32_t C, int32_t k, const float* wc,
+                    const float* bc, float* logits, void* stream) {
+  const int kk = k * k;
+  if (kk > 256 || 256 % kk) return set_error(MTBC_ERR_INVALID, "dshead: k*k must divide 256");
+  const int PB = 256 / kk;
+  const int64_t npix = static_cast<int64_t>(N) * H * W;
+  int g = cdiv(npix, PB); if (g > 148 * 8) g = 148 * 8;
+  const size_t smem = (static_cast<size_t>(C) * kk + static_cast<size_t>(PB) * C) * sizeof(float);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(dshead_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  dshead_fwd_kernel<<<g, 256, smem, ST(stream)>>>(CBF(a), N, H, W, Cp, C, k, wc, bc, logits);
+  return check_launch("dshead_fwd");
+}
+int mtbc_dshead_bwd(const void* a, const float* dlogits, int32_t N, int32_t H, int32_t W, int32_t Cp, int32_t C,
+                    int32_t k, const float* wc, void* dA, int32_t accumulate, float* dwc, float* dbc, void* stream) {
+  const int kk = k * k;
+  if (kk > 256 || 256 % kk) return set_error(MTBC_ERR_INVALID, "dshead: k*k must divide 256");
+  const int PB = 256 / kk;
+  if ((C + PB - 1) / PB > 32) return set_error(MTBC_ERR_INVALID, "dshead_bwd: C*k*k too large");
+  const int64_t npix = static_cast<int64_t>(N) * H * W;
+  int g = cdiv(npix, PB * 8); if (g > 148 * 2) g = 148 * 2; if (g < 1) g = 1;
+  const size_t smem = (static_cast<size_t>(C) * kk + static_cast<size_t>(PB) * C + static_cast<size_t>(PB) * kk) * sizeof(float);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(dshead_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  dshead_bwd_kernel<<<g, 256, smem, ST(stream)>>>(CBF(a), dlogits, N, H, W, Cp, C, k, wc, BF(dA), accumulate, dwc, dbc);
+  return check_launch("dshead_bwd");
+}
+int mtbc_dshead_decompose(const float* dwc, const float* dbc, const float* wt, const float* bt, const float* w1,
+                          int32_t C, int32_t k, float* dwt, float* dbt, float* dw1, float* db1, void* stream) {
+  const int kk = k * k;
+  const int64_t total = static_cast<int64_t>(C) * C * kk;
+  int g = cdiv(total, 256); if (g > 148 * 4) g = 148 * 4;
+  dshead_decompose_kernel<<<g, 256, 0, ST(stream)>>>(dwc, dbc, wt, bt, w1, C, kk, dwt, dbt, dw1, db1);
+  return check_launch("dshead_decompose");
+}
+
+int mtbc_gap_fc_fwd(const void* a, int32_t N, int32_t HW, int32_t Cp, int32_t F, const float* w1, const float* b1,
+                    int32_t Hd, const float* w2, const float* b2, int32_t K, float* gap, float* hidden, float* logits,
+                    void* stream) {
+  gap_fc_fwd_kernel<<<N, 256, (F + Hd) * sizeof(float), ST(stream)>>>(CBF(a), HW, Cp, F, w1, b1, Hd, w2, b2, K, gap,
+                                                                      hidden, logits);
+  return check_launch("gap_fc_fwd");
+}
+int mtbc_gap_fc_bwd(const float* dlogits, int32_t N, int32_t HW, int32_t Cp, int32_t F, const float* w1, int32_t Hd,
+                    const float* w2, int32_t K, const float* gap, float* hidden, void* dA, int32_t accumulate,
+                    float* dw1, float* db1, float* dw2, float* db2, void* stream) {
+  gap_fc_bwd_sample_kernel<<<N, 256, (Hd + K) * sizeof(float), ST(stream)>>>(dlogits, HW, Cp, F, w1, Hd, w2, K, hidden,
+                                                                             BF(dA), accumulate, dw2, db2);
+  int rc = check_launch("gap_fc_bwd_sample");
+  if (rc) return rc;
+  int g = cdiv(static_cast<int64_t>(Hd) * F, 256); if (g > 148 * 4) g = 148 * 4;
+  fc1_wgrad_kernel<<<g, 256, 0, ST(stream)>>>(hidden, gap, N, Hd, F, dw1, db1);
+  return check_launch("fc1_wgrad");
+}
+
+int mtbc_flat_fc_fwd(const void* a, int32_t N, int32_t HW, int32_t Cp, int32_t C, const float* w1, const float* b1,
+                     int32_t Hd, const float* w2, const float* b2, int32_t K, float* hidden, float* logits,
+                     void* stream) {
+  cudaError_t e = cudaMemsetAsync(hidden, 0, static_cast<size_t>(N) * Hd * sizeof(float), ST(stream));
+  if (e != cudaSuccess) return set_error(MTBC_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
+  const int slices = 4;
+  flat_fc1_kernel<<<dim3(Hd, slices), 256, 0, ST(stream)>>>(CBF(a), N, HW, Cp, C, w1, Hd, slices, hidden);
+  int rc = check_launch("flat_fc1");
+  if (rc) return rc;
+  flat_fc2_kernel<<<N, 128, Hd * sizeof(float), ST(stream)>>>(hidden, b1, N, Hd, w2, b2, K, logits);
+  return check_launch("flat_fc2");
+}
+int mtbc_flat_fc_bwd(const void* a, const float* dlogits, int32_t N, int32_t HW, int32_t Cp, int32_t C,
+                     const float* w1, int32_t Hd, const float* w2, int32_t K, const float* hidden, void* dA,
+                     int32_t accumulate, float* dw1, float* db1, float* dw2, float* db2, float* scratch, void* stream) {
+  flat_fc_bwd_small_kernel<<<cdiv(Hd > K ? Hd : K, 128), 128, 0, ST(stream)>>>(dlogits, N, Hd, w2, K, hidden, scratch,
+                                                                             db1, dw2, db2);
+  int rc = check_launch("flat_fc_bwd_small");
+  if (rc) return rc;
+  const int64_t F = static_cast<int64_t>(C) * HW;
+  const size_t smem = static_cast<size_t>(N) * Hd * sizeof(float);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(flat_fc_bwd_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  flat_fc_bwd_big_kernel<<<cdiv(F, 256), 256, smem, ST(stream)>>>(CBF(a), N, HW, Cp, C, w1, Hd, scratch, BF(dA),
+                                                                 accumulate, dw1);
+  return check_launch("flat_fc_bwd_big");
+}
+
+}  // extern "C"

@@ -1,0 +1,25 @@
+// Internal (non-ABI) declarations shared by the translation units of libmtbc.
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/mtbc.h"
+
+namespace mtbc {
+
+// printf-style error recording (thread local); returns `code` so callers can `return set_error(...)`.
+int set_error(int code, const char* fmt, ...);
+// cudaGetLastError() after a launch -> MTBC status (never synchronises).
+int check_launch(const char* what);
+
+struct OpBase {
+  virtual ~OpBase() {}
+  virtual int launch(cudaStream_t st) = 0;
+  virtual double op_flops() const { return 0.0; }
+};
+
+int conv_gemm_create(const mtbc_conv_gemm_desc* d, OpBase** out);
+int wgrad_create(const mtbc_wgrad_desc* d, OpBase** out);
+bool tensor_map_available();
+
+inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
+
+}  // namespace mtbc

@@ -1,0 +1,299 @@
+// Dice + focal multi-task objective, prediction refinement, hard-Dice counts and the fused Adam step.
+#include "ptx.cuh"
+#include "internal.h"
+
+namespace mtbc {
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// ------------------------------------------------------------------------------------------------ Dice
+__global__ void __launch_bounds__(256) dice_sums_kernel(const float* __restrict__ logits,
+                                                        const float* __restrict__ target, int64_t HW,
+                                                        float* __restrict__ sums) {
+  const int n = blockIdx.y;
+  const float4* x4 = reinterpret_cast<const float4*>(logits + static_cast<int64_t>(n) * HW);
+  const float4* t4 = reinterpret_cast<const float4*>(target + static_cast<int64_t>(n) * HW);
+  const int64_t nv = HW / 4;
+  float sI = 0.f, sG = 0.f, sP = 0.f;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < nv; i += gridDim.x * 256ll) {
+    const float4 x = x4[i], t = t4[i];
+    const float p0 = sigmoidf_(x.x), p1 = sigmoidf_(x.y), p2 = sigmoidf_(x.z), p3 = sigmoidf_(x.w);
+    sI += t.x * p0 + t.y * p1 + t.z * p2 + t.w * p3;
+    sG += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
+    sP += p0 * p0 + p1 * p1 + p2 * p2 + p3 * p3;
+  }
+  if (blockIdx.x == 0) {  // tail (HW % 4)
+    for (int64_t i = nv * 4 + threadIdx.x; i < HW; i += 256) {
+      const float x = logits[static_cast<int64_t>(n) * HW + i], t = target[static_cast<int64_t>(n) * HW + i];
+      const float p = sigmoidf_(x);
+      sI += t * p; sG += t * t; sP += p * p;
+    }
+  }
+  __shared__ float s_red[3][8];
+  sI = warp_sum(sI); sG = warp_sum(sG); sP = warp_sum(sP);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_red[0][warp] = sI; s_red[1][warp] = sG; s_red[2][warp] = sP; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += s_red[threadIdx.x][w];
+    atomicAdd(sums + static_cast<int64_t>(n) * 3 + threadIdx.x, t);
+  }
+}
+
+__global__ void dice_finalize_kernel(const float* __restrict__ sums, int N, float* __restrict__ loss) {
+  float s = 0.f;
+  for (int n = threadIdx.x; n < N; n += 32) {
+    const float I = sums[n * 3], G = sums[n * 3 + 1], P = sums[n * 3 + 2];
+    s += 1.f - (2.f * I + 1.f) / (G + P + 1.f);
+  }
+  s = warp_sum(s);
+  if (threadIdx.x == 0) loss[0] = s / static_cast<float>(N);
+}
+
+__global__ void __launch_bounds__(256) dice_bwd_kernel(const float* __restrict__ logits,
+                                                       const float* __restrict__ target, int64_t HW, int N,
+                                                       const float* __restrict__ sums, const float* __restrict__ gscale,
+                                                       float gmul, float* __restrict__ dlogits) {
+  const int n = blockIdx.y;
+  const float I = sums[n * 3], G = sums[n * 3 + 1], P = sums[n * 3 + 2];
+  const float D = G + P + 1.f, num = 2.f * I + 1.f;
+  const float gs = (gscale ? gscale[0] : 1.f) * gmul / static_cast<float>(N);
+  const float c1 = -2.f * gs / D;          // coefficient of t
+  const float c2 = 2.f * gs * num / (D * D);  // coefficient of p
+  const float* x = logits + static_cast<int64_t>(n) * HW;
+  const float* t = target + static_cast<int64_t>(n) * HW;
+  float* d = dlogits + static_cast<int64_t>(n) * HW;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < HW; i += gridDim.x * 256ll) {
+    const float p = sigmoidf_(x[i]);
+    d[i] = (c1 * t[i] + c2 * p) * p * (1.f - p);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ focal
+__device__ __forceinline__ void focal_sample(const float* x, const float* t, int K, float alpha, float gamma,
+                                             float* fl, float* dfl_dce, float* lse_out, float* tsum_out) {
+  float mx = x[0];
+  for (int k = 1; k < K; ++k) mx = fmaxf(mx, x[k]);
+  float se = 0.f;
+  for (int k = 0; k < K; ++k) se += expf(x[k] - mx);
+  const float lse = mx + logf(se);
+  float ce = 0.f, ts = 0.f;
+  for (int k = 0; k < K; ++k) { ce -= t[k] * (x[k] - lse); ts += t[k]; }
+  const float pt = expf(-ce);
+  const float om = 1.f - pt;
+  const float pw = powf(fmaxf(om, 0.f), gamma);
+  *fl = alpha * pw * ce;
+  // d/dce [ (1-pt)^g * ce ] = (1-pt)^g + g*(1-pt)^(g-1)*pt*ce
+  const float pwm1 = (gamma == 2.f) ? om : powf(fmaxf(om, 0.f), gamma - 1.f);
+  *dfl_dce = alpha * (pw + gamma * pwm1 * pt * ce);
+  *lse_out = lse;
+  *tsum_out = ts;
+}
+
+__global__ void focal_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ target, int N, int K,
+                                 float alpha, float gamma, float* __restrict__ loss) {
+  float s = 0.f;
+  for (int n = threadIdx.x; n < N; n += 32) {
+    float fl, d, lse, ts;
+    focal_sample(logits + static_cast<int64_t>(n) * K, target + static_cast<int64_t>(n) * K, K, alpha, gamma, &fl, &d,
+                 &lse, &ts);
+    s += fl;
+  }
+  s = warp_sum(s);
+  if (threadIdx.x == 0) loss[0] = s / static_cast<float>(N);
+}
+__global__ void focal_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ target, int N, int K,
+                                 float alpha, float gamma, const float* __restrict__ gscale, float gmul,
+                                 float* __restrict__ dlogits) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float* x = logits + static_cast<int64_t>(n) * K;
+  const float* t = target + static_cast<int64_t>(n) * K;
+  float fl, d, lse, ts;
+  focal_sample(x, t, K, alpha, gamma, &fl, &d, &lse, &ts);
+  const float gs = (gscale ? gscale[0] : 1.f) * gmul / static_cast<float>(N);
+  for (int k = 0; k < K; ++k) {
+    const float sm = expf(x[k] - lse);
+    dlogits[static_cast<int64_t>(n) * K + k] = gs * d * (sm * ts - t[k]);
+  }
+}
+
+__global__ void multitask_loss_kernel(const float* __restrict__ dice, int nheads, int inv_w,
+                                      const float* __restrict__ focal, float alpha_mix, float* __restrict__ out) {
+  float seg = 0.f;
+  for (int j = 0; j < nheads; ++j) seg += inv_w ? dice[j] / static_cast<float>(j + 1) : dice[j];
+  const float cls = focal[0];
+  out[0] = alpha_mix * seg + (1.f - alpha_mix) * cls;
+  out[1] = seg;
+  out[2] = cls;
+  out[3] = (isnan(seg) || isnan(cls)) ? 1.f : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------ refinement
+__global__ void __launch_bounds__(256) refine_count_kernel(const float* __restrict__ mask_logits, int64_t HW,
+                                                           int32_t* __restrict__ count) {
+  const int n = blockIdx.y;
+  const float* x = mask_logits + static_cast<int64_t>(n) * HW;
+  int c = 0;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < HW; i += gridDim.x * 256ll) c += x[i] > 0.f ? 1 : 0;
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(count + n, c);
+}
+__global__ void __launch_bounds__(256) refine_apply_kernel(const float* __restrict__ mask_logits,
+                                                           const float* __restrict__ class_logits, int64_t HW, int K,
+                                                           int normal_id, int seg_by_class, int class_by_seg,
+                                                           int pixel_threshold, const int32_t* __restrict__ count,
+                                                           uint8_t* __restrict__ mask_out,
+                                                           int32_t* __restrict__ class_out) {
+  const int n = blockIdx.y;
+  int cls = 0;
+  float best = class_logits[static_cast<int64_t>(n) * K];
+  for (int k = 1; k < K; ++k) {
+    const float v = class_logits[static_cast<int64_t>(n) * K + k];
+    if (v > best) { best = v; cls = k; }
+  }
+  const int cnt = count[n];
+  const bool kill = (pixel_threshold > 0 && cnt <= pixel_threshold) || (seg_by_class && cls == normal_id);
+  if (blockIdx.x == 0 && threadIdx.x == 0) class_out[n] = (class_by_seg && cnt == 0) ? normal_id : cls;
+  const float* x = mask_logits + static_cast<int64_t>(n) * HW;
+  uint8_t* m = mask_out + static_cast<int64_t>(n) * HW;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < HW; i += gridDim.x * 256ll)
+    m[i] = (!kill && x[i] > 0.f) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) hard_dice_counts_kernel(const float* __restrict__ logits,
+                                                               const float* __restrict__ target, int64_t n,
+                                                               unsigned long long* __restrict__ out) {
+  int tp = 0, fp = 0, fn = 0;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) {
+    const bool s = logits[i] > 0.f, g = target[i] != 0.f;
+    tp += (s && g); fp += (s && !g); fn += (!s && g);
+  }
+  tp = __reduce_add_sync(0xffffffffu, tp);
+  fp = __reduce_add_sync(0xffffffffu, fp);
+  fn = __reduce_add_sync(0xffffffffu, fn);
+  if ((threadIdx.x & 31) == 0) {
+    if (tp) atomicAdd(out, static_cast<unsigned long long>(tp));
+    if (fp) atomicAdd(out + 1, static_cast<unsigned long long>(fp));
+    if (fn) atomicAdd(out + 2, static_cast<unsigned long long>(fn));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ Adam
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
+                                                   float b1, float b2, float eps, float gscale, float bc1, float bc2s) {
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) {
+    const float gg = g[i] * gscale;
+    const float mm = b1 * m[i] + (1.f - b1) * gg;
+    const float vv = b2 * v[i] + (1.f - b2) * gg * gg;
+    m[i] = mm;
+    v[i] = vv;
+    const float denom = sqrtf(vv) / bc2s + eps;
+    p[i] -= (lr / bc1) * (mm / denom);
+  }
+}
+
+// Graph-friendly variant: step count and learning rate live in device memory so a captured launch stays valid.
+__global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                       float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                       const float* __restrict__ lr_dev, float b1, float b2, float eps,
+                                                       float gscale, const int32_t* __restrict__ step_dev) {
+  const float step = static_cast<float>(step_dev[0]);
+  const float bc1 = 1.f - powf(b1, step);
+  const float bc2s = sqrtf(1.f - powf(b2, step));
+  const float lr = lr_dev[0];
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) {
+    const float gg = g[i] * gscale;
+    const float mm = b1 * m[i] + (1.f - b1) * gg;
+    const float vv = b2 * v[i] + (1.f - b2) * gg * gg;
+    m[i] = mm;
+    v[i] = vv;
+    const float denom = sqrtf(vv) / bc2s + eps;
+    p[i] -= (lr / bc1) * (mm / denom);
+  }
+}
+__global__ void increment_i32_kernel(int32_t* p) { p[0] += 1; }
+
+}  // namespace mtbc
+
+using namespace mtbc;
+#define ST(s) static_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int mtbc_dice_sums(const float* logits, const float* target, int32_t N, int64_t HW, float* sums, void* stream) {
+  int gx = cdiv(HW / 4 + 1, 256 * 4); if (gx > (148 * 8) / N + 1) gx = (148 * 8) / N + 1; if (gx < 1) gx = 1;
+  dice_sums_kernel<<<dim3(gx, N), 256, 0, ST(stream)>>>(logits, target, HW, sums);
+  return check_launch("dice_sums");
+}
+int mtbc_dice_finalize(const float* sums, int32_t N, float* loss, void* stream) {
+  dice_finalize_kernel<<<1, 32, 0, ST(stream)>>>(sums, N, loss);
+  return check_launch("dice_finalize");
+}
+int mtbc_dice_bwd(const float* logits, const float* target, int32_t N, int64_t HW, const float* sums,
+                  const float* gscale, float gmul, float* dlogits, void* stream) {
+  int gx = cdiv(HW, 256 * 4); if (gx > (148 * 8) / N + 1) gx = (148 * 8) / N + 1; if (gx < 1) gx = 1;
+  dice_bwd_kernel<<<dim3(gx, N), 256, 0, ST(stream)>>>(logits, target, HW, N, sums, gscale, gmul, dlogits);
+  return check_launch("dice_bwd");
+}
+int mtbc_focal_fwd(const float* logits, const float* target, int32_t N, int32_t K, float alpha, float gamma,
+                   float* loss, void* stream) {
+  focal_fwd_kernel<<<1, 32, 0, ST(stream)>>>(logits, target, N, K, alpha, gamma, loss);
+  return check_launch("focal_fwd");
+}
+int mtbc_focal_bwd(const float* logits, const float* target, int32_t N, int32_t K, float alpha, float gamma,
+                   const float* gscale, float gmul, float* dlogits, void* stream) {
+  focal_bwd_kernel<<<cdiv(N, 64), 64, 0, ST(stream)>>>(logits, target, N, K, alpha, gamma, gscale, gmul, dlogits);
+  return check_launch("focal_bwd");
+}
+int mtbc_multitask_loss(const float* dice_losses, int32_t nheads, int32_t inversely_weighted, const float* focal,
+                        float alpha_mix, float* out, void* stream) {
+  multitask_loss_kernel<<<1, 1, 0, ST(stream)>>>(dice_losses, nheads, inversely_weighted, focal, alpha_mix, out);
+  return check_launch("multitask_loss");
+}
+
+int mtbc_refine_predictions(const float* mask_logits, const float* class_logits, int32_t N, int64_t HW, int32_t K,
+                            int32_t normal_id, int32_t seg_by_class, int32_t class_by_seg, int32_t pixel_threshold,
+                            uint8_t* mask_out, int32_t* class_out, int32_t* count_out, void* stream) {
+  cudaError_t e = cudaMemsetAsync(count_out, 0, N * sizeof(int32_t), ST(stream));
+  if (e != cudaSuccess) return set_error(MTBC_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
+  int gx = cdiv(HW, 256 * 8); if (gx > (148 * 8) / N + 1) gx = (148 * 8) / N + 1; if (gx < 1) gx = 1;
+  refine_count_kernel<<<dim3(gx, N), 256, 0, ST(stream)>>>(mask_logits, HW, count_out);
+  int rc = check_launch("refine_count");
+  if (rc) return rc;
+  refine_apply_kernel<<<dim3(gx, N), 256, 0, ST(stream)>>>(mask_logits, class_logits, HW, K, normal_id, seg_by_class,
+                                                          class_by_seg, pixel_threshold, count_out, mask_out, class_out);
+  return check_launch("refine_apply");
+}
+int mtbc_hard_dice_counts(const float* logits, const float* target, int64_t n, long long* out, void* stream) {
+  int g = cdiv(n, 256 * 8); if (g > 148 * 8) g = 148 * 8; if (g < 1) g = 1;
+  hard_dice_counts_kernel<<<g, 256, 0, ST(stream)>>>(logits, target, n, reinterpret_cast<unsigned long long*>(out));
+  return check_launch("hard_dice_counts");
+}
+
+int mtbc_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                   float beta1, float beta2, float eps, float grad_scale, int32_t step, void* stream) {
+  if (n <= 0) return 0;
+  const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
+  const float bc2s = sqrtf(1.f - powf(beta2, static_cast<float>(step)));
+  int g = cdiv(n, 256 * 4); if (g > 148 * 8) g = 148 * 8;
+  adam_kernel<<<g, 256, 0, ST(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, grad_scale, bc1, bc2s);
+  return check_launch("adam_step");
+}
+
+int mtbc_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                       const float* lr_dev, float beta1, float beta2, float eps, float grad_scale,
+                       const int32_t* step_dev, void* stream) {
+  if (n <= 0) return 0;
+  int g = cdiv(n, 256 * 4); if (g > 148 * 8) g = 148 * 8;
+  adam_dev_kernel<<<g, 256, 0, ST(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr_dev, beta1, beta2, eps, grad_scale, step_dev);
+  return check_launch("adam_step_dev");
+}
+int mtbc_increment_i32(int32_t* p, void* stream) {
+  increment_i32_kernel<<<1, 1, 0, ST(stream)>>>(p);
+  return check_launch("increment_i32");
+}
+
+}  // extern "C"

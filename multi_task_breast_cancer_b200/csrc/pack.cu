@@ -1,0 +1,323 @@
+// Parameter (fp32, PyTorch layout) <-> GEMM operand (bf16, padded, K-major) packing, the Cin<=4 first layer, and small
+// utilities.  All memory bound / tiny.
+#include "ptx.cuh"
+#include "internal.h"
+
+namespace mtbc {
+
+// ------------------------------------------------------------------------------------------------ conv weights
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int ksz, int c_begin,
+                                        int c_count, __nv_bfloat16* __restrict__ wf, int wf_rows, int wf_ld, int wf_k0,
+                                        __nv_bfloat16* __restrict__ wd, int wd_rows, int wd_ld) {
+  const int taps = ksz * ksz;
+  const int64_t total = static_cast<int64_t>(Cout) * c_count * taps;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int tap = static_cast<int>(i % taps);
+    const int cl = static_cast<int>((i / taps) % c_count);
+    const int co = static_cast<int>(i / (static_cast<int64_t>(taps) * c_count));
+    const float v = w[(static_cast<int64_t>(co) * Cin + c_begin + cl) * taps + tap];
+    const __nv_bfloat16 b = __float2bfloat16(v);
+    if (wf) wf[(static_cast<int64_t>(tap) * wf_rows + co) * wf_ld + wf_k0 + cl] = b;
+    if (wd) wd[(static_cast<int64_t>(taps - 1 - tap) * wd_rows + cl) * wd_ld + co] = b;
+  }
+}
+
+__global__ void pack_convT_weight_kernel(const float* __restrict__ w, int Cin, int Cout, int k, int cp,
+                                         __nv_bfloat16* __restrict__ wf, int wf_ld, __nv_bfloat16* __restrict__ wd,
+                                         int wd_rows, int wd_ld) {
+  const int kk = k * k;
+  const int64_t total = static_cast<int64_t>(Cin) * Cout * kk;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int q = static_cast<int>(i % kk);
+    const int co = static_cast<int>((i / kk) % Cout);
+    const int ci = static_cast<int>(i / (static_cast<int64_t>(kk) * Cout));
+    const __nv_bfloat16 b = __float2bfloat16(w[i]);
+    if (wf) wf[(static_cast<int64_t>(q) * cp + co) * wf_ld + ci] = b;
+    if (wd) wd[(static_cast<int64_t>(q) * wd_rows + ci) * wd_ld + co] = b;
+  }
+}
+
+__global__ void unpack_conv_wgrad_kernel(const float* __restrict__ acc, int rows, int ld, int k0,
+                                         float* __restrict__ grad, int Cout, int Cin, int ksz, int c_begin,
+                                         int c_count, int add) {
+  const int taps = ksz * ksz;
+  const int64_t total = static_cast<int64_t>(Cout) * c_count * taps;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int tap = static_cast<int>(i % taps);
+    const int cl = static_cast<int>((i / taps) % c_count);
+    const int co = static_cast<int>(i / (static_cast<int64_t>(taps) * c_count));
+    const float v = acc[(static_cast<int64_t>(tap) * rows + co) * ld + k0 + cl];
+    float* g = grad + (static_cast<int64_t>(co) * Cin + c_begin + cl) * taps + tap;
+    *g = add ? (*g + v) : v;
+  }
+}
+
+__global__ void unpack_convT_wgrad_kernel(const float* __restrict__ acc, int rows, int ld, float* __restrict__ grad,
+                                          int Cin, int Cout, int k, int add) {
+  const int kk = k * k;
+  const int cp = rows / kk;
+  const int64_t total = static_cast<int64_t>(Cin) * Cout * kk;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int q = static_cast<int>(i % kk);
+    const int co = static_cast<int>((i / kk) % Cout);
+    const int ci = static_cast<int>(i / (static_cast<int64_t>(kk) * Cout));
+    const float v = acc[(static_cast<int64_t>(q) * cp + co) * ld + ci];
+    grad[i] = add ? (grad[i] + v) : v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ first layer
+// One thread per output pixel, 128 consecutive pixels of one sample per block; weights staged in smem.
+__global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __restrict__ x, int N, int Cin, int H, int W,
+                                                             const float* __restrict__ w, const float* __restrict__ bias,
+                                                             int Cout, __nv_bfloat16* __restrict__ y, int Cp,
+                                                             float* __restrict__ stat_sum, float* __restrict__ stat_sq) {
+  extern __shared__ float sm[];
+  float* s_w = sm;                    // [Cp][Cin*9], zero padded
+  float* s_b = s_w + Cp * Cin * 9;    // [Cp]
+  float* s_st = s_b + Cp;             // [2][Cp]
+  const int K = Cin * 9;
+  for (int i = threadIdx.x; i < Cp * K; i += 128) s_w[i] = (i / K) < Cout ? w[i] : 0.f;
+  for (int i = threadIdx.x; i < Cp; i += 128) {
+    s_b[i] = (bias != nullptr && i < Cout) ? bias[i] : 0.f;
+    s_st[i] = 0.f;
+    s_st[Cp + i] = 0.f;
+  }
+  __syncthreads();
+  const int64_t HW = static_cast<int64_t>(H) * W;
+  const int64_t pix = blockIdx.x * 128ll + threadIdx.x;  // within the whole batch
+  const int n = static_cast<int>(pix / HW);
+  const int hw = static_cast<int>(pix - n * HW);
+  const int h = hw / W, ww = hw - h * W;
+  const int lane = threadIdx.x & 31;
+  float xin[36];
+#pragma unroll 4
+  for (int ci = 0; ci < Cin; ++ci)
+    for (int r = 0; r < 3; ++r)
+      for (int s = 0; s < 3; ++s) {
+        const int hh = h + r - 1, wc = ww + s - 1;
+        xin[ci * 9 + r * 3 + s] =
+            (hh >= 0 && hh < H && wc >= 0 && wc < W) ? x[(static_cast<int64_t>(n) * Cin + ci) * HW + hh * W + wc] : 0.f;
+      }
+  __nv_bfloat16* dst = y + pix * Cp;
+  for (int c0 = 0; c0 < Cp; c0 += 16) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float a = s_b[c0 + i];
+      const float* wr = s_w + (c0 + i) * K;
+      for (int k = 0; k < K; ++k) a = fmaf(xin[k], wr[k], a);
+      v[i] = a;
+    }
+    if (stat_sum != nullptr) {
+      float sq[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) sq[i] = v[i] * v[i];
+      const float cs = warp_colsum16(v, lane);
+      const float cq = warp_colsum16(sq, lane);
+      if ((lane & 1) == 0) {
+        const int cc = c0 + col16_of_lane(lane);
+        atomicAdd(&s_st[cc], cs);
+        atomicAdd(&s_st[Cp + cc], cq);
+      }
+    }
+    uint4 r0, r1;
+    r0.x = pack_bf16x2(v[0], v[1]); r0.y = pack_bf16x2(v[2], v[3]); r0.z = pack_bf16x2(v[4], v[5]); r0.w = pack_bf16x2(v[6], v[7]);
+    r1.x = pack_bf16x2(v[8], v[9]); r1.y = pack_bf16x2(v[10], v[11]); r1.z = pack_bf16x2(v[12], v[13]); r1.w = pack_bf16x2(v[14], v[15]);
+    reinterpret_cast<uint4*>(dst + c0)[0] = r0;
+    reinterpret_cast<uint4*>(dst + c0)[1] = r1;
+  }
+  if (stat_sum != nullptr) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < Cp; i += 128) {
+      atomicAdd(stat_sum + static_cast<int64_t>(n) * Cp + i, s_st[i]);
+      atomicAdd(stat_sq + static_cast<int64_t>(n) * Cp + i, s_st[Cp + i]);
+    }
+  }
+}
+
+// dW[co][ci][r][s] += sum_pix x[n,ci,h+r-1,w+s-1] * dy[pix][co].  grid = (pixel blocks, Cin*3): one (ci, r) per y.
+__global__ void __launch_bounds__(128) conv_first_wgrad_kernel(const float* __restrict__ x, int N, int Cin, int H,
+                                                               int W, const __nv_bfloat16* __restrict__ dy, int Cp,
+                                                               int Cout, float* __restrict__ dw) {
+  __shared__ float s_acc[3][64];
+  const int ci = blockIdx.y / 3, r = blockIdx.y % 3;
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 3 * 64; i += 128) (&s_acc[0][0])[i] = 0.f;
+  __syncthreads();
+  const int64_t HW = static_cast<int64_t>(H) * W;
+  const int64_t total = static_cast<int64_t>(N) * HW;
+  for (int c0 = 0; c0 < Cp && c0 < 64; c0 += 16) {
+    float acc[3][16];
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[s][i] = 0.f;
+    for (int64_t pix = blockIdx.x * 128ll + threadIdx.x; pix < total; pix += static_cast<int64_t>(gridDim.x) * 128) {
+      const int n = static_cast<int>(pix / HW);
+      const int hw = static_cast<int>(pix - n * HW);
+      const int h = hw / W, ww = hw - h * W;
+      const int hh = h + r - 1;
+      float xs[3];
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int wc = ww + s - 1;
+        xs[s] = (hh >= 0 && hh < H && wc >= 0 && wc < W) ? x[(static_cast<int64_t>(n) * Cin + ci) * HW + hh * W + wc] : 0.f;
+      }
+      const uint4* src = reinterpret_cast<const uint4*>(dy + pix * Cp + c0);
+      const uint4 d0 = src[0], d1 = src[1];
+      const uint32_t du[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 f = unpack_bf16x2(du[i]);
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          acc[s][2 * i] = fmaf(xs[s], f.x, acc[s][2 * i]);
+          acc[s][2 * i + 1] = fmaf(xs[s], f.y, acc[s][2 * i + 1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const float cs = warp_colsum16(acc[s], lane);
+      if ((lane & 1) == 0) atomicAdd(&s_acc[s][c0 + col16_of_lane(lane)], cs);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * 64; i += 128) {
+    const int s = i / 64, co = i % 64;
+    if (co < Cout) atomicAdd(dw + ((static_cast<int64_t>(co) * Cin + ci) * 3 + r) * 3 + s, s_acc[s][co]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ utilities
+__global__ void fill_f32_kernel(float* p, int64_t n, float v) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    p[i] = v;
+}
+__global__ void f32_to_bf16_nhwc_kernel(const float* __restrict__ x, int N, int C, int H, int W,
+                                        __nv_bfloat16* __restrict__ y, int Cp) {
+  const int64_t HW = static_cast<int64_t>(H) * W;
+  const int64_t total = static_cast<int64_t>(N) * HW * Cp;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % Cp);
+    const int64_t pix = i / Cp;
+    const int n = static_cast<int>(pix / HW);
+    const int64_t hw = pix - n * HW;
+    y[i] = __float2bfloat16(c < C ? x[(static_cast<int64_t>(n) * C + c) * HW + hw] : 0.f);
+  }
+}
+__global__ void bf16_nhwc_to_f32_kernel(const __nv_bfloat16* __restrict__ x, int N, int C, int H, int W, int Cp,
+                                        float* __restrict__ y) {
+  const int64_t HW = static_cast<int64_t>(H) * W;
+  const int64_t total = static_cast<int64_t>(N) * C * HW;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t hw = i % HW;
+    const int c = static_cast<int>((i / HW) % C);
+    const int n = static_cast<int>(i / (HW * C));
+    y[i] = __bfloat162float(x[(n * HW + hw) * Cp + c]);
+  }
+}
+
+static int grid_for(int64_t n, int block) {
+  int64_t g = (n + block - 1) / block;
+  if (g > 148 * 16) g = 148 * 16;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace mtbc
+
+using namespace mtbc;
+
+extern "C" {
+
+int mtbc_pack_conv_weight(const float* w, int32_t Cout, int32_t Cin, int32_t ksz, int32_t c_begin, int32_t c_count,
+                          void* wf, int32_t wf_rows, int32_t wf_ld, int32_t wf_k0, void* wd, int32_t wd_rows,
+                          int32_t wd_ld, void* stream) {
+  if (!w || c_begin < 0 || c_begin + c_count > Cin) return set_error(MTBC_ERR_INVALID, "pack_conv_weight: bad slice");
+  const int64_t total = static_cast<int64_t>(Cout) * c_count * ksz * ksz;
+  pack_conv_weight_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, Cout, Cin, ksz, c_begin, c_count, static_cast<__nv_bfloat16*>(wf), wf_rows, wf_ld, wf_k0,
+      static_cast<__nv_bfloat16*>(wd), wd_rows, wd_ld);
+  return check_launch("pack_conv_weight");
+}
+int mtbc_pack_convT_weight(const float* w, int32_t Cin, int32_t Cout, int32_t k, int32_t cp, void* wf, int32_t wf_ld,
+                           void* wd, int32_t wd_rows, int32_t wd_ld, void* stream) {
+  if (!w) return set_error(MTBC_ERR_INVALID, "pack_convT_weight: null");
+  const int64_t total = static_cast<int64_t>(Cin) * Cout * k * k;
+  pack_convT_weight_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, Cin, Cout, k, cp, static_cast<__nv_bfloat16*>(wf), wf_ld, static_cast<__nv_bfloat16*>(wd), wd_rows, wd_ld);
+  return check_launch("pack_convT_weight");
+}
+int mtbc_unpack_conv_wgrad(const float* acc, int32_t rows, int32_t ld, int32_t k0, float* grad, int32_t Cout,
+                           int32_t Cin, int32_t ksz, int32_t c_begin, int32_t c_count, int32_t add, void* stream) {
+  const int64_t total = static_cast<int64_t>(Cout) * c_count * ksz * ksz;
+  unpack_conv_wgrad_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      acc, rows, ld, k0, grad, Cout, Cin, ksz, c_begin, c_count, add);
+  return check_launch("unpack_conv_wgrad");
+}
+int mtbc_unpack_convT_wgrad(const float* acc, int32_t rows, int32_t ld, float* grad, int32_t Cin, int32_t Cout,
+                            int32_t k, int32_t add, void* stream) {
+  const int64_t total = static_cast<int64_t>(Cin) * Cout * k * k;
+  unpack_convT_wgrad_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(acc, rows, ld, grad,
+                                                                                                 Cin, Cout, k, add);
+  return check_launch("unpack_convT_wgrad");
+}
+
+int mtbc_conv_first_fwd(const float* x, int32_t N, int32_t Cin, int32_t H, int32_t W, const float* w, const float* bias,
+                        int32_t Cout, void* y, int32_t Cp, float* stat_sum, float* stat_sq, void* stream) {
+  if (Cin < 1 || Cin > 4 || Cp % 16 != 0 || Cout > Cp) return set_error(MTBC_ERR_INVALID, "conv_first_fwd: Cin must be 1..4");
+  const int64_t HW = static_cast<int64_t>(H) * W;
+  if (HW % 128 != 0) return set_error(MTBC_ERR_INVALID, "conv_first_fwd: H*W must be a multiple of 128");
+  const int smem = (Cp * Cin * 9 + 3 * Cp) * sizeof(float);
+  conv_first_fwd_kernel<<<static_cast<int>(N * HW / 128), 128, smem, static_cast<cudaStream_t>(stream)>>>(
+      x, N, Cin, H, W, w, bias, Cout, static_cast<__nv_bfloat16*>(y), Cp, stat_sum, stat_sq);
+  return check_launch("conv_first_fwd");
+}
+int mtbc_conv_first_wgrad(const float* x, int32_t N, int32_t Cin, int32_t H, int32_t W, const void* dy, int32_t Cp,
+                          int32_t Cout, float* dw, void* stream) {
+  if (Cin < 1 || Cin > 4 || Cout > 64 || Cp % 16 != 0) return set_error(MTBC_ERR_INVALID, "conv_first_wgrad: Cin 1..4, Cout <= 64");
+  const int64_t total = static_cast<int64_t>(N) * H * W;
+  int gx = static_cast<int>((total + 128 * 16 - 1) / (128 * 16));
+  if (gx > 148 * 4) gx = 148 * 4;
+  if (gx < 1) gx = 1;
+  conv_first_wgrad_kernel<<<dim3(gx, Cin * 3), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, N, Cin, H, W, static_cast<const __nv_bfloat16*>(dy), Cp, Cout, dw);
+  return check_launch("conv_first_wgrad");
+}
+
+int mtbc_fill_f32(float* p, int64_t n, float v, void* stream) {
+  if (n <= 0) return 0;
+  fill_f32_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, n, v);
+  return check_launch("fill_f32");
+}
+int mtbc_zero_bytes(void* p, int64_t nbytes, void* stream) {
+  if (nbytes <= 0) return 0;
+  cudaError_t e = cudaMemsetAsync(p, 0, static_cast<size_t>(nbytes), static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return set_error(MTBC_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+  return 0;
+}
+int mtbc_f32_to_bf16_nhwc(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, void* y, int32_t Cp,
+                          void* stream) {
+  const int64_t total = static_cast<int64_t>(N) * H * W * Cp;
+  f32_to_bf16_nhwc_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, N, C, H, W, static_cast<__nv_bfloat16*>(y), Cp);
+  return check_launch("f32_to_bf16_nhwc");
+}
+int mtbc_bf16_nhwc_to_f32(const void* x, int32_t N, int32_t C, int32_t H, int32_t W, int32_t Cp, float* y,
+                          void* stream) {
+  const int64_t total = static_cast<int64_t>(N) * C * H * W;
+  bf16_nhwc_to_f32_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), N, C, H, W, Cp, y);
+  return check_launch("bf16_nhwc_to_f32");
+}
+
+}  // extern "C"
