@@ -1,0 +1,243 @@
+"""Host-side builders that turn feature maps into libmtbc op handles / calls.
+
+A feature map (`Feat`) is a bf16 NHWC torch tensor whose channel count is padded to a multiple of 32; PyTorch only owns
+the memory.  The builders mirror the reference layers they replace:
+
+* conv3x3 (+ folded skip concatenation)   MTnnUNet.py:12-16, MONAI Convolution (MTUNetPlusPlus.py:47-71,107-118)
+* ConvTranspose2d k == stride             MTnnUNet.py:96-100, MONAI UpCat.upsample.deconv
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import ActView, ConvGemmDesc, GemmSeg, WgradDesc, WgradTap
+
+
+def pad32(c: int) -> int:
+    return (c + 31) // 32 * 32
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+@dataclass
+class Feat:
+    """bf16 NHWC activation with padded channels."""
+    t: torch.Tensor  # [N, H, W, Cp] bf16
+    C: int           # true channels
+
+    @property
+    def N(self): return self.t.shape[0]
+    @property
+    def H(self): return self.t.shape[1]
+    @property
+    def W(self): return self.t.shape[2]
+    @property
+    def Cp(self): return self.t.shape[3]
+
+    @staticmethod
+    def empty(N, H, W, C, device="cuda", zero=True) -> "Feat":
+        f = torch.zeros if zero else torch.empty
+        return Feat(f((N, H, W, pad32(C)), dtype=torch.bfloat16, device=device), C)
+
+    @staticmethod
+    def from_nchw(x: torch.Tensor) -> "Feat":
+        N, Cc, H, W = x.shape
+        out = Feat.empty(N, H, W, Cc, device=x.device)
+        out.t[..., :Cc] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
+        return out
+
+    def to_nchw(self) -> torch.Tensor:
+        return self.t[..., : self.C].permute(0, 3, 1, 2).float().contiguous()
+
+
+def _view(f: Feat) -> ActView:
+    v = ActView()
+    v.ptr = f.t.data_ptr()
+    v.C, v.W, v.H, v.N = f.Cp, f.W, f.H, f.N
+    v.sW, v.sH, v.sN = f.Cp, f.W * f.Cp, f.H * f.W * f.Cp
+    return v
+
+
+def _strided_view(f: Feat, k: int, i: int, j: int) -> ActView:
+    """View of every k-th pixel of f starting at (i, j): the (i, j) sub-lattice of a k-times upsampled map."""
+    v = ActView()
+    v.ptr = f.t.data_ptr() + 2 * ((i * f.W + j) * f.Cp)
+    v.C, v.W, v.H, v.N = f.Cp, f.W // k, f.H // k, f.N
+    v.sW, v.sH, v.sN = k * f.Cp, k * f.W * f.Cp, f.H * f.W * f.Cp
+    return v
+
+
+class Op:
+    """Owning wrapper of an opaque mtbc_op handle."""
+
+    def __init__(self, handle: C.c_void_p, keep: Sequence[object], kind: str):
+        self.handle = handle
+        self._keep = list(keep)  # tensors whose memory the encoded tensor maps point to
+        self.kind = kind
+        self.flops = _lib.load().mtbc_op_flops(handle)
+
+    def launch(self, stream: Optional[int] = None):
+        _lib.check(_lib.load().mtbc_op_launch(self.handle, C.c_void_p(stream if stream is not None else stream_ptr())),
+                   self.kind)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.load().mtbc_op_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def k_offsets(srcs: Sequence[Feat]):
+    """Column offsets of each concat source inside a packed weight row, and the padded row length."""
+    offs, o = [], 0
+    for s in srcs:
+        a = 64 if s.Cp % 64 == 0 else 32
+        o = (o + a - 1) // a * a
+        offs.append(o)
+        o += s.Cp
+    return offs, o
+
+
+def _create_gemm(d: ConvGemmDesc, keep, kind) -> Op:
+    h = C.c_void_p()
+    _lib.check(_lib.load().mtbc_conv_gemm_create(C.byref(d), C.byref(h)), kind)
+    return Op(h, keep, kind)
+
+
+def conv3x3_fwd_op(srcs: Sequence[Feat], wpack: torch.Tensor, out: Feat, bias: Optional[torch.Tensor] = None,
+                   stat_sum: Optional[torch.Tensor] = None, stat_sq: Optional[torch.Tensor] = None,
+                   accumulate: bool = False, ksz: int = 3) -> Op:
+    """wpack: bf16 [ksz*ksz][out.Cp][Ktot] laid out by `k_offsets(srcs)`."""
+    offs, ktot = k_offsets(srcs)
+    assert wpack.shape == (ksz * ksz, out.Cp, ktot), (wpack.shape, (ksz * ksz, out.Cp, ktot))
+    d = ConvGemmDesc()
+    d.nviews = len(srcs)
+    for i, s in enumerate(srcs):
+        d.views[i] = _view(s)
+    n = 0
+    half = ksz // 2
+    for r in range(ksz):
+        for c in range(ksz):
+            for i, s in enumerate(srcs):
+                d.seg[n] = GemmSeg(i, r - half, c - half, offs[i], r * ksz + c)
+                n += 1
+    d.nseg = n
+    d.wpack = wpack.data_ptr(); d.w_ntaps = ksz * ksz; d.w_ktot = ktot; d.ncols = out.Cp
+    d.W, d.H, d.N = out.W, out.H, out.N
+    d.epi_mode = 0; d.out = out.t.data_ptr(); d.out_C = out.Cp; d.up_k = 1; d.up_cp = out.Cp
+    d.bias = None if bias is None else bias.data_ptr()
+    d.stat_sum = None if stat_sum is None else stat_sum.data_ptr()
+    d.stat_sq = None if stat_sq is None else stat_sq.data_ptr()
+    d.stat_C = out.Cp
+    d.accumulate = int(accumulate)
+    return _create_gemm(d, [*(s.t for s in srcs), wpack, out.t, bias, stat_sum, stat_sq], "conv3x3_fwd")
+
+
+def conv3x3_dgrad_op(dy: Feat, wd: torch.Tensor, dx: Feat, accumulate: bool, ksz: int = 3) -> Op:
+    """wd: bf16 [ksz*ksz][dx.Cp][dy.Cp] (flipped taps, transposed channels) -> dx (+)= conv(dy, wd)."""
+    return conv3x3_fwd_op([dy], wd, dx, accumulate=accumulate, ksz=ksz)
+
+
+def convT_fwd_op(x: Feat, wf: torch.Tensor, out: Feat, k: int, bias: Optional[torch.Tensor]) -> Op:
+    """wf: bf16 [1][k*k*out.Cp][x.Cp]; out spatial = k * x spatial."""
+    assert wf.shape == (1, k * k * out.Cp, x.Cp)
+    d = ConvGemmDesc()
+    d.nviews = 1; d.views[0] = _view(x)
+    d.nseg = 1; d.seg[0] = GemmSeg(0, 0, 0, 0, 0)
+    d.wpack = wf.data_ptr(); d.w_ntaps = 1; d.w_ktot = x.Cp; d.ncols = k * k * out.Cp
+    d.W, d.H, d.N = x.W, x.H, x.N
+    d.epi_mode = 1; d.out = out.t.data_ptr(); d.out_C = out.Cp; d.up_k = k; d.up_cp = out.Cp
+    d.bias = None if bias is None else bias.data_ptr()
+    d.stat_sum = None; d.stat_sq = None; d.stat_C = 0; d.accumulate = 0
+    return _create_gemm(d, [x.t, wf, out.t, bias], "convT_fwd")
+
+
+def convT_dgrad_op(dout: Feat, wd: torch.Tensor, dx: Feat, k: int, accumulate: bool) -> Op:
+    """wd: bf16 [k*k][dx.Cp][dout.Cp]; dx (+)= sum_q dout_q * wd[q]."""
+    assert wd.shape == (k * k, dx.Cp, dout.Cp)
+    d = ConvGemmDesc()
+    d.nviews = k * k
+    for q in range(k * k):
+        d.views[q] = _strided_view(dout, k, q // k, q % k)
+        d.seg[q] = GemmSeg(q, 0, 0, 0, q)
+    d.nseg = k * k
+    d.wpack = wd.data_ptr(); d.w_ntaps = k * k; d.w_ktot = dout.Cp; d.ncols = dx.Cp
+    d.W, d.H, d.N = dx.W, dx.H, dx.N
+    d.epi_mode = 0; d.out = dx.t.data_ptr(); d.out_C = dx.Cp; d.up_k = 1; d.up_cp = dx.Cp
+    d.bias = None; d.stat_sum = None; d.stat_sq = None; d.stat_C = 0; d.accumulate = int(accumulate)
+    return _create_gemm(d, [dout.t, wd, dx.t], "convT_dgrad")
+
+
+def conv3x3_wgrad_op(x: Feat, dy: Feat, dw_acc: torch.Tensor, k0: int, ksz: int = 3, splits: int = 0) -> Op:
+    """dw_acc: fp32 [ksz*ksz][dy.Cp][Ktot]; accumulates the slice of source x at column k0."""
+    assert dw_acc.dtype == torch.float32 and dw_acc.shape[0] == ksz * ksz and dw_acc.shape[1] == dy.Cp
+    d = WgradDesc()
+    d.a_nviews = 1; d.a_views[0] = _view(x)
+    d.b_nviews = 1; d.b_views[0] = _view(dy)
+    half = ksz // 2
+    n = 0
+    for r in range(ksz):
+        for c in range(ksz):
+            d.taps[n] = WgradTap(0, r - half, c - half, 0)
+            n += 1
+    d.ntaps = n
+    d.W, d.H, d.N = dy.W, dy.H, dy.N
+    d.dw_acc = dw_acc.data_ptr(); d.n_rows = dw_acc.shape[1]; d.ld_k = dw_acc.shape[2]; d.k0 = k0; d.splits = splits
+    h = C.c_void_p()
+    _lib.check(_lib.load().mtbc_wgrad_create(C.byref(d), C.byref(h)), "conv3x3_wgrad")
+    return Op(h, [x.t, dy.t, dw_acc], "conv3x3_wgrad")
+
+
+def convT_wgrad_op(x: Feat, dout: Feat, dw_acc: torch.Tensor, k: int, splits: int = 0) -> Op:
+    """dw_acc: fp32 [k*k][dout.Cp][x.Cp]."""
+    assert dw_acc.shape == (k * k, dout.Cp, x.Cp)
+    d = WgradDesc()
+    d.a_nviews = 1; d.a_views[0] = _view(x)
+    d.b_nviews = k * k
+    assert k * k <= 4, "tensor-core convT wgrad supports k = 2 (b_views[4])"
+    for q in range(k * k):
+        d.b_views[q] = _strided_view(dout, k, q // k, q % k)
+        d.taps[q] = WgradTap(0, 0, 0, q)
+    d.ntaps = k * k
+    d.W, d.H, d.N = x.W, x.H, x.N
+    d.dw_acc = dw_acc.data_ptr(); d.n_rows = dw_acc.shape[1]; d.ld_k = dw_acc.shape[2]; d.k0 = 0; d.splits = splits
+    h = C.c_void_p()
+    _lib.check(_lib.load().mtbc_wgrad_create(C.byref(d), C.byref(h)), "convT_wgrad")
+    return Op(h, [x.t, dout.t, dw_acc], "convT_wgrad")
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Weight packing helpers (fp32 parameters -> bf16 GEMM operands).  The packed buffers are allocated zeroed once; only
+# true (unpadded) entries are ever rewritten, so pad rows/columns stay exactly zero.
+
+def pack_conv_weight(w: torch.Tensor, srcs_C: Sequence[int], offs: Sequence[int], wf: torch.Tensor,
+                     wds: Sequence[Optional[torch.Tensor]], stream: Optional[int] = None):
+    Cout, Cin, ksz, _ = w.shape
+    st = C.c_void_p(stream if stream is not None else stream_ptr())
+    c0 = 0
+    for cs, off, wd in zip(srcs_C, offs, wds):
+        _lib.call("mtbc_pack_conv_weight", ptr(w), Cout, Cin, ksz, c0, cs, ptr(wf), wf.shape[1], wf.shape[2], off,
+                  ptr(wd), 0 if wd is None else wd.shape[1], 0 if wd is None else wd.shape[2], st)
+        c0 += cs
+    assert c0 == Cin
+
+
+def pack_convT_weight(w: torch.Tensor, cp: int, wf: torch.Tensor, wd: Optional[torch.Tensor],
+                      stream: Optional[int] = None):
+    Cin, Cout, k, _ = w.shape
+    st = C.c_void_p(stream if stream is not None else stream_ptr())
+    _lib.call("mtbc_pack_convT_weight", ptr(w), Cin, Cout, k, cp, ptr(wf), wf.shape[2], ptr(wd),
+              0 if wd is None else wd.shape[1], 0 if wd is None else wd.shape[2], st)

@@ -1,0 +1,362 @@
+"""GPU diagnostic: run every tcgen05 GEMM variant (and the streaming kernels) against torch fp32 on the same bf16-rounded
+inputs and print an error summary per case.  Never stops at the first failure; meant for `gpurun`.
+
+    python tools/diag_kernels.py [--quick]
+"""
+import os
+import sys
+import traceback
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch
+import torch.nn.functional as F
+
+from multi_task_breast_cancer_b200 import _lib, ops
+from multi_task_breast_cancer_b200.ops import Feat, pad32
+
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+dev = "cuda"
+RESULTS = []
+
+
+def report(name, got, ref, tol=2e-2):
+    got = got.float()
+    ref = ref.float()
+    err = (got - ref).abs()
+    scale = ref.abs().max().item() + 1e-12
+    rel = err.max().item() / scale
+    ok = bool(torch.isfinite(got).all().item()) and rel < tol
+    RESULTS.append((name, ok, rel))
+    print(f"[{'OK ' if ok else 'BAD'}] {name}: max|err|={err.max().item():.4g} ref max={scale:.4g} rel={rel:.3g}", flush=True)
+    if not ok:
+        idx = torch.nonzero(err > tol * scale)[:6]
+        for i in idx:
+            t = tuple(i.tolist())
+            print("      at", t, "got", got[t].item(), "ref", ref[t].item())
+        print("      fraction bad:", (err > tol * scale).float().mean().item())
+    return ok
+
+
+def rnd(*shape, scale=1.0):
+    return (torch.randn(*shape, device=dev) * scale).to(torch.bfloat16).float()
+
+
+def run_case(fn, name):
+    try:
+        fn()
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa
+        RESULTS.append((name, False, float("nan")))
+        print(f"[EXC] {name}: {e}")
+        traceback.print_exc()
+
+
+def conv_fwd_case(N, H, W, src_C, Cout, bias=True, stats=True, identity=False):
+    name = f"conv3x3_fwd N{N} {H}x{W} src{src_C}->{Cout} bias={bias} stats={stats} id={identity}"
+
+    def fn():
+        xs = [rnd(N, c, H, W) for c in src_C]
+        Cin = sum(src_C)
+        w = rnd(Cout, Cin, 3, 3, scale=0.1)
+        if identity:
+            w.zero_()
+            for i in range(min(Cout, Cin)):
+                w[i, i, 1, 1] = 1.0
+        b = rnd(Cout) if bias else None
+        srcs = [Feat.from_nchw(x) for x in xs]
+        out = Feat.empty(N, H, W, Cout)
+        offs, ktot = ops.k_offsets(srcs)
+        wf = torch.zeros(9, out.Cp, ktot, dtype=torch.bfloat16, device=dev)
+        ops.pack_conv_weight(w, src_C, offs, wf, [None] * len(srcs))
+        bp = None
+        if bias:
+            bp = torch.zeros(out.Cp, device=dev)
+            bp[:Cout] = b
+        ssum = ssq = None
+        if stats:
+            ssum = torch.zeros(N, out.Cp, device=dev)
+            ssq = torch.zeros(N, out.Cp, device=dev)
+        op = ops.conv3x3_fwd_op(srcs, wf, out, bias=bp, stat_sum=ssum, stat_sq=ssq)
+        op.launch()
+        torch.cuda.synchronize()
+        ref = F.conv2d(torch.cat(xs, 1), w, b, padding=1)
+        report(name, out.to_nchw(), ref)
+        if out.Cp > Cout:
+            report(name + " [pad lanes zero]", out.t[..., Cout:].float(), torch.zeros_like(out.t[..., Cout:]).float(), tol=1e-6)
+        if stats:
+            report(name + " [sum]", ssum[:, :Cout], ref.sum((2, 3)), tol=1e-2)
+            report(name + " [sumsq]", ssq[:, :Cout], (ref * ref).sum((2, 3)), tol=1e-2)
+
+    run_case(fn, name)
+
+
+def conv_dgrad_case(N, H, W, Cin, Cout, accumulate):
+    name = f"conv3x3_dgrad N{N} {H}x{W} {Cin}<-{Cout} acc={accumulate}"
+
+    def fn():
+        w = rnd(Cout, Cin, 3, 3, scale=0.1)
+        dy = rnd(N, Cout, H, W)
+        dyf = Feat.from_nchw(dy)
+        dx = Feat.empty(N, H, W, Cin)
+        base = rnd(N, Cin, H, W)
+        if accumulate:
+            dx = Feat.from_nchw(base)
+        wd = torch.zeros(9, dx.Cp, dyf.Cp, dtype=torch.bfloat16, device=dev)
+        wf = torch.zeros(9, dyf.Cp, dx.Cp, dtype=torch.bfloat16, device=dev)
+        ops.pack_conv_weight(w, [Cin], [0], wf, [wd])
+        op = ops.conv3x3_dgrad_op(dyf, wd, dx, accumulate)
+        op.launch()
+        torch.cuda.synchronize()
+        ref = F.conv_transpose2d(dy, w, padding=1)
+        if accumulate:
+            ref = ref + base
+        report(name, dx.to_nchw(), ref)
+
+    run_case(fn, name)
+
+
+def conv_wgrad_case(N, H, W, Cin, Cout, splits=0):
+    name = f"conv3x3_wgrad N{N} {H}x{W} {Cin}->{Cout} splits={splits}"
+
+    def fn():
+        x = rnd(N, Cin, H, W)
+        dy = rnd(N, Cout, H, W)
+        xf, dyf = Feat.from_nchw(x), Feat.from_nchw(dy)
+        acc = torch.zeros(9, dyf.Cp, xf.Cp, device=dev)
+        op = ops.conv3x3_wgrad_op(xf, dyf, acc, 0, splits=splits)
+        op.launch()
+        torch.cuda.synchronize()
+        grad = torch.zeros(Cout, Cin, 3, 3, device=dev)
+        _lib.call("mtbc_unpack_conv_wgrad", ops.ptr(acc), acc.shape[1], acc.shape[2], 0, ops.ptr(grad), Cout, Cin, 3, 0,
+                  Cin, 0, None)
+        torch.cuda.synchronize()
+        ref = torch.nn.grad.conv2d_weight(x, (Cout, Cin, 3, 3), dy, padding=1)
+        report(name, grad, ref)
+
+    run_case(fn, name)
+
+
+def convT_case(N, H, W, Cin, Cout, k=2):
+    name = f"convT k{k} N{N} {H}x{W} {Cin}->{Cout}"
+
+    def fn():
+        x = rnd(N, Cin, H, W)
+        w = rnd(Cin, Cout, k, k, scale=0.1)
+        b = rnd(Cout)
+        xf = Feat.from_nchw(x)
+        out = Feat.empty(N, H * k, W * k, Cout)
+        wf = torch.zeros(1, k * k * out.Cp, xf.Cp, dtype=torch.bfloat16, device=dev)
+        wd = torch.zeros(k * k, xf.Cp, out.Cp, dtype=torch.bfloat16, device=dev)
+        ops.pack_convT_weight(w, out.Cp, wf, wd)
+        bp = torch.zeros(out.Cp, device=dev)
+        bp[:Cout] = b
+        ops.convT_fwd_op(xf, wf, out, k, bp).launch()
+        torch.cuda.synchronize()
+        ref = F.conv_transpose2d(x, w, b, stride=k)
+        report(name + " fwd", out.to_nchw(), ref)
+        # dgrad
+        dout = rnd(N, Cout, H * k, W * k)
+        df = Feat.from_nchw(dout)
+        dx = Feat.empty(N, H, W, Cin)
+        ops.convT_dgrad_op(df, wd, dx, k, False).launch()
+        torch.cuda.synchronize()
+        refdx = F.conv2d(dout, w, stride=k)
+        report(name + " dgrad", dx.to_nchw(), refdx)
+        # wgrad
+        acc = torch.zeros(k * k, out.Cp, xf.Cp, device=dev)
+        ops.convT_wgrad_op(xf, df, acc, k).launch()
+        grad = torch.zeros(Cin, Cout, k, k, device=dev)
+        _lib.call("mtbc_unpack_convT_wgrad", ops.ptr(acc), acc.shape[0] * acc.shape[1], acc.shape[2], ops.ptr(grad), Cin,
+                  Cout, k, 0, None)
+        torch.cuda.synchronize()
+        xr = x.clone().requires_grad_(False)
+        wr = w.clone().requires_grad_(True)
+        F.conv_transpose2d(xr, wr, None, stride=k).backward(dout)
+        report(name + " wgrad", grad, wr.grad)
+
+    run_case(fn, name)
+
+
+def first_conv_case(N, H, W, Cout):
+    name = f"conv_first N{N} {H}x{W} 1->{Cout}"
+
+    def fn():
+        x = torch.randint(0, 256, (N, 1, H, W), device=dev).float()
+        w = rnd(Cout, 1, 3, 3, scale=0.1)
+        b = rnd(Cout)
+        out = Feat.empty(N, H, W, Cout)
+        ssum = torch.zeros(N, out.Cp, device=dev)
+        ssq = torch.zeros(N, out.Cp, device=dev)
+        _lib.call("mtbc_conv_first_fwd", ops.ptr(x), N, 1, H, W, ops.ptr(w), ops.ptr(b), Cout, ops.ptr(out.t), out.Cp,
+                  ops.ptr(ssum), ops.ptr(ssq), None)
+        torch.cuda.synchronize()
+        ref = F.conv2d(x, w, b, padding=1)
+        report(name + " fwd", out.to_nchw(), ref)
+        report(name + " sum", ssum[:, :Cout], ref.sum((2, 3)), tol=1e-3)
+        report(name + " sumsq", ssq[:, :Cout], (ref * ref).sum((2, 3)), tol=1e-3)
+        dy = rnd(N, Cout, H, W)
+        dyf = Feat.from_nchw(dy)
+        dw = torch.zeros(Cout, 1, 3, 3, device=dev)
+        _lib.call("mtbc_conv_first_wgrad", ops.ptr(x), N, 1, H, W, ops.ptr(dyf.t), dyf.Cp, Cout, ops.ptr(dw), None)
+        torch.cuda.synchronize()
+        refw = torch.nn.grad.conv2d_weight(x, (Cout, 1, 3, 3), dy, padding=1)
+        report(name + " wgrad", dw, refw)
+
+    run_case(fn, name)
+
+
+def norm_case(N, H, W, C, affine, pool, slope=0.1):
+    name = f"in_lrelu N{N} {H}x{W} C{C} affine={affine} pool={pool}"
+
+    def fn():
+        y = rnd(N, C, H, W, scale=3.0) + 1.5
+        y = y.to(torch.bfloat16).float()
+        yf = Feat.from_nchw(y)
+        Cp = yf.Cp
+        g = b = gp = bp = None
+        if affine:
+            g = torch.rand(C, device=dev) + 0.5
+            b = torch.randn(C, device=dev) * 0.3
+            gp = torch.zeros(Cp, device=dev); gp[:C] = g
+            bp = torch.zeros(Cp, device=dev); bp[:C] = b
+        ssum = torch.zeros(N, Cp, device=dev); ssq = torch.zeros(N, Cp, device=dev)
+        _lib.call("mtbc_in_stats", ops.ptr(yf.t), N, H * W, Cp, ops.ptr(ssum), ops.ptr(ssq), None)
+        a = Feat.empty(N, H, W, C)
+        pooled = Feat.empty(N, H // 2, W // 2, C) if pool else None
+        mean = torch.zeros(N, Cp, device=dev); rstd = torch.zeros(N, Cp, device=dev)
+        _lib.call("mtbc_in_apply", ops.ptr(yf.t), N, H, W, Cp, ops.ptr(ssum), ops.ptr(ssq), ops.ptr(gp), ops.ptr(bp), C,
+                  1e-5, slope, ops.ptr(a.t), None if pooled is None else ops.ptr(pooled.t), ops.ptr(mean), ops.ptr(rstd),
+                  None)
+        torch.cuda.synchronize()
+        yr = y.clone().requires_grad_(True)
+        ref = F.leaky_relu(F.instance_norm(yr, weight=g, bias=b, eps=1e-5), slope)
+        report(name + " fwd", a.to_nchw(), ref.detach())
+        if pool:
+            report(name + " pooled", pooled.to_nchw(), F.max_pool2d(a.to_nchw(), 2))
+        # backward
+        dA = rnd(N, C, H, W)
+        ref.backward(dA)
+        dAf = Feat.from_nchw(dA)
+        s1 = torch.zeros(N, Cp, device=dev); s2 = torch.zeros(N, Cp, device=dev)
+        _lib.call("mtbc_in_bwd_reduce", ops.ptr(dAf.t), ops.ptr(yf.t), N, H * W, Cp, ops.ptr(mean), ops.ptr(rstd),
+                  ops.ptr(gp), ops.ptr(bp), slope, ops.ptr(s1), ops.ptr(s2), None)
+        dy = Feat.empty(N, H, W, C)
+        dg = torch.zeros(C, device=dev) if affine else None
+        db = torch.zeros(C, device=dev) if affine else None
+        _lib.call("mtbc_in_bwd_apply", ops.ptr(dAf.t), ops.ptr(yf.t), N, H * W, Cp, ops.ptr(mean), ops.ptr(rstd),
+                  ops.ptr(gp), ops.ptr(bp), slope, ops.ptr(s1), ops.ptr(s2), ops.ptr(dy.t), ops.ptr(dg), ops.ptr(db), C,
+                  None)
+        torch.cuda.synchronize()
+        report(name + " bwd dy", dy.to_nchw(), yr.grad, tol=3e-2)
+        if affine:
+            # reference affine grads
+            yr2 = y.clone()
+            gg = g.clone().requires_grad_(True); bb = b.clone().requires_grad_(True)
+            F.leaky_relu(F.instance_norm(yr2, weight=gg, bias=bb, eps=1e-5), slope).backward(dA)
+            report(name + " dgamma", dg, gg.grad, tol=2e-2)
+            report(name + " dbeta", db, bb.grad, tol=2e-2)
+        if pool:
+            dP = rnd(N, C, H // 2, W // 2)
+            ar = a.to_nchw().requires_grad_(True)
+            F.max_pool2d(ar, 2).backward(dP)
+            dPf = Feat.from_nchw(dP)
+            dA2 = Feat.empty(N, H, W, C)
+            _lib.call("mtbc_maxpool2_bwd", ops.ptr(a.t), ops.ptr(dPf.t), N, H, W, Cp, ops.ptr(dA2.t), 0, None)
+            torch.cuda.synchronize()
+            report(name + " pool bwd", dA2.to_nchw(), ar.grad)
+
+    run_case(fn, name)
+
+
+GROUPS = ["fwd_identity", "fwd", "dgrad", "wgrad", "convT", "first", "norm"]
+
+
+def run_group(group):
+    lib = _lib.load()
+    _lib.check(lib.mtbc_device_check(), "device_check")
+    torch.manual_seed(0)
+    if group == "fwd_identity":
+        conv_fwd_case(2, 16, 16, [64], 64, bias=False, stats=False, identity=True)
+        conv_fwd_case(2, 16, 16, [32], 32, bias=False, stats=False, identity=True)
+    elif group == "fwd":
+        fwd_cases()
+    elif group == "dgrad":
+        dgrad_cases()
+    elif group == "wgrad":
+        wgrad_cases()
+    elif group == "convT":
+        convT_cases()
+    elif group == "first":
+        first_conv_case(2, 32, 32, 24)
+        first_conv_case(2, 32, 32, 32)
+    elif group == "norm":
+        norm_case(2, 32, 32, 24, True, True)
+        norm_case(2, 16, 16, 96, True, False)
+        norm_case(2, 16, 16, 320, False, True, slope=0.01)
+        norm_case(3, 8, 8, 512, False, False, slope=0.01)
+    bad = [r for r in RESULTS if not r[1]]
+    print(f"==== group {group}: {len(RESULTS) - len(bad)}/{len(RESULTS)} OK", flush=True)
+    return 1 if bad else 0
+
+
+def main():
+    import subprocess
+    if len(sys.argv) > 2 and sys.argv[1] == "--group":
+        return run_group(sys.argv[2])
+    groups = sys.argv[1:] or GROUPS
+    rc = 0
+    for g in groups:
+        print(f"\n######## group {g}", flush=True)
+        try:
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--group", g], timeout=300)
+            if p.returncode != 0:
+                rc = 1
+                print(f"group {g} exit code {p.returncode}", flush=True)
+        except subprocess.TimeoutExpired:
+            rc = 1
+            print(f"group {g} TIMED OUT", flush=True)
+    return rc
+
+
+def fwd_cases():
+    conv_fwd_case(2, 16, 16, [64], 64, bias=False, stats=False)
+    conv_fwd_case(2, 16, 16, [32], 32, bias=False, stats=False)
+    conv_fwd_case(2, 32, 32, [24, 24, 48], 24)
+    conv_fwd_case(2, 32, 32, [48, 48, 48], 48)
+    conv_fwd_case(2, 16, 16, [96, 96], 96)
+    conv_fwd_case(3, 16, 16, [128], 512, stats=True)
+    conv_fwd_case(2, 16, 16, [384, 384, 384], 512)
+    conv_fwd_case(4, 8, 8, [320], 320, stats=False)
+    conv_fwd_case(9, 4, 4, [64], 64, stats=False)
+    conv_fwd_case(2, 64, 64, [24, 24, 24, 24, 48], 24)
+
+
+def dgrad_cases():
+    conv_dgrad_case(2, 16, 16, 64, 64, False)
+    conv_dgrad_case(2, 32, 32, 24, 48, True)
+    conv_dgrad_case(2, 16, 16, 192, 96, False)
+
+
+def wgrad_cases():
+    conv_wgrad_case(2, 16, 16, 64, 64)
+    conv_wgrad_case(2, 16, 16, 32, 32)
+    conv_wgrad_case(2, 32, 32, 24, 24)
+    conv_wgrad_case(2, 32, 32, 48, 24)
+    conv_wgrad_case(2, 16, 16, 192, 96)
+    conv_wgrad_case(2, 16, 16, 128, 256)
+    conv_wgrad_case(2, 16, 16, 384, 512)
+    conv_wgrad_case(4, 8, 8, 320, 320)
+    conv_wgrad_case(2, 64, 64, 24, 24, splits=7)
+
+
+def convT_cases():
+    convT_case(2, 16, 16, 64, 32)
+    convT_case(2, 16, 16, 48, 48)
+    convT_case(2, 8, 8, 384, 192)
+    convT_case(4, 8, 8, 320, 320)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
