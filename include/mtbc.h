@@ -256,6 +256,7 @@ int mtbc_increment_i32(int32_t* p, void* stream);
 /* Utilities. */
 int mtbc_fill_f32(float* p, int64_t n, float v, void* stream);
 int mtbc_zero_bytes(void* p, int64_t nbytes, void* stream);
+int mtbc_copy_f32(float* dst, const float* src, int64_t n, void* stream);
 int mtbc_f32_to_bf16_nhwc(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, void* y, int32_t Cp,
                           void* stream);
 int mtbc_bf16_nhwc_to_f32(const void* x, int32_t N, int32_t C, int32_t H, int32_t W, int32_t Cp, float* y,

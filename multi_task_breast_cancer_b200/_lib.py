@@ -97,6 +97,7 @@ _SIGS = {
     "mtbc_increment_i32": [c_vp, c_vp],
     "mtbc_fill_f32": [c_vp, c_i64, c_f32, c_vp],
     "mtbc_zero_bytes": [c_vp, c_i64, c_vp],
+    "mtbc_copy_f32": [c_vp, c_vp, c_i64, c_vp],
     "mtbc_f32_to_bf16_nhwc": [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp],
     "mtbc_bf16_nhwc_to_f32": [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp],
 }

@@ -305,6 +305,13 @@ int mtbc_zero_bytes(void* p, int64_t nbytes, void* stream) {
   if (e != cudaSuccess) return set_error(MTBC_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
   return 0;
 }
+int mtbc_copy_f32(float* dst, const float* src, int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  cudaError_t e = cudaMemcpyAsync(dst, src, static_cast<size_t>(n) * sizeof(float), cudaMemcpyDeviceToDevice,
+                                  static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return set_error(MTBC_ERR_CUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(e));
+  return 0;
+}
 int mtbc_f32_to_bf16_nhwc(const float* x, int32_t N, int32_t C, int32_t H, int32_t W, void* y, int32_t Cp,
                           void* stream) {
   const int64_t total = static_cast<int64_t>(N) * H * W * Cp;

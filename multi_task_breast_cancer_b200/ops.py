@@ -26,8 +26,17 @@ def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class _TensorPtr(C.c_void_p):
+    """c_void_p that keeps its tensor alive: bound launch closures hold raw device pointers, so the pointer object
+    itself must own a reference or the caching allocator may hand the memory to someone else."""
+
+
 def ptr(t: Optional[torch.Tensor]):
-    return None if t is None else C.c_void_p(t.data_ptr())
+    if t is None:
+        return None
+    p = _TensorPtr(t.data_ptr())
+    p._keep = t
+    return p
 
 
 @dataclass

@@ -1,0 +1,529 @@
+"""Static execution plan for one (architecture, batch, H, W): every activation / gradient buffer is allocated once,
+every tensor-core op has its TMA descriptors encoded once, and forward / backward are flat lists of C-ABI launches on
+the current CUDA stream (capturable in a CUDA graph).  No autograd, no ATen kernels on the hot path.
+
+Reverse-mode bookkeeping is explicit: each plan tensor owns an optional gradient buffer; the first backward
+contribution stores, later ones accumulate inside the producing kernel's epilogue (dense nested skips of U-Net++:
+x_0_0 feeds five consumers, MTUNetPlusPlus.py:101-118).  Shared modules applied twice (process_level_3,
+MTUNetPlusPlus.py:128; upsample5, MTnnUNet.py:160,174) accumulate into one weight-gradient buffer.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib, ops
+from .ops import Feat, pad32, ptr
+
+EPS = 1e-5
+
+
+class PTensor:
+    """A bf16 NHWC activation of the plan plus its (lazily allocated) gradient."""
+
+    def __init__(self, feat: Feat, name: str):
+        self.feat = feat
+        self.name = name
+        self.g: Optional[Feat] = None
+        self.g_init = False  # set during backward emission once some consumer has written the gradient
+
+    def grad(self) -> Feat:
+        if self.g is None:
+            self.g = Feat.empty(self.feat.N, self.feat.H, self.feat.W, self.feat.C, device=self.feat.t.device)
+        return self.g
+
+
+class Arena:
+    """fp32 scratch that must be zero at the start of a phase: carved from a few big chunks -> few memsets."""
+
+    def __init__(self, device, chunk_floats=1 << 24):
+        self.device, self.chunk_floats = device, chunk_floats
+        self.chunks: List[torch.Tensor] = []
+        self.used = 0
+
+    def alloc(self, *shape) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= s
+        n_al = (n + 63) // 64 * 64
+        if not self.chunks or self.used + n_al > self.chunks[-1].numel():
+            self.chunks.append(torch.zeros(max(self.chunk_floats, n_al), dtype=torch.float32, device=self.device))
+            self.used = 0
+        v = self.chunks[-1][self.used:self.used + n].view(*shape)
+        self.used += n_al
+        return v
+
+    def zero_launches(self) -> List[Callable]:
+        out = []
+        for i, c in enumerate(self.chunks):
+            nbytes = (self.used if i == len(self.chunks) - 1 else c.numel()) * 4
+            if nbytes:
+                out.append(_mk("mtbc_zero_bytes", ptr(c), nbytes))
+        return out
+
+
+def _mk(name: str, *args) -> Callable[[C.c_void_p], None]:
+    """Bind a C-ABI call; the stream is supplied at launch time."""
+    fn = getattr(_lib.load(), name)
+
+    def launch(stream):
+        rc = fn(*args, stream)
+        if rc != 0:
+            _lib.check(rc, name)
+    launch.kind = name
+    return launch
+
+
+def _mk_op(op: ops.Op) -> Callable:
+    lib = _lib.load()
+    h = op.handle
+
+    def launch(stream):
+        rc = lib.mtbc_op_launch(h, stream)
+        if rc != 0:
+            _lib.check(rc, op.kind)
+    launch.kind = op.kind
+    launch.op = op
+    return launch
+
+
+class Plan:
+    """Builder + executor.  Model files call the layer methods in forward order; `finalize()` emits the backward."""
+
+    def __init__(self, B: int, H: int, W: int, device, params: Dict[str, torch.nn.Parameter], training: bool = True):
+        self.B, self.H, self.W, self.device = B, H, W, device
+        self.params = params
+        self.training = training
+        self.pack: List[Callable] = []
+        self.fwd: List[Callable] = []
+        self._bwd_blocks: List[List[Callable]] = []  # one block per forward op, reversed at finalize
+        self.bwd: List[Callable] = []
+        self.fwd_arena = Arena(device, 1 << 20)   # InstanceNorm statistics (zeroed every forward)
+        self.bwd_arena = Arena(device, 1 << 24)   # s1/s2, weight-gradient accumulators (zeroed every backward)
+        self._keep: List[object] = []
+        self._scratch: Dict[Tuple, Feat] = {}
+        self.tc_flops_fwd = 0.0
+        self.tc_flops_bwd = 0.0
+        # outputs (fp32, plan-owned static buffers) and their incoming gradients
+        self.outputs_cls: List[torch.Tensor] = []
+        self.outputs_seg: List[torch.Tensor] = []
+        self.g_cls: List[torch.Tensor] = []
+        self.g_seg: List[Optional[torch.Tensor]] = []
+        # flat parameter gradients (param-shaped views); registration order reversed ~ backward completion order
+        names = list(params.keys())
+        total = sum((params[n].numel() + 63) // 64 * 64 for n in names)
+        self.grad_flat = torch.zeros(total, dtype=torch.float32, device=device)
+        self.grad_view: Dict[str, torch.Tensor] = {}
+        self.grad_range: Dict[str, Tuple[int, int]] = {}
+        off = 0
+        for n in reversed(names):
+            p = params[n]
+            self.grad_view[n] = self.grad_flat[off:off + p.numel()].view_as(p)
+            self.grad_range[n] = (off, off + p.numel())
+            off += (p.numel() + 63) // 64 * 64
+        self.has_grad: Dict[str, bool] = {n: False for n in names}
+        # deferred conv weight-gradient unpacks: param name -> (pending applications, launches)
+        self._wg_pending: Dict[str, int] = {}
+        self._wg_acc: Dict[str, torch.Tensor] = {}
+        self._wg_unpack: Dict[str, List[Callable]] = {}
+        self._packed: Dict[str, dict] = {}
+        self.finalized = False
+        self.tensors: Dict[str, PTensor] = {}  # name -> activation (debug / tests)
+        self.debug: Dict[str, Feat] = {}
+        self.param_done_at: Dict[str, int] = {}  # index into self.bwd after which the param's grad is final
+
+    # ------------------------------------------------------------------------------------------------ helpers
+    def P(self, name: str) -> torch.nn.Parameter:
+        return self.params[name]
+
+    def new(self, N, H, W, Cc, name) -> PTensor:
+        t = PTensor(Feat.empty(N, H, W, Cc, device=self.device), name)
+        self.tensors[name] = t
+        return t
+
+    def scratch(self, N, H, W, Cc) -> Feat:
+        key = (N, H, W, pad32(Cc))
+        if os.environ.get("MTBC_DEBUG_UNIQUE_SCRATCH"):
+            key = key + (len(self._scratch),)
+        if key not in self._scratch:
+            self._scratch[key] = Feat.empty(N, H, W, Cc, device=self.device)
+        f = self._scratch[key]
+        return Feat(f.t, Cc)
+
+    def _padded_vec(self, name: Optional[str], Cp: int) -> Optional[torch.Tensor]:
+        """fp32 [Cp] copy target for a per-channel parameter (bias / gamma / beta); refreshed in the pack phase."""
+        if name is None:
+            return None
+        p = self.P(name)
+        buf = torch.zeros(Cp, dtype=torch.float32, device=self.device)
+        n = p.numel()
+        self.pack.append(_mk_copy_f32(buf, p, n))
+        self._keep.append(buf)
+        return buf
+
+    def _mark_grad(self, *names):
+        for n in names:
+            if n is not None:
+                self.has_grad[n] = True
+
+    # ------------------------------------------------------------------------------------------------ layers
+    def input_conv_in_act(self, x_in: torch.Tensor, w: str, b: Optional[str], gamma: Optional[str],
+                          beta: Optional[str], slope: float, pool: bool, name: str):
+        """First layer: Conv2d(Cin<=4 -> C, 3x3) on the fp32 NCHW image + InstanceNorm + LeakyReLU (+pool)."""
+        Wt = self.P(w)
+        Cout, Cin = Wt.shape[0], Wt.shape[1]
+        N, H, Wd = self.B, self.H, self.W
+        y = self.new(N, H, Wd, Cout, name + ".y")
+        ssum = self.fwd_arena.alloc(N, y.feat.Cp)
+        ssq = self.fwd_arena.alloc(N, y.feat.Cp)
+        bvec = None if b is None else self.P(b)
+        self.fwd.append(_mk("mtbc_conv_first_fwd", ptr(x_in), N, Cin, H, Wd, ptr(Wt), ptr(bvec), Cout, ptr(y.feat.t),
+                            y.feat.Cp, ptr(ssum), ptr(ssq)))
+        a, p, aux = self._norm_act(y, ssum, ssq, gamma, beta, slope, pool, name)
+
+        def backward():
+            blk: List[Callable] = []
+            dy = self._norm_act_bwd(blk, y, a, p, aux, gamma, beta, slope)
+            if dy is None:
+                return blk
+            blk.append(_mk("mtbc_conv_first_wgrad", ptr(x_in), N, Cin, H, Wd, ptr(dy.t), dy.Cp, Cout,
+                           ptr(self.grad_view[w])))
+            self._mark_grad(w, b)  # bias grad of a conv followed by InstanceNorm is identically zero
+            return blk
+        self._bwd_blocks.append(backward)
+        return a, p
+
+    def conv_in_act(self, srcs: Sequence[PTensor], w: str, b: Optional[str], gamma: Optional[str], beta: Optional[str],
+                    slope: float, pool: bool, name: str):
+        """Conv2d 3x3 over the (virtual) channel concatenation of `srcs` + InstanceNorm + LeakyReLU (+ 2x2 max-pool).
+        MTnnUNet.py:19-39 / MONAI Convolution; the concat (MTUNetPlusPlus.py:107-118) is folded into the K loop."""
+        Wt = self.P(w)
+        Cout, Cin = Wt.shape[0], Wt.shape[1]
+        feats = [s.feat for s in srcs]
+        assert sum(f.C for f in feats) == Cin, (name, [f.C for f in feats], Cin)
+        N, H, Wd = feats[0].N, feats[0].H, feats[0].W
+        y = self.new(N, H, Wd, Cout, name + ".y")
+        Cp = y.feat.Cp
+        pk = self._pack_conv(w, feats, Cp)
+        ssum = self.fwd_arena.alloc(N, Cp)
+        ssq = self.fwd_arena.alloc(N, Cp)
+        fused = H * Wd >= 128
+        bias = self._padded_vec(b, Cp)
+        op = ops.conv3x3_fwd_op(feats, pk["wf"], y.feat, bias=bias, stat_sum=ssum if fused else None,
+                                stat_sq=ssq if fused else None)
+        self.tc_flops_fwd += op.flops
+        self.fwd.append(_mk_op(op))
+        if not fused:
+            self.fwd.append(_mk("mtbc_in_stats", ptr(y.feat.t), N, H * Wd, Cp, ptr(ssum), ptr(ssq)))
+        a, p, aux = self._norm_act(y, ssum, ssq, gamma, beta, slope, pool, name)
+        self._wg_pending[w] = self._wg_pending.get(w, 0) + 1
+
+        def backward():
+            blk: List[Callable] = []
+            dy = self._norm_act_bwd(blk, y, a, p, aux, gamma, beta, slope)
+            self._wg_pending[w] -= 1
+            if dy is None:
+                return blk
+            acc = self._wg_accum(w, pk)
+            for f, off in zip(feats, pk["offs"]):
+                o = ops.conv3x3_wgrad_op(f, dy, acc, off)
+                self.tc_flops_bwd += o.flops
+                blk.append(_mk_op(o))
+            self._mark_grad(w, b)
+            if self._wg_pending[w] == 0:
+                blk.extend(self._wg_unpack.pop(w))
+            for s, wd in zip(srcs, pk["wd"]):
+                g = s.grad()
+                o = ops.conv3x3_dgrad_op(dy, wd, g, accumulate=s.g_init)
+                self.tc_flops_bwd += o.flops
+                blk.append(_mk_op(o))
+                s.g_init = True
+            return blk
+        self._bwd_blocks.append(backward)
+        return a, p
+
+    def _pack_conv(self, w: str, feats: Sequence[Feat], Cp: int) -> dict:
+        """bf16 forward / data-gradient operands of a conv weight (shared modules are packed once per step)."""
+        key = w
+        if key in self._packed:
+            pk = self._packed[key]
+            assert [f.Cp for f in feats] == pk["src_cp"]
+            return pk
+        Wt = self.P(w)
+        offs, ktot = ops.k_offsets(feats)
+        wf = torch.zeros(9, Cp, ktot, dtype=torch.bfloat16, device=self.device)
+        wds = [torch.zeros(9, f.Cp, Cp, dtype=torch.bfloat16, device=self.device) if self.training else None
+               for f in feats]
+        st_c = [f.C for f in feats]
+        c0 = 0
+        for cs, off, wd in zip(st_c, offs, wds):
+            self.pack.append(_mk("mtbc_pack_conv_weight", ptr(Wt), Wt.shape[0], Wt.shape[1], 3, c0, cs, ptr(wf),
+                                 wf.shape[1], wf.shape[2], off, ptr(wd), 0 if wd is None else wd.shape[1],
+                                 0 if wd is None else wd.shape[2]))
+            c0 += cs
+        pk = {"wf": wf, "wd": wds, "offs": offs, "ktot": ktot, "src_cp": [f.Cp for f in feats], "src_c": st_c}
+        self._packed[key] = pk
+        return pk
+
+    def _wg_accum(self, w: str, pk: dict) -> torch.Tensor:
+        if w not in self._wg_acc:
+            Wt = self.P(w)
+            acc = self.bwd_arena.alloc(*pk["wf"].shape)
+            self._wg_acc[w] = acc
+            launches = []
+            c0 = 0
+            for cs, off in zip(pk["src_c"], pk["offs"]):
+                launches.append(_mk("mtbc_unpack_conv_wgrad", ptr(acc), acc.shape[1], acc.shape[2], off,
+                                    ptr(self.grad_view[w]), Wt.shape[0], Wt.shape[1], 3, c0, cs, 0))
+                c0 += cs
+            self._wg_unpack[w] = launches
+        return self._wg_acc[w]
+
+    def _norm_act(self, y: PTensor, ssum, ssq, gamma, beta, slope, pool, name):
+        N, H, Wd, Cp, Cc = y.feat.N, y.feat.H, y.feat.W, y.feat.Cp, y.feat.C
+        a = self.new(N, H, Wd, Cc, name)
+        p = self.new(N, H // 2, Wd // 2, Cc, name + ".pool") if pool else None
+        mean = torch.zeros(N, Cp, dtype=torch.float32, device=self.device)
+        rstd = torch.zeros(N, Cp, dtype=torch.float32, device=self.device)
+        gv = self._padded_vec(gamma, Cp)
+        bv = self._padded_vec(beta, Cp)
+        self.fwd.append(_mk("mtbc_in_apply", ptr(y.feat.t), N, H, Wd, Cp, ptr(ssum), ptr(ssq), ptr(gv), ptr(bv), Cc,
+                            C.c_float(EPS), C.c_float(slope), ptr(a.feat.t), None if p is None else ptr(p.feat.t),
+                            ptr(mean), ptr(rstd)))
+        return a, p, (mean, rstd, gv, bv)
+
+    def _norm_act_bwd(self, blk, y: PTensor, a: PTensor, p: Optional[PTensor], aux, gamma, beta, slope):
+        """Emit pool / InstanceNorm / LeakyReLU backward; returns dy (gradient of the raw conv output) or None."""
+        mean, rstd, gv, bv = aux
+        N, H, Wd, Cp, Cc = y.feat.N, y.feat.H, y.feat.W, y.feat.Cp, y.feat.C
+        if p is not None and p.g_init:
+            g = a.grad()
+            blk.append(_mk("mtbc_maxpool2_bwd", ptr(a.feat.t), ptr(p.g.t), N, H, Wd, Cp, ptr(g.t), int(a.g_init)))
+            a.g_init = True
+        if not a.g_init:
+            return None
+        s1 = self.bwd_arena.alloc(N, Cp)
+        s2 = self.bwd_arena.alloc(N, Cp)
+        blk.append(_mk("mtbc_in_bwd_reduce", ptr(a.g.t), ptr(y.feat.t), N, H * Wd, Cp, ptr(mean), ptr(rstd), ptr(gv),
+                       ptr(bv), C.c_float(slope), ptr(s1), ptr(s2)))
+        dy = self.scratch(N, H, Wd, Cc)
+        self.debug[a.name + ".dy"] = dy
+        self.debug[a.name + ".aux"] = (mean, rstd, gv, bv, s1, s2)
+        dg = self.grad_view[gamma] if gamma else None
+        db = self.grad_view[beta] if beta else None
+        blk.append(_mk("mtbc_in_bwd_apply", ptr(a.g.t), ptr(y.feat.t), N, H * Wd, Cp, ptr(mean), ptr(rstd), ptr(gv),
+                       ptr(bv), C.c_float(slope), ptr(s1), ptr(s2), ptr(dy.t), ptr(dg), ptr(db), Cc))
+        self._mark_grad(gamma, beta)
+        return dy
+
+    def convT(self, x: PTensor, w: str, b: Optional[str], k: int, name: str) -> PTensor:
+        """ConvTranspose2d(kernel = stride = k) as one GEMM with a pixel-shuffle epilogue (MTnnUNet.py:96-100)."""
+        Wt = self.P(w)
+        Cin, Cout = Wt.shape[0], Wt.shape[1]
+        f = x.feat
+        assert f.C == Cin
+        out = self.new(f.N, f.H * k, f.W * k, Cout, name)
+        cp = out.feat.Cp
+        wf = torch.zeros(1, k * k * cp, f.Cp, dtype=torch.bfloat16, device=self.device)
+        wd = torch.zeros(k * k, f.Cp, cp, dtype=torch.bfloat16, device=self.device) if self.training else None
+        self.pack.append(_mk("mtbc_pack_convT_weight", ptr(Wt), Cin, Cout, k, cp, ptr(wf), wf.shape[2], ptr(wd),
+                             0 if wd is None else wd.shape[1], 0 if wd is None else wd.shape[2]))
+        bias = self._padded_vec(b, cp)
+        op = ops.convT_fwd_op(f, wf, out.feat, k, bias)
+        self.tc_flops_fwd += op.flops
+        self.fwd.append(_mk_op(op))
+
+        def backward():
+            blk: List[Callable] = []
+            if not out.g_init:
+                return blk
+            acc = self.bwd_arena.alloc(k * k, cp, f.Cp)
+            o = ops.convT_wgrad_op(f, out.g, acc, k)
+            self.tc_flops_bwd += o.flops
+            blk.append(_mk_op(o))
+            blk.append(_mk("mtbc_unpack_convT_wgrad", ptr(acc), k * k * cp, f.Cp, ptr(self.grad_view[w]), Cin, Cout, k,
+                           0))
+            if b is not None:
+                blk.append(_mk("mtbc_channel_sum", ptr(out.g.t), out.g.N * out.g.H * out.g.W, cp, Cout,
+                               ptr(self.grad_view[b]), 1))
+            self._mark_grad(w, b)
+            g = x.grad()
+            o = ops.convT_dgrad_op(out.g, wd, g, k, accumulate=x.g_init)
+            self.tc_flops_bwd += o.flops
+            blk.append(_mk_op(o))
+            x.g_init = True
+            return blk
+        self._bwd_blocks.append(backward)
+        return out
+
+    def upsample2(self, x: PTensor, name: str) -> PTensor:
+        """nn.Upsample(scale_factor=2, mode='nearest') (Multi_BTS_UNet.py:100)."""
+        f = x.feat
+        out = self.new(f.N, f.H * 2, f.W * 2, f.C, name)
+        self.fwd.append(_mk("mtbc_upsample2_fwd", ptr(f.t), f.N, f.H, f.W, f.Cp, ptr(out.feat.t)))
+
+        def backward():
+            if not out.g_init:
+                return []
+            g = x.grad()
+            blk = [_mk("mtbc_upsample2_bwd", ptr(out.g.t), f.N, f.H, f.W, f.Cp, ptr(g.t), int(x.g_init))]
+            x.g_init = True
+            return blk
+        self._bwd_blocks.append(backward)
+        return out
+
+    def head1x1(self, a: PTensor, w: str, b: str, active: bool = True) -> Optional[torch.Tensor]:
+        """Conv2d 1x1 C -> 1 mask head (MTnnUNet.py:6-9; MTUNetPlusPlus.py:73-76,120-123) -> fp32 logits (B,1,H,W)."""
+        if not active:
+            return None
+        f = a.feat
+        assert self.P(w).shape[0] == 1, "mask heads project to a single region"
+        logits = torch.zeros(f.N, 1, f.H, f.W, dtype=torch.float32, device=self.device)
+        dlog = torch.zeros_like(logits)
+        npix = f.N * f.H * f.W
+        self.fwd.append(_mk("mtbc_head1x1_fwd", ptr(f.t), npix, f.Cp, f.C, ptr(self.P(w)), ptr(self.P(b)), ptr(logits)))
+        idx = len(self.outputs_seg)
+        self.outputs_seg.append(logits)
+        self.g_seg.append(dlog)
+
+        def backward():
+            if not self.seg_grad_active[idx]:
+                return []
+            g = a.grad()
+            blk = [_mk("mtbc_head1x1_bwd", ptr(f.t), ptr(dlog), npix, f.Cp, f.C, ptr(self.P(w)), ptr(g.t),
+                       int(a.g_init), ptr(self.grad_view[w]), ptr(self.grad_view[b]))]
+            a.g_init = True
+            self._mark_grad(w, b)
+            return blk
+        self._bwd_blocks.append(backward)
+        return logits
+
+    def dshead(self, a: PTensor, wt: str, bt: str, w1: str, b1: str, k: int) -> torch.Tensor:
+        """Deep-supervision head ConvTranspose2d(C,C,k,k) -> Conv2d 1x1 (C->1) (MTnnUNet.py:106-117), composed into a
+        single C -> k*k projection so the k*k*C full-resolution intermediate never exists."""
+        f = a.feat
+        Cc, kk = f.C, k * k
+        wc = torch.zeros(Cc, kk, dtype=torch.float32, device=self.device)
+        bc = torch.zeros(1, dtype=torch.float32, device=self.device)
+        logits = torch.zeros(f.N, 1, f.H * k, f.W * k, dtype=torch.float32, device=self.device)
+        dlog = torch.zeros_like(logits)
+        self.pack.append(_mk("mtbc_dshead_compose", ptr(self.P(wt)), ptr(self.P(bt)), ptr(self.P(w1)), ptr(self.P(b1)),
+                             Cc, k, ptr(wc), ptr(bc)))
+        self.fwd.append(_mk("mtbc_dshead_fwd", ptr(f.t), f.N, f.H, f.W, f.Cp, Cc, k, ptr(wc), ptr(bc), ptr(logits)))
+        idx = len(self.outputs_seg)
+        self.outputs_seg.append(logits)
+        self.g_seg.append(dlog)
+
+        def backward():
+            if not self.seg_grad_active[idx]:
+                return []
+            dwc = self.bwd_arena.alloc(Cc, kk)
+            dbc = self.bwd_arena.alloc(1)
+            g = a.grad()
+            blk = [_mk("mtbc_dshead_bwd", ptr(f.t), ptr(dlog), f.N, f.H, f.W, f.Cp, Cc, k, ptr(wc), ptr(g.t),
+                       int(a.g_init), ptr(dwc), ptr(dbc)),
+                   _mk("mtbc_dshead_decompose", ptr(dwc), ptr(dbc), ptr(self.P(wt)), ptr(self.P(bt)), ptr(self.P(w1)),
+                       Cc, k, ptr(self.grad_view[wt]), ptr(self.grad_view[bt]), ptr(self.grad_view[w1]),
+                       ptr(self.grad_view[b1]))]
+            a.g_init = True
+            self._mark_grad(wt, bt, w1, b1)
+            return blk
+        self._bwd_blocks.append(backward)
+        return logits
+
+    def gap_fc(self, a: PTensor, w1: str, b1: str, w2: str, b2: str) -> torch.Tensor:
+        """AdaptiveAvgPool2d(1) -> Flatten -> Linear -> ReLU -> Linear (MTnnUNet.py:125-132)."""
+        f = a.feat
+        Fdim, Hd, K = self.P(w1).shape[1], self.P(w1).shape[0], self.P(w2).shape[0]
+        assert Fdim == f.C
+        gap = torch.zeros(f.N, Fdim, dtype=torch.float32, device=self.device)
+        hid = torch.zeros(f.N, Hd, dtype=torch.float32, device=self.device)
+        logits = torch.zeros(f.N, K, dtype=torch.float32, device=self.device)
+        dlog = torch.zeros_like(logits)
+        self.fwd.append(_mk("mtbc_gap_fc_fwd", ptr(f.t), f.N, f.H * f.W, f.Cp, Fdim, ptr(self.P(w1)), ptr(self.P(b1)),
+                            Hd, ptr(self.P(w2)), ptr(self.P(b2)), K, ptr(gap), ptr(hid), ptr(logits)))
+        self.outputs_cls.append(logits)
+        self.g_cls.append(dlog)
+
+        def backward():
+            g = a.grad()
+            blk = [_mk("mtbc_gap_fc_bwd", ptr(dlog), f.N, f.H * f.W, f.Cp, Fdim, ptr(self.P(w1)), Hd, ptr(self.P(w2)),
+                       K, ptr(gap), ptr(hid), ptr(g.t), int(a.g_init), ptr(self.grad_view[w1]), ptr(self.grad_view[b1]),
+                       ptr(self.grad_view[w2]), ptr(self.grad_view[b2]))]
+            a.g_init = True
+            self._mark_grad(w1, b1, w2, b2)
+            return blk
+        self._bwd_blocks.append(backward)
+        return logits
+
+    def flat_fc(self, a: PTensor, w1: str, b1: str, w2: str, b2: str) -> torch.Tensor:
+        """Flatten -> Linear(C*H*W, 256) -> ReLU -> Linear (Multi_BTS_UNet.py:107-115)."""
+        f = a.feat
+        Hd, K = self.P(w1).shape[0], self.P(w2).shape[0]
+        assert self.P(w1).shape[1] == f.C * f.H * f.W, "Multi_BTS_UNet's classifier hard-codes a 16x16 bottleneck"
+        hid = torch.zeros(f.N, Hd, dtype=torch.float32, device=self.device)
+        dh = torch.zeros(f.N, Hd, dtype=torch.float32, device=self.device)
+        logits = torch.zeros(f.N, K, dtype=torch.float32, device=self.device)
+        dlog = torch.zeros_like(logits)
+        self.fwd.append(_mk("mtbc_flat_fc_fwd", ptr(f.t), f.N, f.H * f.W, f.Cp, f.C, ptr(self.P(w1)), ptr(self.P(b1)),
+                            Hd, ptr(self.P(w2)), ptr(self.P(b2)), K, ptr(hid), ptr(logits)))
+        self.outputs_cls.append(logits)
+        self.g_cls.append(dlog)
+
+        def backward():
+            g = a.grad()
+            blk = [_mk("mtbc_flat_fc_bwd", ptr(f.t), ptr(dlog), f.N, f.H * f.W, f.Cp, f.C, ptr(self.P(w1)), Hd,
+                       ptr(self.P(w2)), K, ptr(hid), ptr(g.t), int(a.g_init), ptr(self.grad_view[w1]),
+                       ptr(self.grad_view[b1]), ptr(self.grad_view[w2]), ptr(self.grad_view[b2]), ptr(dh))]
+            a.g_init = True
+            self._mark_grad(w1, b1, w2, b2)
+            return blk
+        self._bwd_blocks.append(backward)
+        return logits
+
+    # ------------------------------------------------------------------------------------------------ finalize / run
+    def finalize(self, seg_grad_active: Optional[Sequence[bool]] = None):
+        """Emit the backward launch list (reverse order of the forward ops)."""
+        assert not self.finalized
+        self.seg_grad_active = list(seg_grad_active) if seg_grad_active is not None else [True] * len(self.outputs_seg)
+        if self.training:
+            body: List[Callable] = []
+            for mk_block in reversed(self._bwd_blocks):
+                body.extend(mk_block())
+            for w, launches in list(self._wg_unpack.items()):  # shared weights whose last application had no grad
+                body.extend(launches)
+            self._wg_unpack.clear()
+            self.bwd = [_mk("mtbc_zero_bytes", ptr(self.grad_flat), self.grad_flat.numel() * 4)]
+            self.bwd += self.bwd_arena.zero_launches()
+            self.bwd += body
+        self.fwd = self.fwd_arena.zero_launches() + self.fwd
+        self._bwd_blocks = []
+        self.finalized = True
+
+    def run_pack(self, stream=None):
+        st = C.c_void_p(stream if stream is not None else ops.stream_ptr())
+        for l in self.pack:
+            l(st)
+
+    def run_forward(self, stream=None):
+        st = C.c_void_p(stream if stream is not None else ops.stream_ptr())
+        for l in self.fwd:
+            l(st)
+
+    def run_backward(self, stream=None):
+        st = C.c_void_p(stream if stream is not None else ops.stream_ptr())
+        for l in self.bwd:
+            l(st)
+
+    def launch_counts(self) -> Dict[str, int]:
+        return {"pack": len(self.pack), "fwd": len(self.fwd), "bwd": len(self.bwd)}
+
+
+def _mk_copy_f32(dst: torch.Tensor, src: torch.Tensor, n: int) -> Callable:
+    """Refresh a zero-padded fp32 copy of a small parameter vector (device-to-device, graph-capturable)."""
+    l = _mk("mtbc_copy_f32", ptr(dst), ptr(src), n)
+    l._keep = (dst, src)
+    return l

@@ -92,15 +92,15 @@ def conv_fwd_case(N, H, W, src_C, Cout, bias=True, stats=True, identity=False):
     run_case(fn, name)
 
 
-def conv_dgrad_case(N, H, W, Cin, Cout, accumulate):
-    name = f"conv3x3_dgrad N{N} {H}x{W} {Cin}<-{Cout} acc={accumulate}"
+def conv_dgrad_case(N, H, W, Cin, Cout, accumulate, dyscale=1.0):
+    name = f"conv3x3_dgrad N{N} {H}x{W} {Cin}<-{Cout} acc={accumulate} dyscale={dyscale}"
 
     def fn():
         w = rnd(Cout, Cin, 3, 3, scale=0.1)
-        dy = rnd(N, Cout, H, W)
+        dy = rnd(N, Cout, H, W, scale=dyscale)
         dyf = Feat.from_nchw(dy)
         dx = Feat.empty(N, H, W, Cin)
-        base = rnd(N, Cin, H, W)
+        base = rnd(N, Cin, H, W, scale=dyscale)
         if accumulate:
             dx = Feat.from_nchw(base)
         wd = torch.zeros(9, dx.Cp, dyf.Cp, dtype=torch.bfloat16, device=dev)
@@ -334,6 +334,9 @@ def fwd_cases():
 
 
 def dgrad_cases():
+    conv_dgrad_case(4, 64, 64, 24, 24, False, dyscale=1e-5)
+    conv_dgrad_case(4, 64, 64, 24, 24, False, dyscale=1.0)
+    conv_dgrad_case(4, 4, 4, 512, 512, False, dyscale=1e-3)
     conv_dgrad_case(2, 16, 16, 64, 64, False)
     conv_dgrad_case(2, 32, 32, 24, 48, True)
     conv_dgrad_case(2, 16, 16, 192, 96, False)
