@@ -513,7 +513,7 @@ int mtbc_dshead_fwd(const void* a, int32_t N, int32_t H, int32_t W, int32_t Cp, 
   const int64_t npix = static_cast<int64_t>(N) * H * W;
   int g = cdiv(npix, PB); if (g > 148 * 8) g = 148 * 8;
   const size_t smem = (static_cast<size_t>(C) * kk + static_cast<size_t>(PB) * C) * sizeof(float);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(dshead_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  { static bool done = false; if (smem > 48 * 1024 && !done) { cudaFuncSetAttribute(dshead_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); done = true; } }
   dshead_fwd_kernel<<<g, 256, smem, ST(stream)>>>(CBF(a), N, H, W, Cp, C, k, wc, bc, logits);
   return check_launch("dshead_fwd");
 }
@@ -526,7 +526,7 @@ int mtbc_dshead_bwd(const void* a, const float* dlogits, int32_t N, int32_t H, i
   const int64_t npix = static_cast<int64_t>(N) * H * W;
   int g = cdiv(npix, PB * 8); if (g > 148 * 2) g = 148 * 2; if (g < 1) g = 1;
   const size_t smem = (static_cast<size_t>(C) * kk + static_cast<size_t>(PB) * C + static_cast<size_t>(PB) * kk) * sizeof(float);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(dshead_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  { static bool done = false; if (smem > 48 * 1024 && !done) { cudaFuncSetAttribute(dshead_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); done = true; } }
   dshead_bwd_kernel<<<g, 256, smem, ST(stream)>>>(CBF(a), dlogits, N, H, W, Cp, C, k, wc, BF(dA), accumulate, dwc, dbc);
   return check_launch("dshead_bwd");
 }
@@ -579,7 +579,7 @@ int mtbc_flat_fc_bwd(const void* a, const float* dlogits, int32_t N, int32_t HW,
   if (rc) return rc;
   const int64_t F = static_cast<int64_t>(C) * HW;
   const size_t smem = static_cast<size_t>(N) * Hd * sizeof(float);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(flat_fc_bwd_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  { static bool done = false; if (smem > 48 * 1024 && !done) { cudaFuncSetAttribute(flat_fc_bwd_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); done = true; } }
   flat_fc_bwd_big_kernel<<<cdiv(F, 256), 256, smem, ST(stream)>>>(CBF(a), N, HW, Cp, C, w1, Hd, scratch, BF(dA),
                                                                  accumulate, dw1);
   return check_launch("flat_fc_bwd_big");

@@ -77,7 +77,8 @@ def _mk(name: str, *args) -> Callable[[C.c_void_p], None]:
     return launch
 
 
-def _mk_op(op: ops.Op) -> Callable:
+def _mk_op(op: ops.Op, true_flops: float = 0.0, desc: str = "") -> Callable:
+    """Bind a tensor-core op launch; `true_flops` = algorithmic 2*M*N*K with unpadded channels (roofline numerator)."""
     lib = _lib.load()
     h = op.handle
 
@@ -87,6 +88,8 @@ def _mk_op(op: ops.Op) -> Callable:
             _lib.check(rc, op.kind)
     launch.kind = op.kind
     launch.op = op
+    launch.true_flops = true_flops
+    launch.desc = desc
     return launch
 
 
@@ -114,16 +117,10 @@ class Plan:
         self.g_seg: List[Optional[torch.Tensor]] = []
         # flat parameter gradients (param-shaped views); registration order reversed ~ backward completion order
         names = list(params.keys())
-        total = sum((params[n].numel() + 63) // 64 * 64 for n in names)
+        self.grad_range, total = flat_layout(params)
         self.grad_flat = torch.zeros(total, dtype=torch.float32, device=device)
-        self.grad_view: Dict[str, torch.Tensor] = {}
-        self.grad_range: Dict[str, Tuple[int, int]] = {}
-        off = 0
-        for n in reversed(names):
-            p = params[n]
-            self.grad_view[n] = self.grad_flat[off:off + p.numel()].view_as(p)
-            self.grad_range[n] = (off, off + p.numel())
-            off += (p.numel() + 63) // 64 * 64
+        self.grad_view: Dict[str, torch.Tensor] = {
+            n: self.grad_flat[a:b].view_as(params[n]) for n, (a, b) in self.grad_range.items()}
         self.has_grad: Dict[str, bool] = {n: False for n in names}
         # deferred conv weight-gradient unpacks: param name -> (pending applications, launches)
         self._wg_pending: Dict[str, int] = {}
@@ -131,6 +128,7 @@ class Plan:
         self._wg_unpack: Dict[str, List[Callable]] = {}
         self._packed: Dict[str, dict] = {}
         self.finalized = False
+        self._touched = set()
         self.tensors: Dict[str, PTensor] = {}  # name -> activation (debug / tests)
         self.debug: Dict[str, Feat] = {}
         self.param_done_at: Dict[str, int] = {}  # index into self.bwd after which the param's grad is final
@@ -168,6 +166,7 @@ class Plan:
         for n in names:
             if n is not None:
                 self.has_grad[n] = True
+                self._touched.add(n)
 
     # ------------------------------------------------------------------------------------------------ layers
     def input_conv_in_act(self, x_in: torch.Tensor, w: str, b: Optional[str], gamma: Optional[str],
@@ -215,7 +214,8 @@ class Plan:
         op = ops.conv3x3_fwd_op(feats, pk["wf"], y.feat, bias=bias, stat_sum=ssum if fused else None,
                                 stat_sq=ssq if fused else None)
         self.tc_flops_fwd += op.flops
-        self.fwd.append(_mk_op(op))
+        self.fwd.append(_mk_op(op, 2.0 * N * H * Wd * Cout * Cin * 9,
+                               f"{name} fwd {N}x{H}x{Wd} {[f.C for f in feats]}->{Cout}"))
         if not fused:
             self.fwd.append(_mk("mtbc_in_stats", ptr(y.feat.t), N, H * Wd, Cp, ptr(ssum), ptr(ssq)))
         a, p, aux = self._norm_act(y, ssum, ssq, gamma, beta, slope, pool, name)
@@ -231,7 +231,7 @@ class Plan:
             for f, off in zip(feats, pk["offs"]):
                 o = ops.conv3x3_wgrad_op(f, dy, acc, off)
                 self.tc_flops_bwd += o.flops
-                blk.append(_mk_op(o))
+                blk.append(_mk_op(o, 2.0 * N * H * Wd * Cout * f.C * 9, f"{name} wgrad {N}x{H}x{Wd} {f.C}x{Cout}"))
             self._mark_grad(w, b)
             if self._wg_pending[w] == 0:
                 blk.extend(self._wg_unpack.pop(w))
@@ -239,7 +239,8 @@ class Plan:
                 g = s.grad()
                 o = ops.conv3x3_dgrad_op(dy, wd, g, accumulate=s.g_init)
                 self.tc_flops_bwd += o.flops
-                blk.append(_mk_op(o))
+                blk.append(_mk_op(o, 2.0 * N * H * Wd * Cout * s.feat.C * 9,
+                                  f"{name} dgrad {N}x{H}x{Wd} {s.feat.C}<-{Cout} acc={int(o.kind is None)}"))
                 s.g_init = True
             return blk
         self._bwd_blocks.append(backward)
@@ -334,7 +335,8 @@ class Plan:
         bias = self._padded_vec(b, cp)
         op = ops.convT_fwd_op(f, wf, out.feat, k, bias)
         self.tc_flops_fwd += op.flops
-        self.fwd.append(_mk_op(op))
+        t_flops = 2.0 * f.N * f.H * f.W * Cin * Cout * k * k
+        self.fwd.append(_mk_op(op, t_flops, f"{name} convT fwd {f.N}x{f.H}x{f.W} {Cin}->{Cout}"))
 
         def backward():
             blk: List[Callable] = []
@@ -343,7 +345,7 @@ class Plan:
             acc = self.bwd_arena.alloc(k * k, cp, f.Cp)
             o = ops.convT_wgrad_op(f, out.g, acc, k)
             self.tc_flops_bwd += o.flops
-            blk.append(_mk_op(o))
+            blk.append(_mk_op(o, t_flops, f"{name} convT wgrad {f.N}x{f.H}x{f.W} {Cin}->{Cout}"))
             blk.append(_mk("mtbc_unpack_convT_wgrad", ptr(acc), k * k * cp, f.Cp, ptr(self.grad_view[w]), Cin, Cout, k,
                            0))
             if b is not None:
@@ -353,7 +355,7 @@ class Plan:
             g = x.grad()
             o = ops.convT_dgrad_op(out.g, wd, g, k, accumulate=x.g_init)
             self.tc_flops_bwd += o.flops
-            blk.append(_mk_op(o))
+            blk.append(_mk_op(o, t_flops, f"{name} convT dgrad {f.N}x{f.H}x{f.W} {Cin}<-{Cout}"))
             x.g_init = True
             return blk
         self._bwd_blocks.append(backward)
@@ -491,14 +493,20 @@ class Plan:
         self.seg_grad_active = list(seg_grad_active) if seg_grad_active is not None else [True] * len(self.outputs_seg)
         if self.training:
             body: List[Callable] = []
+            n_pre = 1 + len(self.bwd_arena.chunks) + 1  # zero launches precede the body (upper bound fixed below)
             for mk_block in reversed(self._bwd_blocks):
+                self._touched = set()
                 body.extend(mk_block())
+                for n in self._touched:  # the last block touching a parameter finalises its gradient
+                    self.param_done_at[n] = len(body)
             for w, launches in list(self._wg_unpack.items()):  # shared weights whose last application had no grad
                 body.extend(launches)
             self._wg_unpack.clear()
             self.bwd = [_mk("mtbc_zero_bytes", ptr(self.grad_flat), self.grad_flat.numel() * 4)]
             self.bwd += self.bwd_arena.zero_launches()
+            n_pre = len(self.bwd)
             self.bwd += body
+            self.param_done_at = {n: i + n_pre for n, i in self.param_done_at.items()}
         self.fwd = self.fwd_arena.zero_launches() + self.fwd
         self._bwd_blocks = []
         self.finalized = True
@@ -520,6 +528,18 @@ class Plan:
 
     def launch_counts(self) -> Dict[str, int]:
         return {"pack": len(self.pack), "fwd": len(self.fwd), "bwd": len(self.bwd)}
+
+
+def flat_layout(params) -> Tuple[Dict[str, Tuple[int, int]], int]:
+    """Offsets of every parameter inside the flat fp32 gradient (and, for TrainStep, parameter / Adam-state) buffers:
+    reversed registration order (~ the order in which backward finishes them), each slot padded to 64 floats."""
+    ranges: Dict[str, Tuple[int, int]] = {}
+    off = 0
+    for n in reversed(list(params.keys())):
+        k = params[n].numel()
+        ranges[n] = (off, off + k)
+        off += (k + 63) // 64 * 64
+    return ranges, off
 
 
 def _mk_copy_f32(dst: torch.Tensor, src: torch.Tensor, n: int) -> Callable:

@@ -1,0 +1,188 @@
+"""Sync-free training step for the multi-task models (the loop body of src/training_multitask.py:79-103).
+
+    zero_grad -> forward -> Dice(+deep supervision weights) + focal -> alpha mix -> backward -> Adam(lr, eps=1e-4)
+
+Everything between the host->device copy of the batch and the optimizer update is a flat list of C-ABI launches on one
+stream (plan.py), captured once into a CUDA graph and replayed.  The reference's per-step host syncs (`torch.isnan` in a
+Python `if`, `.item()` on the loss: criterions.py:72, training_multitask.py:99) become a device-side NaN flag and a
+4-float device buffer that the caller reads when it wants to.
+
+Data parallel (new functionality, the reference is single device): one process per GPU, gradients are summed with one
+NCCL all-reduce over the flat gradient buffer and the 1/world scaling is folded into the Adam kernel.  No operation
+couples samples (InstanceNorm is per sample, Dice is per sample then mean, focal is per sample then mean), so R ranks x
+B/R samples equals 1 rank x B samples up to fp32 summation order.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from .ops import ptr, stream_ptr
+from .plan import Plan, _mk, flat_layout
+
+
+class TrainStep:
+    def __init__(self, model: torch.nn.Module, batch_shape: Sequence[int], lr: float = 1e-4, betas=(0.9, 0.999),
+                 eps: float = 1e-4, alpha: float = 0.35, inversely_weighted: bool = True, focal_alpha: float = 1.0,
+                 focal_gamma: float = 2.0, process_group=None, use_graph: bool = True, device=None):
+        """`model` is one of models.{MTUNetPlusPlus, MTnnUNet, Multi_BTS_UNet} already on its CUDA device.
+        Hyper-parameters keep the meaning of src/config.yaml (optimizer.lr, training.alpha, loss.inversely_weighted)."""
+        self.model = model
+        self.device = device or next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise _lib.MtbcError("TrainStep needs a CUDA (sm_100a) device; there is no CPU fallback")
+        self.B, self.Cin, self.H, self.W = (int(v) for v in batch_shape)
+        self.alpha, self.inv_w = float(alpha), bool(inversely_weighted)
+        self.focal_alpha, self.focal_gamma = float(focal_alpha), float(focal_gamma)
+        self.betas, self.eps = (float(betas[0]), float(betas[1])), float(eps)
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(process_group)
+        self.use_graph = use_graph
+        with torch.cuda.device(self.device):
+            self._flatten_params()
+            x = torch.zeros(self.B, self.Cin, self.H, self.W, dtype=torch.float32, device=self.device)
+            self.plan: Plan = model._get_plan(x, True)
+            self.x = self.plan.x_in
+            self.mask = torch.zeros(self.B, 1, self.H, self.W, dtype=torch.float32, device=self.device)
+            K = self.plan.outputs_cls[0].shape[1]
+            self.onehot = torch.zeros(self.B, K, dtype=torch.float32, device=self.device)
+            self.K = K
+            nh = len(self.plan.outputs_seg)
+            self.nheads = nh
+            self.dice_sums = torch.zeros(nh, self.B, 3, dtype=torch.float32, device=self.device)
+            self.dice_loss = torch.zeros(nh, dtype=torch.float32, device=self.device)  # [0] = full decoder head
+            self.focal_loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+            self.loss_out = torch.zeros(4, dtype=torch.float32, device=self.device)  # total, seg, cls, nan flag
+            self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=self.device)
+            self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self.exp_avg = torch.zeros_like(self.flat_p)
+            self.exp_avg_sq = torch.zeros_like(self.flat_p)
+            self._build_launches()
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.steps_done = 0
+        self._pinned: Dict[str, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------------------------------------ set-up
+    def _flatten_params(self):
+        """Re-home every parameter as a view of one flat fp32 buffer laid out like the plan's gradient buffer, so Adam
+        and the gradient all-reduce are single launches.  Values, shapes, dtypes and state_dict keys are unchanged."""
+        params = dict(self.model.named_parameters())
+        ranges, total = flat_layout(params)
+        self.flat_p = torch.zeros(total, dtype=torch.float32, device=self.device)
+        for n, p in params.items():
+            a, b = ranges[n]
+            v = self.flat_p[a:b].view_as(p)
+            v.copy_(p.data)
+            p.data = v
+        self.param_ranges = ranges
+
+    def _build_launches(self):
+        plan = self.plan
+        nh, B, HW = self.nheads, self.B, self.H * self.W
+        L: List = []
+        L += plan.pack
+        L += plan.fwd
+        # ---- fused objective (criterions.py:52-76 + training_multitask.py:98)
+        L.append(_mk("mtbc_zero_bytes", ptr(self.dice_sums), self.dice_sums.numel() * 4))
+        for i, logits in enumerate(plan.outputs_seg):
+            j = nh - 1 - i  # reversed list: the last head (full decoder) gets weight 1
+            L.append(_mk("mtbc_dice_sums", ptr(logits), ptr(self.mask), B, HW, ptr(self.dice_sums[i])))
+            L.append(_mk("mtbc_dice_finalize", ptr(self.dice_sums[i]), B, ptr(self.dice_loss[j:j + 1])))
+        L.append(_mk("mtbc_focal_fwd", ptr(plan.outputs_cls[0]), ptr(self.onehot), B, self.K,
+                     C.c_float(self.focal_alpha), C.c_float(self.focal_gamma), ptr(self.focal_loss)))
+        L.append(_mk("mtbc_multitask_loss", ptr(self.dice_loss), nh, int(self.inv_w), ptr(self.focal_loss),
+                     C.c_float(self.alpha), ptr(self.loss_out)))
+        # ---- d(total)/d(logits)
+        for i, logits in enumerate(plan.outputs_seg):
+            j = nh - 1 - i
+            wgt = self.alpha * (1.0 / (j + 1) if self.inv_w else 1.0)
+            L.append(_mk("mtbc_dice_bwd", ptr(logits), ptr(self.mask), B, HW, ptr(self.dice_sums[i]), None,
+                         C.c_float(wgt), ptr(plan.g_seg[i])))
+        L.append(_mk("mtbc_focal_bwd", ptr(plan.outputs_cls[0]), ptr(self.onehot), B, self.K,
+                     C.c_float(self.focal_alpha), C.c_float(self.focal_gamma), None, C.c_float(1.0 - self.alpha),
+                     ptr(plan.g_cls[0])))
+        L += plan.bwd
+        self.launches_fb = L
+        # ---- optimizer (after the all-reduce when data parallel)
+        self.launches_opt = [
+            _mk("mtbc_increment_i32", ptr(self.step_dev)),
+            _mk("mtbc_adam_step_dev", ptr(self.flat_p), ptr(plan.grad_flat), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                self.flat_p.numel(), ptr(self.lr_dev), C.c_float(self.betas[0]), C.c_float(self.betas[1]),
+                C.c_float(self.eps), C.c_float(1.0 / self.world), ptr(self.step_dev)),
+        ]
+
+    # ------------------------------------------------------------------------------------------------ running
+    @property
+    def n_launches(self) -> int:
+        """Kernel / memset launches of one step (our own kernels only; the NCCL all-reduce is not counted)."""
+        return len(self.launches_fb) + len(self.launches_opt)
+
+    def _run_list(self, launches):
+        st = C.c_void_p(stream_ptr())
+        for l in launches:
+            l(st)
+
+    def _capture(self):
+        # warm up on a side stream, then capture forward+loss+backward (+ optimizer when single GPU)
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        saved = (self.flat_p.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.step_dev.clone())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._run_list(self.launches_fb)
+                if self.world == 1:
+                    self._run_list(self.launches_opt)
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        self.flat_p.copy_(saved[0]); self.exp_avg.copy_(saved[1]); self.exp_avg_sq.copy_(saved[2])
+        self.step_dev.copy_(saved[3])
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._run_list(self.launches_fb)
+            if self.world == 1:
+                self._run_list(self.launches_opt)
+        self.graph = g
+
+    def load_batch(self, x: torch.Tensor, mask: torch.Tensor, onehot: torch.Tensor):
+        """Copy a batch (host pinned or device tensors) into the static input buffers, asynchronously."""
+        self.x.copy_(x, non_blocking=True)
+        self.mask.copy_(mask, non_blocking=True)
+        self.onehot.copy_(onehot, non_blocking=True)
+
+    def step(self):
+        """One optimisation step on the currently loaded batch.  Asynchronous; losses stay on the device."""
+        with torch.cuda.device(self.device):
+            if self.use_graph:
+                if self.graph is None:
+                    self._capture()
+                self.graph.replay()
+            else:
+                self._run_list(self.launches_fb)
+                if self.world == 1:
+                    self._run_list(self.launches_opt)
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(self.plan.grad_flat, op=dist.ReduceOp.SUM, group=self.pg)
+                self._run_list(self.launches_opt)
+        self.steps_done += 1
+
+    def set_lr(self, lr: float):
+        self.lr_dev.fill_(float(lr))
+
+    def losses(self) -> torch.Tensor:
+        """Device tensor [total, seg, cls, nan_flag] of the last step (reading it synchronises)."""
+        return self.loss_out
+
+    def forward_backward_only(self):
+        """Forward + loss + backward without the optimizer (parity tests)."""
+        with torch.cuda.device(self.device):
+            self._run_list(self.launches_fb)
+
+    def deliver_grads(self):
+        self.model._deliver_grads(self.plan)

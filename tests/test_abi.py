@@ -1,0 +1,51 @@
+"""The C-ABI library loads and exports every symbol include/mtbc.h declares (no compute calls: CPU only)."""
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _decls():
+    src = open(os.path.join(ROOT, "include", "mtbc.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return re.findall(r"\b(?:int|void|double|const char\*)\s+(mtbc_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S)
+
+
+def test_header_symbols_exported(lib):
+    decls = _decls()
+    assert len(decls) >= 45
+    for name, _ in decls:
+        assert hasattr(lib, name), f"{name} declared in mtbc.h but not exported by libmtbc.so"
+
+
+def test_ctypes_signatures_match_header(lib):
+    from multi_task_breast_cancer_b200 import _lib
+    decls = dict(_decls())
+    assert set(_lib._SIGS) | {"mtbc_last_error"} == set(decls), set(decls) ^ (set(_lib._SIGS) | {"mtbc_last_error"})
+    for name, args in decls.items():
+        if name == "mtbc_last_error":
+            continue
+        n = 0 if args.strip() in ("", "void") else len(args.split(","))
+        assert n == len(_lib._SIGS[name]), (name, n, len(_lib._SIGS[name]))
+
+
+def test_abi_version_and_error_string(lib):
+    assert lib.mtbc_abi_version() == 1
+    assert isinstance(lib.mtbc_last_error(), bytes)
+
+
+def test_no_library_fallback_symbols():
+    """The hot path may not reach cuDNN / cuBLAS: the shared object must not link them."""
+    import subprocess
+    from multi_task_breast_cancer_b200 import _lib
+    out = subprocess.run(["ldd", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "cudnn" not in out and "cublas" not in out, out
+
+
+def test_invalid_descriptor_is_an_error_not_a_crash(lib):
+    import ctypes as C
+    from multi_task_breast_cancer_b200 import _lib
+    d = _lib.ConvGemmDesc()
+    h = C.c_void_p()
+    rc = lib.mtbc_conv_gemm_create(C.byref(d), C.byref(h))
+    assert rc != 0 and b"conv_gemm" in lib.mtbc_last_error()

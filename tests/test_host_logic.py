@@ -1,0 +1,136 @@
+"""CPU tests of the host-side logic: drop-in module surface, flat layouts, data-parallel averaging (gloo, 2 ranks)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from oracle import torch_oracle as O
+from multi_task_breast_cancer_b200 import models as M, ops
+from multi_task_breast_cancer_b200.plan import flat_layout
+from multi_task_breast_cancer_b200._lib import MtbcError
+
+
+def _pairs():
+    return [
+        (lambda m: m.MTUNetPlusPlus(in_channels=1, out_channels=1, n_classes=3, deep_supervision=True), 14927455, 168),
+        (lambda m: m.MTnnUNet(1, 1, 3), 15819799, 53),
+        (lambda m: m.Multi_BTS_UNet(1, 1, 3, 32, True), 21751142, 33),
+    ]
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_state_dict_and_init_identical_to_oracle(idx):
+    mk, n_params, n_state = _pairs()[idx]
+    torch.manual_seed(1993)
+    a = mk(O)
+    torch.manual_seed(1993)
+    b = mk(M)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa.keys()) == list(sb.keys())
+    assert all(torch.equal(sa[k], sb[k]) for k in sa)
+    assert sum(p.numel() for p in b.parameters()) == n_params and len(sb) == n_state
+    b.load_state_dict(sa)  # reference checkpoints load (training_multitask.py:243-249, utils/models.py:28-32)
+
+
+def test_n_classes_two_means_one_logit():
+    assert M.MTnnUNet(1, 1, n_classes=2).classifier[5].out_features == 1
+    assert M.MTUNetPlusPlus(n_classes=2).classifier[5].out_features == 1
+
+
+def test_factory_mirrors_reference():
+    assert isinstance(M.init_multitask_model("MTnnUNet", 1, 1, 3), M.MTnnUNet)
+    assert isinstance(M.init_multitask_model("MTUNetPlusPlus", 1, 1, 3, deep_supervision=True), M.MTUNetPlusPlus)
+    assert isinstance(M.init_multitask_model("Multi_BTSUNet", 1, 1, 3, width=32), M.Multi_BTS_UNet)
+    unknown = M.init_multitask_model("does-not-exist")
+    assert type(unknown) is torch.nn.Module  # the reference silently returns an empty module
+
+
+def test_cpu_input_fails_loudly():
+    m = M.MTnnUNet(1, 1, 3)
+    with pytest.raises(MtbcError):
+        m(torch.zeros(1, 1, 64, 64))
+
+
+def test_flat_layout_is_reverse_registration_order_and_padded():
+    m = M.MTnnUNet(1, 1, 3)
+    params = dict(m.named_parameters())
+    ranges, total = flat_layout(params)
+    names = list(params)
+    assert ranges[names[-1]][0] == 0
+    prev_end = 0
+    for n in reversed(names):
+        a, b = ranges[n]
+        assert a % 64 == 0 and a >= prev_end and b - a == params[n].numel()
+        prev_end = b
+    assert total % 64 == 0 and total >= sum(p.numel() for p in params.values())
+
+
+def test_k_offsets_alignment():
+    class F:  # minimal stand-in for ops.Feat
+        def __init__(self, cp): self.Cp = cp
+    offs, ktot = ops.k_offsets([F(32), F(64)])
+    assert offs == [0, 64] and ktot == 128          # 64-wide sources start on a 64 boundary
+    offs, ktot = ops.k_offsets([F(32), F(32), F(96)])
+    assert offs == [0, 32, 64] and ktot == 160
+    assert ops.pad32(24) == 32 and ops.pad32(320) == 320 and ops.pad32(1) == 32
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _dp_worker(rank, world, port, out_path):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    torch.manual_seed(1993)
+    model = O.MTnnUNet(1, 1, 3)
+    B = 4
+    img, mask, onehot, _ = O.synthetic_batch(B, 64, 64)
+    sl = slice(rank * B // world, (rank + 1) * B // world)
+    logits, outs = model(img[sl])
+    seg, cls = O.multitask_criterion(O.DiceLoss(), mask[sl], outs, O.FocalLoss(), onehot[sl], logits, True)
+    (0.35 * seg + 0.65 * cls).backward()
+    params = dict(model.named_parameters())
+    ranges, total = flat_layout(params)
+    flat = torch.zeros(total)
+    for n, p in params.items():
+        a, b = ranges[n]
+        flat[a:b] = p.grad.reshape(-1)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)   # what TrainStep does over NCCL ...
+    flat *= 1.0 / world                           # ... with the 1/world folded into the Adam kernel
+    if rank == 0:
+        torch.save(flat, out_path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_mean_equals_full_batch_gloo():
+    """2 ranks x B/2 samples == 1 rank x B samples (no op couples samples): the DP averaging rule of train.py."""
+    world, port = 2, _free_port()
+    import tempfile
+    ctx = mp.get_context("spawn")
+    out_path = os.path.join(tempfile.mkdtemp(), "flat.pt")
+    procs = [ctx.Process(target=_dp_worker, args=(r, world, port, out_path)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    flat = torch.load(out_path)
+    torch.manual_seed(1993)
+    model = O.MTnnUNet(1, 1, 3)
+    img, mask, onehot, _ = O.synthetic_batch(4, 64, 64)
+    logits, outs = model(img)
+    seg, cls = O.multitask_criterion(O.DiceLoss(), mask, outs, O.FocalLoss(), onehot, logits, True)
+    (0.35 * seg + 0.65 * cls).backward()
+    params = dict(model.named_parameters())
+    ranges, total = flat_layout(params)
+    want = torch.zeros(total)
+    for n, p in params.items():
+        a, b = ranges[n]
+        want[a:b] = p.grad.reshape(-1)
+    torch.testing.assert_close(flat, want, rtol=2e-3, atol=1e-6)

@@ -1,0 +1,96 @@
+"""GPU parity of every C-ABI kernel against torch fp32 on the same (bf16-rounded) inputs.  Tolerances: 2e-2 of the
+reference's max magnitude for bf16 outputs (one bf16 rounding of the result), 1e-4..1e-2 for fp32 outputs."""
+import os
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+@pytest.fixture(scope="module")
+def D(lib):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs CUDA")
+    import diag_kernels as d
+    from multi_task_breast_cancer_b200 import _lib
+    _lib.check(lib.mtbc_device_check(), "device check")
+    torch.manual_seed(0)
+    return d
+
+
+def _run(D, fn, *a, **k):
+    D.RESULTS.clear()
+    fn(*a, **k)
+    bad = [r for r in D.RESULTS if not r[1]]
+    assert D.RESULTS and not bad, bad
+
+
+@pytest.mark.parametrize("N,H,W,src,cout,kw", [
+    (2, 16, 16, [64], 64, dict(bias=False, stats=False, identity=True)),
+    (2, 16, 16, [32], 32, dict(bias=False, stats=False, identity=True)),
+    (2, 32, 32, [24, 24, 48], 24, {}),
+    (2, 32, 32, [48, 48, 48], 48, {}),
+    (2, 16, 16, [96, 96], 96, {}),
+    (3, 16, 16, [128], 512, {}),
+    (2, 16, 16, [384, 384, 384], 512, {}),
+    (4, 8, 8, [320], 320, dict(stats=False)),      # small planes: several samples per 128-row tile
+    (9, 4, 4, [64], 64, dict(stats=False)),        # ragged batch (9 is not a multiple of the 8 samples per tile)
+    (2, 64, 64, [24, 24, 24, 24, 48], 24, {}),     # x_0_4 of U-Net++: five concat sources folded into the K loop
+])
+def test_conv3x3_forward(D, N, H, W, src, cout, kw):
+    _run(D, D.conv_fwd_case, N, H, W, src, cout, **kw)
+
+
+@pytest.mark.parametrize("args", [(2, 16, 16, 64, 64, False), (2, 32, 32, 24, 48, True), (2, 16, 16, 192, 96, False),
+                                  (4, 64, 64, 24, 24, False, 1e-5), (4, 4, 4, 512, 512, False, 1e-3)])
+def test_conv3x3_dgrad(D, args):
+    _run(D, D.conv_dgrad_case, *args)
+
+
+@pytest.mark.parametrize("args", [(2, 16, 16, 64, 64), (2, 16, 16, 32, 32), (2, 32, 32, 24, 24), (2, 32, 32, 48, 24),
+                                  (2, 16, 16, 192, 96), (2, 16, 16, 128, 256), (2, 16, 16, 384, 512), (4, 8, 8, 320, 320),
+                                  (2, 64, 64, 24, 24, 7)])
+def test_conv3x3_wgrad(D, args):
+    _run(D, D.conv_wgrad_case, *args)
+
+
+@pytest.mark.parametrize("args", [(2, 16, 16, 64, 32), (2, 16, 16, 48, 48), (2, 8, 8, 384, 192), (4, 8, 8, 320, 320)])
+def test_conv_transpose_k2(D, args):
+    _run(D, D.convT_case, *args)
+
+
+@pytest.mark.parametrize("cout", [24, 32, 16])
+def test_first_layer(D, cout):
+    _run(D, D.first_conv_case, 2, 32, 32, cout)
+
+
+@pytest.mark.parametrize("args", [(2, 32, 32, 24, True, True), (2, 16, 16, 96, True, False),
+                                  (2, 16, 16, 320, False, True, 0.01), (3, 8, 8, 512, False, False, 0.01)])
+def test_instance_norm_lrelu_pool(D, args):
+    _run(D, D.norm_case, *args)
+
+
+@pytest.mark.parametrize("args", [(2, 32, 32, 24), (2, 16, 16, 16)])
+def test_head1x1(D, args):
+    _run(D, D.head1x1_case, *args)
+
+
+@pytest.mark.parametrize("args", [(2, 8, 8, 128, 8), (2, 16, 16, 64, 4), (3, 16, 16, 32, 2)])
+def test_composed_deep_supervision_head(D, args):
+    _run(D, D.dshead_case, *args)
+
+
+def test_gap_fc_head(D):
+    _run(D, D.gap_fc_case, 3, 4, 4, 512)
+
+
+def test_flatten_fc_head(D):
+    _run(D, D.flat_fc_case, 3, 16, 16, 256)
+
+
+def test_losses_and_adam(D):
+    _run(D, D.loss_cases)

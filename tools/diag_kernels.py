@@ -270,7 +270,177 @@ def norm_case(N, H, W, C, affine, pool, slope=0.1):
     run_case(fn, name)
 
 
-GROUPS = ["fwd_identity", "fwd", "dgrad", "wgrad", "convT", "first", "norm"]
+def head1x1_case(N, H, W, C):
+    name = f"head1x1 N{N} {H}x{W} C{C}"
+
+    def fn():
+        a = rnd(N, C, H, W)
+        w = rnd(1, C, 1, 1, scale=0.2)
+        b = rnd(1)
+        af = Feat.from_nchw(a)
+        logits = torch.zeros(N, 1, H, W, device=dev)
+        _lib.call("mtbc_head1x1_fwd", ops.ptr(af.t), N * H * W, af.Cp, C, ops.ptr(w), ops.ptr(b), ops.ptr(logits), None)
+        ar = a.clone().requires_grad_(True); wr = w.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
+        ref = F.conv2d(ar, wr, br)
+        report(name + " fwd", logits, ref.detach(), tol=1e-4)
+        dl = rnd(N, 1, H, W)
+        ref.backward(dl)
+        base = rnd(N, C, H, W)
+        dA = Feat.from_nchw(base)
+        dw = torch.zeros(C, device=dev); db = torch.zeros(1, device=dev)
+        _lib.call("mtbc_head1x1_bwd", ops.ptr(af.t), ops.ptr(dl), N * H * W, af.Cp, C, ops.ptr(w), ops.ptr(dA.t), 1,
+                  ops.ptr(dw), ops.ptr(db), None)
+        report(name + " dA(acc)", dA.to_nchw(), ar.grad + base, tol=1e-2)
+        report(name + " dw", dw, wr.grad.flatten(), tol=1e-4)
+        report(name + " db", db, br.grad, tol=1e-4)
+        if af.Cp > C:
+            report(name + " dA pad", dA.t[..., C:].float(), torch.zeros_like(dA.t[..., C:]).float(), tol=1e-6)
+
+    run_case(fn, name)
+
+
+def dshead_case(N, H, W, C, k):
+    name = f"dshead N{N} {H}x{W} C{C} k{k}"
+
+    def fn():
+        a = rnd(N, C, H, W)
+        wt = rnd(C, C, k, k, scale=0.1); bt = rnd(C, scale=0.1); w1 = rnd(1, C, 1, 1, scale=0.2); b1 = rnd(1)
+        af = Feat.from_nchw(a)
+        wc = torch.zeros(C, k * k, device=dev); bc = torch.zeros(1, device=dev)
+        _lib.call("mtbc_dshead_compose", ops.ptr(wt), ops.ptr(bt), ops.ptr(w1), ops.ptr(b1), C, k, ops.ptr(wc), ops.ptr(bc), None)
+        logits = torch.zeros(N, 1, H * k, W * k, device=dev)
+        _lib.call("mtbc_dshead_fwd", ops.ptr(af.t), N, H, W, af.Cp, C, k, ops.ptr(wc), ops.ptr(bc), ops.ptr(logits), None)
+        ps = [t.clone().requires_grad_(True) for t in (a, wt, bt, w1, b1)]
+        ref = F.conv2d(F.conv_transpose2d(ps[0], ps[1], ps[2], stride=k), ps[3], ps[4])
+        report(name + " fwd", logits, ref.detach(), tol=1e-4)
+        dl = rnd(N, 1, H * k, W * k)
+        ref.backward(dl)
+        dA = Feat.empty(N, H, W, C)
+        dwc = torch.zeros(C, k * k, device=dev); dbc = torch.zeros(1, device=dev)
+        _lib.call("mtbc_dshead_bwd", ops.ptr(af.t), ops.ptr(dl), N, H, W, af.Cp, C, k, ops.ptr(wc), ops.ptr(dA.t), 0,
+                  ops.ptr(dwc), ops.ptr(dbc), None)
+        g = [torch.zeros_like(t) for t in (wt, bt, w1, b1)]
+        _lib.call("mtbc_dshead_decompose", ops.ptr(dwc), ops.ptr(dbc), ops.ptr(wt), ops.ptr(bt), ops.ptr(w1), C, k,
+                  ops.ptr(g[0]), ops.ptr(g[1]), ops.ptr(g[2]), ops.ptr(g[3]), None)
+        report(name + " dA", dA.to_nchw(), ps[0].grad, tol=1e-2)
+        for nm, mine, r in zip(("dwt", "dbt", "dw1", "db1"), g, ps[1:]):
+            report(name + " " + nm, mine, r.grad, tol=2e-4)
+
+    run_case(fn, name)
+
+
+def gap_fc_case(N, H, W, Fd, Hd=256, K=3):
+    name = f"gap_fc N{N} {H}x{W} F{Fd}"
+
+    def fn():
+        a = rnd(N, Fd, H, W)
+        w1 = rnd(Hd, Fd, scale=0.05); b1 = rnd(Hd, scale=0.1); w2 = rnd(K, Hd, scale=0.1); b2 = rnd(K, scale=0.1)
+        af = Feat.from_nchw(a)
+        gap = torch.zeros(N, Fd, device=dev); hid = torch.zeros(N, Hd, device=dev); logits = torch.zeros(N, K, device=dev)
+        _lib.call("mtbc_gap_fc_fwd", ops.ptr(af.t), N, H * W, af.Cp, Fd, ops.ptr(w1), ops.ptr(b1), Hd, ops.ptr(w2),
+                  ops.ptr(b2), K, ops.ptr(gap), ops.ptr(hid), ops.ptr(logits), None)
+        ps = [t.clone().requires_grad_(True) for t in (a, w1, b1, w2, b2)]
+        ref = F.linear(F.relu(F.linear(ps[0].mean((2, 3)), ps[1], ps[2])), ps[3], ps[4])
+        report(name + " fwd", logits, ref.detach(), tol=1e-4)
+        dl = rnd(N, K)
+        ref.backward(dl)
+        dA = Feat.empty(N, H, W, Fd)
+        g = [torch.zeros_like(t) for t in (w1, b1, w2, b2)]
+        _lib.call("mtbc_gap_fc_bwd", ops.ptr(dl), N, H * W, af.Cp, Fd, ops.ptr(w1), Hd, ops.ptr(w2), K, ops.ptr(gap),
+                  ops.ptr(hid), ops.ptr(dA.t), 0, ops.ptr(g[0]), ops.ptr(g[1]), ops.ptr(g[2]), ops.ptr(g[3]), None)
+        report(name + " dA", dA.to_nchw(), ps[0].grad, tol=1e-2)
+        for nm, mine, r in zip(("dw1", "db1", "dw2", "db2"), g, ps[1:]):
+            report(name + " " + nm, mine, r.grad, tol=2e-4)
+
+    run_case(fn, name)
+
+
+def flat_fc_case(N, H, W, C, Hd=256, K=3):
+    name = f"flat_fc N{N} {H}x{W} C{C}"
+
+    def fn():
+        a = rnd(N, C, H, W)
+        Fd = C * H * W
+        w1 = rnd(Hd, Fd, scale=0.01); b1 = rnd(Hd, scale=0.1); w2 = rnd(K, Hd, scale=0.1); b2 = rnd(K, scale=0.1)
+        af = Feat.from_nchw(a)
+        hid = torch.zeros(N, Hd, device=dev); logits = torch.zeros(N, K, device=dev)
+        _lib.call("mtbc_flat_fc_fwd", ops.ptr(af.t), N, H * W, af.Cp, C, ops.ptr(w1), ops.ptr(b1), Hd, ops.ptr(w2),
+                  ops.ptr(b2), K, ops.ptr(hid), ops.ptr(logits), None)
+        ps = [t.clone().requires_grad_(True) for t in (a, w1, b1, w2, b2)]
+        ref = F.linear(F.relu(F.linear(ps[0].flatten(1), ps[1], ps[2])), ps[3], ps[4])
+        report(name + " fwd", logits, ref.detach(), tol=1e-3)
+        dl = rnd(N, K)
+        ref.backward(dl)
+        dA = Feat.empty(N, H, W, C)
+        g = [torch.zeros_like(t) for t in (w1, b1, w2, b2)]
+        scratch = torch.zeros(N, Hd, device=dev)
+        _lib.call("mtbc_flat_fc_bwd", ops.ptr(af.t), ops.ptr(dl), N, H * W, af.Cp, C, ops.ptr(w1), Hd, ops.ptr(w2), K,
+                  ops.ptr(hid), ops.ptr(dA.t), 0, ops.ptr(g[0]), ops.ptr(g[1]), ops.ptr(g[2]), ops.ptr(g[3]),
+                  ops.ptr(scratch), None)
+        report(name + " dA", dA.to_nchw(), ps[0].grad, tol=1e-2)
+        for nm, mine, r in zip(("dw1", "db1", "dw2", "db2"), g, ps[1:]):
+            report(name + " " + nm, mine, r.grad, tol=1e-3)
+
+    run_case(fn, name)
+
+
+def loss_cases():
+    import ctypes as C
+    name = "losses"
+
+    def fn():
+        N, H, W, K = 5, 24, 20, 3
+        x = torch.randn(N, 1, H, W, device=dev) * 2
+        t = (torch.rand(N, 1, H, W, device=dev) > 0.7).float()
+        t[2] = 0
+        xr = x.clone().requires_grad_(True)
+        p = torch.sigmoid(xr)
+        f = 1 - (2 * (t * p).sum((1, 2, 3)) + 1) / ((t * t).sum((1, 2, 3)) + (p * p).sum((1, 2, 3)) + 1)
+        ref = f.mean()
+        ref.backward()
+        sums = torch.zeros(N, 3, device=dev); loss = torch.zeros(1, device=dev); d = torch.zeros_like(x)
+        _lib.call("mtbc_dice_sums", ops.ptr(x), ops.ptr(t), N, H * W, ops.ptr(sums), None)
+        _lib.call("mtbc_dice_finalize", ops.ptr(sums), N, ops.ptr(loss), None)
+        gs = torch.full((1,), 0.35, device=dev)
+        _lib.call("mtbc_dice_bwd", ops.ptr(x), ops.ptr(t), N, H * W, ops.ptr(sums), ops.ptr(gs), C.c_float(0.5), ops.ptr(d), None)
+        report("dice fwd", loss, ref.detach().reshape(1), tol=1e-5)
+        report("dice bwd", d, xr.grad * 0.35 * 0.5, tol=1e-4)
+        # focal
+        lg = torch.randn(7, K, device=dev)
+        tg = F.one_hot(torch.arange(7, device=dev) % K, K).float()
+        lr_ = lg.clone().requires_grad_(True)
+        ce = F.cross_entropy(lr_, tg, reduction="none")
+        fr = ((1 - torch.exp(-ce)) ** 2 * ce).mean()
+        fr.backward()
+        fl = torch.zeros(1, device=dev); dg = torch.zeros_like(lg)
+        _lib.call("mtbc_focal_fwd", ops.ptr(lg), ops.ptr(tg), 7, K, C.c_float(1.0), C.c_float(2.0), ops.ptr(fl), None)
+        _lib.call("mtbc_focal_bwd", ops.ptr(lg), ops.ptr(tg), 7, K, C.c_float(1.0), C.c_float(2.0), None, C.c_float(0.65),
+                  ops.ptr(dg), None)
+        report("focal fwd", fl, fr.detach().reshape(1), tol=1e-5)
+        report("focal bwd", dg, lr_.grad * 0.65, tol=1e-4)
+        zl = torch.zeros(2, 3, device=dev); zt = torch.tensor([[1., 0, 0], [0, 0, 1.]], device=dev)
+        _lib.call("mtbc_focal_fwd", ops.ptr(zl), ops.ptr(zt), 2, 3, C.c_float(1.0), C.c_float(2.0), ops.ptr(fl), None)
+        report("focal anchor (2/3)^2 ln3", fl, torch.tensor([0.488272], device=dev), tol=1e-5)
+        # multitask mix
+        dl_ = torch.tensor([0.5, 0.6, 0.7, 0.8], device=dev); out = torch.zeros(4, device=dev)
+        _lib.call("mtbc_multitask_loss", ops.ptr(dl_), 4, 1, ops.ptr(fl), C.c_float(0.35), ops.ptr(out), None)
+        seg = 0.5 + 0.6 / 2 + 0.7 / 3 + 0.8 / 4
+        report("multitask mix", out[:3], torch.tensor([0.35 * seg + 0.65 * 0.488272, seg, 0.488272], device=dev), tol=1e-5)
+        # adam vs torch
+        prm = torch.randn(1000, device=dev); g = torch.randn(1000, device=dev) * 1e-3
+        pt = prm.clone().requires_grad_(True); opt = torch.optim.Adam([pt], lr=1e-4, eps=1e-4)
+        m = torch.zeros_like(prm); v = torch.zeros_like(prm); mine = prm.clone()
+        for step in range(1, 4):
+            pt.grad = g.clone() * step; opt.step()
+            gg = g * step * 2.0
+            _lib.call("mtbc_adam_step", ops.ptr(mine), ops.ptr(gg), ops.ptr(m), ops.ptr(v), 1000, C.c_float(1e-4),
+                      C.c_float(0.9), C.c_float(0.999), C.c_float(1e-4), C.c_float(0.5), step, None)
+        report("adam 3 steps (grad_scale 0.5)", mine - prm, pt.detach() - prm, tol=2e-3)
+
+    run_case(fn, name)
+
+
+GROUPS = ["fwd_identity", "fwd", "dgrad", "wgrad", "convT", "first", "norm", "heads", "loss"]
 
 
 def run_group(group):
@@ -291,6 +461,16 @@ def run_group(group):
     elif group == "first":
         first_conv_case(2, 32, 32, 24)
         first_conv_case(2, 32, 32, 32)
+    elif group == "heads":
+        head1x1_case(2, 32, 32, 24)
+        head1x1_case(2, 16, 16, 16)
+        dshead_case(2, 8, 8, 128, 8)
+        dshead_case(2, 16, 16, 64, 4)
+        dshead_case(3, 16, 16, 32, 2)
+        gap_fc_case(3, 4, 4, 512)
+        flat_fc_case(3, 16, 16, 256)
+    elif group == "loss":
+        loss_cases()
     elif group == "norm":
         norm_case(2, 32, 32, 24, True, True)
         norm_case(2, 16, 16, 96, True, False)
