@@ -393,7 +393,7 @@ static PFN_tmapEncodeTiled get_encode() {
 bool tensor_map_available() { return get_encode() != nullptr; }
 
 // bf16 NHWC view -> 4D tensor map with box (kc, TW, TH, TN)
-static int encode_act(CUtensorMap* m, const mtbc_act_view& v, int kc, int TW, int TH, int TN) {
+int encode_act(CUtensorMap* m, const mtbc_act_view& v, int kc, int TW, int TH, int TN) {
   PFN_tmapEncodeTiled enc = get_encode();
   if (!enc) return set_error(MTBC_ERR_NO_DEVICE, "cuTensorMapEncodeTiled not available");
   if (v.C % 32 != 0 || (reinterpret_cast<uintptr_t>(v.ptr) & 15) != 0)
@@ -408,7 +408,7 @@ static int encode_act(CUtensorMap* m, const mtbc_act_view& v, int kc, int TW, in
   if (r != CUDA_SUCCESS) return set_error(MTBC_ERR_CUDA, "cuTensorMapEncodeTiled(act) failed: %d", (int)r);
   return 0;
 }
-static int encode_w(CUtensorMap* m, const void* w, int ktot, int nrows, int ntaps, int kc, int BN) {
+int encode_w(CUtensorMap* m, const void* w, int ktot, int nrows, int ntaps, int kc, int BN) {
   PFN_tmapEncodeTiled enc = get_encode();
   if (!enc) return set_error(MTBC_ERR_NO_DEVICE, "cuTensorMapEncodeTiled not available");
   cuuint64_t gdim[3] = {(cuuint64_t)ktot, (cuuint64_t)nrows, (cuuint64_t)ntaps};
@@ -465,6 +465,10 @@ struct WgradOp : public OpBase {
 
 int conv_gemm_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   if (!d || !out) return set_error(MTBC_ERR_INVALID, "null argument");
+  {
+    int rc = conv_halo_try_create(d, out);  // halo-tile kernel for 3x3 convs on large planes (conv_halo.cu)
+    if (rc <= 0) return rc;                  // 0 = created, < 0 = error, > 0 = not eligible -> generic kernel below
+  }
   if (d->nviews < 1 || d->nviews > MTBC_MAX_VIEWS || d->nseg < 1 || d->nseg > MTBC_MAX_SEGS)
     return set_error(MTBC_ERR_INVALID, "conv_gemm: bad nviews/nseg (%d, %d)", d->nviews, d->nseg);
   if (d->ncols % 32 != 0) return set_error(MTBC_ERR_INVALID, "conv_gemm: ncols %% 32 != 0");
@@ -535,6 +539,10 @@ int conv_gemm_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
 
 int wgrad_create(const mtbc_wgrad_desc* d, OpBase** out) {
   if (!d || !out) return set_error(MTBC_ERR_INVALID, "null argument");
+  {
+    int rc = wgrad_halo_try_create(d, out);
+    if (rc <= 0) return rc;
+  }
   if (d->a_nviews < 1 || d->a_nviews > 4 || d->b_nviews < 1 || d->b_nviews > 4 || d->ntaps < 1 || d->ntaps > 9)
     return set_error(MTBC_ERR_INVALID, "wgrad: bad view/tap counts");
   WgradOp* op = new WgradOp();

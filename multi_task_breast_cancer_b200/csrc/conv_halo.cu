@@ -1,0 +1,519 @@
+// Halo-tile 3x3 convolution kernels for sm_100a (large planes: H % 16 == 0, W % 8 == 0).
+//
+// The generic kernels of conv_gemm.cu fetch one 128-pixel box per (tap, source chunk): every input pixel crosses
+// L2 -> SM nine times and the 24/48-channel full-resolution layers of U-Net++ end up L2-bound.  Here one TMA load
+// brings the (16+2) x (8+2) pixel halo of an 8x16 output tile into shared memory ONCE per source chunk and the nine taps
+// are nine UMMA descriptors that start at different rows of that same tile (row pitch 10 pixels -> 8-row group stride
+// SBO = 10 rows).  tools/exp_swizzle.cu verified on a B200 that tcgen05 applies the 64B/128B swizzle on absolute
+// shared-memory address bits, so a descriptor whose start is shifted by whole rows (base_offset = 0) reads a
+// TMA-written swizzled tile correctly, for K-major and MN-major operands alike.
+//
+//  * conv_halo_kernel  (forward / data gradient): persistent CTAs, weights of the layer RESIDENT in shared memory,
+//    multi-stage halo ring, two TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+//  * wgrad_halo_kernel (weight gradient): per CTA one 32-channel chunk of one source; the three horizontal taps of a
+//    kernel row are stacked along M (they are the same halo rows shifted by one pixel = leading-dimension offset of one
+//    row), so 9 taps cost 3 MMA groups instead of 9 and no M lane is wasted on padding.
+#include "ptx.cuh"
+#include "internal.h"
+#include <stdlib.h>
+#include <string.h>
+
+namespace mtbc {
+
+constexpr int kHaloW = 10;   // 8 + 2
+constexpr int kHaloH = 18;   // 16 + 2
+constexpr int kHaloRows = kHaloW * kHaloH;  // 180
+
+// ================================================================================================ forward / dgrad
+struct HaloSrc {
+  int16_t nchunk, kc;   // chunks of kc channels
+  int32_t wk0;          // first column in the packed weight row
+  int32_t b_off;        // byte offset of this source's first resident weight block inside one tap plane
+};
+
+struct ConvHaloParams {
+  CUtensorMap amap[MTBC_MAX_VIEWS];
+  CUtensorMap wmap[2];
+  HaloSrc src[MTBC_MAX_VIEWS];
+  int32_t nsrc;
+  int32_t W, H, N, tiles_w, tiles_h, n_mtiles;
+  int32_t BN, tmem_cols, stages, a_stage_bytes, b_tap_bytes, b_total_bytes;
+  int32_t out_C, accumulate, stat_C;
+  __nv_bfloat16* out;
+  const float* bias;
+  float* stat_sum;
+  float* stat_sq;
+};
+
+constexpr int kHaloMaxStages = 8;
+
+__global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t s_afull[kHaloMaxStages], s_aempty[kHaloMaxStages];
+  __shared__ uint64_t s_bfull, s_accfull[2], s_accempty[2];
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_stat[2][2][256];  // [accumulator buffer][sum|sumsq][col]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_b = smem;                       // resident weights: [9 taps][source][chunk][BN x kc]
+  uint8_t* smem_a = smem + p.b_total_bytes;     // halo ring
+  const int ntile = blockIdx.y;
+  const int BN = p.BN;
+
+  for (int i = tid; i < 2 * 2 * 256; i += 192) (&s_stat[0][0][0])[i] = 0.f;
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&s_afull[s], 1); mbar_init(&s_aempty[s], 1); }
+    mbar_init(&s_bfull, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&s_accfull[b], 1); mbar_init(&s_accempty[b], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&s_tmem, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ producer: weights once, then halo tiles
+      mbar_arrive_expect_tx(&s_bfull, static_cast<uint32_t>(p.b_total_bytes));
+      for (int tap = 0; tap < 9; ++tap)
+        for (int s = 0; s < p.nsrc; ++s) {
+          const HaloSrc sc = p.src[s];
+          const CUtensorMap* wm = &p.wmap[sc.kc == 64 ? 1 : 0];
+          for (int ch = 0; ch < sc.nchunk; ++ch)
+            tma_load_3d(smem_b + tap * p.b_tap_bytes + sc.b_off + ch * (BN * sc.kc * 2), wm, &s_bfull,
+                        sc.wk0 + ch * sc.kc, ntile * BN, tap);
+        }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.n_mtiles; t += gridDim.x) {
+        const int w0 = (t % p.tiles_w) * 8;
+        const int h0 = ((t / p.tiles_w) % p.tiles_h) * 16;
+        const int n = t / (p.tiles_w * p.tiles_h);
+        for (int s = 0; s < p.nsrc; ++s) {
+          const HaloSrc sc = p.src[s];
+          const uint32_t bytes = static_cast<uint32_t>(kHaloRows * sc.kc * 2);
+          for (int ch = 0; ch < sc.nchunk; ++ch) {
+            mbar_wait(&s_aempty[stage], phase ^ 1u);
+            mbar_arrive_expect_tx(&s_afull[stage], bytes);
+            tma_load_4d(smem_a + stage * p.a_stage_bytes, &p.amap[s], &s_afull[stage], ch * sc.kc, w0 - 1, h0 - 1, n);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ MMA issuer
+      const uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      mbar_wait(&s_bfull, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < p.n_mtiles; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&s_accempty[buf], acc_phase ^ 1u);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + static_cast<uint32_t>(buf * BN);
+        uint32_t accumulate = 0;
+        for (int s = 0; s < p.nsrc; ++s) {
+          const HaloSrc sc = p.src[s];
+          const uint32_t rowb = sc.kc * 2u;
+          const uint32_t layout = sc.kc == 64 ? 2u : 4u;
+          for (int ch = 0; ch < sc.nchunk; ++ch) {
+            mbar_wait(&s_afull[stage], phase);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(smem_a + stage * p.a_stage_bytes);
+            const uint32_t b_base = smem_u32(smem_b) + sc.b_off + ch * (BN * sc.kc * 2);
+            for (int tap = 0; tap < 9; ++tap) {
+              const int dh = tap / 3, dw = tap - dh * 3;  // already offset by +1 (halo origin)
+              const uint32_t a_tap = a_base + (dh * kHaloW + dw) * rowb;
+              const uint32_t b_tap = b_base + tap * p.b_tap_bytes;
+              for (int k = 0; k < sc.kc / 16; ++k) {
+                const uint64_t da = umma_smem_desc(a_tap + k * 32, 16, kHaloW * rowb, layout);
+                const uint64_t db = umma_smem_desc(b_tap + k * 32, 16, 8 * rowb, layout);
+                umma_bf16(d_addr, da, db, idesc, accumulate);
+                accumulate = 1;
+              }
+            }
+            umma_commit(&s_aempty[stage]);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+        umma_commit(&s_accfull[buf]);
+      }
+    }
+  } else {
+    // -------------------------------------------------------------- epilogue warps 2..5 (TMEM lane quarter = warp % 4)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int tw = row & 7, th = row >> 3;
+    const bool do_stats = (p.stat_sum != nullptr);
+    const int etid = tid - 64;  // 0..127
+    int it = 0;
+    for (int t = blockIdx.x; t < p.n_mtiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int w = (t % p.tiles_w) * 8 + tw;
+      const int h = ((t / p.tiles_w) % p.tiles_h) * 16 + th;
+      const int n = t / (p.tiles_w * p.tiles_h);
+      mbar_wait(&s_accfull[buf], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
+      __nv_bfloat16* dst_row = p.out + ((static_cast<int64_t>(n) * p.H + h) * p.W + w) * p.out_C + ntile * BN;
+      for (int c = 0; c < BN; c += 16) {
+        float v[16];
+        tmem_ld16(taddr + c, v);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + ntile * BN + c + i);
+        }
+        if (do_stats) {
+          float sq[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) sq[i] = v[i] * v[i];
+          const float cs = warp_colsum16(v, lane);
+          const float cq = warp_colsum16(sq, lane);
+          if ((lane & 1) == 0) {
+            const int cc = c + col16_of_lane(lane);
+            atomicAdd(&s_stat[buf][0][cc], cs);
+            atomicAdd(&s_stat[buf][1][cc], cq);
+          }
+        }
+        uint4* d4 = reinterpret_cast<uint4*>(dst_row + c);
+        if (p.accumulate) {
+          const uint4 o0 = d4[0], o1 = d4[1];
+          const uint32_t ou[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 f = unpack_bf16x2(ou[i]);
+            v[2 * i] += f.x;
+            v[2 * i + 1] += f.y;
+          }
+        }
+        uint4 r0, r1;
+        r0.x = pack_bf16x2(v[0], v[1]); r0.y = pack_bf16x2(v[2], v[3]); r0.z = pack_bf16x2(v[4], v[5]); r0.w = pack_bf16x2(v[6], v[7]);
+        r1.x = pack_bf16x2(v[8], v[9]); r1.y = pack_bf16x2(v[10], v[11]); r1.z = pack_bf16x2(v[12], v[13]); r1.w = pack_bf16x2(v[14], v[15]);
+        d4[0] = r0;
+        d4[1] = r1;
+      }
+      // accumulator fully read: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_accempty[buf]);
+      if (do_stats) {
+        // the 4 epilogue warps of this tile combine their column sums, then one atomic per column
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = etid; i < BN; i += 128) {
+          const int64_t o = static_cast<int64_t>(n) * p.stat_C + ntile * BN + i;
+          atomicAdd(p.stat_sum + o, s_stat[buf][0][i]);
+          atomicAdd(p.stat_sq + o, s_stat[buf][1][i]);
+          s_stat[buf][0][i] = 0.f;
+          s_stat[buf][1][i] = 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ================================================================================================ weight gradient
+struct WgradHaloParams {
+  CUtensorMap amap;       // x source, box (32, 10, 18, 1), 64B swizzle
+  CUtensorMap bmap;       // dy, box (b_kc, 8, 16, 1)
+  int32_t a_C;            // padded channels of the source
+  int32_t b_kc, b_boxes;  // dy boxes per N tile
+  int32_t BN, n_tiles, tmem_cols, stages;
+  int32_t tiles_w, tiles_h, n_ptiles, splits;
+  int32_t a_bytes, b_bytes, stage_bytes, b_box_bytes;
+  int32_t n_rows, ld_k, k0;
+  float* dw_acc;
+};
+
+__global__ void __launch_bounds__(128) wgrad_halo_kernel(const __grid_constant__ WgradHaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t s_full[kHaloMaxStages], s_empty[kHaloMaxStages];
+  __shared__ uint64_t s_accum;
+  __shared__ uint32_t s_tmem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int split = blockIdx.x, chunk = blockIdx.y, ntile = blockIdx.z;
+  const int BN = p.BN;
+  const int per = (p.n_ptiles + p.splits - 1) / p.splits;
+  const int pt_begin = split * per;
+  const int pt_end = min(p.n_ptiles, pt_begin + per);
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
+    mbar_init(&s_accum, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&s_tmem, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+
+  if (pt_end > pt_begin) {
+    if (warp == 0 && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = pt_begin; pt < pt_end; ++pt) {
+        const int w0 = (pt % p.tiles_w) * 8;
+        const int h0 = ((pt / p.tiles_w) % p.tiles_h) * 16;
+        const int n = pt / (p.tiles_w * p.tiles_h);
+        mbar_wait(&s_empty[stage], phase ^ 1u);
+        uint8_t* a_dst = smem + stage * p.stage_bytes;
+        uint8_t* b_dst = a_dst + p.a_bytes;
+        mbar_arrive_expect_tx(&s_full[stage], static_cast<uint32_t>(kHaloRows * 64 + p.b_bytes));
+        tma_load_4d(a_dst, &p.amap, &s_full[stage], chunk * 32, w0 - 1, h0 - 1, n);
+        for (int b = 0; b < p.b_boxes; ++b)
+          tma_load_4d(b_dst + b * p.b_box_bytes, &p.bmap, &s_full[stage], ntile * BN + b * p.b_kc, w0, h0, n);
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    } else if (warp == 1 && lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
+      const uint32_t b_rowb = p.b_kc * 2u;
+      const uint32_t b_layout = p.b_kc == 64 ? 2u : 4u;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = pt_begin; pt < pt_end; ++pt) {
+        mbar_wait(&s_full[stage], phase);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem + stage * p.stage_bytes);
+        const uint32_t b_base = a_base + p.a_bytes;
+        for (int g = 0; g < 3; ++g) {      // kernel row dh = g - 1; M = [dw=-1 | dw=0 | dw=+1 | unused] x 32 channels
+          for (int j = 0; j < 8; ++j) {    // 16 pixels = tile rows 2j, 2j+1
+            const uint32_t a_addr = a_base + ((2 * j + g) * kHaloW) * 64;
+            const uint64_t da = umma_smem_desc(a_addr, 64, kHaloW * 64, 4u);
+            const uint64_t db = umma_smem_desc(b_base + j * 16 * b_rowb, p.b_box_bytes, 8 * b_rowb, b_layout);
+            umma_bf16(tmem_base + static_cast<uint32_t>(g * BN), da, db, idesc, (pt > pt_begin || j > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&s_empty[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(&s_accum);
+    }
+    __syncwarp();
+    mbar_wait(&s_accum, 0);
+    tc_fence_after();
+    __syncwarp();
+
+    const int m = warp * 32 + lane;  // warp = horizontal tap (dw + 1), lane = channel inside the chunk
+    const int ci = chunk * 32 + lane;
+    const bool valid = (warp < 3) && (ci < p.a_C);
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    for (int g = 0; g < 3; ++g) {
+      const int tap = g * 3 + warp;
+      for (int c = 0; c < BN; c += 16) {
+        float v[16];
+        tmem_ld16(taddr + g * BN + c, v);
+        if (valid) {
+          float* dst = p.dw_acc + (static_cast<int64_t>(tap) * p.n_rows + ntile * BN + c) * p.ld_k + p.k0 + ci;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) atomicAdd(dst + static_cast<int64_t>(i) * p.ld_k, v[i]);
+        }
+      }
+    }
+    (void)m;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ================================================================================================ host side
+static int tmem_cols_pow2(int n) { int c = 32; while (c < n) c <<= 1; return c; }
+static bool halo_disabled() { const char* e = getenv("MTBC_NO_HALO"); return e && e[0] == '1'; }
+static int sm_count() {
+  static int n = 0;
+  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+  return n;
+}
+
+struct ConvHaloOp : public OpBase {
+  ConvHaloParams p;
+  dim3 grid;
+  int smem_bytes;
+  double flops;
+  int launch(cudaStream_t st) override {
+    conv_halo_kernel<<<grid, 192, smem_bytes, st>>>(p);
+    return check_launch("conv_halo_kernel");
+  }
+  double op_flops() const override { return flops; }
+};
+
+struct WgradHaloOp : public OpBase {
+  WgradHaloParams p;
+  dim3 grid;
+  int smem_bytes;
+  double flops;
+  int launch(cudaStream_t st) override {
+    wgrad_halo_kernel<<<grid, 128, smem_bytes, st>>>(p);
+    return check_launch("wgrad_halo_kernel");
+  }
+  double op_flops() const override { return flops; }
+};
+
+int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
+  if (halo_disabled()) return 1;
+  if (d->epi_mode != 0 || d->nviews < 1 || d->nviews > MTBC_MAX_VIEWS || d->nseg != 9 * d->nviews) return 1;
+  if (d->H % 16 != 0 || d->W % 8 != 0 || d->w_ntaps != 9 || d->ncols % 32 != 0) return 1;
+  // every view must appear with the full 3x3 stencil, tap index = (dh+1)*3 + (dw+1), one weight column offset
+  int wk0[MTBC_MAX_VIEWS];
+  int seen[MTBC_MAX_VIEWS];
+  for (int v = 0; v < d->nviews; ++v) { wk0[v] = -1; seen[v] = 0; }
+  for (int s = 0; s < d->nseg; ++s) {
+    const mtbc_gemm_seg& g = d->seg[s];
+    if (g.view < 0 || g.view >= d->nviews || g.dh < -1 || g.dh > 1 || g.dw < -1 || g.dw > 1) return 1;
+    if (g.wtap != (g.dh + 1) * 3 + (g.dw + 1)) return 1;
+    if (wk0[g.view] >= 0 && wk0[g.view] != g.wk0) return 1;
+    wk0[g.view] = g.wk0;
+    seen[g.view] |= 1 << g.wtap;
+  }
+  int kused = 0;
+  for (int v = 0; v < d->nviews; ++v) {
+    if (seen[v] != 0x1FF) return 1;
+    const mtbc_act_view& a = d->views[v];
+    if (a.W != d->W || a.H != d->H || a.N != d->N || a.C % 32 != 0) return 1;
+    kused += a.C;
+  }
+  // N tile such that the layer's weights stay resident in shared memory
+  int BN = 0;
+  for (int bn = 16; bn <= 256 && bn <= d->ncols; bn += 16)
+    if (d->ncols % bn == 0 && 9 * bn * kused * 2 <= 120 * 1024) BN = bn;
+  if (BN < 32 && BN != d->ncols) return 1;
+  if (d->stat_sum && false) return 1;
+
+  ConvHaloOp* op = new ConvHaloOp();
+  ConvHaloParams& p = op->p;
+  memset(&p, 0, sizeof(p));
+  p.nsrc = d->nviews;
+  int kcmax = 32, b_off = 0;
+  bool use32 = false, use64 = false;
+  for (int v = 0; v < d->nviews; ++v) {
+    const mtbc_act_view& a = d->views[v];
+    const int kc = (a.C % 64 == 0 && wk0[v] % 64 == 0) ? 64 : 32;
+    if (kc > kcmax) kcmax = kc;
+    (kc == 64 ? use64 : use32) = true;
+    p.src[v].kc = (int16_t)kc; p.src[v].nchunk = (int16_t)(a.C / kc); p.src[v].wk0 = wk0[v]; p.src[v].b_off = b_off;
+    b_off += a.C * BN * 2;
+    if (wk0[v] % 32 != 0 || wk0[v] + a.C > d->w_ktot) { delete op; return set_error(MTBC_ERR_INVALID, "conv_halo: weight columns out of range"); }
+    int rc = encode_act(&p.amap[v], a, kc, kHaloW, kHaloH, 1);
+    if (rc) { delete op; return rc; }
+  }
+  p.b_tap_bytes = b_off;
+  p.b_total_bytes = 9 * b_off;
+  if (use32) { int rc = encode_w(&p.wmap[0], d->wpack, d->w_ktot, d->ncols, 9, 32, BN); if (rc) { delete op; return rc; } }
+  if (use64) { int rc = encode_w(&p.wmap[1], d->wpack, d->w_ktot, d->ncols, 9, 64, BN); if (rc) { delete op; return rc; } }
+  p.W = d->W; p.H = d->H; p.N = d->N;
+  p.tiles_w = d->W / 8; p.tiles_h = d->H / 16;
+  p.n_mtiles = p.tiles_w * p.tiles_h * d->N;
+  p.BN = BN;
+  p.tmem_cols = tmem_cols_pow2(2 * BN);
+  p.a_stage_bytes = ((kHaloRows * kcmax * 2) + 1023) & ~1023;
+  int total_chunks = 0;
+  for (int v = 0; v < d->nviews; ++v) total_chunks += p.src[v].nchunk;
+  int stages = (200 * 1024 - p.b_total_bytes) / p.a_stage_bytes;
+  if (stages > kHaloMaxStages) stages = kHaloMaxStages;
+  // with small resident weights keep the footprint below half an SM so two CTAs overlap each other's epilogues
+  const int half = 100 * 1024;
+  if (p.b_total_bytes + 3 * p.a_stage_bytes <= half) {
+    int s2 = (half - p.b_total_bytes) / p.a_stage_bytes;
+    if (s2 < stages) stages = s2;
+  }
+  if (stages < 2) { delete op; return 1; }
+  p.stages = stages;
+  op->smem_bytes = p.b_total_bytes + stages * p.a_stage_bytes + 1024;
+  const int ctas_per_sm = (op->smem_bytes + 6 * 1024) * 2 <= 227 * 1024 ? 2 : 1;
+  int gx = sm_count() * ctas_per_sm;
+  if (gx > p.n_mtiles) gx = p.n_mtiles;
+  p.out_C = d->out_C; p.accumulate = d->accumulate; p.stat_C = d->stat_C;
+  p.out = reinterpret_cast<__nv_bfloat16*>(d->out);
+  p.bias = d->bias; p.stat_sum = d->stat_sum; p.stat_sq = d->stat_sq;
+  op->grid = dim3(gx, d->ncols / BN, 1);
+  op->flops = 2.0 * double(d->N) * d->H * d->W * double(d->ncols) * kused * 9.0;
+  cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  if (e != cudaSuccess) { delete op; return set_error(MTBC_ERR_CUDA, "cudaFuncSetAttribute(conv_halo): %s", cudaGetErrorString(e)); }
+  *out = op;
+  return 0;
+}
+
+int wgrad_halo_try_create(const mtbc_wgrad_desc* d, OpBase** out) {
+  if (halo_disabled()) return 1;
+  if (d->a_nviews != 1 || d->b_nviews != 1 || d->ntaps != 9) return 1;
+  if (d->H % 16 != 0 || d->W % 8 != 0) return 1;
+  for (int t = 0; t < 9; ++t) {
+    const mtbc_wgrad_tap& tp = d->taps[t];
+    if (tp.a_view != 0 || tp.b_view != 0 || tp.a_dh != t / 3 - 1 || tp.a_dw != t % 3 - 1) return 1;
+  }
+  const mtbc_act_view& a = d->a_views[0];
+  const mtbc_act_view& b = d->b_views[0];
+  if (a.C % 32 != 0 || b.C % 32 != 0 || a.W != d->W || a.H != d->H || a.N != d->N) return 1;
+  const int b_kc = (b.C % 64 == 0) ? 64 : 32;
+  int BN = 0;
+  for (int bn = b_kc; bn <= 128 && bn <= b.C; bn += b_kc)
+    if (b.C % bn == 0 && bn % 16 == 0) BN = bn;
+  if (BN == 0) return 1;
+  WgradHaloOp* op = new WgradHaloOp();
+  WgradHaloParams& p = op->p;
+  memset(&p, 0, sizeof(p));
+  int rc = encode_act(&p.amap, a, 32, kHaloW, kHaloH, 1);
+  if (rc) { delete op; return rc; }
+  rc = encode_act(&p.bmap, b, b_kc, 8, 16, 1);
+  if (rc) { delete op; return rc; }
+  p.a_C = a.C; p.b_kc = b_kc; p.BN = BN; p.n_tiles = b.C / BN; p.b_boxes = BN / b_kc;
+  p.tmem_cols = tmem_cols_pow2(3 * BN);
+  p.tiles_w = d->W / 8; p.tiles_h = d->H / 16;
+  p.n_ptiles = p.tiles_w * p.tiles_h * d->N;
+  p.a_bytes = ((kHaloRows * 64) + 1023) & ~1023;  // 12 KB
+  p.b_box_bytes = 128 * b_kc * 2;
+  p.b_bytes = p.b_boxes * p.b_box_bytes;
+  p.stage_bytes = p.a_bytes + p.b_bytes;
+  int stages = (96 * 1024) / p.stage_bytes;  // <= half an SM: two CTAs hide each other's epilogue / start-up
+  if (stages > kHaloMaxStages) stages = kHaloMaxStages;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  op->smem_bytes = stages * p.stage_bytes + 1024;
+  p.n_rows = d->n_rows; p.ld_k = d->ld_k; p.k0 = d->k0; p.dw_acc = d->dw_acc;
+  const int chunks = a.C / 32;
+  const int base = chunks * p.n_tiles;
+  int splits = d->splits;
+  if (splits <= 0) {
+    splits = (2 * sm_count() + base - 1) / base;
+    int maxs = (p.n_ptiles + 3) / 4; if (maxs < 1) maxs = 1;
+    if (splits > maxs) splits = maxs;
+  }
+  if (splits > p.n_ptiles) splits = p.n_ptiles;
+  if (splits < 1) splits = 1;
+  p.splits = splits;
+  op->grid = dim3(splits, chunks, p.n_tiles);
+  op->flops = 2.0 * double(d->N) * d->H * d->W * double(a.C) * double(b.C) * 9.0;
+  cudaError_t e = cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  if (e != cudaSuccess) { delete op; return set_error(MTBC_ERR_CUDA, "cudaFuncSetAttribute(wgrad_halo): %s", cudaGetErrorString(e)); }
+  *out = op;
+  return 0;
+}
+
+}  // namespace mtbc

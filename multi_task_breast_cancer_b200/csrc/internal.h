@@ -1,6 +1,7 @@
 // Internal (non-ABI) declarations shared by the translation units of libmtbc.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda.h>
 #include "../../include/mtbc.h"
 
 namespace mtbc {
@@ -19,6 +20,12 @@ struct OpBase {
 int conv_gemm_create(const mtbc_conv_gemm_desc* d, OpBase** out);
 int wgrad_create(const mtbc_wgrad_desc* d, OpBase** out);
 bool tensor_map_available();
+// > 0: not eligible (caller falls back to the generic kernel), 0: created, < 0: error
+int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out);
+int wgrad_halo_try_create(const mtbc_wgrad_desc* d, OpBase** out);
+// tensor-map encoders (conv_gemm.cu): bf16 NHWC view with box (kc, bw, bh, bn); packed weights with box (kc, BN, 1)
+int encode_act(CUtensorMap* m, const mtbc_act_view& v, int kc, int bw, int bh, int bn);
+int encode_w(CUtensorMap* m, const void* w, int ktot, int nrows, int ntaps, int kc, int BN);
 
 inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
