@@ -132,6 +132,28 @@ int mtbc_unpack_conv_wgrad(const float* acc, int32_t rows, int32_t ld, int32_t k
 int mtbc_unpack_convT_wgrad(const float* acc, int32_t rows, int32_t ld, float* grad, int32_t Cin, int32_t Cout,
                             int32_t k, int32_t add, void* stream);
 
+/* Batched form of the five parameter-side jobs above plus mtbc_copy_f32: one launch runs a whole table (a U-Net++ step
+ * has ~250 of them; nn.Module parameters stay in PyTorch layout, MTUNetPlusPlus.py:47-87).  Integer arguments, in
+ * the order of the single-job entry points:
+ *   COPY_F32      i = {n}                                                            src -> dst0
+ *   PACK_CONV     i = {Cout, Cin, ksz, c_begin, c_count, wf_rows, wf_ld, wf_k0, wd_rows, wd_ld}   src=w dst0=wf dst1=wd|NULL
+ *   PACK_CONVT    i = {Cin, Cout, k, cp, wf_ld, wd_rows, wd_ld}                      src=w dst0=wf dst1=wd|NULL
+ *   UNPACK_CONV   i = {rows, ld, k0, Cout, Cin, ksz, c_begin, c_count, add}          src=acc dst0=grad
+ *   UNPACK_CONVT  i = {rows, ld, Cin, Cout, k, add}                                  src=acc dst0=grad
+ * The table is copied to the device at creation; launch with mtbc_op_launch. */
+enum mtbc_job_kind {
+  MTBC_JOB_COPY_F32 = 0, MTBC_JOB_PACK_CONV = 1, MTBC_JOB_PACK_CONVT = 2, MTBC_JOB_UNPACK_CONV = 3,
+  MTBC_JOB_UNPACK_CONVT = 4
+};
+typedef struct {
+  int32_t kind;
+  int32_t i[11];
+  const void* src;
+  void* dst0;
+  void* dst1;
+} mtbc_param_job;
+int mtbc_param_jobs_create(const mtbc_param_job* jobs, int32_t n, mtbc_op** out);
+
 /* ------------------------------------------------------------------------------------------------------------- */
 /* First layer: Conv2d 3x3 with Cin <= 4 on the fp32 NCHW input image (K = 9*Cin is too small for a tensor tile).  */
 /* Replaces conv_0_0.conv_0 / encoder1.ConvInNormLRelu1.Conv forward + weight gradient (no data gradient: the image

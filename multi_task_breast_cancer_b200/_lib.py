@@ -44,12 +44,20 @@ class WgradDesc(C.Structure):
                 ("dw_acc", c_vp), ("n_rows", c_i32), ("ld_k", c_i32), ("k0", c_i32), ("splits", c_i32)]
 
 
+class ParamJob(C.Structure):
+    _fields_ = [("kind", c_i32), ("i", c_i32 * 11), ("src", c_vp), ("dst0", c_vp), ("dst1", c_vp)]
+
+
+JOB_COPY_F32, JOB_PACK_CONV, JOB_PACK_CONVT, JOB_UNPACK_CONV, JOB_UNPACK_CONVT = range(5)
+
+
 # name -> argtypes (return type is int unless listed in _RESTYPES)
 _SIGS = {
     "mtbc_abi_version": [],
     "mtbc_device_check": [],
     "mtbc_conv_gemm_create": [C.POINTER(ConvGemmDesc), C.POINTER(c_vp)],
     "mtbc_wgrad_create": [C.POINTER(WgradDesc), C.POINTER(c_vp)],
+    "mtbc_param_jobs_create": [C.POINTER(ParamJob), c_i32, C.POINTER(c_vp)],
     "mtbc_op_launch": [c_vp, c_vp],
     "mtbc_ops_launch": [C.POINTER(c_vp), c_i32, c_vp],
     "mtbc_op_destroy": [c_vp],

@@ -60,6 +60,13 @@ int mtbc_wgrad_create(const mtbc_wgrad_desc* d, mtbc_op** out) {
   *out = new mtbc_op{b};
   return 0;
 }
+int mtbc_param_jobs_create(const mtbc_param_job* jobs, int32_t n, mtbc_op** out) {
+  mtbc::OpBase* b = nullptr;
+  int rc = mtbc::param_jobs_create(jobs, n, &b);
+  if (rc) return rc;
+  *out = new mtbc_op{b};
+  return 0;
+}
 int mtbc_op_launch(mtbc_op* op, void* stream) {
   if (!op || !op->impl) return mtbc::set_error(MTBC_ERR_INVALID, "null op");
   return op->impl->launch(static_cast<cudaStream_t>(stream));

@@ -102,19 +102,20 @@ __global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ 
     uint32_t accumulate = 0;
     for (int s = 0; s < p.nseg; ++s) {
       const SegDev sg = p.seg[s];
-      const uint32_t sbo = 8u * sg.kc * 2u;
-      const uint32_t layout = sg.kc == 64 ? 2u : 4u;
+      const uint32_t hi = umma_desc_hi(8u * sg.kc * 2u, sg.kc == 64 ? 2u : 4u);
       for (int ch = 0; ch < sg.nchunk; ++ch) {
         mbar_wait(&s_full[stage], phase);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + stage * p.stage_bytes);
-        const uint32_t b_addr = a_addr + p.a_stage_bytes;
-        for (int k = 0; k < sg.kc / 16; ++k) {
-          const uint64_t da = umma_smem_desc(a_addr + k * 32, 16, sbo, layout);
-          const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, sbo, layout);
-          umma_bf16(tmem_base, da, db, idesc, accumulate);
-          accumulate = 1;
+        const uint32_t a_lo = umma_desc_lo(a_addr, 16), b_lo = umma_desc_lo(a_addr + p.a_stage_bytes, 16);
+        // low descriptor words advance by compile-time steps: keeps the issuing lane at the tensor pipe's floor
+        umma_bf16_lohi(tmem_base, a_lo, hi, b_lo, hi, idesc, accumulate);
+        umma_bf16_lohi(tmem_base, a_lo + 2, hi, b_lo + 2, hi, idesc, 1u);
+        if (sg.kc == 64) {
+          umma_bf16_lohi(tmem_base, a_lo + 4, hi, b_lo + 4, hi, idesc, 1u);
+          umma_bf16_lohi(tmem_base, a_lo + 6, hi, b_lo + 6, hi, idesc, 1u);
         }
+        accumulate = 1;
         umma_commit(&s_empty[stage]);
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
@@ -307,9 +308,9 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const __grid_constant__ Wgra
       }
     } else if (warp == 1 && lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
-      const uint32_t a_sbo = 8u * p.a_kc * 2u, b_sbo = 8u * p.b_kc * 2u;
-      const uint32_t a_layout = p.a_kc == 64 ? 2u : 4u, b_layout = p.b_kc == 64 ? 2u : 4u;
-      const uint32_t a_kstep = 16u * p.a_kc * 2u, b_kstep = 16u * p.b_kc * 2u;  // 16 pixel rows
+      const uint32_t a_hi = umma_desc_hi(8u * p.a_kc * 2u, p.a_kc == 64 ? 2u : 4u);
+      const uint32_t b_hi = umma_desc_hi(8u * p.b_kc * 2u, p.b_kc == 64 ? 2u : 4u);
+      const uint32_t a_k16 = 2u * p.a_kc, b_k16 = 2u * p.b_kc;  // 16 pixel rows, in 16-byte units
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int cur_b = -1;
@@ -327,13 +328,12 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const __grid_constant__ Wgra
           }
           mbar_wait(&s_afull[sa], pa);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + sa * p.a_stage_bytes);
-          const uint32_t b_addr = smem_u32(smem_b + cur_b * p.b_stage_bytes);
+          const uint32_t a_lo = umma_desc_lo(smem_u32(smem_a + sa * p.a_stage_bytes), p.a_box_bytes);
+          const uint32_t b_lo = umma_desc_lo(smem_u32(smem_b + cur_b * p.b_stage_bytes), p.b_box_bytes);
           const uint32_t d_addr = tmem_base + static_cast<uint32_t>(t * BN);
+#pragma unroll
           for (int k = 0; k < 8; ++k) {  // 128 pixels / 16
-            const uint64_t da = umma_smem_desc(a_addr + k * a_kstep, p.a_box_bytes, a_sbo, a_layout);
-            const uint64_t db = umma_smem_desc(b_addr + k * b_kstep, p.b_box_bytes, b_sbo, b_layout);
-            umma_bf16(d_addr, da, db, idesc, (pt > pt_begin || k > 0) ? 1u : 0u);
+            umma_bf16_lohi(d_addr, a_lo + k * a_k16, a_hi, b_lo + k * b_k16, b_hi, idesc, (pt > pt_begin || k > 0) ? 1u : 0u);
           }
           umma_commit(&s_aempty[sa]);
           if (++sa == kWgAStages) { sa = 0; pa ^= 1u; }

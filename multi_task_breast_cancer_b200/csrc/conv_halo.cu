@@ -47,6 +47,27 @@ struct ConvHaloParams {
 
 constexpr int kHaloMaxStages = 8;
 
+// The 9 taps x KC/16 K-steps of one halo chunk, fully unrolled: only the low descriptor words change, by compile-time
+// (A) or per-kernel (B tap plane) offsets, so the single issuing lane stays at the tensor pipe's ~45-cycle
+// per-instruction floor (tools/exp_mma_rate2.cu) instead of ~160 cycles when descriptors are rebuilt in 64-bit.
+template <int KC>
+__device__ __forceinline__ void halo_issue_chunk(uint32_t d_addr, uint32_t a_lo, uint32_t b_lo, uint32_t b_tap16,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  constexpr uint32_t rowb = KC * 2u;
+  constexpr uint32_t layout = KC == 64 ? 2u : 4u;
+  const uint32_t a_hi = umma_desc_hi(kHaloW * rowb, layout);
+  const uint32_t b_hi = umma_desc_hi(8u * rowb, layout);
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const uint32_t a_t = a_lo + (((tap / 3) * kHaloW + (tap % 3)) * rowb >> 4);
+    const uint32_t b_t = b_lo + tap * b_tap16;
+#pragma unroll
+    for (int k = 0; k < KC / 16; ++k) {
+      umma_bf16_lohi(d_addr, a_t + 2 * k, a_hi, b_t + 2 * k, b_hi, idesc, (tap | k) ? 1u : accumulate);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t s_afull[kHaloMaxStages], s_aempty[kHaloMaxStages];
@@ -112,6 +133,7 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
       // ------------------------------------------------------------ MMA issuer
       const uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
       mbar_wait(&s_bfull, 0);
+      const uint32_t b_tap16 = static_cast<uint32_t>(p.b_tap_bytes) >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -124,24 +146,14 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
         uint32_t accumulate = 0;
         for (int s = 0; s < p.nsrc; ++s) {
           const HaloSrc sc = p.src[s];
-          const uint32_t rowb = sc.kc * 2u;
-          const uint32_t layout = sc.kc == 64 ? 2u : 4u;
           for (int ch = 0; ch < sc.nchunk; ++ch) {
             mbar_wait(&s_afull[stage], phase);
             tc_fence_after();
-            const uint32_t a_base = smem_u32(smem_a + stage * p.a_stage_bytes);
-            const uint32_t b_base = smem_u32(smem_b) + sc.b_off + ch * (BN * sc.kc * 2);
-            for (int tap = 0; tap < 9; ++tap) {
-              const int dh = tap / 3, dw = tap - dh * 3;  // already offset by +1 (halo origin)
-              const uint32_t a_tap = a_base + (dh * kHaloW + dw) * rowb;
-              const uint32_t b_tap = b_base + tap * p.b_tap_bytes;
-              for (int k = 0; k < sc.kc / 16; ++k) {
-                const uint64_t da = umma_smem_desc(a_tap + k * 32, 16, kHaloW * rowb, layout);
-                const uint64_t db = umma_smem_desc(b_tap + k * 32, 16, 8 * rowb, layout);
-                umma_bf16(d_addr, da, db, idesc, accumulate);
-                accumulate = 1;
-              }
-            }
+            const uint32_t a_lo = umma_desc_lo(smem_u32(smem_a + stage * p.a_stage_bytes), 16);
+            const uint32_t b_lo = umma_desc_lo(smem_u32(smem_b) + sc.b_off + ch * (BN * sc.kc * 2), 16);
+            if (sc.kc == 64) halo_issue_chunk<64>(d_addr, a_lo, b_lo, b_tap16, idesc, accumulate);
+            else halo_issue_chunk<32>(d_addr, a_lo, b_lo, b_tap16, idesc, accumulate);
+            accumulate = 1;
             umma_commit(&s_aempty[stage]);
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
@@ -291,20 +303,24 @@ __global__ void __launch_bounds__(128) wgrad_halo_kernel(const __grid_constant__
     } else if (warp == 1 && lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
       const uint32_t b_rowb = p.b_kc * 2u;
-      const uint32_t b_layout = p.b_kc == 64 ? 2u : 4u;
+      const uint32_t a_hi = umma_desc_hi(kHaloW * 64, 4u);
+      const uint32_t b_hi = umma_desc_hi(8 * b_rowb, p.b_kc == 64 ? 2u : 4u);
+      const uint32_t b_j16 = b_rowb;  // 16 pixel rows of the dy tile, in 16-byte units
       int stage = 0;
       uint32_t phase = 0;
       for (int pt = pt_begin; pt < pt_end; ++pt) {
         mbar_wait(&s_full[stage], phase);
         tc_fence_after();
         const uint32_t a_base = smem_u32(smem + stage * p.stage_bytes);
-        const uint32_t b_base = a_base + p.a_bytes;
+        const uint32_t a_lo = umma_desc_lo(a_base, 64);
+        const uint32_t b_lo = umma_desc_lo(a_base + p.a_bytes, p.b_box_bytes);
+        const uint32_t first = (pt > pt_begin) ? 1u : 0u;
+#pragma unroll
         for (int g = 0; g < 3; ++g) {      // kernel row dh = g - 1; M = [dw=-1 | dw=0 | dw=+1 | unused] x 32 channels
+#pragma unroll
           for (int j = 0; j < 8; ++j) {    // 16 pixels = tile rows 2j, 2j+1
-            const uint32_t a_addr = a_base + ((2 * j + g) * kHaloW) * 64;
-            const uint64_t da = umma_smem_desc(a_addr, 64, kHaloW * 64, 4u);
-            const uint64_t db = umma_smem_desc(b_base + j * 16 * b_rowb, p.b_box_bytes, 8 * b_rowb, b_layout);
-            umma_bf16(tmem_base + static_cast<uint32_t>(g * BN), da, db, idesc, (pt > pt_begin || j > 0) ? 1u : 0u);
+            umma_bf16_lohi(tmem_base + static_cast<uint32_t>(g * BN), a_lo + ((2 * j + g) * kHaloW) * 4, a_hi,
+                           b_lo + j * b_j16, b_hi, idesc, j > 0 ? 1u : first);
           }
         }
         umma_commit(&s_empty[stage]);

@@ -19,6 +19,7 @@ struct OpBase {
 
 int conv_gemm_create(const mtbc_conv_gemm_desc* d, OpBase** out);
 int wgrad_create(const mtbc_wgrad_desc* d, OpBase** out);
+int param_jobs_create(const mtbc_param_job* jobs, int n, OpBase** out);
 bool tensor_map_available();
 // > 0: not eligible (caller falls back to the generic kernel), 0: created, < 0: error
 int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out);

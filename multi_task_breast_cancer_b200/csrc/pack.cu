@@ -2,6 +2,7 @@
 // utilities.  All memory bound / tiny.
 #include "ptx.cuh"
 #include "internal.h"
+#include <vector>
 
 namespace mtbc {
 
@@ -68,6 +69,151 @@ __global__ void unpack_convT_wgrad_kernel(const float* __restrict__ acc, int row
     const float v = acc[(static_cast<int64_t>(q) * cp + co) * ld + ci];
     grad[i] = add ? (grad[i] + v) : v;
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------ batched jobs
+// One launch for all the small parameter-side jobs of a step (padded copies of bias/gamma/beta vectors, weight packs,
+// weight-gradient unpacks): a U-Net++ step has ~250 of them and as separate launches they cost more in launch gaps
+// than in work.  Block b handles kChunk consecutive elements of job chunk_job[b].
+constexpr int kChunk = 2048;
+
+struct ParamJobDev {
+  int32_t kind;
+  int32_t i[11];
+  const void* src;
+  void* dst0;
+  void* dst1;
+};
+
+__global__ void __launch_bounds__(256) param_jobs_kernel(const ParamJobDev* __restrict__ jobs,
+                                                         const int32_t* __restrict__ chunk_job,
+                                                         const int32_t* __restrict__ chunk_first) {
+  const ParamJobDev j = jobs[chunk_job[blockIdx.x]];
+  const int64_t begin = static_cast<int64_t>(blockIdx.x - chunk_first[blockIdx.x]) * kChunk;
+  if (j.kind == MTBC_JOB_COPY_F32) {
+    const int64_t n = j.i[0];
+    const float* src = static_cast<const float*>(j.src);
+    float* dst = static_cast<float*>(j.dst0);
+    for (int64_t e = begin + threadIdx.x; e < begin + kChunk && e < n; e += 256) dst[e] = src[e];
+  } else if (j.kind == MTBC_JOB_PACK_CONV) {
+    // i: Cout, Cin, ksz, c_begin, c_count, wf_rows, wf_ld, wf_k0, wd_rows, wd_ld ; element order (co, tap, cl)
+    const int Cin = j.i[1], taps = j.i[2] * j.i[2], c_begin = j.i[3], c_count = j.i[4];
+    const int64_t total = static_cast<int64_t>(j.i[0]) * c_count * taps;
+    const float* w = static_cast<const float*>(j.src);
+    __nv_bfloat16* wf = static_cast<__nv_bfloat16*>(j.dst0);
+    __nv_bfloat16* wd = static_cast<__nv_bfloat16*>(j.dst1);
+    for (int64_t e = begin + threadIdx.x; e < begin + kChunk && e < total; e += 256) {
+      const int cl = static_cast<int>(e % c_count);
+      const int tap = static_cast<int>((e / c_count) % taps);
+      const int co = static_cast<int>(e / (static_cast<int64_t>(c_count) * taps));
+      const __nv_bfloat16 b = __float2bfloat16(w[(static_cast<int64_t>(co) * Cin + c_begin + cl) * taps + tap]);
+      if (wf) wf[(static_cast<int64_t>(tap) * j.i[5] + co) * j.i[6] + j.i[7] + cl] = b;
+      if (wd) wd[(static_cast<int64_t>(taps - 1 - tap) * j.i[8] + cl) * j.i[9] + co] = b;
+    }
+  } else if (j.kind == MTBC_JOB_PACK_CONVT) {
+    // i: Cin, Cout, k, cp, wf_ld, wd_rows, wd_ld ; element order = parameter order (ci, co, q)
+    const int Cout = j.i[1], kk = j.i[2] * j.i[2], cp = j.i[3];
+    const int64_t total = static_cast<int64_t>(j.i[0]) * Cout * kk;
+    const float* w = static_cast<const float*>(j.src);
+    __nv_bfloat16* wf = static_cast<__nv_bfloat16*>(j.dst0);
+    __nv_bfloat16* wd = static_cast<__nv_bfloat16*>(j.dst1);
+    for (int64_t e = begin + threadIdx.x; e < begin + kChunk && e < total; e += 256) {
+      const int q = static_cast<int>(e % kk);
+      const int co = static_cast<int>((e / kk) % Cout);
+      const int ci = static_cast<int>(e / (static_cast<int64_t>(kk) * Cout));
+      const __nv_bfloat16 b = __float2bfloat16(w[e]);
+      if (wf) wf[(static_cast<int64_t>(q) * cp + co) * j.i[4] + ci] = b;
+      if (wd) wd[(static_cast<int64_t>(q) * j.i[5] + ci) * j.i[6] + co] = b;
+    }
+  } else if (j.kind == MTBC_JOB_UNPACK_CONV) {
+    // i: rows, ld, k0, Cout, Cin, ksz, c_begin, c_count, add ; element order (co, tap, cl)
+    const int rows = j.i[0], ld = j.i[1], k0 = j.i[2], Cin = j.i[4], taps = j.i[5] * j.i[5], c_begin = j.i[6],
+              c_count = j.i[7], add = j.i[8];
+    const int64_t total = static_cast<int64_t>(j.i[3]) * c_count * taps;
+    const float* acc = static_cast<const float*>(j.src);
+    float* grad = static_cast<float*>(j.dst0);
+    for (int64_t e = begin + threadIdx.x; e < begin + kChunk && e < total; e += 256) {
+      const int cl = static_cast<int>(e % c_count);
+      const int tap = static_cast<int>((e / c_count) % taps);
+      const int co = static_cast<int>(e / (static_cast<int64_t>(c_count) * taps));
+      const float v = acc[(static_cast<int64_t>(tap) * rows + co) * ld + k0 + cl];
+      float* g = grad + (static_cast<int64_t>(co) * Cin + c_begin + cl) * taps + tap;
+      *g = add ? (*g + v) : v;
+    }
+  } else if (j.kind == MTBC_JOB_UNPACK_CONVT) {
+    // i: rows, ld, Cin, Cout, k, add ; element order = parameter order (ci, co, q)
+    const int rows = j.i[0], ld = j.i[1], Cout = j.i[3], kk = j.i[4] * j.i[4], add = j.i[5];
+    const int cp = rows / kk;
+    const int64_t total = static_cast<int64_t>(j.i[2]) * Cout * kk;
+    const float* acc = static_cast<const float*>(j.src);
+    float* grad = static_cast<float*>(j.dst0);
+    for (int64_t e = begin + threadIdx.x; e < begin + kChunk && e < total; e += 256) {
+      const int q = static_cast<int>(e % kk);
+      const int co = static_cast<int>((e / kk) % Cout);
+      const int ci = static_cast<int>(e / (static_cast<int64_t>(kk) * Cout));
+      const float v = acc[(static_cast<int64_t>(q) * cp + co) * ld + ci];
+      grad[e] = add ? (grad[e] + v) : v;
+    }
+  }
+}
+
+struct ParamJobsOp : public OpBase {
+  ParamJobDev* d_jobs = nullptr;
+  int32_t* d_chunk_job = nullptr;
+  int32_t* d_chunk_first = nullptr;
+  int nblocks = 0;
+  ~ParamJobsOp() override {
+    cudaFree(d_jobs);
+    cudaFree(d_chunk_job);
+    cudaFree(d_chunk_first);
+  }
+  int launch(cudaStream_t st) override {
+    if (nblocks == 0) return 0;
+    param_jobs_kernel<<<nblocks, 256, 0, st>>>(d_jobs, d_chunk_job, d_chunk_first);
+    return check_launch("param_jobs_kernel");
+  }
+};
+
+static int64_t job_elems(const mtbc_param_job& j) {
+  switch (j.kind) {
+    case MTBC_JOB_COPY_F32: return j.i[0];
+    case MTBC_JOB_PACK_CONV: return static_cast<int64_t>(j.i[0]) * j.i[4] * j.i[2] * j.i[2];
+    case MTBC_JOB_PACK_CONVT: return static_cast<int64_t>(j.i[0]) * j.i[1] * j.i[2] * j.i[2];
+    case MTBC_JOB_UNPACK_CONV: return static_cast<int64_t>(j.i[3]) * j.i[7] * j.i[5] * j.i[5];
+    case MTBC_JOB_UNPACK_CONVT: return static_cast<int64_t>(j.i[2]) * j.i[3] * j.i[4] * j.i[4];
+    default: return -1;
+  }
+}
+
+int param_jobs_create(const mtbc_param_job* jobs, int n, OpBase** out) {
+  if (n < 0 || (n > 0 && !jobs) || !out) return set_error(MTBC_ERR_INVALID, "param_jobs: bad arguments");
+  std::vector<ParamJobDev> h(n);
+  std::vector<int32_t> cj, cf;
+  for (int a = 0; a < n; ++a) {
+    const int64_t e = job_elems(jobs[a]);
+    if (e < 0 || !jobs[a].src || !jobs[a].dst0) return set_error(MTBC_ERR_INVALID, "param_jobs: job %d is malformed", a);
+    h[a].kind = jobs[a].kind;
+    for (int k = 0; k < 11; ++k) h[a].i[k] = jobs[a].i[k];
+    h[a].src = jobs[a].src; h[a].dst0 = jobs[a].dst0; h[a].dst1 = jobs[a].dst1;
+    const int first = static_cast<int>(cj.size());
+    for (int64_t c = 0; c * kChunk < e; ++c) { cj.push_back(a); cf.push_back(first); }
+  }
+  ParamJobsOp* op = new ParamJobsOp();
+  op->nblocks = static_cast<int>(cj.size());
+  if (op->nblocks > 0) {
+    cudaError_t e1 = cudaMalloc(&op->d_jobs, sizeof(ParamJobDev) * n);
+    cudaError_t e2 = cudaMalloc(&op->d_chunk_job, sizeof(int32_t) * cj.size());
+    cudaError_t e3 = cudaMalloc(&op->d_chunk_first, sizeof(int32_t) * cf.size());
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { delete op; return set_error(MTBC_ERR_CUDA, "param_jobs: cudaMalloc failed"); }
+    // synchronous copies: creation is a set-up time call (never inside a capture)
+    cudaMemcpy(op->d_jobs, h.data(), sizeof(ParamJobDev) * n, cudaMemcpyHostToDevice);
+    cudaMemcpy(op->d_chunk_job, cj.data(), sizeof(int32_t) * cj.size(), cudaMemcpyHostToDevice);
+    cudaError_t e4 = cudaMemcpy(op->d_chunk_first, cf.data(), sizeof(int32_t) * cf.size(), cudaMemcpyHostToDevice);
+    if (e4 != cudaSuccess) { delete op; return set_error(MTBC_ERR_CUDA, "param_jobs: upload failed: %s", cudaGetErrorString(e4)); }
+  }
+  *out = op;
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------ first layer

@@ -77,6 +77,33 @@ def _mk(name: str, *args) -> Callable[[C.c_void_p], None]:
     return launch
 
 
+class JobTable:
+    """Parameter-side jobs (padded vector copies, weight packs, weight-gradient unpacks) run as ONE launch."""
+
+    def __init__(self):
+        self.jobs: List[_lib.ParamJob] = []
+        self._keep: List[object] = []
+
+    def add(self, kind: int, ints: Sequence[int], src: torch.Tensor, dst0: torch.Tensor,
+            dst1: Optional[torch.Tensor] = None):
+        j = _lib.ParamJob()
+        j.kind = kind
+        for k, v in enumerate(ints):
+            j.i[k] = int(v)
+        j.src = src.data_ptr(); j.dst0 = dst0.data_ptr(); j.dst1 = None if dst1 is None else dst1.data_ptr()
+        self.jobs.append(j)
+        self._keep += [src, dst0, dst1]
+
+    def launch(self) -> List[Callable]:
+        if not self.jobs:
+            return []
+        arr = (_lib.ParamJob * len(self.jobs))(*self.jobs)
+        h = C.c_void_p()
+        _lib.check(_lib.load().mtbc_param_jobs_create(arr, len(self.jobs), C.byref(h)), "param_jobs")
+        op = ops.Op(h, self._keep, "param_jobs")
+        return [_mk_op(op, 0.0, f"{len(self.jobs)} parameter jobs")]
+
+
 def _mk_op(op: ops.Op, true_flops: float = 0.0, desc: str = "") -> Callable:
     """Bind a tensor-core op launch; `true_flops` = algorithmic 2*M*N*K with unpadded channels (roofline numerator)."""
     lib = _lib.load()
@@ -101,6 +128,8 @@ class Plan:
         self.params = params
         self.training = training
         self.pack: List[Callable] = []
+        self.pack_jobs = JobTable()     # vector copies + weight packs, one launch at the head of `pack`
+        self.unpack_jobs = JobTable()   # weight-gradient unpacks, one launch at the tail of `bwd`
         self.fwd: List[Callable] = []
         self._bwd_blocks: List[List[Callable]] = []  # one block per forward op, reversed at finalize
         self.bwd: List[Callable] = []
@@ -125,7 +154,7 @@ class Plan:
         # deferred conv weight-gradient unpacks: param name -> (pending applications, launches)
         self._wg_pending: Dict[str, int] = {}
         self._wg_acc: Dict[str, torch.Tensor] = {}
-        self._wg_unpack: Dict[str, List[Callable]] = {}
+        self._late_unpacked: List[str] = []  # convT weights: unpacked by the batched job at the end of backward
         self._packed: Dict[str, dict] = {}
         self.finalized = False
         self._touched = set()
@@ -158,7 +187,7 @@ class Plan:
         p = self.P(name)
         buf = torch.zeros(Cp, dtype=torch.float32, device=self.device)
         n = p.numel()
-        self.pack.append(_mk_copy_f32(buf, p, n))
+        self.pack_jobs.add(_lib.JOB_COPY_F32, [n], p, buf)
         self._keep.append(buf)
         return buf
 
@@ -233,8 +262,6 @@ class Plan:
                 self.tc_flops_bwd += o.flops
                 blk.append(_mk_op(o, 2.0 * N * H * Wd * Cout * f.C * 9, f"{name} wgrad {N}x{H}x{Wd} {f.C}x{Cout}"))
             self._mark_grad(w, b)
-            if self._wg_pending[w] == 0:
-                blk.extend(self._wg_unpack.pop(w))
             for s, wd in zip(srcs, pk["wd"]):
                 g = s.grad()
                 o = ops.conv3x3_dgrad_op(dy, wd, g, accumulate=s.g_init)
@@ -261,9 +288,9 @@ class Plan:
         st_c = [f.C for f in feats]
         c0 = 0
         for cs, off, wd in zip(st_c, offs, wds):
-            self.pack.append(_mk("mtbc_pack_conv_weight", ptr(Wt), Wt.shape[0], Wt.shape[1], 3, c0, cs, ptr(wf),
-                                 wf.shape[1], wf.shape[2], off, ptr(wd), 0 if wd is None else wd.shape[1],
-                                 0 if wd is None else wd.shape[2]))
+            self.pack_jobs.add(_lib.JOB_PACK_CONV, [Wt.shape[0], Wt.shape[1], 3, c0, cs, wf.shape[1], wf.shape[2], off,
+                                                    0 if wd is None else wd.shape[1], 0 if wd is None else wd.shape[2]],
+                               Wt, wf, wd)
             c0 += cs
         pk = {"wf": wf, "wd": wds, "offs": offs, "ktot": ktot, "src_cp": [f.Cp for f in feats], "src_c": st_c}
         self._packed[key] = pk
@@ -274,13 +301,11 @@ class Plan:
             Wt = self.P(w)
             acc = self.bwd_arena.alloc(*pk["wf"].shape)
             self._wg_acc[w] = acc
-            launches = []
             c0 = 0
             for cs, off in zip(pk["src_c"], pk["offs"]):
-                launches.append(_mk("mtbc_unpack_conv_wgrad", ptr(acc), acc.shape[1], acc.shape[2], off,
-                                    ptr(self.grad_view[w]), Wt.shape[0], Wt.shape[1], 3, c0, cs, 0))
+                self.unpack_jobs.add(_lib.JOB_UNPACK_CONV, [acc.shape[1], acc.shape[2], off, Wt.shape[0], Wt.shape[1],
+                                                            3, c0, cs, 0], acc, self.grad_view[w])
                 c0 += cs
-            self._wg_unpack[w] = launches
         return self._wg_acc[w]
 
     def _norm_act(self, y: PTensor, ssum, ssq, gamma, beta, slope, pool, name):
@@ -330,8 +355,8 @@ class Plan:
         cp = out.feat.Cp
         wf = torch.zeros(1, k * k * cp, f.Cp, dtype=torch.bfloat16, device=self.device)
         wd = torch.zeros(k * k, f.Cp, cp, dtype=torch.bfloat16, device=self.device) if self.training else None
-        self.pack.append(_mk("mtbc_pack_convT_weight", ptr(Wt), Cin, Cout, k, cp, ptr(wf), wf.shape[2], ptr(wd),
-                             0 if wd is None else wd.shape[1], 0 if wd is None else wd.shape[2]))
+        self.pack_jobs.add(_lib.JOB_PACK_CONVT, [Cin, Cout, k, cp, wf.shape[2], 0 if wd is None else wd.shape[1],
+                                                 0 if wd is None else wd.shape[2]], Wt, wf, wd)
         bias = self._padded_vec(b, cp)
         op = ops.convT_fwd_op(f, wf, out.feat, k, bias)
         self.tc_flops_fwd += op.flops
@@ -346,8 +371,8 @@ class Plan:
             o = ops.convT_wgrad_op(f, out.g, acc, k)
             self.tc_flops_bwd += o.flops
             blk.append(_mk_op(o, t_flops, f"{name} convT wgrad {f.N}x{f.H}x{f.W} {Cin}->{Cout}"))
-            blk.append(_mk("mtbc_unpack_convT_wgrad", ptr(acc), k * k * cp, f.Cp, ptr(self.grad_view[w]), Cin, Cout, k,
-                           0))
+            self.unpack_jobs.add(_lib.JOB_UNPACK_CONVT, [k * k * cp, f.Cp, Cin, Cout, k, 0], acc, self.grad_view[w])
+            self._late_unpacked.append(w)
             if b is not None:
                 blk.append(_mk("mtbc_channel_sum", ptr(out.g.t), out.g.N * out.g.H * out.g.W, cp, Cout,
                                ptr(self.grad_view[b]), 1))
@@ -499,14 +524,15 @@ class Plan:
                 body.extend(mk_block())
                 for n in self._touched:  # the last block touching a parameter finalises its gradient
                     self.param_done_at[n] = len(body)
-            for w, launches in list(self._wg_unpack.items()):  # shared weights whose last application had no grad
-                body.extend(launches)
-            self._wg_unpack.clear()
+            body.extend(self.unpack_jobs.launch())  # every conv / convT weight gradient -> parameter layout
+            for n in list(self._wg_acc) + self._late_unpacked:
+                self.param_done_at[n] = len(body)
             self.bwd = [_mk("mtbc_zero_bytes", ptr(self.grad_flat), self.grad_flat.numel() * 4)]
             self.bwd += self.bwd_arena.zero_launches()
             n_pre = len(self.bwd)
             self.bwd += body
             self.param_done_at = {n: i + n_pre for n, i in self.param_done_at.items()}
+        self.pack = self.pack_jobs.launch() + self.pack
         self.fwd = self.fwd_arena.zero_launches() + self.fwd
         self._bwd_blocks = []
         self.finalized = True
