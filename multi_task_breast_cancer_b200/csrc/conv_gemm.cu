@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     // ---------------------------------------------------------------- TMA producer
     int stage = 0;
     uint32_t phase = 0;
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ 
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && elect_one()) {
     // ---------------------------------------------------------------- MMA issuer (one thread)
     const uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
     int stage = 0;
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const __grid_constant__ Wgra
   const int a_nbox = min(p.a_boxes, (p.a_C - a_c0 + p.a_kc - 1) / p.a_kc);
 
   if (n_my > 0) {
-    if (warp == 0 && lane == 0) {
+    if (warp == 0 && elect_one()) {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       for (int pt = pt_begin; pt < pt_end; ++pt) {
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const __grid_constant__ Wgra
           if (++sa == kWgAStages) { sa = 0; pa ^= 1u; }
         }
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1 && elect_one()) {
       const uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
       const uint32_t a_hi = umma_desc_hi(8u * p.a_kc * 2u, p.a_kc == 64 ? 2u : 4u);
       const uint32_t b_hi = umma_desc_hi(8u * p.b_kc * 2u, p.b_kc == 64 ? 2u : 4u);

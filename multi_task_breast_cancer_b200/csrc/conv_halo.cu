@@ -68,12 +68,137 @@ __device__ __forceinline__ void halo_issue_chunk(uint32_t d_addr, uint32_t a_lo,
   }
 }
 
+
+// Epilogue of the halo kernel, run by the 4 warps that own the 4 TMEM lane quarters (thread <-> output pixel).
+//   RACC > 0 (= BN, 32 or 64): InstanceNorm partial sums (sum y, sum y^2 per column) live in registers across the
+//     tiles of one sample and are combined (butterfly shuffles -> per-warp partials in smem -> one global atomic per
+//     column) only when the sample changes: per tile the statistics cost 2 FP32 ops per element and nothing else.
+//   RACC == 0: any BN; statistics (if requested) are combined per tile.
+template <int RACC>
+__device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t tmem_base, int t_begin, int t_end,
+                                              int ntile, int warp, int lane, const float* s_bias,
+                                              float (*s_part)[2][256], uint64_t* s_accfull, uint64_t* s_accempty) {
+  const int q = warp & 3;
+  const int row = q * 32 + lane;
+  const int tw = row & 7, th = row >> 3;
+  const int BN = p.BN;
+  const bool do_stats = (p.stat_sum != nullptr);
+  const int etid = q * 32 + lane;
+  const int tiles_per_n = p.tiles_w * p.tiles_h;
+  constexpr int NR = RACC > 0 ? RACC : 1;
+  float rs[NR], rq[NR];
+#pragma unroll
+  for (int i = 0; i < NR; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
+  int cur_n = t_begin < t_end ? t_begin / tiles_per_n : 0;
+
+  // combine the 4 warps' column partials and add them to the per-(n, channel) statistics
+  auto flush_cols = [&](int n) {
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int i = etid; i < BN; i += 128) {
+      const int64_t o = static_cast<int64_t>(n) * p.stat_C + ntile * BN + i;
+      atomicAdd(p.stat_sum + o, s_part[0][0][i] + s_part[1][0][i] + s_part[2][0][i] + s_part[3][0][i]);
+      atomicAdd(p.stat_sq + o, s_part[0][1][i] + s_part[1][1][i] + s_part[2][1][i] + s_part[3][1][i]);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+  };
+  auto flush_regs = [&](int n) {
+    if constexpr (RACC > 0) {
+#pragma unroll
+      for (int c = 0; c < RACC; c += 16) {
+        float a[16], b[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { a[i] = rs[c + i]; b[i] = rq[c + i]; rs[c + i] = 0.f; rq[c + i] = 0.f; }
+        const float cs = warp_colsum16(a, lane);
+        const float cq = warp_colsum16(b, lane);
+        if ((lane & 1) == 0) {
+          const int cc = c + col16_of_lane(lane);
+          s_part[q][0][cc] = cs;
+          s_part[q][1][cc] = cq;
+        }
+      }
+      flush_cols(n);
+    }
+  };
+
+  int it = 0;
+  for (int t = t_begin; t < t_end; ++t, ++it) {
+    const int buf = it & 1;
+    const uint32_t acc_phase = (it >> 1) & 1;
+    const int n = t / tiles_per_n;
+    const int rem = t - n * tiles_per_n;
+    const int w = (rem % p.tiles_w) * 8 + tw;
+    const int h = (rem / p.tiles_w) * 16 + th;
+    if (RACC > 0 && n != cur_n) { flush_regs(cur_n); cur_n = n; }
+    mbar_wait(&s_accfull[buf], acc_phase);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
+    __nv_bfloat16* dst_row = p.out + ((static_cast<int64_t>(n) * p.H + h) * p.W + w) * p.out_C + ntile * BN;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 16) {
+      float v[16];
+      tmem_ld16(taddr + c, v);
+      if (p.bias != nullptr) {
+        const float4* b4 = reinterpret_cast<const float4*>(s_bias + c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 bb = b4[i];
+          v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+        }
+      }
+      if constexpr (RACC > 0) {
+        // c is a multiple of 16 < RACC: unrolled select keeps rs/rq in registers
+#pragma unroll
+        for (int cb = 0; cb < RACC; cb += 16) {
+          if (c == cb) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { rs[cb + i] += v[i]; rq[cb + i] = fmaf(v[i], v[i], rq[cb + i]); }
+          }
+        }
+      } else if (do_stats) {
+        float sq[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sq[i] = v[i] * v[i];
+        const float cs = warp_colsum16(v, lane);
+        const float cq = warp_colsum16(sq, lane);
+        if ((lane & 1) == 0) {
+          const int cc = c + col16_of_lane(lane);
+          s_part[q][0][cc] = cs;
+          s_part[q][1][cc] = cq;
+        }
+      }
+      uint4* d4 = reinterpret_cast<uint4*>(dst_row + c);
+      if (p.accumulate) {
+        const uint4 o0 = d4[0], o1 = d4[1];
+        const uint32_t ou[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 f = unpack_bf16x2(ou[i]);
+          v[2 * i] += f.x;
+          v[2 * i + 1] += f.y;
+        }
+      }
+      uint4 r0, r1;
+      r0.x = pack_bf16x2(v[0], v[1]); r0.y = pack_bf16x2(v[2], v[3]); r0.z = pack_bf16x2(v[4], v[5]); r0.w = pack_bf16x2(v[6], v[7]);
+      r1.x = pack_bf16x2(v[8], v[9]); r1.y = pack_bf16x2(v[10], v[11]); r1.z = pack_bf16x2(v[12], v[13]); r1.w = pack_bf16x2(v[14], v[15]);
+      d4[0] = r0;
+      d4[1] = r1;
+    }
+    // accumulator fully read: hand it back to the MMA warp
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_accempty[buf]);
+    if (RACC == 0 && do_stats) flush_cols(n);
+  }
+  if (RACC > 0 && t_begin < t_end) flush_regs(cur_n);
+}
+
 __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t s_afull[kHaloMaxStages], s_aempty[kHaloMaxStages];
   __shared__ uint64_t s_bfull, s_accfull[2], s_accempty[2];
   __shared__ uint32_t s_tmem;
-  __shared__ float s_stat[2][2][256];  // [accumulator buffer][sum|sumsq][col]
+  __shared__ __align__(16) float s_bias[256];
+  __shared__ float s_part[4][2][256];  // [epilogue warp][sum|sumsq][col]: per-warp column partials at a flush
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -81,8 +206,12 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
   uint8_t* smem_a = smem + p.b_total_bytes;     // halo ring
   const int ntile = blockIdx.y;
   const int BN = p.BN;
+  // contiguous tile range per CTA: neighbouring tiles share halo rows in L2 and mostly belong to one sample, so the
+  // epilogue can keep InstanceNorm partial sums in registers across tiles
+  const int t_begin = static_cast<int>(static_cast<int64_t>(p.n_mtiles) * blockIdx.x / gridDim.x);
+  const int t_end = static_cast<int>(static_cast<int64_t>(p.n_mtiles) * (blockIdx.x + 1) / gridDim.x);
 
-  for (int i = tid; i < 2 * 2 * 256; i += 192) (&s_stat[0][0][0])[i] = 0.f;
+  for (int i = tid; i < 256; i += 192) s_bias[i] = (p.bias != nullptr && i < BN) ? p.bias[ntile * BN + i] : 0.f;
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&s_afull[s], 1); mbar_init(&s_aempty[s], 1); }
     mbar_init(&s_bfull, 1);
@@ -99,7 +228,7 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
   const uint32_t tmem_base = s_tmem;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ------------------------------------------------------------ producer: weights once, then halo tiles
       mbar_arrive_expect_tx(&s_bfull, static_cast<uint32_t>(p.b_total_bytes));
       for (int tap = 0; tap < 9; ++tap)
@@ -112,7 +241,7 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
         }
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < p.n_mtiles; t += gridDim.x) {
+      for (int t = t_begin; t < t_end; ++t) {
         const int w0 = (t % p.tiles_w) * 8;
         const int h0 = ((t / p.tiles_w) % p.tiles_h) * 16;
         const int n = t / (p.tiles_w * p.tiles_h);
@@ -129,7 +258,7 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ------------------------------------------------------------ MMA issuer
       const uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
       mbar_wait(&s_bfull, 0);
@@ -137,7 +266,7 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < p.n_mtiles; t += gridDim.x, ++it) {
+      for (int t = t_begin; t < t_end; ++t, ++it) {
         const int buf = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&s_accempty[buf], acc_phase ^ 1u);  // epilogue has drained this accumulator
@@ -163,75 +292,9 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
     }
   } else {
     // -------------------------------------------------------------- epilogue warps 2..5 (TMEM lane quarter = warp % 4)
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int tw = row & 7, th = row >> 3;
-    const bool do_stats = (p.stat_sum != nullptr);
-    const int etid = tid - 64;  // 0..127
-    int it = 0;
-    for (int t = blockIdx.x; t < p.n_mtiles; t += gridDim.x, ++it) {
-      const int buf = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      const int w = (t % p.tiles_w) * 8 + tw;
-      const int h = ((t / p.tiles_w) % p.tiles_h) * 16 + th;
-      const int n = t / (p.tiles_w * p.tiles_h);
-      mbar_wait(&s_accfull[buf], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
-      __nv_bfloat16* dst_row = p.out + ((static_cast<int64_t>(n) * p.H + h) * p.W + w) * p.out_C + ntile * BN;
-      for (int c = 0; c < BN; c += 16) {
-        float v[16];
-        tmem_ld16(taddr + c, v);
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + ntile * BN + c + i);
-        }
-        if (do_stats) {
-          float sq[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) sq[i] = v[i] * v[i];
-          const float cs = warp_colsum16(v, lane);
-          const float cq = warp_colsum16(sq, lane);
-          if ((lane & 1) == 0) {
-            const int cc = c + col16_of_lane(lane);
-            atomicAdd(&s_stat[buf][0][cc], cs);
-            atomicAdd(&s_stat[buf][1][cc], cq);
-          }
-        }
-        uint4* d4 = reinterpret_cast<uint4*>(dst_row + c);
-        if (p.accumulate) {
-          const uint4 o0 = d4[0], o1 = d4[1];
-          const uint32_t ou[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float2 f = unpack_bf16x2(ou[i]);
-            v[2 * i] += f.x;
-            v[2 * i + 1] += f.y;
-          }
-        }
-        uint4 r0, r1;
-        r0.x = pack_bf16x2(v[0], v[1]); r0.y = pack_bf16x2(v[2], v[3]); r0.z = pack_bf16x2(v[4], v[5]); r0.w = pack_bf16x2(v[6], v[7]);
-        r1.x = pack_bf16x2(v[8], v[9]); r1.y = pack_bf16x2(v[10], v[11]); r1.z = pack_bf16x2(v[12], v[13]); r1.w = pack_bf16x2(v[14], v[15]);
-        d4[0] = r0;
-        d4[1] = r1;
-      }
-      // accumulator fully read: hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_accempty[buf]);
-      if (do_stats) {
-        // the 4 epilogue warps of this tile combine their column sums, then one atomic per column
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int i = etid; i < BN; i += 128) {
-          const int64_t o = static_cast<int64_t>(n) * p.stat_C + ntile * BN + i;
-          atomicAdd(p.stat_sum + o, s_stat[buf][0][i]);
-          atomicAdd(p.stat_sq + o, s_stat[buf][1][i]);
-          s_stat[buf][0][i] = 0.f;
-          s_stat[buf][1][i] = 0.f;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-      }
-    }
+    if (p.stat_sum != nullptr && BN == 32) halo_epilogue<32>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_accfull, s_accempty);
+    else if (p.stat_sum != nullptr && BN == 64) halo_epilogue<64>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_accfull, s_accempty);
+    else halo_epilogue<0>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_accfull, s_accempty);
   }
 
   tc_fence_before();
@@ -284,7 +347,7 @@ __global__ void __launch_bounds__(128) wgrad_halo_kernel(const __grid_constant__
   const uint32_t tmem_base = s_tmem;
 
   if (pt_end > pt_begin) {
-    if (warp == 0 && lane == 0) {
+    if (warp == 0 && elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int pt = pt_begin; pt < pt_end; ++pt) {
@@ -300,7 +363,7 @@ __global__ void __launch_bounds__(128) wgrad_halo_kernel(const __grid_constant__
           tma_load_4d(b_dst + b * p.b_box_bytes, &p.bmap, &s_full[stage], ntile * BN + b * p.b_kc, w0, h0, n);
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1 && elect_one()) {
       const uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
       const uint32_t b_rowb = p.b_kc * 2u;
       const uint32_t a_hi = umma_desc_hi(kHaloW * 64, 4u);
@@ -470,7 +533,7 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   p.bias = d->bias; p.stat_sum = d->stat_sum; p.stat_sq = d->stat_sq;
   op->grid = dim3(gx, d->ncols / BN, 1);
   op->flops = 2.0 * double(d->N) * d->H * d->W * double(d->ncols) * kused * 9.0;
-  cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
   if (e != cudaSuccess) { delete op; return set_error(MTBC_ERR_CUDA, "cudaFuncSetAttribute(conv_halo): %s", cudaGetErrorString(e)); }
   *out = op;
   return 0;

@@ -11,6 +11,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a fully converged warp.  ptxas only emits straight-line UTCHMMA / UTMALDG sequences (operands in uniform
+// registers) when it can prove a single thread executes them; behind a plain `lane == 0` test every tcgen05.mma is
+// wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop that costs ~45 cycles per instruction (tools/exp_mma_rate2.cu).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+  return p != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

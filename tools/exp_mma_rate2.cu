@@ -18,13 +18,18 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint32_t b_l
 __device__ __forceinline__ void cp_128x256b(uint32_t taddr, uint32_t lo, uint32_t hi) {
   asm volatile("{\n\t.reg .b64 d;\n\tmov.b64 d, {%1, %2};\n\ttcgen05.cp.cta_group::1.128x256b [%0], d;\n\t}" ::"r"(taddr), "r"(lo), "r"(hi) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+  return p != 0;
+}
 __device__ __forceinline__ void shift_down(uint32_t taddr) {
   asm volatile("tcgen05.shift.cta_group::1.down [%0];" ::"r"(taddr) : "memory");
 }
 
 // mode 0: SS, one issuer; 1: SS, two issuers; 2: TS (A in TMEM); 3: cp only; 4: shift only; 5: per input row: 3 cp + 9 TS MMAs
 template <int mode>
-__global__ void __launch_bounds__(128) rate_kernel(int M, int N, int iters, long long* out) {
+__global__ void __launch_bounds__(128) rate_kernel(int M, int N, int iters, long long* out, int kc = 64, int shift_rows = 0, int sbo_rows = 8, int a_mn = 0, int lbo = 16) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t s_bar[2];
   __shared__ uint32_t s_tmem;
@@ -36,11 +41,11 @@ __global__ void __launch_bounds__(128) rate_kernel(int M, int N, int iters, long
   fence_proxy_async_smem();
   tc_fence_before(); __syncthreads(); tc_fence_after();
   const int nissue = (mode == 1) ? 2 : 1;
-  if (lane == 0 && warp < nissue) {
-    const uint32_t rowb = 128, layout = 2u;
-    const uint32_t idesc = umma_idesc_bf16(M, N, 0, 0);
+  if (warp < nissue && elect_one()) {
+    const uint32_t rowb = kc * 2, layout = kc == 64 ? 2u : 4u;
+    const uint32_t idesc = umma_idesc_bf16(M, N, a_mn, 0);
     const uint32_t a0 = smem_u32(smem) + warp * 16384, b0 = smem_u32(smem) + 48 * 1024;
-    const uint32_t a_lo = umma_desc_lo(a0, 16), a_hi = umma_desc_hi(8 * rowb, layout);
+    const uint32_t a_lo = umma_desc_lo(a0 + shift_rows * rowb, lbo), a_hi = umma_desc_hi(sbo_rows * rowb, layout);
     const uint32_t b_lo = umma_desc_lo(b0, 16), b_hi = umma_desc_hi(8 * rowb, layout);
     const uint32_t tm = s_tmem + warp * 256;   // accumulators: columns [0,128) of this issuer's half; A staging: [128, 256)
     const long long t0 = clock64();
@@ -67,8 +72,13 @@ __global__ void __launch_bounds__(128) rate_kernel(int M, int N, int iters, long
 int main() {
   long long* d; cudaMalloc(&d, 8);
   const int iters = 4500;
-  struct C { int mode, M, N; const char* note; };
+  struct C { int mode, M, N; const char* note; int kc = 64, shift = 0, sbo = 8, amn = 0, lbo = 16; };
   std::vector<C> cs = {
+      {0, 128, 32, "SS kc=32 canonical", 32, 0, 8}, {0, 128, 32, "SS kc=32 halo view shift 11 sbo 10", 32, 11, 10},
+      {0, 128, 32, "SS kc=64 halo view shift 11 sbo 10", 64, 11, 10}, {0, 128, 32, "SS kc=32 halo view shift 1 sbo 10", 32, 1, 10},
+      {0, 128, 32, "SS kc=32 halo view shift 0 sbo 10", 32, 0, 10}, {0, 128, 64, "SS N=64 kc=64 halo shift 11", 64, 11, 10},
+      {0, 128, 32, "SS MN-major A (wgrad halo) kc=32 lbo=64 sbo=10 rows", 32, 10, 10, 1, 64},
+      {0, 128, 32, "SS MN-major A canonical kc=64 lbo=16384", 64, 0, 8, 1, 16384},
       {0, 128, 32, "SS 1 issuer"}, {0, 64, 32, "SS 1 issuer M=64"}, {0, 64, 64, "SS 1 issuer M=64"}, {0, 128, 16, "SS N=16"},
       {0, 128, 64, "SS 1 issuer"}, {0, 128, 96, "SS 1 issuer"}, {0, 128, 128, "SS"}, {0, 128, 192, "SS"},
       {1, 128, 32, "SS 2 issuers (per-issuer MMAs)"}, {1, 128, 64, "SS 2 issuers"},
@@ -78,7 +88,7 @@ int main() {
   };
   for (const C& c : cs) {
     switch (c.mode) {
-#define RUN(m) case m: cudaFuncSetAttribute(rate_kernel<m>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024); rate_kernel<m><<<148, 128, 120 * 1024>>>(c.M, c.N, iters, d); break;
+#define RUN(m) case m: cudaFuncSetAttribute(rate_kernel<m>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024); rate_kernel<m><<<148, 128, 120 * 1024>>>(c.M, c.N, iters, d, c.kc, c.shift, c.sbo, c.amn, c.lbo); break;
       RUN(0) RUN(1) RUN(2) RUN(3) RUN(4) RUN(5)
     }
     cudaError_t e = cudaDeviceSynchronize();
