@@ -157,9 +157,14 @@ int mtbc_param_jobs_create(const mtbc_param_job* jobs, int32_t n, mtbc_op** out)
 /* ------------------------------------------------------------------------------------------------------------- */
 /* First layer: Conv2d 3x3 with Cin <= 4 on the fp32 NCHW input image (K = 9*Cin is too small for a tensor tile).  */
 /* Replaces conv_0_0.conv_0 / encoder1.ConvInNormLRelu1.Conv forward + weight gradient (no data gradient: the image
- * needs none, training_multitask.py:82-90). */
+ * needs none, training_multitask.py:82-90).
+ * center_scratch (fp32 [N][Cin*9], optional): when given, y is stored with its exact per-(n,channel) mean removed
+ * (computed from nine shifted plane sums of x, which land in the scratch).  Only valid when InstanceNorm follows
+ * (shift invariant): the raw 0..255 image puts a large DC level on this layer, and centred storage keeps bf16's
+ * mantissa for the signal and sum(y^2) free of cancellation.  bias is ignored in that mode (it cancels). */
 int mtbc_conv_first_fwd(const float* x, int32_t N, int32_t Cin, int32_t H, int32_t W, const float* w, const float* bias,
-                        int32_t Cout, void* y, int32_t Cp, float* stat_sum, float* stat_sq, void* stream);
+                        int32_t Cout, void* y, int32_t Cp, float* stat_sum, float* stat_sq, float* center_scratch,
+                        void* stream);
 int mtbc_conv_first_wgrad(const float* x, int32_t N, int32_t Cin, int32_t H, int32_t W, const void* dy, int32_t Cp,
                           int32_t Cout, float* dw, void* stream);
 

@@ -67,7 +67,7 @@ _SIGS = {
     "mtbc_pack_convT_weight": [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_i32, c_i32, c_vp],
     "mtbc_unpack_conv_wgrad": [c_vp, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],
     "mtbc_unpack_convT_wgrad": [c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp],
-    "mtbc_conv_first_fwd": [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp],
+    "mtbc_conv_first_fwd": [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp],
     "mtbc_conv_first_wgrad": [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp],
     "mtbc_in_stats": [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp],
     "mtbc_in_apply": [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_f32, c_f32, c_vp, c_vp,

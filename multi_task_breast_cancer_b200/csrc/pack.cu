@@ -217,11 +217,62 @@ int param_jobs_create(const mtbc_param_job* jobs, int n, OpBase** out) {
 }
 
 // ------------------------------------------------------------------------------------------------ first layer
+// xs[n][ci][r*3+s] = sum over output pixels (h,w) of x[n,ci,h+r-1,w+s-1] (zero padded): the nine shifted plane sums
+// from which the per-(n,channel) mean of the conv output follows linearly.  grid = N*Cin blocks of 256 threads.
+__global__ void __launch_bounds__(256) conv_first_shift_sums_kernel(const float* __restrict__ x, int H, int W,
+                                                                    float* __restrict__ xs) {
+  const float* plane = x + static_cast<int64_t>(blockIdx.x) * H * W;
+  // total, first/last row, first/last column, four corners
+  float tot = 0.f, r0 = 0.f, rl = 0.f, c0 = 0.f, cl = 0.f;
+  for (int i = threadIdx.x; i < H * W; i += 256) {
+    const float v = plane[i];
+    const int h = i / W, w = i - h * W;
+    tot += v;
+    if (h == 0) r0 += v;
+    if (h == H - 1) rl += v;
+    if (w == 0) c0 += v;
+    if (w == W - 1) cl += v;
+  }
+  __shared__ float red[5][8];
+  float vals[5] = {tot, r0, rl, c0, cl};
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    float v = vals[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t[5];
+    for (int k = 0; k < 5; ++k) { t[k] = 0.f; for (int j = 0; j < 8; ++j) t[k] += red[k][j]; }
+    const float x00 = plane[0], x0l = plane[W - 1], xl0 = plane[(H - 1) * W], xll = plane[(H - 1) * W + W - 1];
+    // tap (r,s) reads x[h+r-1][w+s-1]: r=0 never touches the last row, r=2 never the first; same for columns
+    for (int r = 0; r < 3; ++r)
+      for (int s = 0; s < 3; ++s) {
+        float v = t[0];
+        if (r == 0) v -= t[2];
+        if (r == 2) v -= t[1];
+        if (s == 0) v -= t[4];
+        if (s == 2) v -= t[3];
+        if (r == 0 && s == 0) v += xll;
+        if (r == 0 && s == 2) v += xl0;
+        if (r == 2 && s == 0) v += x0l;
+        if (r == 2 && s == 2) v += x00;
+        xs[blockIdx.x * 9 + r * 3 + s] = v;
+      }
+  }
+}
+
 // One thread per output pixel, 128 consecutive pixels of one sample per block; weights staged in smem.
+// xs != nullptr: the per-(n,channel) mean of the conv output (exact, from the shifted plane sums) is subtracted before
+// the bf16 rounding and the statistics.  InstanceNorm is shift invariant, so everything downstream is unchanged, but
+// the raw 0..255 image (BUSI_dataset.py:102, no normalisation) puts a DC level of many standard deviations on this
+// layer's output: stored centred, bf16 spends its 8 mantissa bits on the signal and sum(y^2) does not cancel.
 __global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __restrict__ x, int N, int Cin, int H, int W,
                                                              const float* __restrict__ w, const float* __restrict__ bias,
                                                              int Cout, __nv_bfloat16* __restrict__ y, int Cp,
-                                                             float* __restrict__ stat_sum, float* __restrict__ stat_sq) {
+                                                             float* __restrict__ stat_sum, float* __restrict__ stat_sq,
+                                                             const float* __restrict__ xs) {
   extern __shared__ float sm[];
   float* s_w = sm;                    // [Cp][Cin*9], zero padded
   float* s_b = s_w + Cp * Cin * 9;    // [Cp]
@@ -240,6 +291,16 @@ __global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __rest
   const int hw = static_cast<int>(pix - n * HW);
   const int h = hw / W, ww = hw - h * W;
   const int lane = threadIdx.x & 31;
+  if (xs != nullptr) {
+    // the block's 128 pixels belong to one sample (HW % 128 == 0): replace the bias by -(mean of w * x)
+    const float inv = 1.f / static_cast<float>(HW);
+    for (int c = threadIdx.x; c < Cp; c += 128) {
+      float m = 0.f;
+      for (int k = 0; k < K; ++k) m = fmaf(s_w[c * K + k], xs[static_cast<int64_t>(n) * K + k], m);
+      s_b[c] = -m * inv;
+    }
+    __syncthreads();
+  }
   float xin[36];
 #pragma unroll 4
   for (int ci = 0; ci < Cin; ++ci)
@@ -419,13 +480,20 @@ int mtbc_unpack_convT_wgrad(const float* acc, int32_t rows, int32_t ld, float* g
 }
 
 int mtbc_conv_first_fwd(const float* x, int32_t N, int32_t Cin, int32_t H, int32_t W, const float* w, const float* bias,
-                        int32_t Cout, void* y, int32_t Cp, float* stat_sum, float* stat_sq, void* stream) {
+                        int32_t Cout, void* y, int32_t Cp, float* stat_sum, float* stat_sq, float* center_scratch,
+                        void* stream) {
   if (Cin < 1 || Cin > 4 || Cp % 16 != 0 || Cout > Cp) return set_error(MTBC_ERR_INVALID, "conv_first_fwd: Cin must be 1..4");
   const int64_t HW = static_cast<int64_t>(H) * W;
   if (HW % 128 != 0) return set_error(MTBC_ERR_INVALID, "conv_first_fwd: H*W must be a multiple of 128");
+  if (center_scratch != nullptr) {
+    if (H < 2 || W < 2) return set_error(MTBC_ERR_INVALID, "conv_first_fwd: centring needs H, W >= 2");
+    conv_first_shift_sums_kernel<<<N * Cin, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, H, W, center_scratch);
+    int rc = check_launch("conv_first_shift_sums");
+    if (rc) return rc;
+  }
   const int smem = (Cp * Cin * 9 + 3 * Cp) * sizeof(float);
   conv_first_fwd_kernel<<<static_cast<int>(N * HW / 128), 128, smem, static_cast<cudaStream_t>(stream)>>>(
-      x, N, Cin, H, W, w, bias, Cout, static_cast<__nv_bfloat16*>(y), Cp, stat_sum, stat_sq);
+      x, N, Cin, H, W, w, bias, Cout, static_cast<__nv_bfloat16*>(y), Cp, stat_sum, stat_sq, center_scratch);
   return check_launch("conv_first_fwd");
 }
 int mtbc_conv_first_wgrad(const float* x, int32_t N, int32_t Cin, int32_t H, int32_t W, const void* dy, int32_t Cp,

@@ -208,8 +208,10 @@ class Plan:
         ssum = self.fwd_arena.alloc(N, y.feat.Cp)
         ssq = self.fwd_arena.alloc(N, y.feat.Cp)
         bvec = None if b is None else self.P(b)
+        xs = torch.zeros(N, Cin * 9, dtype=torch.float32, device=self.device)  # shifted plane sums (mean removal)
+        self._keep.append(xs)
         self.fwd.append(_mk("mtbc_conv_first_fwd", ptr(x_in), N, Cin, H, Wd, ptr(Wt), ptr(bvec), Cout, ptr(y.feat.t),
-                            y.feat.Cp, ptr(ssum), ptr(ssq)))
+                            y.feat.Cp, ptr(ssum), ptr(ssq), ptr(xs)))
         a, p, aux = self._norm_act(y, ssum, ssq, gamma, beta, slope, pool, name)
 
         def backward():

@@ -190,12 +190,22 @@ def first_conv_case(N, H, W, Cout):
         ssum = torch.zeros(N, out.Cp, device=dev)
         ssq = torch.zeros(N, out.Cp, device=dev)
         _lib.call("mtbc_conv_first_fwd", ops.ptr(x), N, 1, H, W, ops.ptr(w), ops.ptr(b), Cout, ops.ptr(out.t), out.Cp,
-                  ops.ptr(ssum), ops.ptr(ssq), None)
+                  ops.ptr(ssum), ops.ptr(ssq), None, None)
         torch.cuda.synchronize()
         ref = F.conv2d(x, w, b, padding=1)
         report(name + " fwd", out.to_nchw(), ref)
         report(name + " sum", ssum[:, :Cout], ref.sum((2, 3)), tol=1e-3)
         report(name + " sumsq", ssq[:, :Cout], (ref * ref).sum((2, 3)), tol=1e-3)
+        # centred storage: y - mean_(h,w)(y), statistics of the centred values
+        ssum.zero_(); ssq.zero_()
+        xs = torch.zeros(N, 9, device=dev)
+        _lib.call("mtbc_conv_first_fwd", ops.ptr(x), N, 1, H, W, ops.ptr(w), ops.ptr(b), Cout, ops.ptr(out.t), out.Cp,
+                  ops.ptr(ssum), ops.ptr(ssq), ops.ptr(xs), None)
+        torch.cuda.synchronize()
+        refc = ref - ref.mean((2, 3), keepdim=True)
+        report(name + " fwd centred", out.to_nchw(), refc)
+        report(name + " sumsq centred", ssq[:, :Cout], (refc * refc).sum((2, 3)), tol=1e-3)
+        report(name + " mean centred (+1)", ssum[:, :Cout] / (H * W) + 1.0, torch.ones(N, Cout, device=dev), tol=1e-2)
         dy = rnd(N, Cout, H, W)
         dyf = Feat.from_nchw(dy)
         dw = torch.zeros(Cout, 1, 3, 3, device=dev)
