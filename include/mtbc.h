@@ -58,6 +58,16 @@ typedef struct {
  * out[n, up_k*h+i, up_k*w+j, co].  bias (fp32[ncols or up_cp]) optional.  stat_sum/stat_sq (fp32 [N][stat_C]) optional:
  * per-(n,channel) sum and sum of squares of the fp32 result = InstanceNorm statistics (MTnnUNet.py:35).
  * accumulate != 0: out += D (gradient accumulation for tensors with several consumers). */
+/* Routing of a range of GEMM output columns to its own tensor (fused data gradient of a conv over a folded concat:
+ * one launch writes every source's gradient).  Column ranges are multiples of 32 and must tile [0, ncols). */
+typedef struct {
+  void* ptr;       /* bf16 NHWC, channel stride out_C                 */
+  int32_t out_C;
+  int32_t col0;    /* first GEMM column of this slice                 */
+  int32_t ncols;   /* columns of this slice                           */
+  int32_t accumulate;
+} mtbc_out_slice;
+
 typedef struct {
   int32_t nviews;
   mtbc_act_view views[MTBC_MAX_VIEWS];
@@ -76,6 +86,10 @@ typedef struct {
   float* stat_sq;
   int32_t stat_C;
   int32_t accumulate;
+  /* nouts == 0: single output (out / out_C / accumulate above).  nouts > 0 (epi_mode 0, halo-eligible 3x3 only, no
+   * bias/statistics): columns are routed to outs[]; creation fails with MTBC_ERR_INVALID if the shape is not eligible. */
+  int32_t nouts;
+  mtbc_out_slice outs[MTBC_MAX_VIEWS];
 } mtbc_conv_gemm_desc;
 
 /* One tap of a weight-gradient GEMM: dW[tap][co][k0 + ci] += sum_pixels A[a_view][pixel + (a_dh,a_dw)][ci] *
@@ -136,7 +150,7 @@ int mtbc_unpack_convT_wgrad(const float* acc, int32_t rows, int32_t ld, float* g
  * has ~250 of them; nn.Module parameters stay in PyTorch layout, MTUNetPlusPlus.py:47-87).  Integer arguments, in
  * the order of the single-job entry points:
  *   COPY_F32      i = {n}                                                            src -> dst0
- *   PACK_CONV     i = {Cout, Cin, ksz, c_begin, c_count, wf_rows, wf_ld, wf_k0, wd_rows, wd_ld}   src=w dst0=wf dst1=wd|NULL
+ *   PACK_CONV     i = {Cout, Cin, ksz, c_begin, c_count, wf_rows, wf_ld, wf_k0, wd_rows, wd_ld}   src=w dst0=wf|NULL dst1=wd|NULL
  *   PACK_CONVT    i = {Cin, Cout, k, cp, wf_ld, wd_rows, wd_ld}                      src=w dst0=wf dst1=wd|NULL
  *   UNPACK_CONV   i = {rows, ld, k0, Cout, Cin, ksz, c_begin, c_count, add}          src=acc dst0=grad
  *   UNPACK_CONVT  i = {rows, ld, Cin, Cout, k, add}                                  src=acc dst0=grad

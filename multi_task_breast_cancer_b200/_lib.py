@@ -26,12 +26,16 @@ class GemmSeg(C.Structure):
     _fields_ = [("view", c_i32), ("dh", c_i32), ("dw", c_i32), ("wk0", c_i32), ("wtap", c_i32)]
 
 
+class OutSlice(C.Structure):
+    _fields_ = [("ptr", c_vp), ("out_C", c_i32), ("col0", c_i32), ("ncols", c_i32), ("accumulate", c_i32)]
+
+
 class ConvGemmDesc(C.Structure):
     _fields_ = [("nviews", c_i32), ("views", ActView * MAX_VIEWS), ("nseg", c_i32), ("seg", GemmSeg * MAX_SEGS),
                 ("wpack", c_vp), ("w_ntaps", c_i32), ("w_ktot", c_i32), ("ncols", c_i32),
                 ("W", c_i32), ("H", c_i32), ("N", c_i32), ("epi_mode", c_i32), ("out", c_vp), ("out_C", c_i32),
                 ("up_k", c_i32), ("up_cp", c_i32), ("bias", c_vp), ("stat_sum", c_vp), ("stat_sq", c_vp),
-                ("stat_C", c_i32), ("accumulate", c_i32)]
+                ("stat_C", c_i32), ("accumulate", c_i32), ("nouts", c_i32), ("outs", OutSlice * MAX_VIEWS)]
 
 
 class WgradTap(C.Structure):

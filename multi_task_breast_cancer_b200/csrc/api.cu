@@ -30,7 +30,7 @@ struct mtbc_op {
 extern "C" {
 
 const char* mtbc_last_error(void) { return mtbc::g_err; }
-int mtbc_abi_version(void) { return 1; }
+int mtbc_abi_version(void) { return 2; }
 
 int mtbc_device_check(void) {
   int dev = 0;

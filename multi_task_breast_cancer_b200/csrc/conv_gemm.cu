@@ -26,10 +26,10 @@ struct ConvGemmParams {
   CUtensorMap wmap[2];  // [0]: 32-channel boxes / 64B swizzle, [1]: 64-channel boxes / 128B swizzle
   SegDev seg[MTBC_MAX_SEGS];
   int32_t nseg;
-  int32_t TW, TH, TN, tiles_w, tiles_h;
+  int32_t TW, TH, TN, tiles_w, tiles_h, n_mtiles, n_ntiles;
   int32_t W, H, N;
   int32_t BN, tmem_cols, stages, a_stage_bytes, stage_bytes;
-  int32_t epi_mode, out_C, up_k, up_cp, accumulate, stat_C;
+  int32_t epi_mode, out_C, up_k, up_cp, accumulate, stat_C, bias_len;
   __nv_bfloat16* out;
   const float* bias;
   float* stat_sum;
@@ -37,33 +37,35 @@ struct ConvGemmParams {
 };
 
 constexpr int kMaxStages = 8;
+constexpr int kMaxBias = 1024;
 
-__global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue (TMEM lane quarter =
+// warp % 4).  Two TMEM accumulators: the epilogue of work item i (TMEM -> registers -> bf16 global stores, the
+// dominant cost of the transposed convolutions, whose GEMM is a single K block) overlaps the loads and MMAs of item
+// i+1.  Work item = (pixel tile, N tile), N tile fastest so neighbouring CTAs share the A tile in L2.
+__global__ void __launch_bounds__(320) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t s_full[kMaxStages];
   __shared__ uint64_t s_empty[kMaxStages];
-  __shared__ uint64_t s_accum;
+  __shared__ uint64_t s_accfull[2], s_accempty[2];
   __shared__ uint32_t s_tmem;
   __shared__ float s_stat[2][256];
+  __shared__ __align__(16) float s_bias[kMaxBias];   // whole bias vector (epi_mode 0: ncols, pixel shuffle: up_cp)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-
-  // tile coordinates
-  const int bx = blockIdx.x;
-  const int w0 = (bx % p.tiles_w) * p.TW;
-  const int h0 = ((bx / p.tiles_w) % p.tiles_h) * p.TH;
-  const int n0 = (bx / (p.tiles_w * p.tiles_h)) * p.TN;
-  const int ntile = blockIdx.y;
   const int BN = p.BN;
+  const int n_items = p.n_mtiles * p.n_ntiles;
 
-  for (int i = tid; i < 512; i += 128) (&s_stat[0][0])[i] = 0.f;
+  for (int i = tid; i < 512; i += 320) (&s_stat[0][0])[i] = 0.f;
+  if (p.bias != nullptr)
+    for (int i = tid; i < p.bias_len; i += 320) s_bias[i] = p.bias[i];
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&s_full[s], 1);
       mbar_init(&s_empty[s], 1);
     }
-    mbar_init(&s_accum, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&s_accfull[b], 1); mbar_init(&s_accempty[b], 8); }
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -75,138 +77,185 @@ __global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
 
-  if (warp == 0 && elect_one()) {
-    // ---------------------------------------------------------------- TMA producer
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int s = 0; s < p.nseg; ++s) {
-      const SegDev sg = p.seg[s];
-      const CUtensorMap* am = &p.amap[sg.view];
-      const CUtensorMap* wm = &p.wmap[sg.kc == 64 ? 1 : 0];
-      const uint32_t bytes = static_cast<uint32_t>((128 + BN) * sg.kc * 2);
-      for (int ch = 0; ch < sg.nchunk; ++ch) {
-        mbar_wait(&s_empty[stage], phase ^ 1u);
-        uint8_t* a_dst = smem + stage * p.stage_bytes;
-        uint8_t* b_dst = a_dst + p.a_stage_bytes;
-        mbar_arrive_expect_tx(&s_full[stage], bytes);
-        tma_load_4d(a_dst, am, &s_full[stage], ch * sg.kc, w0 + sg.dw, h0 + sg.dh, n0);
-        tma_load_3d(b_dst, wm, &s_full[stage], sg.wk0 + ch * sg.kc, ntile * BN, sg.wtap);
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+  if (warp == 0) {
+    if (elect_one()) {
+      // -------------------------------------------------------------- TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int mt = item / p.n_ntiles, ntile = item - mt * p.n_ntiles;
+        const int w0 = (mt % p.tiles_w) * p.TW;
+        const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.TH;
+        const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.TN;
+        for (int s = 0; s < p.nseg; ++s) {
+          const SegDev sg = p.seg[s];
+          const CUtensorMap* am = &p.amap[sg.view];
+          const CUtensorMap* wm = &p.wmap[sg.kc == 64 ? 1 : 0];
+          const uint32_t bytes = static_cast<uint32_t>((128 + BN) * sg.kc * 2);
+          for (int ch = 0; ch < sg.nchunk; ++ch) {
+            mbar_wait(&s_empty[stage], phase ^ 1u);
+            uint8_t* a_dst = smem + stage * p.stage_bytes;
+            uint8_t* b_dst = a_dst + p.a_stage_bytes;
+            mbar_arrive_expect_tx(&s_full[stage], bytes);
+            tma_load_4d(a_dst, am, &s_full[stage], ch * sg.kc, w0 + sg.dw, h0 + sg.dh, n0);
+            tma_load_3d(b_dst, wm, &s_full[stage], sg.wk0 + ch * sg.kc, ntile * BN, sg.wtap);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+        }
       }
     }
-  } else if (warp == 1 && elect_one()) {
-    // ---------------------------------------------------------------- MMA issuer (one thread)
-    const uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
-    int stage = 0;
-    uint32_t phase = 0;
-    uint32_t accumulate = 0;
-    for (int s = 0; s < p.nseg; ++s) {
-      const SegDev sg = p.seg[s];
-      const uint32_t hi = umma_desc_hi(8u * sg.kc * 2u, sg.kc == 64 ? 2u : 4u);
-      for (int ch = 0; ch < sg.nchunk; ++ch) {
-        mbar_wait(&s_full[stage], phase);
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // -------------------------------------------------------------- MMA issuer (one thread)
+      const uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&s_accempty[buf], acc_phase ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + stage * p.stage_bytes);
-        const uint32_t a_lo = umma_desc_lo(a_addr, 16), b_lo = umma_desc_lo(a_addr + p.a_stage_bytes, 16);
-        // low descriptor words advance by compile-time steps: keeps the issuing lane at the tensor pipe's floor
-        umma_bf16_lohi(tmem_base, a_lo, hi, b_lo, hi, idesc, accumulate);
-        umma_bf16_lohi(tmem_base, a_lo + 2, hi, b_lo + 2, hi, idesc, 1u);
-        if (sg.kc == 64) {
-          umma_bf16_lohi(tmem_base, a_lo + 4, hi, b_lo + 4, hi, idesc, 1u);
-          umma_bf16_lohi(tmem_base, a_lo + 6, hi, b_lo + 6, hi, idesc, 1u);
+        const uint32_t d_addr = tmem_base + static_cast<uint32_t>(buf * BN);
+        uint32_t accumulate = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const SegDev sg = p.seg[s];
+          const uint32_t hi = umma_desc_hi(8u * sg.kc * 2u, sg.kc == 64 ? 2u : 4u);
+          for (int ch = 0; ch < sg.nchunk; ++ch) {
+            mbar_wait(&s_full[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + stage * p.stage_bytes);
+            const uint32_t a_lo = umma_desc_lo(a_addr, 16), b_lo = umma_desc_lo(a_addr + p.a_stage_bytes, 16);
+            // low descriptor words advance by compile-time steps: keeps the issuing lane at the tensor pipe's floor
+            umma_bf16_lohi(d_addr, a_lo, hi, b_lo, hi, idesc, accumulate);
+            umma_bf16_lohi(d_addr, a_lo + 2, hi, b_lo + 2, hi, idesc, 1u);
+            if (sg.kc == 64) {
+              umma_bf16_lohi(d_addr, a_lo + 4, hi, b_lo + 4, hi, idesc, 1u);
+              umma_bf16_lohi(d_addr, a_lo + 6, hi, b_lo + 6, hi, idesc, 1u);
+            }
+            accumulate = 1;
+            umma_commit(&s_empty[stage]);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
         }
-        accumulate = 1;
-        umma_commit(&s_empty[stage]);
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        umma_commit(&s_accfull[buf]);
       }
     }
-    umma_commit(&s_accum);
-  }
-  __syncwarp();
-
-  // ------------------------------------------------------------------ epilogue (all 4 warps, thread <-> TMEM lane)
-  mbar_wait(&s_accum, 0);
-  tc_fence_after();
-  __syncwarp();
-
-  const int row = warp * 32 + lane;
-  const int tw = row % p.TW, th = (row / p.TW) % p.TH, tn = row / (p.TW * p.TH);
-  const int n = n0 + tn, h = h0 + th, w = w0 + tw;
-  const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
-  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-  const bool do_stats = (p.stat_sum != nullptr);
-
-  for (int c = 0; c < BN; c += 16) {
-    float v[16];
-    tmem_ld16(taddr + c, v);
-    const int col = ntile * BN + c;
-    __nv_bfloat16* dst;
-    int bcol;
-    if (p.epi_mode == 0) {
-      bcol = col;
-      dst = p.out + ((static_cast<int64_t>(n) * p.H + h) * p.W + w) * p.out_C + col;
-    } else {
-      const int q = col / p.up_cp;
-      bcol = col - q * p.up_cp;
-      const int i = q / p.up_k, j = q - i * p.up_k;
-      const int64_t Ho = static_cast<int64_t>(p.H) * p.up_k, Wo = static_cast<int64_t>(p.W) * p.up_k;
-      dst = p.out + ((n * Ho + static_cast<int64_t>(h) * p.up_k + i) * Wo + static_cast<int64_t>(w) * p.up_k + j) * p.out_C + bcol;
-    }
-    if (p.bias != nullptr) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + bcol + i);
-    }
-    if (do_stats) {
-      float sv[16], sq[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        sv[i] = valid ? v[i] : 0.f;
-        sq[i] = sv[i] * sv[i];
+  } else {
+    // ---------------------------------------------------------------- epilogue: 8 warps, two per TMEM lane quarter,
+    // each pair splitting the N tile's 16-column chunks in halves.  Short dependent chain per chunk (these warps are
+    // alone on their schedulers): running output pointers instead of divisions, bias from shared memory, TMEM loads
+    // issued in pairs, 32-byte stores, accumulation as fire-and-forget bf16 reductions.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const int TW = p.TW, TH = p.TH, TN = p.TN, tiles_w = p.tiles_w, tiles_h = p.tiles_h, n_ntiles = p.n_ntiles;
+    const int tw = row % TW, th = (row / TW) % TH, tn = row / (TW * TH);
+    const int etid = (warp - 2) * 32 + lane;
+    const bool do_stats = (p.stat_sum != nullptr);
+    const bool has_bias = (p.bias != nullptr);
+    const bool acc = p.accumulate != 0;
+    const int epi_mode = p.epi_mode, up_k = p.up_k, up_cp = p.up_cp, out_C = p.out_C;
+    const int H = p.H, W = p.W, N = p.N;
+    const int64_t Wo = static_cast<int64_t>(W) * up_k;
+    __nv_bfloat16* const out = p.out;
+    const int nchunks = BN >> 4;
+    const int k_begin = half ? (nchunks + 1) >> 1 : 0;
+    const int k_end = half ? nchunks : (nchunks + 1) >> 1;
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int mt = item / n_ntiles, ntile = item - mt * n_ntiles;
+      const int w = (mt % tiles_w) * TW + tw;
+      const int h = ((mt / tiles_w) % tiles_h) * TH + th;
+      const int n0 = (mt / (tiles_w * tiles_h)) * TN;
+      const int n = n0 + tn;
+      const bool valid = (n < N) && (h < H) && (w < W);
+      // destination of this thread's first chunk, then running (q, bcol) for the pixel shuffle
+      const int col0 = ntile * BN + k_begin * 16;
+      __nv_bfloat16* pixbase;
+      int bcol, qi = 0, qj = 0;
+      if (epi_mode == 0) {
+        pixbase = out + ((static_cast<int64_t>(n) * H + h) * W + w) * out_C;
+        bcol = col0;
+      } else {
+        pixbase = out + ((static_cast<int64_t>(n) * H * up_k + static_cast<int64_t>(h) * up_k) * Wo + static_cast<int64_t>(w) * up_k) * out_C;
+        const int qq = col0 / up_cp;
+        bcol = col0 - qq * up_cp;
+        qi = qq / up_k;
+        qj = qq - qi * up_k;
       }
-      const float cs = warp_colsum16(sv, lane);
-      const float cq = warp_colsum16(sq, lane);
-      if ((lane & 1) == 0) {
-        const int cc = c + col16_of_lane(lane);
-        atomicAdd(&s_stat[0][cc], cs);
-        atomicAdd(&s_stat[1][cc], cq);
-      }
-    }
-    if (valid) {
-      uint4* d4 = reinterpret_cast<uint4*>(dst);
-      if (p.accumulate) {
-        uint4 o0 = d4[0], o1 = d4[1];
-        const uint32_t ou[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+      mbar_wait(&s_accfull[buf], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
+
+      auto do_chunk = [&](int k, uint32_t (&r)[16]) {
+        float v[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float2 f = unpack_bf16x2(ou[i]);
-          v[2 * i] += f.x;
-          v[2 * i + 1] += f.y;
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+        if (has_bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + bcol);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 bb = b4[i];
+            v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+          }
         }
+        if (do_stats) {
+          float sv[16], sq[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            sv[i] = valid ? v[i] : 0.f;
+            sq[i] = sv[i] * sv[i];
+          }
+          const float cs = warp_colsum16(sv, lane);
+          const float cq = warp_colsum16(sq, lane);
+          if ((lane & 1) == 0) {
+            const int cc = k * 16 + col16_of_lane(lane);
+            atomicAdd(&s_stat[0][cc], cs);
+            atomicAdd(&s_stat[1][cc], cq);
+          }
+        }
+        if (valid) emit_bf16x16(pixbase + (static_cast<int64_t>(qi) * Wo + qj) * out_C + bcol, v, acc);
+        bcol += 16;
+        if (epi_mode != 0 && bcol == up_cp) {   // next sub-pixel of the transposed convolution
+          bcol = 0;
+          if (++qj == up_k) { qj = 0; ++qi; }
+        }
+      };
+#pragma unroll 1
+      for (int k = k_begin; k < k_end; k += 2) {
+        const bool two = (k + 1 < k_end);   // warp uniform
+        uint32_t r[2][16];
+        tmem_ld16_nowait(taddr + k * 16, r[0]);
+        if (two) tmem_ld16_nowait(taddr + k * 16 + 16, r[1]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (u == 0 || two) do_chunk(k + u, r[u]);
       }
-      uint4 r0, r1;
-      r0.x = pack_bf16x2(v[0], v[1]);
-      r0.y = pack_bf16x2(v[2], v[3]);
-      r0.z = pack_bf16x2(v[4], v[5]);
-      r0.w = pack_bf16x2(v[6], v[7]);
-      r1.x = pack_bf16x2(v[8], v[9]);
-      r1.y = pack_bf16x2(v[10], v[11]);
-      r1.z = pack_bf16x2(v[12], v[13]);
-      r1.w = pack_bf16x2(v[14], v[15]);
-      d4[0] = r0;
-      d4[1] = r1;
+      // accumulator fully read: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_accempty[buf]);
+      if (do_stats) {
+        // TN == 1 is enforced by the host when statistics are fused: the whole tile belongs to sample n0.
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int i = etid; i < BN; i += 256) {
+          const int64_t o = static_cast<int64_t>(n0) * p.stat_C + ntile * BN + i;
+          atomicAdd(p.stat_sum + o, s_stat[0][i]);
+          atomicAdd(p.stat_sq + o, s_stat[1][i]);
+          s_stat[0][i] = 0.f;
+          s_stat[1][i] = 0.f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (do_stats) {
-    // TN == 1 is enforced by the host when statistics are fused: the whole tile belongs to sample n0.
-    for (int i = tid; i < BN; i += 128) {
-      const int64_t o = static_cast<int64_t>(n0) * p.stat_C + ntile * BN + i;
-      atomicAdd(p.stat_sum + o, s_stat[0][i]);
-      atomicAdd(p.stat_sq + o, s_stat[1][i]);
-    }
-  }
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
@@ -445,7 +494,7 @@ struct ConvGemmOp : public OpBase {
   int smem_bytes;
   double flops;
   int launch(cudaStream_t st) override {
-    conv_gemm_kernel<<<grid, 128, smem_bytes, st>>>(p);
+    conv_gemm_kernel<<<grid, 320, smem_bytes, st>>>(p);
     return check_launch("conv_gemm_kernel");
   }
   double op_flops() const override { return flops; }
@@ -469,6 +518,7 @@ int conv_gemm_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
     int rc = conv_halo_try_create(d, out);  // halo-tile kernel for 3x3 convs on large planes (conv_halo.cu)
     if (rc <= 0) return rc;                  // 0 = created, < 0 = error, > 0 = not eligible -> generic kernel below
   }
+  if (d->nouts > 0) return set_error(MTBC_ERR_INVALID, "conv_gemm: routed outputs need a halo-eligible 3x3 shape");
   if (d->nviews < 1 || d->nviews > MTBC_MAX_VIEWS || d->nseg < 1 || d->nseg > MTBC_MAX_SEGS)
     return set_error(MTBC_ERR_INVALID, "conv_gemm: bad nviews/nseg (%d, %d)", d->nviews, d->nseg);
   if (d->ncols % 32 != 0) return set_error(MTBC_ERR_INVALID, "conv_gemm: ncols %% 32 != 0");
@@ -486,7 +536,7 @@ int conv_gemm_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   const int BN = pick_bn(d->ncols, 256, 16);
   if (BN == 0) { delete op; return set_error(MTBC_ERR_INVALID, "conv_gemm: no N tile for ncols=%d", d->ncols); }
   p.BN = BN;
-  p.tmem_cols = tmem_cols_for(BN);
+  p.tmem_cols = tmem_cols_for(2 * BN);
   int kcmax = 32;
   int kc_of_view[MTBC_MAX_VIEWS];
   for (int i = 0; i < d->nviews; ++i) {
@@ -517,9 +567,11 @@ int conv_gemm_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   p.a_stage_bytes = 128 * kcmax * 2;
   p.stage_bytes = (128 + BN) * kcmax * 2;
   p.stage_bytes = (p.stage_bytes + 1023) & ~1023;
-  const int budget = (p.stage_bytes * 3 <= 100 * 1024) ? 100 * 1024 : 200 * 1024;
+  // small stages and <= 256 TMEM columns: two persistent CTAs per SM (they hide each other's pipeline bubbles)
+  const bool two = (p.stage_bytes * 3 <= 100 * 1024) && (2 * p.tmem_cols <= 512);
+  const int budget = two ? 100 * 1024 : 200 * 1024;
   int stages = budget / p.stage_bytes;
-  if (stages > 6) stages = 6;
+  if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
   p.stages = stages;
   op->smem_bytes = stages * p.stage_bytes + 1024;
@@ -527,9 +579,21 @@ int conv_gemm_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   p.accumulate = d->accumulate; p.stat_C = d->stat_C;
   p.out = reinterpret_cast<__nv_bfloat16*>(d->out);
   p.bias = d->bias; p.stat_sum = d->stat_sum; p.stat_sq = d->stat_sq;
+  p.bias_len = d->epi_mode == 1 ? p.up_cp : d->ncols;
+  if (d->bias && p.bias_len > kMaxBias) { delete op; return set_error(MTBC_ERR_INVALID, "conv_gemm: bias longer than %d", kMaxBias); }
   if (d->stat_sum && TN != 1) { delete op; return set_error(MTBC_ERR_INVALID, "conv_gemm: fused statistics need >= 128 pixels per sample (TN=%d)", TN); }
   if (d->epi_mode == 1 && (p.up_cp % 16 != 0)) { delete op; return set_error(MTBC_ERR_INVALID, "conv_gemm: up_cp %% 16"); }
-  op->grid = dim3(p.tiles_w * p.tiles_h * tiles_n, d->ncols / BN, 1);
+  p.n_mtiles = p.tiles_w * p.tiles_h * tiles_n;
+  p.n_ntiles = d->ncols / BN;
+  {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    int gx = sms * (two ? 2 : 1);
+    if (gx > p.n_mtiles * p.n_ntiles) gx = p.n_mtiles * p.n_ntiles;
+    op->grid = dim3(gx, 1, 1);
+  }
   op->flops = 2.0 * double(d->N) * d->H * d->W * double(d->ncols) * ksum;
   cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   if (e != cudaSuccess) { delete op; return set_error(MTBC_ERR_CUDA, "cudaFuncSetAttribute(conv_gemm): %s", cudaGetErrorString(e)); }

@@ -31,15 +31,20 @@ struct HaloSrc {
   int32_t b_off;        // byte offset of this source's first resident weight block inside one tap plane
 };
 
+struct HaloOut {
+  __nv_bfloat16* ptr;
+  int32_t out_C, col0, col_end, accumulate;
+};
+
 struct ConvHaloParams {
   CUtensorMap amap[MTBC_MAX_VIEWS];
   CUtensorMap wmap[2];
   HaloSrc src[MTBC_MAX_VIEWS];
-  int32_t nsrc;
+  HaloOut outs[MTBC_MAX_VIEWS];  // column ranges of the GEMM output -> destination tensors (>= 1 entry)
+  int32_t nsrc, nouts;
   int32_t W, H, N, tiles_w, tiles_h, n_mtiles;
   int32_t BN, tmem_cols, stages, a_stage_bytes, b_tap_bytes, b_total_bytes;
-  int32_t out_C, accumulate, stat_C;
-  __nv_bfloat16* out;
+  int32_t stat_C;
   const float* bias;
   float* stat_sum;
   float* stat_sq;
@@ -69,49 +74,73 @@ __device__ __forceinline__ void halo_issue_chunk(uint32_t d_addr, uint32_t a_lo,
 }
 
 
-// Epilogue of the halo kernel, run by the 4 warps that own the 4 TMEM lane quarters (thread <-> output pixel).
+// Epilogue of the halo kernel: 8 warps, two per TMEM lane quarter (thread <-> output pixel), each pair splitting the
+// tile's columns in halves.  The epilogue warps share their schedulers with nobody, so the loop is written for a short
+// dependent chain: destinations per 16-column chunk are precomputed in shared memory (s_chunk), TMEM loads are issued
+// in pairs before one wait, stores are 32-byte (one full sector per thread) and gradient accumulation is a
+// fire-and-forget bf16 reduction in L2 instead of a read-modify-write.
 //   RACC > 0 (= BN, 32 or 64): InstanceNorm partial sums (sum y, sum y^2 per column) live in registers across the
-//     tiles of one sample and are combined (butterfly shuffles -> per-warp partials in smem -> one global atomic per
+//     tiles of one sample and are combined (butterfly shuffles -> per-quarter partials in smem -> one global atomic per
 //     column) only when the sample changes: per tile the statistics cost 2 FP32 ops per element and nothing else.
 //   RACC == 0: any BN; statistics (if requested) are combined per tile.
+struct HaloChunk {
+  __nv_bfloat16* base;   // destination of column 0 of this chunk for pixel 0
+  int32_t out_C;
+  int32_t accumulate;
+};
+
+template <int V> struct IntC { static constexpr int value = V; };
+
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+
 template <int RACC>
 __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t tmem_base, int t_begin, int t_end,
                                               int ntile, int warp, int lane, const float* s_bias,
-                                              float (*s_part)[2][256], uint64_t* s_accfull, uint64_t* s_accempty) {
-  const int q = warp & 3;
+                                              float (*s_part)[2][256], const HaloChunk* s_chunk,
+                                              uint64_t* s_accfull, uint64_t* s_accempty) {
+  const int q = warp & 3;                  // TMEM lane quarter this warp may read
+  const int half = (warp - 2) >> 2;        // column half
   const int row = q * 32 + lane;
   const int tw = row & 7, th = row >> 3;
   const int BN = p.BN;
+  const int nchunks = BN >> 4;
+  const int k_begin = half ? (nchunks + 1) >> 1 : 0;
+  const int k_end = half ? nchunks : (nchunks + 1) >> 1;
   const bool do_stats = (p.stat_sum != nullptr);
-  const int etid = q * 32 + lane;
-  const int tiles_per_n = p.tiles_w * p.tiles_h;
-  constexpr int NR = RACC > 0 ? RACC : 1;
+  const bool has_bias = (p.bias != nullptr);
+  const int etid = (warp - 2) * 32 + lane;
+  const int tiles_w = p.tiles_w, tiles_per_n = p.tiles_w * p.tiles_h;
+  const int H = p.H, W = p.W, stat_C = p.stat_C;
+  float* const stat_sum = p.stat_sum;
+  float* const stat_sq = p.stat_sq;
+  constexpr int NR = RACC > 0 ? RACC / 2 : 1;   // columns of this warp's half
   float rs[NR], rq[NR];
 #pragma unroll
   for (int i = 0; i < NR; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
   int cur_n = t_begin < t_end ? t_begin / tiles_per_n : 0;
 
-  // combine the 4 warps' column partials and add them to the per-(n, channel) statistics
+  // combine the 4 quarters' column partials and add them to the per-(n, channel) statistics
   auto flush_cols = [&](int n) {
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    for (int i = etid; i < BN; i += 128) {
-      const int64_t o = static_cast<int64_t>(n) * p.stat_C + ntile * BN + i;
-      atomicAdd(p.stat_sum + o, s_part[0][0][i] + s_part[1][0][i] + s_part[2][0][i] + s_part[3][0][i]);
-      atomicAdd(p.stat_sq + o, s_part[0][1][i] + s_part[1][1][i] + s_part[2][1][i] + s_part[3][1][i]);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    for (int i = etid; i < BN; i += kEpiThreads) {
+      const int64_t o = static_cast<int64_t>(n) * stat_C + ntile * BN + i;
+      atomicAdd(stat_sum + o, s_part[0][0][i] + s_part[1][0][i] + s_part[2][0][i] + s_part[3][0][i]);
+      atomicAdd(stat_sq + o, s_part[0][1][i] + s_part[1][1][i] + s_part[2][1][i] + s_part[3][1][i]);
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
   };
   auto flush_regs = [&](int n) {
     if constexpr (RACC > 0) {
 #pragma unroll
-      for (int c = 0; c < RACC; c += 16) {
+      for (int c = 0; c < NR; c += 16) {
         float a[16], b[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) { a[i] = rs[c + i]; b[i] = rq[c + i]; rs[c + i] = 0.f; rq[c + i] = 0.f; }
         const float cs = warp_colsum16(a, lane);
         const float cq = warp_colsum16(b, lane);
         if ((lane & 1) == 0) {
-          const int cc = c + col16_of_lane(lane);
+          const int cc = k_begin * 16 + c + col16_of_lane(lane);
           s_part[q][0][cc] = cs;
           s_part[q][1][cc] = cq;
         }
@@ -120,68 +149,73 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
     }
   };
 
+  // one 16-column chunk: bias, statistics, bf16 store / accumulate
+  auto do_chunk = [&](int k, auto jc, uint32_t (&r)[16], int64_t pix) {
+    constexpr int J = decltype(jc)::value;   // position of the chunk inside this warp's half (RACC > 0 only)
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+    if (has_bias) {
+      const float4* b4 = reinterpret_cast<const float4*>(s_bias + k * 16);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 bb = b4[i];
+        v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+      }
+    }
+    if constexpr (RACC > 0) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { rs[J * 16 + i] += v[i]; rq[J * 16 + i] = fmaf(v[i], v[i], rq[J * 16 + i]); }
+    } else if (do_stats) {
+      float sq[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) sq[i] = v[i] * v[i];
+      const float cs = warp_colsum16(v, lane);
+      const float cq = warp_colsum16(sq, lane);
+      if ((lane & 1) == 0) {
+        const int cc = k * 16 + col16_of_lane(lane);
+        s_part[q][0][cc] = cs;
+        s_part[q][1][cc] = cq;
+      }
+    }
+    const HaloChunk hc = s_chunk[k];
+    emit_bf16x16(hc.base + pix * hc.out_C, v, hc.accumulate != 0);
+  };
+
   int it = 0;
   for (int t = t_begin; t < t_end; ++t, ++it) {
     const int buf = it & 1;
     const uint32_t acc_phase = (it >> 1) & 1;
     const int n = t / tiles_per_n;
     const int rem = t - n * tiles_per_n;
-    const int w = (rem % p.tiles_w) * 8 + tw;
-    const int h = (rem / p.tiles_w) * 16 + th;
+    const int tr = rem / tiles_w;
+    const int w = (rem - tr * tiles_w) * 8 + tw;
+    const int h = tr * 16 + th;
     if (RACC > 0 && n != cur_n) { flush_regs(cur_n); cur_n = n; }
+    const int64_t pix = (static_cast<int64_t>(n) * H + h) * W + w;
     mbar_wait(&s_accfull[buf], acc_phase);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
-    __nv_bfloat16* dst_row = p.out + ((static_cast<int64_t>(n) * p.H + h) * p.W + w) * p.out_C + ntile * BN;
+    if constexpr (RACC > 0) {
+      // this warp's half is NR / 16 = 1 or 2 chunks, known at compile time: statistics stay in registers
+      uint32_t r[NR / 16][16];
+      tmem_ld16_nowait(taddr + k_begin * 16, r[0]);
+      if constexpr (NR > 16) tmem_ld16_nowait(taddr + k_begin * 16 + 16, r[1]);
+      tmem_wait_ld();
+      do_chunk(k_begin, IntC<0>{}, r[0], pix);
+      if constexpr (NR > 16) do_chunk(k_begin + 1, IntC<1>{}, r[1], pix);
+    } else {
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 16) {
-      float v[16];
-      tmem_ld16(taddr + c, v);
-      if (p.bias != nullptr) {
-        const float4* b4 = reinterpret_cast<const float4*>(s_bias + c);
+      for (int k = k_begin; k < k_end; k += 2) {
+        const bool two = (k + 1 < k_end);   // warp uniform
+        uint32_t r[2][16];
+        tmem_ld16_nowait(taddr + k * 16, r[0]);
+        if (two) tmem_ld16_nowait(taddr + k * 16 + 16, r[1]);
+        tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 bb = b4[i];
-          v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
-        }
+        for (int u = 0; u < 2; ++u)
+          if (u == 0 || two) do_chunk(k + u, IntC<0>{}, r[u], pix);
       }
-      if constexpr (RACC > 0) {
-        // c is a multiple of 16 < RACC: unrolled select keeps rs/rq in registers
-#pragma unroll
-        for (int cb = 0; cb < RACC; cb += 16) {
-          if (c == cb) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { rs[cb + i] += v[i]; rq[cb + i] = fmaf(v[i], v[i], rq[cb + i]); }
-          }
-        }
-      } else if (do_stats) {
-        float sq[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) sq[i] = v[i] * v[i];
-        const float cs = warp_colsum16(v, lane);
-        const float cq = warp_colsum16(sq, lane);
-        if ((lane & 1) == 0) {
-          const int cc = c + col16_of_lane(lane);
-          s_part[q][0][cc] = cs;
-          s_part[q][1][cc] = cq;
-        }
-      }
-      uint4* d4 = reinterpret_cast<uint4*>(dst_row + c);
-      if (p.accumulate) {
-        const uint4 o0 = d4[0], o1 = d4[1];
-        const uint32_t ou[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float2 f = unpack_bf16x2(ou[i]);
-          v[2 * i] += f.x;
-          v[2 * i + 1] += f.y;
-        }
-      }
-      uint4 r0, r1;
-      r0.x = pack_bf16x2(v[0], v[1]); r0.y = pack_bf16x2(v[2], v[3]); r0.z = pack_bf16x2(v[4], v[5]); r0.w = pack_bf16x2(v[6], v[7]);
-      r1.x = pack_bf16x2(v[8], v[9]); r1.y = pack_bf16x2(v[10], v[11]); r1.z = pack_bf16x2(v[12], v[13]); r1.w = pack_bf16x2(v[14], v[15]);
-      d4[0] = r0;
-      d4[1] = r1;
     }
     // accumulator fully read: hand it back to the MMA warp
     tc_fence_before();
@@ -192,13 +226,17 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
   if (RACC > 0 && t_begin < t_end) flush_regs(cur_n);
 }
 
-__global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
+// MINB = resident CTAs per SM the register budget is compiled for: 2 for the narrow layers (small resident weights, two
+// CTAs overlap each other's pipeline bubbles), 1 for wide N tiles (no spills, one CTA owns the SM).
+template <int MINB>
+__global__ void __launch_bounds__(64 + kEpiThreads, MINB) conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t s_afull[kHaloMaxStages], s_aempty[kHaloMaxStages];
   __shared__ uint64_t s_bfull, s_accfull[2], s_accempty[2];
   __shared__ uint32_t s_tmem;
   __shared__ __align__(16) float s_bias[256];
-  __shared__ float s_part[4][2][256];  // [epilogue warp][sum|sumsq][col]: per-warp column partials at a flush
+  __shared__ float s_part[4][2][256];  // [lane quarter][sum|sumsq][col]: per-warp column partials at a flush
+  __shared__ HaloChunk s_chunk[16];    // destination of every 16-column chunk of this CTA's N tile
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -211,11 +249,19 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
   const int t_begin = static_cast<int>(static_cast<int64_t>(p.n_mtiles) * blockIdx.x / gridDim.x);
   const int t_end = static_cast<int>(static_cast<int64_t>(p.n_mtiles) * (blockIdx.x + 1) / gridDim.x);
 
-  for (int i = tid; i < 256; i += 192) s_bias[i] = (p.bias != nullptr && i < BN) ? p.bias[ntile * BN + i] : 0.f;
+  for (int i = tid; i < 256; i += 64 + kEpiThreads) s_bias[i] = (p.bias != nullptr && i < BN) ? p.bias[ntile * BN + i] : 0.f;
+  if (tid < (BN >> 4)) {
+    const int gc = ntile * BN + tid * 16;
+    int o = 0;
+    while (o + 1 < p.nouts && gc >= p.outs[o].col_end) ++o;   // slices are ordered by column
+    s_chunk[tid].base = p.outs[o].ptr + (gc - p.outs[o].col0);
+    s_chunk[tid].out_C = p.outs[o].out_C;
+    s_chunk[tid].accumulate = p.outs[o].accumulate;
+  }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&s_afull[s], 1); mbar_init(&s_aempty[s], 1); }
     mbar_init(&s_bfull, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(&s_accfull[b], 1); mbar_init(&s_accempty[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&s_accfull[b], 1); mbar_init(&s_accempty[b], kEpiWarps); }
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -291,10 +337,10 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
       }
     }
   } else {
-    // -------------------------------------------------------------- epilogue warps 2..5 (TMEM lane quarter = warp % 4)
-    if (p.stat_sum != nullptr && BN == 32) halo_epilogue<32>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_accfull, s_accempty);
-    else if (p.stat_sum != nullptr && BN == 64) halo_epilogue<64>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_accfull, s_accempty);
-    else halo_epilogue<0>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_accfull, s_accempty);
+    // -------------------------------------------------------------- epilogue warps 2..9 (TMEM lane quarter = warp % 4)
+    if (p.stat_sum != nullptr && BN == 32) halo_epilogue<32>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_chunk, s_accfull, s_accempty);
+    else if (p.stat_sum != nullptr && BN == 64) halo_epilogue<64>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_chunk, s_accfull, s_accempty);
+    else halo_epilogue<0>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_chunk, s_accfull, s_accempty);
   }
 
   tc_fence_before();
@@ -306,14 +352,21 @@ __global__ void __launch_bounds__(192) conv_halo_kernel(const __grid_constant__ 
 }
 
 // ================================================================================================ weight gradient
+// dW[dh,dw][ci][co] = sum_p x[p + (dh,dw)][ci] * dy[p][co].  With p' = p + (dh,0) the sum becomes
+// sum_p' x[p' + (0,dw)][ci] * dy[p' - (dh,0)][co]: the three horizontal taps are the SAME x rows shifted by one pixel
+// (stacked along M through the leading-dimension offset = one pixel), and the three vertical taps are the SAME dy rows
+// shifted by one tile row (stacked along N, leading-dimension offset = 8 pixels).  One 128-pixel tile therefore costs
+// 8 MMAs of shape M = 128 ([dw=-1|0|+1|unused] x 32 ci), N = 3 x b_kc ([dh=+1|0|-1] x co), K = 16 pixels, instead of
+// 24 narrow ones: an SS MMA pays 32 cycles of shared-memory bandwidth for its A slice whatever N is, so wide N is what
+// makes the 24/48-channel layers cheap.
 struct WgradHaloParams {
-  CUtensorMap amap;       // x source, box (32, 10, 18, 1), 64B swizzle
-  CUtensorMap bmap;       // dy, box (b_kc, 8, 16, 1)
+  CUtensorMap amap;       // x source, box (32, 10, 16, 1), 64B swizzle: column halo only
+  CUtensorMap bmap;       // dy, box (b_kc, 8, 18, 1): row halo only
   int32_t a_C;            // padded channels of the source
-  int32_t b_kc, b_boxes;  // dy boxes per N tile
-  int32_t BN, n_tiles, tmem_cols, stages;
+  int32_t b_kc;           // dy channels per CTA (32: 64B swizzle, 64: 128B swizzle)
+  int32_t NN, n_tiles, tmem_cols, stages;
   int32_t tiles_w, tiles_h, n_ptiles, splits;
-  int32_t a_bytes, b_bytes, stage_bytes, b_box_bytes;
+  int32_t a_bytes, b_bytes, stage_bytes;
   int32_t n_rows, ld_k, k0;
   float* dw_acc;
 };
@@ -326,8 +379,8 @@ __global__ void __launch_bounds__(128) wgrad_halo_kernel(const __grid_constant__
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int split = blockIdx.x, chunk = blockIdx.y, ntile = blockIdx.z;
-  const int BN = p.BN;
+  // chunk (source channels) fastest: CTAs that run together read the same dy tiles -> L2 hits
+  const int chunk = blockIdx.x, split = blockIdx.y, ntile = blockIdx.z;
   const int per = (p.n_ptiles + p.splits - 1) / p.splits;
   const int pt_begin = split * per;
   const int pt_end = min(p.n_ptiles, pt_begin + per);
@@ -357,17 +410,16 @@ __global__ void __launch_bounds__(128) wgrad_halo_kernel(const __grid_constant__
         mbar_wait(&s_empty[stage], phase ^ 1u);
         uint8_t* a_dst = smem + stage * p.stage_bytes;
         uint8_t* b_dst = a_dst + p.a_bytes;
-        mbar_arrive_expect_tx(&s_full[stage], static_cast<uint32_t>(kHaloRows * 64 + p.b_bytes));
-        tma_load_4d(a_dst, &p.amap, &s_full[stage], chunk * 32, w0 - 1, h0 - 1, n);
-        for (int b = 0; b < p.b_boxes; ++b)
-          tma_load_4d(b_dst + b * p.b_box_bytes, &p.bmap, &s_full[stage], ntile * BN + b * p.b_kc, w0, h0, n);
+        mbar_arrive_expect_tx(&s_full[stage], static_cast<uint32_t>(kHaloW * 16 * 64 + 8 * kHaloH * p.b_kc * 2));
+        tma_load_4d(a_dst, &p.amap, &s_full[stage], chunk * 32, w0 - 1, h0, n);
+        tma_load_4d(b_dst, &p.bmap, &s_full[stage], ntile * p.b_kc, w0, h0 - 1, n);
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     } else if (warp == 1 && elect_one()) {
-      const uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
+      const uint32_t idesc = umma_idesc_bf16(128, p.NN, 1, 1);
       const uint32_t b_rowb = p.b_kc * 2u;
-      const uint32_t a_hi = umma_desc_hi(kHaloW * 64, 4u);
-      const uint32_t b_hi = umma_desc_hi(8 * b_rowb, p.b_kc == 64 ? 2u : 4u);
+      const uint32_t a_hi = umma_desc_hi(kHaloW * 64, 4u);                      // K step of 8 pixels = one halo row
+      const uint32_t b_hi = umma_desc_hi(8 * b_rowb, p.b_kc == 64 ? 2u : 4u);   // K step of 8 pixels = one tile row
       const uint32_t b_j16 = b_rowb;  // 16 pixel rows of the dy tile, in 16-byte units
       int stage = 0;
       uint32_t phase = 0;
@@ -375,16 +427,12 @@ __global__ void __launch_bounds__(128) wgrad_halo_kernel(const __grid_constant__
         mbar_wait(&s_full[stage], phase);
         tc_fence_after();
         const uint32_t a_base = smem_u32(smem + stage * p.stage_bytes);
-        const uint32_t a_lo = umma_desc_lo(a_base, 64);
-        const uint32_t b_lo = umma_desc_lo(a_base + p.a_bytes, p.b_box_bytes);
+        const uint32_t a_lo = umma_desc_lo(a_base, 64);                          // next M atom = next pixel (dw + 1)
+        const uint32_t b_lo = umma_desc_lo(a_base + p.a_bytes, 8 * b_rowb);      // next N atom = next tile row (dh - 1)
         const uint32_t first = (pt > pt_begin) ? 1u : 0u;
 #pragma unroll
-        for (int g = 0; g < 3; ++g) {      // kernel row dh = g - 1; M = [dw=-1 | dw=0 | dw=+1 | unused] x 32 channels
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {    // 16 pixels = tile rows 2j, 2j+1
-            umma_bf16_lohi(tmem_base + static_cast<uint32_t>(g * BN), a_lo + ((2 * j + g) * kHaloW) * 4, a_hi,
-                           b_lo + j * b_j16, b_hi, idesc, j > 0 ? 1u : first);
-          }
+        for (int j = 0; j < 8; ++j) {    // 16 pixels = tile rows 2j, 2j+1
+          umma_bf16_lohi(tmem_base, a_lo + (2 * j * kHaloW) * 4, a_hi, b_lo + j * b_j16, b_hi, idesc, j > 0 ? 1u : first);
         }
         umma_commit(&s_empty[stage]);
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -396,23 +444,22 @@ __global__ void __launch_bounds__(128) wgrad_halo_kernel(const __grid_constant__
     tc_fence_after();
     __syncwarp();
 
-    const int m = warp * 32 + lane;  // warp = horizontal tap (dw + 1), lane = channel inside the chunk
+    // warp = horizontal tap (dw + 1), lane = channel inside the chunk; column group a = 0,1,2 <-> dh = 1 - a
     const int ci = chunk * 32 + lane;
     const bool valid = (warp < 3) && (ci < p.a_C);
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    for (int g = 0; g < 3; ++g) {
-      const int tap = g * 3 + warp;
-      for (int c = 0; c < BN; c += 16) {
+    for (int a = 0; a < 3; ++a) {
+      const int tap = (2 - a) * 3 + warp;
+      for (int c = 0; c < p.b_kc; c += 16) {
         float v[16];
-        tmem_ld16(taddr + g * BN + c, v);
+        tmem_ld16(taddr + a * p.b_kc + c, v);
         if (valid) {
-          float* dst = p.dw_acc + (static_cast<int64_t>(tap) * p.n_rows + ntile * BN + c) * p.ld_k + p.k0 + ci;
+          float* dst = p.dw_acc + (static_cast<int64_t>(tap) * p.n_rows + ntile * p.b_kc + c) * p.ld_k + p.k0 + ci;
 #pragma unroll
           for (int i = 0; i < 16; ++i) atomicAdd(dst + static_cast<int64_t>(i) * p.ld_k, v[i]);
         }
       }
     }
-    (void)m;
   }
   tc_fence_before();
   __syncthreads();
@@ -436,8 +483,10 @@ struct ConvHaloOp : public OpBase {
   dim3 grid;
   int smem_bytes;
   double flops;
+  int ctas_per_sm = 1;
   int launch(cudaStream_t st) override {
-    conv_halo_kernel<<<grid, 192, smem_bytes, st>>>(p);
+    if (ctas_per_sm == 2) conv_halo_kernel<2><<<grid, 64 + kEpiThreads, smem_bytes, st>>>(p);
+    else conv_halo_kernel<1><<<grid, 64 + kEpiThreads, smem_bytes, st>>>(p);
     return check_launch("conv_halo_kernel");
   }
   double op_flops() const override { return flops; }
@@ -458,6 +507,18 @@ struct WgradHaloOp : public OpBase {
 int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   if (halo_disabled()) return 1;
   if (d->epi_mode != 0 || d->nviews < 1 || d->nviews > MTBC_MAX_VIEWS || d->nseg != 9 * d->nviews) return 1;
+  if (d->nouts < 0 || d->nouts > MTBC_MAX_VIEWS) return set_error(MTBC_ERR_INVALID, "conv_gemm: bad nouts");
+  if (d->nouts > 0) {
+    if (d->bias || d->stat_sum) return set_error(MTBC_ERR_INVALID, "conv_gemm: routed outputs take no bias / statistics");
+    int col = 0;
+    for (int i = 0; i < d->nouts; ++i) {
+      const mtbc_out_slice& o = d->outs[i];
+      if (!o.ptr || o.col0 != col || o.ncols <= 0 || o.ncols % 32 != 0 || o.out_C < o.ncols)
+        return set_error(MTBC_ERR_INVALID, "conv_gemm: output slice %d malformed", i);
+      col += o.ncols;
+    }
+    if (col != d->ncols) return set_error(MTBC_ERR_INVALID, "conv_gemm: output slices do not tile ncols");
+  }
   if (d->H % 16 != 0 || d->W % 8 != 0 || d->w_ntaps != 9 || d->ncols % 32 != 0) return 1;
   // every view must appear with the full 3x3 stencil, tap index = (dh+1)*3 + (dw+1), one weight column offset
   int wk0[MTBC_MAX_VIEWS];
@@ -478,12 +539,20 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
     if (a.W != d->W || a.H != d->H || a.N != d->N || a.C % 32 != 0) return 1;
     kused += a.C;
   }
-  // N tile such that the layer's weights stay resident in shared memory
+  // N tile such that the layer's weights stay resident in shared memory next to at least two halo stages
+  int kc_any = 32;
+  for (int v = 0; v < d->nviews; ++v) if (d->views[v].C % 64 == 0 && wk0[v] % 64 == 0) kc_any = 64;
+  const int a_stage = ((kHaloRows * kc_any * 2) + 1023) & ~1023;
   int BN = 0;
-  for (int bn = 16; bn <= 256 && bn <= d->ncols; bn += 16)
-    if (d->ncols % bn == 0 && 9 * bn * kused * 2 <= 120 * 1024) BN = bn;
+  for (int bn = 16; bn <= 256 && bn <= d->ncols; bn += 16) {
+    if (d->ncols % bn != 0) continue;
+    const int wbytes = 9 * bn * kused * 2;
+    // single-output layers keep the historical 120 KB cap (more halo stages); routed outputs (fused data gradients)
+    // prefer wide N tiles: the dy halo is then read once per tile instead of once per source
+    const int cap = d->nouts > 0 ? 200 * 1024 - 2 * a_stage : 120 * 1024;
+    if (wbytes <= cap) BN = bn;
+  }
   if (BN < 32 && BN != d->ncols) return 1;
-  if (d->stat_sum && false) return 1;
 
   ConvHaloOp* op = new ConvHaloOp();
   ConvHaloParams& p = op->p;
@@ -525,15 +594,28 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   if (stages < 2) { delete op; return 1; }
   p.stages = stages;
   op->smem_bytes = p.b_total_bytes + stages * p.a_stage_bytes + 1024;
-  const int ctas_per_sm = (op->smem_bytes + 6 * 1024) * 2 <= 227 * 1024 ? 2 : 1;
+  const int ctas_per_sm = ((op->smem_bytes + 6 * 1024) * 2 <= 227 * 1024 && 2 * p.tmem_cols <= 512) ? 2 : 1;
+  op->ctas_per_sm = ctas_per_sm;
   int gx = sm_count() * ctas_per_sm;
   if (gx > p.n_mtiles) gx = p.n_mtiles;
-  p.out_C = d->out_C; p.accumulate = d->accumulate; p.stat_C = d->stat_C;
-  p.out = reinterpret_cast<__nv_bfloat16*>(d->out);
+  p.stat_C = d->stat_C;
+  if (d->nouts > 0) {
+    p.nouts = d->nouts;
+    for (int i = 0; i < d->nouts; ++i) {
+      p.outs[i].ptr = reinterpret_cast<__nv_bfloat16*>(d->outs[i].ptr);
+      p.outs[i].out_C = d->outs[i].out_C; p.outs[i].col0 = d->outs[i].col0;
+      p.outs[i].col_end = d->outs[i].col0 + d->outs[i].ncols; p.outs[i].accumulate = d->outs[i].accumulate;
+    }
+  } else {
+    p.nouts = 1;
+    p.outs[0].ptr = reinterpret_cast<__nv_bfloat16*>(d->out);
+    p.outs[0].out_C = d->out_C; p.outs[0].col0 = 0; p.outs[0].col_end = d->ncols; p.outs[0].accumulate = d->accumulate;
+  }
   p.bias = d->bias; p.stat_sum = d->stat_sum; p.stat_sq = d->stat_sq;
   op->grid = dim3(gx, d->ncols / BN, 1);
   op->flops = 2.0 * double(d->N) * d->H * d->W * double(d->ncols) * kused * 9.0;
-  cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
   if (e != cudaSuccess) { delete op; return set_error(MTBC_ERR_CUDA, "cudaFuncSetAttribute(conv_halo): %s", cudaGetErrorString(e)); }
   *out = op;
   return 0;
@@ -551,24 +633,19 @@ int wgrad_halo_try_create(const mtbc_wgrad_desc* d, OpBase** out) {
   const mtbc_act_view& b = d->b_views[0];
   if (a.C % 32 != 0 || b.C % 32 != 0 || a.W != d->W || a.H != d->H || a.N != d->N) return 1;
   const int b_kc = (b.C % 64 == 0) ? 64 : 32;
-  int BN = 0;
-  for (int bn = b_kc; bn <= 128 && bn <= b.C; bn += b_kc)
-    if (b.C % bn == 0 && bn % 16 == 0) BN = bn;
-  if (BN == 0) return 1;
   WgradHaloOp* op = new WgradHaloOp();
   WgradHaloParams& p = op->p;
   memset(&p, 0, sizeof(p));
-  int rc = encode_act(&p.amap, a, 32, kHaloW, kHaloH, 1);
+  int rc = encode_act(&p.amap, a, 32, kHaloW, 16, 1);
   if (rc) { delete op; return rc; }
-  rc = encode_act(&p.bmap, b, b_kc, 8, 16, 1);
+  rc = encode_act(&p.bmap, b, b_kc, 8, kHaloH, 1);
   if (rc) { delete op; return rc; }
-  p.a_C = a.C; p.b_kc = b_kc; p.BN = BN; p.n_tiles = b.C / BN; p.b_boxes = BN / b_kc;
-  p.tmem_cols = tmem_cols_pow2(3 * BN);
+  p.a_C = a.C; p.b_kc = b_kc; p.NN = 3 * b_kc; p.n_tiles = b.C / b_kc;
+  p.tmem_cols = tmem_cols_pow2(p.NN);
   p.tiles_w = d->W / 8; p.tiles_h = d->H / 16;
   p.n_ptiles = p.tiles_w * p.tiles_h * d->N;
-  p.a_bytes = ((kHaloRows * 64) + 1023) & ~1023;  // 12 KB
-  p.b_box_bytes = 128 * b_kc * 2;
-  p.b_bytes = p.b_boxes * p.b_box_bytes;
+  p.a_bytes = ((kHaloW * 16 * 64) + 1023) & ~1023;            // 10 KB
+  p.b_bytes = ((8 * kHaloH * b_kc * 2) + 1023) & ~1023;       // 9 / 18 KB
   p.stage_bytes = p.a_bytes + p.b_bytes;
   int stages = (96 * 1024) / p.stage_bytes;  // <= half an SM: two CTAs hide each other's epilogue / start-up
   if (stages > kHaloMaxStages) stages = kHaloMaxStages;
@@ -586,8 +663,9 @@ int wgrad_halo_try_create(const mtbc_wgrad_desc* d, OpBase** out) {
   }
   if (splits > p.n_ptiles) splits = p.n_ptiles;
   if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
   p.splits = splits;
-  op->grid = dim3(splits, chunks, p.n_tiles);
+  op->grid = dim3(chunks, splits, p.n_tiles);
   op->flops = 2.0 * double(d->N) * d->H * d->W * double(a.C) * double(b.C) * 9.0;
   cudaError_t e = cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   if (e != cudaSuccess) { delete op; return set_error(MTBC_ERR_CUDA, "cudaFuncSetAttribute(wgrad_halo): %s", cudaGetErrorString(e)); }

@@ -192,7 +192,9 @@ int param_jobs_create(const mtbc_param_job* jobs, int n, OpBase** out) {
   std::vector<int32_t> cj, cf;
   for (int a = 0; a < n; ++a) {
     const int64_t e = job_elems(jobs[a]);
-    if (e < 0 || !jobs[a].src || !jobs[a].dst0) return set_error(MTBC_ERR_INVALID, "param_jobs: job %d is malformed", a);
+    const bool is_pack = jobs[a].kind == MTBC_JOB_PACK_CONV || jobs[a].kind == MTBC_JOB_PACK_CONVT;
+    if (e < 0 || !jobs[a].src || !(jobs[a].dst0 || (is_pack && jobs[a].dst1)))
+      return set_error(MTBC_ERR_INVALID, "param_jobs: job %d is malformed", a);
     h[a].kind = jobs[a].kind;
     for (int k = 0; k < 11; ++k) h[a].i[k] = jobs[a].i[k];
     h[a].src = jobs[a].src; h[a].dst0 = jobs[a].dst0; h[a].dst1 = jobs[a].dst1;

@@ -146,6 +146,34 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Same without the wait: issue several loads back to back, then one tmem_wait_ld() -- the epilogue warps are alone on
+// their scheduler, so every exposed TMEM round trip is dead time.
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 32-byte (256-bit) global store of 16 bf16: one full sector per thread, no partial-sector merges in L2.
+__device__ __forceinline__ void st_global_256(void* p, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4,
+                                              uint32_t w5, uint32_t w6, uint32_t w7) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w0), "r"(w1), "r"(w2), "r"(w3), "r"(w4),
+               "r"(w5), "r"(w6), "r"(w7)
+               : "memory");
+}
+// Fire-and-forget bf16 accumulation of 8 values (16 B) in L2: gradient accumulation for tensors with several
+// consumers without the read-modify-write round trip in the epilogue.
+__device__ __forceinline__ void red_add_bf16x8(void* p, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+  asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(w0), "r"(w1), "r"(w2), "r"(w3)
+               : "memory");
+}
+// 16 fp32 -> bf16 -> global (store or accumulate), 32 B per thread.
+__device__ __forceinline__ void emit_bf16x16(__nv_bfloat16* dst, const float (&v)[16], bool accumulate);
+
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor (sm_100 "version 1"), see DESIGN.md section "UMMA descriptors".
 //   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4
@@ -238,6 +266,17 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(t);
+}
+__device__ __forceinline__ void emit_bf16x16(__nv_bfloat16* dst, const float (&v)[16], bool accumulate) {
+  const uint32_t w0 = pack_bf16x2(v[0], v[1]), w1 = pack_bf16x2(v[2], v[3]), w2 = pack_bf16x2(v[4], v[5]),
+                 w3 = pack_bf16x2(v[6], v[7]), w4 = pack_bf16x2(v[8], v[9]), w5 = pack_bf16x2(v[10], v[11]),
+                 w6 = pack_bf16x2(v[12], v[13]), w7 = pack_bf16x2(v[14], v[15]);
+  if (accumulate) {
+    red_add_bf16x8(dst, w0, w1, w2, w3);
+    red_add_bf16x8(dst + 8, w4, w5, w6, w7);
+  } else {
+    st_global_256(dst, w0, w1, w2, w3, w4, w5, w6, w7);
+  }
 }
 
 }  // namespace mtbc

@@ -15,7 +15,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import ActView, ConvGemmDesc, GemmSeg, WgradDesc, WgradTap
+from ._lib import OutSlice, ActView, ConvGemmDesc, GemmSeg, WgradDesc, WgradTap
 
 
 def pad32(c: int) -> int:
@@ -128,7 +128,7 @@ def _create_gemm(d: ConvGemmDesc, keep, kind) -> Op:
 
 def conv3x3_fwd_op(srcs: Sequence[Feat], wpack: torch.Tensor, out: Feat, bias: Optional[torch.Tensor] = None,
                    stat_sum: Optional[torch.Tensor] = None, stat_sq: Optional[torch.Tensor] = None,
-                   accumulate: bool = False, ksz: int = 3) -> Op:
+                   accumulate: bool = False, ksz: int = 3, kind: str = "conv3x3_fwd") -> Op:
     """wpack: bf16 [ksz*ksz][out.Cp][Ktot] laid out by `k_offsets(srcs)`."""
     offs, ktot = k_offsets(srcs)
     assert wpack.shape == (ksz * ksz, out.Cp, ktot), (wpack.shape, (ksz * ksz, out.Cp, ktot))
@@ -152,12 +152,41 @@ def conv3x3_fwd_op(srcs: Sequence[Feat], wpack: torch.Tensor, out: Feat, bias: O
     d.stat_sq = None if stat_sq is None else stat_sq.data_ptr()
     d.stat_C = out.Cp
     d.accumulate = int(accumulate)
-    return _create_gemm(d, [*(s.t for s in srcs), wpack, out.t, bias, stat_sum, stat_sq], "conv3x3_fwd")
+    d.nouts = 0
+    return _create_gemm(d, [*(s.t for s in srcs), wpack, out.t, bias, stat_sum, stat_sq], kind)
 
 
 def conv3x3_dgrad_op(dy: Feat, wd: torch.Tensor, dx: Feat, accumulate: bool, ksz: int = 3) -> Op:
     """wd: bf16 [ksz*ksz][dx.Cp][dy.Cp] (flipped taps, transposed channels) -> dx (+)= conv(dy, wd)."""
-    return conv3x3_fwd_op([dy], wd, dx, accumulate=accumulate, ksz=ksz)
+    return conv3x3_fwd_op([dy], wd, dx, accumulate=accumulate, ksz=ksz, kind="conv3x3_dgrad")
+
+
+def conv3x3_dgrad_multi_op(dy: Feat, wd_all: torch.Tensor, dxs: Sequence[Feat], accumulates: Sequence[bool]) -> Op:
+    """Fused data gradient of a conv over a folded concat: ONE launch reads dy once and writes every source's gradient.
+    wd_all: bf16 [9][sum(dx.Cp)][dy.Cp] (flipped taps, rows = the sources' padded channels back to back).
+    Raises MtbcError when the shape is not served by the halo kernel (caller falls back to one launch per source)."""
+    rows = sum(f.Cp for f in dxs)
+    assert wd_all.shape == (9, rows, dy.Cp) and wd_all.is_contiguous(), (wd_all.shape, rows, dy.Cp)
+    d = ConvGemmDesc()
+    d.nviews = 1
+    d.views[0] = _view(dy)
+    n = 0
+    for r in range(3):
+        for c in range(3):
+            d.seg[n] = GemmSeg(0, r - 1, c - 1, 0, r * 3 + c)
+            n += 1
+    d.nseg = n
+    d.wpack = wd_all.data_ptr(); d.w_ntaps = 9; d.w_ktot = dy.Cp; d.ncols = rows
+    d.W, d.H, d.N = dy.W, dy.H, dy.N
+    d.epi_mode = 0; d.out = None; d.out_C = 0; d.up_k = 1; d.up_cp = rows
+    d.bias = None; d.stat_sum = None; d.stat_sq = None; d.stat_C = 0; d.accumulate = 0
+    d.nouts = len(dxs)
+    col = 0
+    for i, (f, acc) in enumerate(zip(dxs, accumulates)):
+        assert (f.N, f.H, f.W) == (dy.N, dy.H, dy.W)
+        d.outs[i] = OutSlice(f.t.data_ptr(), f.Cp, col, f.Cp, int(acc))
+        col += f.Cp
+    return _create_gemm(d, [dy.t, wd_all, *(f.t for f in dxs)], "conv3x3_dgrad")
 
 
 def convT_fwd_op(x: Feat, wf: torch.Tensor, out: Feat, k: int, bias: Optional[torch.Tensor]) -> Op:

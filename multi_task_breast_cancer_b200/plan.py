@@ -84,13 +84,15 @@ class JobTable:
         self.jobs: List[_lib.ParamJob] = []
         self._keep: List[object] = []
 
-    def add(self, kind: int, ints: Sequence[int], src: torch.Tensor, dst0: torch.Tensor,
+    def add(self, kind: int, ints: Sequence[int], src: torch.Tensor, dst0: Optional[torch.Tensor],
             dst1: Optional[torch.Tensor] = None):
         j = _lib.ParamJob()
         j.kind = kind
         for k, v in enumerate(ints):
             j.i[k] = int(v)
-        j.src = src.data_ptr(); j.dst0 = dst0.data_ptr(); j.dst1 = None if dst1 is None else dst1.data_ptr()
+        j.src = src.data_ptr()
+        j.dst0 = None if dst0 is None else dst0.data_ptr()
+        j.dst1 = None if dst1 is None else dst1.data_ptr()
         self.jobs.append(j)
         self._keep += [src, dst0, dst1]
 
@@ -264,13 +266,7 @@ class Plan:
                 self.tc_flops_bwd += o.flops
                 blk.append(_mk_op(o, 2.0 * N * H * Wd * Cout * f.C * 9, f"{name} wgrad {N}x{H}x{Wd} {f.C}x{Cout}"))
             self._mark_grad(w, b)
-            for s, wd in zip(srcs, pk["wd"]):
-                g = s.grad()
-                o = ops.conv3x3_dgrad_op(dy, wd, g, accumulate=s.g_init)
-                self.tc_flops_bwd += o.flops
-                blk.append(_mk_op(o, 2.0 * N * H * Wd * Cout * s.feat.C * 9,
-                                  f"{name} dgrad {N}x{H}x{Wd} {s.feat.C}<-{Cout} acc={int(o.kind is None)}"))
-                s.g_init = True
+            self._emit_dgrad(blk, srcs, dy, w, pk, name, Cout)
             return blk
         self._bwd_blocks.append(backward)
         return a, p
@@ -285,18 +281,71 @@ class Plan:
         Wt = self.P(w)
         offs, ktot = ops.k_offsets(feats)
         wf = torch.zeros(9, Cp, ktot, dtype=torch.bfloat16, device=self.device)
-        wds = [torch.zeros(9, f.Cp, Cp, dtype=torch.bfloat16, device=self.device) if self.training else None
-               for f in feats]
         st_c = [f.C for f in feats]
         c0 = 0
-        for cs, off, wd in zip(st_c, offs, wds):
+        for cs, off in zip(st_c, offs):
             self.pack_jobs.add(_lib.JOB_PACK_CONV, [Wt.shape[0], Wt.shape[1], 3, c0, cs, wf.shape[1], wf.shape[2], off,
-                                                    0 if wd is None else wd.shape[1], 0 if wd is None else wd.shape[2]],
-                               Wt, wf, wd)
+                                                    0, 0], Wt, wf, None)
             c0 += cs
-        pk = {"wf": wf, "wd": wds, "offs": offs, "ktot": ktot, "src_cp": [f.Cp for f in feats], "src_c": st_c}
+        pk = {"wf": wf, "offs": offs, "ktot": ktot, "src_cp": [f.Cp for f in feats], "src_c": st_c, "Cp": Cp}
         self._packed[key] = pk
         return pk
+
+    def _dgrad_pack(self, w: str, pk: dict, fused: bool):
+        """Data-gradient operand(s) of a conv weight, created when the backward is emitted: one tall pack
+        [9][sum Cp_src][Cp_out] for the fused launch, or one [9][Cp_src][Cp_out] per source."""
+        key = "wd_all" if fused else "wd"
+        if key in pk:
+            return pk[key]
+        Wt = self.P(w)
+        Cp = pk["Cp"]
+        rows = sum(pk["src_cp"])
+        if fused:
+            wd_all = torch.zeros(9, rows, Cp, dtype=torch.bfloat16, device=self.device)
+            c0, r0 = 0, 0
+            for cs, cp in zip(pk["src_c"], pk["src_cp"]):
+                # rows of this source start at r0 inside every tap plane: pass the offset pointer, plane stride = rows
+                self.pack_jobs.add(_lib.JOB_PACK_CONV, [Wt.shape[0], Wt.shape[1], 3, c0, cs, 0, 0, 0, rows, Cp],
+                                   Wt, None, wd_all[0, r0:])
+                c0 += cs
+                r0 += cp
+            self._keep.append(wd_all)
+            pk[key] = wd_all
+        else:
+            wds = []
+            c0 = 0
+            for cs, cp in zip(pk["src_c"], pk["src_cp"]):
+                wd = torch.zeros(9, cp, Cp, dtype=torch.bfloat16, device=self.device)
+                self.pack_jobs.add(_lib.JOB_PACK_CONV, [Wt.shape[0], Wt.shape[1], 3, c0, cs, 0, 0, 0, cp, Cp],
+                                   Wt, None, wd)
+                c0 += cs
+                wds.append(wd)
+            pk[key] = wds
+        return pk[key]
+
+    def _emit_dgrad(self, blk, srcs, dy: Feat, w: str, pk: dict, name: str, Cout: int):
+        N, H, Wd = dy.N, dy.H, dy.W
+        if len(srcs) > 1 and H % 16 == 0 and Wd % 8 == 0 and not os.environ.get("MTBC_NO_FUSED_DGRAD"):
+            grads = [s.grad() for s in srcs]
+            try:
+                o = ops.conv3x3_dgrad_multi_op(dy, self._dgrad_pack(w, pk, True), grads, [s.g_init for s in srcs])
+            except _lib.MtbcError:
+                o = None  # weights of this width do not fit next to the halo ring: one launch per source below
+            if o is not None:
+                self.tc_flops_bwd += o.flops
+                cin = sum(s.feat.C for s in srcs)
+                blk.append(_mk_op(o, 2.0 * N * H * Wd * Cout * cin * 9,
+                                  f"{name} dgrad {N}x{H}x{Wd} {[s.feat.C for s in srcs]}<-{Cout} fused"))
+                for s in srcs:
+                    s.g_init = True
+                return
+        for s, wd in zip(srcs, self._dgrad_pack(w, pk, False)):
+            g = s.grad()
+            o = ops.conv3x3_dgrad_op(dy, wd, g, accumulate=s.g_init)
+            self.tc_flops_bwd += o.flops
+            blk.append(_mk_op(o, 2.0 * N * H * Wd * Cout * s.feat.C * 9,
+                              f"{name} dgrad {N}x{H}x{Wd} {s.feat.C}<-{Cout} acc={int(s.g_init)}"))
+            s.g_init = True
 
     def _wg_accum(self, w: str, pk: dict) -> torch.Tensor:
         if w not in self._wg_acc:

@@ -30,7 +30,7 @@ def test_ctypes_signatures_match_header(lib):
 
 
 def test_abi_version_and_error_string(lib):
-    assert lib.mtbc_abi_version() == 1
+    assert lib.mtbc_abi_version() == 2
     assert isinstance(lib.mtbc_last_error(), bytes)
 
 

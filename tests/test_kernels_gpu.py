@@ -51,6 +51,25 @@ def test_conv3x3_dgrad(D, args):
     _run(D, D.conv_dgrad_case, *args)
 
 
+@pytest.mark.parametrize("args", [(2, 32, 32, [24, 48], 24), (2, 64, 64, [24, 24, 24, 24, 48], 24),
+                                  (2, 32, 32, [48, 48, 96], 48), (2, 16, 16, [96, 96, 192], 96)])
+def test_conv3x3_dgrad_fused_over_concat_sources(D, args):
+    """One launch reads dy once and writes every concat source's gradient (some stored, some accumulated)."""
+    _run(D, D.conv_dgrad_multi_case, *args)
+
+
+def test_conv3x3_dgrad_fused_refuses_what_it_cannot_serve(D):
+    """Weights too wide to stay resident next to the halo ring: creation fails cleanly (the plan then emits one launch
+    per source); nothing silently falls back inside the library."""
+    import torch
+    from multi_task_breast_cancer_b200 import _lib, ops
+    dy = ops.Feat.empty(2, 16, 16, 512)
+    dxs = [ops.Feat.empty(2, 16, 16, 384) for _ in range(3)]
+    wd = torch.zeros(9, 3 * 384, 512, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(_lib.MtbcError):
+        ops.conv3x3_dgrad_multi_op(dy, wd, dxs, [False] * 3)
+
+
 @pytest.mark.parametrize("args", [(2, 16, 16, 64, 64), (2, 16, 16, 32, 32), (2, 32, 32, 24, 24), (2, 32, 32, 48, 24),
                                   (2, 16, 16, 192, 96), (2, 16, 16, 128, 256), (2, 16, 16, 384, 512), (4, 8, 8, 320, 320),
                                   (2, 64, 64, 24, 24, 7)])

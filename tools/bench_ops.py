@@ -63,7 +63,19 @@ def convT(N, H, W, Cin, Cout, name):
     timeit(op, 2.0 * N * H * W * Cin * Cout * 4, name)
 
 
+def conv_dgrad_multi(N, H, W, src_C, Cout, name, acc):
+    dy = feat(N, H, W, Cout)
+    dxs = [feat(N, H, W, c) for c in src_C]
+    rows = sum(d.Cp for d in dxs)
+    wd = (torch.randn(9, rows, dy.Cp, device=dev) * 0.05).to(torch.bfloat16)
+    op = ops.conv3x3_dgrad_multi_op(dy, wd, dxs, [acc] * len(dxs))
+    timeit(op, 2.0 * N * H * W * Cout * sum(src_C) * 9, name)
+
+
 CASES = {
+    "dgrad_l0": lambda: conv_dgrad_multi(32, 256, 256, [24, 24, 24, 24, 48], 24, "dgrad L0 fused [24x4,48]<-24 store", False),
+    "dgrad_l0_acc": lambda: conv_dgrad_multi(32, 256, 256, [24, 24, 24, 24, 48], 24, "dgrad L0 fused [24x4,48]<-24 accumulate", True),
+    "dgrad_l1": lambda: conv_dgrad_multi(32, 128, 128, [48, 48, 48, 96], 48, "dgrad L1 fused [48x3,96]<-48 store", False),
     "l0_single": lambda: conv_fwd(32, 256, 256, [24], 24, "fwd L0 [24]->24 @256"),
     "l0_multi": lambda: conv_fwd(32, 256, 256, [24, 24, 24, 24, 48], 24, "fwd L0 [24x4,48]->24 @256"),
     "l1_multi": lambda: conv_fwd(32, 128, 128, [48, 48, 48, 48], 48, "fwd L1 [48x4]->48 @128"),

@@ -117,6 +117,44 @@ def conv_dgrad_case(N, H, W, Cin, Cout, accumulate, dyscale=1.0):
     run_case(fn, name)
 
 
+def conv_dgrad_multi_case(N, H, W, src_C, Cout, acc_flags=None):
+    """Fused data gradient: one launch writes the gradient of every concat source (some accumulating)."""
+    name = f"conv3x3_dgrad_multi N{N} {H}x{W} {src_C}<-{Cout}"
+
+    def fn():
+        Cin = sum(src_C)
+        w = rnd(Cout, Cin, 3, 3, scale=0.1)
+        dy = rnd(N, Cout, H, W)
+        dyf = Feat.from_nchw(dy)
+        flags = list(acc_flags) if acc_flags is not None else [i % 2 == 1 for i in range(len(src_C))]
+        bases = [rnd(N, c, H, W) for c in src_C]
+        dxs = [Feat.from_nchw(b) if f else Feat.empty(N, H, W, c) for b, f, c in zip(bases, flags, src_C)]
+        for d, f in zip(dxs, flags):
+            if not f:
+                d.t.fill_(7.0)  # must be overwritten, pad lanes included
+        rows = sum(d.Cp for d in dxs)
+        wd_all = torch.zeros(9, rows, dyf.Cp, dtype=torch.bfloat16, device=dev)
+        c0 = r0 = 0
+        for c, d in zip(src_C, dxs):
+            _lib.call("mtbc_pack_conv_weight", ops.ptr(w), Cout, Cin, 3, c0, c, None, 0, 0, 0, ops.ptr(wd_all[0, r0:]),
+                      rows, dyf.Cp, None)
+            c0 += c
+            r0 += d.Cp
+        op = ops.conv3x3_dgrad_multi_op(dyf, wd_all, dxs, flags)
+        op.launch()
+        torch.cuda.synchronize()
+        ref = F.conv_transpose2d(dy, w, padding=1)
+        c0 = 0
+        for i, (c, d, b, f) in enumerate(zip(src_C, dxs, bases, flags)):
+            r = ref[:, c0:c0 + c] + (b if f else 0)
+            report(f"{name} [src {i} acc={f}]", d.to_nchw(), r)
+            if d.Cp > c and not f:
+                report(f"{name} [src {i} pad lanes zero]", d.t[..., c:].float(), torch.zeros_like(d.t[..., c:].float()) + 0, tol=1e-6)
+            c0 += c
+
+    run_case(fn, name)
+
+
 def conv_wgrad_case(N, H, W, Cin, Cout, splits=0):
     name = f"conv3x3_wgrad N{N} {H}x{W} {Cin}->{Cout} splits={splits}"
 
@@ -530,6 +568,10 @@ def dgrad_cases():
     conv_dgrad_case(2, 16, 16, 64, 64, False)
     conv_dgrad_case(2, 32, 32, 24, 48, True)
     conv_dgrad_case(2, 16, 16, 192, 96, False)
+    conv_dgrad_multi_case(2, 32, 32, [24, 48], 24)
+    conv_dgrad_multi_case(2, 64, 64, [24, 24, 24, 24, 48], 24)
+    conv_dgrad_multi_case(2, 32, 32, [48, 48, 96], 48)
+    conv_dgrad_multi_case(2, 16, 16, [96, 96, 192], 96)
 
 
 def wgrad_cases():
