@@ -201,6 +201,13 @@ int mtbc_in_bwd_reduce(const void* dA, const void* y, int32_t N, int32_t HW, int
 int mtbc_in_bwd_apply(const void* dA, const void* y, int32_t N, int32_t HW, int32_t Cp, const float* mean,
                       const float* rstd, const float* gamma, const float* beta, float slope, const float* s1,
                       const float* s2, void* dy, float* dgamma, float* dbeta, int32_t C_true, void* stream);
+/* Both backward passes in one call (replaces the autograd of nn.InstanceNorm2d + LeakyReLU, MTnnUNet.py:35-36 / MONAI
+ * ADN "NDA").  When dA and y together exceed L2 this is ONE cooperative launch whose second pass re-reads the planes out
+ * of L2 (6 instead of 10 bytes of DRAM traffic per element); otherwise it is mtbc_in_bwd_reduce + mtbc_in_bwd_apply.
+ * s1, s2: fp32 [N][Cp] zeroed by the caller; counters: int32 [N] zeroed by the caller (group-barrier arrivals). */
+int mtbc_in_bwd(const void* dA, const void* y, int32_t N, int32_t HW, int32_t Cp, const float* mean, const float* rstd,
+                const float* gamma, const float* beta, float slope, float* s1, float* s2, void* dy, float* dgamma,
+                float* dbeta, int32_t C_true, int32_t* counters, void* stream);
 /* Stand-alone 2x2/2 max-pool backward: dA (+)= route(dP) to the first maximum of each window of a. */
 int mtbc_maxpool2_bwd(const void* a, const void* dP, int32_t N, int32_t H, int32_t W, int32_t Cp, void* dA,
                       int32_t accumulate, void* stream);

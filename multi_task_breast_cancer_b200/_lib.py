@@ -79,6 +79,8 @@ _SIGS = {
     "mtbc_in_bwd_reduce": [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp],
     "mtbc_in_bwd_apply": [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp,
                           c_vp, c_i32, c_vp],
+    "mtbc_in_bwd": [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32,
+                    c_vp, c_vp],
     "mtbc_maxpool2_bwd": [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp],
     "mtbc_upsample2_fwd": [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp],
     "mtbc_upsample2_bwd": [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp],

@@ -28,6 +28,21 @@ int wgrad_halo_try_create(const mtbc_wgrad_desc* d, OpBase** out);
 int encode_act(CUtensorMap* m, const mtbc_act_view& v, int kc, int bw, int bh, int bn);
 int encode_w(CUtensorMap* m, const void* w, int ktot, int nrows, int ntaps, int kc, int BN);
 
+// bulk-copy pipelined streaming kernels (stream_pipe.cu) for large tensors
+bool pipe_eligible(int64_t N, int64_t HW, int Cp);
+int in_apply_pipe(const void* y, int N, int64_t HW, int Cp, const float* ssum, const float* ssq, const float* gamma,
+                  const float* beta, float eps, float slope, void* a, float* mean, float* rstd, cudaStream_t st);
+int in_bwd_reduce_pipe(const void* dA, const void* y, int N, int64_t HW, int Cp, const float* mean, const float* rstd,
+                       const float* gamma, const float* beta, float slope, float* s1, float* s2, cudaStream_t st);
+int in_bwd_apply_pipe(const void* dA, const void* y, int N, int64_t HW, int Cp, const float* mean, const float* rstd,
+                      const float* gamma, const float* beta, float slope, const float* s1, const float* s2, void* dy,
+                      float* dgamma, float* dbeta, int C_true, cudaStream_t st);
+bool in_bwd_fused_eligible(int64_t N, int64_t HW, int Cp);
+int in_bwd_fused(const void* dA, const void* y, int N, int64_t HW, int Cp, const float* mean, const float* rstd,
+                 const float* gamma, const float* beta, float slope, float* s1, float* s2, void* dy, float* dgamma,
+                 float* dbeta, int C_true, int* counters, cudaStream_t st);
+int channel_sum_pipe(const void* t, int64_t npix, int Cp, int C_true, float* out, cudaStream_t st);
+
 inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
 }  // namespace mtbc

@@ -270,17 +270,24 @@ __global__ void __launch_bounds__(256) conv_first_shift_sums_kernel(const float*
 // the bf16 rounding and the statistics.  InstanceNorm is shift invariant, so everything downstream is unchanged, but
 // the raw 0..255 image (BUSI_dataset.py:102, no normalisation) puts a DC level of many standard deviations on this
 // layer's output: stored centred, bf16 spends its 8 mantissa bits on the signal and sum(y^2) does not cancel.
-__global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __restrict__ x, int N, int Cin, int H, int W,
+// CIN is a compile-time constant so the 9*CIN input taps live in registers (a run-time Cin puts them in local memory
+// and every FMA pays a local load); weights are staged k-major [k][Cp] so 4 output channels come from one 128-bit
+// shared-memory broadcast load.
+template <int CIN>
+__global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __restrict__ x, int N, int H, int W,
                                                              const float* __restrict__ w, const float* __restrict__ bias,
                                                              int Cout, __nv_bfloat16* __restrict__ y, int Cp,
                                                              float* __restrict__ stat_sum, float* __restrict__ stat_sq,
                                                              const float* __restrict__ xs) {
-  extern __shared__ float sm[];
-  float* s_w = sm;                    // [Cp][Cin*9], zero padded
-  float* s_b = s_w + Cp * Cin * 9;    // [Cp]
+  extern __shared__ __align__(16) float sm[];
+  constexpr int K = CIN * 9;
+  float* s_w = sm;                    // [K][Cp], zero padded
+  float* s_b = s_w + Cp * K;          // [Cp]
   float* s_st = s_b + Cp;             // [2][Cp]
-  const int K = Cin * 9;
-  for (int i = threadIdx.x; i < Cp * K; i += 128) s_w[i] = (i / K) < Cout ? w[i] : 0.f;
+  for (int i = threadIdx.x; i < Cp * K; i += 128) {
+    const int c = i / K, k = i - c * K;
+    s_w[k * Cp + c] = c < Cout ? w[i] : 0.f;
+  }
   for (int i = threadIdx.x; i < Cp; i += 128) {
     s_b[i] = (bias != nullptr && i < Cout) ? bias[i] : 0.f;
     s_st[i] = 0.f;
@@ -298,29 +305,40 @@ __global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __rest
     const float inv = 1.f / static_cast<float>(HW);
     for (int c = threadIdx.x; c < Cp; c += 128) {
       float m = 0.f;
-      for (int k = 0; k < K; ++k) m = fmaf(s_w[c * K + k], xs[static_cast<int64_t>(n) * K + k], m);
+#pragma unroll
+      for (int k = 0; k < K; ++k) m = fmaf(s_w[k * Cp + c], xs[static_cast<int64_t>(n) * K + k], m);
       s_b[c] = -m * inv;
     }
     __syncthreads();
   }
-  float xin[36];
-#pragma unroll 4
-  for (int ci = 0; ci < Cin; ++ci)
+  float xin[K];
+#pragma unroll
+  for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
     for (int r = 0; r < 3; ++r)
+#pragma unroll
       for (int s = 0; s < 3; ++s) {
         const int hh = h + r - 1, wc = ww + s - 1;
         xin[ci * 9 + r * 3 + s] =
-            (hh >= 0 && hh < H && wc >= 0 && wc < W) ? x[(static_cast<int64_t>(n) * Cin + ci) * HW + hh * W + wc] : 0.f;
+            (hh >= 0 && hh < H && wc >= 0 && wc < W) ? __ldg(x + (static_cast<int64_t>(n) * CIN + ci) * HW + hh * W + wc) : 0.f;
       }
   __nv_bfloat16* dst = y + pix * Cp;
   for (int c0 = 0; c0 < Cp; c0 += 16) {
     float v[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      float a = s_b[c0 + i];
-      const float* wr = s_w + (c0 + i) * K;
-      for (int k = 0; k < K; ++k) a = fmaf(xin[k], wr[k], a);
-      v[i] = a;
+    for (int q = 0; q < 4; ++q) {
+      const float4 b4 = *reinterpret_cast<const float4*>(s_b + c0 + 4 * q);
+      v[4 * q] = b4.x; v[4 * q + 1] = b4.y; v[4 * q + 2] = b4.z; v[4 * q + 3] = b4.w;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float xk = xin[k];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 w4 = *reinterpret_cast<const float4*>(s_w + k * Cp + c0 + 4 * q);
+        v[4 * q] = fmaf(xk, w4.x, v[4 * q]); v[4 * q + 1] = fmaf(xk, w4.y, v[4 * q + 1]);
+        v[4 * q + 2] = fmaf(xk, w4.z, v[4 * q + 2]); v[4 * q + 3] = fmaf(xk, w4.w, v[4 * q + 3]);
+      }
     }
     if (stat_sum != nullptr) {
       float sq[16];
@@ -334,11 +352,7 @@ __global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __rest
         atomicAdd(&s_st[Cp + cc], cq);
       }
     }
-    uint4 r0, r1;
-    r0.x = pack_bf16x2(v[0], v[1]); r0.y = pack_bf16x2(v[2], v[3]); r0.z = pack_bf16x2(v[4], v[5]); r0.w = pack_bf16x2(v[6], v[7]);
-    r1.x = pack_bf16x2(v[8], v[9]); r1.y = pack_bf16x2(v[10], v[11]); r1.z = pack_bf16x2(v[12], v[13]); r1.w = pack_bf16x2(v[14], v[15]);
-    reinterpret_cast<uint4*>(dst + c0)[0] = r0;
-    reinterpret_cast<uint4*>(dst + c0)[1] = r1;
+    emit_bf16x16(dst + c0, v, false);
   }
   if (stat_sum != nullptr) {
     __syncthreads();
@@ -494,8 +508,15 @@ int mtbc_conv_first_fwd(const float* x, int32_t N, int32_t Cin, int32_t H, int32
     if (rc) return rc;
   }
   const int smem = (Cp * Cin * 9 + 3 * Cp) * sizeof(float);
-  conv_first_fwd_kernel<<<static_cast<int>(N * HW / 128), 128, smem, static_cast<cudaStream_t>(stream)>>>(
-      x, N, Cin, H, W, w, bias, Cout, static_cast<__nv_bfloat16*>(y), Cp, stat_sum, stat_sq, center_scratch);
+  const int grid = static_cast<int>(N * HW / 128);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* yb = static_cast<__nv_bfloat16*>(y);
+  switch (Cin) {
+    case 1: conv_first_fwd_kernel<1><<<grid, 128, smem, st>>>(x, N, H, W, w, bias, Cout, yb, Cp, stat_sum, stat_sq, center_scratch); break;
+    case 2: conv_first_fwd_kernel<2><<<grid, 128, smem, st>>>(x, N, H, W, w, bias, Cout, yb, Cp, stat_sum, stat_sq, center_scratch); break;
+    case 3: conv_first_fwd_kernel<3><<<grid, 128, smem, st>>>(x, N, H, W, w, bias, Cout, yb, Cp, stat_sum, stat_sq, center_scratch); break;
+    default: conv_first_fwd_kernel<4><<<grid, 128, smem, st>>>(x, N, H, W, w, bias, Cout, yb, Cp, stat_sum, stat_sq, center_scratch); break;
+  }
   return check_launch("conv_first_fwd");
 }
 int mtbc_conv_first_wgrad(const float* x, int32_t N, int32_t Cin, int32_t H, int32_t W, const void* dy, int32_t Cp,

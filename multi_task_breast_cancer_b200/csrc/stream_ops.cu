@@ -428,6 +428,8 @@ int mtbc_in_apply(const void* y, int32_t N, int32_t H, int32_t W, int32_t Cp, co
     in_apply_pool_kernel<<<dim3(gx, N), 256, 0, ST(stream)>>>(CBF(y), H, W, Cp, stat_sum, stat_sq, gamma, beta, eps,
                                                              slope, BF(a), BF(pooled), mean, rstd);
   } else {
+    if (pipe_eligible(N, HW, Cp))
+      return in_apply_pipe(y, N, HW, Cp, stat_sum, stat_sq, gamma, beta, eps, slope, a, mean, rstd, ST(stream));
     const int gx = pick_gx(HW * cvec, 256, cvec, N, 4);
     in_apply_kernel<<<dim3(gx, N), 256, 0, ST(stream)>>>(CBF(y), HW, Cp, stat_sum, stat_sq, gamma, beta, eps, slope,
                                                         BF(a), mean, rstd);
@@ -438,6 +440,8 @@ int mtbc_in_apply(const void* y, int32_t N, int32_t H, int32_t W, int32_t Cp, co
 int mtbc_in_bwd_reduce(const void* dA, const void* y, int32_t N, int32_t HW, int32_t Cp, const float* mean,
                        const float* rstd, const float* gamma, const float* beta, float slope, float* s1, float* s2,
                        void* stream) {
+  if (pipe_eligible(N, HW, Cp))
+    return in_bwd_reduce_pipe(dA, y, N, HW, Cp, mean, rstd, gamma, beta, slope, s1, s2, ST(stream));
   const int cvec = Cp / 8;
   const int gx = pick_gx(static_cast<int64_t>(HW) * cvec, 256, cvec, N, 8);
   in_bwd_reduce_kernel<<<dim3(gx, N), 256, 2 * Cp * sizeof(float), ST(stream)>>>(CBF(dA), CBF(y), HW, Cp, mean, rstd,
@@ -448,6 +452,9 @@ int mtbc_in_bwd_reduce(const void* dA, const void* y, int32_t N, int32_t HW, int
 int mtbc_in_bwd_apply(const void* dA, const void* y, int32_t N, int32_t HW, int32_t Cp, const float* mean,
                       const float* rstd, const float* gamma, const float* beta, float slope, const float* s1,
                       const float* s2, void* dy, float* dgamma, float* dbeta, int32_t C_true, void* stream) {
+  if (pipe_eligible(N, HW, Cp))
+    return in_bwd_apply_pipe(dA, y, N, HW, Cp, mean, rstd, gamma, beta, slope, s1, s2, dy, dgamma, dbeta, C_true,
+                             ST(stream));
   const int cvec = Cp / 8;
   const int gx = pick_gx(static_cast<int64_t>(HW) * cvec, 256, cvec, N, 4);
   in_bwd_apply_kernel<<<dim3(gx, N), 256, 0, ST(stream)>>>(CBF(dA), CBF(y), HW, Cp, mean, rstd, gamma, beta, slope, s1,
@@ -459,6 +466,17 @@ int mtbc_in_bwd_apply(const void* dA, const void* y, int32_t N, int32_t HW, int3
     rc = check_launch("in_affine_grad");
   }
   return rc;
+}
+
+int mtbc_in_bwd(const void* dA, const void* y, int32_t N, int32_t HW, int32_t Cp, const float* mean, const float* rstd,
+                const float* gamma, const float* beta, float slope, float* s1, float* s2, void* dy, float* dgamma,
+                float* dbeta, int32_t C_true, int32_t* counters, void* stream) {
+  if (counters != nullptr && in_bwd_fused_eligible(N, HW, Cp))
+    return in_bwd_fused(dA, y, N, HW, Cp, mean, rstd, gamma, beta, slope, s1, s2, dy, dgamma, dbeta, C_true, counters,
+                        ST(stream));
+  int rc = mtbc_in_bwd_reduce(dA, y, N, HW, Cp, mean, rstd, gamma, beta, slope, s1, s2, stream);
+  if (rc) return rc;
+  return mtbc_in_bwd_apply(dA, y, N, HW, Cp, mean, rstd, gamma, beta, slope, s1, s2, dy, dgamma, dbeta, C_true, stream);
 }
 
 int mtbc_maxpool2_bwd(const void* a, const void* dP, int32_t N, int32_t H, int32_t W, int32_t Cp, void* dA,
@@ -486,6 +504,7 @@ int mtbc_channel_sum(const void* t, int64_t npix, int32_t Cp, int32_t C_true, fl
     cudaError_t e = cudaMemsetAsync(out, 0, C_true * sizeof(float), ST(stream));
     if (e != cudaSuccess) return set_error(MTBC_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
   }
+  if (pipe_eligible(1, npix, Cp)) return channel_sum_pipe(t, npix, Cp, C_true, out, ST(stream));
   const int cvec = Cp / 8;
   const int gx = pick_gx(npix * cvec, 256, cvec, 1, 16);
   channel_sum_kernel<<<gx, 256, Cp * sizeof(float), ST(stream)>>>(CBF(t), npix, Cp, C_true, out);

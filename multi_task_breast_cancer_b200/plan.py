@@ -384,15 +384,14 @@ class Plan:
             return None
         s1 = self.bwd_arena.alloc(N, Cp)
         s2 = self.bwd_arena.alloc(N, Cp)
-        blk.append(_mk("mtbc_in_bwd_reduce", ptr(a.g.t), ptr(y.feat.t), N, H * Wd, Cp, ptr(mean), ptr(rstd), ptr(gv),
-                       ptr(bv), C.c_float(slope), ptr(s1), ptr(s2)))
+        cnt = self.bwd_arena.alloc(N)   # zeroed with the arena; reinterpreted as int32 arrival counters
         dy = self.scratch(N, H, Wd, Cc)
         self.debug[a.name + ".dy"] = dy
         self.debug[a.name + ".aux"] = (mean, rstd, gv, bv, s1, s2)
         dg = self.grad_view[gamma] if gamma else None
         db = self.grad_view[beta] if beta else None
-        blk.append(_mk("mtbc_in_bwd_apply", ptr(a.g.t), ptr(y.feat.t), N, H * Wd, Cp, ptr(mean), ptr(rstd), ptr(gv),
-                       ptr(bv), C.c_float(slope), ptr(s1), ptr(s2), ptr(dy.t), ptr(dg), ptr(db), Cc))
+        blk.append(_mk("mtbc_in_bwd", ptr(a.g.t), ptr(y.feat.t), N, H * Wd, Cp, ptr(mean), ptr(rstd), ptr(gv), ptr(bv),
+                       C.c_float(slope), ptr(s1), ptr(s2), ptr(dy.t), ptr(dg), ptr(db), Cc, ptr(cnt)))
         self._mark_grad(gamma, beta)
         return dy
 

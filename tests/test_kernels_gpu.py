@@ -88,9 +88,23 @@ def test_first_layer(D, cout):
 
 
 @pytest.mark.parametrize("args", [(2, 32, 32, 24, True, True), (2, 16, 16, 96, True, False),
-                                  (2, 16, 16, 320, False, True, 0.01), (3, 8, 8, 512, False, False, 0.01)])
-def test_instance_norm_lrelu_pool(D, args):
+                                  (2, 16, 16, 320, False, True, 0.01), (3, 8, 8, 512, False, False, 0.01),
+                                  # >= 1 Mi elements: the bulk-copy pipelined kernels (stream_pipe.cu)
+                                  (3, 128, 128, 24, True, False),          # cvec 4, whole tiles
+                                  (3, 64, 64, 96, True, False),            # cvec 12: 252 threads, ragged last tile
+                                  (5, 32, 32, 320, False, False, 0.01),    # cvec 40: 240 threads, several samples / CTA
+                                  (40, 16, 16, 384, True, False),          # more samples than tiles per CTA
+                                  # dA + y > 96 MB: the fused cooperative backward (group barriers, L2 second pass)
+                                  (13, 256, 256, 24, True, False),
+                                  (25, 128, 128, 48, False, False, 0.01)])
+def test_instance_norm_lrelu_pool(D, args, monkeypatch):
+    monkeypatch.setenv("MTBC_FUSED_INBWD", "1")   # also exercise the opt-in cooperative backward where it is eligible
     _run(D, D.norm_case, *args)
+
+
+@pytest.mark.parametrize("args", [(2, 16, 16, 48), (3, 128, 128, 48), (3, 64, 64, 96)])
+def test_channel_sum(D, args):
+    _run(D, D.chansum_case, *args)
 
 
 @pytest.mark.parametrize("args", [(2, 32, 32, 24), (2, 16, 16, 16)])

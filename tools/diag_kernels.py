@@ -298,6 +298,22 @@ def norm_case(N, H, W, C, affine, pool, slope=0.1):
                   None)
         torch.cuda.synchronize()
         report(name + " bwd dy", dy.to_nchw(), yr.grad, tol=3e-2)
+        # the single-call backward (one cooperative launch with an L2-resident second pass when the planes exceed L2)
+        s1b = torch.zeros(N, Cp, device=dev); s2b = torch.zeros(N, Cp, device=dev)
+        cnt = torch.zeros(N, dtype=torch.int32, device=dev)
+        dy2 = Feat.empty(N, H, W, C)
+        dg2 = torch.zeros(C, device=dev) if affine else None
+        db2 = torch.zeros(C, device=dev) if affine else None
+        _lib.call("mtbc_in_bwd", ops.ptr(dAf.t), ops.ptr(yf.t), N, H * W, Cp, ops.ptr(mean), ops.ptr(rstd), ops.ptr(gp),
+                  ops.ptr(bp), slope, ops.ptr(s1b), ops.ptr(s2b), ops.ptr(dy2.t), ops.ptr(dg2), ops.ptr(db2), C,
+                  ops.ptr(cnt), None)
+        torch.cuda.synchronize()
+        report(name + " bwd dy (mtbc_in_bwd)", dy2.to_nchw(), yr.grad, tol=3e-2)
+        report(name + " s1 (mtbc_in_bwd)", s1b, s1, tol=1e-4)
+        report(name + " s2 (mtbc_in_bwd)", s2b, s2, tol=1e-4)
+        if affine:
+            report(name + " dgamma (mtbc_in_bwd)", dg2, dg, tol=1e-4)
+            report(name + " dbeta (mtbc_in_bwd)", db2, db, tol=1e-4)
         if affine:
             # reference affine grads
             yr2 = y.clone()
@@ -314,6 +330,21 @@ def norm_case(N, H, W, C, affine, pool, slope=0.1):
             _lib.call("mtbc_maxpool2_bwd", ops.ptr(a.t), ops.ptr(dPf.t), N, H, W, Cp, ops.ptr(dA2.t), 0, None)
             torch.cuda.synchronize()
             report(name + " pool bwd", dA2.to_nchw(), ar.grad)
+
+    run_case(fn, name)
+
+
+def chansum_case(N, H, W, C):
+    """Per-channel sum over all pixels (bias gradient of the transposed convolutions)."""
+    name = f"channel_sum N{N} {H}x{W} C{C}"
+
+    def fn():
+        t = rnd(N, C, H, W).to(torch.bfloat16).float()
+        tf = Feat.from_nchw(t)
+        out = torch.full((C,), 0.5, device=dev)
+        _lib.call("mtbc_channel_sum", ops.ptr(tf.t), N * H * W, tf.Cp, C, ops.ptr(out), 1, None)
+        torch.cuda.synchronize()
+        report(name, out, t.sum(dim=(0, 2, 3)) + 0.5, tol=1e-4)
 
     run_case(fn, name)
 

@@ -1,5 +1,5 @@
 #!/bin/bash
-# One gpurun call: GPU tests, bench (both arms), per-launch timing, ncu launch list + one --set full capture.
+# One gpurun call: GPU tests, bench (both arms), per-launch timing, ncu launch list of one step (+ optional full capture).
 #   gpurun --timeout 1800 -- 'bash tools/gpu_round.sh [tag]'
 TAG=${1:-r01}
 OUT=gpurun_out
@@ -17,17 +17,21 @@ if [ -z "$SKIP_REF" ]; then
   timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err; echo "ref exit $?"
   cat $OUT/${TAG}_bench_ref.json
 fi
-timeout 300 python tools/profile_plan.py unetpp 32 256 70 > $OUT/${TAG}_profile_plan.txt 2>&1; echo "profile exit $?"
+timeout 300 python tools/profile_plan.py unetpp 32 256 400 > $OUT/${TAG}_profile_plan.txt 2>&1; echo "profile exit $?"
 head -30 $OUT/${TAG}_profile_plan.txt
 if [ -z "$SKIP_NCU" ]; then
-  CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
-  timeout 300 $CMD > $OUT/${TAG}_plain.log 2>&1 &&
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 1100 -c 420 --csv \
-      --log-file $OUT/${TAG}_launches.csv $CMD > $OUT/${TAG}_ncu1.log 2>&1
+  # launch list of ONE eager step, kernels renamed by the NVTX label of their plan launch (tools/ncu_step.py)
+  timeout 300 python tools/ncu_step.py $OUT/${TAG}_step_launches.json > $OUT/${TAG}_plain.log 2>&1 &&
+  timeout 900 ncu --profile-from-start off --nvtx --print-nvtx-rename kernel --print-units base \
+      --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor.sum \
+      --clock-control none --csv --log-file $OUT/${TAG}_launches.csv python tools/ncu_step.py /dev/null > $OUT/${TAG}_ncu1.log 2>&1
   echo "ncu launches exit $?"
-  timeout 300 $CMD > $OUT/${TAG}_plain2.log 2>&1 &&
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-conv_halo} -s ${NCU_SKIP:-60} -c ${NCU_COUNT:-4} \
-      -f -o $OUT/${TAG}_top $CMD > $OUT/${TAG}_ncu2.log 2>&1
-  echo "ncu full exit $?"
+  if [ -n "$NCU_FULL" ]; then
+    timeout 300 python tools/ncu_step.py /dev/null > $OUT/${TAG}_plain2.log 2>&1 &&
+    timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on \
+        -k regex:${NCU_KERNEL:-conv_halo} -s ${NCU_SKIP:-0} -c ${NCU_COUNT:-3} \
+        -f -o $OUT/${TAG}_top python tools/ncu_step.py /dev/null > $OUT/${TAG}_ncu2.log 2>&1
+    echo "ncu full exit $?"
+  fi
 fi
-ls -la $OUT
+ls -la $OUT | tail -20
