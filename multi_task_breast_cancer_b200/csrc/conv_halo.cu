@@ -44,6 +44,7 @@ struct ConvHaloParams {
   int32_t nsrc, nouts;
   int32_t W, H, N, tiles_w, tiles_h, n_mtiles;
   int32_t BN, tmem_cols, stages, a_stage_bytes, b_tap_bytes, b_total_bytes;
+  int32_t G, bn1;   // G = output rows stacked along N (1 or 2); bn1 = columns per output pixel; BN = G * bn1
   int32_t stat_C;
   const float* bias;
   float* stat_sum;
@@ -73,6 +74,40 @@ __device__ __forceinline__ void halo_issue_chunk(uint32_t d_addr, uint32_t a_lo,
   }
 }
 
+// G = 2: two vertically adjacent output pixels share one accumulator row (columns [0, bn1) = row 2t, [bn1, 2*bn1) =
+// row 2t+1).  An instruction costs the same ~45 cycles for any N <= ~96 (tools/exp_mma_rate2.cu), so the 24-channel
+// layers (bn1 = 32) waste two thirds of every MMA; stacking the two rows makes the two middle input rows (dh' = 1, 2)
+// single N = 2*bn1 instructions: 12 instructions per K step and 256 pixels instead of 18.  The resident weights are
+// stored [dw][dh descending][bn1 x KC] so the N = 2*bn1 operand is just a window over two neighbouring tap blocks:
+// input row dh' feeds tap dh' of the upper pixel and tap dh'-1 of the lower one.
+template <int KC>
+__device__ __forceinline__ void halo_issue_chunk_g2(uint32_t d_addr, uint32_t a_lo, uint32_t b_lo, uint32_t b_dw16,
+                                                    uint32_t b_blk16, uint32_t bn1, uint32_t idesc1, uint32_t idesc2,
+                                                    uint32_t accumulate) {
+  constexpr uint32_t rowb = KC * 2u;
+  constexpr uint32_t layout = KC == 64 ? 2u : 4u;
+  const uint32_t a_hi = umma_desc_hi(2 * kHaloW * rowb, layout);   // 8-row group stride = two halo rows
+  const uint32_t b_hi = umma_desc_hi(8u * rowb, layout);
+#pragma unroll
+  for (int dw = 0; dw < 3; ++dw) {
+    const uint32_t b_w = b_lo + dw * b_dw16;   // blocks of this dw: [dh=2][dh=1][dh=0]
+    // order: the two N = bn1 instructions first so that each column half is initialised by its own instruction
+#pragma unroll
+    for (int step = 0; step < 4; ++step) {
+      const int dhp = step == 0 ? 3 : (step == 1 ? 0 : step - 1);   // 3, 0, 1, 2
+      const uint32_t a_t = a_lo + ((dhp * kHaloW + dw) * rowb >> 4);
+      // dhp = 0: block dh=0 -> upper half; 3: block dh=2 -> lower half; 1: blocks [dh=1, dh=0]; 2: blocks [dh=2, dh=1]
+      const uint32_t b_t = b_w + (dhp == 0 ? 2 * b_blk16 : (dhp == 1 ? b_blk16 : 0u));
+      const uint32_t d_t = d_addr + (dhp == 3 ? bn1 : 0u);
+      const uint32_t idesc = (dhp == 0 || dhp == 3) ? idesc1 : idesc2;
+#pragma unroll
+      for (int k = 0; k < KC / 16; ++k) {
+        const uint32_t acc = (dw == 0 && (dhp == 3 || dhp == 0) && k == 0) ? accumulate : 1u;
+        umma_bf16_lohi(d_t, a_t + 2 * k, a_hi, b_t + 2 * k, b_hi, idesc, acc);
+      }
+    }
+  }
+}
 
 // Epilogue of the halo kernel: 8 warps, two per TMEM lane quarter (thread <-> output pixel), each pair splitting the
 // tile's columns in halves.  The epilogue warps share their schedulers with nobody, so the loop is written for a short
@@ -112,6 +147,7 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
   const int etid = (warp - 2) * 32 + lane;
   const int tiles_w = p.tiles_w, tiles_per_n = p.tiles_w * p.tiles_h;
   const int H = p.H, W = p.W, stat_C = p.stat_C;
+  const int G = p.G, bn1 = p.bn1;
   float* const stat_sum = p.stat_sum;
   float* const stat_sq = p.stat_sq;
   constexpr int NR = RACC > 0 ? RACC / 2 : 1;   // columns of this warp's half
@@ -124,7 +160,7 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
   auto flush_cols = [&](int n) {
     asm volatile("bar.sync 1, 256;" ::: "memory");
     for (int i = etid; i < BN; i += kEpiThreads) {
-      const int64_t o = static_cast<int64_t>(n) * stat_C + ntile * BN + i;
+      const int64_t o = static_cast<int64_t>(n) * stat_C + ntile * bn1 + (i % bn1);   // G = 2: both rows -> one channel
       atomicAdd(stat_sum + o, s_part[0][0][i] + s_part[1][0][i] + s_part[2][0][i] + s_part[3][0][i]);
       atomicAdd(stat_sq + o, s_part[0][1][i] + s_part[1][1][i] + s_part[2][1][i] + s_part[3][1][i]);
     }
@@ -190,7 +226,7 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
     const int rem = t - n * tiles_per_n;
     const int tr = rem / tiles_w;
     const int w = (rem - tr * tiles_w) * 8 + tw;
-    const int h = tr * 16 + th;
+    const int h = (tr * 16 + th) * G;   // G = 2: row of the upper pixel; the lower one is folded into s_chunk[k].base
     if (RACC > 0 && n != cur_n) { flush_regs(cur_n); cur_n = n; }
     const int64_t pix = (static_cast<int64_t>(n) * H + h) * W + w;
     mbar_wait(&s_accfull[buf], acc_phase);
@@ -249,12 +285,16 @@ __global__ void __launch_bounds__(64 + kEpiThreads, MINB) conv_halo_kernel(const
   const int t_begin = static_cast<int>(static_cast<int64_t>(p.n_mtiles) * blockIdx.x / gridDim.x);
   const int t_end = static_cast<int>(static_cast<int64_t>(p.n_mtiles) * (blockIdx.x + 1) / gridDim.x);
 
-  for (int i = tid; i < 256; i += 64 + kEpiThreads) s_bias[i] = (p.bias != nullptr && i < BN) ? p.bias[ntile * BN + i] : 0.f;
+  const int bn1 = p.bn1;
+  for (int i = tid; i < 256; i += 64 + kEpiThreads)
+    s_bias[i] = (p.bias != nullptr && i < BN) ? p.bias[ntile * bn1 + (i % bn1)] : 0.f;
   if (tid < (BN >> 4)) {
-    const int gc = ntile * BN + tid * 16;
+    const int lc = tid * 16;                      // column inside the accumulator
+    const int prow = lc / bn1;                    // G = 2: 0 = upper pixel, 1 = lower pixel
+    const int gc = ntile * bn1 + (lc - prow * bn1);
     int o = 0;
     while (o + 1 < p.nouts && gc >= p.outs[o].col_end) ++o;   // slices are ordered by column
-    s_chunk[tid].base = p.outs[o].ptr + (gc - p.outs[o].col0);
+    s_chunk[tid].base = p.outs[o].ptr + (gc - p.outs[o].col0) + static_cast<int64_t>(prow) * p.W * p.outs[o].out_C;
     s_chunk[tid].out_C = p.outs[o].out_C;
     s_chunk[tid].accumulate = p.outs[o].accumulate;
   }
@@ -281,19 +321,23 @@ __global__ void __launch_bounds__(64 + kEpiThreads, MINB) conv_halo_kernel(const
         for (int s = 0; s < p.nsrc; ++s) {
           const HaloSrc sc = p.src[s];
           const CUtensorMap* wm = &p.wmap[sc.kc == 64 ? 1 : 0];
-          for (int ch = 0; ch < sc.nchunk; ++ch)
-            tma_load_3d(smem_b + tap * p.b_tap_bytes + sc.b_off + ch * (BN * sc.kc * 2), wm, &s_bfull,
-                        sc.wk0 + ch * sc.kc, ntile * BN, tap);
+          for (int ch = 0; ch < sc.nchunk; ++ch) {
+            const int blk = bn1 * sc.kc * 2;
+            // G = 1: [tap][source][chunk];  G = 2: [dw][source][chunk][dh = 2, 1, 0]
+            uint8_t* dst = p.G == 1 ? smem_b + tap * p.b_tap_bytes + sc.b_off + ch * blk
+                                    : smem_b + (tap % 3) * (3 * p.b_tap_bytes) + 3 * (sc.b_off + ch * blk) + (2 - tap / 3) * blk;
+            tma_load_3d(dst, wm, &s_bfull, sc.wk0 + ch * sc.kc, ntile * bn1, tap);
+          }
         }
       int stage = 0;
       uint32_t phase = 0;
       for (int t = t_begin; t < t_end; ++t) {
         const int w0 = (t % p.tiles_w) * 8;
-        const int h0 = ((t / p.tiles_w) % p.tiles_h) * 16;
+        const int h0 = ((t / p.tiles_w) % p.tiles_h) * 16 * p.G;
         const int n = t / (p.tiles_w * p.tiles_h);
         for (int s = 0; s < p.nsrc; ++s) {
           const HaloSrc sc = p.src[s];
-          const uint32_t bytes = static_cast<uint32_t>(kHaloRows * sc.kc * 2);
+          const uint32_t bytes = static_cast<uint32_t>(kHaloW * (16 * p.G + 2) * sc.kc * 2);
           for (int ch = 0; ch < sc.nchunk; ++ch) {
             mbar_wait(&s_aempty[stage], phase ^ 1u);
             mbar_arrive_expect_tx(&s_afull[stage], bytes);
@@ -307,8 +351,10 @@ __global__ void __launch_bounds__(64 + kEpiThreads, MINB) conv_halo_kernel(const
     if (elect_one()) {
       // ------------------------------------------------------------ MMA issuer
       const uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      const uint32_t idesc1 = umma_idesc_bf16(128, bn1, 0, 0);
       mbar_wait(&s_bfull, 0);
       const uint32_t b_tap16 = static_cast<uint32_t>(p.b_tap_bytes) >> 4;
+      const bool g2 = p.G == 2;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -325,9 +371,16 @@ __global__ void __launch_bounds__(64 + kEpiThreads, MINB) conv_halo_kernel(const
             mbar_wait(&s_afull[stage], phase);
             tc_fence_after();
             const uint32_t a_lo = umma_desc_lo(smem_u32(smem_a + stage * p.a_stage_bytes), 16);
-            const uint32_t b_lo = umma_desc_lo(smem_u32(smem_b) + sc.b_off + ch * (BN * sc.kc * 2), 16);
-            if (sc.kc == 64) halo_issue_chunk<64>(d_addr, a_lo, b_lo, b_tap16, idesc, accumulate);
-            else halo_issue_chunk<32>(d_addr, a_lo, b_lo, b_tap16, idesc, accumulate);
+            const uint32_t blk = static_cast<uint32_t>(bn1 * sc.kc * 2);
+            if (g2) {
+              const uint32_t b_lo = umma_desc_lo(smem_u32(smem_b) + 3 * (sc.b_off + ch * blk), 16);
+              if (sc.kc == 64) halo_issue_chunk_g2<64>(d_addr, a_lo, b_lo, 3 * b_tap16, blk >> 4, bn1, idesc1, idesc, accumulate);
+              else halo_issue_chunk_g2<32>(d_addr, a_lo, b_lo, 3 * b_tap16, blk >> 4, bn1, idesc1, idesc, accumulate);
+            } else {
+              const uint32_t b_lo = umma_desc_lo(smem_u32(smem_b) + sc.b_off + ch * blk, 16);
+              if (sc.kc == 64) halo_issue_chunk<64>(d_addr, a_lo, b_lo, b_tap16, idesc, accumulate);
+              else halo_issue_chunk<32>(d_addr, a_lo, b_lo, b_tap16, idesc, accumulate);
+            }
             accumulate = 1;
             umma_commit(&s_aempty[stage]);
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -554,21 +607,31 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   }
   if (BN < 32 && BN != d->ncols) return 1;
 
+  // G = 2 (two output rows per accumulator row) for single-N-tile 32-column layers on planes with H % 32 == 0: the
+  // 24-channel full-resolution convolutions, whose N = 32 MMAs cost the same cycles as N = 64 ones
+  const char* g_env = getenv("MTBC_HALO_G");
+  int G = 1;
+  if (BN == 32 && d->H % 32 == 0 && d->nouts <= 1 && !(g_env && g_env[0] == '1')) G = 2;
+
   ConvHaloOp* op = new ConvHaloOp();
   ConvHaloParams& p = op->p;
   memset(&p, 0, sizeof(p));
   p.nsrc = d->nviews;
+  p.G = G; p.bn1 = BN;
+  const int halo_h = 16 * G + 2;
   int kcmax = 32, b_off = 0;
   bool use32 = false, use64 = false;
+  // G = 2 doubles the halo tile: keep 32-channel chunks so that at least three stages fit next to the weights
+  const bool allow64 = (G == 1) || (9 * BN * kused * 2 <= 64 * 1024);
   for (int v = 0; v < d->nviews; ++v) {
     const mtbc_act_view& a = d->views[v];
-    const int kc = (a.C % 64 == 0 && wk0[v] % 64 == 0) ? 64 : 32;
+    const int kc = (allow64 && a.C % 64 == 0 && wk0[v] % 64 == 0) ? 64 : 32;
     if (kc > kcmax) kcmax = kc;
     (kc == 64 ? use64 : use32) = true;
     p.src[v].kc = (int16_t)kc; p.src[v].nchunk = (int16_t)(a.C / kc); p.src[v].wk0 = wk0[v]; p.src[v].b_off = b_off;
     b_off += a.C * BN * 2;
     if (wk0[v] % 32 != 0 || wk0[v] + a.C > d->w_ktot) { delete op; return set_error(MTBC_ERR_INVALID, "conv_halo: weight columns out of range"); }
-    int rc = encode_act(&p.amap[v], a, kc, kHaloW, kHaloH, 1);
+    int rc = encode_act(&p.amap[v], a, kc, kHaloW, halo_h, 1);
     if (rc) { delete op; return rc; }
   }
   p.b_tap_bytes = b_off;
@@ -576,11 +639,11 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   if (use32) { int rc = encode_w(&p.wmap[0], d->wpack, d->w_ktot, d->ncols, 9, 32, BN); if (rc) { delete op; return rc; } }
   if (use64) { int rc = encode_w(&p.wmap[1], d->wpack, d->w_ktot, d->ncols, 9, 64, BN); if (rc) { delete op; return rc; } }
   p.W = d->W; p.H = d->H; p.N = d->N;
-  p.tiles_w = d->W / 8; p.tiles_h = d->H / 16;
+  p.tiles_w = d->W / 8; p.tiles_h = d->H / (16 * G);
   p.n_mtiles = p.tiles_w * p.tiles_h * d->N;
-  p.BN = BN;
-  p.tmem_cols = tmem_cols_pow2(2 * BN);
-  p.a_stage_bytes = ((kHaloRows * kcmax * 2) + 1023) & ~1023;
+  p.BN = G * BN;
+  p.tmem_cols = tmem_cols_pow2(2 * G * BN);
+  p.a_stage_bytes = ((kHaloW * halo_h * kcmax * 2) + 1023) & ~1023;
   int total_chunks = 0;
   for (int v = 0; v < d->nviews; ++v) total_chunks += p.src[v].nchunk;
   int stages = (200 * 1024 - p.b_total_bytes) / p.a_stage_bytes;
@@ -594,7 +657,18 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   if (stages < 2) { delete op; return 1; }
   p.stages = stages;
   op->smem_bytes = p.b_total_bytes + stages * p.a_stage_bytes + 1024;
-  const int ctas_per_sm = ((op->smem_bytes + 6 * 1024) * 2 <= 227 * 1024 && 2 * p.tmem_cols <= 512) ? 2 : 1;
+  int ctas_per_sm = ((op->smem_bytes + 6 * 1024) * 2 <= 227 * 1024 && 2 * p.tmem_cols <= 512) ? 2 : 1;
+  const char* c_env = getenv("MTBC_HALO_CTAS");
+  // forward G = 2 layers keep 64 statistics accumulators per epilogue thread: the 2-CTA variant (96 registers) spills
+  // them, one CTA per SM with a deeper halo ring measured 4 % faster (3.24 -> 3.11 ms over the 35 forward convs)
+  const bool one_cta = (c_env && c_env[0] == '1') || (G == 2 && d->stat_sum != nullptr && !(c_env && c_env[0] == '2'));
+  if (one_cta && ctas_per_sm == 2) {
+    ctas_per_sm = 1;
+    int st1 = (200 * 1024 - p.b_total_bytes) / p.a_stage_bytes;
+    if (st1 > kHaloMaxStages) st1 = kHaloMaxStages;
+    p.stages = st1;
+    op->smem_bytes = p.b_total_bytes + st1 * p.a_stage_bytes + 1024;
+  }
   op->ctas_per_sm = ctas_per_sm;
   int gx = sm_count() * ctas_per_sm;
   if (gx > p.n_mtiles) gx = p.n_mtiles;
