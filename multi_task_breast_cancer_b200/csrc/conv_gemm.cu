@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(320) conv_gemm_kernel(const __grid_constant__ 
     const bool do_stats = (p.stat_sum != nullptr);
     const bool has_bias = (p.bias != nullptr);
     const bool acc = p.accumulate != 0;
+    const bool wide = (p.out_C % 16) == 0;
     const int epi_mode = p.epi_mode, up_k = p.up_k, up_cp = p.up_cp, out_C = p.out_C;
     const int H = p.H, W = p.W, N = p.N;
     const int64_t Wo = static_cast<int64_t>(W) * up_k;
@@ -217,7 +218,11 @@ __global__ void __launch_bounds__(320) conv_gemm_kernel(const __grid_constant__ 
             atomicAdd(&s_stat[1][cc], cq);
           }
         }
-        if (valid) emit_bf16x16(pixbase + (static_cast<int64_t>(qi) * Wo + qj) * out_C + bcol, v, acc);
+        if (valid) {
+          const int left = out_C - bcol;   // columns of this chunk that exist in the (possibly dense) destination
+          emit_bf16x16_n(pixbase + (static_cast<int64_t>(qi) * Wo + qj) * out_C + bcol, v, acc,
+                         left >= 16 ? 16 : (left >= 8 ? 8 : 0), wide);
+        }
         bcol += 16;
         if (epi_mode != 0 && bcol == up_cp) {   // next sub-pixel of the transposed convolution
           bcol = 0;
@@ -243,9 +248,11 @@ __global__ void __launch_bounds__(320) conv_gemm_kernel(const __grid_constant__ 
         // TN == 1 is enforced by the host when statistics are fused: the whole tile belongs to sample n0.
         asm volatile("bar.sync 1, 256;" ::: "memory");
         for (int i = etid; i < BN; i += 256) {
-          const int64_t o = static_cast<int64_t>(n0) * p.stat_C + ntile * BN + i;
-          atomicAdd(p.stat_sum + o, s_stat[0][i]);
-          atomicAdd(p.stat_sq + o, s_stat[1][i]);
+          if (ntile * BN + i < p.stat_C) {   // GEMM pad columns of a dense tensor have no channel
+            const int64_t o = static_cast<int64_t>(n0) * p.stat_C + ntile * BN + i;
+            atomicAdd(p.stat_sum + o, s_stat[0][i]);
+            atomicAdd(p.stat_sq + o, s_stat[1][i]);
+          }
           s_stat[0][i] = 0.f;
           s_stat[1][i] = 0.f;
         }
@@ -445,8 +452,8 @@ bool tensor_map_available() { return get_encode() != nullptr; }
 int encode_act(CUtensorMap* m, const mtbc_act_view& v, int kc, int TW, int TH, int TN) {
   PFN_tmapEncodeTiled enc = get_encode();
   if (!enc) return set_error(MTBC_ERR_NO_DEVICE, "cuTensorMapEncodeTiled not available");
-  if (v.C % 32 != 0 || (reinterpret_cast<uintptr_t>(v.ptr) & 15) != 0)
-    return set_error(MTBC_ERR_INVALID, "activation view: C %% 32 != 0 or pointer not 16B aligned");
+  if (v.C % 8 != 0 || (reinterpret_cast<uintptr_t>(v.ptr) & 15) != 0)
+    return set_error(MTBC_ERR_INVALID, "activation view: C %% 8 != 0 or pointer not 16B aligned");
   cuuint64_t gdim[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N};
   cuuint64_t gstr[3] = {(cuuint64_t)v.sW * 2, (cuuint64_t)v.sH * 2, (cuuint64_t)v.sN * 2};
   cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
@@ -542,7 +549,7 @@ int conv_gemm_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   for (int i = 0; i < d->nviews; ++i) {
     const mtbc_act_view& v = d->views[i];
     if (v.W != d->W || v.H != d->H || v.N != d->N) { delete op; return set_error(MTBC_ERR_INVALID, "conv_gemm: view %d geometry mismatch", i); }
-    kc_of_view[i] = (v.C % 64 == 0) ? 64 : 32;
+    kc_of_view[i] = (((v.C + 31) & ~31) % 64 == 0) ? 64 : 32;
     if (kc_of_view[i] > kcmax) kcmax = kc_of_view[i];
     int rc = encode_act(&p.amap[i], v, kc_of_view[i], TW, TH, TN);
     if (rc) { delete op; return rc; }
@@ -553,7 +560,7 @@ int conv_gemm_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
     const mtbc_gemm_seg& g = d->seg[s];
     if (g.view < 0 || g.view >= d->nviews || g.wtap < 0 || g.wtap >= d->w_ntaps) { delete op; return set_error(MTBC_ERR_INVALID, "conv_gemm: segment %d out of range", s); }
     const int kc = kc_of_view[g.view];
-    const int C = d->views[g.view].C;
+    const int C = (d->views[g.view].C + 31) & ~31;   // K extent per source, padded (TMA zero-fills missing channels)
     if (g.wk0 % 32 != 0 || g.wk0 + C > d->w_ktot) { delete op; return set_error(MTBC_ERR_INVALID, "conv_gemm: segment %d weight columns out of range", s); }
     if (kc == 64 && g.wk0 % 64 != 0) { delete op; return set_error(MTBC_ERR_INVALID, "conv_gemm: 64-wide source at a non-64-aligned K offset"); }
     p.seg[s].view = (int16_t)g.view; p.seg[s].dh = (int16_t)g.dh; p.seg[s].dw = (int16_t)g.dw;
@@ -621,13 +628,15 @@ int wgrad_create(const mtbc_wgrad_desc* d, OpBase** out) {
   const int aC = d->a_views[0].C, bC = d->b_views[0].C;
   for (int i = 0; i < d->a_nviews; ++i) if (d->a_views[i].C != aC) { delete op; return set_error(MTBC_ERR_INVALID, "wgrad: A views differ in C"); }
   for (int i = 0; i < d->b_nviews; ++i) if (d->b_views[i].C != bC) { delete op; return set_error(MTBC_ERR_INVALID, "wgrad: B views differ in C"); }
+  if (aC % 8 != 0 || bC % 8 != 0) { delete op; return set_error(MTBC_ERR_INVALID, "wgrad: C %% 8 != 0"); }
+  const int aCp = (aC + 31) & ~31, bCp = (bC + 31) & ~31;   // GEMM extents of dense tensors
   p.a_C = aC;
-  p.a_kc = (aC % 64 == 0) ? 64 : 32;
-  p.b_kc = (bC % 64 == 0) ? 64 : 32;
+  p.a_kc = (aCp % 64 == 0) ? 64 : 32;
+  p.b_kc = (bCp % 64 == 0) ? 64 : 32;
   p.a_boxes = 128 / p.a_kc;
-  const int BN = pick_bn(bC, 128, p.b_kc);
+  const int BN = pick_bn(bCp, 128, p.b_kc);
   if (BN == 0) { delete op; return set_error(MTBC_ERR_INVALID, "wgrad: no N tile for C=%d", bC); }
-  p.BN = BN; p.n_tiles = bC / BN; p.b_boxes = BN / p.b_kc;
+  p.BN = BN; p.n_tiles = bCp / BN; p.b_boxes = BN / p.b_kc;
   int T = 1;
   for (int t = 1; t <= d->ntaps; ++t) if (d->ntaps % t == 0 && t * BN <= 512) T = t;
   p.T = T; p.ntaps = d->ntaps;

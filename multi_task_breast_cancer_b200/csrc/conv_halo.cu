@@ -33,7 +33,7 @@ struct HaloSrc {
 
 struct HaloOut {
   __nv_bfloat16* ptr;
-  int32_t out_C, col0, col_end, accumulate;
+  int32_t out_C, col0, col_end, accumulate;   // out_C = channel pitch of the destination = number of columns that exist
 };
 
 struct ConvHaloParams {
@@ -121,7 +121,9 @@ __device__ __forceinline__ void halo_issue_chunk_g2(uint32_t d_addr, uint32_t a_
 struct HaloChunk {
   __nv_bfloat16* base;   // destination of column 0 of this chunk for pixel 0
   int32_t out_C;
-  int32_t accumulate;
+  int16_t accumulate;
+  int8_t nvalid;         // 0 / 8 / 16 columns of this chunk exist in the destination (dense pitch < GEMM columns)
+  int8_t wide;           // 32-byte aligned chunk addresses: 256-bit stores allowed
 };
 
 template <int V> struct IntC { static constexpr int value = V; };
@@ -160,6 +162,7 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
   auto flush_cols = [&](int n) {
     asm volatile("bar.sync 1, 256;" ::: "memory");
     for (int i = etid; i < BN; i += kEpiThreads) {
+      if (ntile * bn1 + (i % bn1) >= stat_C) continue;   // GEMM pad column of a dense tensor: no such channel
       const int64_t o = static_cast<int64_t>(n) * stat_C + ntile * bn1 + (i % bn1);   // G = 2: both rows -> one channel
       atomicAdd(stat_sum + o, s_part[0][0][i] + s_part[1][0][i] + s_part[2][0][i] + s_part[3][0][i]);
       atomicAdd(stat_sq + o, s_part[0][1][i] + s_part[1][1][i] + s_part[2][1][i] + s_part[3][1][i]);
@@ -215,7 +218,7 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
       }
     }
     const HaloChunk hc = s_chunk[k];
-    emit_bf16x16(hc.base + pix * hc.out_C, v, hc.accumulate != 0);
+    emit_bf16x16_n(hc.base + pix * hc.out_C, v, hc.accumulate != 0, hc.nvalid, hc.wide != 0);
   };
 
   int it = 0;
@@ -296,7 +299,10 @@ __global__ void __launch_bounds__(64 + kEpiThreads, MINB) conv_halo_kernel(const
     while (o + 1 < p.nouts && gc >= p.outs[o].col_end) ++o;   // slices are ordered by column
     s_chunk[tid].base = p.outs[o].ptr + (gc - p.outs[o].col0) + static_cast<int64_t>(prow) * p.W * p.outs[o].out_C;
     s_chunk[tid].out_C = p.outs[o].out_C;
-    s_chunk[tid].accumulate = p.outs[o].accumulate;
+    s_chunk[tid].accumulate = static_cast<int16_t>(p.outs[o].accumulate);
+    const int left = p.outs[o].out_C - (gc - p.outs[o].col0);
+    s_chunk[tid].nvalid = static_cast<int8_t>(left >= 16 ? 16 : (left >= 8 ? 8 : 0));
+    s_chunk[tid].wide = static_cast<int8_t>(p.outs[o].out_C % 16 == 0);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&s_afull[s], 1); mbar_init(&s_aempty[s], 1); }
@@ -566,7 +572,8 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
     int col = 0;
     for (int i = 0; i < d->nouts; ++i) {
       const mtbc_out_slice& o = d->outs[i];
-      if (!o.ptr || o.col0 != col || o.ncols <= 0 || o.ncols % 32 != 0 || o.out_C < o.ncols)
+      if (!o.ptr || o.col0 != col || o.ncols <= 0 || o.ncols % 32 != 0 || o.out_C % 8 != 0 || o.out_C > o.ncols ||
+          o.out_C + 31 < o.ncols)
         return set_error(MTBC_ERR_INVALID, "conv_gemm: output slice %d malformed", i);
       col += o.ncols;
     }
@@ -589,12 +596,12 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   for (int v = 0; v < d->nviews; ++v) {
     if (seen[v] != 0x1FF) return 1;
     const mtbc_act_view& a = d->views[v];
-    if (a.W != d->W || a.H != d->H || a.N != d->N || a.C % 32 != 0) return 1;
-    kused += a.C;
+    if (a.W != d->W || a.H != d->H || a.N != d->N || a.C % 8 != 0) return 1;
+    kused += (a.C + 31) & ~31;   // K is padded to 32 per source (TMA zero-fills the channels a dense tensor lacks)
   }
   // N tile such that the layer's weights stay resident in shared memory next to at least two halo stages
   int kc_any = 32;
-  for (int v = 0; v < d->nviews; ++v) if (d->views[v].C % 64 == 0 && wk0[v] % 64 == 0) kc_any = 64;
+  for (int v = 0; v < d->nviews; ++v) if (((d->views[v].C + 31) & ~31) % 64 == 0 && wk0[v] % 64 == 0) kc_any = 64;
   const int a_stage = ((kHaloRows * kc_any * 2) + 1023) & ~1023;
   int BN = 0;
   for (int bn = 16; bn <= 256 && bn <= d->ncols; bn += 16) {
@@ -625,12 +632,13 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   const bool allow64 = (G == 1) || (9 * BN * kused * 2 <= 64 * 1024);
   for (int v = 0; v < d->nviews; ++v) {
     const mtbc_act_view& a = d->views[v];
-    const int kc = (allow64 && a.C % 64 == 0 && wk0[v] % 64 == 0) ? 64 : 32;
+    const int aC = (a.C + 31) & ~31;
+    const int kc = (allow64 && aC % 64 == 0 && wk0[v] % 64 == 0) ? 64 : 32;
     if (kc > kcmax) kcmax = kc;
     (kc == 64 ? use64 : use32) = true;
-    p.src[v].kc = (int16_t)kc; p.src[v].nchunk = (int16_t)(a.C / kc); p.src[v].wk0 = wk0[v]; p.src[v].b_off = b_off;
-    b_off += a.C * BN * 2;
-    if (wk0[v] % 32 != 0 || wk0[v] + a.C > d->w_ktot) { delete op; return set_error(MTBC_ERR_INVALID, "conv_halo: weight columns out of range"); }
+    p.src[v].kc = (int16_t)kc; p.src[v].nchunk = (int16_t)(aC / kc); p.src[v].wk0 = wk0[v]; p.src[v].b_off = b_off;
+    b_off += aC * BN * 2;
+    if (wk0[v] % 32 != 0 || wk0[v] + aC > d->w_ktot) { delete op; return set_error(MTBC_ERR_INVALID, "conv_halo: weight columns out of range"); }
     int rc = encode_act(&p.amap[v], a, kc, kHaloW, halo_h, 1);
     if (rc) { delete op; return rc; }
   }
@@ -705,8 +713,9 @@ int wgrad_halo_try_create(const mtbc_wgrad_desc* d, OpBase** out) {
   }
   const mtbc_act_view& a = d->a_views[0];
   const mtbc_act_view& b = d->b_views[0];
-  if (a.C % 32 != 0 || b.C % 32 != 0 || a.W != d->W || a.H != d->H || a.N != d->N) return 1;
-  const int b_kc = (b.C % 64 == 0) ? 64 : 32;
+  if (a.C % 8 != 0 || b.C % 8 != 0 || a.W != d->W || a.H != d->H || a.N != d->N) return 1;
+  const int aCp = (a.C + 31) & ~31, bCp = (b.C + 31) & ~31;   // GEMM extents; TMA zero-fills what a dense tensor lacks
+  const int b_kc = (bCp % 64 == 0) ? 64 : 32;
   WgradHaloOp* op = new WgradHaloOp();
   WgradHaloParams& p = op->p;
   memset(&p, 0, sizeof(p));
@@ -714,7 +723,7 @@ int wgrad_halo_try_create(const mtbc_wgrad_desc* d, OpBase** out) {
   if (rc) { delete op; return rc; }
   rc = encode_act(&p.bmap, b, b_kc, 8, kHaloH, 1);
   if (rc) { delete op; return rc; }
-  p.a_C = a.C; p.b_kc = b_kc; p.NN = 3 * b_kc; p.n_tiles = b.C / b_kc;
+  p.a_C = a.C; p.b_kc = b_kc; p.NN = 3 * b_kc; p.n_tiles = bCp / b_kc;
   p.tmem_cols = tmem_cols_pow2(p.NN);
   p.tiles_w = d->W / 8; p.tiles_h = d->H / 16;
   p.n_ptiles = p.tiles_w * p.tiles_h * d->N;
@@ -727,7 +736,7 @@ int wgrad_halo_try_create(const mtbc_wgrad_desc* d, OpBase** out) {
   p.stages = stages;
   op->smem_bytes = stages * p.stage_bytes + 1024;
   p.n_rows = d->n_rows; p.ld_k = d->ld_k; p.k0 = d->k0; p.dw_acc = d->dw_acc;
-  const int chunks = a.C / 32;
+  const int chunks = aCp / 32;
   const int base = chunks * p.n_tiles;
   int splits = d->splits;
   if (splits <= 0) {

@@ -40,10 +40,10 @@ __global__ void __launch_bounds__(256) head1x1_bwd_kernel(const __nv_bfloat16* _
                                                           float* __restrict__ db) {
   extern __shared__ float s_acc[];  // [Cp + 1]
   const int cvec = Cp / 8;
-  for (int i = threadIdx.x; i <= Cp; i += 256) s_acc[i] = 0.f;
+  for (int i = threadIdx.x; i <= Cp; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   const int64_t total = npix * cvec;
-  const int64_t start = blockIdx.x * 256ll + threadIdx.x, stride = gridDim.x * 256ll;
+  const int64_t start = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x, stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   const int v = static_cast<int>(start % cvec);
   float wv[8], acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, accb = 0.f;
 #pragma unroll
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) head1x1_bwd_kernel(const __nv_bfloat16* _
     if (v == 0) atomicAdd(&s_acc[Cp], accb);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += 256) atomicAdd(dw + i, s_acc[i]);
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dw + i, s_acc[i]);
   if (threadIdx.x == 0) atomicAdd(db, s_acc[Cp]);
 }
 
@@ -493,9 +493,10 @@ int mtbc_head1x1_fwd(const void* a, int64_t npix, int32_t Cp, int32_t C, const f
 int mtbc_head1x1_bwd(const void* a, const float* dlogits, int64_t npix, int32_t Cp, int32_t C, const float* w,
                      void* dA, int32_t accumulate, float* dw, float* db, void* stream) {
   const int cvec = Cp / 8;
-  if (256 % cvec != 0) return set_error(MTBC_ERR_INVALID, "head1x1_bwd: Cp/8 must divide 256");
-  int g = cdiv(npix * cvec, 256 * 8); if (g > 148 * 8) g = 148 * 8; if (g < 1) g = 1;
-  head1x1_bwd_kernel<<<g, 256, (Cp + 1) * sizeof(float), ST(stream)>>>(CBF(a), dlogits, npix, Cp, C, w, BF(dA),
+  if (Cp % 8 != 0 || cvec > 256) return set_error(MTBC_ERR_INVALID, "head1x1_bwd: Cp %% 8 != 0 or Cp > 2048");
+  const int bd = (256 / cvec) * cvec;   // block size multiple of the channel-group count: a thread's group is invariant
+  int g = cdiv(npix * cvec, bd * 8); if (g > 148 * 8) g = 148 * 8; if (g < 1) g = 1;
+  head1x1_bwd_kernel<<<g, bd, (Cp + 1) * sizeof(float), ST(stream)>>>(CBF(a), dlogits, npix, Cp, C, w, BF(dA),
                                                                       accumulate, dw, db);
   return check_launch("head1x1_bwd");
 }

@@ -281,17 +281,18 @@ __global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __rest
                                                              const float* __restrict__ xs) {
   extern __shared__ __align__(16) float sm[];
   constexpr int K = CIN * 9;
-  float* s_w = sm;                    // [K][Cp], zero padded
-  float* s_b = s_w + Cp * K;          // [Cp]
-  float* s_st = s_b + Cp;             // [2][Cp]
-  for (int i = threadIdx.x; i < Cp * K; i += 128) {
+  const int Cs = (Cp + 15) & ~15;     // staging pitch: whole 16-column chunks even when the tensor pitch is dense
+  float* s_w = sm;                    // [K][Cs], zero padded
+  float* s_b = s_w + Cs * K;          // [Cs]
+  float* s_st = s_b + Cs;             // [2][Cs]
+  for (int i = threadIdx.x; i < Cs * K; i += 128) {
     const int c = i / K, k = i - c * K;
-    s_w[k * Cp + c] = c < Cout ? w[i] : 0.f;
+    s_w[k * Cs + c] = c < Cout ? w[i] : 0.f;
   }
-  for (int i = threadIdx.x; i < Cp; i += 128) {
+  for (int i = threadIdx.x; i < Cs; i += 128) {
     s_b[i] = (bias != nullptr && i < Cout) ? bias[i] : 0.f;
     s_st[i] = 0.f;
-    s_st[Cp + i] = 0.f;
+    s_st[Cs + i] = 0.f;
   }
   __syncthreads();
   const int64_t HW = static_cast<int64_t>(H) * W;
@@ -303,10 +304,10 @@ __global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __rest
   if (xs != nullptr) {
     // the block's 128 pixels belong to one sample (HW % 128 == 0): replace the bias by -(mean of w * x)
     const float inv = 1.f / static_cast<float>(HW);
-    for (int c = threadIdx.x; c < Cp; c += 128) {
+    for (int c = threadIdx.x; c < Cs; c += 128) {
       float m = 0.f;
 #pragma unroll
-      for (int k = 0; k < K; ++k) m = fmaf(s_w[k * Cp + c], xs[static_cast<int64_t>(n) * K + k], m);
+      for (int k = 0; k < K; ++k) m = fmaf(s_w[k * Cs + c], xs[static_cast<int64_t>(n) * K + k], m);
       s_b[c] = -m * inv;
     }
     __syncthreads();
@@ -323,7 +324,8 @@ __global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __rest
             (hh >= 0 && hh < H && wc >= 0 && wc < W) ? __ldg(x + (static_cast<int64_t>(n) * CIN + ci) * HW + hh * W + wc) : 0.f;
       }
   __nv_bfloat16* dst = y + pix * Cp;
-  for (int c0 = 0; c0 < Cp; c0 += 16) {
+  const bool wide = (Cp % 16) == 0;
+  for (int c0 = 0; c0 < Cs; c0 += 16) {
     float v[16];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -335,7 +337,7 @@ __global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __rest
       const float xk = xin[k];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float4 w4 = *reinterpret_cast<const float4*>(s_w + k * Cp + c0 + 4 * q);
+        const float4 w4 = *reinterpret_cast<const float4*>(s_w + k * Cs + c0 + 4 * q);
         v[4 * q] = fmaf(xk, w4.x, v[4 * q]); v[4 * q + 1] = fmaf(xk, w4.y, v[4 * q + 1]);
         v[4 * q + 2] = fmaf(xk, w4.z, v[4 * q + 2]); v[4 * q + 3] = fmaf(xk, w4.w, v[4 * q + 3]);
       }
@@ -349,16 +351,17 @@ __global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __rest
       if ((lane & 1) == 0) {
         const int cc = c0 + col16_of_lane(lane);
         atomicAdd(&s_st[cc], cs);
-        atomicAdd(&s_st[Cp + cc], cq);
+        atomicAdd(&s_st[Cs + cc], cq);
       }
     }
-    emit_bf16x16(dst + c0, v, false);
+    const int left = Cp - c0;
+    emit_bf16x16_n(dst + c0, v, false, left >= 16 ? 16 : 8, wide);
   }
   if (stat_sum != nullptr) {
     __syncthreads();
     for (int i = threadIdx.x; i < Cp; i += 128) {
       atomicAdd(stat_sum + static_cast<int64_t>(n) * Cp + i, s_st[i]);
-      atomicAdd(stat_sq + static_cast<int64_t>(n) * Cp + i, s_st[Cp + i]);
+      atomicAdd(stat_sq + static_cast<int64_t>(n) * Cp + i, s_st[Cs + i]);
     }
   }
 }
@@ -392,7 +395,8 @@ __global__ void __launch_bounds__(128) conv_first_wgrad_kernel(const float* __re
         xs[s] = (hh >= 0 && hh < H && wc >= 0 && wc < W) ? x[(static_cast<int64_t>(n) * Cin + ci) * HW + hh * W + wc] : 0.f;
       }
       const uint4* src = reinterpret_cast<const uint4*>(dy + pix * Cp + c0);
-      const uint4 d0 = src[0], d1 = src[1];
+      const uint4 d0 = src[0];
+      const uint4 d1 = (c0 + 8 < Cp) ? src[1] : make_uint4(0u, 0u, 0u, 0u);   // dense pitch: the chunk may be half
       const uint32_t du[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -498,7 +502,7 @@ int mtbc_unpack_convT_wgrad(const float* acc, int32_t rows, int32_t ld, float* g
 int mtbc_conv_first_fwd(const float* x, int32_t N, int32_t Cin, int32_t H, int32_t W, const float* w, const float* bias,
                         int32_t Cout, void* y, int32_t Cp, float* stat_sum, float* stat_sq, float* center_scratch,
                         void* stream) {
-  if (Cin < 1 || Cin > 4 || Cp % 16 != 0 || Cout > Cp) return set_error(MTBC_ERR_INVALID, "conv_first_fwd: Cin must be 1..4");
+  if (Cin < 1 || Cin > 4 || Cp % 8 != 0 || Cout > Cp) return set_error(MTBC_ERR_INVALID, "conv_first_fwd: Cin must be 1..4");
   const int64_t HW = static_cast<int64_t>(H) * W;
   if (HW % 128 != 0) return set_error(MTBC_ERR_INVALID, "conv_first_fwd: H*W must be a multiple of 128");
   if (center_scratch != nullptr) {
@@ -507,7 +511,8 @@ int mtbc_conv_first_fwd(const float* x, int32_t N, int32_t Cin, int32_t H, int32
     int rc = check_launch("conv_first_shift_sums");
     if (rc) return rc;
   }
-  const int smem = (Cp * Cin * 9 + 3 * Cp) * sizeof(float);
+  const int Cs = (Cp + 15) & ~15;
+  const int smem = (Cs * Cin * 9 + 3 * Cs) * sizeof(float);
   const int grid = static_cast<int>(N * HW / 128);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   __nv_bfloat16* yb = static_cast<__nv_bfloat16*>(y);
@@ -521,7 +526,7 @@ int mtbc_conv_first_fwd(const float* x, int32_t N, int32_t Cin, int32_t H, int32
 }
 int mtbc_conv_first_wgrad(const float* x, int32_t N, int32_t Cin, int32_t H, int32_t W, const void* dy, int32_t Cp,
                           int32_t Cout, float* dw, void* stream) {
-  if (Cin < 1 || Cin > 4 || Cout > 64 || Cp % 16 != 0) return set_error(MTBC_ERR_INVALID, "conv_first_wgrad: Cin 1..4, Cout <= 64");
+  if (Cin < 1 || Cin > 4 || Cout > 64 || Cp % 8 != 0) return set_error(MTBC_ERR_INVALID, "conv_first_wgrad: Cin 1..4, Cout <= 64");
   const int64_t total = static_cast<int64_t>(N) * H * W;
   int gx = static_cast<int>((total + 128 * 16 - 1) / (128 * 16));
   if (gx > 148 * 4) gx = 148 * 4;

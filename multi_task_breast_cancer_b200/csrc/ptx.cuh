@@ -279,4 +279,33 @@ __device__ __forceinline__ void emit_bf16x16(__nv_bfloat16* dst, const float (&v
   }
 }
 
+// Same for a destination whose channel pitch is only a multiple of 8 (dense 24 / 48-channel tensors): `nvalid` (0, 8 or
+// 16) leading columns exist in the tensor, and the pixel address is 16-byte but not always 32-byte aligned, so plain
+// stores go out as 128-bit halves unless `wide` (pitch % 16 == 0 channels, i.e. 32-byte aligned chunks).
+__device__ __forceinline__ void st_global_128(void* p, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+  asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+}
+__device__ __forceinline__ void emit_bf16x16_n(__nv_bfloat16* dst, const float (&v)[16], bool accumulate, int nvalid,
+                                               bool wide) {
+  if (nvalid <= 0) return;
+  const uint32_t w0 = pack_bf16x2(v[0], v[1]), w1 = pack_bf16x2(v[2], v[3]), w2 = pack_bf16x2(v[4], v[5]),
+                 w3 = pack_bf16x2(v[6], v[7]);
+  if (nvalid >= 16) {
+    const uint32_t w4 = pack_bf16x2(v[8], v[9]), w5 = pack_bf16x2(v[10], v[11]), w6 = pack_bf16x2(v[12], v[13]),
+                   w7 = pack_bf16x2(v[14], v[15]);
+    if (accumulate) {
+      red_add_bf16x8(dst, w0, w1, w2, w3);
+      red_add_bf16x8(dst + 8, w4, w5, w6, w7);
+    } else if (wide) {
+      st_global_256(dst, w0, w1, w2, w3, w4, w5, w6, w7);
+    } else {
+      st_global_128(dst, w0, w1, w2, w3);
+      st_global_128(dst + 8, w4, w5, w6, w7);
+    }
+  } else {
+    if (accumulate) red_add_bf16x8(dst, w0, w1, w2, w3);
+    else st_global_128(dst, w0, w1, w2, w3);
+  }
+}
+
 }  // namespace mtbc

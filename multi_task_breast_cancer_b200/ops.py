@@ -22,6 +22,19 @@ def pad32(c: int) -> int:
     return (c + 31) // 32 * 32
 
 
+def _pitch_multiple() -> int:
+    """Channel pitch of activation tensors: 8 (dense: a 24-channel tensor is stored with 24 channels, 48 bytes per
+    pixel) or 32 (legacy padded layout, MTBC_PAD=32).  GEMM extents (K per source, N) are always padded to 32: TMA
+    zero-fills the channels a dense tensor lacks and the epilogues only write the columns that exist."""
+    import os
+    return 32 if os.environ.get("MTBC_PAD", "8") == "32" else 8
+
+
+def pitch_of(c: int) -> int:
+    m = _pitch_multiple()
+    return (c + m - 1) // m * m
+
+
 def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -41,7 +54,7 @@ def ptr(t: Optional[torch.Tensor]):
 
 @dataclass
 class Feat:
-    """bf16 NHWC activation with padded channels."""
+    """bf16 NHWC activation.  Cp = channel pitch of the tensor (multiple of 8), Ck = its GEMM extent (multiple of 32)."""
     t: torch.Tensor  # [N, H, W, Cp] bf16
     C: int           # true channels
 
@@ -53,11 +66,13 @@ class Feat:
     def W(self): return self.t.shape[2]
     @property
     def Cp(self): return self.t.shape[3]
+    @property
+    def Ck(self): return pad32(self.t.shape[3])
 
     @staticmethod
     def empty(N, H, W, C, device="cuda", zero=True) -> "Feat":
         f = torch.zeros if zero else torch.empty
-        return Feat(f((N, H, W, pad32(C)), dtype=torch.bfloat16, device=device), C)
+        return Feat(f((N, H, W, pitch_of(C)), dtype=torch.bfloat16, device=device), C)
 
     @staticmethod
     def from_nchw(x: torch.Tensor) -> "Feat":
@@ -113,10 +128,10 @@ def k_offsets(srcs: Sequence[Feat]):
     """Column offsets of each concat source inside a packed weight row, and the padded row length."""
     offs, o = [], 0
     for s in srcs:
-        a = 64 if s.Cp % 64 == 0 else 32
+        a = 64 if s.Ck % 64 == 0 else 32
         o = (o + a - 1) // a * a
         offs.append(o)
-        o += s.Cp
+        o += s.Ck
     return offs, o
 
 
@@ -129,9 +144,9 @@ def _create_gemm(d: ConvGemmDesc, keep, kind) -> Op:
 def conv3x3_fwd_op(srcs: Sequence[Feat], wpack: torch.Tensor, out: Feat, bias: Optional[torch.Tensor] = None,
                    stat_sum: Optional[torch.Tensor] = None, stat_sq: Optional[torch.Tensor] = None,
                    accumulate: bool = False, ksz: int = 3, kind: str = "conv3x3_fwd") -> Op:
-    """wpack: bf16 [ksz*ksz][out.Cp][Ktot] laid out by `k_offsets(srcs)`."""
+    """wpack: bf16 [ksz*ksz][out.Ck][Ktot] laid out by `k_offsets(srcs)`."""
     offs, ktot = k_offsets(srcs)
-    assert wpack.shape == (ksz * ksz, out.Cp, ktot), (wpack.shape, (ksz * ksz, out.Cp, ktot))
+    assert wpack.shape == (ksz * ksz, out.Ck, ktot), (wpack.shape, (ksz * ksz, out.Ck, ktot))
     d = ConvGemmDesc()
     d.nviews = len(srcs)
     for i, s in enumerate(srcs):
@@ -144,9 +159,9 @@ def conv3x3_fwd_op(srcs: Sequence[Feat], wpack: torch.Tensor, out: Feat, bias: O
                 d.seg[n] = GemmSeg(i, r - half, c - half, offs[i], r * ksz + c)
                 n += 1
     d.nseg = n
-    d.wpack = wpack.data_ptr(); d.w_ntaps = ksz * ksz; d.w_ktot = ktot; d.ncols = out.Cp
+    d.wpack = wpack.data_ptr(); d.w_ntaps = ksz * ksz; d.w_ktot = ktot; d.ncols = out.Ck
     d.W, d.H, d.N = out.W, out.H, out.N
-    d.epi_mode = 0; d.out = out.t.data_ptr(); d.out_C = out.Cp; d.up_k = 1; d.up_cp = out.Cp
+    d.epi_mode = 0; d.out = out.t.data_ptr(); d.out_C = out.Cp; d.up_k = 1; d.up_cp = out.Ck
     d.bias = None if bias is None else bias.data_ptr()
     d.stat_sum = None if stat_sum is None else stat_sum.data_ptr()
     d.stat_sq = None if stat_sq is None else stat_sq.data_ptr()
@@ -157,16 +172,16 @@ def conv3x3_fwd_op(srcs: Sequence[Feat], wpack: torch.Tensor, out: Feat, bias: O
 
 
 def conv3x3_dgrad_op(dy: Feat, wd: torch.Tensor, dx: Feat, accumulate: bool, ksz: int = 3) -> Op:
-    """wd: bf16 [ksz*ksz][dx.Cp][dy.Cp] (flipped taps, transposed channels) -> dx (+)= conv(dy, wd)."""
+    """wd: bf16 [ksz*ksz][dx.Ck][dy.Ck] (flipped taps, transposed channels) -> dx (+)= conv(dy, wd)."""
     return conv3x3_fwd_op([dy], wd, dx, accumulate=accumulate, ksz=ksz, kind="conv3x3_dgrad")
 
 
 def conv3x3_dgrad_multi_op(dy: Feat, wd_all: torch.Tensor, dxs: Sequence[Feat], accumulates: Sequence[bool]) -> Op:
     """Fused data gradient of a conv over a folded concat: ONE launch reads dy once and writes every source's gradient.
-    wd_all: bf16 [9][sum(dx.Cp)][dy.Cp] (flipped taps, rows = the sources' padded channels back to back).
+    wd_all: bf16 [9][sum(dx.Ck)][dy.Ck] (flipped taps, rows = the sources' padded channels back to back).
     Raises MtbcError when the shape is not served by the halo kernel (caller falls back to one launch per source)."""
-    rows = sum(f.Cp for f in dxs)
-    assert wd_all.shape == (9, rows, dy.Cp) and wd_all.is_contiguous(), (wd_all.shape, rows, dy.Cp)
+    rows = sum(f.Ck for f in dxs)
+    assert wd_all.shape == (9, rows, dy.Ck) and wd_all.is_contiguous(), (wd_all.shape, rows, dy.Ck)
     d = ConvGemmDesc()
     d.nviews = 1
     d.views[0] = _view(dy)
@@ -176,7 +191,7 @@ def conv3x3_dgrad_multi_op(dy: Feat, wd_all: torch.Tensor, dxs: Sequence[Feat], 
             d.seg[n] = GemmSeg(0, r - 1, c - 1, 0, r * 3 + c)
             n += 1
     d.nseg = n
-    d.wpack = wd_all.data_ptr(); d.w_ntaps = 9; d.w_ktot = dy.Cp; d.ncols = rows
+    d.wpack = wd_all.data_ptr(); d.w_ntaps = 9; d.w_ktot = dy.Ck; d.ncols = rows
     d.W, d.H, d.N = dy.W, dy.H, dy.N
     d.epi_mode = 0; d.out = None; d.out_C = 0; d.up_k = 1; d.up_cp = rows
     d.bias = None; d.stat_sum = None; d.stat_sq = None; d.stat_C = 0; d.accumulate = 0
@@ -184,44 +199,44 @@ def conv3x3_dgrad_multi_op(dy: Feat, wd_all: torch.Tensor, dxs: Sequence[Feat], 
     col = 0
     for i, (f, acc) in enumerate(zip(dxs, accumulates)):
         assert (f.N, f.H, f.W) == (dy.N, dy.H, dy.W)
-        d.outs[i] = OutSlice(f.t.data_ptr(), f.Cp, col, f.Cp, int(acc))
-        col += f.Cp
+        d.outs[i] = OutSlice(f.t.data_ptr(), f.Cp, col, f.Ck, int(acc))   # (ptr, pitch, first column, GEMM columns)
+        col += f.Ck
     return _create_gemm(d, [dy.t, wd_all, *(f.t for f in dxs)], "conv3x3_dgrad")
 
 
 def convT_fwd_op(x: Feat, wf: torch.Tensor, out: Feat, k: int, bias: Optional[torch.Tensor]) -> Op:
-    """wf: bf16 [1][k*k*out.Cp][x.Cp]; out spatial = k * x spatial."""
-    assert wf.shape == (1, k * k * out.Cp, x.Cp)
+    """wf: bf16 [1][k*k*out.Ck][x.Ck]; out spatial = k * x spatial."""
+    assert wf.shape == (1, k * k * out.Ck, x.Ck)
     d = ConvGemmDesc()
     d.nviews = 1; d.views[0] = _view(x)
     d.nseg = 1; d.seg[0] = GemmSeg(0, 0, 0, 0, 0)
-    d.wpack = wf.data_ptr(); d.w_ntaps = 1; d.w_ktot = x.Cp; d.ncols = k * k * out.Cp
+    d.wpack = wf.data_ptr(); d.w_ntaps = 1; d.w_ktot = x.Ck; d.ncols = k * k * out.Ck
     d.W, d.H, d.N = x.W, x.H, x.N
-    d.epi_mode = 1; d.out = out.t.data_ptr(); d.out_C = out.Cp; d.up_k = k; d.up_cp = out.Cp
+    d.epi_mode = 1; d.out = out.t.data_ptr(); d.out_C = out.Cp; d.up_k = k; d.up_cp = out.Ck
     d.bias = None if bias is None else bias.data_ptr()
     d.stat_sum = None; d.stat_sq = None; d.stat_C = 0; d.accumulate = 0
     return _create_gemm(d, [x.t, wf, out.t, bias], "convT_fwd")
 
 
 def convT_dgrad_op(dout: Feat, wd: torch.Tensor, dx: Feat, k: int, accumulate: bool) -> Op:
-    """wd: bf16 [k*k][dx.Cp][dout.Cp]; dx (+)= sum_q dout_q * wd[q]."""
-    assert wd.shape == (k * k, dx.Cp, dout.Cp)
+    """wd: bf16 [k*k][dx.Ck][dout.Ck]; dx (+)= sum_q dout_q * wd[q]."""
+    assert wd.shape == (k * k, dx.Ck, dout.Ck)
     d = ConvGemmDesc()
     d.nviews = k * k
     for q in range(k * k):
         d.views[q] = _strided_view(dout, k, q // k, q % k)
         d.seg[q] = GemmSeg(q, 0, 0, 0, q)
     d.nseg = k * k
-    d.wpack = wd.data_ptr(); d.w_ntaps = k * k; d.w_ktot = dout.Cp; d.ncols = dx.Cp
+    d.wpack = wd.data_ptr(); d.w_ntaps = k * k; d.w_ktot = dout.Ck; d.ncols = dx.Ck
     d.W, d.H, d.N = dx.W, dx.H, dx.N
-    d.epi_mode = 0; d.out = dx.t.data_ptr(); d.out_C = dx.Cp; d.up_k = 1; d.up_cp = dx.Cp
+    d.epi_mode = 0; d.out = dx.t.data_ptr(); d.out_C = dx.Cp; d.up_k = 1; d.up_cp = dx.Ck
     d.bias = None; d.stat_sum = None; d.stat_sq = None; d.stat_C = 0; d.accumulate = int(accumulate)
     return _create_gemm(d, [dout.t, wd, dx.t], "convT_dgrad")
 
 
 def conv3x3_wgrad_op(x: Feat, dy: Feat, dw_acc: torch.Tensor, k0: int, ksz: int = 3, splits: int = 0) -> Op:
-    """dw_acc: fp32 [ksz*ksz][dy.Cp][Ktot]; accumulates the slice of source x at column k0."""
-    assert dw_acc.dtype == torch.float32 and dw_acc.shape[0] == ksz * ksz and dw_acc.shape[1] == dy.Cp
+    """dw_acc: fp32 [ksz*ksz][dy.Ck][Ktot]; accumulates the slice of source x at column k0."""
+    assert dw_acc.dtype == torch.float32 and dw_acc.shape[0] == ksz * ksz and dw_acc.shape[1] == dy.Ck
     d = WgradDesc()
     d.a_nviews = 1; d.a_views[0] = _view(x)
     d.b_nviews = 1; d.b_views[0] = _view(dy)
@@ -240,8 +255,8 @@ def conv3x3_wgrad_op(x: Feat, dy: Feat, dw_acc: torch.Tensor, k0: int, ksz: int 
 
 
 def convT_wgrad_op(x: Feat, dout: Feat, dw_acc: torch.Tensor, k: int, splits: int = 0) -> Op:
-    """dw_acc: fp32 [k*k][dout.Cp][x.Cp]."""
-    assert dw_acc.shape == (k * k, dout.Cp, x.Cp)
+    """dw_acc: fp32 [k*k][dout.Ck][x.Ck]."""
+    assert dw_acc.shape == (k * k, dout.Ck, x.Ck)
     d = WgradDesc()
     d.a_nviews = 1; d.a_views[0] = _view(x)
     d.b_nviews = k * k

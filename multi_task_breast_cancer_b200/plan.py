@@ -16,7 +16,7 @@ from typing import Callable, Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib, ops
-from .ops import Feat, pad32, ptr
+from .ops import Feat, pad32, pitch_of, ptr
 
 EPS = 1e-5
 
@@ -174,7 +174,7 @@ class Plan:
         return t
 
     def scratch(self, N, H, W, Cc) -> Feat:
-        key = (N, H, W, pad32(Cc))
+        key = (N, H, W, pitch_of(Cc))
         if os.environ.get("MTBC_DEBUG_UNIQUE_SCRATCH"):
             key = key + (len(self._scratch),)
         if key not in self._scratch:
@@ -238,12 +238,12 @@ class Plan:
         assert sum(f.C for f in feats) == Cin, (name, [f.C for f in feats], Cin)
         N, H, Wd = feats[0].N, feats[0].H, feats[0].W
         y = self.new(N, H, Wd, Cout, name + ".y")
-        Cp = y.feat.Cp
-        pk = self._pack_conv(w, feats, Cp)
+        Cp = y.feat.Cp                      # channel pitch of y (statistics arrays follow it)
+        pk = self._pack_conv(w, feats, y.feat.Ck)
         ssum = self.fwd_arena.alloc(N, Cp)
         ssq = self.fwd_arena.alloc(N, Cp)
         fused = H * Wd >= 128
-        bias = self._padded_vec(b, Cp)
+        bias = self._padded_vec(b, y.feat.Ck)
         op = ops.conv3x3_fwd_op(feats, pk["wf"], y.feat, bias=bias, stat_sum=ssum if fused else None,
                                 stat_sq=ssq if fused else None)
         self.tc_flops_fwd += op.flops
@@ -276,7 +276,7 @@ class Plan:
         key = w
         if key in self._packed:
             pk = self._packed[key]
-            assert [f.Cp for f in feats] == pk["src_cp"]
+            assert [f.Ck for f in feats] == pk["src_cp"]
             return pk
         Wt = self.P(w)
         offs, ktot = ops.k_offsets(feats)
@@ -287,7 +287,7 @@ class Plan:
             self.pack_jobs.add(_lib.JOB_PACK_CONV, [Wt.shape[0], Wt.shape[1], 3, c0, cs, wf.shape[1], wf.shape[2], off,
                                                     0, 0], Wt, wf, None)
             c0 += cs
-        pk = {"wf": wf, "offs": offs, "ktot": ktot, "src_cp": [f.Cp for f in feats], "src_c": st_c, "Cp": Cp}
+        pk = {"wf": wf, "offs": offs, "ktot": ktot, "src_cp": [f.Ck for f in feats], "src_c": st_c, "Cp": Cp}
         self._packed[key] = pk
         return pk
 
@@ -365,8 +365,8 @@ class Plan:
         p = self.new(N, H // 2, Wd // 2, Cc, name + ".pool") if pool else None
         mean = torch.zeros(N, Cp, dtype=torch.float32, device=self.device)
         rstd = torch.zeros(N, Cp, dtype=torch.float32, device=self.device)
-        gv = self._padded_vec(gamma, Cp)
-        bv = self._padded_vec(beta, Cp)
+        gv = self._padded_vec(gamma, y.feat.Ck)
+        bv = self._padded_vec(beta, y.feat.Ck)
         self.fwd.append(_mk("mtbc_in_apply", ptr(y.feat.t), N, H, Wd, Cp, ptr(ssum), ptr(ssq), ptr(gv), ptr(bv), Cc,
                             C.c_float(EPS), C.c_float(slope), ptr(a.feat.t), None if p is None else ptr(p.feat.t),
                             ptr(mean), ptr(rstd)))
@@ -402,9 +402,9 @@ class Plan:
         f = x.feat
         assert f.C == Cin
         out = self.new(f.N, f.H * k, f.W * k, Cout, name)
-        cp = out.feat.Cp
-        wf = torch.zeros(1, k * k * cp, f.Cp, dtype=torch.bfloat16, device=self.device)
-        wd = torch.zeros(k * k, f.Cp, cp, dtype=torch.bfloat16, device=self.device) if self.training else None
+        cp = out.feat.Ck                    # GEMM columns per sub-pixel (the tensor itself may be denser: out.feat.Cp)
+        wf = torch.zeros(1, k * k * cp, f.Ck, dtype=torch.bfloat16, device=self.device)
+        wd = torch.zeros(k * k, f.Ck, cp, dtype=torch.bfloat16, device=self.device) if self.training else None
         self.pack_jobs.add(_lib.JOB_PACK_CONVT, [Cin, Cout, k, cp, wf.shape[2], 0 if wd is None else wd.shape[1],
                                                  0 if wd is None else wd.shape[2]], Wt, wf, wd)
         bias = self._padded_vec(b, cp)
@@ -417,14 +417,14 @@ class Plan:
             blk: List[Callable] = []
             if not out.g_init:
                 return blk
-            acc = self.bwd_arena.alloc(k * k, cp, f.Cp)
+            acc = self.bwd_arena.alloc(k * k, cp, f.Ck)
             o = ops.convT_wgrad_op(f, out.g, acc, k)
             self.tc_flops_bwd += o.flops
             blk.append(_mk_op(o, t_flops, f"{name} convT wgrad {f.N}x{f.H}x{f.W} {Cin}->{Cout}"))
-            self.unpack_jobs.add(_lib.JOB_UNPACK_CONVT, [k * k * cp, f.Cp, Cin, Cout, k, 0], acc, self.grad_view[w])
+            self.unpack_jobs.add(_lib.JOB_UNPACK_CONVT, [k * k * cp, f.Ck, Cin, Cout, k, 0], acc, self.grad_view[w])
             self._late_unpacked.append(w)
             if b is not None:
-                blk.append(_mk("mtbc_channel_sum", ptr(out.g.t), out.g.N * out.g.H * out.g.W, cp, Cout,
+                blk.append(_mk("mtbc_channel_sum", ptr(out.g.t), out.g.N * out.g.H * out.g.W, out.g.Cp, Cout,
                                ptr(self.grad_view[b]), 1))
             self._mark_grad(w, b)
             g = x.grad()

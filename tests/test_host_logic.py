@@ -68,8 +68,10 @@ def test_flat_layout_is_reverse_registration_order_and_padded():
 
 
 def test_k_offsets_alignment():
-    class F:  # minimal stand-in for ops.Feat
-        def __init__(self, cp): self.Cp = cp
+    class F:  # minimal stand-in for ops.Feat: Cp = channel pitch of the tensor, Ck = its GEMM extent (padded to 32)
+        def __init__(self, cp): self.Cp, self.Ck = cp, ops.pad32(cp)
+    offs, ktot = ops.k_offsets([F(24), F(48)])     # dense 24 / 48-channel tensors occupy 32 / 64 weight columns
+    assert offs == [0, 64] and ktot == 128
     offs, ktot = ops.k_offsets([F(32), F(64)])
     assert offs == [0, 64] and ktot == 128          # 64-wide sources start on a 64 boundary
     offs, ktot = ops.k_offsets([F(32), F(32), F(96)])

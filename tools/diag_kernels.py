@@ -68,11 +68,11 @@ def conv_fwd_case(N, H, W, src_C, Cout, bias=True, stats=True, identity=False):
         srcs = [Feat.from_nchw(x) for x in xs]
         out = Feat.empty(N, H, W, Cout)
         offs, ktot = ops.k_offsets(srcs)
-        wf = torch.zeros(9, out.Cp, ktot, dtype=torch.bfloat16, device=dev)
+        wf = torch.zeros(9, out.Ck, ktot, dtype=torch.bfloat16, device=dev)
         ops.pack_conv_weight(w, src_C, offs, wf, [None] * len(srcs))
         bp = None
         if bias:
-            bp = torch.zeros(out.Cp, device=dev)
+            bp = torch.zeros(out.Ck, device=dev)
             bp[:Cout] = b
         ssum = ssq = None
         if stats:
@@ -103,8 +103,8 @@ def conv_dgrad_case(N, H, W, Cin, Cout, accumulate, dyscale=1.0):
         base = rnd(N, Cin, H, W, scale=dyscale)
         if accumulate:
             dx = Feat.from_nchw(base)
-        wd = torch.zeros(9, dx.Cp, dyf.Cp, dtype=torch.bfloat16, device=dev)
-        wf = torch.zeros(9, dyf.Cp, dx.Cp, dtype=torch.bfloat16, device=dev)
+        wd = torch.zeros(9, dx.Ck, dyf.Ck, dtype=torch.bfloat16, device=dev)
+        wf = torch.zeros(9, dyf.Ck, dx.Ck, dtype=torch.bfloat16, device=dev)
         ops.pack_conv_weight(w, [Cin], [0], wf, [wd])
         op = ops.conv3x3_dgrad_op(dyf, wd, dx, accumulate)
         op.launch()
@@ -132,14 +132,14 @@ def conv_dgrad_multi_case(N, H, W, src_C, Cout, acc_flags=None):
         for d, f in zip(dxs, flags):
             if not f:
                 d.t.fill_(7.0)  # must be overwritten, pad lanes included
-        rows = sum(d.Cp for d in dxs)
-        wd_all = torch.zeros(9, rows, dyf.Cp, dtype=torch.bfloat16, device=dev)
+        rows = sum(d.Ck for d in dxs)
+        wd_all = torch.zeros(9, rows, dyf.Ck, dtype=torch.bfloat16, device=dev)
         c0 = r0 = 0
         for c, d in zip(src_C, dxs):
             _lib.call("mtbc_pack_conv_weight", ops.ptr(w), Cout, Cin, 3, c0, c, None, 0, 0, 0, ops.ptr(wd_all[0, r0:]),
-                      rows, dyf.Cp, None)
+                      rows, dyf.Ck, None)
             c0 += c
-            r0 += d.Cp
+            r0 += d.Ck
         op = ops.conv3x3_dgrad_multi_op(dyf, wd_all, dxs, flags)
         op.launch()
         torch.cuda.synchronize()
@@ -162,7 +162,7 @@ def conv_wgrad_case(N, H, W, Cin, Cout, splits=0):
         x = rnd(N, Cin, H, W)
         dy = rnd(N, Cout, H, W)
         xf, dyf = Feat.from_nchw(x), Feat.from_nchw(dy)
-        acc = torch.zeros(9, dyf.Cp, xf.Cp, device=dev)
+        acc = torch.zeros(9, dyf.Ck, xf.Ck, device=dev)
         op = ops.conv3x3_wgrad_op(xf, dyf, acc, 0, splits=splits)
         op.launch()
         torch.cuda.synchronize()
@@ -185,10 +185,10 @@ def convT_case(N, H, W, Cin, Cout, k=2):
         b = rnd(Cout)
         xf = Feat.from_nchw(x)
         out = Feat.empty(N, H * k, W * k, Cout)
-        wf = torch.zeros(1, k * k * out.Cp, xf.Cp, dtype=torch.bfloat16, device=dev)
-        wd = torch.zeros(k * k, xf.Cp, out.Cp, dtype=torch.bfloat16, device=dev)
-        ops.pack_convT_weight(w, out.Cp, wf, wd)
-        bp = torch.zeros(out.Cp, device=dev)
+        wf = torch.zeros(1, k * k * out.Ck, xf.Ck, dtype=torch.bfloat16, device=dev)
+        wd = torch.zeros(k * k, xf.Ck, out.Ck, dtype=torch.bfloat16, device=dev)
+        ops.pack_convT_weight(w, out.Ck, wf, wd)
+        bp = torch.zeros(out.Ck, device=dev)
         bp[:Cout] = b
         ops.convT_fwd_op(xf, wf, out, k, bp).launch()
         torch.cuda.synchronize()
@@ -203,7 +203,7 @@ def convT_case(N, H, W, Cin, Cout, k=2):
         refdx = F.conv2d(dout, w, stride=k)
         report(name + " dgrad", dx.to_nchw(), refdx)
         # wgrad
-        acc = torch.zeros(k * k, out.Cp, xf.Cp, device=dev)
+        acc = torch.zeros(k * k, out.Ck, xf.Ck, device=dev)
         ops.convT_wgrad_op(xf, df, acc, k).launch()
         grad = torch.zeros(Cin, Cout, k, k, device=dev)
         _lib.call("mtbc_unpack_convT_wgrad", ops.ptr(acc), acc.shape[0] * acc.shape[1], acc.shape[2], ops.ptr(grad), Cin,
