@@ -241,13 +241,14 @@ int mtbc_dshead_decompose(const float* dwc, const float* dbc, const float* wt, c
 /* ------------------------------------------------------------------------------------------------------------- */
 /* Classification head: AdaptiveAvgPool2d(1) -> Flatten -> Linear(F,Hd) -> ReLU -> Linear(Hd,K)
  * (MTnnUNet.py:125-132, MTUNetPlusPlus.py:80-87).  hidden (fp32 [N][Hd]) and gap (fp32 [N][F]) are saved by the
- * forward; the backward overwrites hidden with d(hidden).  dw1/db1/dw2/db2 accumulate (zeroed by the caller). */
+ * forward; the backward overwrites hidden with d(hidden).  dw1/db1/dw2/db2 accumulate (zeroed by the caller);
+ * dgap is fp32 [N][F] scratch (the pooled gradient, broadcast over the plane by a grid-wide pass). */
 int mtbc_gap_fc_fwd(const void* a, int32_t N, int32_t HW, int32_t Cp, int32_t F, const float* w1, const float* b1,
                     int32_t Hd, const float* w2, const float* b2, int32_t K, float* gap, float* hidden, float* logits,
                     void* stream);
 int mtbc_gap_fc_bwd(const float* dlogits, int32_t N, int32_t HW, int32_t Cp, int32_t F, const float* w1, int32_t Hd,
                     const float* w2, int32_t K, const float* gap, float* hidden, void* dA, int32_t accumulate,
-                    float* dw1, float* db1, float* dw2, float* db2, void* stream);
+                    float* dw1, float* db1, float* dw2, float* db2, float* dgap, void* stream);
 /* Flatten -> Linear(C*HW, Hd) -> ReLU -> Linear(Hd,K) head of Multi_BTS_UNet (Multi_BTS_UNet.py:107-115); the
  * weight columns are indexed in NCHW flatten order (c*HW + hw) as in the reference. */
 int mtbc_flat_fc_fwd(const void* a, int32_t N, int32_t HW, int32_t Cp, int32_t C, const float* w1, const float* b1,

@@ -94,7 +94,7 @@ _SIGS = {
     "mtbc_gap_fc_fwd": [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp,
                         c_vp],
     "mtbc_gap_fc_bwd": [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp,
-                        c_vp, c_vp, c_vp, c_vp],
+                        c_vp, c_vp, c_vp, c_vp, c_vp],
     "mtbc_flat_fc_fwd": [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp],
     "mtbc_flat_fc_bwd": [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp,
                          c_vp, c_vp, c_vp, c_vp, c_vp],

@@ -249,24 +249,48 @@ __global__ void dshead_decompose_kernel(const float* __restrict__ dwc, const flo
 }
 
 // ------------------------------------------------------------------------------------------------ GAP + FC head
-__global__ void __launch_bounds__(256) gap_fc_fwd_kernel(const __nv_bfloat16* __restrict__ a, int HW, int Cp, int F,
-                                                         const float* __restrict__ w1, const float* __restrict__ b1,
-                                                         int Hd, const float* __restrict__ w2,
-                                                         const float* __restrict__ b2, int K, float* __restrict__ gap,
-                                                         float* __restrict__ hidden, float* __restrict__ logits) {
+// gap[n][c] = mean over the plane.  grid (N, ceil(Cp / 64)): 8 channel vectors (16 B each) x 32 pixel lanes per block.
+__global__ void __launch_bounds__(256) gap_kernel(const __nv_bfloat16* __restrict__ a, int HW, int Cp, int F,
+                                                  float* __restrict__ gap) {
+  __shared__ float s_red[32][65];
+  const int n = blockIdx.x, vec = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int c0 = blockIdx.y * 64 + vec * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c0 < Cp) {
+    const __nv_bfloat16* src = a + static_cast<int64_t>(n) * HW * Cp + c0;
+    for (int p = pl; p < HW; p += 32) {
+      const uint4 u = *reinterpret_cast<const uint4*>(src + static_cast<int64_t>(p) * Cp);
+      const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16x2(uu[k]);
+        acc[2 * k] += f.x;
+        acc[2 * k + 1] += f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s_red[pl][vec * 8 + k] = acc[k];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int c = blockIdx.y * 64 + threadIdx.x;
+    float s = 0.f;
+#pragma unroll 8
+    for (int q = 0; q < 32; ++q) s += s_red[q][threadIdx.x];
+    if (c < F) gap[static_cast<int64_t>(n) * F + c] = s / static_cast<float>(HW);
+  }
+}
+
+// hidden = relu(W1 gap + b1), logits = W2 hidden + b2; one block per sample
+__global__ void __launch_bounds__(256) fc_fwd_kernel(const float* __restrict__ gap, int F, const float* __restrict__ w1,
+                                                     const float* __restrict__ b1, int Hd, const float* __restrict__ w2,
+                                                     const float* __restrict__ b2, int K, float* __restrict__ hidden,
+                                                     float* __restrict__ logits) {
   extern __shared__ float sm[];
   float* s_gap = sm;       // [F]
   float* s_h = sm + F;     // [Hd]
   const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const __nv_bfloat16* src = a + static_cast<int64_t>(n) * HW * Cp;
-  const float inv = 1.f / static_cast<float>(HW);
-  for (int c = threadIdx.x; c < F; c += 256) {
-    float s = 0.f;
-    for (int p = 0; p < HW; ++p) s += __bfloat162float(src[static_cast<int64_t>(p) * Cp + c]);
-    s *= inv;
-    s_gap[c] = s;
-    gap[static_cast<int64_t>(n) * F + c] = s;
-  }
+  for (int c = threadIdx.x; c < F; c += 256) s_gap[c] = gap[static_cast<int64_t>(n) * F + c];
   __syncthreads();
   for (int j = warp; j < Hd; j += 8) {
     const float* wr = w1 + static_cast<int64_t>(j) * F;
@@ -289,12 +313,11 @@ __global__ void __launch_bounds__(256) gap_fc_fwd_kernel(const __nv_bfloat16* __
   }
 }
 
-// per sample: dh (written over hidden), dgap -> dA broadcast, dw2/db2 via atomics
-__global__ void __launch_bounds__(256) gap_fc_bwd_sample_kernel(const float* __restrict__ dl, int HW, int Cp, int F,
+// per sample: dh (written over hidden), dgap[n][c] = (1/HW) sum_j w1[j][c] dh[j], dw2/db2 via atomics
+__global__ void __launch_bounds__(256) gap_fc_bwd_sample_kernel(const float* __restrict__ dl, int HW, int F,
                                                                 const float* __restrict__ w1, int Hd,
                                                                 const float* __restrict__ w2, int K,
-                                                                float* __restrict__ hidden,
-                                                                __nv_bfloat16* __restrict__ dA, int accumulate,
+                                                                float* __restrict__ hidden, float* __restrict__ dgap,
                                                                 float* __restrict__ dw2, float* __restrict__ db2) {
   extern __shared__ float sm[];
   float* s_dh = sm;        // [Hd]
@@ -319,18 +342,37 @@ __global__ void __launch_bounds__(256) gap_fc_bwd_sample_kernel(const float* __r
   }
   __syncthreads();
   const float inv = 1.f / static_cast<float>(HW);
-  __nv_bfloat16* dst = dA + static_cast<int64_t>(n) * HW * Cp;
-  for (int c = threadIdx.x; c < Cp; c += 256) {
+  for (int c = threadIdx.x; c < F; c += 256) {
     float s = 0.f;
-    if (c < F)
-      for (int j = 0; j < Hd; ++j) s = fmaf(w1[static_cast<int64_t>(j) * F + c], s_dh[j], s);
-    s *= inv;
-    for (int p = 0; p < HW; ++p) {
-      __nv_bfloat16* d = dst + static_cast<int64_t>(p) * Cp + c;
-      float o = s;
-      if (accumulate) o += __bfloat162float(*d);
-      *d = __float2bfloat16(o);
+    for (int j = 0; j < Hd; ++j) s = fmaf(w1[static_cast<int64_t>(j) * F + c], s_dh[j], s);
+    dgap[static_cast<int64_t>(n) * F + c] = s * inv;
+  }
+}
+
+// dA[n][p][c] (+)= dgap[n][c] for every pixel: one 16-byte vector per thread, whole grid
+__global__ void __launch_bounds__(256) gap_bcast_kernel(const float* __restrict__ dgap, int HW, int Cp, int F,
+                                                        __nv_bfloat16* __restrict__ dA, int accumulate, int64_t total) {
+  const int cvec = Cp / 8;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+    const int v = static_cast<int>(i % cvec);
+    const int64_t n = i / (static_cast<int64_t>(cvec) * HW);
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = (v * 8 + k) < F ? dgap[n * F + v * 8 + k] : 0.f;
+    uint4* dst = reinterpret_cast<uint4*>(dA + i * 8);
+    if (accumulate) {
+      const uint4 q = *dst;
+      const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16x2(qq[k]);
+        o[2 * k] += f.x;
+        o[2 * k + 1] += f.y;
+      }
     }
+    uint4 r;
+    r.x = pack_bf16x2(o[0], o[1]); r.y = pack_bf16x2(o[2], o[3]); r.z = pack_bf16x2(o[4], o[5]); r.w = pack_bf16x2(o[6], o[7]);
+    *dst = r;
   }
 }
 // dw1[j][c] += sum_n dh[n][j]*gap[n][c] ; db1[j] += sum_n dh[n][j]
@@ -543,20 +585,29 @@ int mtbc_dshead_decompose(const float* dwc, const float* dbc, const float* wt, c
 int mtbc_gap_fc_fwd(const void* a, int32_t N, int32_t HW, int32_t Cp, int32_t F, const float* w1, const float* b1,
                     int32_t Hd, const float* w2, const float* b2, int32_t K, float* gap, float* hidden, float* logits,
                     void* stream) {
-  gap_fc_fwd_kernel<<<N, 256, (F + Hd) * sizeof(float), ST(stream)>>>(CBF(a), HW, Cp, F, w1, b1, Hd, w2, b2, K, gap,
-                                                                      hidden, logits);
+  if (Cp % 8 != 0 || F > Cp) return set_error(MTBC_ERR_INVALID, "gap_fc_fwd: Cp %% 8 != 0 or F > Cp");
+  gap_kernel<<<dim3(N, cdiv(Cp, 64)), 256, 0, ST(stream)>>>(CBF(a), HW, Cp, F, gap);
+  int rc = check_launch("gap");
+  if (rc) return rc;
+  fc_fwd_kernel<<<N, 256, (F + Hd) * sizeof(float), ST(stream)>>>(gap, F, w1, b1, Hd, w2, b2, K, hidden, logits);
   return check_launch("gap_fc_fwd");
 }
 int mtbc_gap_fc_bwd(const float* dlogits, int32_t N, int32_t HW, int32_t Cp, int32_t F, const float* w1, int32_t Hd,
                     const float* w2, int32_t K, const float* gap, float* hidden, void* dA, int32_t accumulate,
-                    float* dw1, float* db1, float* dw2, float* db2, void* stream) {
-  gap_fc_bwd_sample_kernel<<<N, 256, (Hd + K) * sizeof(float), ST(stream)>>>(dlogits, HW, Cp, F, w1, Hd, w2, K, hidden,
-                                                                             BF(dA), accumulate, dw2, db2);
+                    float* dw1, float* db1, float* dw2, float* db2, float* dgap, void* stream) {
+  if (!dgap) return set_error(MTBC_ERR_INVALID, "gap_fc_bwd: dgap scratch [N][F] is required");
+  gap_fc_bwd_sample_kernel<<<N, 256, (Hd + K) * sizeof(float), ST(stream)>>>(dlogits, HW, F, w1, Hd, w2, K, hidden,
+                                                                             dgap, dw2, db2);
   int rc = check_launch("gap_fc_bwd_sample");
   if (rc) return rc;
   int g = cdiv(static_cast<int64_t>(Hd) * F, 256); if (g > 148 * 4) g = 148 * 4;
   fc1_wgrad_kernel<<<g, 256, 0, ST(stream)>>>(hidden, gap, N, Hd, F, dw1, db1);
-  return check_launch("fc1_wgrad");
+  rc = check_launch("fc1_wgrad");
+  if (rc) return rc;
+  const int64_t total = static_cast<int64_t>(N) * HW * (Cp / 8);
+  int gb = cdiv(total, 256); if (gb > 148 * 8) gb = 148 * 8;
+  gap_bcast_kernel<<<gb, 256, 0, ST(stream)>>>(dgap, HW, Cp, F, BF(dA), accumulate, total);
+  return check_launch("gap_bcast");
 }
 
 int mtbc_flat_fc_fwd(const void* a, int32_t N, int32_t HW, int32_t Cp, int32_t C, const float* w1, const float* b1,

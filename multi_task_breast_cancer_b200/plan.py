@@ -520,6 +520,7 @@ class Plan:
         hid = torch.zeros(f.N, Hd, dtype=torch.float32, device=self.device)
         logits = torch.zeros(f.N, K, dtype=torch.float32, device=self.device)
         dlog = torch.zeros_like(logits)
+        dgap = torch.zeros_like(gap)
         self.fwd.append(_mk("mtbc_gap_fc_fwd", ptr(f.t), f.N, f.H * f.W, f.Cp, Fdim, ptr(self.P(w1)), ptr(self.P(b1)),
                             Hd, ptr(self.P(w2)), ptr(self.P(b2)), K, ptr(gap), ptr(hid), ptr(logits)))
         self.outputs_cls.append(logits)
@@ -529,7 +530,7 @@ class Plan:
             g = a.grad()
             blk = [_mk("mtbc_gap_fc_bwd", ptr(dlog), f.N, f.H * f.W, f.Cp, Fdim, ptr(self.P(w1)), Hd, ptr(self.P(w2)),
                        K, ptr(gap), ptr(hid), ptr(g.t), int(a.g_init), ptr(self.grad_view[w1]), ptr(self.grad_view[b1]),
-                       ptr(self.grad_view[w2]), ptr(self.grad_view[b2]))]
+                       ptr(self.grad_view[w2]), ptr(self.grad_view[b2]), ptr(dgap))]
             a.g_init = True
             self._mark_grad(w1, b1, w2, b2)
             return blk

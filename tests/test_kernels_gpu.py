@@ -102,6 +102,11 @@ def test_instance_norm_lrelu_pool(D, args, monkeypatch):
     _run(D, D.norm_case, *args)
 
 
+@pytest.mark.parametrize("args", [(24, [24]), (24, [24, 24, 48]), (48, [48, 96]), (100, [70, 33]), (512, [384, 384, 384])])
+def test_param_jobs_tiled_pack_unpack(D, args):
+    _run(D, D.param_jobs_case, *args)
+
+
 @pytest.mark.parametrize("args", [(2, 16, 16, 48), (3, 128, 128, 48), (3, 64, 64, 96)])
 def test_channel_sum(D, args):
     _run(D, D.chansum_case, *args)
@@ -117,8 +122,9 @@ def test_composed_deep_supervision_head(D, args):
     _run(D, D.dshead_case, *args)
 
 
-def test_gap_fc_head(D):
-    _run(D, D.gap_fc_case, 3, 4, 4, 512)
+@pytest.mark.parametrize("args", [(3, 4, 4, 512), (5, 16, 16, 512), (2, 8, 8, 320)])
+def test_gap_fc_head(D, args):
+    _run(D, D.gap_fc_case, *args)
 
 
 def test_flatten_fc_head(D):

@@ -334,6 +334,52 @@ def norm_case(N, H, W, C, affine, pool, slope=0.1):
     run_case(fn, name)
 
 
+def param_jobs_case(Cout, src_C):
+    """Batched parameter jobs (one launch: tiled weight pack + weight-gradient unpack) vs the stand-alone kernels."""
+    name = f"param_jobs Cout{Cout} src{src_C}"
+
+    def fn():
+        import ctypes as C
+        from multi_task_breast_cancer_b200 import plan as P
+        Cin = sum(src_C)
+        w = rnd(Cout, Cin, 3, 3, scale=0.5)
+        cks = [ops.pad32(c) for c in src_C]
+        offs, o = [], 0
+        for ck in cks:
+            a = 64 if ck % 64 == 0 else 32
+            o = (o + a - 1) // a * a
+            offs.append(o); o += ck
+        ktot, Ck = o, ops.pad32(Cout)
+        wf_ref = torch.zeros(9, Ck, ktot, dtype=torch.bfloat16, device=dev)
+        wd_ref = [torch.zeros(9, ck, Ck, dtype=torch.bfloat16, device=dev) for ck in cks]
+        ops.pack_conv_weight(w, src_C, offs, wf_ref, wd_ref)
+        wf = torch.zeros_like(wf_ref)
+        wd = [torch.zeros_like(t) for t in wd_ref]
+        jt = P.JobTable()
+        c0 = 0
+        for cs, off, d in zip(src_C, offs, wd):
+            jt.add(_lib.JOB_PACK_CONV, [Cout, Cin, 3, c0, cs, wf.shape[1], wf.shape[2], off, d.shape[1], d.shape[2]], w, wf, d)
+            c0 += cs
+        acc = rnd(9, Ck, ktot)
+        grad_ref = torch.full((Cout, Cin, 3, 3), 0.25, device=dev)
+        grad = grad_ref.clone()
+        c0 = 0
+        for cs, off in zip(src_C, offs):
+            _lib.call("mtbc_unpack_conv_wgrad", ops.ptr(acc), Ck, ktot, off, ops.ptr(grad_ref), Cout, Cin, 3, c0, cs, 1, None)
+            jt.add(_lib.JOB_UNPACK_CONV, [Ck, ktot, off, Cout, Cin, 3, c0, cs, 1], acc, grad)
+            c0 += cs
+        st = C.c_void_p(ops.stream_ptr())
+        for l in jt.launch():
+            l(st)
+        torch.cuda.synchronize()
+        report(name + " wf", wf, wf_ref, tol=1e-6)
+        for i, (a, b) in enumerate(zip(wd, wd_ref)):
+            report(name + f" wd[{i}]", a, b, tol=1e-6)
+        report(name + " unpack(add)", grad, grad_ref, tol=1e-6)
+
+    run_case(fn, name)
+
+
 def chansum_case(N, H, W, C):
     """Per-channel sum over all pixels (bias gradient of the transposed convolutions)."""
     name = f"channel_sum N{N} {H}x{W} C{C}"
@@ -426,7 +472,8 @@ def gap_fc_case(N, H, W, Fd, Hd=256, K=3):
         dA = Feat.empty(N, H, W, Fd)
         g = [torch.zeros_like(t) for t in (w1, b1, w2, b2)]
         _lib.call("mtbc_gap_fc_bwd", ops.ptr(dl), N, H * W, af.Cp, Fd, ops.ptr(w1), Hd, ops.ptr(w2), K, ops.ptr(gap),
-                  ops.ptr(hid), ops.ptr(dA.t), 0, ops.ptr(g[0]), ops.ptr(g[1]), ops.ptr(g[2]), ops.ptr(g[3]), None)
+                  ops.ptr(hid), ops.ptr(dA.t), 0, ops.ptr(g[0]), ops.ptr(g[1]), ops.ptr(g[2]), ops.ptr(g[3]),
+                  ops.ptr(torch.zeros(N, Fd, device=dev)), None)
         report(name + " dA", dA.to_nchw(), ps[0].grad, tol=1e-2)
         for nm, mine, r in zip(("dw1", "db1", "dw2", "db2"), g, ps[1:]):
             report(name + " " + nm, mine, r.grad, tol=2e-4)
