@@ -44,6 +44,8 @@ struct ConvHaloParams {
   int32_t nsrc, nouts;
   int32_t W, H, N, tiles_w, tiles_h, n_mtiles;
   int32_t BN, tmem_cols, stages, a_stage_bytes, b_tap_bytes, b_total_bytes;
+  int32_t dbg;            // debug (MTBC_HALO_DBG=1): accumulate the MMA lane's cycle breakdown into g_halo_dbg
+  int32_t late_release;   // debug (MTBC_HALO_LATE_RELEASE=1): hand the accumulator back after the stores, not before
   int32_t G, bn1;   // G = output rows stacked along N (1 or 2); bn1 = columns per output pixel; BN = G * bn1
   int32_t stat_C;
   const float* bias;
@@ -52,6 +54,10 @@ struct ConvHaloParams {
 };
 
 constexpr int kHaloMaxStages = 8;
+
+// Debug (MTBC_HALO_DBG=1): where CTA 0's MMA lane spends its cycles: [0] wait accumulator, [1] wait halo data,
+// [2] issuing MMAs, [3] commits, [4] tiles, [5] chunks, [6] total.  Read with mtbc_debug_halo_times().
+__device__ long long g_halo_dbg[8];
 
 // The 9 taps x KC/16 K-steps of one halo chunk, fully unrolled: only the low descriptor words change, by compile-time
 // (A) or per-kernel (B tap plane) offsets, so the single issuing lane stays at the tensor pipe's ~45-cycle
@@ -80,30 +86,35 @@ __device__ __forceinline__ void halo_issue_chunk(uint32_t d_addr, uint32_t a_lo,
 // single N = 2*bn1 instructions: 12 instructions per K step and 256 pixels instead of 18.  The resident weights are
 // stored [dw][dh descending][bn1 x KC] so the N = 2*bn1 operand is just a window over two neighbouring tap blocks:
 // input row dh' feeds tap dh' of the upper pixel and tap dh'-1 of the lower one.
-template <int KC>
+template <int KC, int BN1>
 __device__ __forceinline__ void halo_issue_chunk_g2(uint32_t d_addr, uint32_t a_lo, uint32_t b_lo, uint32_t b_dw16,
-                                                    uint32_t b_blk16, uint32_t bn1, uint32_t idesc1, uint32_t idesc2,
-                                                    uint32_t accumulate) {
+                                                    uint32_t idesc1, uint32_t idesc2, uint32_t accumulate) {
   constexpr uint32_t rowb = KC * 2u;
   constexpr uint32_t layout = KC == 64 ? 2u : 4u;
+  constexpr uint32_t blk16 = BN1 * KC * 2u / 16u;   // one tap block of the resident weights, in 16-byte units
   const uint32_t a_hi = umma_desc_hi(2 * kHaloW * rowb, layout);   // 8-row group stride = two halo rows
   const uint32_t b_hi = umma_desc_hi(8u * rowb, layout);
+  // The single issuing lane is also bound by its scalar instruction stream (every operand must reach a uniform
+  // register): all offsets except the dw plane are compile-time constants, like in halo_issue_chunk.
+  // All N = BN1 instructions first, then all N = 2*BN1 ones (they also initialise the two column halves).
 #pragma unroll
-  for (int dw = 0; dw < 3; ++dw) {
-    const uint32_t b_w = b_lo + dw * b_dw16;   // blocks of this dw: [dh=2][dh=1][dh=0]
-    // order: the two N = bn1 instructions first so that each column half is initialised by its own instruction
+  for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
-    for (int step = 0; step < 4; ++step) {
-      const int dhp = step == 0 ? 3 : (step == 1 ? 0 : step - 1);   // 3, 0, 1, 2
-      const uint32_t a_t = a_lo + ((dhp * kHaloW + dw) * rowb >> 4);
-      // dhp = 0: block dh=0 -> upper half; 3: block dh=2 -> lower half; 1: blocks [dh=1, dh=0]; 2: blocks [dh=2, dh=1]
-      const uint32_t b_t = b_w + (dhp == 0 ? 2 * b_blk16 : (dhp == 1 ? b_blk16 : 0u));
-      const uint32_t d_t = d_addr + (dhp == 3 ? bn1 : 0u);
-      const uint32_t idesc = (dhp == 0 || dhp == 3) ? idesc1 : idesc2;
+    for (int dw = 0; dw < 3; ++dw) {
+      const uint32_t b_w = b_lo + dw * b_dw16;   // blocks of this dw: [dh=2][dh=1][dh=0]
 #pragma unroll
-      for (int k = 0; k < KC / 16; ++k) {
-        const uint32_t acc = (dw == 0 && (dhp == 3 || dhp == 0) && k == 0) ? accumulate : 1u;
-        umma_bf16_lohi(d_t, a_t + 2 * k, a_hi, b_t + 2 * k, b_hi, idesc, acc);
+      for (int step = 0; step < 2; ++step) {
+        const int dhp = pass == 0 ? (step == 0 ? 3 : 0) : (step + 1);   // pass 0: 3, 0;  pass 1: 1, 2
+        const uint32_t a_t = a_lo + ((dhp * kHaloW + dw) * rowb >> 4);
+        // dhp = 0: block dh=0 -> upper half; 3: block dh=2 -> lower half; 1: blocks [dh=1, dh=0]; 2: blocks [dh=2, dh=1]
+        const uint32_t b_t = b_w + (dhp == 0 ? 2 * blk16 : (dhp == 1 ? blk16 : 0u));
+        const uint32_t d_t = d_addr + (dhp == 3 ? BN1 : 0);
+        const uint32_t idesc = pass == 0 ? idesc1 : idesc2;
+#pragma unroll
+        for (int k = 0; k < KC / 16; ++k) {
+          const uint32_t acc = (pass == 0 && dw == 0 && k == 0) ? accumulate : 1u;
+          umma_bf16_lohi(d_t, a_t + 2 * k, a_hi, b_t + 2 * k, b_hi, idesc, acc);
+        }
       }
     }
   }
@@ -128,22 +139,24 @@ struct HaloChunk {
 
 template <int V> struct IntC { static constexpr int value = V; };
 
-constexpr int kEpiWarps = 8;
-constexpr int kEpiThreads = kEpiWarps * 32;
-
-template <int RACC>
+// P = column parts per TMEM lane quarter: 4 * P epilogue warps.  P = 2 everywhere except the 64-column G = 2 layers,
+// whose epilogue is a per-warp dependent chain (TMEM load -> statistics -> pack -> store, ~2600 cycles per tile
+// against ~1100 cycles of MMAs, profiles/r01f): with P = 4 every warp owns one 16-column chunk and the chain halves.
+template <int RACC, int P>
 __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t tmem_base, int t_begin, int t_end,
                                               int ntile, int warp, int lane, const float* s_bias,
                                               float (*s_part)[2][256], const HaloChunk* s_chunk,
                                               uint64_t* s_accfull, uint64_t* s_accempty) {
+  constexpr int kEpiWarps = 4 * P;
+  constexpr int kEpiThreads = kEpiWarps * 32;
   const int q = warp & 3;                  // TMEM lane quarter this warp may read
-  const int half = (warp - 2) >> 2;        // column half
+  const int part = (warp - 2) >> 2;        // column part
   const int row = q * 32 + lane;
   const int tw = row & 7, th = row >> 3;
   const int BN = p.BN;
   const int nchunks = BN >> 4;
-  const int k_begin = half ? (nchunks + 1) >> 1 : 0;
-  const int k_end = half ? nchunks : (nchunks + 1) >> 1;
+  const int k_begin = (nchunks * part + P - 1) / P;
+  const int k_end = (nchunks * (part + 1) + P - 1) / P;
   const bool do_stats = (p.stat_sum != nullptr);
   const bool has_bias = (p.bias != nullptr);
   const int etid = (warp - 2) * 32 + lane;
@@ -152,7 +165,7 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
   const int G = p.G, bn1 = p.bn1;
   float* const stat_sum = p.stat_sum;
   float* const stat_sq = p.stat_sq;
-  constexpr int NR = RACC > 0 ? RACC / 2 : 1;   // columns of this warp's half
+  constexpr int NR = RACC > 0 ? RACC / P : 1;   // columns of this warp's part
   float rs[NR], rq[NR];
 #pragma unroll
   for (int i = 0; i < NR; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
@@ -160,14 +173,14 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
 
   // combine the 4 quarters' column partials and add them to the per-(n, channel) statistics
   auto flush_cols = [&](int n) {
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
     for (int i = etid; i < BN; i += kEpiThreads) {
       if (ntile * bn1 + (i % bn1) >= stat_C) continue;   // GEMM pad column of a dense tensor: no such channel
       const int64_t o = static_cast<int64_t>(n) * stat_C + ntile * bn1 + (i % bn1);   // G = 2: both rows -> one channel
       atomicAdd(stat_sum + o, s_part[0][0][i] + s_part[1][0][i] + s_part[2][0][i] + s_part[3][0][i]);
       atomicAdd(stat_sq + o, s_part[0][1][i] + s_part[1][1][i] + s_part[2][1][i] + s_part[3][1][i]);
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
   };
   auto flush_regs = [&](int n) {
     if constexpr (RACC > 0) {
@@ -189,7 +202,7 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
   };
 
   // one 16-column chunk: bias, statistics, bf16 store / accumulate
-  auto do_chunk = [&](int k, auto jc, uint32_t (&r)[16], int64_t pix) {
+  auto do_chunk = [&](int k, auto jc, uint32_t (&r)[16], int64_t pix, const HaloChunk& hc) {
     constexpr int J = decltype(jc)::value;   // position of the chunk inside this warp's half (RACC > 0 only)
     float v[16];
 #pragma unroll
@@ -217,32 +230,51 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
         s_part[q][1][cc] = cq;
       }
     }
-    const HaloChunk hc = s_chunk[k];
     emit_bf16x16_n(hc.base + pix * hc.out_C, v, hc.accumulate != 0, hc.nvalid, hc.wide != 0);
   };
 
+  // tile coordinates advance incrementally (the 8 epilogue warps are the critical path of the narrow layers: two
+  // integer divisions per tile were ~25 % of their instructions)
+  int n = t_begin < t_end ? t_begin / tiles_per_n : 0;
+  int tr, tc;
+  {
+    const int rem = t_begin - n * tiles_per_n;
+    tr = rem / tiles_w;
+    tc = rem - tr * tiles_w;
+  }
+  // statistics path: this warp's one or two chunk descriptors live in registers
+  HaloChunk hc0 = s_chunk[k_begin], hc1 = s_chunk[(NR > 16) ? k_begin + 1 : k_begin];
   int it = 0;
   for (int t = t_begin; t < t_end; ++t, ++it) {
     const int buf = it & 1;
     const uint32_t acc_phase = (it >> 1) & 1;
-    const int n = t / tiles_per_n;
-    const int rem = t - n * tiles_per_n;
-    const int tr = rem / tiles_w;
-    const int w = (rem - tr * tiles_w) * 8 + tw;
+    const int w = tc * 8 + tw;
     const int h = (tr * 16 + th) * G;   // G = 2: row of the upper pixel; the lower one is folded into s_chunk[k].base
     if (RACC > 0 && n != cur_n) { flush_regs(cur_n); cur_n = n; }
     const int64_t pix = (static_cast<int64_t>(n) * H + h) * W + w;
     mbar_wait(&s_accfull[buf], acc_phase);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
+    if (p.dbg & 8) {   // debug: epilogue releases the accumulator without reading it
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_accempty[buf]);
+      if (++tc == tiles_w) { tc = 0; if (++tr == p.tiles_h) { tr = 0; ++n; } }
+      continue;
+    }
     if constexpr (RACC > 0) {
       // this warp's half is NR / 16 = 1 or 2 chunks, known at compile time: statistics stay in registers
       uint32_t r[NR / 16][16];
       tmem_ld16_nowait(taddr + k_begin * 16, r[0]);
       if constexpr (NR > 16) tmem_ld16_nowait(taddr + k_begin * 16 + 16, r[1]);
       tmem_wait_ld();
-      do_chunk(k_begin, IntC<0>{}, r[0], pix);
-      if constexpr (NR > 16) do_chunk(k_begin + 1, IntC<1>{}, r[1], pix);
+      // the accumulator is in registers: hand it back to the MMA warp before the math and the stores
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0 && !p.late_release) mbar_arrive(&s_accempty[buf]);
+      do_chunk(k_begin, IntC<0>{}, r[0], pix, hc0);
+      if constexpr (NR > 16) do_chunk(k_begin + 1, IntC<1>{}, r[1], pix, hc1);
+      if (p.late_release) { __syncwarp(); if (lane == 0) mbar_arrive(&s_accempty[buf]); }
     } else {
 #pragma unroll 1
       for (int k = k_begin; k < k_end; k += 2) {
@@ -251,24 +283,33 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
         tmem_ld16_nowait(taddr + k * 16, r[0]);
         if (two) tmem_ld16_nowait(taddr + k * 16 + 16, r[1]);
         tmem_wait_ld();
+        if (k + 2 >= k_end && !p.late_release) {   // last loads of this tile are in registers: release the accumulator
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_accempty[buf]);
+        }
 #pragma unroll
         for (int u = 0; u < 2; ++u)
-          if (u == 0 || two) do_chunk(k + u, IntC<0>{}, r[u], pix);
+          if (u == 0 || two) do_chunk(k + u, IntC<0>{}, r[u], pix, s_chunk[k + u]);
       }
+      if (k_begin >= k_end || p.late_release) {   // (no chunk for this warp: still one arrival per warp and tile)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_accempty[buf]);
+      }
+      if (do_stats) flush_cols(n);
     }
-    // accumulator fully read: hand it back to the MMA warp
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&s_accempty[buf]);
-    if (RACC == 0 && do_stats) flush_cols(n);
+    if (++tc == tiles_w) { tc = 0; if (++tr == p.tiles_h) { tr = 0; ++n; } }
   }
   if (RACC > 0 && t_begin < t_end) flush_regs(cur_n);
 }
 
 // MINB = resident CTAs per SM the register budget is compiled for: 2 for the narrow layers (small resident weights, two
 // CTAs overlap each other's pipeline bubbles), 1 for wide N tiles (no spills, one CTA owns the SM).
-template <int MINB>
-__global__ void __launch_bounds__(64 + kEpiThreads, MINB) conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
+template <int MINB, int P>
+__global__ void __launch_bounds__(64 + 128 * P, MINB) conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
+  constexpr int kEpiWarps = 4 * P;
+  constexpr int kEpiThreads = kEpiWarps * 32;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t s_afull[kHaloMaxStages], s_aempty[kHaloMaxStages];
   __shared__ uint64_t s_bfull, s_accfull[2], s_accempty[2];
@@ -276,6 +317,7 @@ __global__ void __launch_bounds__(64 + kEpiThreads, MINB) conv_halo_kernel(const
   __shared__ __align__(16) float s_bias[256];
   __shared__ float s_part[4][2][256];  // [lane quarter][sum|sumsq][col]: per-warp column partials at a flush
   __shared__ HaloChunk s_chunk[16];    // destination of every 16-column chunk of this CTA's N tile
+  __shared__ uint32_t s_cb[64];        // MMA lane's chunk schedule: weight-block descriptor (low word) | 64-wide flag
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -346,8 +388,11 @@ __global__ void __launch_bounds__(64 + kEpiThreads, MINB) conv_halo_kernel(const
           const uint32_t bytes = static_cast<uint32_t>(kHaloW * (16 * p.G + 2) * sc.kc * 2);
           for (int ch = 0; ch < sc.nchunk; ++ch) {
             mbar_wait(&s_aempty[stage], phase ^ 1u);
-            mbar_arrive_expect_tx(&s_afull[stage], bytes);
-            tma_load_4d(smem_a + stage * p.a_stage_bytes, &p.amap[s], &s_afull[stage], ch * sc.kc, w0 - 1, h0 - 1, n);
+            if ((p.dbg & 4) && t > t_begin) { mbar_arrive(&s_afull[stage]); }   // debug: no TMA traffic after tile 0
+            else {
+              mbar_arrive_expect_tx(&s_afull[stage], bytes);
+              tma_load_4d(smem_a + stage * p.a_stage_bytes, &p.amap[s], &s_afull[stage], ch * sc.kc, w0 - 1, h0 - 1, n);
+            }
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -356,50 +401,86 @@ __global__ void __launch_bounds__(64 + kEpiThreads, MINB) conv_halo_kernel(const
   } else if (warp == 1) {
     if (elect_one()) {
       // ------------------------------------------------------------ MMA issuer
+      // This single lane is the critical path of the narrow layers: the tensor pipe only queues a few instructions,
+      // so every scalar instruction between two MMAs is pipe idle time (tools/diag_halo_dbg.py).  The per-tile chunk
+      // schedule is therefore a flat table in shared memory (weight-block descriptor + chunk width per chunk) built
+      // once, the ring slot address advances by one add, and parameters live in registers.
       const uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
       const uint32_t idesc1 = umma_idesc_bf16(128, bn1, 0, 0);
-      mbar_wait(&s_bfull, 0);
       const uint32_t b_tap16 = static_cast<uint32_t>(p.b_tap_bytes) >> 4;
       const bool g2 = p.G == 2;
+      int nch = 0;
+      for (int s = 0; s < p.nsrc; ++s) {
+        const HaloSrc sc = p.src[s];
+        const uint32_t blk = static_cast<uint32_t>(bn1 * sc.kc * 2);
+        for (int ch = 0; ch < sc.nchunk; ++ch, ++nch) {
+          const uint32_t off = g2 ? 3 * (sc.b_off + ch * blk) : (sc.b_off + ch * blk);
+          s_cb[nch] = umma_desc_lo(smem_u32(smem_b) + off, 16) | (sc.kc == 64 ? 0x80000000u : 0u);   // bit 31: 64-wide
+        }
+      }
+      mbar_wait(&s_bfull, 0);
+      const int nstages = p.stages;
+      const uint32_t a_step16 = static_cast<uint32_t>(p.a_stage_bytes) >> 4;
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem_a), 16);
+      uint32_t a_lo = a_lo0;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      const bool dbg = (p.dbg & 1) && blockIdx.x == 0 && blockIdx.y == 0;
+      const bool no_mma = (p.dbg & 2) != 0;
+      long long c_acc = 0, c_data = 0, c_issue = 0, c_commit = 0, n_chunks = 0;
+      const long long c_start = dbg ? clock64() : 0;
       for (int t = t_begin; t < t_end; ++t, ++it) {
         const int buf = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
+        long long t0 = dbg ? clock64() : 0;
         mbar_wait(&s_accempty[buf], acc_phase ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
+        if (dbg) { const long long t1 = clock64(); c_acc += t1 - t0; }
         const uint32_t d_addr = tmem_base + static_cast<uint32_t>(buf * BN);
         uint32_t accumulate = 0;
-        for (int s = 0; s < p.nsrc; ++s) {
-          const HaloSrc sc = p.src[s];
-          for (int ch = 0; ch < sc.nchunk; ++ch) {
-            mbar_wait(&s_afull[stage], phase);
-            tc_fence_after();
-            const uint32_t a_lo = umma_desc_lo(smem_u32(smem_a + stage * p.a_stage_bytes), 16);
-            const uint32_t blk = static_cast<uint32_t>(bn1 * sc.kc * 2);
-            if (g2) {
-              const uint32_t b_lo = umma_desc_lo(smem_u32(smem_b) + 3 * (sc.b_off + ch * blk), 16);
-              if (sc.kc == 64) halo_issue_chunk_g2<64>(d_addr, a_lo, b_lo, 3 * b_tap16, blk >> 4, bn1, idesc1, idesc, accumulate);
-              else halo_issue_chunk_g2<32>(d_addr, a_lo, b_lo, 3 * b_tap16, blk >> 4, bn1, idesc1, idesc, accumulate);
-            } else {
-              const uint32_t b_lo = umma_desc_lo(smem_u32(smem_b) + sc.b_off + ch * blk, 16);
-              if (sc.kc == 64) halo_issue_chunk<64>(d_addr, a_lo, b_lo, b_tap16, idesc, accumulate);
-              else halo_issue_chunk<32>(d_addr, a_lo, b_lo, b_tap16, idesc, accumulate);
-            }
-            accumulate = 1;
-            umma_commit(&s_aempty[stage]);
-            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+#pragma unroll 1
+        for (int c = 0; c < nch; ++c) {
+          if (dbg) t0 = clock64();
+          mbar_wait(&s_afull[stage], phase);   // TMA data: the mbarrier acquire is all the MMA needs
+          long long t1 = 0;
+          if (dbg) { t1 = clock64(); c_data += t1 - t0; }
+          const uint32_t cb = s_cb[c];
+          const uint32_t b_lo = cb & 0x7fffffffu;
+          if (no_mma) {
+            // debug: no MMAs
+          } else if (g2) {
+            if (cb >> 31) halo_issue_chunk_g2<64, 32>(d_addr, a_lo, b_lo, 3 * b_tap16, idesc1, idesc, accumulate);
+            else halo_issue_chunk_g2<32, 32>(d_addr, a_lo, b_lo, 3 * b_tap16, idesc1, idesc, accumulate);
+          } else {
+            if (cb >> 31) halo_issue_chunk<64>(d_addr, a_lo, b_lo, b_tap16, idesc, accumulate);
+            else halo_issue_chunk<32>(d_addr, a_lo, b_lo, b_tap16, idesc, accumulate);
           }
+          accumulate = 1;
+          long long t2 = 0;
+          if (dbg) { t2 = clock64(); c_issue += t2 - t1; }
+          umma_commit(&s_aempty[stage]);
+          if (dbg) { c_commit += clock64() - t2; ++n_chunks; }
+          a_lo += a_step16;
+          if (++stage == nstages) { stage = 0; phase ^= 1u; a_lo = a_lo0; }
         }
         umma_commit(&s_accfull[buf]);
+      }
+      if (dbg) {
+        g_halo_dbg[0] += c_acc; g_halo_dbg[1] += c_data; g_halo_dbg[2] += c_issue; g_halo_dbg[3] += c_commit;
+        g_halo_dbg[4] += it; g_halo_dbg[5] += n_chunks; g_halo_dbg[6] += clock64() - c_start;
       }
     }
   } else {
     // -------------------------------------------------------------- epilogue warps 2..9 (TMEM lane quarter = warp % 4)
-    if (p.stat_sum != nullptr && BN == 32) halo_epilogue<32>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_chunk, s_accfull, s_accempty);
-    else if (p.stat_sum != nullptr && BN == 64) halo_epilogue<64>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_chunk, s_accfull, s_accempty);
-    else halo_epilogue<0>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_chunk, s_accfull, s_accempty);
+    if constexpr (P == 2) {
+      if (p.stat_sum != nullptr && BN == 32) halo_epilogue<32, 2>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_chunk, s_accfull, s_accempty);
+      else if (p.stat_sum != nullptr && BN == 64) halo_epilogue<64, 2>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_chunk, s_accfull, s_accempty);
+      else halo_epilogue<0, 2>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_chunk, s_accfull, s_accempty);
+    } else {
+      if (p.stat_sum != nullptr && BN == 64) halo_epilogue<64, 4>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_chunk, s_accfull, s_accempty);
+      else halo_epilogue<0, 4>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_chunk, s_accfull, s_accempty);
+    }
   }
 
   tc_fence_before();
@@ -543,9 +624,11 @@ struct ConvHaloOp : public OpBase {
   int smem_bytes;
   double flops;
   int ctas_per_sm = 1;
+  int epi_parts = 2;
   int launch(cudaStream_t st) override {
-    if (ctas_per_sm == 2) conv_halo_kernel<2><<<grid, 64 + kEpiThreads, smem_bytes, st>>>(p);
-    else conv_halo_kernel<1><<<grid, 64 + kEpiThreads, smem_bytes, st>>>(p);
+    if (epi_parts == 4) conv_halo_kernel<1, 4><<<grid, 64 + 512, smem_bytes, st>>>(p);
+    else if (ctas_per_sm == 2) conv_halo_kernel<2, 2><<<grid, 64 + 256, smem_bytes, st>>>(p);
+    else conv_halo_kernel<1, 2><<<grid, 64 + 256, smem_bytes, st>>>(p);
     return check_launch("conv_halo_kernel");
   }
   double op_flops() const override { return flops; }
@@ -625,6 +708,8 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   memset(&p, 0, sizeof(p));
   p.nsrc = d->nviews;
   p.G = G; p.bn1 = BN;
+  { const char* lr = getenv("MTBC_HALO_LATE_RELEASE"); p.late_release = (lr && lr[0] == '1') ? 1 : 0; }
+  { const char* dg = getenv("MTBC_HALO_DBG"); p.dbg = dg ? atoi(dg) : 0; }
   const int halo_h = 16 * G + 2;
   int kcmax = 32, b_off = 0;
   bool use32 = false, use64 = false;
@@ -654,6 +739,7 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   p.a_stage_bytes = ((kHaloW * halo_h * kcmax * 2) + 1023) & ~1023;
   int total_chunks = 0;
   for (int v = 0; v < d->nviews; ++v) total_chunks += p.src[v].nchunk;
+  if (total_chunks > 64) { delete op; return 1; }   // chunk schedule table of the MMA lane (s_cb)
   int stages = (200 * 1024 - p.b_total_bytes) / p.a_stage_bytes;
   if (stages > kHaloMaxStages) stages = kHaloMaxStages;
   // with small resident weights keep the footprint below half an SM so two CTAs overlap each other's epilogues
@@ -678,6 +764,21 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
     op->smem_bytes = p.b_total_bytes + st1 * p.a_stage_bytes + 1024;
   }
   op->ctas_per_sm = ctas_per_sm;
+  {
+    const char* e_env = getenv("MTBC_HALO_EPI");
+    const bool want4 = (G == 2 && p.BN == 64) && !(e_env && e_env[0] == '2');
+    if (want4) {   // 16 epilogue warps, one CTA per SM (576 threads)
+      if (ctas_per_sm == 2) {
+        int st1 = (200 * 1024 - p.b_total_bytes) / p.a_stage_bytes;
+        if (st1 > kHaloMaxStages) st1 = kHaloMaxStages;
+        p.stages = st1;
+        op->smem_bytes = p.b_total_bytes + st1 * p.a_stage_bytes + 1024;
+        ctas_per_sm = 1;
+        op->ctas_per_sm = 1;
+      }
+      op->epi_parts = 4;
+    }
+  }
   int gx = sm_count() * ctas_per_sm;
   if (gx > p.n_mtiles) gx = p.n_mtiles;
   p.stat_C = d->stat_C;
@@ -696,8 +797,9 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   p.bias = d->bias; p.stat_sum = d->stat_sum; p.stat_sq = d->stat_sq;
   op->grid = dim3(gx, d->ncols / BN, 1);
   op->flops = 2.0 * double(d->N) * d->H * d->W * double(d->ncols) * kused * 9.0;
-  cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_halo_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_halo_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
   if (e != cudaSuccess) { delete op; return set_error(MTBC_ERR_CUDA, "cudaFuncSetAttribute(conv_halo): %s", cudaGetErrorString(e)); }
   *out = op;
   return 0;
@@ -757,3 +859,11 @@ int wgrad_halo_try_create(const mtbc_wgrad_desc* d, OpBase** out) {
 }
 
 }  // namespace mtbc
+
+// Debug helper (not part of the documented ABI surface used by the product path): copy / reset the cycle breakdown.
+extern "C" int mtbc_debug_halo_times(long long* out8, int reset) {
+  long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (out8 && cudaMemcpyFromSymbol(out8, mtbc::g_halo_dbg, sizeof(z)) != cudaSuccess) return -1;
+  if (reset && cudaMemcpyToSymbol(mtbc::g_halo_dbg, z, sizeof(z)) != cudaSuccess) return -1;
+  return 0;
+}

@@ -281,33 +281,40 @@ __global__ void __launch_bounds__(256) gap_kernel(const __nv_bfloat16* __restric
   }
 }
 
-// hidden = relu(W1 gap + b1), logits = W2 hidden + b2; one block per sample
-__global__ void __launch_bounds__(256) fc_fwd_kernel(const float* __restrict__ gap, int F, const float* __restrict__ w1,
-                                                     const float* __restrict__ b1, int Hd, const float* __restrict__ w2,
-                                                     const float* __restrict__ b2, int K, float* __restrict__ hidden,
-                                                     float* __restrict__ logits) {
-  extern __shared__ float sm[];
-  float* s_gap = sm;       // [F]
-  float* s_h = sm + F;     // [Hd]
+// hidden[n][j] = relu(W1[j] . gap[n] + b1[j]).  grid (N, ceil(Hd / 32)): 8 warps x 4 rows per block, 128-bit loads with
+// all of a row's loads in flight (one block per sample with a row loop per warp was a 180 us chain of dependent loads).
+__global__ void __launch_bounds__(256) fc1_fwd_kernel(const float* __restrict__ gap, int F, const float* __restrict__ w1,
+                                                      const float* __restrict__ b1, int Hd, float* __restrict__ hidden) {
+  extern __shared__ __align__(16) float s_gap[];   // [F]
   const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int c = threadIdx.x; c < F; c += 256) s_gap[c] = gap[static_cast<int64_t>(n) * F + c];
   __syncthreads();
-  for (int j = warp; j < Hd; j += 8) {
-    const float* wr = w1 + static_cast<int64_t>(j) * F;
+  const int F4 = F >> 2;   // F % 4 == 0 is checked by the host
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int j = blockIdx.y * 32 + warp * 4 + r;
+    if (j >= Hd) break;
+    const float4* wr = reinterpret_cast<const float4*>(w1 + static_cast<int64_t>(j) * F);
     float s = 0.f;
-    for (int c = lane; c < F; c += 32) s = fmaf(wr[c], s_gap[c], s);
-    s = warp_sum(s);
-    if (lane == 0) {
-      s = fmaxf(s + b1[j], 0.f);
-      s_h[j] = s;
-      hidden[static_cast<int64_t>(n) * Hd + j] = s;
+#pragma unroll 4
+    for (int c = lane; c < F4; c += 32) {
+      const float4 wv = __ldg(wr + c);
+      const float4 gv = *reinterpret_cast<const float4*>(s_gap + 4 * c);
+      s = fmaf(wv.x, gv.x, s); s = fmaf(wv.y, gv.y, s); s = fmaf(wv.z, gv.z, s); s = fmaf(wv.w, gv.w, s);
     }
+    s = warp_sum(s);
+    if (lane == 0) hidden[static_cast<int64_t>(n) * Hd + j] = fmaxf(s + b1[j], 0.f);
   }
-  __syncthreads();
+}
+// logits[n][k] = W2[k] . hidden[n] + b2[k]; one block per sample
+__global__ void __launch_bounds__(256) fc2_fwd_kernel(const float* __restrict__ hidden, int Hd,
+                                                      const float* __restrict__ w2, const float* __restrict__ b2, int K,
+                                                      float* __restrict__ logits) {
+  const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int k = warp; k < K; k += 8) {
     const float* wr = w2 + static_cast<int64_t>(k) * Hd;
     float s = 0.f;
-    for (int j = lane; j < Hd; j += 32) s = fmaf(wr[j], s_h[j], s);
+    for (int j = lane; j < Hd; j += 32) s = fmaf(wr[j], hidden[static_cast<int64_t>(n) * Hd + j], s);
     s = warp_sum(s);
     if (lane == 0) logits[static_cast<int64_t>(n) * K + k] = s + b2[k];
   }
@@ -589,7 +596,11 @@ int mtbc_gap_fc_fwd(const void* a, int32_t N, int32_t HW, int32_t Cp, int32_t F,
   gap_kernel<<<dim3(N, cdiv(Cp, 64)), 256, 0, ST(stream)>>>(CBF(a), HW, Cp, F, gap);
   int rc = check_launch("gap");
   if (rc) return rc;
-  fc_fwd_kernel<<<N, 256, (F + Hd) * sizeof(float), ST(stream)>>>(gap, F, w1, b1, Hd, w2, b2, K, hidden, logits);
+  if (F % 4 != 0) return set_error(MTBC_ERR_INVALID, "gap_fc_fwd: F %% 4 != 0");
+  fc1_fwd_kernel<<<dim3(N, cdiv(Hd, 32)), 256, F * sizeof(float), ST(stream)>>>(gap, F, w1, b1, Hd, hidden);
+  rc = check_launch("fc1_fwd");
+  if (rc) return rc;
+  fc2_fwd_kernel<<<N, 256, 0, ST(stream)>>>(hidden, Hd, w2, b2, K, logits);
   return check_launch("gap_fc_fwd");
 }
 int mtbc_gap_fc_bwd(const float* dlogits, int32_t N, int32_t HW, int32_t Cp, int32_t F, const float* w1, int32_t Hd,

@@ -258,12 +258,17 @@ int param_jobs_create(const mtbc_param_job* jobs, int n, OpBase** out) {
 // ------------------------------------------------------------------------------------------------ first layer
 // xs[n][ci][r*3+s] = sum over output pixels (h,w) of x[n,ci,h+r-1,w+s-1] (zero padded): the nine shifted plane sums
 // from which the per-(n,channel) mean of the conv output follows linearly.  grid = N*Cin blocks of 256 threads.
+// Two steps: (1) grid (planes, slices): each block adds its slice's five partial sums (total, first / last row,
+// first / last column) into xs[plane][0..4] (zeroed by the caller); (2) one thread per plane turns them into the nine
+// shifted sums in place.  (One block per plane was a 57 us launch for 32 planes of 256 x 256.)
 __global__ void __launch_bounds__(256) conv_first_shift_sums_kernel(const float* __restrict__ x, int H, int W,
                                                                     float* __restrict__ xs) {
   const float* plane = x + static_cast<int64_t>(blockIdx.x) * H * W;
-  // total, first/last row, first/last column, four corners
+  const int HW = H * W;
+  const int per = (HW + gridDim.y - 1) / gridDim.y;
+  const int i0 = blockIdx.y * per, i1 = min(HW, i0 + per);
   float tot = 0.f, r0 = 0.f, rl = 0.f, c0 = 0.f, cl = 0.f;
-  for (int i = threadIdx.x; i < H * W; i += 256) {
+  for (int i = i0 + threadIdx.x; i < i1; i += 256) {
     const float v = plane[i];
     const int h = i / W, w = i - h * W;
     tot += v;
@@ -281,25 +286,34 @@ __global__ void __launch_bounds__(256) conv_first_shift_sums_kernel(const float*
     if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float t[5];
-    for (int k = 0; k < 5; ++k) { t[k] = 0.f; for (int j = 0; j < 8; ++j) t[k] += red[k][j]; }
-    const float x00 = plane[0], x0l = plane[W - 1], xl0 = plane[(H - 1) * W], xll = plane[(H - 1) * W + W - 1];
-    // tap (r,s) reads x[h+r-1][w+s-1]: r=0 never touches the last row, r=2 never the first; same for columns
-    for (int r = 0; r < 3; ++r)
-      for (int s = 0; s < 3; ++s) {
-        float v = t[0];
-        if (r == 0) v -= t[2];
-        if (r == 2) v -= t[1];
-        if (s == 0) v -= t[4];
-        if (s == 2) v -= t[3];
-        if (r == 0 && s == 0) v += xll;
-        if (r == 0 && s == 2) v += xl0;
-        if (r == 2 && s == 0) v += x0l;
-        if (r == 2 && s == 2) v += x00;
-        xs[blockIdx.x * 9 + r * 3 + s] = v;
-      }
+  if (threadIdx.x < 5) {
+    float t = 0.f;
+    for (int j = 0; j < 8; ++j) t += red[threadIdx.x][j];
+    atomicAdd(xs + blockIdx.x * 9 + threadIdx.x, t);
   }
+}
+__global__ void conv_first_shift_finish_kernel(const float* __restrict__ x, int H, int W, int planes,
+                                               float* __restrict__ xs) {
+  const int pl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pl >= planes) return;
+  const float* plane = x + static_cast<int64_t>(pl) * H * W;
+  float t[5];
+  for (int k = 0; k < 5; ++k) t[k] = xs[pl * 9 + k];
+  const float x00 = plane[0], x0l = plane[W - 1], xl0 = plane[(H - 1) * W], xll = plane[(H - 1) * W + W - 1];
+  // tap (r,s) reads x[h+r-1][w+s-1]: r=0 never touches the last row, r=2 never the first; same for columns
+  for (int r = 0; r < 3; ++r)
+    for (int s = 0; s < 3; ++s) {
+      float v = t[0];
+      if (r == 0) v -= t[2];
+      if (r == 2) v -= t[1];
+      if (s == 0) v -= t[4];
+      if (s == 2) v -= t[3];
+      if (r == 0 && s == 0) v += xll;
+      if (r == 0 && s == 2) v += xl0;
+      if (r == 2 && s == 0) v += x0l;
+      if (r == 2 && s == 2) v += x00;
+      xs[pl * 9 + r * 3 + s] = v;
+    }
 }
 
 // One thread per output pixel, 128 consecutive pixels of one sample per block; weights staged in smem.
@@ -403,58 +417,62 @@ __global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __rest
   }
 }
 
-// dW[co][ci][r][s] += sum_pix x[n,ci,h+r-1,w+s-1] * dy[pix][co].  grid = (pixel blocks, Cin*3): one (ci, r) per y.
+// dW[co][ci][r][s] += sum_pix x[n,ci,h+r-1,w+s-1] * dy[pix][co].  grid = (pixel blocks, Cin): all nine taps of one
+// input channel per block, 8 output channels (one 16-byte vector of dy) at a time, so dy is read once per input
+// channel (one (ci, kernel row) per block read it three times: 395 MB of DRAM traffic for a 100 MB tensor).
 __global__ void __launch_bounds__(128) conv_first_wgrad_kernel(const float* __restrict__ x, int N, int Cin, int H,
                                                                int W, const __nv_bfloat16* __restrict__ dy, int Cp,
                                                                int Cout, float* __restrict__ dw) {
-  __shared__ float s_acc[3][64];
-  const int ci = blockIdx.y / 3, r = blockIdx.y % 3;
+  __shared__ float s_acc[9][64];
+  const int ci = blockIdx.y;
   const int lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < 3 * 64; i += 128) (&s_acc[0][0])[i] = 0.f;
+  for (int i = threadIdx.x; i < 9 * 64; i += 128) (&s_acc[0][0])[i] = 0.f;
   __syncthreads();
   const int64_t HW = static_cast<int64_t>(H) * W;
   const int64_t total = static_cast<int64_t>(N) * HW;
-  for (int c0 = 0; c0 < Cp && c0 < 64; c0 += 16) {
-    float acc[3][16];
+  for (int c0 = 0; c0 < Cp && c0 < 64; c0 += 8) {
+    float acc[9][8];
 #pragma unroll
-    for (int s = 0; s < 3; ++s)
+    for (int t = 0; t < 9; ++t)
 #pragma unroll
-      for (int i = 0; i < 16; ++i) acc[s][i] = 0.f;
+      for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
     for (int64_t pix = blockIdx.x * 128ll + threadIdx.x; pix < total; pix += static_cast<int64_t>(gridDim.x) * 128) {
       const int n = static_cast<int>(pix / HW);
       const int hw = static_cast<int>(pix - n * HW);
       const int h = hw / W, ww = hw - h * W;
-      const int hh = h + r - 1;
-      float xs[3];
+      const float* xp = x + (static_cast<int64_t>(n) * Cin + ci) * HW;
+      float xs[9];
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int wc = ww + s - 1;
-        xs[s] = (hh >= 0 && hh < H && wc >= 0 && wc < W) ? x[(static_cast<int64_t>(n) * Cin + ci) * HW + hh * W + wc] : 0.f;
-      }
-      const uint4* src = reinterpret_cast<const uint4*>(dy + pix * Cp + c0);
-      const uint4 d0 = src[0];
-      const uint4 d1 = (c0 + 8 < Cp) ? src[1] : make_uint4(0u, 0u, 0u, 0u);   // dense pitch: the chunk may be half
-      const uint32_t du[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float2 f = unpack_bf16x2(du[i]);
+      for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
-          acc[s][2 * i] = fmaf(xs[s], f.x, acc[s][2 * i]);
-          acc[s][2 * i + 1] = fmaf(xs[s], f.y, acc[s][2 * i + 1]);
+          const int hh = h + r - 1, wc = ww + s - 1;
+          xs[r * 3 + s] = (hh >= 0 && hh < H && wc >= 0 && wc < W) ? __ldg(xp + hh * W + wc) : 0.f;
+        }
+      const uint4 d0 = *reinterpret_cast<const uint4*>(dy + pix * Cp + c0);
+      const uint32_t du[4] = {d0.x, d0.y, d0.z, d0.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16x2(du[i]);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          acc[t][2 * i] = fmaf(xs[t], f.x, acc[t][2 * i]);
+          acc[t][2 * i + 1] = fmaf(xs[t], f.y, acc[t][2 * i + 1]);
         }
       }
     }
 #pragma unroll
-    for (int s = 0; s < 3; ++s) {
-      const float cs = warp_colsum16(acc[s], lane);
-      if ((lane & 1) == 0) atomicAdd(&s_acc[s][c0 + col16_of_lane(lane)], cs);
-    }
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float v = warp_sum(acc[t][i]);
+        if (lane == 0) atomicAdd(&s_acc[t][c0 + i], v);
+      }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 3 * 64; i += 128) {
-    const int s = i / 64, co = i % 64;
-    if (co < Cout) atomicAdd(dw + ((static_cast<int64_t>(co) * Cin + ci) * 3 + r) * 3 + s, s_acc[s][co]);
+  for (int i = threadIdx.x; i < 9 * 64; i += 128) {
+    const int t = i / 64, co = i % 64;
+    if (co < Cout) atomicAdd(dw + (static_cast<int64_t>(co) * Cin + ci) * 9 + t, s_acc[t][co]);
   }
 }
 
@@ -544,8 +562,15 @@ int mtbc_conv_first_fwd(const float* x, int32_t N, int32_t Cin, int32_t H, int32
   if (HW % 128 != 0) return set_error(MTBC_ERR_INVALID, "conv_first_fwd: H*W must be a multiple of 128");
   if (center_scratch != nullptr) {
     if (H < 2 || W < 2) return set_error(MTBC_ERR_INVALID, "conv_first_fwd: centring needs H, W >= 2");
-    conv_first_shift_sums_kernel<<<N * Cin, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, H, W, center_scratch);
+    cudaStream_t st0 = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(center_scratch, 0, static_cast<size_t>(N) * Cin * 9 * sizeof(float), st0);
+    if (e != cudaSuccess) return set_error(MTBC_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
+    int slices = static_cast<int>(HW / 4096); if (slices < 1) slices = 1; if (slices > 32) slices = 32;
+    conv_first_shift_sums_kernel<<<dim3(N * Cin, slices), 256, 0, st0>>>(x, H, W, center_scratch);
     int rc = check_launch("conv_first_shift_sums");
+    if (rc) return rc;
+    conv_first_shift_finish_kernel<<<cdiv(N * Cin, 128), 128, 0, st0>>>(x, H, W, N * Cin, center_scratch);
+    rc = check_launch("conv_first_shift_finish");
     if (rc) return rc;
   }
   const int Cs = (Cp + 15) & ~15;
@@ -568,7 +593,7 @@ int mtbc_conv_first_wgrad(const float* x, int32_t N, int32_t Cin, int32_t H, int
   int gx = static_cast<int>((total + 128 * 16 - 1) / (128 * 16));
   if (gx > 148 * 4) gx = 148 * 4;
   if (gx < 1) gx = 1;
-  conv_first_wgrad_kernel<<<dim3(gx, Cin * 3), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  conv_first_wgrad_kernel<<<dim3(gx, Cin), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       x, N, Cin, H, W, static_cast<const __nv_bfloat16*>(dy), Cp, Cout, dw);
   return check_launch("conv_first_wgrad");
 }

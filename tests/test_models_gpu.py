@@ -231,7 +231,9 @@ def test_train_step_matches_module_api():
             cs = torch.nn.functional.cosine_similarity(pa[n].grad.flatten(), pb[n].grad.flatten(), dim=0).item()
             assert cs > 0.98, (n, cs)
     cos = torch.nn.functional.cosine_similarity(torch.cat(fa), torch.cat(fb), dim=0).item()
-    assert cos > 0.95, cos
+    # two runs of the SAME path already differ this much (tools/diag_determinism.py: cos 0.95-0.965, the backward through
+    # ~25 InstanceNorm stages subtracts plane means from nearly uniform Dice gradients and amplifies bf16 rounding flips)
+    assert cos > 0.90, cos
 
 
 def test_prediction_refinement_bit_exact():

@@ -18,11 +18,6 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint32_t b_l
 __device__ __forceinline__ void cp_128x256b(uint32_t taddr, uint32_t lo, uint32_t hi) {
   asm volatile("{\n\t.reg .b64 d;\n\tmov.b64 d, {%1, %2};\n\ttcgen05.cp.cta_group::1.128x256b [%0], d;\n\t}" ::"r"(taddr), "r"(lo), "r"(hi) : "memory");
 }
-__device__ __forceinline__ bool elect_one() {
-  uint32_t p;
-  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
-  return p != 0;
-}
 __device__ __forceinline__ void shift_down(uint32_t taddr) {
   asm volatile("tcgen05.shift.cta_group::1.down [%0];" ::"r"(taddr) : "memory");
 }
@@ -79,6 +74,9 @@ int main() {
       {0, 128, 32, "SS kc=32 halo view shift 0 sbo 10", 32, 0, 10}, {0, 128, 64, "SS N=64 kc=64 halo shift 11", 64, 11, 10},
       {0, 128, 32, "SS MN-major A (wgrad halo) kc=32 lbo=64 sbo=10 rows", 32, 10, 10, 1, 64},
       {0, 128, 32, "SS MN-major A canonical kc=64 lbo=16384", 64, 0, 8, 1, 16384},
+      {0, 128, 32, "SS kc=32 G=2 view: shift 11 sbo 20", 32, 11, 20}, {0, 128, 64, "SS N=64 kc=32 G=2 view: shift 11 sbo 20", 32, 11, 20},
+      {0, 128, 64, "SS N=64 kc=32 shift 11 sbo 10", 32, 11, 10}, {0, 128, 64, "SS N=64 kc=32 canonical", 32, 0, 8},
+      {0, 128, 64, "SS N=64 kc=32 G=2 view: shift 31 sbo 20", 32, 31, 20}, {0, 128, 32, "SS N=32 kc=32 G=2 view: shift 30 sbo 20", 32, 30, 20},
       {0, 128, 32, "SS 1 issuer"}, {0, 64, 32, "SS 1 issuer M=64"}, {0, 64, 64, "SS 1 issuer M=64"}, {0, 128, 16, "SS N=16"},
       {0, 128, 64, "SS 1 issuer"}, {0, 128, 96, "SS 1 issuer"}, {0, 128, 128, "SS"}, {0, 128, 192, "SS"},
       {1, 128, 32, "SS 2 issuers (per-issuer MMAs)"}, {1, 128, 64, "SS 2 issuers"},
