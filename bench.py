@@ -146,7 +146,7 @@ def per_kernel_times(ts, reps=3):
     import ctypes as C
     import torch
     from multi_task_breast_cancer_b200.ops import stream_ptr
-    launches = ts.launches_fb + (ts.launches_opt if ts.world == 1 else [])
+    launches = [l for l in ts.launches_fb + (ts.launches_opt if ts.world == 1 else []) if l.kind != "bucket_ready"]
     st = C.c_void_p(stream_ptr())
     agg = {}
     for rep in range(reps):

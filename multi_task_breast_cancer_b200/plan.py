@@ -83,9 +83,11 @@ class JobTable:
     def __init__(self):
         self.jobs: List[_lib.ParamJob] = []
         self._keep: List[object] = []
+        self.owner: List[Optional[str]] = []   # parameter name per job (gradient unpacks: decides the bucket)
 
     def add(self, kind: int, ints: Sequence[int], src: torch.Tensor, dst0: Optional[torch.Tensor],
-            dst1: Optional[torch.Tensor] = None):
+            dst1: Optional[torch.Tensor] = None, owner: Optional[str] = None):
+        self.owner.append(owner)
         j = _lib.ParamJob()
         j.kind = kind
         for k, v in enumerate(ints):
@@ -96,14 +98,16 @@ class JobTable:
         self.jobs.append(j)
         self._keep += [src, dst0, dst1]
 
-    def launch(self) -> List[Callable]:
-        if not self.jobs:
+    def launch(self, select: Optional[Sequence[int]] = None) -> List[Callable]:
+        """One launch over all jobs, or over the jobs whose indices are in `select`."""
+        jobs = self.jobs if select is None else [self.jobs[i] for i in select]
+        if not jobs:
             return []
-        arr = (_lib.ParamJob * len(self.jobs))(*self.jobs)
+        arr = (_lib.ParamJob * len(jobs))(*jobs)
         h = C.c_void_p()
-        _lib.check(_lib.load().mtbc_param_jobs_create(arr, len(self.jobs), C.byref(h)), "param_jobs")
+        _lib.check(_lib.load().mtbc_param_jobs_create(arr, len(jobs), C.byref(h)), "param_jobs")
         op = ops.Op(h, self._keep, "param_jobs")
-        return [_mk_op(op, 0.0, f"{len(self.jobs)} parameter jobs")]
+        return [_mk_op(op, 0.0, f"{len(jobs)} parameter jobs")]
 
 
 def _mk_op(op: ops.Op, true_flops: float = 0.0, desc: str = "") -> Callable:
@@ -359,7 +363,7 @@ class Plan:
             c0 = 0
             for cs, off in zip(pk["src_c"], pk["offs"]):
                 self.unpack_jobs.add(_lib.JOB_UNPACK_CONV, [acc.shape[1], acc.shape[2], off, Wt.shape[0], Wt.shape[1],
-                                                            3, c0, cs, 0], acc, self.grad_view[w])
+                                                            3, c0, cs, 0], acc, self.grad_view[w], owner=w)
                 c0 += cs
         return self._wg_acc[w]
 
@@ -425,7 +429,8 @@ class Plan:
             o = ops.convT_wgrad_op(f, out.g, acc, k)
             self.tc_flops_bwd += o.flops
             blk.append(_mk_op(o, t_flops, f"{name} convT wgrad {f.N}x{f.H}x{f.W} {Cin}->{Cout}"))
-            self.unpack_jobs.add(_lib.JOB_UNPACK_CONVT, [k * k * cp, f.Ck, Cin, Cout, k, 0], acc, self.grad_view[w])
+            self.unpack_jobs.add(_lib.JOB_UNPACK_CONVT, [k * k * cp, f.Ck, Cin, Cout, k, 0], acc, self.grad_view[w],
+                                 owner=w)
             self._late_unpacked.append(w)
             if b is not None:
                 blk.append(_mk("mtbc_channel_sum", ptr(out.g.t), out.g.N * out.g.H * out.g.W, out.g.Cp, Cout,
@@ -579,9 +584,7 @@ class Plan:
                 body.extend(mk_block())
                 for n in self._touched:  # the last block touching a parameter finalises its gradient
                     self.param_done_at[n] = len(body)
-            body.extend(self.unpack_jobs.launch())  # every conv / convT weight gradient -> parameter layout
-            for n in list(self._wg_acc) + self._late_unpacked:
-                self.param_done_at[n] = len(body)
+            body = self._bucketize(body)
             self.bwd = [_mk("mtbc_zero_bytes", ptr(self.grad_flat), self.grad_flat.numel() * 4)]
             self.bwd += self.bwd_arena.zero_launches()
             n_pre = len(self.bwd)
@@ -591,6 +594,40 @@ class Plan:
         self.fwd = self.fwd_arena.zero_launches() + self.fwd
         self._bwd_blocks = []
         self.finalized = True
+
+    def _bucketize(self, body: List[Callable]) -> List[Callable]:
+        """Split the flat gradient buffer into `n_buckets` contiguous ranges of about equal size and make each range
+        final as early as the backward order allows: the weight-gradient unpack jobs of a bucket's parameters run as
+        one launch right after the last backward block that touches any of them, followed by a `bucket_ready` marker
+        (a no-op launch that TrainStep turns into the fork point of that bucket's gradient all-reduce).  The flat layout
+        is the reverse registration order, i.e. about the order in which backward finishes parameters, so bucket 0
+        (heads, last decoder node) is ready after a fraction of the backward pass."""
+        nb = max(1, int(os.environ.get("MTBC_DP_BUCKETS", "4")))
+        names = [n for n in self.grad_range if self.has_grad.get(n)]
+        self.buckets, bucket_idx, ready = plan_buckets({n: self.grad_range[n] for n in self.grad_range},
+                                                       {n: self.param_done_at.get(n, len(body)) for n in names},
+                                                       self.grad_flat.numel(), nb)
+
+        def bucket_of(n):
+            return bucket_idx[n]
+        jobs_of = [[i for i, o in enumerate(self.unpack_jobs.owner) if bucket_of(o) == k] for k in range(nb)]
+        out: List[Callable] = []
+        emitted = [False] * nb
+        done_after: Dict[int, int] = {}
+
+        def flush(i):
+            for k in range(nb):
+                if not emitted[k] and ready[k] <= i:
+                    out.extend(self.unpack_jobs.launch(jobs_of[k]))
+                    out.append(_mk_marker(k))
+                    done_after[k] = len(out)
+                    emitted[k] = True
+        flush(0)
+        for i, l in enumerate(body):
+            out.append(l)
+            flush(i + 1)
+        self.param_done_at = {n: done_after[bucket_of(n)] for n in names}
+        return out
 
     def run_pack(self, stream=None):
         st = C.c_void_p(stream if stream is not None else ops.stream_ptr())
@@ -609,6 +646,37 @@ class Plan:
 
     def launch_counts(self) -> Dict[str, int]:
         return {"pack": len(self.pack), "fwd": len(self.fwd), "bwd": len(self.bwd)}
+
+
+def plan_buckets(ranges: Dict[str, Tuple[int, int]], done_at: Dict[str, int], total: int, nb: int):
+    """Pure bucket arithmetic (unit-tested on the CPU): split [0, total) into nb contiguous ranges of about equal size;
+    a parameter belongs to the bucket that contains its first element; a bucket is ready once every one of its
+    parameters that receives a gradient is done (done_at[name] = position in the backward launch list), and never
+    before the bucket in front of it (all-reduces are issued in bucket order on every rank).
+    Returns ([(lo, hi)], {name: bucket}, [ready position])."""
+    cuts = [total * (k + 1) // nb for k in range(nb)]
+    lo = [0] + cuts[:-1]
+    idx = {}
+    for n, (a, _) in ranges.items():
+        k = 0
+        while k < nb - 1 and a >= cuts[k]:
+            k += 1
+        idx[n] = k
+    ready = [0] * nb
+    for n, d in done_at.items():
+        ready[idx[n]] = max(ready[idx[n]], d)
+    for k in range(1, nb):
+        ready[k] = max(ready[k], ready[k - 1])
+    return [(lo[k], cuts[k]) for k in range(nb)], idx, ready
+
+
+def _mk_marker(k: int) -> Callable:
+    """No-op entry of a launch list: 'bucket k of the flat gradient buffer is final from here on'."""
+    def launch(stream):
+        return None
+    launch.kind = "bucket_ready"
+    launch.bucket = k
+    return launch
 
 
 def flat_layout(params) -> Tuple[Dict[str, Tuple[int, int]], int]:

@@ -7,10 +7,16 @@ stream (plan.py), captured once into a CUDA graph and replayed.  The reference's
 Python `if`, `.item()` on the loss: criterions.py:72, training_multitask.py:99) become a device-side NaN flag and a
 4-float device buffer that the caller reads when it wants to.
 
-Data parallel (new functionality, the reference is single device): one process per GPU, gradients are summed with one
-NCCL all-reduce over the flat gradient buffer and the 1/world scaling is folded into the Adam kernel.  No operation
-couples samples (InstanceNorm is per sample, Dice is per sample then mean, focal is per sample then mean), so R ranks x
-B/R samples equals 1 rank x B samples up to fp32 summation order.
+Data parallel (new functionality, the reference is single device): one process per GPU; the flat fp32 gradient buffer
+is split into a few contiguous buckets (plan.Plan._bucketize), each bucket's NCCL all-reduce (sum) is forked onto a
+communication stream at the point of the backward pass where the bucket becomes final, so it overlaps the remaining
+data- / weight-gradient kernels, and the optimizer joins all of them; the 1/world scaling is folded into the Adam
+kernel.  The step is captured as one CUDA graph per segment between bucket boundaries (forward + loss + the first part
+of backward, ..., the optimizer); the NCCL calls are issued eagerly between the replays, on the communication stream
+(capturing the collectives themselves inside the graph hung with the NCCL 2.28.9 / torch 2.11 of this image).  No
+operation couples samples
+(InstanceNorm is per sample, Dice is per sample then mean, focal is per sample then mean), so R ranks x B/R samples
+equals 1 rank x B samples up to fp32 summation order.
 """
 from __future__ import annotations
 
@@ -65,6 +71,11 @@ class TrainStep:
             self.exp_avg_sq = torch.zeros_like(self.flat_p)
             self._build_launches()
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.comm_stream: Optional[torch.cuda.Stream] = None
+        self.seg_graphs = None   # data parallel: [(CUDAGraph, bucket index or None)] + opt_graph
+        self.opt_graph = None
+        import os as _os
+        self.overlap = self.world > 1 and _os.environ.get("MTBC_DP_OVERLAP", "1") != "0"
         self.steps_done = 0
         self._pinned: Dict[str, torch.Tensor] = {}
 
@@ -120,13 +131,58 @@ class TrainStep:
     # ------------------------------------------------------------------------------------------------ running
     @property
     def n_launches(self) -> int:
-        """Kernel / memset launches of one step (our own kernels only; the NCCL all-reduce is not counted)."""
-        return len(self.launches_fb) + len(self.launches_opt)
+        """Kernel / memset launches of one step (our own kernels only; the NCCL all-reduces are not counted)."""
+        return sum(1 for l in self.launches_fb + self.launches_opt if l.kind != "bucket_ready")
 
     def _run_list(self, launches):
         st = C.c_void_p(stream_ptr())
         for l in launches:
             l(st)
+
+    def _segments(self):
+        """launches_fb split at the bucket markers: [(launches, bucket index or None)]."""
+        segs, cur = [], []
+        for l in self.launches_fb:
+            if l.kind == "bucket_ready":
+                segs.append((cur, l.bucket))
+                cur = []
+            else:
+                cur.append(l)
+        segs.append((cur, None))
+        return segs
+
+    def _fork_allreduce(self, k):
+        """All-reduce of gradient bucket k on the communication stream, ordered after everything enqueued so far."""
+        import torch.distributed as dist
+        lo, hi = self.plan.buckets[k]
+        if hi <= lo:
+            return
+        main = torch.cuda.current_stream(self.device)
+        if self.comm_stream is None:
+            self.comm_stream = torch.cuda.Stream(device=self.device)
+        self.comm_stream.wait_stream(main)
+        with torch.cuda.stream(self.comm_stream):
+            dist.all_reduce(self.plan.grad_flat[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+
+    def _run_step_dp(self):
+        """forward + loss + backward with each gradient bucket's all-reduce forked onto the communication stream as soon
+        as the bucket is final, then the optimizer after all of them."""
+        main = torch.cuda.current_stream(self.device)
+        if self.seg_graphs is not None:
+            for g, k in self.seg_graphs:
+                g.replay()
+                if k is not None:
+                    self._fork_allreduce(k)
+            main.wait_stream(self.comm_stream)
+            self.opt_graph.replay()
+            return
+        for launches, k in self._segments():
+            self._run_list(launches)
+            if k is not None:
+                self._fork_allreduce(k)
+        if self.comm_stream is not None:
+            main.wait_stream(self.comm_stream)
+        self._run_list(self.launches_opt)
 
     def _capture(self):
         # warm up on a side stream, then capture forward+loss+backward (+ optimizer when single GPU)
@@ -135,13 +191,31 @@ class TrainStep:
         saved = (self.flat_p.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.step_dev.clone())
         with torch.cuda.stream(s):
             for _ in range(2):
-                self._run_list(self.launches_fb)
-                if self.world == 1:
-                    self._run_list(self.launches_opt)
+                if self.overlap:
+                    self._run_step_dp()
+                else:
+                    self._run_list(self.launches_fb)
+                    if self.world == 1:
+                        self._run_list(self.launches_opt)
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
         self.flat_p.copy_(saved[0]); self.exp_avg.copy_(saved[1]); self.exp_avg_sq.copy_(saved[2])
         self.step_dev.copy_(saved[3])
+        if self.overlap:
+            # one graph per segment between bucket boundaries + one for the optimizer; NCCL stays outside the graphs
+            graphs = []
+            for launches, k in self._segments():
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    self._run_list(launches)
+                graphs.append((g, k))
+            og = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(og, capture_error_mode="thread_local"):
+                self._run_list(self.launches_opt)
+            self.opt_graph = og
+            self.seg_graphs = graphs
+            self.graph = graphs[0][0]
+            return
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._run_list(self.launches_fb)
@@ -161,16 +235,27 @@ class TrainStep:
             if self.use_graph:
                 if self.graph is None:
                     self._capture()
-                self.graph.replay()
+                if self.overlap:
+                    self._run_step_dp()
+                else:
+                    self.graph.replay()
+                    if self.world > 1:
+                        self._allreduce_then_opt()
+            elif self.overlap:
+                self._run_step_dp()
             else:
                 self._run_list(self.launches_fb)
                 if self.world == 1:
                     self._run_list(self.launches_opt)
-            if self.world > 1:
-                import torch.distributed as dist
-                dist.all_reduce(self.plan.grad_flat, op=dist.ReduceOp.SUM, group=self.pg)
-                self._run_list(self.launches_opt)
+                else:
+                    self._allreduce_then_opt()
         self.steps_done += 1
+
+    def _allreduce_then_opt(self):
+        """MTBC_DP_OVERLAP=0: one all-reduce over the whole flat gradient buffer after the backward pass."""
+        import torch.distributed as dist
+        dist.all_reduce(self.plan.grad_flat, op=dist.ReduceOp.SUM, group=self.pg)
+        self._run_list(self.launches_opt)
 
     def set_lr(self, lr: float):
         self.lr_dev.fill_(float(lr))

@@ -79,6 +79,24 @@ def test_k_offsets_alignment():
     assert ops.pad32(24) == 32 and ops.pad32(320) == 320 and ops.pad32(1) == 32
 
 
+def test_gradient_bucket_plan():
+    """Bucket arithmetic of the overlapped gradient all-reduce (plan.plan_buckets)."""
+    from multi_task_breast_cancer_b200.plan import plan_buckets
+    # flat layout = reverse registration order: the head (registered last) sits at offset 0 and finishes first
+    ranges = {"enc.w": (600, 1000), "mid.w": (300, 600), "dec.w": (64, 300), "head.w": (0, 64)}
+    done = {"head.w": 3, "dec.w": 10, "mid.w": 25, "enc.w": 40}
+    buckets, idx, ready = plan_buckets(ranges, done, 1000, 4)
+    assert buckets == [(0, 250), (250, 500), (500, 750), (750, 1000)]
+    assert idx == {"head.w": 0, "dec.w": 0, "mid.w": 1, "enc.w": 2}
+    assert ready == [10, 25, 40, 40]            # monotone; the empty last bucket follows the one before it
+    # a parameter without gradient (unused head) does not hold its bucket back
+    _, _, ready = plan_buckets(ranges, {k: v for k, v in done.items() if k != "dec.w"}, 1000, 4)
+    assert ready[0] == 3
+    # one bucket = the whole buffer, ready at the very end
+    b1, _, r1 = plan_buckets(ranges, done, 1000, 1)
+    assert b1 == [(0, 1000)] and r1 == [40]
+
+
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
