@@ -116,10 +116,27 @@ typedef struct {
   int32_t splits; /* 0 = auto */
 } mtbc_wgrad_desc;
 
+/* Weight gradient of a 3x3 Conv2d over a folded concatenation, ALL sources in one launch: dy is read once per pixel
+ * tile instead of once per source (MTUNetPlusPlus.py:107-118 concatenates up to five tensors in front of a conv; the
+ * reference's aten::convolution_backward sees the materialised concat).  Same accumulator layout as mtbc_wgrad_desc;
+ * source i lands at columns k0[i]...  Only planes with H % 16 == 0 and W % 8 == 0 (the caller falls back to one
+ * mtbc_wgrad_create per source otherwise: creation fails with MTBC_ERR_INVALID). */
+typedef struct {
+  int32_t nsrc;
+  mtbc_act_view x[MTBC_MAX_VIEWS];
+  int32_t k0[MTBC_MAX_VIEWS];
+  mtbc_act_view dy;
+  int32_t W, H, N;
+  float* dw_acc;
+  int32_t n_rows, ld_k;
+  int32_t splits; /* 0 = auto */
+} mtbc_wgrad_multi_desc;
+
 typedef struct mtbc_op mtbc_op; /* opaque: encoded tensor maps + launch geometry */
 
 int mtbc_conv_gemm_create(const mtbc_conv_gemm_desc* d, mtbc_op** out);
 int mtbc_wgrad_create(const mtbc_wgrad_desc* d, mtbc_op** out);
+int mtbc_wgrad_multi_create(const mtbc_wgrad_multi_desc* d, mtbc_op** out);
 int mtbc_op_launch(mtbc_op* op, void* stream);
 int mtbc_ops_launch(mtbc_op* const* ops, int32_t n, void* stream);
 void mtbc_op_destroy(mtbc_op* op);

@@ -48,6 +48,11 @@ class WgradDesc(C.Structure):
                 ("dw_acc", c_vp), ("n_rows", c_i32), ("ld_k", c_i32), ("k0", c_i32), ("splits", c_i32)]
 
 
+class WgradMultiDesc(C.Structure):
+    _fields_ = [("nsrc", c_i32), ("x", ActView * 8), ("k0", c_i32 * 8), ("dy", ActView), ("W", c_i32), ("H", c_i32),
+                ("N", c_i32), ("dw_acc", c_vp), ("n_rows", c_i32), ("ld_k", c_i32), ("splits", c_i32)]
+
+
 class ParamJob(C.Structure):
     _fields_ = [("kind", c_i32), ("i", c_i32 * 11), ("src", c_vp), ("dst0", c_vp), ("dst1", c_vp)]
 
@@ -61,6 +66,7 @@ _SIGS = {
     "mtbc_device_check": [],
     "mtbc_conv_gemm_create": [C.POINTER(ConvGemmDesc), C.POINTER(c_vp)],
     "mtbc_wgrad_create": [C.POINTER(WgradDesc), C.POINTER(c_vp)],
+    "mtbc_wgrad_multi_create": [C.POINTER(WgradMultiDesc), C.POINTER(c_vp)],
     "mtbc_param_jobs_create": [C.POINTER(ParamJob), c_i32, C.POINTER(c_vp)],
     "mtbc_op_launch": [c_vp, c_vp],
     "mtbc_ops_launch": [C.POINTER(c_vp), c_i32, c_vp],

@@ -609,6 +609,132 @@ __global__ void __launch_bounds__(128) wgrad_halo_kernel(const __grid_constant__
   }
 }
 
+
+// ---- all concat sources in one launch ------------------------------------------------------------------------------
+// The per-source kernel above is bound by TMA box rows (~4 cycles per 64-byte row per SM, 160 rows of x + 144 rows of
+// dy per 128-pixel tile), not by its 8 MMAs.  Here one CTA owns a GROUP of up to five 32-channel chunks (any sources)
+// and loads the dy box once per tile for all of them: 144 + 160 k rows for k chunks instead of 304 k.  Each chunk has
+// its own TMEM accumulator (NN columns), so a group is limited by 512 TMEM columns.
+constexpr int kWgMaxChunks = 48;
+struct WgradMultiParams {
+  CUtensorMap amap[MTBC_MAX_VIEWS];
+  CUtensorMap bmap;
+  int16_t c_view[kWgMaxChunks], c_ch[kWgMaxChunks], c_ac[kWgMaxChunks];   // source, first channel, channels of the source
+  int32_t c_col[kWgMaxChunks];                                             // first column in dw_acc rows
+  int32_t nchunks, group;
+  int32_t b_kc, NN, n_tiles, tmem_cols, stages;
+  int32_t tiles_w, tiles_h, n_ptiles, splits;
+  int32_t a_bytes, b_bytes, stage_bytes;
+  int32_t n_rows, ld_k;
+  float* dw_acc;
+};
+
+__global__ void __launch_bounds__(128) wgrad_halo_multi_kernel(const __grid_constant__ WgradMultiParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t s_full[kHaloMaxStages], s_empty[kHaloMaxStages];
+  __shared__ uint64_t s_accum;
+  __shared__ uint32_t s_tmem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int grp = blockIdx.x, split = blockIdx.y, ntile = blockIdx.z;
+  const int c_begin = grp * p.group;
+  const int nck = min(p.group, p.nchunks - c_begin);
+  const int per = (p.n_ptiles + p.splits - 1) / p.splits;
+  const int pt_begin = split * per;
+  const int pt_end = min(p.n_ptiles, pt_begin + per);
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
+    mbar_init(&s_accum, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&s_tmem, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+
+  if (pt_end > pt_begin && nck > 0) {
+    if (warp == 0 && elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t bytes = static_cast<uint32_t>(8 * kHaloH * p.b_kc * 2 + nck * (kHaloW * 16 * 64));
+      for (int pt = pt_begin; pt < pt_end; ++pt) {
+        const int w0 = (pt % p.tiles_w) * 8;
+        const int h0 = ((pt / p.tiles_w) % p.tiles_h) * 16;
+        const int n = pt / (p.tiles_w * p.tiles_h);
+        mbar_wait(&s_empty[stage], phase ^ 1u);
+        uint8_t* b_dst = smem + stage * p.stage_bytes;
+        mbar_arrive_expect_tx(&s_full[stage], bytes);
+        tma_load_4d(b_dst, &p.bmap, &s_full[stage], ntile * p.b_kc, w0, h0 - 1, n);
+        for (int c = 0; c < nck; ++c)
+          tma_load_4d(b_dst + p.b_bytes + c * p.a_bytes, &p.amap[p.c_view[c_begin + c]], &s_full[stage],
+                      p.c_ch[c_begin + c], w0 - 1, h0, n);
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    } else if (warp == 1 && elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.NN, 1, 1);
+      const uint32_t b_rowb = p.b_kc * 2u;
+      const uint32_t a_hi = umma_desc_hi(kHaloW * 64, 4u);                      // K step of 8 pixels = one halo row
+      const uint32_t b_hi = umma_desc_hi(8 * b_rowb, p.b_kc == 64 ? 2u : 4u);   // K step of 8 pixels = one tile row
+      const uint32_t b_j16 = b_rowb;  // 16 pixel rows of the dy tile, in 16-byte units
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = pt_begin; pt < pt_end; ++pt) {
+        mbar_wait(&s_full[stage], phase);
+        tc_fence_after();
+        const uint32_t base = smem_u32(smem + stage * p.stage_bytes);
+        const uint32_t b_lo = umma_desc_lo(base, 8 * b_rowb);                    // next N atom = next tile row (dh - 1)
+        const uint32_t first = (pt > pt_begin) ? 1u : 0u;
+        for (int c = 0; c < nck; ++c) {
+          const uint32_t a_lo = umma_desc_lo(base + p.b_bytes + c * p.a_bytes, 64);   // next M atom = next pixel (dw + 1)
+          const uint32_t d = tmem_base + static_cast<uint32_t>(c * p.NN);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)    // 16 pixels = tile rows 2j, 2j+1
+            umma_bf16_lohi(d, a_lo + (2 * j * kHaloW) * 4, a_hi, b_lo + j * b_j16, b_hi, idesc, j > 0 ? 1u : first);
+        }
+        umma_commit(&s_empty[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(&s_accum);
+    }
+    __syncwarp();
+    mbar_wait(&s_accum, 0);
+    tc_fence_after();
+    __syncwarp();
+
+    // warp = horizontal tap (dw + 1), lane = channel inside the chunk; column group a = 0,1,2 <-> dh = 1 - a
+    for (int c = 0; c < nck; ++c) {
+      const int ci = p.c_ch[c_begin + c] + lane;
+      const bool valid = (warp < 3) && (ci < p.c_ac[c_begin + c]);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(c * p.NN);
+      for (int a = 0; a < 3; ++a) {
+        const int tap = (2 - a) * 3 + warp;
+        for (int cc = 0; cc < p.b_kc; cc += 16) {
+          float v[16];
+          tmem_ld16(taddr + a * p.b_kc + cc, v);
+          if (valid) {
+            float* dst = p.dw_acc + (static_cast<int64_t>(tap) * p.n_rows + ntile * p.b_kc + cc) * p.ld_k +
+                         p.c_col[c_begin + c] + lane;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) atomicAdd(dst + static_cast<int64_t>(i) * p.ld_k, v[i]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
 // ================================================================================================ host side
 static int tmem_cols_pow2(int n) { int c = 32; while (c < n) c <<= 1; return c; }
 static bool halo_disabled() { const char* e = getenv("MTBC_NO_HALO"); return e && e[0] == '1'; }
@@ -854,6 +980,90 @@ int wgrad_halo_try_create(const mtbc_wgrad_desc* d, OpBase** out) {
   op->flops = 2.0 * double(d->N) * d->H * d->W * double(a.C) * double(b.C) * 9.0;
   cudaError_t e = cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   if (e != cudaSuccess) { delete op; return set_error(MTBC_ERR_CUDA, "cudaFuncSetAttribute(wgrad_halo): %s", cudaGetErrorString(e)); }
+  *out = op;
+  return 0;
+}
+
+struct WgradMultiOp : public OpBase {
+  WgradMultiParams p;
+  dim3 grid;
+  int smem_bytes;
+  double flops;
+  int launch(cudaStream_t st) override {
+    wgrad_halo_multi_kernel<<<grid, 128, smem_bytes, st>>>(p);
+    return check_launch("wgrad_halo_multi_kernel");
+  }
+  double op_flops() const override { return flops; }
+};
+
+int wgrad_halo_multi_create(const mtbc_wgrad_multi_desc* d, OpBase** out) {
+  if (d->nsrc < 1 || d->nsrc > MTBC_MAX_VIEWS) return set_error(MTBC_ERR_INVALID, "wgrad_multi: nsrc");
+  if (halo_disabled() || d->H % 16 != 0 || d->W % 8 != 0)
+    return set_error(MTBC_ERR_INVALID, "wgrad_multi: needs H %% 16 == 0 and W %% 8 == 0");
+  const mtbc_act_view& b = d->dy;
+  if (b.C % 8 != 0 || b.W != d->W || b.H != d->H || b.N != d->N) return set_error(MTBC_ERR_INVALID, "wgrad_multi: dy view");
+  const int bCp = (b.C + 31) & ~31;
+  const int b_kc = (bCp % 64 == 0) ? 64 : 32;
+  WgradMultiOp* op = new WgradMultiOp();
+  WgradMultiParams& p = op->p;
+  memset(&p, 0, sizeof(p));
+  int rc = encode_act(&p.bmap, b, b_kc, 8, kHaloH, 1);
+  if (rc) { delete op; return rc; }
+  int nch = 0;
+  double ksum = 0;
+  for (int v = 0; v < d->nsrc; ++v) {
+    const mtbc_act_view& a = d->x[v];
+    if (a.C % 8 != 0 || a.W != d->W || a.H != d->H || a.N != d->N) { delete op; return set_error(MTBC_ERR_INVALID, "wgrad_multi: x view %d", v); }
+    rc = encode_act(&p.amap[v], a, 32, kHaloW, 16, 1);
+    if (rc) { delete op; return rc; }
+    const int aCp = (a.C + 31) & ~31;
+    for (int ch = 0; ch < aCp; ch += 32) {
+      if (nch >= kWgMaxChunks) { delete op; return set_error(MTBC_ERR_INVALID, "wgrad_multi: more than %d chunks", kWgMaxChunks); }
+      p.c_view[nch] = (int16_t)v; p.c_ch[nch] = (int16_t)ch; p.c_ac[nch] = (int16_t)a.C; p.c_col[nch] = d->k0[v] + ch;
+      ++nch;
+    }
+    ksum += a.C;
+  }
+  p.nchunks = nch;
+  p.b_kc = b_kc; p.NN = 3 * b_kc; p.n_tiles = bCp / b_kc;
+  // accumulators per CTA: 5 fit TMEM at NN = 96; at NN = 192 two would need all 512 columns and leave one CTA per SM
+  // (measured slower than one chunk per CTA with two CTAs per SM), so wide dy tiles keep one chunk per CTA
+  const int gmax = p.NN == 96 ? 5 : 1;
+  const int ngroups = (nch + gmax - 1) / gmax;
+  p.group = (nch + ngroups - 1) / ngroups;
+  p.tmem_cols = tmem_cols_pow2(p.group * p.NN);
+  p.tiles_w = d->W / 8; p.tiles_h = d->H / 16;
+  p.n_ptiles = p.tiles_w * p.tiles_h * d->N;
+  p.a_bytes = ((kHaloW * 16 * 64) + 1023) & ~1023;            // 10 KB
+  p.b_bytes = ((8 * kHaloH * b_kc * 2) + 1023) & ~1023;       // 9 / 18 KB
+  p.stage_bytes = p.b_bytes + p.group * p.a_bytes;
+  // two CTAs per SM when two 2-stage rings fit, else one CTA with a deeper ring
+  int ctas = 2;
+  int stages = (100 * 1024) / p.stage_bytes;
+  if (stages < 2) { ctas = 1; stages = (200 * 1024) / p.stage_bytes; }
+  if (stages > kHaloMaxStages) stages = kHaloMaxStages;
+  if (stages < 2 || ctas * p.tmem_cols > 512) {
+    if (ctas == 2) { ctas = 1; stages = (200 * 1024) / p.stage_bytes; if (stages > kHaloMaxStages) stages = kHaloMaxStages; }
+    if (stages < 2) { delete op; return set_error(MTBC_ERR_INVALID, "wgrad_multi: stage does not fit shared memory"); }
+  }
+  p.stages = stages;
+  op->smem_bytes = stages * p.stage_bytes + 1024;
+  p.n_rows = d->n_rows; p.ld_k = d->ld_k; p.dw_acc = d->dw_acc;
+  const int base = ngroups * p.n_tiles;
+  int splits = d->splits;
+  if (splits <= 0) {
+    splits = (ctas * sm_count() + base - 1) / base;
+    int maxs = (p.n_ptiles + 3) / 4; if (maxs < 1) maxs = 1;
+    if (splits > maxs) splits = maxs;
+  }
+  if (splits > p.n_ptiles) splits = p.n_ptiles;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  p.splits = splits;
+  op->grid = dim3(ngroups, splits, p.n_tiles);
+  op->flops = 2.0 * double(d->N) * d->H * d->W * ksum * double(b.C) * 9.0;
+  cudaError_t e = cudaFuncSetAttribute(wgrad_halo_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  if (e != cudaSuccess) { delete op; return set_error(MTBC_ERR_CUDA, "cudaFuncSetAttribute(wgrad_multi): %s", cudaGetErrorString(e)); }
   *out = op;
   return 0;
 }

@@ -24,6 +24,7 @@ bool tensor_map_available();
 // > 0: not eligible (caller falls back to the generic kernel), 0: created, < 0: error
 int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out);
 int wgrad_halo_try_create(const mtbc_wgrad_desc* d, OpBase** out);
+int wgrad_halo_multi_create(const mtbc_wgrad_multi_desc* d, OpBase** out);
 // tensor-map encoders (conv_gemm.cu): bf16 NHWC view with box (kc, bw, bh, bn); packed weights with box (kc, BN, 1)
 int encode_act(CUtensorMap* m, const mtbc_act_view& v, int kc, int bw, int bh, int bn);
 int encode_w(CUtensorMap* m, const void* w, int ktot, int nrows, int ntaps, int kc, int BN);

@@ -15,7 +15,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import OutSlice, ActView, ConvGemmDesc, GemmSeg, WgradDesc, WgradTap
+from ._lib import OutSlice, ActView, ConvGemmDesc, GemmSeg, WgradDesc, WgradMultiDesc, WgradTap
 
 
 def pad32(c: int) -> int:
@@ -252,6 +252,24 @@ def conv3x3_wgrad_op(x: Feat, dy: Feat, dw_acc: torch.Tensor, k0: int, ksz: int 
     h = C.c_void_p()
     _lib.check(_lib.load().mtbc_wgrad_create(C.byref(d), C.byref(h)), "conv3x3_wgrad")
     return Op(h, [x.t, dy.t, dw_acc], "conv3x3_wgrad")
+
+
+def conv3x3_wgrad_multi_op(xs: Sequence[Feat], dy: Feat, dw_acc: torch.Tensor, k0s: Sequence[int], splits: int = 0) -> Op:
+    """Weight gradient of a 3x3 conv over a folded concat, all sources in one launch (dy is read once per pixel tile).
+    dw_acc: fp32 [9][dy.Ck][Ktot]; source i accumulates at column k0s[i].  Raises MtbcError when the plane is not served
+    by the halo kernels (caller falls back to conv3x3_wgrad_op per source)."""
+    assert dw_acc.dtype == torch.float32 and dw_acc.shape[0] == 9 and dw_acc.shape[1] == dy.Ck and len(xs) <= 8
+    d = WgradMultiDesc()
+    d.nsrc = len(xs)
+    for i, (x, k0) in enumerate(zip(xs, k0s)):
+        d.x[i] = _view(x)
+        d.k0[i] = k0
+    d.dy = _view(dy)
+    d.W, d.H, d.N = dy.W, dy.H, dy.N
+    d.dw_acc = dw_acc.data_ptr(); d.n_rows = dw_acc.shape[1]; d.ld_k = dw_acc.shape[2]; d.splits = splits
+    h = C.c_void_p()
+    _lib.check(_lib.load().mtbc_wgrad_multi_create(C.byref(d), C.byref(h)), "conv3x3_wgrad")
+    return Op(h, [*(x.t for x in xs), dy.t, dw_acc], "conv3x3_wgrad")
 
 
 def convT_wgrad_op(x: Feat, dout: Feat, dw_acc: torch.Tensor, k: int, splits: int = 0) -> Op:

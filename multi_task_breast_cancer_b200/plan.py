@@ -269,10 +269,21 @@ class Plan:
             if dy is None:
                 return blk
             acc = self._wg_accum(w, pk)
-            for f, off in zip(feats, pk["offs"]):
-                o = ops.conv3x3_wgrad_op(f, dy, acc, off)
+            o = None
+            if H % 16 == 0 and Wd % 8 == 0 and not os.environ.get("MTBC_NO_FUSED_WGRAD"):
+                try:   # one launch over every concat source: dy is read once per pixel tile
+                    o = ops.conv3x3_wgrad_multi_op(feats, dy, acc, pk["offs"])
+                except _lib.MtbcError:
+                    o = None
+            if o is not None:
                 self.tc_flops_bwd += o.flops
-                blk.append(_mk_op(o, 2.0 * N * H * Wd * Cout * f.C * 9, f"{name} wgrad {N}x{H}x{Wd} {f.C}x{Cout}"))
+                blk.append(_mk_op(o, 2.0 * N * H * Wd * Cout * Cin * 9,
+                                  f"{name} wgrad {N}x{H}x{Wd} {[f.C for f in feats]}x{Cout} fused"))
+            else:
+                for f, off in zip(feats, pk["offs"]):
+                    o = ops.conv3x3_wgrad_op(f, dy, acc, off)
+                    self.tc_flops_bwd += o.flops
+                    blk.append(_mk_op(o, 2.0 * N * H * Wd * Cout * f.C * 9, f"{name} wgrad {N}x{H}x{Wd} {f.C}x{Cout}"))
             self._mark_grad(w, b)
             self._emit_dgrad(blk, srcs, dy, w, pk, name, Cout)
             return blk

@@ -77,6 +77,14 @@ def test_conv3x3_wgrad(D, args):
     _run(D, D.conv_wgrad_case, *args)
 
 
+@pytest.mark.parametrize("args", [(2, 32, 32, [24], 24), (2, 32, 32, [24, 48], 24), (2, 64, 64, [24, 24, 24, 24, 48], 24),
+                                  (2, 32, 32, [48, 48, 48, 48], 48), (2, 16, 16, [96, 96, 192], 96),
+                                  (2, 16, 16, [384, 384, 384], 512), (3, 16, 24, [70, 33], 100)])
+def test_conv3x3_wgrad_fused_over_concat_sources(D, args):
+    """One launch reads dy once per pixel tile and accumulates every concat source's weight gradient."""
+    _run(D, D.conv_wgrad_multi_case, *args)
+
+
 @pytest.mark.parametrize("args", [(2, 16, 16, 64, 32), (2, 16, 16, 48, 48), (2, 8, 8, 384, 192), (4, 8, 8, 320, 320)])
 def test_conv_transpose_k2(D, args):
     _run(D, D.convT_case, *args)

@@ -176,6 +176,38 @@ def conv_wgrad_case(N, H, W, Cin, Cout, splits=0):
     run_case(fn, name)
 
 
+def conv_wgrad_multi_case(N, H, W, src_C, Cout):
+    """Weight gradient over a folded concat, all sources in one launch."""
+    name = f"conv3x3_wgrad_multi N{N} {H}x{W} {src_C}->{Cout}"
+
+    def fn():
+        xs = [rnd(N, c, H, W) for c in src_C]
+        dy = rnd(N, Cout, H, W)
+        xfs, dyf = [Feat.from_nchw(x) for x in xs], Feat.from_nchw(dy)
+        offs, ktot = ops.k_offsets(xfs)
+        acc = torch.zeros(9, dyf.Ck, ktot, device=dev)
+        ops.conv3x3_wgrad_multi_op(xfs, dyf, acc, offs).launch()
+        torch.cuda.synchronize()
+        Cin = sum(src_C)
+        grad = torch.zeros(Cout, Cin, 3, 3, device=dev)
+        c0 = 0
+        for c, off in zip(src_C, offs):
+            _lib.call("mtbc_unpack_conv_wgrad", ops.ptr(acc), acc.shape[1], acc.shape[2], off, ops.ptr(grad), Cout, Cin, 3,
+                      c0, c, 0, None)
+            c0 += c
+        torch.cuda.synchronize()
+        ref = torch.nn.grad.conv2d_weight(torch.cat(xs, 1), (Cout, Cin, 3, 3), dy, padding=1)
+        report(name, grad, ref)
+        # nothing may leak into the pad columns / rows of the accumulator
+        mask = torch.ones_like(acc, dtype=torch.bool)
+        for c, off in zip(src_C, offs):
+            mask[:, :Cout, off:off + c] = False
+        if mask.any():
+            report(name + " [pad entries zero]", acc[mask], torch.zeros_like(acc[mask]), tol=1e-6)
+
+    run_case(fn, name)
+
+
 def convT_case(N, H, W, Cin, Cout, k=2):
     name = f"convT k{k} N{N} {H}x{W} {Cin}->{Cout}"
 
