@@ -11,6 +11,7 @@
 #include <cuda.h>
 #include <vector>
 #include <string.h>
+#include <stdlib.h>
 
 namespace mtbc {
 
@@ -353,13 +354,18 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const __grid_constant__ Wgra
                           ntile * BN + b * p.b_kc, w0, h0, n0);
             if (++sb == kWgBStages) { sb = 0; pb ^= 1u; }
           }
-          mbar_wait(&s_aempty[sa], pa ^ 1u);
-          mbar_arrive_expect_tx(&s_afull[sa], static_cast<uint32_t>(a_nbox * p.a_box_bytes));
-          const CUtensorMap* am = &p.amap[p.t_aview[tap]];
-          for (int b = 0; b < a_nbox; ++b)
-            tma_load_4d(smem_a + sa * p.a_stage_bytes + b * p.a_box_bytes, am, &s_afull[sa], a_c0 + b * p.a_kc,
-                        w0 + p.t_adw[tap], h0 + p.t_adh[tap], n0);
-          if (++sa == kWgAStages) { sa = 0; pa ^= 1u; }
+          // the transposed conv reads the SAME x tile for its k*k taps: load it once per pixel tile
+          const bool need_a = (t == 0) || p.t_aview[tap] != p.t_aview[tap - 1] || p.t_adh[tap] != p.t_adh[tap - 1] ||
+                              p.t_adw[tap] != p.t_adw[tap - 1];
+          if (need_a) {
+            mbar_wait(&s_aempty[sa], pa ^ 1u);
+            mbar_arrive_expect_tx(&s_afull[sa], static_cast<uint32_t>(a_nbox * p.a_box_bytes));
+            const CUtensorMap* am = &p.amap[p.t_aview[tap]];
+            for (int b = 0; b < a_nbox; ++b)
+              tma_load_4d(smem_a + sa * p.a_stage_bytes + b * p.a_box_bytes, am, &s_afull[sa], a_c0 + b * p.a_kc,
+                          w0 + p.t_adw[tap], h0 + p.t_adh[tap], n0);
+            if (++sa == kWgAStages) { sa = 0; pa ^= 1u; }
+          }
         }
       }
     } else if (warp == 1 && elect_one()) {
@@ -369,7 +375,7 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const __grid_constant__ Wgra
       const uint32_t a_k16 = 2u * p.a_kc, b_k16 = 2u * p.b_kc;  // 16 pixel rows, in 16-byte units
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
-      int cur_b = -1;
+      int cur_b = -1, cur_a = -1;
       for (int pt = pt_begin; pt < pt_end; ++pt) {
         for (int t = 0; t < T; ++t) {
           const int tap = tapgroup * T + t;
@@ -382,17 +388,22 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const __grid_constant__ Wgra
             cur_b = sb;
             if (++sb == kWgBStages) { sb = 0; pb ^= 1u; }
           }
-          mbar_wait(&s_afull[sa], pa);
+          const bool need_a = (t == 0) || p.t_aview[tap] != p.t_aview[tap - 1] || p.t_adh[tap] != p.t_adh[tap - 1] ||
+                              p.t_adw[tap] != p.t_adw[tap - 1];
+          if (need_a) {
+            if (cur_a >= 0) umma_commit(&s_aempty[cur_a]);   // all MMAs reading the previous A stage have been issued
+            mbar_wait(&s_afull[sa], pa);
+            cur_a = sa;
+            if (++sa == kWgAStages) { sa = 0; pa ^= 1u; }
+          }
           tc_fence_after();
-          const uint32_t a_lo = umma_desc_lo(smem_u32(smem_a + sa * p.a_stage_bytes), p.a_box_bytes);
+          const uint32_t a_lo = umma_desc_lo(smem_u32(smem_a + cur_a * p.a_stage_bytes), p.a_box_bytes);
           const uint32_t b_lo = umma_desc_lo(smem_u32(smem_b + cur_b * p.b_stage_bytes), p.b_box_bytes);
           const uint32_t d_addr = tmem_base + static_cast<uint32_t>(t * BN);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {  // 128 pixels / 16
             umma_bf16_lohi(d_addr, a_lo + k * a_k16, a_hi, b_lo + k * b_k16, b_hi, idesc, (pt > pt_begin || k > 0) ? 1u : 0u);
           }
-          umma_commit(&s_aempty[sa]);
-          if (++sa == kWgAStages) { sa = 0; pa ^= 1u; }
         }
       }
       umma_commit(&s_accum);
@@ -540,7 +551,12 @@ int conv_gemm_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   p.tiles_w = d->W / TW; p.tiles_h = d->H / TH;
   const int tiles_n = (d->N + TN - 1) / TN;
   p.W = d->W; p.H = d->H; p.N = d->N;
-  const int BN = pick_bn(d->ncols, 256, 16);
+  // Transposed-conv forward (pixel-shuffle epilogue) is bound by its epilogue and by HBM writes, not by MMAs: N tiles of
+  // 128 leave TMEM and shared memory for two CTAs per SM, i.e. 16 epilogue warps instead of 8 (MTBC_CONVT_BN=256 restores
+  // the single 256-wide tile).
+  const char* bn_env = getenv("MTBC_CONVT_BN");
+  const int bn_cap = (d->epi_mode == 1 && !(bn_env && atoi(bn_env) == 256)) ? 128 : 256;
+  const int BN = pick_bn(d->ncols, bn_cap, 16);
   if (BN == 0) { delete op; return set_error(MTBC_ERR_INVALID, "conv_gemm: no N tile for ncols=%d", d->ncols); }
   p.BN = BN;
   p.tmem_cols = tmem_cols_for(2 * BN);

@@ -659,7 +659,12 @@ __global__ void __launch_bounds__(128) wgrad_halo_multi_kernel(const __grid_cons
   const uint32_t tmem_base = s_tmem;
 
   if (pt_end > pt_begin && nck > 0) {
-    if (warp == 0 && elect_one()) {
+    if (warp != 1 && elect_one()) {
+      // Three producer lanes (warps 0, 2, 3): a CTA's TMA box loads are served about one 64-byte row per 4 cycles when
+      // one lane issues them all; halving the CTAs per SM doubled this kernel's time, i.e. the limit is per issuing
+      // stream, so the boxes of a stage are spread over three lanes.  Warp 0 owns the barrier bookkeeping
+      // (arrive + expect_tx for the whole stage) and the dy box; the x boxes are dealt round-robin.
+      const int pw = warp == 0 ? 0 : warp - 1;   // 0, 1, 2
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t bytes = static_cast<uint32_t>(8 * kHaloH * p.b_kc * 2 + nck * (kHaloW * 16 * 64));
@@ -669,9 +674,11 @@ __global__ void __launch_bounds__(128) wgrad_halo_multi_kernel(const __grid_cons
         const int n = pt / (p.tiles_w * p.tiles_h);
         mbar_wait(&s_empty[stage], phase ^ 1u);
         uint8_t* b_dst = smem + stage * p.stage_bytes;
-        mbar_arrive_expect_tx(&s_full[stage], bytes);
-        tma_load_4d(b_dst, &p.bmap, &s_full[stage], ntile * p.b_kc, w0, h0 - 1, n);
-        for (int c = 0; c < nck; ++c)
+        if (pw == 0) {
+          mbar_arrive_expect_tx(&s_full[stage], bytes);
+          tma_load_4d(b_dst, &p.bmap, &s_full[stage], ntile * p.b_kc, w0, h0 - 1, n);
+        }
+        for (int c = pw; c < nck; c += 3)
           tma_load_4d(b_dst + p.b_bytes + c * p.a_bytes, &p.amap[p.c_view[c_begin + c]], &s_full[stage],
                       p.c_ch[c_begin + c], w0 - 1, h0, n);
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -1056,6 +1063,7 @@ int wgrad_halo_multi_create(const mtbc_wgrad_multi_desc* d, OpBase** out) {
     int maxs = (p.n_ptiles + 3) / 4; if (maxs < 1) maxs = 1;
     if (splits > maxs) splits = maxs;
   }
+  { const char* dv = getenv("MTBC_WGRAD_SPLIT_DIV"); if (dv && atoi(dv) > 1) splits = (splits + atoi(dv) - 1) / atoi(dv); }
   if (splits > p.n_ptiles) splits = p.n_ptiles;
   if (splits < 1) splits = 1;
   if (splits > 65535) splits = 65535;
