@@ -142,7 +142,11 @@ class Plan:
         self.fwd_arena = Arena(device, 1 << 20)   # InstanceNorm statistics (zeroed every forward)
         self.bwd_arena = Arena(device, 1 << 24)   # s1/s2, weight-gradient accumulators (zeroed every backward)
         self._keep: List[object] = []
-        self._scratch: Dict[Tuple, Feat] = {}
+        self._scratch: Dict[Tuple, List[Feat]] = {}
+        self._scratch_turn: Dict[Tuple, int] = {}
+        self._slot_readers: Dict[Tuple, List[Callable]] = {}   # dy slot -> side-stream launches that read it
+        self._cur_slot = None
+        self._dy_slot_of: Dict[int, Tuple] = {}
         self.tc_flops_fwd = 0.0
         self.tc_flops_bwd = 0.0
         # outputs (fp32, plan-owned static buffers) and their incoming gradients
@@ -178,12 +182,22 @@ class Plan:
         return t
 
     def scratch(self, N, H, W, Cc) -> Feat:
+        """Gradient-of-conv-output buffer (dy) for one backward block.  Buffers of one shape rotate (two by default) so
+        that a weight-gradient launch running on the side stream may still read the previous one while the next
+        layer's InstanceNorm backward writes the other; `self._slot_readers[slot]` remembers the side launches that read
+        a slot so the next writer can wait for exactly those."""
+        nbuf = max(1, int(os.environ.get("MTBC_DY_BUFFERS", "2")))
         key = (N, H, W, pitch_of(Cc))
         if os.environ.get("MTBC_DEBUG_UNIQUE_SCRATCH"):
             key = key + (len(self._scratch),)
-        if key not in self._scratch:
-            self._scratch[key] = Feat.empty(N, H, W, Cc, device=self.device)
-        f = self._scratch[key]
+        ring = self._scratch.setdefault(key, [])
+        turn = self._scratch_turn.get(key, 0)
+        self._scratch_turn[key] = turn + 1
+        if len(ring) < nbuf:
+            ring.append(Feat.empty(N, H, W, Cc, device=self.device))
+        idx = turn % len(ring) if len(ring) == nbuf else len(ring) - 1
+        f = ring[idx]
+        self._cur_slot = (key, idx)
         return Feat(f.t, Cc)
 
     def _padded_vec(self, name: Optional[str], Cp: int) -> Optional[torch.Tensor]:
@@ -196,6 +210,16 @@ class Plan:
         self.pack_jobs.add(_lib.JOB_COPY_F32, [n], p, buf)
         self._keep.append(buf)
         return buf
+
+    def _side(self, launch: Callable, dy: Optional[Feat] = None) -> Callable:
+        """Mark a weight-gradient launch as runnable on the side stream (it only feeds the accumulators that the
+        bucket unpack reads); if it reads a rotating dy buffer, register it as a reader of that slot."""
+        launch.side = True
+        if dy is not None:
+            slot = self._dy_slot_of.get(id(dy.t))
+            if slot is not None:
+                self._slot_readers.setdefault(slot, []).append(launch)
+        return launch
 
     def _mark_grad(self, *names):
         for n in names:
@@ -225,8 +249,8 @@ class Plan:
             dy = self._norm_act_bwd(blk, y, a, p, aux, gamma, beta, slope)
             if dy is None:
                 return blk
-            blk.append(_mk("mtbc_conv_first_wgrad", ptr(x_in), N, Cin, H, Wd, ptr(dy.t), dy.Cp, Cout,
-                           ptr(self.grad_view[w])))
+            blk.append(self._side(_mk("mtbc_conv_first_wgrad", ptr(x_in), N, Cin, H, Wd, ptr(dy.t), dy.Cp, Cout,
+                                      ptr(self.grad_view[w])), dy))
             self._mark_grad(w, b)  # bias grad of a conv followed by InstanceNorm is identically zero
             return blk
         self._bwd_blocks.append(backward)
@@ -277,13 +301,14 @@ class Plan:
                     o = None
             if o is not None:
                 self.tc_flops_bwd += o.flops
-                blk.append(_mk_op(o, 2.0 * N * H * Wd * Cout * Cin * 9,
-                                  f"{name} wgrad {N}x{H}x{Wd} {[f.C for f in feats]}x{Cout} fused"))
+                blk.append(self._side(_mk_op(o, 2.0 * N * H * Wd * Cout * Cin * 9,
+                                             f"{name} wgrad {N}x{H}x{Wd} {[f.C for f in feats]}x{Cout} fused"), dy))
             else:
                 for f, off in zip(feats, pk["offs"]):
                     o = ops.conv3x3_wgrad_op(f, dy, acc, off)
                     self.tc_flops_bwd += o.flops
-                    blk.append(_mk_op(o, 2.0 * N * H * Wd * Cout * f.C * 9, f"{name} wgrad {N}x{H}x{Wd} {f.C}x{Cout}"))
+                    blk.append(self._side(_mk_op(o, 2.0 * N * H * Wd * Cout * f.C * 9,
+                                                 f"{name} wgrad {N}x{H}x{Wd} {f.C}x{Cout}"), dy))
             self._mark_grad(w, b)
             self._emit_dgrad(blk, srcs, dy, w, pk, name, Cout)
             return blk
@@ -409,8 +434,11 @@ class Plan:
         self.debug[a.name + ".aux"] = (mean, rstd, gv, bv, s1, s2)
         dg = self.grad_view[gamma] if gamma else None
         db = self.grad_view[beta] if beta else None
-        blk.append(_mk("mtbc_in_bwd", ptr(a.g.t), ptr(y.feat.t), N, H * Wd, Cp, ptr(mean), ptr(rstd), ptr(gv), ptr(bv),
-                       C.c_float(slope), ptr(s1), ptr(s2), ptr(dy.t), ptr(dg), ptr(db), Cc, ptr(cnt)))
+        l = _mk("mtbc_in_bwd", ptr(a.g.t), ptr(y.feat.t), N, H * Wd, Cp, ptr(mean), ptr(rstd), ptr(gv), ptr(bv),
+                C.c_float(slope), ptr(s1), ptr(s2), ptr(dy.t), ptr(dg), ptr(db), Cc, ptr(cnt))
+        l.wait_side = self._slot_readers.pop(self._cur_slot, [])   # weight gradients still reading this dy buffer
+        self._dy_slot_of[id(dy.t)] = self._cur_slot
+        blk.append(l)
         self._mark_grad(gamma, beta)
         return dy
 
@@ -439,7 +467,7 @@ class Plan:
             acc = self.bwd_arena.alloc(k * k, cp, f.Ck)
             o = ops.convT_wgrad_op(f, out.g, acc, k)
             self.tc_flops_bwd += o.flops
-            blk.append(_mk_op(o, t_flops, f"{name} convT wgrad {f.N}x{f.H}x{f.W} {Cin}->{Cout}"))
+            blk.append(self._side(_mk_op(o, t_flops, f"{name} convT wgrad {f.N}x{f.H}x{f.W} {Cin}->{Cout}")))
             self.unpack_jobs.add(_lib.JOB_UNPACK_CONVT, [k * k * cp, f.Ck, Cin, Cout, k, 0], acc, self.grad_view[w],
                                  owner=w)
             self._late_unpacked.append(w)
@@ -629,8 +657,12 @@ class Plan:
         def flush(i):
             for k in range(nb):
                 if not emitted[k] and ready[k] <= i:
-                    out.extend(self.unpack_jobs.launch(jobs_of[k]))
-                    out.append(_mk_marker(k))
+                    for ul in self.unpack_jobs.launch(jobs_of[k]):
+                        ul.wait_side = "all"       # the accumulators it reads are written by side-stream launches
+                        out.append(ul)
+                    mk = _mk_marker(k)
+                    mk.wait_side = "all"           # (a bucket without unpack jobs may still hold first-layer grads)
+                    out.append(mk)
                     done_after[k] = len(out)
                     emitted[k] = True
         flush(0)

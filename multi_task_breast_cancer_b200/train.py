@@ -72,6 +72,9 @@ class TrainStep:
             self._build_launches()
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.comm_stream: Optional[torch.cuda.Stream] = None
+        self.side_stream: Optional[torch.cuda.Stream] = None
+        import os as _os2
+        self.side_enabled = _os2.environ.get("MTBC_SIDE_WGRAD", "1") != "0"
         self.seg_graphs = None   # data parallel: [(CUDAGraph, bucket index or None)] + opt_graph
         self.opt_graph = None
         import os as _os
@@ -135,9 +138,42 @@ class TrainStep:
         return sum(1 for l in self.launches_fb + self.launches_opt if l.kind != "bucket_ready")
 
     def _run_list(self, launches):
-        st = C.c_void_p(stream_ptr())
+        """Launch a list on the current stream.  Launches marked `side` (weight gradients: they only feed accumulators
+        read by the bucket unpack) are forked onto a second stream so they overlap the HBM-bound InstanceNorm backward
+        and the data gradients of the following layers; `wait_side` on a launch lists the side launches it must not
+        overtake (a rotating dy buffer about to be overwritten) or "all".  Same code eagerly and under graph capture."""
+        main = torch.cuda.current_stream(self.device)
+        st = C.c_void_p(main.cuda_stream)
+        if not self.side_enabled:
+            for l in launches:
+                l(st)
+            return
+        if self.side_stream is None:
+            self.side_stream = torch.cuda.Stream(device=self.device)
+        side = self.side_stream
+        sst = C.c_void_p(side.cuda_stream)
+        used = False
         for l in launches:
+            if getattr(l, "side", False):
+                side.wait_stream(main)
+                l(sst)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                l.done_event = ev
+                used = True
+                continue
+            ws = getattr(l, "wait_side", None)
+            if ws == "all":
+                if used:
+                    main.wait_stream(side)
+            elif ws:
+                for dep in ws:
+                    ev = getattr(dep, "done_event", None)
+                    if ev is not None:
+                        main.wait_event(ev)
             l(st)
+        if used:
+            main.wait_stream(side)
 
     def _segments(self):
         """launches_fb split at the bucket markers: [(launches, bucket index or None)]."""
