@@ -44,6 +44,7 @@ struct ConvHaloParams {
   int32_t nsrc, nouts;
   int32_t W, H, N, tiles_w, tiles_h, n_mtiles;
   int32_t BN, tmem_cols, stages, a_stage_bytes, b_tap_bytes, b_total_bytes;
+  int32_t lanes;          // MMA-issuing lanes (2: alternate tiles on two accumulators; MTBC_HALO_LANES=1: one)
   int32_t dbg;            // debug (MTBC_HALO_DBG=1): accumulate the MMA lane's cycle breakdown into g_halo_dbg
   int32_t late_release;   // debug (MTBC_HALO_LATE_RELEASE=1): hand the accumulator back after the stores, not before
   int32_t G, bn1;   // G = output rows stacked along N (1 or 2); bn1 = columns per output pixel; BN = G * bn1
@@ -307,7 +308,7 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
 // MINB = resident CTAs per SM the register budget is compiled for: 2 for the narrow layers (small resident weights, two
 // CTAs overlap each other's pipeline bubbles), 1 for wide N tiles (no spills, one CTA owns the SM).
 template <int MINB, int P>
-__global__ void __launch_bounds__(64 + 128 * P, MINB) conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
+__global__ void __launch_bounds__((MINB == 2 ? 64 : 96) + 128 * P, MINB) conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   constexpr int kEpiWarps = 4 * P;
   constexpr int kEpiThreads = kEpiWarps * 32;
   extern __shared__ uint8_t smem_raw[];
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(64 + 128 * P, MINB) conv_halo_kernel(const __g
   __shared__ __align__(16) float s_bias[256];
   __shared__ float s_part[4][2][256];  // [lane quarter][sum|sumsq][col]: per-warp column partials at a flush
   __shared__ HaloChunk s_chunk[16];    // destination of every 16-column chunk of this CTA's N tile
-  __shared__ uint32_t s_cb[64];        // MMA lane's chunk schedule: weight-block descriptor (low word) | 64-wide flag
+  __shared__ uint32_t s_cb[2][64];     // MMA lanes' chunk schedule: weight-block descriptor (low word) | 64-wide flag
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(64 + 128 * P, MINB) conv_halo_kernel(const __g
   const int t_end = static_cast<int>(static_cast<int64_t>(p.n_mtiles) * (blockIdx.x + 1) / gridDim.x);
 
   const int bn1 = p.bn1;
-  for (int i = tid; i < 256; i += 64 + kEpiThreads)
+  for (int i = tid; i < 256; i += blockDim.x)
     s_bias[i] = (p.bias != nullptr && i < BN) ? p.bias[ntile * bn1 + (i % bn1)] : 0.f;
   if (tid < (BN >> 4)) {
     const int lc = tid * 16;                      // column inside the accumulator
@@ -398,13 +399,17 @@ __global__ void __launch_bounds__(64 + 128 * P, MINB) conv_halo_kernel(const __g
         }
       }
     }
-  } else if (warp == 1) {
-    if (elect_one()) {
-      // ------------------------------------------------------------ MMA issuer
-      // This single lane is the critical path of the narrow layers: the tensor pipe only queues a few instructions,
-      // so every scalar instruction between two MMAs is pipe idle time (tools/diag_halo_dbg.py).  The per-tile chunk
-      // schedule is therefore a flat table in shared memory (weight-block descriptor + chunk width per chunk) built
-      // once, the ring slot address advances by one add, and parameters live in registers.
+  } else if (warp == 1 || warp == 2 + kEpiWarps) {
+    // ------------------------------------------------------------ MMA issuers
+    // TWO issuing lanes (warp 1 and the last warp) on alternating tiles, each with its own TMEM accumulator.  A single
+    // lane spends ~45 % of a narrow-layer tile in tcgen05.commit, mbarrier round trips and loop overhead while the
+    // tensor pipe -- which only queues a few instructions -- idles (tools/diag_halo_dbg.py); with two lanes the pipe is
+    // fed by one while the other sits in its overhead.  The chunk ring is consumed in tile order, so lane L takes the
+    // chunks of tiles it = L, L + 2, ... and skips the other lane's.  The per-tile chunk schedule is a flat table in
+    // shared memory built once (weight-block descriptor + chunk width per chunk).
+    const int L = warp == 1 ? 0 : 1;
+    const int nlanes = p.lanes;
+    if (L < nlanes && elect_one()) {
       const uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
       const uint32_t idesc1 = umma_idesc_bf16(128, bn1, 0, 0);
       const uint32_t b_tap16 = static_cast<uint32_t>(p.b_tap_bytes) >> 4;
@@ -415,22 +420,25 @@ __global__ void __launch_bounds__(64 + 128 * P, MINB) conv_halo_kernel(const __g
         const uint32_t blk = static_cast<uint32_t>(bn1 * sc.kc * 2);
         for (int ch = 0; ch < sc.nchunk; ++ch, ++nch) {
           const uint32_t off = g2 ? 3 * (sc.b_off + ch * blk) : (sc.b_off + ch * blk);
-          s_cb[nch] = umma_desc_lo(smem_u32(smem_b) + off, 16) | (sc.kc == 64 ? 0x80000000u : 0u);   // bit 31: 64-wide
+          s_cb[L][nch] = umma_desc_lo(smem_u32(smem_b) + off, 16) | (sc.kc == 64 ? 0x80000000u : 0u);   // bit 31: 64-wide
         }
       }
       mbar_wait(&s_bfull, 0);
       const int nstages = p.stages;
       const uint32_t a_step16 = static_cast<uint32_t>(p.a_stage_bytes) >> 4;
       const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem_a), 16);
-      uint32_t a_lo = a_lo0;
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      const bool dbg = (p.dbg & 1) && blockIdx.x == 0 && blockIdx.y == 0;
+      auto skip = [&](int n) {   // advance the ring position over n chunks (the other lane's tile)
+        stage += n;
+        while (stage >= nstages) { stage -= nstages; phase ^= 1u; }
+      };
+      if (L == 1) skip(nch);
+      const bool dbg = (p.dbg & 1) && blockIdx.x == 0 && blockIdx.y == 0 && L == 0;
       const bool no_mma = (p.dbg & 2) != 0;
-      long long c_acc = 0, c_data = 0, c_issue = 0, c_commit = 0, n_chunks = 0;
+      long long c_acc = 0, c_data = 0, c_issue = 0, c_commit = 0, n_chunks = 0, n_tiles = 0;
       const long long c_start = dbg ? clock64() : 0;
-      for (int t = t_begin; t < t_end; ++t, ++it) {
+      for (int it = L; t_begin + it < t_end; it += nlanes) {
         const int buf = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         long long t0 = dbg ? clock64() : 0;
@@ -439,13 +447,14 @@ __global__ void __launch_bounds__(64 + 128 * P, MINB) conv_halo_kernel(const __g
         if (dbg) { const long long t1 = clock64(); c_acc += t1 - t0; }
         const uint32_t d_addr = tmem_base + static_cast<uint32_t>(buf * BN);
         uint32_t accumulate = 0;
+        uint32_t a_lo = a_lo0 + stage * a_step16;
 #pragma unroll 1
         for (int c = 0; c < nch; ++c) {
           if (dbg) t0 = clock64();
           mbar_wait(&s_afull[stage], phase);   // TMA data: the mbarrier acquire is all the MMA needs
           long long t1 = 0;
           if (dbg) { t1 = clock64(); c_data += t1 - t0; }
-          const uint32_t cb = s_cb[c];
+          const uint32_t cb = s_cb[L][c];
           const uint32_t b_lo = cb & 0x7fffffffu;
           if (no_mma) {
             // debug: no MMAs
@@ -465,10 +474,12 @@ __global__ void __launch_bounds__(64 + 128 * P, MINB) conv_halo_kernel(const __g
           if (++stage == nstages) { stage = 0; phase ^= 1u; a_lo = a_lo0; }
         }
         umma_commit(&s_accfull[buf]);
+        if (nlanes == 2) skip(nch);
+        ++n_tiles;
       }
       if (dbg) {
         g_halo_dbg[0] += c_acc; g_halo_dbg[1] += c_data; g_halo_dbg[2] += c_issue; g_halo_dbg[3] += c_commit;
-        g_halo_dbg[4] += it; g_halo_dbg[5] += n_chunks; g_halo_dbg[6] += clock64() - c_start;
+        g_halo_dbg[4] += n_tiles; g_halo_dbg[5] += n_chunks; g_halo_dbg[6] += clock64() - c_start;
       }
     }
   } else {
@@ -759,9 +770,10 @@ struct ConvHaloOp : public OpBase {
   int ctas_per_sm = 1;
   int epi_parts = 2;
   int launch(cudaStream_t st) override {
-    if (epi_parts == 4) conv_halo_kernel<1, 4><<<grid, 64 + 512, smem_bytes, st>>>(p);
+    // two CTAs per SM: the other CTA's MMA lane already feeds the pipe, one lane each (and no extra warp: registers)
+    if (epi_parts == 4) conv_halo_kernel<1, 4><<<grid, 96 + 512, smem_bytes, st>>>(p);
     else if (ctas_per_sm == 2) conv_halo_kernel<2, 2><<<grid, 64 + 256, smem_bytes, st>>>(p);
-    else conv_halo_kernel<1, 2><<<grid, 64 + 256, smem_bytes, st>>>(p);
+    else conv_halo_kernel<1, 2><<<grid, 96 + 256, smem_bytes, st>>>(p);
     return check_launch("conv_halo_kernel");
   }
   double op_flops() const override { return flops; }
@@ -843,6 +855,7 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   p.G = G; p.bn1 = BN;
   { const char* lr = getenv("MTBC_HALO_LATE_RELEASE"); p.late_release = (lr && lr[0] == '1') ? 1 : 0; }
   { const char* dg = getenv("MTBC_HALO_DBG"); p.dbg = dg ? atoi(dg) : 0; }
+  { const char* ln = getenv("MTBC_HALO_LANES"); p.lanes = (ln && ln[0] == '1') ? 1 : 2; }
   const int halo_h = 16 * G + 2;
   int kcmax = 32, b_off = 0;
   bool use32 = false, use64 = false;
@@ -910,6 +923,22 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
         op->ctas_per_sm = 1;
       }
       op->epi_parts = 4;
+    }
+  }
+  // Two MMA lanes only when the ring holds a whole number of lane PAIRS of tiles (stages % (2 * chunks per tile) == 0):
+  // each lane then revisits only ring slots whose previous fill it consumed itself, so its one-bit mbarrier parity can
+  // never be a lap ahead of the barrier (a lane that skips the other lane's chunks could otherwise pass a wait on a
+  // slot whose previous fill has not even landed).  Otherwise, and with two CTAs per SM, one lane.
+  if (ctas_per_sm == 2) {
+    p.lanes = 1;
+  } else if (p.lanes == 2) {
+    const int pair = 2 * total_chunks;
+    const int s2 = (p.stages / pair) * pair;
+    if (s2 >= pair) {
+      p.stages = s2;
+      op->smem_bytes = p.b_total_bytes + s2 * p.a_stage_bytes + 1024;
+    } else {
+      p.lanes = 1;
     }
   }
   int gx = sm_count() * ctas_per_sm;
