@@ -41,6 +41,31 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return u;
 }
 
+// Packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 on sm_100): these streaming kernels need about half of the SM's issue
+// slots at HBM speed, so halving the FMA / MUL / ADD instruction count is bandwidth (tools/bench_stream.py).
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
+      "l"(*reinterpret_cast<unsigned long long*>(&b)), "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
+      "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
+      "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+// bf16x2 word -> two fp32 (a bf16 is the upper half of an fp32: one shift, one mask)
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t u) {
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+
 struct PipeGeom {
   int64_t sample_vecs;      // HW * cvec: 16-byte vectors per sample
   int32_t tiles_per_sample; // ceil(sample_vecs / tile_vecs)
@@ -162,8 +187,10 @@ struct ApplyBody {
   float *mean, *rstd;
   int Cp, cvec;
   float inv_hw, eps, slope;
-  float sc[8], sh[8], m[8], r[8];
+  float2 sc[4], sh[4];
+  float m[8], r[8];
   __device__ __forceinline__ void begin_sample(int n, int v) {
+    float scs[8], shs[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int ch = v * 8 + k;
@@ -173,10 +200,12 @@ struct ApplyBody {
       const float rs = rsqrtf(var + eps);
       const float gg = gamma ? gamma[ch] : 1.f;
       const float bb = beta ? beta[ch] : 0.f;
-      sc[k] = rs * gg;
-      sh[k] = bb - mu * rs * gg;
+      scs[k] = rs * gg;
+      shs[k] = bb - mu * rs * gg;
       m[k] = mu; r[k] = rs;
     }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { sc[k] = make_float2(scs[2 * k], scs[2 * k + 1]); sh[k] = make_float2(shs[2 * k], shs[2 * k + 1]); }
   }
   __device__ __forceinline__ void tile0(int n, int v, int tid) {
     if (tid < cvec) {
@@ -188,19 +217,21 @@ struct ApplyBody {
     }
   }
   __device__ __forceinline__ void vec(const uint4 (&in)[1], uint4& out) {
-    float x[8], o[8];
-    unpack8(in[0], x);
+    const uint32_t w[4] = {in[0].x, in[0].y, in[0].z, in[0].w};
+    uint32_t o[4];
+    const float2 sl = make_float2(slope, slope);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float z = fmaf(x[k], sc[k], sh[k]);
-      o[k] = z > 0.f ? z : z * slope;
+    for (int k = 0; k < 4; ++k) {
+      const float2 z = ffma2(bf2_to_f2(w[k]), sc[k], sh[k]);
+      const float2 zs = fmul2(z, sl);                       // LeakyReLU, 0 < slope < 1: max(z, slope * z)
+      o[k] = pack_bf16x2(fmaxf(z.x, zs.x), fmaxf(z.y, zs.y));
     }
-    out = pack8(o);
+    out = make_uint4(o[0], o[1], o[2], o[3]);
   }
   __device__ __forceinline__ void end_sample(int, int) {}
 };
 
-__global__ void __launch_bounds__(kPipeMaxThreads + 32, 3)
+__global__ void __launch_bounds__(kPipeMaxThreads + 32, 2)
 in_apply_pipe_kernel(PipeGeom g, const __nv_bfloat16* __restrict__ y, const float* __restrict__ ssum,
                      const float* __restrict__ ssq, const float* __restrict__ gamma, const float* __restrict__ beta,
                      float inv_hw, float eps, float slope, __nv_bfloat16* __restrict__ a, float* __restrict__ mean,
@@ -221,64 +252,83 @@ in_apply_pipe_kernel(PipeGeom g, const __nv_bfloat16* __restrict__ y, const floa
 struct BwdReduceBody {
   const float *mean, *rstd, *gamma, *beta;
   float *s1, *s2;
-  float* s_acc;   // shared [2][Cp]
+  float* s_stage;   // shared [16][kPipeMaxThreads]: per-thread partials parked for the block reduction
   int Cp, cvec, nactive;
   float slope;
-  float A[8], B[8], zc[8], zd[8], a1[8], a2[8];
+  // s2 = sum gg * xh with xh = x*A + B  ==  A * sum(gg * x) + B * sum(gg): only sum(gg) and sum(gg * x) are accumulated
+  float2 zc[4], zd[4], a1[4], ax[4];
+  float A[8], B[8];
   __device__ __forceinline__ void begin_sample(int n, int v) {
+    float zcs[8], zds[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int ch = v * 8 + k;
       const float mu = mean[static_cast<int64_t>(n) * Cp + ch], rs = rstd[static_cast<int64_t>(n) * Cp + ch];
       const float gg = gamma ? gamma[ch] : 1.f, bb = beta ? beta[ch] : 0.f;
-      A[k] = rs; B[k] = -mu * rs; zc[k] = gg * rs; zd[k] = fmaf(gg, -mu * rs, bb);
-      a1[k] = 0.f; a2[k] = 0.f;
+      A[k] = rs; B[k] = -mu * rs; zcs[k] = gg * rs; zds[k] = fmaf(gg, -mu * rs, bb);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      zc[k] = make_float2(zcs[2 * k], zcs[2 * k + 1]); zd[k] = make_float2(zds[2 * k], zds[2 * k + 1]);
+      a1[k] = make_float2(0.f, 0.f); ax[k] = make_float2(0.f, 0.f);
     }
   }
   __device__ __forceinline__ void tile0(int, int, int) {}
   __device__ __forceinline__ void vec(const uint4 (&in)[2], uint4&) {
-    float g[8], x[8];
-    unpack8(in[0], g);
-    unpack8(in[1], x);
+    const uint32_t gw[4] = {in[0].x, in[0].y, in[0].z, in[0].w};
+    const uint32_t xw[4] = {in[1].x, in[1].y, in[1].z, in[1].w};
+    const float2 sl = make_float2(slope, slope);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float xh = fmaf(x[k], A[k], B[k]);
-      const float z = fmaf(x[k], zc[k], zd[k]);
-      const float gg = z > 0.f ? g[k] : g[k] * slope;
-      a1[k] += gg;
-      a2[k] = fmaf(gg, xh, a2[k]);
+    for (int k = 0; k < 4; ++k) {
+      const float2 x = bf2_to_f2(xw[k]), g = bf2_to_f2(gw[k]);
+      const float2 z = ffma2(x, zc[k], zd[k]);
+      const float2 gs = fmul2(g, sl);
+      const float2 gg = make_float2(z.x > 0.f ? g.x : gs.x, z.y > 0.f ? g.y : gs.y);
+      a1[k] = fadd2(a1[k], gg);
+      ax[k] = ffma2(gg, x, ax[k]);
     }
   }
+  // Block reduction without shared-memory atomics: with a dense 24-channel tensor 85 threads share each channel and
+  // 255 x 16 contended atomicAdds cost several microseconds per sample.  Every thread parks its 16 partials in
+  // s_stage[k][thread]; one thread per (sum, channel) then adds the rows that belong to its channel group.
   __device__ __forceinline__ void end_sample(int n, int v) {
     const int ctid = threadIdx.x - 32, nc = blockDim.x - 32;
-    for (int i = ctid; i < 2 * Cp; i += nc) s_acc[i] = 0.f;
-    consumer_sync(nc);
+    (void)v;
     if (ctid < nactive) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { atomicAdd(&s_acc[v * 8 + k], a1[k]); atomicAdd(&s_acc[Cp + v * 8 + k], a2[k]); }
+      for (int k = 0; k < 4; ++k) {
+        s_stage[(2 * k) * kPipeMaxThreads + ctid] = a1[k].x;
+        s_stage[(2 * k + 1) * kPipeMaxThreads + ctid] = a1[k].y;
+        s_stage[(8 + 2 * k) * kPipeMaxThreads + ctid] = fmaf(A[2 * k], ax[k].x, B[2 * k] * a1[k].x);
+        s_stage[(9 + 2 * k) * kPipeMaxThreads + ctid] = fmaf(A[2 * k + 1], ax[k].y, B[2 * k + 1] * a1[k].y);
+      }
     }
     consumer_sync(nc);
-    for (int i = ctid; i < Cp; i += nc) {
-      atomicAdd(s1 + static_cast<int64_t>(n) * Cp + i, s_acc[i]);
-      atomicAdd(s2 + static_cast<int64_t>(n) * Cp + i, s_acc[Cp + i]);
+    for (int col = ctid; col < 2 * Cp; col += nc) {
+      const int which = col >= Cp ? 1 : 0;
+      const int ch = col - which * Cp;
+      const float* row = s_stage + (which * 8 + (ch & 7)) * kPipeMaxThreads;
+      float sum = 0.f;
+      for (int r = ch >> 3; r < nactive; r += cvec) sum += row[r];
+      atomicAdd((which ? s2 : s1) + static_cast<int64_t>(n) * Cp + ch, sum);
     }
     consumer_sync(nc);
   }
 };
 
-__global__ void __launch_bounds__(kPipeMaxThreads + 32, 3)
+__global__ void __launch_bounds__(kPipeMaxThreads + 32, 2)
 in_bwd_reduce_pipe_kernel(PipeGeom g, const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ y,
                           const float* __restrict__ mean, const float* __restrict__ rstd,
                           const float* __restrict__ gamma, const float* __restrict__ beta, float slope,
                           float* __restrict__ s1, float* __restrict__ s2) {
   extern __shared__ __align__(128) uint8_t pipe_smem[];
   __shared__ uint64_t s_full[kPipeMaxStages], s_empty[kPipeMaxStages];
-  __shared__ float s_acc[2 * 512];
+  __shared__ float s_stage[16 * kPipeMaxThreads];
   BwdReduceBody b;
-  b.mean = mean; b.rstd = rstd; b.gamma = gamma; b.beta = beta; b.s1 = s1; b.s2 = s2; b.s_acc = s_acc;
+  b.mean = mean; b.rstd = rstd; b.gamma = gamma; b.beta = beta; b.s1 = s1; b.s2 = s2; b.s_stage = s_stage;
   b.Cp = g.Cp; b.cvec = g.cvec; b.slope = slope; b.nactive = g.tile_vecs / kPipeVPT;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { b.a1[k] = 0.f; b.a2[k] = 0.f; }
+  for (int k = 0; k < 4; ++k) { b.a1[k] = make_float2(0.f, 0.f); b.ax[k] = make_float2(0.f, 0.f); }
   const __nv_bfloat16* const ins[2] = {dA, y};
   pipe_run<2, false>(g, ins, nullptr, b, pipe_smem, s_full, s_empty);
 }
@@ -287,8 +337,9 @@ struct BwdApplyBody {
   const float *mean, *rstd, *gamma, *beta, *s1, *s2;
   int Cp, cvec;
   float slope, inv_hw;
-  float zc[8], zd[8], rg[8], c0[8], c1[8];
+  float2 zc[4], zd[4], rg[4], c0[4], c1[4];
   __device__ __forceinline__ void begin_sample(int n, int v) {
+    float t[5][8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int ch = v * 8 + k;
@@ -297,29 +348,39 @@ struct BwdApplyBody {
       const float gg = gamma ? gamma[ch] : 1.f, bb = beta ? beta[ch] : 0.f;
       const float m1 = s1[o] * inv_hw, m2 = s2[o] * inv_hw;
       const float Bk = -mu * rs;
-      zc[k] = gg * rs; zd[k] = fmaf(gg, Bk, bb);
-      rg[k] = rs * gg;
-      c1[k] = -rg[k] * m2 * rs;
-      c0[k] = -rg[k] * fmaf(m2, Bk, m1);
+      t[0][k] = gg * rs; t[1][k] = fmaf(gg, Bk, bb);
+      t[2][k] = rs * gg;
+      t[4][k] = -t[2][k] * m2 * rs;
+      t[3][k] = -t[2][k] * fmaf(m2, Bk, m1);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      zc[k] = make_float2(t[0][2 * k], t[0][2 * k + 1]); zd[k] = make_float2(t[1][2 * k], t[1][2 * k + 1]);
+      rg[k] = make_float2(t[2][2 * k], t[2][2 * k + 1]); c0[k] = make_float2(t[3][2 * k], t[3][2 * k + 1]);
+      c1[k] = make_float2(t[4][2 * k], t[4][2 * k + 1]);
     }
   }
   __device__ __forceinline__ void tile0(int, int, int) {}
   __device__ __forceinline__ void vec(const uint4 (&in)[2], uint4& out) {
-    float g[8], x[8], o[8];
-    unpack8(in[0], g);
-    unpack8(in[1], x);
+    const uint32_t gw[4] = {in[0].x, in[0].y, in[0].z, in[0].w};
+    const uint32_t xw[4] = {in[1].x, in[1].y, in[1].z, in[1].w};
+    uint32_t o[4];
+    const float2 sl = make_float2(slope, slope);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float z = fmaf(x[k], zc[k], zd[k]);
-      const float gg = z > 0.f ? g[k] : g[k] * slope;
-      o[k] = fmaf(rg[k], gg, fmaf(c1[k], x[k], c0[k]));
+    for (int k = 0; k < 4; ++k) {
+      const float2 x = bf2_to_f2(xw[k]), g = bf2_to_f2(gw[k]);
+      const float2 z = ffma2(x, zc[k], zd[k]);
+      const float2 gs = fmul2(g, sl);
+      const float2 gg = make_float2(z.x > 0.f ? g.x : gs.x, z.y > 0.f ? g.y : gs.y);
+      const float2 r = ffma2(rg[k], gg, ffma2(c1[k], x, c0[k]));
+      o[k] = pack_bf16x2(r.x, r.y);
     }
-    out = pack8(o);
+    out = make_uint4(o[0], o[1], o[2], o[3]);
   }
   __device__ __forceinline__ void end_sample(int, int) {}
 };
 
-__global__ void __launch_bounds__(kPipeMaxThreads + 32, 3)
+__global__ void __launch_bounds__(kPipeMaxThreads + 32, 2)
 in_bwd_apply_pipe_kernel(PipeGeom g, const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ y,
                          const float* __restrict__ mean, const float* __restrict__ rstd,
                          const float* __restrict__ gamma, const float* __restrict__ beta, float slope, float inv_hw,
@@ -573,27 +634,31 @@ struct ChanSumBody {
   __device__ __forceinline__ void end_sample(int, int) {}   // sums run over all samples: flushed once by the kernel
 };
 
-__global__ void __launch_bounds__(kPipeMaxThreads + 32, 3)
+__global__ void __launch_bounds__(kPipeMaxThreads + 32, 2)
 channel_sum_pipe_kernel(PipeGeom g, const __nv_bfloat16* __restrict__ t, int C_true, float* __restrict__ out) {
   extern __shared__ __align__(128) uint8_t pipe_smem[];
   __shared__ uint64_t s_full[kPipeMaxStages], s_empty[kPipeMaxStages];
-  __shared__ float s_acc[512];
+  __shared__ float s_stage[8 * kPipeMaxThreads];
   ChanSumBody b;
-  b.out = out; b.s_acc = s_acc; b.Cp = g.Cp; b.C_true = C_true; b.started = true;
+  b.out = out; b.s_acc = s_stage; b.Cp = g.Cp; b.C_true = C_true; b.started = true;
 #pragma unroll
   for (int k = 0; k < 8; ++k) b.a[k] = 0.f;
   const __nv_bfloat16* const ins[1] = {t};
-  for (int i = threadIdx.x; i < g.Cp; i += blockDim.x) s_acc[i] = 0.f;
-  pipe_run<1, false>(g, ins, nullptr, b, pipe_smem, s_full, s_empty);   // starts with a __syncthreads: s_acc is zero
+  pipe_run<1, false>(g, ins, nullptr, b, pipe_smem, s_full, s_empty);
   if (threadIdx.x < 32) return;   // producer warp is done; consumers only from here
   const int ctid = threadIdx.x - 32, nc = blockDim.x - 32;
-  if (ctid < g.tile_vecs / kPipeVPT) {
-    const int v = ctid % g.cvec;
+  const int nactive = g.tile_vecs / kPipeVPT;
+  if (ctid < nactive) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) atomicAdd(&s_acc[v * 8 + k], b.a[k]);
+    for (int k = 0; k < 8; ++k) s_stage[k * kPipeMaxThreads + ctid] = b.a[k];
   }
   consumer_sync(nc);
-  for (int i = ctid; i < C_true; i += nc) atomicAdd(out + i, s_acc[i]);
+  for (int ch = ctid; ch < C_true; ch += nc) {
+    const float* row = s_stage + (ch & 7) * kPipeMaxThreads;
+    float sum = 0.f;
+    for (int r = ch >> 3; r < nactive; r += g.cvec) sum += row[r];
+    atomicAdd(out + ch, sum);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
