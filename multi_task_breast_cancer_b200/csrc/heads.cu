@@ -33,58 +33,80 @@ __global__ void __launch_bounds__(256) head1x1_fwd_kernel(const __nv_bfloat16* _
 }
 
 // dA[pix][c] (+)= dl[pix]*w[c];  dw[c] += sum_pix dl[pix]*a[pix][c];  db += sum_pix dl[pix]
+// Four independent 16-byte vectors per thread and iteration (loads issued before use), block reduction through a
+// parked-partials table instead of contended shared-memory atomics (see stream_pipe.cu).
 __global__ void __launch_bounds__(256) head1x1_bwd_kernel(const __nv_bfloat16* __restrict__ a,
                                                           const float* __restrict__ dl, int64_t npix, int Cp, int C,
                                                           const float* __restrict__ w, __nv_bfloat16* __restrict__ dA,
                                                           int accumulate, float* __restrict__ dw,
                                                           float* __restrict__ db) {
-  extern __shared__ float s_acc[];  // [Cp + 1]
+  __shared__ float s_stage[9 * 256];   // [k][thread]: 8 channel partials + the bias partial
   const int cvec = Cp / 8;
-  for (int i = threadIdx.x; i <= Cp; i += blockDim.x) s_acc[i] = 0.f;
-  __syncthreads();
+  const int bd = blockDim.x;
   const int64_t total = npix * cvec;
-  const int64_t start = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x, stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t start = static_cast<int64_t>(blockIdx.x) * bd + threadIdx.x, stride = static_cast<int64_t>(gridDim.x) * bd;
   const int v = static_cast<int>(start % cvec);
   float wv[8], acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, accb = 0.f;
 #pragma unroll
   for (int k = 0; k < 8; ++k) wv[k] = (v * 8 + k) < C ? w[v * 8 + k] : 0.f;
-  for (int64_t i = start; i < total; i += stride) {
-    const int64_t pix = i / cvec;
-    const float g = dl[pix];
-    const uint4 u = *reinterpret_cast<const uint4*>(a + i * 8);
-    const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
-    float o[8];
+  constexpr int U = 4;
+  for (int64_t i0 = start; i0 < total; i0 += U * stride) {
+    uint4 u[U], q[U];
+    float g[U];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 f = unpack_bf16x2(uu[k]);
-      acc[2 * k] = fmaf(g, f.x, acc[2 * k]);
-      acc[2 * k + 1] = fmaf(g, f.y, acc[2 * k + 1]);
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = g * wv[k];
-    if (accumulate) {
-      const uint4 q = *reinterpret_cast<const uint4*>(dA + i * 8);
-      const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = unpack_bf16x2(qq[k]);
-        o[2 * k] += f.x;
-        o[2 * k + 1] += f.y;
+    for (int j = 0; j < U; ++j) {
+      const int64_t i = i0 + j * stride;
+      if (i < total) {
+        u[j] = *reinterpret_cast<const uint4*>(a + i * 8);
+        g[j] = dl[i / cvec];
+        if (accumulate) q[j] = *reinterpret_cast<const uint4*>(dA + i * 8);
       }
     }
-    uint4 r;
-    r.x = pack_bf16x2(o[0], o[1]); r.y = pack_bf16x2(o[2], o[3]); r.z = pack_bf16x2(o[4], o[5]); r.w = pack_bf16x2(o[6], o[7]);
-    *reinterpret_cast<uint4*>(dA + i * 8) = r;
-    if (v == 0) accb += g;
-  }
-  if (start < total) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) atomicAdd(&s_acc[v * 8 + k], acc[k]);
-    if (v == 0) atomicAdd(&s_acc[Cp], accb);
+    for (int j = 0; j < U; ++j) {
+      const int64_t i = i0 + j * stride;
+      if (i >= total) break;
+      const uint32_t uu[4] = {u[j].x, u[j].y, u[j].z, u[j].w};
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16x2(uu[k]);
+        acc[2 * k] = fmaf(g[j], f.x, acc[2 * k]);
+        acc[2 * k + 1] = fmaf(g[j], f.y, acc[2 * k + 1]);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = g[j] * wv[k];
+      if (accumulate) {
+        const uint32_t qq[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = unpack_bf16x2(qq[k]);
+          o[2 * k] += f.x;
+          o[2 * k + 1] += f.y;
+        }
+      }
+      uint4 r;
+      r.x = pack_bf16x2(o[0], o[1]); r.y = pack_bf16x2(o[2], o[3]); r.z = pack_bf16x2(o[4], o[5]); r.w = pack_bf16x2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(dA + i * 8) = r;
+      if (v == 0) accb += g[j];
+    }
   }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s_stage[k * 256 + threadIdx.x] = acc[k];
+  s_stage[8 * 256 + threadIdx.x] = accb;
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dw + i, s_acc[i]);
-  if (threadIdx.x == 0) atomicAdd(db, s_acc[Cp]);
+  // thread's channel group is (blockIdx.x * bd + threadIdx.x) % cvec = threadIdx.x % cvec (bd is a multiple of cvec)
+  for (int ch = threadIdx.x; ch < C; ch += bd) {
+    const float* row = s_stage + (ch & 7) * 256;
+    float sum = 0.f;
+    for (int r = ch >> 3; r < bd; r += cvec) sum += row[r];
+    atomicAdd(dw + ch, sum);
+  }
+  if (threadIdx.x == 0) {
+    float sum = 0.f;
+    for (int r = 0; r < bd; r += cvec) sum += s_stage[8 * 256 + r];
+    atomicAdd(db, sum);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ composed DS head
@@ -545,7 +567,7 @@ int mtbc_head1x1_bwd(const void* a, const float* dlogits, int64_t npix, int32_t 
   if (Cp % 8 != 0 || cvec > 256) return set_error(MTBC_ERR_INVALID, "head1x1_bwd: Cp %% 8 != 0 or Cp > 2048");
   const int bd = (256 / cvec) * cvec;   // block size multiple of the channel-group count: a thread's group is invariant
   int g = cdiv(npix * cvec, bd * 8); if (g > 148 * 8) g = 148 * 8; if (g < 1) g = 1;
-  head1x1_bwd_kernel<<<g, bd, (Cp + 1) * sizeof(float), ST(stream)>>>(CBF(a), dlogits, npix, Cp, C, w, BF(dA),
+  head1x1_bwd_kernel<<<g, bd, 0, ST(stream)>>>(CBF(a), dlogits, npix, Cp, C, w, BF(dA),
                                                                       accumulate, dw, db);
   return check_launch("head1x1_bwd");
 }
