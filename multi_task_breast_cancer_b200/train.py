@@ -75,6 +75,9 @@ class TrainStep:
         self.side_stream: Optional[torch.cuda.Stream] = None
         import os as _os2
         self.side_enabled = _os2.environ.get("MTBC_SIDE_WGRAD", "1") != "0"
+        self._copy_stream: Optional[torch.cuda.Stream] = None
+        self._pending = None
+        self._load_turn = 0
         self.seg_graphs = None   # data parallel: [(CUDAGraph, bucket index or None)] + opt_graph
         self.opt_graph = None
         import os as _os
@@ -260,14 +263,53 @@ class TrainStep:
         self.graph = g
 
     def load_batch(self, x: torch.Tensor, mask: torch.Tensor, onehot: torch.Tensor):
-        """Copy a batch (host pinned or device tensors) into the static input buffers, asynchronously."""
-        self.x.copy_(x, non_blocking=True)
-        self.mask.copy_(mask, non_blocking=True)
-        self.onehot.copy_(onehot, non_blocking=True)
+        """Hand the next batch to the step.  Device tensors are copied into the static input buffers on the current
+        stream.  Host (pinned) tensors are prefetched: the host->device copy runs on a copy stream into one of two
+        staging slots, so the transfer of batch i+1 overlaps the kernels of step i; `step()` waits for the slot and
+        moves it into the static buffers with three small device copies."""
+        if x.is_cuda:
+            self.x.copy_(x, non_blocking=True)
+            self.mask.copy_(mask, non_blocking=True)
+            self.onehot.copy_(onehot, non_blocking=True)
+            self._pending = None
+            return
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._stage = [(torch.empty_like(self.x), torch.empty_like(self.mask), torch.empty_like(self.onehot))
+                           for _ in range(2)]
+            self._stage_ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_free = [None, None]
+        slot = self._load_turn & 1
+        self._load_turn += 1
+        cs = self._copy_stream
+        if self._stage_free[slot] is not None:
+            cs.wait_event(self._stage_free[slot])      # the step that consumed this slot has copied it out
+        with torch.cuda.stream(cs):
+            sx, sm, so = self._stage[slot]
+            sx.copy_(x, non_blocking=True)
+            sm.copy_(mask, non_blocking=True)
+            so.copy_(onehot, non_blocking=True)
+            self._stage_ready[slot].record(cs)
+        self._pending = slot
+
+    def _consume_pending(self):
+        if self._pending is None:
+            return
+        slot, self._pending = self._pending, None
+        main = torch.cuda.current_stream(self.device)
+        main.wait_event(self._stage_ready[slot])
+        sx, sm, so = self._stage[slot]
+        self.x.copy_(sx, non_blocking=True)
+        self.mask.copy_(sm, non_blocking=True)
+        self.onehot.copy_(so, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._stage_free[slot] = ev
 
     def step(self):
         """One optimisation step on the currently loaded batch.  Asynchronous; losses stay on the device."""
         with torch.cuda.device(self.device):
+            self._consume_pending()
             if self.use_graph:
                 if self.graph is None:
                     self._capture()
@@ -303,6 +345,7 @@ class TrainStep:
     def forward_backward_only(self):
         """Forward + loss + backward without the optimizer (parity tests)."""
         with torch.cuda.device(self.device):
+            self._consume_pending()
             self._run_list(self.launches_fb)
 
     def deliver_grads(self):

@@ -261,3 +261,30 @@ def test_criteria_reject_unsupported_configurations():
         Cr.DiceLoss(sigmoid=True, squared_pred=False)
     with pytest.raises(NotImplementedError):
         Cr.FocalLoss(reduction="sum")
+
+
+def test_train_step_prefetches_host_batches():
+    """load_batch with pinned host tensors (copy stream + two staging slots) feeds the same data as device tensors:
+    alternating two different batches, every step's loss matches the device-tensor path."""
+    from oracle import torch_oracle as O
+    from multi_task_breast_cancer_b200.train import TrainStep
+    _, a = pair("nnunet")
+    _, b = pair("nnunet")
+    batches = [O.synthetic_batch(2, 64, 64, seed=1993 + i) for i in range(2)]
+    ta = TrainStep(a, (2, 1, 64, 64), use_graph=False)
+    tb = TrainStep(b, (2, 1, 64, 64), use_graph=False)
+    la, lb = [], []
+    for i in range(5):
+        img, mask, onehot, _ = batches[i % 2]
+        ta.load_batch(img.cuda(), mask.cuda(), onehot.cuda())
+        ta.step()
+        la.append(ta.losses().clone())
+        tb.load_batch(img.pin_memory(), mask.pin_memory(), onehot.pin_memory())
+        tb.step()
+        lb.append(tb.losses().clone())
+    torch.cuda.synchronize()
+    for x, y in zip(la, lb):
+        assert x[3].item() == 0.0 and y[3].item() == 0.0
+        assert abs(x[0].item() - y[0].item()) < 2e-3 * abs(x[0].item()), (x, y)
+    # the two batches really differ (the check above is not vacuous)
+    assert abs(la[0][0].item() - la[1][0].item()) > 1e-4
