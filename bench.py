@@ -23,8 +23,17 @@ sys.path.insert(0, ROOT)
 
 METRIC = "train_images_per_s"
 UNIT = "img/s"
-WORKLOAD = "MTUNetPlusPlus(deep_supervision=True) training step, batch 32/GPU, 1x256x256, 3 classes, Dice+focal, Adam(eps=1e-4), + prediction refinement"
-TRAIN_GFLOP_PER_IMG = 128.29  # BASELINE.md section 3 (true channels, fwd + dgrad + wgrad)
+MODEL_NAMES = {"unetpp": "MTUNetPlusPlus(deep_supervision=True)", "nnunet": "MTnnUNet", "bts": "Multi_BTS_UNet(width=32, deep_supervision=True)"}
+# GFLOP per image of one training step (true channels, fwd + dgrad + wgrad; SURVEY section 8d / BASELINE.md section 3)
+TRAIN_GFLOP = {("unetpp", 256): 128.29, ("unetpp", 512): 513.16, ("nnunet", 256): 68.90, ("nnunet", 128): 17.23, ("bts", 128): 15.29}
+
+
+def workload(arch: str, batch: int, size: int) -> str:
+    """The default (unetpp, 32, 256) is BASELINE.json configs[1]; --arch nnunet is configs[2], --size 512 configs[4]."""
+    return (f"{MODEL_NAMES[arch]} training step, batch {batch}/GPU, 1x{size}x{size}, 3 classes, Dice+focal, "
+            f"Adam(eps=1e-4), + prediction refinement")
+
+
 
 
 def parse():
@@ -133,7 +142,7 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
            "steps": r["steps"], "warmup": 1, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": WORKLOAD, "arch": args.arch, "size": args.size, "batch_per_step": B,
+           "config": {"workload": workload(args.arch, args.batch, args.size), "arch": args.arch, "size": args.size, "batch_per_step": B,
                       "note": "reference CPU training loop (oracle port of the reference modules, fp32, all host threads)"},
            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -275,10 +284,10 @@ def run_ours(args):
         out = {"metric": METRIC, "value": world * B / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-               "config": {"workload": WORKLOAD, "arch": args.arch, "batch_per_gpu": B, "global_batch": world * B,
+               "config": {"workload": workload(args.arch, B, S), "arch": args.arch, "batch_per_gpu": B, "global_batch": world * B,
                           "size": S, "parallelism": f"dp{world}", "l2": "per-step working set (GBs of activations) >> 126 MB L2",
                           "cuda_graph": True},
-               "tflops_true": world * B * TRAIN_GFLOP_PER_IMG / ms_dev if args.arch == "unetpp" and S == 256 else None,
+               "tflops_true": world * B * TRAIN_GFLOP[(args.arch, S)] / ms_dev if (args.arch, S) in TRAIN_GFLOP else None,
                "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
                        "ms_per_step": ms_e2e},
                "gpu_launches": n_launch, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}

