@@ -306,6 +306,15 @@ int mtbc_refine_predictions(const float* mask_logits, const float* class_logits,
                             uint8_t* mask_out, int32_t* class_out, int32_t* count_out, void* stream);
 /* tp/fp/fn of (logit > 0) against a {0,1} mask over the whole batch -> int64 out[3] (zeroed by caller). */
 int mtbc_hard_dice_counts(const float* logits, const float* target, int64_t n, long long* out, void* stream);
+/* Per-sample confusion counts of a refined uint8 mask against a {0,1} mask: out[n][4] = tp, fp, fn, tn (int64, zeroed
+ * by the caller) -- the inputs of calculate_metrics (utils/metrics.py, called at utils/models.py:335) without moving
+ * the masks to the host. */
+int mtbc_confusion_counts(const uint8_t* mask, const float* target, int32_t N, int64_t HW, long long* out, void* stream);
+/* Epoch bookkeeping of train_one_epoch / validate_one_epoch (training_multitask.py:99,108-109,146-152) without host
+ * syncs: acc[0..5] (double) += total, seg, cls, nan flag, hard Dice of the batch (metrics.py:255-267 from counts =
+ * tp/fp/fn of mtbc_hard_dice_counts, which is zeroed afterwards), 1; confusion[gt*K+pred] (int64) += 1 per sample. */
+int mtbc_metrics_accumulate(const float* loss4, long long* counts, const float* class_logits, const float* onehot,
+                            int32_t B, int32_t K, double* acc, long long* confusion, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------- */
 /* Optimizer (next-row f1): torch.optim.Adam(lr, betas, eps) semantics (experiment_init.py:186-187), fused with the

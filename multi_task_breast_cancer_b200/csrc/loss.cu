@@ -180,6 +180,82 @@ __global__ void __launch_bounds__(256) hard_dice_counts_kernel(const float* __re
   }
 }
 
+// Per-sample confusion counts of a refined uint8 mask against a {0,1} fp32 target: out[n][4] = tp, fp, fn, tn.
+// grid = (blocks per sample, N); 16 mask bytes + 4 x 16 target bytes per thread and iteration.
+__global__ void __launch_bounds__(256) confusion_counts_kernel(const uint8_t* __restrict__ mask,
+                                                               const float* __restrict__ target, int64_t HW,
+                                                               unsigned long long* __restrict__ out) {
+  const int n = blockIdx.y;
+  const uint8_t* m = mask + n * HW;
+  const float* t = target + n * HW;
+  int tp = 0, fp = 0, fn = 0, tn = 0;
+  const bool vec = (HW % 16 == 0) && ((reinterpret_cast<uintptr_t>(m) & 15) == 0) && ((reinterpret_cast<uintptr_t>(t) & 15) == 0);
+  if (vec) {
+    for (int64_t i = (blockIdx.x * 256ll + threadIdx.x) * 16; i < HW; i += gridDim.x * 256ll * 16) {
+      const uint4 mv = *reinterpret_cast<const uint4*>(m + i);
+      const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 tv = *reinterpret_cast<const float4*>(t + i + 4 * q);
+        const float tt[4] = {tv.x, tv.y, tv.z, tv.w};
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const bool s = ((mw[q] >> (8 * b)) & 0xffu) != 0, g = tt[b] != 0.f;
+          tp += (s && g); fp += (s && !g); fn += (!s && g); tn += (!s && !g);
+        }
+      }
+    }
+  } else {
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < HW; i += gridDim.x * 256ll) {
+      const bool s = m[i] != 0, g = t[i] != 0.f;
+      tp += (s && g); fp += (s && !g); fn += (!s && g); tn += (!s && !g);
+    }
+  }
+  tp = __reduce_add_sync(0xffffffffu, tp);
+  fp = __reduce_add_sync(0xffffffffu, fp);
+  fn = __reduce_add_sync(0xffffffffu, fn);
+  tn = __reduce_add_sync(0xffffffffu, tn);
+  if ((threadIdx.x & 31) == 0) {
+    unsigned long long* o = out + 4 * n;
+    if (tp) atomicAdd(o, static_cast<unsigned long long>(tp));
+    if (fp) atomicAdd(o + 1, static_cast<unsigned long long>(fp));
+    if (fn) atomicAdd(o + 2, static_cast<unsigned long long>(fn));
+    if (tn) atomicAdd(o + 3, static_cast<unsigned long long>(tn));
+  }
+}
+
+// One step of the epoch bookkeeping the reference does with .item() calls (training_multitask.py:99,108-109,146-152):
+//   acc[0..2] += total / seg / cls loss, acc[3] += NaN flag, acc[4] += hard Dice of this batch
+//   (metrics.py:255-267: 1 or 0 when the batch has no foreground), acc[5] += 1; confusion[gt][pred] += 1 per sample
+//   (pred = argmax of the class logits, gt = argmax of the one-hot label; first maximum on ties).
+// counts (tp, fp, fn of mtbc_hard_dice_counts) is zeroed afterwards so the next step accumulates from 0.
+__global__ void metrics_accumulate_kernel(const float* __restrict__ loss4, unsigned long long* __restrict__ counts,
+                                          const float* __restrict__ class_logits, const float* __restrict__ onehot,
+                                          int B, int K, double* __restrict__ acc,
+                                          unsigned long long* __restrict__ confusion) {
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    int p = 0, g = 0;
+    for (int k = 1; k < K; ++k) {
+      if (class_logits[b * K + k] > class_logits[b * K + p]) p = k;
+      if (onehot[b * K + k] > onehot[b * K + g]) g = k;
+    }
+    atomicAdd(confusion + g * K + p, 1ull);
+  }
+  if (threadIdx.x == 0) {
+    acc[0] += static_cast<double>(loss4[0]);
+    acc[1] += static_cast<double>(loss4[1]);
+    acc[2] += static_cast<double>(loss4[2]);
+    acc[3] += static_cast<double>(loss4[3]);
+    const double tp = static_cast<double>(counts[0]), fp = static_cast<double>(counts[1]), fn = static_cast<double>(counts[2]);
+    double dice;
+    if (tp + fn == 0.0) dice = (tp + fp == 0.0) ? 1.0 : 0.0;
+    else dice = 2.0 * tp / (2.0 * tp + fp + fn);
+    acc[4] += dice;
+    acc[5] += 1.0;
+    counts[0] = 0; counts[1] = 0; counts[2] = 0;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ Adam
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
@@ -271,6 +347,19 @@ int mtbc_hard_dice_counts(const float* logits, const float* target, int64_t n, l
   int g = cdiv(n, 256 * 8); if (g > 148 * 8) g = 148 * 8; if (g < 1) g = 1;
   hard_dice_counts_kernel<<<g, 256, 0, ST(stream)>>>(logits, target, n, reinterpret_cast<unsigned long long*>(out));
   return check_launch("hard_dice_counts");
+}
+
+int mtbc_confusion_counts(const uint8_t* mask, const float* target, int32_t N, int64_t HW, long long* out, void* stream) {
+  if (N <= 0 || HW <= 0) return 0;
+  int gx = cdiv(HW, 256 * 16 * 4); if (gx < 1) gx = 1; if (gx > 64) gx = 64;
+  confusion_counts_kernel<<<dim3(gx, N), 256, 0, ST(stream)>>>(mask, target, HW, reinterpret_cast<unsigned long long*>(out));
+  return check_launch("confusion_counts");
+}
+int mtbc_metrics_accumulate(const float* loss4, long long* counts, const float* class_logits, const float* onehot,
+                            int32_t B, int32_t K, double* acc, long long* confusion, void* stream) {
+  metrics_accumulate_kernel<<<1, 128, 0, ST(stream)>>>(loss4, reinterpret_cast<unsigned long long*>(counts), class_logits,
+                                                       onehot, B, K, acc, reinterpret_cast<unsigned long long*>(confusion));
+  return check_launch("metrics_accumulate");
 }
 
 int mtbc_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,

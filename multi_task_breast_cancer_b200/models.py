@@ -130,7 +130,9 @@ class _PlanModule(nn.Module):
                     plan.x_in.copy_(x)
                 plan.run_pack()
                 plan.run_forward()
-                outs = tuple(plan.outputs_cls) + tuple(plan.outputs_seg)
+                # copies: the plan's output buffers are static and the next forward overwrites them; an inference
+                # loop that keeps the logits of several batches (utils/models.py:309-386) must not see them change
+                outs = tuple(t.clone() for t in plan.outputs_cls) + tuple(t.clone() for t in plan.outputs_seg)
         ncls = len(plan.outputs_cls)
         return list(outs[:ncls]), list(outs[ncls:])
 

@@ -65,6 +65,7 @@ class TrainStep:
             self.dice_loss = torch.zeros(nh, dtype=torch.float32, device=self.device)  # [0] = full decoder head
             self.focal_loss = torch.zeros(1, dtype=torch.float32, device=self.device)
             self.loss_out = torch.zeros(4, dtype=torch.float32, device=self.device)  # total, seg, cls, nan flag
+            self.lr = float(lr)   # host copy (exact double) of the device scalar the captured Adam launch reads
             self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=self.device)
             self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
             self.exp_avg = torch.zeros_like(self.flat_p)
@@ -336,6 +337,7 @@ class TrainStep:
         self._run_list(self.launches_opt)
 
     def set_lr(self, lr: float):
+        self.lr = float(lr)
         self.lr_dev.fill_(float(lr))
 
     def losses(self) -> torch.Tensor:

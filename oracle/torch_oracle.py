@@ -13,6 +13,9 @@ What is restated (reference file:line, relative to /root/reference):
   * multi-task criterion    src/utils/criterions.py:52-76
   * training step           src/training_multitask.py:79-103 (Adam eps=1e-4, src/utils/experiment_init.py:186-187)
   * prediction refinement   src/utils/models.py:316-332,366-386
+  * epoch loops / metrics   src/training_multitask.py:33-159 (train_one_epoch, validate_one_epoch, class lists),
+                            src/utils/metrics.py:26-76,173-267 (calculate_metrics and its scalar helpers, Hausdorff
+                            excepted), src/utils/models.py:273-397 (test-time inference, per image)
 
 Pinning: the reference ships no tests or golden vectors for this path, and MONAI itself is absent, so parity is
 UNPINNED at the MONAI boundary.  The restatement is pinned against the reference's own module files instead: in the
@@ -408,3 +411,95 @@ def synthetic_batch(B, H, W, n_classes=3, seed=1993, device="cpu"):
         masks[b, 0] = (((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1).float()
     onehot = F.one_hot(label, n_classes).float()
     return img.to(device), masks.to(device), onehot.to(device), label.to(device)
+
+
+# ======================================================================================================================
+# epoch loops and metrics (checker for multi_task_breast_cancer_b200/trainer.py)
+# ======================================================================================================================
+def class_lists(pred_logits, onehot, gt_list, pred_list):
+    """src/training_multitask.py:33-62, num_classes > 2 branch: mean over the logits list, softmax, argmax."""
+    if isinstance(pred_logits, list):
+        pred_logits = torch.mean(torch.stack(pred_logits, dim=0), dim=0)
+    prob = F.softmax(pred_logits, dim=1)
+    for la, p in zip(onehot, prob):
+        gt_list.append(float(torch.argmax(la).item()))
+        pred_list.append(float(torch.argmax(p).item()))
+    return gt_list, pred_list
+
+
+def classification_scores(gt_list, pred_list):
+    """accuracy_score + f1(labels=[0, 1, 2], average='weighted') as at src/training_multitask.py:112-113."""
+    from sklearn.metrics import accuracy_score, f1_score
+    return (float(accuracy_score(gt_list, pred_list)),
+            float(f1_score(y_true=gt_list, y_pred=pred_list, labels=[0, 1, 2], average="weighted", zero_division=0)))
+
+
+def train_one_epoch(model, optimizer, batches, alpha=0.35, inversely_weighted=True):
+    """src/training_multitask.py:74-116 over a list of (image, mask, one-hot) batches."""
+    loss, dice, gt, pr = 0.0, 0.0, [], []
+    for img, mask, onehot in batches:
+        tot, _, _, logits, outs = train_step(model, optimizer, img, mask, onehot, alpha, inversely_weighted)
+        loss += tot.item()
+        dice += hard_dice(mask, outs)
+        gt, pr = class_lists([l.detach() for l in logits] if isinstance(logits, list) else logits.detach(), onehot, gt, pr)
+    acc, f1w = classification_scores(gt, pr)
+    return loss / len(batches), dice / len(batches), acc, f1w
+
+
+@torch.inference_mode()
+def validate_one_epoch(model, batches, alpha=0.35, inversely_weighted=True):
+    """src/training_multitask.py:119-159."""
+    loss, segl, clsl, dice, gt, pr = 0.0, 0.0, 0.0, 0.0, [], []
+    dl, fl = DiceLoss(), FocalLoss(alpha=1, gamma=2)
+    for img, mask, onehot in batches:
+        logits, outs = model(img)
+        seg, cls = multitask_criterion(dl, mask, outs, fl, onehot, logits, inversely_weighted)
+        loss += (alpha * seg + (1 - alpha) * cls).item()
+        segl += seg.item()
+        clsl += cls.item()
+        dice += hard_dice(mask, outs)
+        gt, pr = class_lists(logits, onehot, gt, pr)
+    acc, f1w = classification_scores(gt, pr)
+    n = len(batches)
+    return loss / n, dice / n, acc, f1w, segl / n, clsl / n
+
+
+def segmentation_metrics(gt, seg):
+    """calculate_metrics (src/utils/metrics.py:26-76) without the Hausdorff distance, from boolean numpy-like arrays."""
+    import numpy as np
+    gt = np.asarray(gt).astype(float)
+    seg = np.asarray(seg).astype(float)
+    tp = float(np.sum(np.logical_and(seg, gt)))
+    tn = float(np.sum(np.logical_and(np.logical_not(seg), np.logical_not(gt))))
+    fp = float(np.sum(np.logical_and(seg, np.logical_not(gt))))
+    fn = float(np.sum(np.logical_and(np.logical_not(seg), gt)))
+    empty_gt, empty_seg = np.sum(gt) == 0, np.sum(seg) == 0
+    return {
+        "DICE": (1 if empty_seg else 0) if empty_gt else 2 * tp / (2 * tp + fp + fn),
+        "Sensitivity": np.nan if tp == 0 else tp / (tp + fn),
+        "Specificity": tn / (tn + fp),
+        "Accuracy": (tp + tn) / (tp + tn + fp + fn),
+        "Jaccard index": (1 if empty_seg else 0) if empty_gt else tp / (tp + fp + fn),
+        "Precision": np.nan if tp == 0 else tp / (tp + fp),
+    }
+
+
+@torch.no_grad()
+def inference_multitask(mask_logits, class_logits, masks, labels, overlap_seg_based_on_class=False,
+                        overlap_class_based_on_seg=False, normal_id=2):
+    """src/utils/models.py:299-386 image by image, GIVEN the model outputs (full-decoder mask logits (B,1,H,W), class
+    logits (B,K)): -> (segmentation rows, classification rows) like the two CSV files (no Hausdorff, no postprocess)."""
+    seg_rows, cls_rows = [], []
+    for b in range(mask_logits.shape[0]):
+        out = (torch.sigmoid(mask_logits[b:b + 1]) > 0.5).float().cpu().numpy()
+        pred = int(class_logits[b].argmax().item())
+        seg_out = out.copy()
+        if overlap_seg_based_on_class and pred == normal_id:
+            seg_out[seg_out > 0] = 0
+        row = segmentation_metrics(masks[b:b + 1].cpu().numpy(), seg_out)
+        row["class"] = int(labels[b])
+        seg_rows.append(row)
+        tumor_pixels = int((out == 1).sum())
+        final = normal_id if (overlap_class_based_on_seg and tumor_pixels == 0) else pred
+        cls_rows.append({"ground_truth": int(labels[b]), "predicted_label": final})
+    return seg_rows, cls_rows

@@ -1,0 +1,213 @@
+"""GPU tests of the epoch drivers: sync-free metric accumulation, validation, checkpoints in
+the reference's format, LR schedule reaching the captured Adam launch, batched test-time inference with refinement.
+
+Integer / bookkeeping work is checked EXACTLY against the oracle's restatement of the reference loops applied to the
+very logits the CUDA path produced; the losses are checked against the fp32 oracle model within the bf16 tolerance."""
+import math
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _cuda(lib):
+    if not torch.cuda.is_available():
+        pytest.skip("needs CUDA")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _pair(arch="nnunet"):
+    from oracle import torch_oracle as O
+    from multi_task_breast_cancer_b200 import models as M
+    torch.manual_seed(1993)
+    mk = {"nnunet": lambda m: m.MTnnUNet(1, 1, 3),
+          "unetpp": lambda m: m.MTUNetPlusPlus(in_channels=1, out_channels=1, n_classes=3, deep_supervision=True)}[arch]
+    ref, new = mk(O), mk(M)
+    new.load_state_dict(ref.state_dict())
+    return ref.cuda(), new.cuda()
+
+
+def _batches(n, B, S, device="cpu", seed=1993):
+    from oracle import torch_oracle as O
+    return [O.synthetic_batch(B, S, S, seed=seed + i, device=device)[:3] for i in range(n)]
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_train_one_epoch_bookkeeping_is_exact_and_losses_match_oracle(use_graph):
+    from oracle import torch_oracle as O
+    from multi_task_breast_cancer_b200.train import TrainStep
+    from multi_task_breast_cancer_b200.trainer import EpochRunner
+    ref, new = _pair("nnunet")
+    B, S, n = 3, 128, 5
+    host = _batches(n, B, S)
+    ts = TrainStep(new, (B, 1, S, S), lr=1e-4, use_graph=use_graph)
+    runner = EpochRunner(ts, 3)
+    seen = []
+
+    def loader():
+        # the body after a `yield` runs when the runner asks for the next batch, i.e. right after the previous step's
+        # bookkeeping launches: snapshot what that step produced
+        for i, (img, mask, onehot) in enumerate(host):
+            if i % 2:
+                yield {"image": img, "mask": mask, "label": onehot.argmax(1, keepdim=True).float()}   # loader protocol
+            else:
+                yield (img, mask, onehot)
+            seen.append((ts.loss_out.clone(), ts.plan.outputs_seg[-1].clone(), ts.plan.outputs_cls[0].clone()))
+
+    loss, dice, acc, f1w = runner.train_one_epoch(loader())
+    assert len(seen) == n
+    # exact: same arithmetic as the reference loop on the same logits
+    exp_loss = sum(float(s[0][0].item()) for s in seen) / n
+    exp_dice = sum(O.hard_dice(host[i][1].cuda(), seen[i][1]) for i in range(n)) / n
+    gt, pr = [], []
+    for i in range(n):
+        gt, pr = O.class_lists([seen[i][2]], host[i][2].cuda(), gt, pr)
+    exp_acc, exp_f1 = O.classification_scores(gt, pr)
+    assert abs(loss - exp_loss) < 1e-6 * abs(exp_loss)
+    assert abs(dice - exp_dice) < 1e-12 and abs(acc - exp_acc) < 1e-12 and abs(f1w - exp_f1) < 1e-12
+    # against the fp32 oracle running the reference loop on the same data
+    opt = O.make_optimizer(ref, 1e-4)
+    rl, rd, ra, rf = O.train_one_epoch(ref, opt, [tuple(t.cuda() for t in b) for b in host])
+    assert abs(loss - rl) < 1e-2 * abs(rl), (loss, rl)
+    assert abs(dice - rd) < 2e-2, (dice, rd)
+    assert int(ts.step_dev.item()) == n
+
+
+def test_validate_one_epoch_matches_oracle_and_leaves_weights_alone():
+    from oracle import torch_oracle as O
+    from multi_task_breast_cancer_b200.train import TrainStep
+    from multi_task_breast_cancer_b200.trainer import EpochRunner
+    ref, new = _pair("unetpp")
+    B, S, n = 2, 64, 3
+    dev = _batches(n, B, S, device="cuda", seed=7)
+    ts = TrainStep(new, (B, 1, S, S))
+    runner = EpochRunner(ts, 3)
+    before = ts.flat_p.clone()
+    out = runner.validate_one_epoch(iter(dev))
+    out2 = runner.validate_one_epoch(iter(dev))          # graph replay path
+    exp = O.validate_one_epoch(ref, dev)
+    assert torch.equal(before, ts.flat_p) and int(ts.step_dev.item()) == 0
+    names = ["val_loss", "val_dice", "val_acc", "val_f1", "seg_val_loss", "cls_val_loss"]
+    for k, a, a2, b in zip(names, out, out2, exp):
+        tol = {"val_dice": 3e-2, "val_acc": 0.5, "val_f1": 0.6}.get(k)
+        if tol is None:
+            assert abs(a - b) < 1e-2 * abs(b), (k, a, b)
+        else:
+            assert abs(a - b) <= tol, (k, a, b)
+        assert abs(a - a2) < 1e-3 * max(1.0, abs(a)), (k, a, a2)
+    assert abs(out[0] - (0.35 * out[4] + 0.65 * out[5])) < 1e-5
+    with pytest.raises(ValueError):
+        runner.validate_one_epoch(iter([tuple(t[:1] for t in dev[0])]))     # ragged batch: explicit error
+
+
+def test_checkpoint_round_trip_in_reference_format(tmp_path):
+    from oracle import torch_oracle as O
+    from multi_task_breast_cancer_b200 import models as M
+    from multi_task_breast_cancer_b200.train import TrainStep
+    from multi_task_breast_cancer_b200.trainer import EpochRunner, FlatAdam, load_pretrained_model, save_checkpoint
+    ref, new = _pair("nnunet")
+    B, S = 2, 128
+    batches = _batches(4, B, S, device="cuda")
+    ts = TrainStep(new, (B, 1, S, S), lr=2e-4)
+    runner = EpochRunner(ts, 3)
+    runner.train_one_epoch(iter(batches[:3]))
+    path = str(tmp_path / "model_20260101_fold_0")
+    save_checkpoint(path, 0, new, runner.optimizer, 0.5)
+    ck = torch.load(path, weights_only=False)
+    assert list(ck) == ["epoch", "model_state_dict", "optimizer_state_dict", "scheduler", "val_loss"]
+    assert list(ck["model_state_dict"]) == list(ref.state_dict())
+    # the reference side reads it: plain torch modules + torch.optim.Adam
+    ref.load_state_dict(ck["model_state_dict"])
+    opt = O.make_optimizer(ref, 2e-4)
+    opt.load_state_dict(ck["optimizer_state_dict"])
+    assert float(opt.state_dict()["state"][0]["step"]) == 3.0
+    # resume on a fresh fused step: the continuation matches the uninterrupted run
+    p_before = ts.flat_p.clone()
+    ts.load_batch(*batches[3]); ts.step()
+    want = ts.losses().clone()
+    p_want = ts.flat_p.clone()
+    torch.manual_seed(5)
+    fresh = M.MTnnUNet(1, 1, 3).cuda()
+    ts2 = TrainStep(fresh, (B, 1, S, S), lr=1e-3)
+    load_pretrained_model(fresh, path)
+    fa = FlatAdam(ts2)
+    fa.load_state_dict(ck["optimizer_state_dict"])
+    assert int(ts2.step_dev.item()) == 3 and ts2.lr == pytest.approx(2e-4)
+    ts2.load_batch(*batches[3]); ts2.step()
+    got = ts2.losses()
+    assert abs(got[0].item() - want[0].item()) < 1e-2 * abs(want[0].item())
+    # same weights AND same Adam moments: the 4th update has the same direction and size (a fresh Adam state would take
+    # a sign-like first step instead); run-to-run atomics noise leaves cos > 0.97
+    u1, u2 = (p_want - p_before), (ts2.flat_p - p_before)
+    cos = torch.nn.functional.cosine_similarity(u1, u2, dim=0).item()
+    assert cos > 0.97 and 0.9 < (u2.norm() / u1.norm()).item() < 1.1, (cos, u1.norm().item(), u2.norm().item())
+    # and the oracle continues from the same checkpoint with the same loss (bf16 tolerance)
+    tot, *_ = O.train_step(ref, opt, *batches[3])
+    assert abs(tot.item() - want[0].item()) < 1e-2 * abs(tot.item())
+
+
+def test_lr_schedule_reaches_the_captured_adam_kernel():
+    from multi_task_breast_cancer_b200.train import TrainStep
+    from multi_task_breast_cancer_b200.trainer import EpochRunner, init_lr_scheduler
+    _, new = _pair("nnunet")
+    B, S = 2, 64
+    batches = _batches(1, B, S, device="cuda")
+    ts = TrainStep(new, (B, 1, S, S), lr=1e-3)
+    runner = EpochRunner(ts, 3)
+    sched = init_lr_scheduler(runner.optimizer, "plateau", factor=0.5, min_lr=1e-6, patience=0)
+    moved = []
+    for epoch in range(3):
+        before = ts.flat_p.clone()
+        runner.train_one_epoch(iter(batches))
+        moved.append((ts.flat_p - before).abs().max().item())
+        sched.step(1.0)                        # never improves after the first epoch -> halves from epoch 2 on
+    assert ts.lr == pytest.approx(5e-4)                      # what epoch 3 ran with
+    runner.optimizer.sync_lr()                               # (pushed at the start of the next epoch otherwise)
+    assert ts.lr == pytest.approx(2.5e-4) and ts.lr_dev.item() == pytest.approx(2.5e-4)
+    # |Adam update| <= ~lr early on: the halved rate is visible in what the graph's Adam launch did to the weights
+    assert moved[0] <= 1.01e-3 and moved[1] <= 1.01e-3 and 0 < moved[2] <= 0.51e-3 and moved[2] < 0.6 * moved[1]
+
+
+@pytest.mark.parametrize("flags", [(False, False), (True, True)])
+def test_batched_inference_with_refinement_is_exact(flags):
+    from oracle import torch_oracle as O
+    from multi_task_breast_cancer_b200.trainer import inference_multitask
+    _, new = _pair("unetpp")
+    B, S = 4, 64
+    img, mask, onehot, label = O.synthetic_batch(B, S, S, device="cuda")
+    with torch.no_grad():
+        # push two samples into the refinement branches: a class head that says "normal", an empty prediction
+        new.classifier[5].bias.data = torch.tensor([0.0, 0.0, 0.3], device="cuda")
+    loader = [{"image": img[:2].cpu(), "mask": mask[:2].cpu(), "label": label[:2].view(-1, 1).float().cpu(),
+               "patient_id": torch.tensor([11, 12])},
+              {"image": img[2:].cpu(), "mask": mask[2:].cpu(), "label": label[2:].view(-1, 1).float().cpu(),
+               "patient_id": torch.tensor([13, 14])}]
+    keep = {}
+    seg_rows, cls_rows = inference_multitask(new, loader, device="cuda", overlap_seg_based_on_class=flags[0],
+                                             overlap_class_based_on_seg=flags[1], keep=keep)
+    assert [r["patient_id"] for r in seg_rows] == [11, 12, 13, 14]
+    e_seg, e_cls = [], []
+    for d, ml, cl in zip(loader, keep["mask_logits"], keep["class_logits"]):
+        # the reference's per-image numpy procedure applied to the very logits the batched path used
+        s, c = O.inference_multitask(ml, cl, d["mask"].cuda(), d["label"].flatten().long(), flags[0], flags[1])
+        e_seg += s; e_cls += c
+    assert not torch.equal(keep["mask_logits"][0], keep["mask_logits"][1])   # outputs of different batches do not alias
+    for a, b in zip(seg_rows, e_seg):
+        for k, v in b.items():
+            assert (math.isnan(a[k]) and math.isnan(v)) or a[k] == pytest.approx(v, abs=1e-12), (k, a[k], v)
+    for a, b in zip(cls_rows, e_cls):
+        assert a["ground_truth"] == b["ground_truth"] and a["predicted_label"] == b["predicted_label"]
+    assert len(keep["masks"]) == 2 and keep["masks"][0].dtype == torch.uint8
+    if flags[0]:
+        assert all(int(m.sum()) == 0 for m in keep["masks"])        # every sample predicted "normal": masks cleared
+    # close to the fp32 oracle model as well (bf16 tolerance: a few boundary pixels may differ)
+    ref, _ = _pair("unetpp")
+    with torch.no_grad():
+        ref.classifier[5].bias.data = torch.tensor([0.0, 0.0, 0.3], device="cuda")
+        rl, ro = ref(img)
+    agree = ((ro[-1] > 0) == (torch.cat(keep["mask_logits"]) > 0)).float().mean().item()
+    assert agree > 0.97, agree
