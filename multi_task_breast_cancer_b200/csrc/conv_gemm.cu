@@ -10,6 +10,7 @@
 #include "internal.h"
 #include <cuda.h>
 #include <vector>
+#include <algorithm>
 #include <string.h>
 #include <stdlib.h>
 
@@ -282,22 +283,24 @@ struct WgradParams {
   int32_t TW, TH, TN, tiles_w, tiles_h, n_ptiles, splits;
   int32_t a_stage_bytes, b_stage_bytes, a_box_bytes, b_box_bytes;
   int32_t n_rows, ld_k, k0;
+  int32_t a_stages, b_stages;  // ring depths, sized by the host to fill shared memory (bytes in flight, not MMA rate,
+                               // bound this kernel: with 3 + 2 stages the 48 -> 48 transposed-conv gradient ran at 2.3 TB/s)
   float* dw_acc;
 };
 
-constexpr int kWgAStages = 3;
-constexpr int kWgBStages = 2;
+constexpr int kWgMaxStages = 8;
 
 __global__ void __launch_bounds__(128) wgrad_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t s_afull[kWgAStages], s_aempty[kWgAStages];
-  __shared__ uint64_t s_bfull[kWgBStages], s_bempty[kWgBStages];
+  __shared__ uint64_t s_afull[kWgMaxStages], s_aempty[kWgMaxStages];
+  __shared__ uint64_t s_bfull[kWgMaxStages], s_bempty[kWgMaxStages];
   __shared__ uint64_t s_accum;
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
+  const int kWgAStages = p.a_stages, kWgBStages = p.b_stages;
   uint8_t* smem_b = smem + kWgAStages * p.a_stage_bytes;
 
   const int split = blockIdx.x;
@@ -665,15 +668,42 @@ int wgrad_create(const mtbc_wgrad_desc* d, OpBase** out) {
     p.t_aview[t] = (int16_t)tp.a_view; p.t_adh[t] = (int16_t)tp.a_dh; p.t_adw[t] = (int16_t)tp.a_dw; p.t_bview[t] = (int16_t)tp.b_view;
   }
   p.a_box_bytes = 128 * p.a_kc * 2; p.b_box_bytes = 128 * p.b_kc * 2;
-  p.a_stage_bytes = 128 * 128 * 2;               // always room for a full 128-channel M block
+  {
+    const int a_nbox_max = std::min(p.a_boxes, (aC + p.a_kc - 1) / p.a_kc);   // boxes of the fullest M block
+    p.a_stage_bytes = a_nbox_max * p.a_box_bytes;
+  }
   p.b_stage_bytes = p.b_boxes * p.b_box_bytes;   // BN * 256 B
-  op->smem_bytes = kWgAStages * p.a_stage_bytes + kWgBStages * p.b_stage_bytes + 1024;
+  // Ring depths: one CTA per SM, shared memory filled with whichever operand is (re)loaded more often per pixel tile
+  // (transposed conv: one x tile, k*k dy tiles; 3x3 conv on small planes: nine shifted x tiles, one dy tile).
+  {
+    int a_loads = 0, b_loads = 0;
+    for (int t = 0; t < T; ++t) {
+      if (t == 0 || p.t_bview[t] != p.t_bview[t - 1]) ++b_loads;
+      if (t == 0 || p.t_aview[t] != p.t_aview[t - 1] || p.t_adh[t] != p.t_adh[t - 1] || p.t_adw[t] != p.t_adw[t - 1]) ++a_loads;
+    }
+    const char* env = getenv("MTBC_WGRAD_SMEM_KB");
+    const int budget = (env ? atoi(env) : 200) * 1024;
+    int as = 2, bs = 2;
+    for (;;) {
+      const bool a_first = a_loads * bs >= b_loads * as;   // loads per stage: deepen the busier ring first
+      const bool can_a = as < kWgMaxStages && (as + 1) * p.a_stage_bytes + bs * p.b_stage_bytes + 1024 <= budget;
+      const bool can_b = bs < kWgMaxStages && as * p.a_stage_bytes + (bs + 1) * p.b_stage_bytes + 1024 <= budget;
+      if (a_first && can_a) ++as;
+      else if (!a_first && can_b) ++bs;
+      else if (can_a && as < 2 * a_loads + 1) ++as;
+      else if (can_b && bs < 2 * b_loads + 1) ++bs;
+      else break;
+    }
+    p.a_stages = as; p.b_stages = bs;
+  }
+  op->smem_bytes = p.a_stages * p.a_stage_bytes + p.b_stages * p.b_stage_bytes + 1024;
   p.n_rows = d->n_rows; p.ld_k = d->ld_k; p.k0 = d->k0; p.dw_acc = d->dw_acc;
   const int mblocks = (aC + 127) / 128;
   const int base_ctas = mblocks * (d->ntaps / T) * p.n_tiles;
   int splits = d->splits;
   if (splits <= 0) {
-    splits = (2 * 148 + base_ctas - 1) / base_ctas;
+    const int per_sm = op->smem_bytes <= 110 * 1024 ? 2 : 1;
+    splits = (per_sm * 148 + base_ctas - 1) / base_ctas;
     // keep at least 4 pixel tiles per split so the TMEM/setup cost amortises
     int maxs = (p.n_ptiles + 3) / 4; if (maxs < 1) maxs = 1;
     if (splits > maxs) splits = maxs;

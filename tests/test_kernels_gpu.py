@@ -85,7 +85,9 @@ def test_conv3x3_wgrad_fused_over_concat_sources(D, args):
     _run(D, D.conv_wgrad_multi_case, *args)
 
 
-@pytest.mark.parametrize("args", [(2, 16, 16, 64, 32), (2, 16, 16, 48, 48), (2, 8, 8, 384, 192), (4, 8, 8, 320, 320)])
+@pytest.mark.parametrize("args", [(2, 16, 16, 64, 32), (2, 16, 16, 48, 48), (2, 8, 8, 384, 192), (4, 8, 8, 320, 320),
+                                  # several pixel tiles per CTA: the weight-gradient operand rings wrap around
+                                  (8, 128, 128, 48, 48), (6, 64, 64, 96, 48)])
 def test_conv_transpose_k2(D, args):
     _run(D, D.convT_case, *args)
 
