@@ -317,6 +317,17 @@ int mtbc_metrics_accumulate(const float* loss4, long long* counts, const float* 
                             int32_t B, int32_t K, double* acc, long long* confusion, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------- */
+/* GPU input pipeline (next-row f3; replaces the per-sample host transforms of src/dataset/BUSI_dataset.py:151-163 and
+ * the pageable host->device copies of src/training_multitask.py:82): gathers B samples idx[b] from a uint8 dataset
+ * resident on the device (images, masks: [n][H][W]; labels: [n] int32), applies RandomHorizontalFlip ->
+ * RandomVerticalFlip -> RandomRotation (nearest, zero fill) with the per-sample draw in flips[b] (bit 0 h-flip,
+ * bit 1 v-flip, bit 2 rotation present) and theta[b][6] (the inverse affine matrix of torchvision's rotate divided by
+ * (W/2, H/2), row major), and writes fp32 image / mask (B,1,H,W) and the one-hot label (B,K; may be NULL). */
+int mtbc_augment_batch(const uint8_t* images, const uint8_t* masks, const int32_t* labels, const int32_t* idx,
+                       const uint8_t* flips, const float* theta, int32_t B, int32_t H, int32_t W, int32_t K,
+                       float* out_img, float* out_mask, float* out_onehot, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------- */
 /* Optimizer (next-row f1): torch.optim.Adam(lr, betas, eps) semantics (experiment_init.py:186-187), fused with the
  * 1/world gradient scaling of the data-parallel all-reduce.  step is the 1-based step count. */
 int mtbc_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,

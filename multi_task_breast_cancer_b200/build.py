@@ -16,7 +16,7 @@ CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libmtbc.so"
 STAMP = PKG_DIR / ".libmtbc.stamp"
 
-SOURCES = ["api.cu", "conv_gemm.cu", "conv_halo.cu", "pack.cu", "stream_ops.cu", "stream_pipe.cu", "heads.cu", "loss.cu"]
+SOURCES = ["api.cu", "conv_gemm.cu", "conv_halo.cu", "pack.cu", "stream_ops.cu", "stream_pipe.cu", "heads.cu", "loss.cu", "augment.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -157,6 +157,11 @@ class TrainStep:
         side = self.side_stream
         sst = C.c_void_p(side.cuda_stream)
         used = False
+        # Events recorded by an EARLIER call are already covered by that call's final join (and, under the data-parallel
+        # per-segment graph capture, belong to another capture: waiting on them is cudaErrorInvalidValue), so a
+        # dependency is only waited for when its side launch was issued by this very call.
+        self._run_gen = getattr(self, "_run_gen", 0) + 1
+        gen = self._run_gen
         for l in launches:
             if getattr(l, "side", False):
                 side.wait_stream(main)
@@ -164,6 +169,7 @@ class TrainStep:
                 ev = torch.cuda.Event()
                 ev.record(side)
                 l.done_event = ev
+                l.done_gen = gen
                 used = True
                 continue
             ws = getattr(l, "wait_side", None)
@@ -173,7 +179,7 @@ class TrainStep:
             elif ws:
                 for dep in ws:
                     ev = getattr(dep, "done_event", None)
-                    if ev is not None:
+                    if ev is not None and getattr(dep, "done_gen", -1) == gen:
                         main.wait_event(ev)
             l(st)
         if used:
