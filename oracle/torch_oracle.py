@@ -16,6 +16,10 @@ What is restated (reference file:line, relative to /root/reference):
   * epoch loops / metrics   src/training_multitask.py:33-159 (train_one_epoch, validate_one_epoch, class lists),
                             src/utils/metrics.py:26-76,173-267 (calculate_metrics and its scalar helpers, Hausdorff
                             excepted), src/utils/models.py:273-397 (test-time inference, per image)
+  * input pipeline          src/dataset/BUSI_dataset.py:97-163 (flip / flip / rotate on cat([mask, image]) through
+                            torchvision itself), src/dataset/BUSI_dataloader.py:320-340 (deterministic oversampling;
+                            restated for pandas 1.x semantics -- the function does not run under the pandas 3 of this
+                            image, so this one is UNPINNED)
 
 Pinning: the reference ships no tests or golden vectors for this path, and MONAI itself is absent, so parity is
 UNPINNED at the MONAI boundary.  The restatement is pinned against the reference's own module files instead: in the
@@ -503,3 +507,62 @@ def inference_multitask(mask_logits, class_logits, masks, labels, overlap_seg_ba
         final = normal_id if (overlap_class_based_on_seg and tumor_pixels == 0) else pred
         cls_rows.append({"ground_truth": int(labels[b]), "predicted_label": final})
     return seg_rows, cls_rows
+
+
+# ======================================================================================================================
+# input pipeline (checker for multi_task_breast_cancer_b200/data.py)
+# ======================================================================================================================
+def augment_sample(image_u8, mask_u8, hflip: bool, vflip: bool, angle):
+    """What BUSI.__getitem__ (src/dataset/BUSI_dataset.py:100-163) + the transforms of training_multitask.py:193-197 do
+    to one sample for a GIVEN draw, using torchvision's own functional ops on the host: joined = cat([mask, image]);
+    hflip; vflip; rotate(angle) (nearest, zero fill).  `angle=None` = no transforms (validation / test loaders)."""
+    import torchvision.transforms.functional as TF
+    image = torch.unsqueeze(torch.as_tensor(image_u8, dtype=torch.float32), 0)
+    mask = torch.unsqueeze(torch.as_tensor(mask_u8, dtype=torch.float32), 0)
+    joined = torch.cat([mask, image], dim=0)
+    if hflip:
+        joined = TF.hflip(joined)
+    if vflip:
+        joined = TF.vflip(joined)
+    if angle is not None:
+        joined = TF.rotate(joined, float(angle))
+    return joined[1:2], joined[0:1]
+
+
+def draw_reference_transform_params(n: int):
+    """Run torchvision's RandomHorizontalFlip / RandomVerticalFlip / RandomRotation(360) MODULES sample by sample on a
+    probe image and read back what they drew (flip decisions from the probe, the angle from get_params' RNG call)."""
+    import torchvision.transforms as T
+    hf, vf, ang = [], [], []
+    probe = torch.arange(16, dtype=torch.float32).reshape(1, 4, 4)
+    for _ in range(n):
+        h = T.RandomHorizontalFlip(p=0.5)(probe)
+        hf.append(not torch.equal(h, probe))
+        v = T.RandomVerticalFlip(p=0.5)(probe)
+        vf.append(not torch.equal(v, probe))
+        ang.append(float(T.RandomRotation.get_params([-360.0, 360.0])))
+    return hf, vf, ang
+
+
+def deterministic_oversampling(classes):
+    """src/dataset/BUSI_dataloader.py:320-340 with pandas-1.x `value_counts().reset_index()` semantics, on a list of
+    class names; returns the row indices of the concatenated frame."""
+    import numpy as np
+    classes = list(classes)
+    names, first, counts = [], {}, {}
+    for i, c in enumerate(classes):
+        if c not in counts:
+            names.append(c); first[c] = i; counts[c] = 0
+        counts[c] += 1
+    n = len(classes)
+    order = sorted(names, key=lambda c: (-counts[c], first[c]))
+    rows = list(range(n))
+    for c in order:
+        factor = int(np.round(1.0 / (counts[c] / n), 0))
+        block = [i for i, k in enumerate(classes) if k == c]
+        if factor > 1:
+            for _ in range(factor - 1):
+                rows += block
+        else:
+            rows += block
+    return rows
