@@ -29,6 +29,8 @@ struct HaloSrc {
   int16_t nchunk, kc;   // chunks of kc channels
   int32_t wk0;          // first column in the packed weight row
   int32_t b_off;        // byte offset of this source's first resident weight block inside one tap plane
+  int32_t drop_last;    // the last 16 channels of the last chunk do not exist in the (dense) source: TMA zero-fills
+                        // them, so that K step is not issued at all (48-channel tensors: 3 instead of 4 K steps)
 };
 
 struct HaloOut {
@@ -63,7 +65,7 @@ __device__ long long g_halo_dbg[8];
 // The 9 taps x KC/16 K-steps of one halo chunk, fully unrolled: only the low descriptor words change, by compile-time
 // (A) or per-kernel (B tap plane) offsets, so the single issuing lane stays at the tensor pipe's ~45-cycle
 // per-instruction floor (tools/exp_mma_rate2.cu) instead of ~160 cycles when descriptors are rebuilt in 64-bit.
-template <int KC>
+template <int KC, int KS = KC / 16>
 __device__ __forceinline__ void halo_issue_chunk(uint32_t d_addr, uint32_t a_lo, uint32_t b_lo, uint32_t b_tap16,
                                                  uint32_t idesc, uint32_t accumulate) {
   constexpr uint32_t rowb = KC * 2u;
@@ -75,7 +77,7 @@ __device__ __forceinline__ void halo_issue_chunk(uint32_t d_addr, uint32_t a_lo,
     const uint32_t a_t = a_lo + (((tap / 3) * kHaloW + (tap % 3)) * rowb >> 4);
     const uint32_t b_t = b_lo + tap * b_tap16;
 #pragma unroll
-    for (int k = 0; k < KC / 16; ++k) {
+    for (int k = 0; k < KS; ++k) {
       umma_bf16_lohi(d_addr, a_t + 2 * k, a_hi, b_t + 2 * k, b_hi, idesc, (tap | k) ? 1u : accumulate);
     }
   }
@@ -87,7 +89,7 @@ __device__ __forceinline__ void halo_issue_chunk(uint32_t d_addr, uint32_t a_lo,
 // single N = 2*bn1 instructions: 12 instructions per K step and 256 pixels instead of 18.  The resident weights are
 // stored [dw][dh descending][bn1 x KC] so the N = 2*bn1 operand is just a window over two neighbouring tap blocks:
 // input row dh' feeds tap dh' of the upper pixel and tap dh'-1 of the lower one.
-template <int KC, int BN1>
+template <int KC, int BN1, int KS = KC / 16>
 __device__ __forceinline__ void halo_issue_chunk_g2(uint32_t d_addr, uint32_t a_lo, uint32_t b_lo, uint32_t b_dw16,
                                                     uint32_t idesc1, uint32_t idesc2, uint32_t accumulate) {
   constexpr uint32_t rowb = KC * 2u;
@@ -112,7 +114,7 @@ __device__ __forceinline__ void halo_issue_chunk_g2(uint32_t d_addr, uint32_t a_
         const uint32_t d_t = d_addr + (dhp == 3 ? BN1 : 0);
         const uint32_t idesc = pass == 0 ? idesc1 : idesc2;
 #pragma unroll
-        for (int k = 0; k < KC / 16; ++k) {
+        for (int k = 0; k < KS; ++k) {
           const uint32_t acc = (pass == 0 && dw == 0 && k == 0) ? accumulate : 1u;
           umma_bf16_lohi(d_t, a_t + 2 * k, a_hi, b_t + 2 * k, b_hi, idesc, acc);
         }
@@ -420,7 +422,8 @@ __global__ void __launch_bounds__((MINB == 2 ? 64 : 96) + 128 * P, MINB) conv_ha
         const uint32_t blk = static_cast<uint32_t>(bn1 * sc.kc * 2);
         for (int ch = 0; ch < sc.nchunk; ++ch, ++nch) {
           const uint32_t off = g2 ? 3 * (sc.b_off + ch * blk) : (sc.b_off + ch * blk);
-          s_cb[L][nch] = umma_desc_lo(smem_u32(smem_b) + off, 16) | (sc.kc == 64 ? 0x80000000u : 0u);   // bit 31: 64-wide
+          s_cb[L][nch] = umma_desc_lo(smem_u32(smem_b) + off, 16) | (sc.kc == 64 ? 0x80000000u : 0u)   // bit 31: 64-wide
+                         | ((sc.drop_last && ch == sc.nchunk - 1) ? 0x40000000u : 0u);                  // bit 30: last K step is all zero
         }
       }
       mbar_wait(&s_bfull, 0);
@@ -455,15 +458,20 @@ __global__ void __launch_bounds__((MINB == 2 ? 64 : 96) + 128 * P, MINB) conv_ha
           long long t1 = 0;
           if (dbg) { t1 = clock64(); c_data += t1 - t0; }
           const uint32_t cb = s_cb[L][c];
-          const uint32_t b_lo = cb & 0x7fffffffu;
+          const uint32_t b_lo = cb & 0x3fffffffu;
+          const uint32_t kind = cb >> 30;   // 0: 32 wide, 1: 32 wide minus one K step, 2: 64 wide, 3: 64 wide minus one
           if (no_mma) {
             // debug: no MMAs
           } else if (g2) {
-            if (cb >> 31) halo_issue_chunk_g2<64, 32>(d_addr, a_lo, b_lo, 3 * b_tap16, idesc1, idesc, accumulate);
-            else halo_issue_chunk_g2<32, 32>(d_addr, a_lo, b_lo, 3 * b_tap16, idesc1, idesc, accumulate);
+            if (kind == 2) halo_issue_chunk_g2<64, 32>(d_addr, a_lo, b_lo, 3 * b_tap16, idesc1, idesc, accumulate);
+            else if (kind == 0) halo_issue_chunk_g2<32, 32>(d_addr, a_lo, b_lo, 3 * b_tap16, idesc1, idesc, accumulate);
+            else if (kind == 3) halo_issue_chunk_g2<64, 32, 3>(d_addr, a_lo, b_lo, 3 * b_tap16, idesc1, idesc, accumulate);
+            else halo_issue_chunk_g2<32, 32, 1>(d_addr, a_lo, b_lo, 3 * b_tap16, idesc1, idesc, accumulate);
           } else {
-            if (cb >> 31) halo_issue_chunk<64>(d_addr, a_lo, b_lo, b_tap16, idesc, accumulate);
-            else halo_issue_chunk<32>(d_addr, a_lo, b_lo, b_tap16, idesc, accumulate);
+            if (kind == 2) halo_issue_chunk<64>(d_addr, a_lo, b_lo, b_tap16, idesc, accumulate);
+            else if (kind == 0) halo_issue_chunk<32>(d_addr, a_lo, b_lo, b_tap16, idesc, accumulate);
+            else if (kind == 3) halo_issue_chunk<64, 3>(d_addr, a_lo, b_lo, b_tap16, idesc, accumulate);
+            else halo_issue_chunk<32, 1>(d_addr, a_lo, b_lo, b_tap16, idesc, accumulate);
           }
           accumulate = 1;
           long long t2 = 0;
@@ -876,6 +884,10 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
     if (kc > kcmax) kcmax = kc;
     (kc == 64 ? use64 : use32) = true;
     p.src[v].kc = (int16_t)kc; p.src[v].nchunk = (int16_t)(aC / kc); p.src[v].wk0 = wk0[v]; p.src[v].b_off = b_off;
+    {
+      const char* k_env = getenv("MTBC_HALO_SKIP_ZERO_K");
+      p.src[v].drop_last = (aC - a.C >= 16 && !(k_env && k_env[0] == '0')) ? 1 : 0;
+    }
     b_off += aC * BN * 2;
     if (wk0[v] % 32 != 0 || wk0[v] + aC > d->w_ktot) { delete op; return set_error(MTBC_ERR_INVALID, "conv_halo: weight columns out of range"); }
     int rc = encode_act(&p.amap[v], a, kc, kHaloW, halo_h, 1);
