@@ -324,7 +324,11 @@ __global__ void conv_first_shift_finish_kernel(const float* __restrict__ x, int 
 // CIN is a compile-time constant so the 9*CIN input taps live in registers (a run-time Cin puts them in local memory
 // and every FMA pays a local load); weights are staged k-major [k][Cp] so 4 output channels come from one 128-bit
 // shared-memory broadcast load.
-template <int CIN>
+// PPT pixels per thread (same sample, 128 pixels apart so every access stays coalesced): the InstanceNorm partial sums
+// stay in registers over the PPT pixels and are combined once (16 shuffles per 16 columns and quantity), not per pixel:
+// at one pixel per thread the 64 shuffles + shared-memory atomics per pixel, not the 100 MB store, bounded the kernel
+// (105 us at 32 x 256 x 256 x 24 against a 26 us write floor).  NCH = 16-column chunks (Cs / 16) when PPT > 1.
+template <int CIN, int NCH = 0, int PPT = 1>
 __global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __restrict__ x, int N, int H, int W,
                                                              const float* __restrict__ w, const float* __restrict__ bias,
                                                              int Cout, __nv_bfloat16* __restrict__ y, int Cp,
@@ -347,13 +351,11 @@ __global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __rest
   }
   __syncthreads();
   const int64_t HW = static_cast<int64_t>(H) * W;
-  const int64_t pix = blockIdx.x * 128ll + threadIdx.x;  // within the whole batch
-  const int n = static_cast<int>(pix / HW);
-  const int hw = static_cast<int>(pix - n * HW);
-  const int h = hw / W, ww = hw - h * W;
+  const int64_t pix0 = blockIdx.x * (128ll * PPT) + threadIdx.x;  // within the whole batch
+  const int n = static_cast<int>(pix0 / HW);
   const int lane = threadIdx.x & 31;
   if (xs != nullptr) {
-    // the block's 128 pixels belong to one sample (HW % 128 == 0): replace the bias by -(mean of w * x)
+    // the block's pixels belong to one sample (HW % (128 * PPT) == 0): replace the bias by -(mean of w * x)
     const float inv = 1.f / static_cast<float>(HW);
     for (int c = threadIdx.x; c < Cs; c += 128) {
       float m = 0.f;
@@ -363,50 +365,92 @@ __global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __rest
     }
     __syncthreads();
   }
-  float xin[K];
-#pragma unroll
-  for (int ci = 0; ci < CIN; ++ci)
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int hh = h + r - 1, wc = ww + s - 1;
-        xin[ci * 9 + r * 3 + s] =
-            (hh >= 0 && hh < H && wc >= 0 && wc < W) ? __ldg(x + (static_cast<int64_t>(n) * CIN + ci) * HW + hh * W + wc) : 0.f;
-      }
-  __nv_bfloat16* dst = y + pix * Cp;
   const bool wide = (Cp % 16) == 0;
-  for (int c0 = 0; c0 < Cs; c0 += 16) {
-    float v[16];
+  constexpr int NACC = NCH > 0 ? NCH * 16 : 1;
+  float ps[NACC], pq[NACC];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 b4 = *reinterpret_cast<const float4*>(s_b + c0 + 4 * q);
-      v[4 * q] = b4.x; v[4 * q + 1] = b4.y; v[4 * q + 2] = b4.z; v[4 * q + 3] = b4.w;
-    }
+  for (int i = 0; i < NACC; ++i) { ps[i] = 0.f; pq[i] = 0.f; }
+#pragma unroll 1
+  for (int j = 0; j < PPT; ++j) {
+    const int64_t pix = pix0 + j * 128ll;
+    const int hw = static_cast<int>(pix - n * HW);
+    const int h = hw / W, ww = hw - h * W;
+    float xin[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const float xk = xin[k];
+    for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int hh = h + r - 1, wc = ww + s - 1;
+          xin[ci * 9 + r * 3 + s] =
+              (hh >= 0 && hh < H && wc >= 0 && wc < W) ? __ldg(x + (static_cast<int64_t>(n) * CIN + ci) * HW + hh * W + wc) : 0.f;
+        }
+    __nv_bfloat16* dst = y + pix * Cp;
+    auto chunk = [&](int c0, float (&v)[16]) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float4 w4 = *reinterpret_cast<const float4*>(s_w + k * Cs + c0 + 4 * q);
-        v[4 * q] = fmaf(xk, w4.x, v[4 * q]); v[4 * q + 1] = fmaf(xk, w4.y, v[4 * q + 1]);
-        v[4 * q + 2] = fmaf(xk, w4.z, v[4 * q + 2]); v[4 * q + 3] = fmaf(xk, w4.w, v[4 * q + 3]);
+        const float4 b4 = *reinterpret_cast<const float4*>(s_b + c0 + 4 * q);
+        v[4 * q] = b4.x; v[4 * q + 1] = b4.y; v[4 * q + 2] = b4.z; v[4 * q + 3] = b4.w;
       }
-    }
-    if (stat_sum != nullptr) {
-      float sq[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) sq[i] = v[i] * v[i];
-      const float cs = warp_colsum16(v, lane);
-      const float cq = warp_colsum16(sq, lane);
-      if ((lane & 1) == 0) {
-        const int cc = c0 + col16_of_lane(lane);
-        atomicAdd(&s_st[cc], cs);
-        atomicAdd(&s_st[Cs + cc], cq);
+      for (int k = 0; k < K; ++k) {
+        const float xk = xin[k];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 w4 = *reinterpret_cast<const float4*>(s_w + k * Cs + c0 + 4 * q);
+          v[4 * q] = fmaf(xk, w4.x, v[4 * q]); v[4 * q + 1] = fmaf(xk, w4.y, v[4 * q + 1]);
+          v[4 * q + 2] = fmaf(xk, w4.z, v[4 * q + 2]); v[4 * q + 3] = fmaf(xk, w4.w, v[4 * q + 3]);
+        }
+      }
+    };
+    if constexpr (NCH > 0) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        float v[16];
+        chunk(c * 16, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { ps[c * 16 + i] += v[i]; pq[c * 16 + i] = fmaf(v[i], v[i], pq[c * 16 + i]); }
+        const int left = Cp - c * 16;
+        emit_bf16x16_n(dst + c * 16, v, false, left >= 16 ? 16 : 8, wide);
+      }
+    } else {
+      for (int c0 = 0; c0 < Cs; c0 += 16) {
+        float v[16];
+        chunk(c0, v);
+        if (stat_sum != nullptr) {
+          float sq[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) sq[i] = v[i] * v[i];
+          const float cs = warp_colsum16(v, lane);
+          const float cq = warp_colsum16(sq, lane);
+          if ((lane & 1) == 0) {
+            const int cc = c0 + col16_of_lane(lane);
+            atomicAdd(&s_st[cc], cs);
+            atomicAdd(&s_st[Cs + cc], cq);
+          }
+        }
+        const int left = Cp - c0;
+        emit_bf16x16_n(dst + c0, v, false, left >= 16 ? 16 : 8, wide);
       }
     }
-    const int left = Cp - c0;
-    emit_bf16x16_n(dst + c0, v, false, left >= 16 ? 16 : 8, wide);
+  }
+  if constexpr (NCH > 0) {
+    if (stat_sum != nullptr) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        float a[16], q[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { a[i] = ps[c * 16 + i]; q[i] = pq[c * 16 + i]; }
+        const float cs = warp_colsum16(a, lane);
+        const float cq = warp_colsum16(q, lane);
+        if ((lane & 1) == 0) {
+          const int cc = c * 16 + col16_of_lane(lane);
+          atomicAdd(&s_st[cc], cs);
+          atomicAdd(&s_st[Cs + cc], cq);
+        }
+      }
+    }
   }
   if (stat_sum != nullptr) {
     __syncthreads();
@@ -417,30 +461,42 @@ __global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __rest
   }
 }
 
-// dW[co][ci][r][s] += sum_pix x[n,ci,h+r-1,w+s-1] * dy[pix][co].  grid = (pixel blocks, Cin): all nine taps of one
-// input channel per block, 8 output channels (one 16-byte vector of dy) at a time, so dy is read once per input
-// channel (one (ci, kernel row) per block read it three times: 395 MB of DRAM traffic for a 100 MB tensor).
-__global__ void __launch_bounds__(128) conv_first_wgrad_kernel(const float* __restrict__ x, int N, int Cin, int H,
+// dW[co][ci][r][s] += sum_pix x[n,ci,h+r-1,w+s-1] * dy[pix][co].  grid = (pixel blocks, Cin).  G = 4 or 8 consecutive
+// threads share one pixel and each owns one 16-byte vector (8 output channels) of its dy row, so a warp reads whole
+// contiguous pixel rows and dy crosses HBM exactly once per input channel (the previous version looped over the
+// 8-channel groups OUTSIDE the pixel loop and fetched every 32-byte sector of the dense 48-byte rows up to three
+// times: 289 MB of DRAM traffic for a 100 MB tensor, 139 us).  The nine taps x 8 channels accumulate in registers over
+// the whole pixel range and are combined once: xor shuffles across the lanes of equal group, then shared-memory atomics.
+template <int G>
+__global__ void __launch_bounds__(256) conv_first_wgrad_kernel(const float* __restrict__ x, int N, int Cin, int H,
                                                                int W, const __nv_bfloat16* __restrict__ dy, int Cp,
                                                                int Cout, float* __restrict__ dw) {
   __shared__ float s_acc[9][64];
   const int ci = blockIdx.y;
-  const int lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < 9 * 64; i += 128) (&s_acc[0][0])[i] = 0.f;
+  for (int i = threadIdx.x; i < 9 * 64; i += 256) (&s_acc[0][0])[i] = 0.f;
   __syncthreads();
   const int64_t HW = static_cast<int64_t>(H) * W;
   const int64_t total = static_cast<int64_t>(N) * HW;
-  for (int c0 = 0; c0 < Cp && c0 < 64; c0 += 8) {
-    float acc[9][8];
+  const int g = threadIdx.x & (G - 1);          // 8-channel group of this thread
+  const int slot = threadIdx.x / G;             // pixel slot inside the block
+  constexpr int PPB = 256 / G;                  // pixels per block and iteration
+  const bool active = g * 8 < Cp;
+  float acc[9][8];
 #pragma unroll
-    for (int t = 0; t < 9; ++t)
+  for (int t = 0; t < 9; ++t)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
-    for (int64_t pix = blockIdx.x * 128ll + threadIdx.x; pix < total; pix += static_cast<int64_t>(gridDim.x) * 128) {
-      const int n = static_cast<int>(pix / HW);
-      const int hw = static_cast<int>(pix - n * HW);
+    for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
+  if (active) {
+#pragma unroll 2
+    for (int64_t pix = blockIdx.x * static_cast<int64_t>(PPB) + slot; pix < total; pix += static_cast<int64_t>(gridDim.x) * PPB) {
+      // 32-bit index arithmetic (the host checks N*H*W < 2^31): a 64-bit division per pixel costs more issue slots
+      // than the 72 FMAs it feeds
+      const uint32_t p32 = static_cast<uint32_t>(pix), hw32 = static_cast<uint32_t>(HW);
+      const int n = static_cast<int>(p32 / hw32);
+      const int hw = static_cast<int>(p32 - static_cast<uint32_t>(n) * hw32);
       const int h = hw / W, ww = hw - h * W;
       const float* xp = x + (static_cast<int64_t>(n) * Cin + ci) * HW;
+      const uint4 d0 = *reinterpret_cast<const uint4*>(dy + pix * Cp + g * 8);
       float xs[9];
 #pragma unroll
       for (int r = 0; r < 3; ++r)
@@ -449,7 +505,6 @@ __global__ void __launch_bounds__(128) conv_first_wgrad_kernel(const float* __re
           const int hh = h + r - 1, wc = ww + s - 1;
           xs[r * 3 + s] = (hh >= 0 && hh < H && wc >= 0 && wc < W) ? __ldg(xp + hh * W + wc) : 0.f;
         }
-      const uint4 d0 = *reinterpret_cast<const uint4*>(dy + pix * Cp + c0);
       const uint32_t du[4] = {d0.x, d0.y, d0.z, d0.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -461,16 +516,19 @@ __global__ void __launch_bounds__(128) conv_first_wgrad_kernel(const float* __re
         }
       }
     }
-#pragma unroll
-    for (int t = 0; t < 9; ++t)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float v = warp_sum(acc[t][i]);
-        if (lane == 0) atomicAdd(&s_acc[t][c0 + i], v);
-      }
   }
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = acc[t][i];
+#pragma unroll
+      for (int o = 16; o >= G; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);   // lanes of equal group
+      if (lane < G && active) atomicAdd(&s_acc[t][g * 8 + i], v);
+    }
   __syncthreads();
-  for (int i = threadIdx.x; i < 9 * 64; i += 128) {
+  for (int i = threadIdx.x; i < 9 * 64; i += 256) {
     const int t = i / 64, co = i % 64;
     if (co < Cout) atomicAdd(dw + (static_cast<int64_t>(co) * Cin + ci) * 9 + t, s_acc[t][co]);
   }
@@ -575,9 +633,16 @@ int mtbc_conv_first_fwd(const float* x, int32_t N, int32_t Cin, int32_t H, int32
   }
   const int Cs = (Cp + 15) & ~15;
   const int smem = (Cs * Cin * 9 + 3 * Cs) * sizeof(float);
-  const int grid = static_cast<int>(N * HW / 128);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   __nv_bfloat16* yb = static_cast<__nv_bfloat16*>(y);
+  // single-channel images on planes of whole 1024-pixel blocks (every benchmark shape): 8 pixels per thread
+  if (Cin == 1 && Cs <= 32 && HW % 1024 == 0 && !getenv("MTBC_FIRST_PPT1")) {
+    const int g8 = static_cast<int>(N * HW / 1024);
+    if (Cs == 16) conv_first_fwd_kernel<1, 1, 8><<<g8, 128, smem, st>>>(x, N, H, W, w, bias, Cout, yb, Cp, stat_sum, stat_sq, center_scratch);
+    else conv_first_fwd_kernel<1, 2, 8><<<g8, 128, smem, st>>>(x, N, H, W, w, bias, Cout, yb, Cp, stat_sum, stat_sq, center_scratch);
+    return check_launch("conv_first_fwd");
+  }
+  const int grid = static_cast<int>(N * HW / 128);
   switch (Cin) {
     case 1: conv_first_fwd_kernel<1><<<grid, 128, smem, st>>>(x, N, H, W, w, bias, Cout, yb, Cp, stat_sum, stat_sq, center_scratch); break;
     case 2: conv_first_fwd_kernel<2><<<grid, 128, smem, st>>>(x, N, H, W, w, bias, Cout, yb, Cp, stat_sum, stat_sq, center_scratch); break;
@@ -590,11 +655,17 @@ int mtbc_conv_first_wgrad(const float* x, int32_t N, int32_t Cin, int32_t H, int
                           int32_t Cout, float* dw, void* stream) {
   if (Cin < 1 || Cin > 4 || Cout > 64 || Cp % 8 != 0) return set_error(MTBC_ERR_INVALID, "conv_first_wgrad: Cin 1..4, Cout <= 64");
   const int64_t total = static_cast<int64_t>(N) * H * W;
-  int gx = static_cast<int>((total + 128 * 16 - 1) / (128 * 16));
+  if (total >= (1ll << 31)) return set_error(MTBC_ERR_INVALID, "conv_first_wgrad: N*H*W must be below 2^31");
+  const int G = Cp <= 32 ? 4 : 8;
+  int gx = static_cast<int>((total + (256 / G) * 16 - 1) / ((256 / G) * 16));
   if (gx > 148 * 4) gx = 148 * 4;
   if (gx < 1) gx = 1;
-  conv_first_wgrad_kernel<<<dim3(gx, Cin), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, N, Cin, H, W, static_cast<const __nv_bfloat16*>(dy), Cp, Cout, dw);
+  if (G == 4)
+    conv_first_wgrad_kernel<4><<<dim3(gx, Cin), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, N, Cin, H, W, static_cast<const __nv_bfloat16*>(dy), Cp, Cout, dw);
+  else
+    conv_first_wgrad_kernel<8><<<dim3(gx, Cin), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, N, Cin, H, W, static_cast<const __nv_bfloat16*>(dy), Cp, Cout, dw);
   return check_launch("conv_first_wgrad");
 }
 

@@ -97,6 +97,13 @@ def test_first_layer(D, cout):
     _run(D, D.first_conv_case, 2, 32, 32, cout)
 
 
+@pytest.mark.parametrize("args", [(3, 64, 64, 24), (2, 128, 128, 32), (2, 16, 24, 24), (5, 32, 32, 16)])
+def test_first_layer_shapes(D, args):
+    """Whole 1024-pixel blocks (8 pixels per thread, register-resident statistics) and planes that are not (one pixel
+    per thread); the weight gradient's pixel loop wraps around the grid."""
+    _run(D, D.first_conv_case, *args)
+
+
 @pytest.mark.parametrize("args", [(2, 32, 32, 24, True, True), (2, 16, 16, 96, True, False),
                                   (2, 16, 16, 320, False, True, 0.01), (3, 8, 8, 512, False, False, 0.01),
                                   # >= 1 Mi elements: the bulk-copy pipelined kernels (stream_pipe.cu)
