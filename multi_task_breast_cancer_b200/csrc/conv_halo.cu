@@ -316,6 +316,7 @@ __global__ void __launch_bounds__((MINB == 2 ? 64 : 96) + 128 * P, MINB) conv_ha
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t s_afull[kHaloMaxStages], s_aempty[kHaloMaxStages];
   __shared__ uint64_t s_bfull, s_accfull[2], s_accempty[2];
+  __shared__ uint64_t s_init[2];   // split-chunk MMA lanes: "the first chunk of this tile has initialised the accumulator"
   __shared__ uint32_t s_tmem;
   __shared__ __align__(16) float s_bias[256];
   __shared__ float s_part[4][2][256];  // [lane quarter][sum|sumsq][col]: per-warp column partials at a flush
@@ -352,7 +353,11 @@ __global__ void __launch_bounds__((MINB == 2 ? 64 : 96) + 128 * P, MINB) conv_ha
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&s_afull[s], 1); mbar_init(&s_aempty[s], 1); }
     mbar_init(&s_bfull, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(&s_accfull[b], 1); mbar_init(&s_accempty[b], kEpiWarps); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&s_accfull[b], p.lanes == 3 ? 2 : 1);   // split-chunk mode: both lanes commit every tile
+      mbar_init(&s_accempty[b], kEpiWarps);
+      mbar_init(&s_init[b], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -411,7 +416,75 @@ __global__ void __launch_bounds__((MINB == 2 ? 64 : 96) + 128 * P, MINB) conv_ha
     // shared memory built once (weight-block descriptor + chunk width per chunk).
     const int L = warp == 1 ? 0 : 1;
     const int nlanes = p.lanes;
-    if (L < nlanes && elect_one()) {
+    if (nlanes == 3) {
+      // SPLIT-CHUNK mode (tiles of >= 2 chunks, one CTA per SM): the two lanes share every tile and the same
+      // accumulator; lane L takes the chunks whose GLOBAL index (over the CTA's whole tile range) has parity L.  With an
+      // even ring depth every ring slot then has one fixed consumer lane, so the one-bit mbarrier parities stay exact.
+      // Measured on the one-lane version (tools/diag_halo_dbg.py, [24,24,24,24,48] -> 24): per 24-MMA chunk 925 cycles
+      // of issue (the pipe's 42 cycles per instruction) + 188 in tcgen05.commit + 225 waiting for the next chunk's
+      // barrier although its data had landed + ~100 loop: the pipe idles a third of the time behind ONE lane's
+      // bookkeeping; a second lane issues its chunk meanwhile.  The lane that owns chunk 0 of a tile zero-initialises
+      // the accumulator (accumulate = 0) and commits s_init; the other lane waits for that commit before its first
+      // MMA of the tile (MMAs of different threads are not ordered otherwise).  Both lanes commit s_accfull (count 2).
+      if (elect_one()) {
+        const uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+        const uint32_t idesc1 = umma_idesc_bf16(128, bn1, 0, 0);
+        const uint32_t b_tap16 = static_cast<uint32_t>(p.b_tap_bytes) >> 4;
+        const bool g2 = p.G == 2;
+        int nch = 0;
+        for (int s = 0; s < p.nsrc; ++s) {
+          const HaloSrc sc = p.src[s];
+          const uint32_t blk = static_cast<uint32_t>(bn1 * sc.kc * 2);
+          for (int ch = 0; ch < sc.nchunk; ++ch, ++nch) {
+            const uint32_t off = g2 ? 3 * (sc.b_off + ch * blk) : (sc.b_off + ch * blk);
+            s_cb[L][nch] = umma_desc_lo(smem_u32(smem_b) + off, 16) | (sc.kc == 64 ? 0x80000000u : 0u)
+                           | ((sc.drop_last && ch == sc.nchunk - 1) ? 0x40000000u : 0u);
+          }
+        }
+        mbar_wait(&s_bfull, 0);
+        const int nstages = p.stages;   // even (host)
+        const uint32_t a_step16 = static_cast<uint32_t>(p.a_stage_bytes) >> 4;
+        const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem_a), 16);
+        const bool no_mma = (p.dbg & 2) != 0;
+        int stage = L;
+        uint32_t phase = 0;
+        for (int it = 0; t_begin + it < t_end; ++it) {
+          const int buf = it & 1;
+          const uint32_t acc_phase = (it >> 1) & 1;
+          const uint32_t d_addr = tmem_base + static_cast<uint32_t>(buf * BN);
+          const int c0 = (((it * nch) & 1) == L) ? 0 : 1;   // my first chunk of this tile
+          mbar_wait(&s_accempty[buf], acc_phase ^ 1u);       // epilogue has drained this accumulator
+          if (c0 != 0) mbar_wait(&s_init[buf], acc_phase);   // the other lane's chunk 0 has initialised it
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = c0; c < nch; c += 2) {
+            mbar_wait(&s_afull[stage], phase);
+            const uint32_t cb = s_cb[L][c];
+            const uint32_t b_lo = cb & 0x3fffffffu;
+            const uint32_t kind = cb >> 30;
+            const uint32_t a_lo = a_lo0 + stage * a_step16;
+            const uint32_t accumulate = c == 0 ? 0u : 1u;
+            if (no_mma) {
+            } else if (g2) {
+              if (kind == 2) halo_issue_chunk_g2<64, 32>(d_addr, a_lo, b_lo, 3 * b_tap16, idesc1, idesc, accumulate);
+              else if (kind == 0) halo_issue_chunk_g2<32, 32>(d_addr, a_lo, b_lo, 3 * b_tap16, idesc1, idesc, accumulate);
+              else if (kind == 3) halo_issue_chunk_g2<64, 32, 3>(d_addr, a_lo, b_lo, 3 * b_tap16, idesc1, idesc, accumulate);
+              else halo_issue_chunk_g2<32, 32, 1>(d_addr, a_lo, b_lo, 3 * b_tap16, idesc1, idesc, accumulate);
+            } else {
+              if (kind == 2) halo_issue_chunk<64>(d_addr, a_lo, b_lo, b_tap16, idesc, accumulate);
+              else if (kind == 0) halo_issue_chunk<32>(d_addr, a_lo, b_lo, b_tap16, idesc, accumulate);
+              else if (kind == 3) halo_issue_chunk<64, 3>(d_addr, a_lo, b_lo, b_tap16, idesc, accumulate);
+              else halo_issue_chunk<32, 1>(d_addr, a_lo, b_lo, b_tap16, idesc, accumulate);
+            }
+            if (c == 0) umma_commit(&s_init[buf]);
+            umma_commit(&s_aempty[stage]);
+            stage += 2;
+            if (stage >= nstages) { stage -= nstages; phase ^= 1u; }
+          }
+          umma_commit(&s_accfull[buf]);
+        }
+      }
+    } else if (L < nlanes && elect_one()) {
       const uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
       const uint32_t idesc1 = umma_idesc_bf16(128, bn1, 0, 0);
       const uint32_t b_tap16 = static_cast<uint32_t>(p.b_tap_bytes) >> 4;
@@ -949,7 +1022,15 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   // each lane then revisits only ring slots whose previous fill it consumed itself, so its one-bit mbarrier parity can
   // never be a lap ahead of the barrier (a lane that skips the other lane's chunks could otherwise pass a wait on a
   // slot whose previous fill has not even landed).  Otherwise, and with two CTAs per SM, one lane.
-  if (ctas_per_sm == 2) {
+  const char* sp_env = getenv("MTBC_HALO_SPLIT");
+  if (ctas_per_sm == 1 && p.lanes == 2 && total_chunks >= 2 && p.stages >= 4 && !(sp_env && sp_env[0] == '0')) {
+    // split-chunk lanes: every tile's chunks alternate between the two lanes (see the kernel); needs an even ring
+    p.lanes = 3;
+    if (p.stages & 1) {
+      p.stages -= 1;
+      op->smem_bytes = p.b_total_bytes + p.stages * p.a_stage_bytes + 1024;
+    }
+  } else if (ctas_per_sm == 2) {
     p.lanes = 1;
   } else if (p.lanes == 2) {
     const int pair = 2 * total_chunks;
