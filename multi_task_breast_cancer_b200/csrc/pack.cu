@@ -86,6 +86,66 @@ struct ParamJobDev {
   void* dst1;
 };
 
+// 32 (co) x 32 (ci) x TAPS weight tile through shared memory.  TAPS is a compile-time constant (1 or 9 on this path)
+// so the index divisions become multiply-shifts: with run-time `taps` the two divisions per element made the 15 M
+// parameter pack an instruction-bound 134 us launch (0.9 TB/s).
+template <int TAPS>
+__device__ __forceinline__ void pack_conv_tile(const ParamJobDev& j, int local, float (*s_tile)[32 * 9 + 1]) {
+  const int Cout = j.i[0], Cin = j.i[1], c_begin = j.i[3], c_count = j.i[4];
+  const int tiles_cl = (c_count + 31) >> 5;
+  const int co0 = (local / tiles_cl) << 5, cl0 = (local % tiles_cl) << 5;
+  constexpr int roww = 32 * TAPS;
+  const float* w = static_cast<const float*>(j.src);
+  __nv_bfloat16* wf = static_cast<__nv_bfloat16*>(j.dst0);
+  __nv_bfloat16* wd = static_cast<__nv_bfloat16*>(j.dst1);
+  for (int idx = threadIdx.x; idx < 32 * roww; idx += 256) {
+    const int r = idx / roww, off = idx - r * roww;
+    const int co = co0 + r, cl = cl0 + off / TAPS;
+    s_tile[r][off] = (co < Cout && cl < c_count)
+                         ? w[(static_cast<int64_t>(co) * Cin + c_begin + cl0) * TAPS + off] : 0.f;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < TAPS * 1024; idx += 256) {
+    const int lo = idx & 31, mid = (idx >> 5) & 31, tap = idx >> 10;
+    if (wf) {   // lanes run over ci
+      const int cl = cl0 + lo, co = co0 + mid;
+      if (cl < c_count && co < Cout)
+        wf[(static_cast<int64_t>(tap) * j.i[5] + co) * j.i[6] + j.i[7] + cl] = __float2bfloat16(s_tile[mid][lo * TAPS + tap]);
+    }
+    if (wd) {   // lanes run over co
+      const int co = co0 + lo, cl = cl0 + mid;
+      if (cl < c_count && co < Cout)
+        wd[(static_cast<int64_t>(TAPS - 1 - tap) * j.i[8] + cl) * j.i[9] + co] = __float2bfloat16(s_tile[lo][mid * TAPS + tap]);
+    }
+  }
+}
+
+template <int TAPS>
+__device__ __forceinline__ void unpack_conv_tile(const ParamJobDev& j, int local, float (*s_tile)[32 * 9 + 1]) {
+  const int rows = j.i[0], ld = j.i[1], k0 = j.i[2], Cout = j.i[3], Cin = j.i[4], c_begin = j.i[6], c_count = j.i[7],
+            add = j.i[8];
+  const int tiles_cl = (c_count + 31) >> 5;
+  const int co0 = (local / tiles_cl) << 5, cl0 = (local % tiles_cl) << 5;
+  constexpr int roww = 32 * TAPS;
+  const float* acc = static_cast<const float*>(j.src);
+  float* grad = static_cast<float*>(j.dst0);
+  for (int idx = threadIdx.x; idx < TAPS * 1024; idx += 256) {
+    const int lo = idx & 31, mid = (idx >> 5) & 31, tap = idx >> 10;
+    const int cl = cl0 + lo, co = co0 + mid;
+    s_tile[mid][lo * TAPS + tap] =
+        (cl < c_count && co < Cout) ? acc[(static_cast<int64_t>(tap) * rows + co) * ld + k0 + cl] : 0.f;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 32 * roww; idx += 256) {
+    const int r = idx / roww, off = idx - r * roww;
+    const int co = co0 + r, cl = cl0 + off / TAPS;
+    if (co < Cout && cl < c_count) {
+      float* g = grad + (static_cast<int64_t>(co) * Cin + c_begin + cl0) * TAPS + off;
+      *g = add ? (*g + s_tile[r][off]) : s_tile[r][off];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) param_jobs_kernel(const ParamJobDev* __restrict__ jobs,
                                                          const int32_t* __restrict__ chunk_job,
                                                          const int32_t* __restrict__ chunk_first) {
@@ -102,33 +162,11 @@ __global__ void __launch_bounds__(256) param_jobs_kernel(const ParamJobDev* __re
     // tile with all taps, transposed through shared memory: the parameter is read in rows of 32*taps contiguous
     // floats, wf is written in runs of 32 ci (64 B) and wd in runs of 32 co (64 B).  (Element-wise, the wd writes were
     // 2-byte scatters with a stride of a whole weight row: 0.27 ms per step for 15 M parameters.)
-    const int Cout = j.i[0], Cin = j.i[1], taps = j.i[2] * j.i[2], c_begin = j.i[3], c_count = j.i[4];
-    const int tiles_cl = (c_count + 31) >> 5;
     const int local = blockIdx.x - chunk_first[blockIdx.x];
-    const int co0 = (local / tiles_cl) << 5, cl0 = (local % tiles_cl) << 5;
-    const int roww = 32 * taps;
-    const float* w = static_cast<const float*>(j.src);
-    __nv_bfloat16* wf = static_cast<__nv_bfloat16*>(j.dst0);
-    __nv_bfloat16* wd = static_cast<__nv_bfloat16*>(j.dst1);
-    for (int idx = threadIdx.x; idx < 32 * roww; idx += 256) {
-      const int r = idx / roww, off = idx - r * roww;
-      const int co = co0 + r, cl = cl0 + off / taps;
-      s_tile[r][off] = (co < Cout && cl < c_count)
-                           ? w[(static_cast<int64_t>(co) * Cin + c_begin + cl0) * taps + off] : 0.f;
-    }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < taps * 1024; idx += 256) {
-      const int lo = idx & 31, mid = (idx >> 5) & 31, tap = idx >> 10;
-      if (wf) {   // lanes run over ci
-        const int cl = cl0 + lo, co = co0 + mid;
-        if (cl < c_count && co < Cout)
-          wf[(static_cast<int64_t>(tap) * j.i[5] + co) * j.i[6] + j.i[7] + cl] = __float2bfloat16(s_tile[mid][lo * taps + tap]);
-      }
-      if (wd) {   // lanes run over co
-        const int co = co0 + lo, cl = cl0 + mid;
-        if (cl < c_count && co < Cout)
-          wd[(static_cast<int64_t>(taps - 1 - tap) * j.i[8] + cl) * j.i[9] + co] = __float2bfloat16(s_tile[lo][mid * taps + tap]);
-      }
+    switch (j.i[2]) {
+      case 1: pack_conv_tile<1>(j, local, s_tile); break;
+      case 2: pack_conv_tile<4>(j, local, s_tile); break;
+      default: pack_conv_tile<9>(j, local, s_tile); break;
     }
   } else if (j.kind == MTBC_JOB_PACK_CONVT) {
     // i: Cin, Cout, k, cp, wf_ld, wd_rows, wd_ld ; element order = parameter order (ci, co, q)
@@ -147,28 +185,11 @@ __global__ void __launch_bounds__(256) param_jobs_kernel(const ParamJobDev* __re
     }
   } else if (j.kind == MTBC_JOB_UNPACK_CONV) {
     // i: rows, ld, k0, Cout, Cin, ksz, c_begin, c_count, add.  Same 32 x 32 x taps tile, the other way round.
-    const int rows = j.i[0], ld = j.i[1], k0 = j.i[2], Cout = j.i[3], Cin = j.i[4], taps = j.i[5] * j.i[5],
-              c_begin = j.i[6], c_count = j.i[7], add = j.i[8];
-    const int tiles_cl = (c_count + 31) >> 5;
     const int local = blockIdx.x - chunk_first[blockIdx.x];
-    const int co0 = (local / tiles_cl) << 5, cl0 = (local % tiles_cl) << 5;
-    const int roww = 32 * taps;
-    const float* acc = static_cast<const float*>(j.src);
-    float* grad = static_cast<float*>(j.dst0);
-    for (int idx = threadIdx.x; idx < taps * 1024; idx += 256) {
-      const int lo = idx & 31, mid = (idx >> 5) & 31, tap = idx >> 10;
-      const int cl = cl0 + lo, co = co0 + mid;
-      s_tile[mid][lo * taps + tap] =
-          (cl < c_count && co < Cout) ? acc[(static_cast<int64_t>(tap) * rows + co) * ld + k0 + cl] : 0.f;
-    }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < 32 * roww; idx += 256) {
-      const int r = idx / roww, off = idx - r * roww;
-      const int co = co0 + r, cl = cl0 + off / taps;
-      if (co < Cout && cl < c_count) {
-        float* g = grad + (static_cast<int64_t>(co) * Cin + c_begin + cl0) * taps + off;
-        *g = add ? (*g + s_tile[r][off]) : s_tile[r][off];
-      }
+    switch (j.i[5]) {
+      case 1: unpack_conv_tile<1>(j, local, s_tile); break;
+      case 2: unpack_conv_tile<4>(j, local, s_tile); break;
+      default: unpack_conv_tile<9>(j, local, s_tile); break;
     }
   } else if (j.kind == MTBC_JOB_UNPACK_CONVT) {
     // i: rows, ld, Cin, Cout, k, add ; element order = parameter order (ci, co, q)
