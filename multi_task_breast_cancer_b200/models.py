@@ -483,6 +483,157 @@ class Multi_BTS_UNet(_PlainUNetBase):
         return cls[0], seg[-1]
 
 
+# ======================================================================================================================
+# single-task siblings sharing the same kernels: segmentation-only graphs
+# ======================================================================================================================
+class nnUNet2021(_PlainUNetBase):
+    """Segmentation nnU-Net (reference src/models/segmentation/nnUNet.py:64-162): MTnnUNet's encoder / decoder / four
+    mask heads without the classification branch; returns [output4, output3, output2, output1]."""
+
+    name = "nn-UNet2021"
+
+    def __init__(self, sequences, regions):
+        super().__init__()
+        if regions != 1:
+            raise NotImplementedError("mask heads project to one region (reference: regions=1)")
+        widths = [32, 64, 128, 256, 320]
+        self.encoder1 = LevelBlock(sequences, widths[0], widths[0])
+        self.encoder2 = LevelBlock(widths[0], widths[1], widths[1])
+        self.encoder3 = LevelBlock(widths[1], widths[2], widths[2])
+        self.encoder4 = LevelBlock(widths[2], widths[3], widths[3])
+        self.encoder5 = LevelBlock(widths[3], widths[4], widths[4])
+        self.bottleneck = LevelBlock(widths[4], widths[4], widths[4])
+        self.decoder5 = LevelBlock(widths[4] + widths[4], widths[3], widths[3])
+        self.decoder4 = LevelBlock(widths[3] + widths[3], widths[2], widths[2])
+        self.decoder3 = LevelBlock(widths[2] + widths[2], widths[1], widths[1])
+        self.decoder2 = LevelBlock(widths[1] + widths[1], widths[0], widths[0])
+        self.decoder1 = LevelBlock(widths[0] + widths[0], widths[0], widths[0] // 2)
+        self.upsample5 = nn.ConvTranspose2d(widths[4], widths[4], kernel_size=2, stride=2)
+        self.upsample4 = nn.ConvTranspose2d(widths[3], widths[3], kernel_size=2, stride=2)
+        self.upsample3 = nn.ConvTranspose2d(widths[2], widths[2], kernel_size=2, stride=2)
+        self.upsample2 = nn.ConvTranspose2d(widths[1], widths[1], kernel_size=2, stride=2)
+        self.upsample1 = nn.ConvTranspose2d(widths[0], widths[0], kernel_size=2, stride=2)
+        self.downsample = nn.MaxPool2d(2, 2)
+        self.output4 = nn.Sequential(nn.ConvTranspose2d(widths[2], widths[2], kernel_size=8, stride=8),
+                                     conv1x1(widths[2], regions))
+        self.output3 = nn.Sequential(nn.ConvTranspose2d(widths[1], widths[1], kernel_size=4, stride=4),
+                                     conv1x1(widths[1], regions))
+        self.output2 = nn.Sequential(nn.ConvTranspose2d(widths[0], widths[0], kernel_size=2, stride=2),
+                                     conv1x1(widths[0], regions))
+        self.output1 = conv1x1(widths[0] // 2, regions)
+        self.weights_initialization()
+        self._init_runtime()
+
+    def weights_initialization(self):
+        _kaiming_conv2d(self)
+
+    def _build_graph(self, plan: Plan, x_in: torch.Tensor):
+        B, Cin, H, W = x_in.shape
+        if H % 32 or W % 32:
+            raise ValueError("nnUNet2021 needs H and W divisible by 32 (five 2x2 poolings)")
+        e1, p1 = self._level(plan, None, "encoder1", pool=True, first_input=x_in)
+        e2, p2 = self._level(plan, [p1], "encoder2", pool=True)
+        e3, p3 = self._level(plan, [p2], "encoder3", pool=True)
+        e4, p4 = self._level(plan, [p3], "encoder4", pool=True)
+        e5, p5 = self._level(plan, [p4], "encoder5", pool=True)
+        bott, _ = self._level(plan, [p5], "bottleneck")
+        up5 = plan.convT(bott, "upsample5.weight", "upsample5.bias", 2, "up5")
+        d5, _ = self._level(plan, [e5, up5], "decoder5")
+        up4 = plan.convT(d5, "upsample4.weight", "upsample4.bias", 2, "up4")
+        d4, _ = self._level(plan, [e4, up4], "decoder4")
+        up3 = plan.convT(d4, "upsample3.weight", "upsample3.bias", 2, "up3")
+        d3, _ = self._level(plan, [e3, up3], "decoder3")
+        up2 = plan.convT(d3, "upsample2.weight", "upsample2.bias", 2, "up2")
+        d2, _ = self._level(plan, [e2, up2], "decoder2")
+        up1 = plan.convT(d2, "upsample1.weight", "upsample1.bias", 2, "up1")
+        d1, _ = self._level(plan, [e1, up1], "decoder1")
+        plan.dshead(d4, "output4.0.weight", "output4.0.bias", "output4.1.weight", "output4.1.bias", 8)
+        plan.dshead(d3, "output3.0.weight", "output3.0.bias", "output3.1.weight", "output3.1.bias", 4)
+        plan.dshead(d2, "output2.0.weight", "output2.0.bias", "output2.1.weight", "output2.1.bias", 2)
+        plan.head1x1(d1, "output1.weight", "output1.bias")
+
+    def forward(self, x):
+        _, seg = self._run(x)
+        return seg
+
+
+class BTSUNet(_PlainUNetBase):
+    """Segmentation BTS U-Net (reference src/models/segmentation/BTS_UNet.py:64-152): Multi_BTS_UNet without the
+    classification branch (so any H, W divisible by 8); a list under deep supervision, else the full-decoder logits."""
+
+    name = "BTS U-Net"
+
+    def __init__(self, sequences, regions, width, deep_supervision):
+        super().__init__()
+        if regions != 1:
+            raise NotImplementedError("mask heads project to one region (reference: regions=1)")
+        self.deep_supervision = deep_supervision
+        widths = [width * 2 ** i for i in range(4)]
+        self.encoder1 = LevelBlock(sequences, widths[0] // 2, widths[0])
+        self.encoder2 = LevelBlock(widths[0], widths[1] // 2, widths[1])
+        self.encoder3 = LevelBlock(widths[1], widths[2] // 2, widths[2])
+        self.encoder4 = LevelBlock(widths[2], widths[3] // 2, widths[3])
+        self.bottleneck = LevelBlock(widths[3], widths[3], widths[3])
+        self.bottleneck2 = ConvInNormLeReLU(widths[3] * 2, widths[2])
+        self.decoder3 = LevelBlock(widths[2] * 2, widths[2], widths[1])
+        self.decoder2 = LevelBlock(widths[1] * 2, widths[1], widths[0])
+        self.decoder1 = LevelBlock(widths[0] * 2, widths[0], widths[0] // 2)
+        self.upsample = nn.Upsample(scale_factor=2, mode="nearest")
+        self.downsample = nn.MaxPool2d(2, 2)
+        if self.deep_supervision:
+            self.output3 = nn.Sequential(nn.ConvTranspose2d(widths[1], widths[1], kernel_size=4, stride=4),
+                                         conv1x1(widths[1], regions))
+            self.output2 = nn.Sequential(nn.ConvTranspose2d(widths[0], widths[0], kernel_size=2, stride=2),
+                                         conv1x1(widths[0], regions))
+        self.output1 = conv1x1(widths[0] // 2, regions)
+        self.weights_initialization()
+        self._init_runtime()
+
+    def weights_initialization(self):
+        _kaiming_conv2d(self)
+
+    def _build_graph(self, plan: Plan, x_in: torch.Tensor):
+        B, Cin, H, W = x_in.shape
+        if H % 8 or W % 8:
+            raise ValueError("BTSUNet needs H and W divisible by 8 (three 2x2 poolings)")
+        for k in range(4):   # plane extents the conv kernels tile: multiples of 16, or 1 / 2 / 4 / 8
+            for v in (H >> k, W >> k):
+                if not (v % 16 == 0 or v in (1, 2, 4, 8)):
+                    raise ValueError(f"BTSUNet on sm_100a: the {v}-pixel planes of a {H}x{W} input are not tileable "
+                                     "(every level's extent must be a multiple of 16, or 8 / 4 / 2 / 1)")
+        e1, p1 = self._level(plan, None, "encoder1", pool=True, first_input=x_in)
+        e2, p2 = self._level(plan, [p1], "encoder2", pool=True)
+        e3, p3 = self._level(plan, [p2], "encoder3", pool=True)
+        e4, _ = self._level(plan, [p3], "encoder4")
+        bott, _ = self._level(plan, [e4], "bottleneck")
+        bott2, _ = self._cil(plan, [e4, bott], "bottleneck2")
+        up3 = plan.upsample2(bott2, "up3")
+        d3, _ = self._level(plan, [e3, up3], "decoder3")
+        up2 = plan.upsample2(d3, "up2")
+        d2, _ = self._level(plan, [e2, up2], "decoder2")
+        up1 = plan.upsample2(d2, "up1")
+        d1, _ = self._level(plan, [e1, up1], "decoder1")
+        if self.deep_supervision:
+            plan.dshead(d3, "output3.0.weight", "output3.0.bias", "output3.1.weight", "output3.1.bias", 4)
+            plan.dshead(d2, "output2.0.weight", "output2.0.bias", "output2.1.weight", "output2.1.bias", 2)
+        plan.head1x1(d1, "output1.weight", "output1.bias")
+
+    def forward(self, x):
+        _, seg = self._run(x)
+        return seg if self.deep_supervision else seg[-1]
+
+
+def init_segmentation_model(architecture: str, sequences: int = 1, regions: int = 1, width: int = 48, save_folder=None,
+                            deep_supervision: bool = False) -> nn.Module:
+    """The two branches of src/utils/experiment_init.py:26-92 whose graphs are subsets of the multi-task ones."""
+    if architecture == "BTSUNet":
+        return BTSUNet(sequences=sequences, regions=regions, width=width, deep_supervision=deep_supervision)
+    if architecture == "nnUNet":
+        return nnUNet2021(sequences=sequences, regions=regions)
+    raise NotImplementedError(f"segmentation architecture {architecture!r} is outside the accelerated path "
+                              "(MONAI UNet / AttentionUnet / SwinUNETR / SegResNet, ResidualUNet)")
+
+
 def init_multitask_model(architecture: str, sequences: int = 1, regions: int = 1, n_classes: int = 2, width: int = 48,
                          save_folder=None, deep_supervision: bool = False) -> nn.Module:
     """String-keyed factory with the reference's signature (src/utils/experiment_init.py:130-174)."""

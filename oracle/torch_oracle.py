@@ -8,6 +8,7 @@ What is restated (reference file:line, relative to /root/reference):
   * MTUNetPlusPlus          src/models/multitask/MTUNetPlusPlus.py:11-136  (+ MONAI 1.3.0 TwoConv/Down/UpCat)
   * MTnnUNet                src/models/multitask/MTnnUNet.py:64-183
   * Multi_BTS_UNet          src/models/multitask/Multi_BTS_UNet.py:64-176
+  * nnUNet2021, BTSUNet     src/models/segmentation/nnUNet.py:64-162, BTS_UNet.py:64-152 (single-task siblings, row f4)
   * FocalLoss               src/utils/criterions.py:6-24
   * DiceLoss                monai.losses.DiceLoss as configured at src/utils/experiment_init.py:209-211
   * multi-task criterion    src/utils/criterions.py:52-76
@@ -283,6 +284,90 @@ class Multi_BTS_UNet(nn.Module):
         if self.deep_supervision:
             return [cls], [self.output3(d3), self.output2(d2), self.output1(d1)]
         return cls, self.output1(d1)
+
+
+class nnUNet2021(nn.Module):
+    """Restates src/models/segmentation/nnUNet.py:64-162: MTnnUNet without the classification branch; returns the list
+    [output4, output3, output2, output1]."""
+
+    def __init__(self, sequences, regions):
+        super().__init__()
+        w = [32, 64, 128, 256, 320]
+        self.encoder1 = LevelBlock(sequences, w[0], w[0])
+        self.encoder2 = LevelBlock(w[0], w[1], w[1])
+        self.encoder3 = LevelBlock(w[1], w[2], w[2])
+        self.encoder4 = LevelBlock(w[2], w[3], w[3])
+        self.encoder5 = LevelBlock(w[3], w[4], w[4])
+        self.bottleneck = LevelBlock(w[4], w[4], w[4])
+        self.decoder5 = LevelBlock(w[4] + w[4], w[3], w[3])
+        self.decoder4 = LevelBlock(w[3] + w[3], w[2], w[2])
+        self.decoder3 = LevelBlock(w[2] + w[2], w[1], w[1])
+        self.decoder2 = LevelBlock(w[1] + w[1], w[0], w[0])
+        self.decoder1 = LevelBlock(w[0] + w[0], w[0], w[0] // 2)
+        self.upsample5 = nn.ConvTranspose2d(w[4], w[4], kernel_size=2, stride=2)
+        self.upsample4 = nn.ConvTranspose2d(w[3], w[3], kernel_size=2, stride=2)
+        self.upsample3 = nn.ConvTranspose2d(w[2], w[2], kernel_size=2, stride=2)
+        self.upsample2 = nn.ConvTranspose2d(w[1], w[1], kernel_size=2, stride=2)
+        self.upsample1 = nn.ConvTranspose2d(w[0], w[0], kernel_size=2, stride=2)
+        self.downsample = nn.MaxPool2d(2, 2)
+        self.output4 = nn.Sequential(nn.ConvTranspose2d(w[2], w[2], kernel_size=8, stride=8), _conv1x1(w[2], regions))
+        self.output3 = nn.Sequential(nn.ConvTranspose2d(w[1], w[1], kernel_size=4, stride=4), _conv1x1(w[1], regions))
+        self.output2 = nn.Sequential(nn.ConvTranspose2d(w[0], w[0], kernel_size=2, stride=2), _conv1x1(w[0], regions))
+        self.output1 = _conv1x1(w[0] // 2, regions)
+        _kaiming_all_conv2d(self)
+
+    def forward(self, x):
+        e1 = self.encoder1(x)
+        e2 = self.encoder2(self.downsample(e1))
+        e3 = self.encoder3(self.downsample(e2))
+        e4 = self.encoder4(self.downsample(e3))
+        e5 = self.encoder5(self.downsample(e4))
+        bott = self.bottleneck(self.downsample(e5))
+        d5 = self.decoder5(torch.cat([e5, self.upsample5(bott)], 1))
+        d4 = self.decoder4(torch.cat([e4, self.upsample4(d5)], 1))
+        d3 = self.decoder3(torch.cat([e3, self.upsample3(d4)], 1))
+        d2 = self.decoder2(torch.cat([e2, self.upsample2(d3)], 1))
+        d1 = self.decoder1(torch.cat([e1, self.upsample1(d2)], 1))
+        return [self.output4(d4), self.output3(d3), self.output2(d2), self.output1(d1)]
+
+
+class BTSUNet(nn.Module):
+    """Restates src/models/segmentation/BTS_UNet.py:64-152: Multi_BTS_UNet without the classification branch."""
+
+    def __init__(self, sequences, regions, width, deep_supervision):
+        super().__init__()
+        self.deep_supervision = deep_supervision
+        w = [width * 2 ** i for i in range(4)]
+        self.encoder1 = LevelBlock(sequences, w[0] // 2, w[0])
+        self.encoder2 = LevelBlock(w[0], w[1] // 2, w[1])
+        self.encoder3 = LevelBlock(w[1], w[2] // 2, w[2])
+        self.encoder4 = LevelBlock(w[2], w[3] // 2, w[3])
+        self.bottleneck = LevelBlock(w[3], w[3], w[3])
+        self.bottleneck2 = ConvInNormLeReLU(w[3] * 2, w[2])
+        self.decoder3 = LevelBlock(w[2] * 2, w[2], w[1])
+        self.decoder2 = LevelBlock(w[1] * 2, w[1], w[0])
+        self.decoder1 = LevelBlock(w[0] * 2, w[0], w[0] // 2)
+        self.upsample = nn.Upsample(scale_factor=2, mode="nearest")
+        self.downsample = nn.MaxPool2d(2, 2)
+        if self.deep_supervision:
+            self.output3 = nn.Sequential(nn.ConvTranspose2d(w[1], w[1], kernel_size=4, stride=4), _conv1x1(w[1], regions))
+            self.output2 = nn.Sequential(nn.ConvTranspose2d(w[0], w[0], kernel_size=2, stride=2), _conv1x1(w[0], regions))
+        self.output1 = _conv1x1(w[0] // 2, regions)
+        _kaiming_all_conv2d(self)
+
+    def forward(self, x):
+        e1 = self.encoder1(x)
+        e2 = self.encoder2(self.downsample(e1))
+        e3 = self.encoder3(self.downsample(e2))
+        e4 = self.encoder4(self.downsample(e3))
+        bott = self.bottleneck(e4)
+        bott2 = self.bottleneck2(torch.cat([e4, bott], 1))
+        d3 = self.decoder3(torch.cat([e3, self.upsample(bott2)], 1))
+        d2 = self.decoder2(torch.cat([e2, self.upsample(d3)], 1))
+        d1 = self.decoder1(torch.cat([e1, self.upsample(d2)], 1))
+        if self.deep_supervision:
+            return [self.output3(d3), self.output2(d2), self.output1(d1)]
+        return self.output1(d1)
 
 
 def build_model(architecture: str, sequences: int = 1, regions: int = 1, n_classes: int = 3, width: int = 32,
