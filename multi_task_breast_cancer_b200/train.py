@@ -33,7 +33,8 @@ from .plan import Plan, _mk, flat_layout
 class TrainStep:
     def __init__(self, model: torch.nn.Module, batch_shape: Sequence[int], lr: float = 1e-4, betas=(0.9, 0.999),
                  eps: float = 1e-4, alpha: float = 0.35, inversely_weighted: bool = True, focal_alpha: float = 1.0,
-                 focal_gamma: float = 2.0, process_group=None, use_graph: bool = True, device=None):
+                 focal_gamma: float = 2.0, process_group=None, use_graph: bool = True, device=None,
+                 refine: bool = False, refine_flags=(True, True, 0), normal_id: int = 2):
         """`model` is one of models.{MTUNetPlusPlus, MTnnUNet, Multi_BTS_UNet} already on its CUDA device.
         Hyper-parameters keep the meaning of src/config.yaml (optimizer.lr, training.alpha, loss.inversely_weighted)."""
         self.model = model
@@ -50,6 +51,11 @@ class TrainStep:
             import torch.distributed as dist
             self.world = dist.get_world_size(process_group)
         self.use_graph = use_graph
+        # refine=True: the prediction-refining module (utils/models.py:316-332,366-386) runs inside the step (and its
+        # CUDA graph) on the full-decoder logits: `refined_mask` (uint8), `refined_class`, `pixel_count` (int32).
+        # Any eager launch between two graph replays exposes ~0.35 ms of graph start-up per step (tools/diag_e2e.py),
+        # which is why it lives in the graph and not in the caller's loop.
+        self.refine, self.refine_flags, self.normal_id = bool(refine), tuple(refine_flags), int(normal_id)
         with torch.cuda.device(self.device):
             self._flatten_params()
             x = torch.zeros(self.B, self.Cin, self.H, self.W, dtype=torch.float32, device=self.device)
@@ -70,8 +76,13 @@ class TrainStep:
             self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
             self.exp_avg = torch.zeros_like(self.flat_p)
             self.exp_avg_sq = torch.zeros_like(self.flat_p)
+            if self.refine:
+                self.refined_mask = torch.zeros(self.B, 1, self.H, self.W, dtype=torch.uint8, device=self.device)
+                self.refined_class = torch.zeros(self.B, dtype=torch.int32, device=self.device)
+                self.pixel_count = torch.zeros(self.B, dtype=torch.int32, device=self.device)
             self._build_launches()
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self._heads: Dict[Optional[int], torch.cuda.CUDAGraph] = {}   # first graph of a step, per staging slot (None: no copy)
         self.comm_stream: Optional[torch.cuda.Stream] = None
         self.side_stream: Optional[torch.cuda.Stream] = None
         import os as _os2
@@ -116,6 +127,11 @@ class TrainStep:
                      C.c_float(self.focal_alpha), C.c_float(self.focal_gamma), ptr(self.focal_loss)))
         L.append(_mk("mtbc_multitask_loss", ptr(self.dice_loss), nh, int(self.inv_w), ptr(self.focal_loss),
                      C.c_float(self.alpha), ptr(self.loss_out)))
+        if self.refine:
+            sbc, cbs, thr = self.refine_flags
+            L.append(_mk("mtbc_refine_predictions", ptr(plan.outputs_seg[-1]), ptr(plan.outputs_cls[0]), B, HW, self.K,
+                         self.normal_id, int(bool(sbc)), int(bool(cbs)), int(thr), ptr(self.refined_mask),
+                         ptr(self.refined_class), ptr(self.pixel_count)))
         # ---- d(total)/d(logits)
         for i, logits in enumerate(plan.outputs_seg):
             j = nh - 1 - i
@@ -210,13 +226,14 @@ class TrainStep:
         with torch.cuda.stream(self.comm_stream):
             dist.all_reduce(self.plan.grad_flat[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
 
-    def _run_step_dp(self):
+    def _run_step_dp(self, head=None):
         """forward + loss + backward with each gradient bucket's all-reduce forked onto the communication stream as soon
-        as the bucket is final, then the optimizer after all of them."""
+        as the bucket is final, then the optimizer after all of them.  `head` replaces the first segment's graph (the
+        variant that starts with the staging-slot copies)."""
         main = torch.cuda.current_stream(self.device)
         if self.seg_graphs is not None:
-            for g, k in self.seg_graphs:
-                g.replay()
+            for i, (g, k) in enumerate(self.seg_graphs):
+                (head if (i == 0 and head is not None) else g).replay()
                 if k is not None:
                     self._fork_allreduce(k)
             main.wait_stream(self.comm_stream)
@@ -261,13 +278,29 @@ class TrainStep:
             self.opt_graph = og
             self.seg_graphs = graphs
             self.graph = graphs[0][0]
+            self._heads[None] = self.graph
             return
+        self.graph = self._capture_head(None)
+        self._heads[None] = self.graph
+
+    def _head_launches(self):
+        if self.overlap:
+            return self._segments()[0][0]
+        return self.launches_fb + (self.launches_opt if self.world == 1 else [])
+
+    def _capture_head(self, slot):
+        """The first graph of a step (the whole step when single GPU).  slot = 0 / 1: the graph starts with the three
+        device copies staging slot -> static inputs, so a prefetched host batch costs no eager launch between replays."""
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._run_list(self.launches_fb)
-            if self.world == 1:
-                self._run_list(self.launches_opt)
-        self.graph = g
+        kw = dict(capture_error_mode="thread_local") if self.overlap else {}
+        with torch.cuda.graph(g, **kw):
+            if slot is not None:
+                sx, sm, so = self._stage[slot]
+                self.x.copy_(sx, non_blocking=True)
+                self.mask.copy_(sm, non_blocking=True)
+                self.onehot.copy_(so, non_blocking=True)
+            self._run_list(self._head_launches())
+        return g
 
     def load_batch(self, x: torch.Tensor, mask: torch.Tensor, onehot: torch.Tensor):
         """Hand the next batch to the step.  Device tensors are copied into the static input buffers on the current
@@ -299,34 +332,51 @@ class TrainStep:
             self._stage_ready[slot].record(cs)
         self._pending = slot
 
-    def _consume_pending(self):
+    def _consume_pending(self, in_graph: bool = False):
+        """Make the compute stream wait for the prefetched batch; copy it into the static inputs here (eager paths) or
+        leave that to the slot's head graph (returns the slot; the caller records `_stage_free` after the replay)."""
         if self._pending is None:
-            return
+            return None
         slot, self._pending = self._pending, None
         main = torch.cuda.current_stream(self.device)
         main.wait_event(self._stage_ready[slot])
+        if in_graph:
+            return slot
         sx, sm, so = self._stage[slot]
         self.x.copy_(sx, non_blocking=True)
         self.mask.copy_(sm, non_blocking=True)
         self.onehot.copy_(so, non_blocking=True)
+        self._mark_stage_free(slot)
+        return None
+
+    def _mark_stage_free(self, slot):
         ev = torch.cuda.Event()
-        ev.record(main)
+        ev.record(torch.cuda.current_stream(self.device))
         self._stage_free[slot] = ev
 
     def step(self):
         """One optimisation step on the currently loaded batch.  Asynchronous; losses stay on the device."""
         with torch.cuda.device(self.device):
-            self._consume_pending()
             if self.use_graph:
                 if self.graph is None:
+                    self._consume_pending()      # first step: copy eagerly so the warm-up runs on the real batch
                     self._capture()
+                slot = self._consume_pending(in_graph=True)
+                head = self._heads.get(slot)
+                if head is None:
+                    head = self._heads[slot] = self._capture_head(slot)
                 if self.overlap:
-                    self._run_step_dp()
+                    self._run_step_dp(head)
                 else:
-                    self.graph.replay()
+                    head.replay()
                     if self.world > 1:
                         self._allreduce_then_opt()
-            elif self.overlap:
+                if slot is not None:
+                    self._mark_stage_free(slot)
+                self.steps_done += 1
+                return
+            self._consume_pending()
+            if self.overlap:
                 self._run_step_dp()
             else:
                 self._run_list(self.launches_fb)
@@ -349,6 +399,33 @@ class TrainStep:
     def losses(self) -> torch.Tensor:
         """Device tensor [total, seg, cls, nan_flag] of the last step (reading it synchronises)."""
         return self.loss_out
+
+    def losses_to_host(self, out: torch.Tensor):
+        """Asynchronous device->host read of [total, seg, cls, nan_flag] of the step just enqueued into the pinned
+        tensor `out` (valid after `torch.cuda.synchronize()` or once the returned event has completed).  The copy runs
+        on a read-back stream from a snapshot taken on the compute stream, so the next step's launches never queue
+        behind a copy engine that is busy with the next batch's host->device transfer."""
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, "_read_stream", None) is None:
+            self._read_stream = torch.cuda.Stream(device=self.device)
+            self._loss_snap = [torch.zeros_like(self.loss_out) for _ in range(2)]
+            self._read_done = [None, None]
+            self._read_turn = 0
+        slot = self._read_turn & 1
+        self._read_turn += 1
+        if self._read_done[slot] is not None:
+            main.wait_event(self._read_done[slot])       # the read of two steps ago has left this snapshot
+        self._loss_snap[slot].copy_(self.loss_out, non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        rs = self._read_stream
+        rs.wait_event(ready)
+        with torch.cuda.stream(rs):
+            out.copy_(self._loss_snap[slot], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(rs)
+        self._read_done[slot] = done
+        return done
 
     def forward_backward_only(self):
         """Forward + loss + backward without the optimizer (parity tests)."""

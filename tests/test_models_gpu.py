@@ -266,7 +266,8 @@ def test_criteria_reject_unsupported_configurations():
         Cr.FocalLoss(reduction="sum")
 
 
-def test_train_step_prefetches_host_batches():
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_train_step_prefetches_host_batches(use_graph):
     """load_batch with pinned host tensors (copy stream + two staging slots) feeds the same data as device tensors:
     alternating two different batches, the static graph inputs hold exactly the batch that was handed over when the
     step runs (bit-exact), and every step's loss matches the device-tensor path."""
@@ -280,7 +281,9 @@ def test_train_step_prefetches_host_batches():
     batches = [O.synthetic_batch(2, S, S, seed=1993 + i) for i in range(2)]
     assert not torch.equal(batches[0][0], batches[1][0]) and not torch.equal(batches[0][1], batches[1][1])
     ta = TrainStep(a, (2, 1, S, S), use_graph=False)
-    tb = TrainStep(b, (2, 1, S, S), use_graph=False)
+    # use_graph=True: the staging-slot -> static-input copies live at the head of one captured graph per slot
+    tb = TrainStep(b, (2, 1, S, S), use_graph=use_graph, refine=True)
+    h_loss = torch.zeros(4).pin_memory()
     la, lb = [], []
     for i in range(5):
         img, mask, onehot, _ = batches[i % 2]
@@ -290,8 +293,15 @@ def test_train_step_prefetches_host_batches():
         tb.load_batch(img.pin_memory(), mask.pin_memory(), onehot.pin_memory())
         tb.step()
         lb.append(tb.losses().clone())
+        done = tb.losses_to_host(h_loss)
         assert torch.equal(tb.x.cpu().reshape(img.shape), img) and torch.equal(tb.mask.cpu().reshape(mask.shape), mask)
         assert torch.equal(tb.onehot.cpu(), onehot)
+        done.synchronize()
+        assert torch.equal(h_loss, lb[-1].cpu())                 # read-back stream delivers this step's losses
+        # in-step prediction refinement == the stand-alone entry point on the step's logits
+        from multi_task_breast_cancer_b200.criterions import refine_predictions
+        m, c, n = refine_predictions(tb.plan.outputs_seg[-1], tb.plan.outputs_cls[0])
+        assert torch.equal(m, tb.refined_mask) and torch.equal(c, tb.refined_class) and torch.equal(n, tb.pixel_count)
     torch.cuda.synchronize()
     for x, y in zip(la, lb):
         assert x[3].item() == 0.0 and y[3].item() == 0.0

@@ -44,3 +44,21 @@ run("step + refine + D2H loss", None)
 run("device-tensor load_batch + step + refine + D2H", d)
 run("pinned-host load_batch + step + refine", h, d2h=False)
 run("pinned-host load_batch + step + refine + D2H", h)
+
+
+def run2(name, load):
+    for _ in range(3):
+        ts.load_batch(*load); ts.step(); ts.losses_to_host(h_loss)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        ts.load_batch(*load)
+        ts.step()
+        refine_predictions(ts.plan.outputs_seg[-1], ts.plan.outputs_cls[0])
+        ts.losses_to_host(h_loss)
+    e1.record(); torch.cuda.synchronize()
+    print(f"{name:44s} {e0.elapsed_time(e1) / steps:.3f} ms/step   loss {h_loss.tolist()}", flush=True)
+
+
+run2("pinned-host + step + refine + read-back stream", h)
