@@ -275,6 +275,11 @@ int mtbc_flat_fc_bwd(const void* a, const float* dlogits, int32_t N, int32_t HW,
                      const float* w1, int32_t Hd, const float* w2, int32_t K, const float* hidden, void* dA,
                      int32_t accumulate, float* dw1, float* db1, float* dw2, float* db2, float* scratch, void* stream);
 
+/* nn.Softmax(dim=1) over the (N, K) class logits (nnUNet_classifier.py:110,165-166; K <= 32) and its backward
+ * dlogits = probs * (dprobs - sum_k dprobs*probs).  fp32, overwriting. */
+int mtbc_softmax_rows_fwd(const float* logits, int32_t N, int32_t K, float* probs, void* stream);
+int mtbc_softmax_rows_bwd(const float* probs, const float* dprobs, int32_t N, int32_t K, float* dlogits, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------- */
 /* Losses.  Dice = monai.losses.DiceLoss(sigmoid=True, squared_pred=True, smooth_nr=1, smooth_dr=1)
  * (experiment_init.py:209-211); focal = FocalLoss(alpha, gamma=2) on soft targets (criterions.py:6-24). */

@@ -104,6 +104,8 @@ _SIGS = {
     "mtbc_flat_fc_fwd": [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp],
     "mtbc_flat_fc_bwd": [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp,
                          c_vp, c_vp, c_vp, c_vp, c_vp],
+    "mtbc_softmax_rows_fwd": [c_vp, c_i32, c_i32, c_vp, c_vp],
+    "mtbc_softmax_rows_bwd": [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp],
     "mtbc_dice_sums": [c_vp, c_vp, c_i32, c_i64, c_vp, c_vp],
     "mtbc_dice_finalize": [c_vp, c_i32, c_vp, c_vp],
     "mtbc_dice_bwd": [c_vp, c_vp, c_i32, c_i64, c_vp, c_vp, c_f32, c_vp, c_vp],

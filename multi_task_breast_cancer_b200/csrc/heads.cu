@@ -546,6 +546,39 @@ __global__ void __launch_bounds__(256) flat_fc_bwd_big_kernel(const __nv_bfloat1
   }
 }
 
+// ------------------------------------------------------------------------------------------------ row softmax
+// nn.Softmax(dim=1) on the (N, K) class logits of nnUNetClassifier (nnUNet_classifier.py:110,165-166).  K is the class
+// count (<= 32): one thread per sample, the row lives in registers; N * K * 4 bytes, latency bound by construction.
+__global__ void __launch_bounds__(128) softmax_rows_fwd_kernel(const float* __restrict__ x, int N, int K,
+                                                               float* __restrict__ p) {
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  if (n >= N) return;
+  const float* r = x + static_cast<int64_t>(n) * K;
+  float m = r[0];
+  for (int k = 1; k < K; ++k) m = fmaxf(m, r[k]);
+  float e[32];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    if (k < K) { e[k] = expf(r[k] - m); s += e[k]; }
+  }
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    if (k < K) p[static_cast<int64_t>(n) * K + k] = e[k] / s;
+  }
+}
+// dx_k = p_k * (dp_k - sum_j dp_j p_j)
+__global__ void __launch_bounds__(128) softmax_rows_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dp,
+                                                               int N, int K, float* __restrict__ dx) {
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  if (n >= N) return;
+  const float* pr = p + static_cast<int64_t>(n) * K;
+  const float* gr = dp + static_cast<int64_t>(n) * K;
+  float dot = 0.f;
+  for (int k = 0; k < K; ++k) dot = fmaf(gr[k], pr[k], dot);
+  for (int k = 0; k < K; ++k) dx[static_cast<int64_t>(n) * K + k] = pr[k] * (gr[k] - dot);
+}
+
 }  // namespace mtbc
 
 using namespace mtbc;
@@ -668,6 +701,17 @@ int mtbc_flat_fc_bwd(const void* a, const float* dlogits, int32_t N, int32_t HW,
   flat_fc_bwd_big_kernel<<<cdiv(F, 256), 256, smem, ST(stream)>>>(CBF(a), N, HW, Cp, C, w1, Hd, scratch, BF(dA),
                                                                  accumulate, dw1);
   return check_launch("flat_fc_bwd_big");
+}
+
+int mtbc_softmax_rows_fwd(const float* logits, int32_t N, int32_t K, float* probs, void* stream) {
+  if (K < 1 || K > 32) return set_error(MTBC_ERR_INVALID, "softmax_rows_fwd: K must be in [1, 32]");
+  softmax_rows_fwd_kernel<<<cdiv(N, 128), 128, 0, ST(stream)>>>(logits, N, K, probs);
+  return check_launch("softmax_rows_fwd");
+}
+int mtbc_softmax_rows_bwd(const float* probs, const float* dprobs, int32_t N, int32_t K, float* dlogits, void* stream) {
+  if (K < 1 || K > 32) return set_error(MTBC_ERR_INVALID, "softmax_rows_bwd: K must be in [1, 32]");
+  softmax_rows_bwd_kernel<<<cdiv(N, 128), 128, 0, ST(stream)>>>(probs, dprobs, N, K, dlogits);
+  return check_launch("softmax_rows_bwd");
 }
 
 }  // extern "C"

@@ -623,6 +623,191 @@ class BTSUNet(_PlainUNetBase):
         return seg if self.deep_supervision else seg[-1]
 
 
+# ======================================================================================================================
+# single-task siblings: classification-only graphs (encoder + class branch of the multi-task parents)
+# ======================================================================================================================
+class UNetPlusPlusClassifier(MTUNetPlusPlus):
+    """Classification U-Net++ (reference src/models/classification/UnetPlusPlus_Classifier.py:20-147): the encoder,
+    upcat_3_1 and the class branch of MTUNetPlusPlus; returns the raw class logits (the reference's softmax is
+    commented out, :142-143)."""
+
+    def __init__(self, spatial_dims: int = 2, in_channels: int = 1, n_classes: int = 3,
+                 features: Sequence[int] = (24, 48, 96, 192, 384, 24),
+                 act: Union[str, tuple] = ("LeakyReLU", {"negative_slope": 0.1, "inplace": True}),
+                 norm: Union[str, tuple] = ("instance", {"affine": True}), bias: bool = True,
+                 dropout: Union[float, tuple] = 0.0, upsample: str = "deconv"):
+        nn.Module.__init__(self)
+        if spatial_dims != 2 or upsample != "deconv":
+            raise NotImplementedError("only the reference configuration (2-D, deconv upsampling) is implemented")
+        norm_name, norm_kw = norm if isinstance(norm, (tuple, list)) else (norm, {})
+        act_name, act_kw = act if isinstance(act, (tuple, list)) else (act, {})
+        if norm_name.lower() != "instance" or not norm_kw.get("affine", False) or act_name.lower() != "leakyrelu":
+            raise NotImplementedError("only InstanceNorm(affine=True) + LeakyReLU blocks are implemented")
+        if float(dropout if not isinstance(dropout, (tuple, list)) else dropout[0]) != 0.0:
+            raise NotImplementedError("dropout must be 0.0 (the reference value)")
+        self._slope = float(act_kw.get("negative_slope", 0.01))
+        self.n_classes = 1 if n_classes == 2 else n_classes
+        fea = tuple(features)
+        assert len(fea) == 6
+        a = (self._slope, bias, 0.0)
+        self.conv_0_0 = _MonaiTwoConv(in_channels, fea[0], *a)
+        self.conv_1_0 = _MonaiDown(fea[0], fea[1], *a)
+        self.conv_2_0 = _MonaiDown(fea[1], fea[2], *a)
+        self.conv_3_0 = _MonaiDown(fea[2], fea[3], *a)
+        self.conv_4_0 = _MonaiDown(fea[3], fea[4], *a)
+        self.upcat_3_1 = _MonaiUpCat(fea[4], fea[3], fea[3], *a)
+        self.softmax = nn.Softmax(dim=1)
+        self.process_level_3 = _MonaiDown(fea[3], fea[4], *a)
+        self.classifier = nn.Sequential(
+            _MonaiTwoConv(fea[4] * 3, 512, *a), nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(512, 256), nn.ReLU(),
+            nn.Linear(in_features=256, out_features=self.n_classes))
+        self._has_bias = bias
+        self._init_runtime()
+
+    def _build_graph(self, plan: Plan, x_in: torch.Tensor):
+        B, Cin, H, W = x_in.shape
+        if H % 16 or W % 16:
+            raise ValueError("UNetPlusPlusClassifier needs H and W divisible by 16 (four 2x2 poolings)")
+        if Cin > 4:
+            raise NotImplementedError("first layer supports up to 4 input channels")
+        _, p00 = self._two(plan, None, "conv_0_0", pool=True, first_input=x_in)
+        _, p10 = self._two(plan, [p00], "conv_1_0.convs", pool=True)
+        _, p20 = self._two(plan, [p10], "conv_2_0.convs", pool=True)
+        x30, p30 = self._two(plan, [p20], "conv_3_0.convs", pool=True)
+        x40, _ = self._two(plan, [p30], "conv_4_0.convs")
+        _, p31 = self._upcat(plan, x40, [x30], "upcat_3_1", pool=True)
+        f0, _ = self._two(plan, [p30], "process_level_3.convs")
+        f2, _ = self._two(plan, [p31], "process_level_3.convs")
+        feat, _ = self._two(plan, [f0, x40, f2], "classifier.0")
+        plan.gap_fc(feat, "classifier.3.weight", "classifier.3.bias", "classifier.5.weight", "classifier.5.bias")
+
+    def forward(self, x: torch.Tensor):
+        cls, _ = self._run(x)
+        return cls[0]
+
+
+class nnUNetClassifier(_PlainUNetBase):
+    """Classification nnU-Net (reference src/models/classification/nnUNet_classifier.py:73-167): encoder, bottleneck,
+    decoder5 and the class branch of MTnnUNet.  Like the reference it still OWNS decoder4..decoder1 (never evaluated;
+    their gradients stay None) and returns softmax probabilities when n_classes > 2 (:165-166)."""
+
+    name = "nn-UNet2021"
+
+    def __init__(self, sequences, n_classes=3):
+        super().__init__()
+        widths = [32, 64, 128, 256, 320]
+        self.n_classes = 1 if n_classes == 2 else n_classes
+        self.encoder1 = LevelBlock(sequences, widths[0], widths[0])
+        self.encoder2 = LevelBlock(widths[0], widths[1], widths[1])
+        self.encoder3 = LevelBlock(widths[1], widths[2], widths[2])
+        self.encoder4 = LevelBlock(widths[2], widths[3], widths[3])
+        self.encoder5 = LevelBlock(widths[3], widths[4], widths[4])
+        self.bottleneck = LevelBlock(widths[4], widths[4], widths[4])
+        self.decoder5 = LevelBlock(widths[4] + widths[4], widths[3], widths[3])
+        self.decoder4 = LevelBlock(widths[3] + widths[3], widths[2], widths[2])
+        self.decoder3 = LevelBlock(widths[2] + widths[2], widths[1], widths[1])
+        self.decoder2 = LevelBlock(widths[1] + widths[1], widths[0], widths[0])
+        self.decoder1 = LevelBlock(widths[0] + widths[0], widths[0], widths[0] // 2)
+        self.upsample5 = nn.ConvTranspose2d(widths[4], widths[4], kernel_size=2, stride=2)
+        self.downsample = nn.MaxPool2d(2, 2)
+        self.weights_initialization()
+        # created after the kaiming pass, as in the reference (:107-120): PyTorch default init
+        self.softmax = nn.Softmax(dim=1)
+        self.process_encoder_5 = ConvInNormLeReLU(widths[4], widths[4])
+        self.process_decoder_5 = ConvInNormLeReLU(widths[3], widths[4])
+        self.classifier = nn.Sequential(ConvInNormLeReLU(widths[4] * 3, 512), nn.AdaptiveAvgPool2d(1), nn.Flatten(),
+                                        nn.Linear(512, 256), nn.ReLU(),
+                                        nn.Linear(in_features=256, out_features=self.n_classes))
+        self._init_runtime()
+
+    def weights_initialization(self):
+        _kaiming_conv2d(self)
+
+    def _build_graph(self, plan: Plan, x_in: torch.Tensor):
+        B, Cin, H, W = x_in.shape
+        if H % 32 or W % 32:
+            raise ValueError("nnUNetClassifier needs H and W divisible by 32 (five 2x2 poolings)")
+        _, p1 = self._level(plan, None, "encoder1", pool=True, first_input=x_in)
+        _, p2 = self._level(plan, [p1], "encoder2", pool=True)
+        _, p3 = self._level(plan, [p2], "encoder3", pool=True)
+        _, p4 = self._level(plan, [p3], "encoder4", pool=True)
+        e5, p5 = self._level(plan, [p4], "encoder5", pool=True)
+        bott, _ = self._level(plan, [p5], "bottleneck")
+        # upsample5(bottleneck) appears twice (:155,163): one evaluation, two consumers (as in MTnnUNet)
+        up5 = plan.convT(bott, "upsample5.weight", "upsample5.bias", 2, "up5")
+        d5, _ = self._level(plan, [e5, up5], "decoder5")
+        pe5, _ = self._cil(plan, [e5], "process_encoder_5")
+        pd5, _ = self._cil(plan, [d5], "process_decoder_5")
+        feat, _ = self._cil(plan, [pe5, up5, pd5], "classifier.0")
+        plan.gap_fc(feat, "classifier.3.weight", "classifier.3.bias", "classifier.5.weight", "classifier.5.bias")
+        if self.n_classes > 2:
+            plan.softmax_cls()
+
+    def forward(self, x):
+        cls, _ = self._run(x)
+        return cls[0]
+
+
+class BTSUNetClassifier(_PlainUNetBase):
+    """Classification BTS U-Net (reference src/models/classification/BTS_UNET_classifier.py:55-116): four pooled
+    LevelBlocks + a bottleneck LevelBlock in one nn.Sequential `encoder`, then Flatten -> Linear(8*width*8*8, 256) ->
+    ReLU -> Linear; 128x128 inputs only (the Linear hard-codes the 8x8 bottleneck, :92)."""
+
+    name = "BTS U-Net Classifier"
+
+    def __init__(self, sequences, classes, width, deep_supervision=False):
+        super().__init__()
+        self.deep_supervision = deep_supervision
+        widths = [width * 2 ** i for i in range(4)]
+        self.classes = 1 if classes == 2 else classes
+        self.encoder = nn.Sequential(
+            LevelBlock(sequences, widths[0] // 2, widths[0]), nn.MaxPool2d(2, 2),
+            LevelBlock(widths[0], widths[1] // 2, widths[1]), nn.MaxPool2d(2, 2),
+            LevelBlock(widths[1], widths[2] // 2, widths[2]), nn.MaxPool2d(2, 2),
+            LevelBlock(widths[2], widths[3] // 2, widths[3]), nn.MaxPool2d(2, 2),
+            LevelBlock(widths[3], widths[3], widths[3]))
+        self.classifier = nn.Sequential(nn.Flatten(), nn.Linear(widths[3] * 8 * 8, 256), nn.ReLU(),
+                                        nn.Linear(256, self.classes))
+        self.weights_initialization()
+        self._init_runtime()
+
+    def weights_initialization(self):
+        _kaiming_conv2d(self)
+
+    def _build_graph(self, plan: Plan, x_in: torch.Tensor):
+        B, Cin, H, W = x_in.shape
+        if (H, W) != (128, 128):
+            raise ValueError("BTSUNetClassifier only accepts 128x128 inputs: its classifier is Linear(widths[3]*8*8, "
+                             "256) (BTS_UNET_classifier.py:92)")
+        _, p = self._level(plan, None, "encoder.0", pool=True, first_input=x_in)
+        _, p = self._level(plan, [p], "encoder.2", pool=True)
+        _, p = self._level(plan, [p], "encoder.4", pool=True)
+        _, p = self._level(plan, [p], "encoder.6", pool=True)
+        feat, _ = self._level(plan, [p], "encoder.8")
+        plan.flat_fc(feat, "classifier.1.weight", "classifier.1.bias", "classifier.3.weight", "classifier.3.bias")
+
+    def forward(self, x):
+        cls, _ = self._run(x)
+        return cls[0]
+
+
+def init_classification_model(architecture: str, sequences: int = 1, n_classes: int = 1, width: int = 48,
+                              save_folder=None) -> nn.Module:
+    """String-keyed factory with the reference's signature (src/utils/experiment_init.py:86-127)."""
+    if architecture == "BTSUNetClassifier":
+        model = BTSUNetClassifier(sequences=sequences, classes=n_classes, width=width)
+    elif architecture == "UNetPlusPlusClassifier":
+        model = UNetPlusPlusClassifier(spatial_dims=2, in_channels=sequences, n_classes=n_classes)
+    elif architecture == "nnUNetClassifier":
+        model = nnUNetClassifier(sequences=sequences, n_classes=n_classes)
+    else:
+        model = torch.nn.Module()  # the reference does not raise for unknown names (experiment_init.py:113-116)
+    if save_folder is not None:
+        with (save_folder / "model.txt").open("w") as f:
+            print(model, file=f)
+    return model
+
+
 def init_segmentation_model(architecture: str, sequences: int = 1, regions: int = 1, width: int = 48, save_folder=None,
                             deep_supervision: bool = False) -> nn.Module:
     """The two branches of src/utils/experiment_init.py:26-92 whose graphs are subsets of the multi-task ones."""

@@ -586,10 +586,10 @@ class Plan:
         return logits
 
     def flat_fc(self, a: PTensor, w1: str, b1: str, w2: str, b2: str) -> torch.Tensor:
-        """Flatten -> Linear(C*H*W, 256) -> ReLU -> Linear (Multi_BTS_UNet.py:107-115)."""
+        """Flatten -> Linear(C*H*W, 256) -> ReLU -> Linear (Multi_BTS_UNet.py:107-115, BTS_UNET_classifier.py:89-95)."""
         f = a.feat
         Hd, K = self.P(w1).shape[0], self.P(w2).shape[0]
-        assert self.P(w1).shape[1] == f.C * f.H * f.W, "Multi_BTS_UNet's classifier hard-codes a 16x16 bottleneck"
+        assert self.P(w1).shape[1] == f.C * f.H * f.W, "the flatten head's Linear fixes the bottleneck extent"
         hid = torch.zeros(f.N, Hd, dtype=torch.float32, device=self.device)
         dh = torch.zeros(f.N, Hd, dtype=torch.float32, device=self.device)
         logits = torch.zeros(f.N, K, dtype=torch.float32, device=self.device)
@@ -609,6 +609,22 @@ class Plan:
             return blk
         self._bwd_blocks.append(backward)
         return logits
+
+    def softmax_cls(self) -> torch.Tensor:
+        """nn.Softmax(dim=1) on the class logits emitted last (nnUNet_classifier.py:165-166): the plan's class output
+        becomes the probabilities, and their gradient is mapped back to the logits' before the head's backward."""
+        logits, dlog = self.outputs_cls[-1], self.g_cls[-1]
+        N, K = logits.shape
+        probs = torch.zeros_like(logits)
+        dprobs = torch.zeros_like(logits)
+        self.fwd.append(_mk("mtbc_softmax_rows_fwd", ptr(logits), N, K, ptr(probs)))
+        self.outputs_cls[-1] = probs
+        self.g_cls[-1] = dprobs
+
+        def backward():
+            return [_mk("mtbc_softmax_rows_bwd", ptr(probs), ptr(dprobs), N, K, ptr(dlog))]
+        self._bwd_blocks.append(backward)
+        return probs
 
     # ------------------------------------------------------------------------------------------------ finalize / run
     def finalize(self, seg_grad_active: Optional[Sequence[bool]] = None):

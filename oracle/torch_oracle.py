@@ -9,6 +9,9 @@ What is restated (reference file:line, relative to /root/reference):
   * MTnnUNet                src/models/multitask/MTnnUNet.py:64-183
   * Multi_BTS_UNet          src/models/multitask/Multi_BTS_UNet.py:64-176
   * nnUNet2021, BTSUNet     src/models/segmentation/nnUNet.py:64-162, BTS_UNet.py:64-152 (single-task siblings, row f4)
+  * UNetPlusPlusClassifier, nnUNetClassifier, BTSUNetClassifier
+                            src/models/classification/UnetPlusPlus_Classifier.py:20-147, nnUNet_classifier.py:73-167,
+                            BTS_UNET_classifier.py:55-116 (classification-only siblings, row f4)
   * FocalLoss               src/utils/criterions.py:6-24
   * DiceLoss                monai.losses.DiceLoss as configured at src/utils/experiment_init.py:209-211
   * multi-task criterion    src/utils/criterions.py:52-76
@@ -368,6 +371,100 @@ class BTSUNet(nn.Module):
         if self.deep_supervision:
             return [self.output3(d3), self.output2(d2), self.output1(d1)]
         return self.output1(d1)
+
+
+class UNetPlusPlusClassifier(nn.Module):
+    """Restates src/models/classification/UnetPlusPlus_Classifier.py:20-147: encoder + upcat_3_1 + class branch of
+    MTUNetPlusPlus; raw class logits (the softmax is commented out in the reference, :142-143)."""
+
+    def __init__(self, spatial_dims: int = 2, in_channels: int = 1, n_classes: int = 3,
+                 features: Sequence[int] = (24, 48, 96, 192, 384, 24),
+                 act=("LeakyReLU", {"negative_slope": 0.1, "inplace": True}), norm=("instance", {"affine": True}),
+                 bias: bool = True, dropout: float = 0.0, upsample: str = "deconv"):
+        super().__init__()
+        assert spatial_dims == 2 and upsample == "deconv"
+        slope = float(act[1].get("negative_slope", 0.01))
+        self.n_classes = 1 if n_classes == 2 else n_classes
+        f = tuple(features)
+        a = (slope, bias, dropout)
+        self.conv_0_0 = _TwoConv(in_channels, f[0], *a)
+        self.conv_1_0 = _Down(f[0], f[1], *a)
+        self.conv_2_0 = _Down(f[1], f[2], *a)
+        self.conv_3_0 = _Down(f[2], f[3], *a)
+        self.conv_4_0 = _Down(f[3], f[4], *a)
+        self.upcat_3_1 = _UpCat(f[4], f[3], f[3], *a)
+        self.softmax = nn.Softmax(dim=1)
+        self.process_level_3 = _Down(f[3], f[4], *a)
+        self.classifier = nn.Sequential(
+            _TwoConv(f[4] * 3, 512, *a), nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(512, 256), nn.ReLU(),
+            nn.Linear(256, self.n_classes))
+
+    def forward(self, x):
+        x30 = self.conv_3_0(self.conv_2_0(self.conv_1_0(self.conv_0_0(x))))
+        x40 = self.conv_4_0(x30)
+        x31 = self.upcat_3_1(x40, x30)
+        return self.classifier(torch.cat([self.process_level_3(x30), x40, self.process_level_3(x31)], 1))
+
+
+class nnUNetClassifier(nn.Module):
+    """Restates src/models/classification/nnUNet_classifier.py:73-167: encoder, bottleneck, decoder5 and the class branch
+    of MTnnUNet (decoder4..1 are owned but never evaluated); softmax probabilities when n_classes > 2 (:165-166)."""
+
+    def __init__(self, sequences, n_classes=3):
+        super().__init__()
+        w = [32, 64, 128, 256, 320]
+        self.n_classes = 1 if n_classes == 2 else n_classes
+        self.encoder1 = LevelBlock(sequences, w[0], w[0])
+        self.encoder2 = LevelBlock(w[0], w[1], w[1])
+        self.encoder3 = LevelBlock(w[1], w[2], w[2])
+        self.encoder4 = LevelBlock(w[2], w[3], w[3])
+        self.encoder5 = LevelBlock(w[3], w[4], w[4])
+        self.bottleneck = LevelBlock(w[4], w[4], w[4])
+        self.decoder5 = LevelBlock(w[4] + w[4], w[3], w[3])
+        self.decoder4 = LevelBlock(w[3] + w[3], w[2], w[2])
+        self.decoder3 = LevelBlock(w[2] + w[2], w[1], w[1])
+        self.decoder2 = LevelBlock(w[1] + w[1], w[0], w[0])
+        self.decoder1 = LevelBlock(w[0] + w[0], w[0], w[0] // 2)
+        self.upsample5 = nn.ConvTranspose2d(w[4], w[4], kernel_size=2, stride=2)
+        self.downsample = nn.MaxPool2d(2, 2)
+        _kaiming_all_conv2d(self)      # the class branch below is created afterwards and keeps the default init
+        self.softmax = nn.Softmax(dim=1)
+        self.process_encoder_5 = ConvInNormLeReLU(w[4], w[4])
+        self.process_decoder_5 = ConvInNormLeReLU(w[3], w[4])
+        self.classifier = nn.Sequential(ConvInNormLeReLU(w[4] * 3, 512), nn.AdaptiveAvgPool2d(1), nn.Flatten(),
+                                        nn.Linear(512, 256), nn.ReLU(), nn.Linear(256, self.n_classes))
+
+    def forward(self, x):
+        e1 = self.encoder1(x)
+        e2 = self.encoder2(self.downsample(e1))
+        e3 = self.encoder3(self.downsample(e2))
+        e4 = self.encoder4(self.downsample(e3))
+        e5 = self.encoder5(self.downsample(e4))
+        bott = self.bottleneck(self.downsample(e5))
+        d5 = self.decoder5(torch.cat([e5, self.upsample5(bott)], 1))
+        feat = torch.cat([self.process_encoder_5(e5), self.upsample5(bott), self.process_decoder_5(d5)], 1)
+        out = self.classifier(feat)
+        return self.softmax(out) if self.n_classes > 2 else out
+
+
+class BTSUNetClassifier(nn.Module):
+    """Restates src/models/classification/BTS_UNET_classifier.py:55-116 (128x128 inputs: Linear(8*width*8*8, 256))."""
+
+    def __init__(self, sequences, classes, width, deep_supervision=False):
+        super().__init__()
+        self.deep_supervision = deep_supervision
+        w = [width * 2 ** i for i in range(4)]
+        self.classes = 1 if classes == 2 else classes
+        self.encoder = nn.Sequential(
+            LevelBlock(sequences, w[0] // 2, w[0]), nn.MaxPool2d(2, 2), LevelBlock(w[0], w[1] // 2, w[1]),
+            nn.MaxPool2d(2, 2), LevelBlock(w[1], w[2] // 2, w[2]), nn.MaxPool2d(2, 2),
+            LevelBlock(w[2], w[3] // 2, w[3]), nn.MaxPool2d(2, 2), LevelBlock(w[3], w[3], w[3]))
+        self.classifier = nn.Sequential(nn.Flatten(), nn.Linear(w[3] * 8 * 8, 256), nn.ReLU(),
+                                        nn.Linear(256, self.classes))
+        _kaiming_all_conv2d(self)
+
+    def forward(self, x):
+        return self.classifier(self.encoder(x))
 
 
 def build_model(architecture: str, sequences: int = 1, regions: int = 1, n_classes: int = 3, width: int = 32,

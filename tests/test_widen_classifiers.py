@@ -1,0 +1,144 @@
+"""Classification-only siblings sharing the multi-task kernels: UNetPlusPlusClassifier,
+nnUNetClassifier, BTSUNetClassifier.
+CPU: the oracle restatement against the fixture generated from the reference's own files
+(tests/golden/make_golden_classifiers.py), identical state_dict between the drop-in and the oracle, the factory.
+GPU: forward / focal-loss parity against the oracle, gradients reach exactly the parameters the reference's backward
+reaches, head gradients agree, the row-softmax kernels against torch."""
+import hashlib
+import os
+
+import pytest
+import torch
+
+from oracle import torch_oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CASES = {"unetpp_cls": lambda m: m.UNetPlusPlusClassifier(in_channels=1, n_classes=3),
+         "nnunet_cls": lambda m: m.nnUNetClassifier(1, 3),
+         "nnunet_cls_binary": lambda m: m.nnUNetClassifier(1, 2),
+         "btsunet_cls": lambda m: m.BTSUNetClassifier(1, 3, 16)}
+
+
+def _digest(sd):
+    h = hashlib.sha256()
+    for k, v in sd.items():
+        h.update(k.encode()); h.update(v.detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def _fixture():
+    return torch.load(os.path.join(HERE, "golden", "classifiers.pt"), weights_only=False)
+
+
+def _objective(out, onehot, focal):
+    if out.shape[1] == 1:   # binary models emit one logit (tests/golden/make_golden_classifiers.py)
+        return torch.nn.functional.binary_cross_entropy_with_logits(out, onehot[:, 1:2])
+    return focal(out, onehot)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_and_dropin_match_reference_fixture(name):
+    from multi_task_breast_cancer_b200 import models as M
+    fx = _fixture()[name]
+    torch.manual_seed(fx["seed"]); ora = CASES[name](O)
+    torch.manual_seed(fx["seed"]); new = CASES[name](M)
+    assert list(ora.state_dict()) == list(new.state_dict())
+    assert _digest(ora.state_dict()) == fx["state_digest"] == _digest(new.state_dict())
+    assert sum(p.numel() for p in new.parameters()) == fx["n_params"]
+    img, _, onehot, _ = O.synthetic_batch(fx["B"], fx["S"], fx["S"], seed=fx["seed"])
+    out = ora(img)
+    assert torch.allclose(out, fx["output"], atol=1e-5)
+    loss = _objective(out, onehot, O.FocalLoss())
+    assert abs(loss.item() - fx["loss"]) < 1e-5
+    loss.backward()
+    assert sorted(n for n, p in ora.named_parameters() if p.grad is None) == fx["params_without_grad"]
+
+
+def test_classification_factory():
+    from multi_task_breast_cancer_b200 import models as M
+    assert isinstance(M.init_classification_model("nnUNetClassifier", n_classes=3), M.nnUNetClassifier)
+    assert isinstance(M.init_classification_model("UNetPlusPlusClassifier", n_classes=3), M.UNetPlusPlusClassifier)
+    m = M.init_classification_model("BTSUNetClassifier", n_classes=2, width=8)
+    assert isinstance(m, M.BTSUNetClassifier) and m.classes == 1
+    # unknown names yield an empty module, as in the reference (experiment_init.py:113-116)
+    assert len(list(M.init_classification_model("nope").parameters())) == 0
+
+
+def test_classifiers_refuse_cpu_inputs():
+    from multi_task_breast_cancer_b200 import _lib, models as M
+    with pytest.raises(_lib.MtbcError):
+        M.BTSUNetClassifier(1, 3, 8)(torch.zeros(1, 1, 128, 128))
+
+
+@pytest.mark.gpu
+def test_softmax_rows_kernels(lib):
+    if not torch.cuda.is_available():
+        pytest.skip("needs CUDA")
+    from multi_task_breast_cancer_b200 import _lib
+    from multi_task_breast_cancer_b200.ops import ptr
+    torch.manual_seed(0)
+    for N, K in [(1, 3), (37, 3), (300, 7), (5, 32)]:
+        x = (torch.randn(N, K, device="cuda") * 4).requires_grad_(True)
+        g = torch.randn(N, K, device="cuda")
+        p = torch.empty(N, K, device="cuda")
+        dx = torch.empty(N, K, device="cuda")
+        _lib.call("mtbc_softmax_rows_fwd", ptr(x.detach()), N, K, ptr(p), None)
+        _lib.call("mtbc_softmax_rows_bwd", ptr(p), ptr(g), N, K, ptr(dx), None)
+        ref = torch.softmax(x, dim=1)
+        ref.backward(g)
+        torch.cuda.synchronize()
+        assert torch.allclose(p, ref.detach(), atol=1e-6, rtol=1e-5)     # fp32 tolerance
+        assert torch.allclose(dx, x.grad, atol=1e-6, rtol=1e-4)
+    assert lib.mtbc_softmax_rows_fwd(None, 1, 33, None, None) != 0       # K > 32 is an error, not a crash
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(CASES))
+def test_forward_backward_parity_on_gpu(name, lib):
+    if not torch.cuda.is_available():
+        pytest.skip("needs CUDA")
+    from multi_task_breast_cancer_b200 import criterions as Cr, models as M
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    fx = _fixture()[name]
+    torch.manual_seed(fx["seed"]); ref = CASES[name](O).cuda()
+    new = CASES[name](M)
+    new.load_state_dict(ref.state_dict())
+    new = new.cuda()
+    B, S = 4, 128
+    img, _, onehot, _ = O.synthetic_batch(B, S, S, device="cuda")
+    ro, no = ref(img), new(img)
+    assert isinstance(no, torch.Tensor) and no.shape == ro.shape and no.dtype == torch.float32
+    # same floor as the class logits of the multi-task parents (tests/test_models_gpu.py: 2e-2 / 3.5e-2 absolute on
+    # O(0.05-0.2) logits); probabilities (3-class nnU-Net) move by at most a quarter of the logit error
+    tol = {"unetpp_cls": 2e-2, "nnunet_cls": 1e-2, "nnunet_cls_binary": 2e-2, "btsunet_cls": 3.5e-2}[name]
+    assert (no - ro).abs().max().item() < tol, (no - ro).abs().max().item()
+    if no.shape[1] > 1:
+        assert torch.equal(no.argmax(1), ro.argmax(1))
+    if name == "nnunet_cls":
+        assert torch.allclose(no.sum(1), torch.ones(B, device="cuda"), atol=1e-5)
+    focal_new = Cr.init_criterion_classification(3, None, "Focal")
+    l_new, l_ref = _objective(no, onehot, focal_new), _objective(ro, onehot, O.FocalLoss())
+    assert abs(l_new.item() - l_ref.item()) < 1e-2 * abs(l_ref.item())
+    l_new.backward(); l_ref.backward()
+    pr = dict(ref.named_parameters())
+    pn = dict(new.named_parameters())
+    # gradients reach exactly the parameters the reference's backward reaches (nnUNetClassifier owns four unused
+    # decoder levels); conv biases in front of InstanceNorm get an exactly-zero gradient here and ~1e-9 noise there
+    assert sorted(n for n, p in pn.items() if p.grad is None) == fx["params_without_grad"]
+    for n, p in pn.items():
+        if p.grad is not None:
+            assert torch.isfinite(p.grad).all() and p.grad.shape == p.shape, n
+    rel = lambda a, b: ((a - b).norm() / b.norm()).item()
+    last_fc = "classifier.5" if "bts" not in name else "classifier.3"
+    for n in [last_fc + ".weight", last_fc + ".bias"]:
+        assert rel(pn[n].grad, pr[n].grad) < 5e-2, (n, rel(pn[n].grad, pr[n].grad))
+    # a second step through the module API after an optimizer update still agrees (plan reuse, re-packed weights)
+    with torch.no_grad():
+        for n, p in pn.items():
+            if p.grad is not None:
+                p -= 1e-3 * p.grad
+                pr[n] -= 1e-3 * p.grad
+    with torch.no_grad():
+        ro2, no2 = ref(img), new(img)
+    assert (no2 - ro2).abs().max().item() < 2 * tol
