@@ -146,7 +146,7 @@ def run_reference(args):
                       "note": "reference CPU training loop (oracle port of the reference modules, fp32, all host threads)"},
            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    _emit(out)
     return 0
 
 
@@ -292,15 +292,27 @@ def run_ours(args):
                "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
                        "ms_per_step": ms_e2e},
                "gpu_launches": n_launch, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
-        print(json.dumps(out), flush=True)
+        _emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+def _emit(out: dict):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    _RESULT.write(json.dumps(out) + "\n")
+    _RESULT.flush()
+
+
 def main():
+    global _RESULT
     args = parse()
+    # Native libraries write to file descriptor 1 (NCCL prints its version banner there at communicator creation):
+    # keep the original stdout for the result line only and send everything else to stderr.
+    sys.stdout.flush()
+    _RESULT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -233,7 +233,9 @@ class TrainStep:
         main = torch.cuda.current_stream(self.device)
         if self.seg_graphs is not None:
             for i, (g, k) in enumerate(self.seg_graphs):
-                (head if (i == 0 and head is not None) else g).replay()
+                g = head if (i == 0 and head is not None) else g
+                if g is not None:
+                    g.replay()
                 if k is not None:
                     self._fork_allreduce(k)
             main.wait_stream(self.comm_stream)
@@ -268,9 +270,11 @@ class TrainStep:
             # one graph per segment between bucket boundaries + one for the optimizer; NCCL stays outside the graphs
             graphs = []
             for launches, k in self._segments():
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                    self._run_list(launches)
+                g = None   # buckets that become final at the same point leave an empty segment: nothing to replay
+                if launches:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                        self._run_list(launches)
                 graphs.append((g, k))
             og = torch.cuda.CUDAGraph()
             with torch.cuda.graph(og, capture_error_mode="thread_local"):
