@@ -315,6 +315,12 @@ int mtbc_hard_dice_counts(const float* logits, const float* target, int64_t n, l
  * by the caller) -- the inputs of calculate_metrics (utils/metrics.py, called at utils/models.py:335) without moving
  * the masks to the host. */
 int mtbc_confusion_counts(const uint8_t* mask, const float* target, int32_t N, int64_t HW, long long* out, void* stream);
+/* The reference's Hausdorff distance (utils/metrics.py:236-252: scipy directed_hausdorff on the (H, W) boolean images,
+ * each image ROW a point of {0,1}^W) as integers: out[n][4] (int32, overwritten) = max_i min_j Hamming(mask row i,
+ * target row j), the same with the roles swapped, #mask pixels, #target pixels.  The distance is the square root of
+ * the larger of the first two; the caller applies the reference's empty-mask rules. */
+int mtbc_row_hausdorff(const uint8_t* mask, const float* target, int32_t N, int32_t H, int32_t W, int32_t* out,
+                       void* stream);
 /* Epoch bookkeeping of train_one_epoch / validate_one_epoch (training_multitask.py:99,108-109,146-152) without host
  * syncs: acc[0..5] (double) += total, seg, cls, nan flag, hard Dice of the batch (metrics.py:255-267 from counts =
  * tp/fp/fn of mtbc_hard_dice_counts, which is zeroed afterwards), 1; confusion[gt*K+pred] (int64) += 1 per sample. */

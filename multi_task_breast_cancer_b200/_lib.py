@@ -115,6 +115,7 @@ _SIGS = {
     "mtbc_refine_predictions": [c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp],
     "mtbc_hard_dice_counts": [c_vp, c_vp, c_i64, c_vp, c_vp],
     "mtbc_confusion_counts": [c_vp, c_vp, c_i32, c_i64, c_vp, c_vp],
+    "mtbc_row_hausdorff": [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp],
     "mtbc_metrics_accumulate": [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp],
     "mtbc_augment_batch": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp],
     "mtbc_adam_step": [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32, c_vp],

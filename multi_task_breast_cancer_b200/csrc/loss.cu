@@ -292,6 +292,65 @@ __global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ p, co
 }
 __global__ void increment_i32_kernel(int32_t* p) { p[0] += 1; }
 
+// Hausdorff distance exactly as the reference computes it (utils/metrics.py:236-252): scipy's directed_hausdorff on the
+// two (H, W) boolean images, i.e. each image ROW is one point of {0,1}^W, so the distance between two rows is
+// sqrt(Hamming distance).  Integer work: rows are packed to bit words in shared memory (one ballot per 32 pixels),
+// every thread owns rows of u and scans all rows of v with XOR + popcount.  grid = (2 directions, N);
+// out[n] = {max_i min_j d2(seg_i, gt_j), max_i min_j d2(gt_i, seg_j), #seg pixels, #gt pixels}.
+__global__ void __launch_bounds__(256) row_hausdorff_kernel(const uint8_t* __restrict__ mask,
+                                                            const float* __restrict__ target, int H, int W,
+                                                            int* __restrict__ out) {
+  extern __shared__ uint32_t s_bits[];  // [2][H][Wd]
+  __shared__ int s_max, s_cnt[2];
+  const int n = blockIdx.y, dir = blockIdx.x;
+  const int Wd = (W + 31) / 32;
+  const int64_t HW = static_cast<int64_t>(H) * W;
+  const uint8_t* m = mask + n * HW;
+  const float* t = target + n * HW;
+  uint32_t* sb = s_bits;
+  uint32_t* gb = s_bits + H * Wd;
+  if (threadIdx.x == 0) { s_max = 0; s_cnt[0] = 0; s_cnt[1] = 0; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int c0 = 0, c1 = 0;
+  for (int idx = warp; idx < H * Wd; idx += 8) {
+    const int r = idx / Wd, w = idx - r * Wd;
+    const int col = w * 32 + lane;
+    bool sv = false, gv = false;
+    if (col < W) {
+      sv = m[static_cast<int64_t>(r) * W + col] != 0;
+      gv = t[static_cast<int64_t>(r) * W + col] != 0.f;
+    }
+    const uint32_t sw = __ballot_sync(0xffffffffu, sv), gw = __ballot_sync(0xffffffffu, gv);
+    if (lane == 0) { sb[idx] = sw; gb[idx] = gw; c0 += __popc(sw); c1 += __popc(gw); }
+  }
+  if (lane == 0) { atomicAdd(&s_cnt[0], c0); atomicAdd(&s_cnt[1], c1); }
+  __syncthreads();
+  const uint32_t* u = dir == 0 ? sb : gb;
+  const uint32_t* v = dir == 0 ? gb : sb;
+  int worst = 0;
+  for (int i = threadIdx.x; i < H; i += 256) {
+    uint32_t ur[32];
+#pragma unroll
+    for (int w = 0; w < 32; ++w) ur[w] = w < Wd ? u[i * Wd + w] : 0u;
+    int best = 0x7fffffff;
+    for (int j = 0; j < H; ++j) {
+      int d = 0;
+#pragma unroll
+      for (int w = 0; w < 32; ++w)
+        if (w < Wd) d += __popc(ur[w] ^ v[j * Wd + w]);
+      best = min(best, d);
+    }
+    worst = max(worst, best);
+  }
+  atomicMax(&s_max, worst);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    out[n * 4 + dir] = s_max;
+    if (dir == 0) { out[n * 4 + 2] = s_cnt[0]; out[n * 4 + 3] = s_cnt[1]; }
+  }
+}
+
 }  // namespace mtbc
 
 using namespace mtbc;
@@ -354,6 +413,16 @@ int mtbc_confusion_counts(const uint8_t* mask, const float* target, int32_t N, i
   int gx = cdiv(HW, 256 * 16 * 4); if (gx < 1) gx = 1; if (gx > 64) gx = 64;
   confusion_counts_kernel<<<dim3(gx, N), 256, 0, ST(stream)>>>(mask, target, HW, reinterpret_cast<unsigned long long*>(out));
   return check_launch("confusion_counts");
+}
+int mtbc_row_hausdorff(const uint8_t* mask, const float* target, int32_t N, int32_t H, int32_t W, int32_t* out,
+                       void* stream) {
+  if (N <= 0) return 0;
+  if (H <= 0 || W <= 0 || W > 1024) return set_error(MTBC_ERR_INVALID, "row_hausdorff: W must be in [1, 1024]");
+  const size_t smem = 2 * static_cast<size_t>(H) * ((W + 31) / 32) * sizeof(uint32_t);
+  if (smem > 200 * 1024) return set_error(MTBC_ERR_INVALID, "row_hausdorff: the packed images do not fit shared memory");
+  { static bool done = false; if (smem > 48 * 1024 && !done) { cudaFuncSetAttribute(row_hausdorff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); done = true; } }
+  row_hausdorff_kernel<<<dim3(2, N), 256, smem, ST(stream)>>>(mask, target, H, W, out);
+  return check_launch("row_hausdorff");
 }
 int mtbc_metrics_accumulate(const float* loss4, long long* counts, const float* class_logits, const float* onehot,
                             int32_t B, int32_t K, double* acc, long long* confusion, void* stream) {

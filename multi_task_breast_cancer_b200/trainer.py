@@ -53,14 +53,25 @@ def classification_scores(confusion: Sequence[Sequence[int]]) -> Tuple[float, fl
     return acc, f1w / total
 
 
-def segmentation_metrics_from_counts(tp: float, fp: float, fn: float, tn: float) -> Dict[str, float]:
-    """calculate_metrics (src/utils/metrics.py:26-76) from the four cardinalities.  The Hausdorff distance needs the
-    masks themselves (scipy on the host) and is reported as NaN here."""
+def hausdorff_from_row_distances(d2_seg_to_gt: int, d2_gt_to_seg: int, n_seg: int, n_gt: int) -> float:
+    """haussdorf_distance (src/utils/metrics.py:236-252) from the integers of `mtbc_row_hausdorff`: the reference hands
+    the (H, W) boolean images to scipy's directed_hausdorff, so rows are the points and distances are sqrt(Hamming);
+    NaN when exactly one mask is empty, 0 when both are (the reference's `hd = 0` is then recomputed as 0 by its
+    else branch)."""
+    if (n_seg == 0) != (n_gt == 0):
+        return float("nan")
+    return math.sqrt(float(max(int(d2_seg_to_gt), int(d2_gt_to_seg))))
+
+
+def segmentation_metrics_from_counts(tp: float, fp: float, fn: float, tn: float,
+                                     hausdorff: float = float("nan")) -> Dict[str, float]:
+    """calculate_metrics (src/utils/metrics.py:26-76) from the four cardinalities; the Hausdorff distance is passed in
+    (hausdorff_from_row_distances) or NaN."""
     tp, fp, fn, tn = float(tp), float(fp), float(fn), float(tn)
     gt_empty, seg_empty = (tp + fn) == 0, (tp + fp) == 0
     nan = float("nan")
     return {
-        "Haussdorf distance": nan,
+        "Haussdorf distance": hausdorff,
         "DICE": (1.0 if seg_empty else 0.0) if gt_empty else 2 * tp / (2 * tp + fp + fn),
         "Sensitivity": nan if tp == 0 else tp / (tp + fn),
         "Specificity": tn / (tn + fp) if (tn + fp) > 0 else nan,
@@ -413,11 +424,13 @@ def load_pretrained_model(model: torch.nn.Module, ckpt_path: str):
 @torch.no_grad()
 def inference_multitask(model: torch.nn.Module, test_loader: Iterable, device=None, threshold: int = 0,
                         overlap_seg_based_on_class: bool = False, overlap_class_based_on_seg: bool = False,
-                        num_classes: int = 3, normal_id: int = 2, keep: Optional[Dict[str, List]] = None):
+                        num_classes: int = 3, normal_id: int = 2, keep: Optional[Dict[str, List]] = None,
+                        hausdorff: bool = True):
     """Batched inference_multitask_multiclass_classification_segmentation (src/utils/models.py:273-397): one forward per
-    batch, refinement (`mtbc_refine_predictions`) and per-image tp/fp/fn/tn (`mtbc_confusion_counts`) on the device,
-    one device->host read at the end.  Returns (segmentation_rows, classification_rows): lists of dicts with the
-    columns of results_segmentation.csv (Hausdorff excepted: NaN) and results_classification.csv.  File output (PNG
+    batch, refinement (`mtbc_refine_predictions`), per-image tp/fp/fn/tn (`mtbc_confusion_counts`) and the reference's
+    row-wise Hausdorff distance (`mtbc_row_hausdorff`; `hausdorff=False` reports NaN instead) on the device, one
+    device->host read at the end.  Returns (segmentation_rows, classification_rows): lists of dicts with the
+    columns of results_segmentation.csv and results_classification.csv.  File output (PNG
     masks, CSVs) stays with the caller: pass a dict as `keep` to receive, per batch, the refined uint8 masks
     (`keep['masks']`), the full-decoder mask logits and the averaged class logits (device tensors)."""
     from .criterions import refine_predictions
@@ -446,23 +459,30 @@ def inference_multitask(model: torch.nn.Module, test_loader: Iterable, device=No
             counts = torch.zeros(B, 4, dtype=torch.int64, device=dev)
             _lib.call("mtbc_confusion_counts", ptr(rmask), ptr(mask), B, mask[0].numel(), ptr(counts),
                       C.c_void_p(stream_ptr()))
+            hd = None
+            if hausdorff:
+                hd = torch.zeros(B, 4, dtype=torch.int32, device=dev)
+                _lib.call("mtbc_row_hausdorff", ptr(rmask), ptr(mask), B, mask.shape[-2], mask.shape[-1], ptr(hd),
+                          C.c_void_p(stream_ptr()))
         if label.dim() >= 2 and label.shape[-1] == num_classes:
             gt = label.argmax(-1).flatten()
         else:
             gt = label.flatten().to(torch.int64)
-        per_batch.append((ids, counts, rcls, cls_logits.float(), gt))
+        per_batch.append((ids, counts, rcls, cls_logits.float(), gt, hd))
         if keep is not None:
             keep.setdefault("masks", []).append(rmask)
             keep.setdefault("mask_logits", []).append(seg_logits)
             keep.setdefault("class_logits", []).append(cls_logits)
     seg_rows, cls_rows = [], []
     k = 0
-    for ids, counts, rcls, cl, gt in per_batch:
+    for ids, counts, rcls, cl, gt, hd in per_batch:
         counts, rcls, cl, gt = counts.cpu().tolist(), rcls.cpu().tolist(), cl.cpu().tolist(), gt.cpu().tolist()
+        hd = hd.cpu().tolist() if hd is not None else None
         for b in range(len(rcls)):
             pid = (ids[b].item() if torch.is_tensor(ids) else ids[b]) if ids is not None else k
             row = {"patient_id": pid}
-            row.update(segmentation_metrics_from_counts(*counts[b]))
+            row.update(segmentation_metrics_from_counts(
+                *counts[b], hausdorff=hausdorff_from_row_distances(*hd[b]) if hd is not None else math.nan))
             row["class"] = int(gt[b])
             seg_rows.append(row)
             cls_rows.append({"patient_id": pid, "ground_truth": int(gt[b]), "predicted_label": int(rcls[b]),

@@ -18,8 +18,8 @@ What is restated (reference file:line, relative to /root/reference):
   * training step           src/training_multitask.py:79-103 (Adam eps=1e-4, src/utils/experiment_init.py:186-187)
   * prediction refinement   src/utils/models.py:316-332,366-386
   * epoch loops / metrics   src/training_multitask.py:33-159 (train_one_epoch, validate_one_epoch, class lists),
-                            src/utils/metrics.py:26-76,173-267 (calculate_metrics and its scalar helpers, Hausdorff
-                            excepted), src/utils/models.py:273-397 (test-time inference, per image)
+                            src/utils/metrics.py:26-76,173-267 (calculate_metrics and its scalar helpers; the
+                            Hausdorff distance of :236-252 as hausdorff_rows), src/utils/models.py:273-397 (test-time inference, per image)
   * input pipeline          src/dataset/BUSI_dataset.py:97-163 (flip / flip / rotate on cat([mask, image]) through
                             torchvision itself), src/dataset/BUSI_dataloader.py:320-340 (deterministic oversampling;
                             restated for pandas 1.x semantics -- the function does not run under the pandas 3 of this
@@ -670,11 +670,26 @@ def segmentation_metrics(gt, seg):
     }
 
 
+def hausdorff_rows(gt, seg) -> float:
+    """haussdorf_distance (src/utils/metrics.py:236-252) restated in numpy: scipy's directed_hausdorff is handed the two
+    (H, W) boolean images, so every image ROW is one point of {0,1}^W and the distance between rows is
+    sqrt(Hamming).  NaN when exactly one of the masks is empty (the reference's second `if`), 0 when both are."""
+    import numpy as np
+    gt = np.asarray(gt, dtype=bool)
+    seg = np.asarray(seg, dtype=bool)
+    if gt.ndim == 4:
+        gt, seg = gt[0, 0], seg[0, 0]
+    if (gt.sum() == 0) != (seg.sum() == 0):
+        return float("nan")
+    d2 = (seg[:, None, :] != gt[None, :, :]).sum(-1)          # [i, j] = Hamming(seg row i, gt row j)
+    return float(np.sqrt(float(max(d2.min(1).max(), d2.min(0).max()))))
+
+
 @torch.no_grad()
 def inference_multitask(mask_logits, class_logits, masks, labels, overlap_seg_based_on_class=False,
                         overlap_class_based_on_seg=False, normal_id=2):
     """src/utils/models.py:299-386 image by image, GIVEN the model outputs (full-decoder mask logits (B,1,H,W), class
-    logits (B,K)): -> (segmentation rows, classification rows) like the two CSV files (no Hausdorff, no postprocess)."""
+    logits (B,K)): -> (segmentation rows, classification rows) like the two CSV files (no postprocess)."""
     seg_rows, cls_rows = [], []
     for b in range(mask_logits.shape[0]):
         out = (torch.sigmoid(mask_logits[b:b + 1]) > 0.5).float().cpu().numpy()
@@ -683,6 +698,7 @@ def inference_multitask(mask_logits, class_logits, masks, labels, overlap_seg_ba
         if overlap_seg_based_on_class and pred == normal_id:
             seg_out[seg_out > 0] = 0
         row = segmentation_metrics(masks[b:b + 1].cpu().numpy(), seg_out)
+        row["Haussdorf distance"] = hausdorff_rows(masks[b:b + 1].cpu().numpy(), seg_out)
         row["class"] = int(labels[b])
         seg_rows.append(row)
         tumor_pixels = int((out == 1).sum())

@@ -4,8 +4,9 @@ ground truth, empty prediction, both empty, full overlap).  Run in the build con
 
     python tests/golden/make_metrics_golden.py      -> tests/golden/metrics.json
 
-The fixture holds the inputs as packed bits and the reference's outputs (Hausdorff dropped: it is not on the device
-path); tests/test_oracle_golden.py re-checks oracle and host helpers against it anywhere."""
+The fixture holds the inputs as packed bits and the reference's outputs (the Hausdorff distance under "hausdorff":
+the reference's haussdorf_distance through scipy, None for NaN); tests/test_oracle_golden.py re-checks oracle and host
+helpers against it anywhere."""
 import json
 import math
 import os
@@ -35,6 +36,10 @@ for i in range(24):
     if gt.sum() + (1 - seg).sum() == 0 or (1 - gt).sum() == 0:
         continue  # specificity 0/0 raises a numpy warning in the reference; not a case the loop meets
     ref = calculate_metrics(gt, seg, patient=i)
+    hdist = ref["Haussdorf distance"]
+    hdist = None if math.isnan(hdist) else float(hdist)
+    o = O.hausdorff_rows(gt, seg)
+    assert (hdist is None and math.isnan(o)) or (hdist is not None and o == hdist), (i, hdist, o)   # bit-exact
     ref = {k: (None if isinstance(v, float) and math.isnan(v) else float(v)) for k, v in ref.items()
            if k not in ("patient_id", "Haussdorf distance")}
     ora = O.segmentation_metrics(gt, seg)
@@ -45,6 +50,6 @@ for i in range(24):
     logits = torch.from_numpy(seg) * 2 - 1
     assert abs(O.hard_dice(torch.from_numpy(gt), logits) - hd) < 1e-12
     cases.append({"gt": np.packbits(gt.astype(np.uint8)).tolist(), "seg": np.packbits(seg.astype(np.uint8)).tolist(),
-                  "metrics": ref, "hard_dice": hd})
+                  "metrics": ref, "hard_dice": hd, "hausdorff": hdist})
 json.dump({"H": H, "W": W, "cases": cases}, open(os.path.join(HERE, "metrics.json"), "w"))
 print(f"wrote {len(cases)} cases")

@@ -211,3 +211,50 @@ def test_batched_inference_with_refinement_is_exact(flags):
         rl, ro = ref(img)
     agree = ((ro[-1] > 0) == (torch.cat(keep["mask_logits"]) > 0)).float().mean().item()
     assert agree > 0.97, agree
+
+
+def test_row_hausdorff_kernel_is_bit_exact():
+    """mtbc_row_hausdorff + the host rule == the reference's haussdorf_distance (utils/metrics.py:236-252): on the
+    fixture the reference itself produced (24x24: a partial last bit word) and, against the oracle restatement, on
+    ellipse-like and random masks up to 512x512, empty / one-sided-empty cases included."""
+    import json
+    import numpy as np
+    from oracle import torch_oracle as O
+    from multi_task_breast_cancer_b200 import _lib, trainer as T
+    from multi_task_breast_cancer_b200.ops import ptr
+
+    def run(seg, gt):   # (B,1,H,W) uint8 / float32 on the device -> list of distances
+        B, _, H, W = seg.shape
+        out = torch.full((B, 4), -1, dtype=torch.int32, device="cuda")
+        _lib.call("mtbc_row_hausdorff", ptr(seg), ptr(gt), B, H, W, ptr(out), None)
+        torch.cuda.synchronize()
+        rows = out.cpu().tolist()
+        for r, s, g in zip(rows, seg, gt):
+            assert r[2] == int((s != 0).sum()) and r[3] == int((g != 0).sum())
+        return [T.hausdorff_from_row_distances(*r) for r in rows]
+
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metrics.json")))
+    n = fx["H"] * fx["W"]
+    gts = np.stack([np.unpackbits(np.array(c["gt"], dtype=np.uint8))[:n].reshape(1, fx["H"], fx["W"]) for c in fx["cases"]])
+    segs = np.stack([np.unpackbits(np.array(c["seg"], dtype=np.uint8))[:n].reshape(1, fx["H"], fx["W"]) for c in fx["cases"]])
+    got = run(torch.from_numpy(segs).cuda().contiguous(), torch.from_numpy(gts).float().cuda().contiguous())
+    for g, c in zip(got, fx["cases"]):
+        assert (c["hausdorff"] is None and math.isnan(g)) or g == c["hausdorff"], (g, c["hausdorff"])
+
+    gen = torch.Generator().manual_seed(5)
+    for H, W in [(256, 256), (64, 40), (512, 512), (32, 1000)]:
+        B = 5
+        _, mask, _, _ = O.synthetic_batch(B, H, W, seed=H + W) if H == W else (None, None, None, None)
+        gt = mask if mask is not None else (torch.rand(B, 1, H, W, generator=gen) < 0.2).float()
+        seg = ((gt + (torch.rand(B, 1, H, W, generator=gen) < 0.02).float()) > 0).float()
+        seg = torch.roll(seg, shifts=(3, -5), dims=(2, 3))
+        seg[1] = 0                      # empty prediction
+        gt = gt.clone(); gt[2] = 0      # empty ground truth
+        seg[3] = 0; gt[3] = 0           # both empty
+        got = run(seg.to(torch.uint8).cuda().contiguous(), gt.cuda().contiguous())
+        for b in range(B):
+            want = O.hausdorff_rows(gt[b:b + 1].numpy(), seg[b:b + 1].numpy())
+            assert (math.isnan(want) and math.isnan(got[b])) or got[b] == want, (H, W, b, got[b], want)
+    assert math.isnan(got[1]) and math.isnan(got[2]) and got[3] == 0.0
+    lib = _lib.load()
+    assert lib.mtbc_row_hausdorff(None, None, 1, 8, 2048, None, None) != 0     # W > 1024: an error, not a crash

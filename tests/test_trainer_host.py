@@ -41,6 +41,14 @@ def test_segmentation_metrics_match_reference_fixture():
             assert _same(float(ora[k]), v), (k, ora[k], v)
             assert _same(float(mine[k]), v), (k, mine[k], v)
         assert abs(O.hard_dice(torch.from_numpy(gt).float(), torch.from_numpy(seg).float() * 2 - 1) - c["hard_dice"]) < 1e-12
+        # Hausdorff distance as the reference computes it (rows are the points): oracle bit-exact, and the product's
+        # host rule fed with the integers the device kernel produces (computed here in numpy)
+        ho = O.hausdorff_rows(gt, seg)
+        assert (c["hausdorff"] is None and math.isnan(ho)) or ho == c["hausdorff"]
+        d2 = (seg[0, 0][:, None, :] != gt[0, 0][None, :, :]).sum(-1)
+        hm = T.hausdorff_from_row_distances(int(d2.min(1).max()), int(d2.min(0).max()), int(seg.sum()), int(gt.sum()))
+        assert (c["hausdorff"] is None and math.isnan(hm)) or hm == c["hausdorff"]
+        assert math.isnan(mine["Haussdorf distance"])    # not supplied -> NaN
         n += 1
     assert n >= 20
 
