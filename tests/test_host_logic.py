@@ -154,3 +154,20 @@ def test_data_parallel_mean_equals_full_batch_gloo():
         a, b = ranges[n]
         want[a:b] = p.grad.reshape(-1)
     torch.testing.assert_close(flat, want, rtol=2e-3, atol=1e-6)
+
+
+def test_step_segments_split_at_bucket_markers():
+    """TrainStep._segments: the launch list is cut at every bucket marker, in order, each cut carrying the bucket whose
+    all-reduce is forked there; markers that coincide leave an EMPTY segment (not captured, nothing to replay) and the
+    tail after the last marker has no bucket."""
+    from types import SimpleNamespace
+    from multi_task_breast_cancer_b200.train import TrainStep
+
+    def L(kind, bucket=None):
+        return SimpleNamespace(kind=kind, bucket=bucket)
+    fb = [L("a"), L("b"), L("bucket_ready", 0), L("c"), L("bucket_ready", 1), L("bucket_ready", 2), L("d"), L("e"),
+          L("bucket_ready", 3)]
+    segs = TrainStep._segments(SimpleNamespace(launches_fb=fb))
+    assert [[l.kind for l in ls] for ls, _ in segs] == [["a", "b"], ["c"], [], ["d", "e"], []]
+    assert [k for _, k in segs] == [0, 1, 2, 3, None]
+    assert sum(len(ls) for ls, _ in segs) == sum(l.kind != "bucket_ready" for l in fb)
