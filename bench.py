@@ -299,6 +299,9 @@ def run_ours(args):
     return 0
 
 
+_RESULT = sys.stdout
+
+
 def _emit(out: dict):
     """The ONE JSON line of the contract, on the process's original stdout."""
     _RESULT.write(json.dumps(out) + "\n")
