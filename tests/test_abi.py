@@ -49,3 +49,24 @@ def test_invalid_descriptor_is_an_error_not_a_crash(lib):
     h = C.c_void_p()
     rc = lib.mtbc_conv_gemm_create(C.byref(d), C.byref(h))
     assert rc != 0 and b"conv_gemm" in lib.mtbc_last_error()
+
+
+def test_product_package_never_imports_the_oracle_or_aten_compute():
+    """The oracle is test infrastructure: nothing under multi_task_breast_cancer_b200/ may import it, and the package
+    may not reach ATen's conv / norm / pooling kernels (the hot path is libmtbc.so or an error)."""
+    import ast
+    pkg = os.path.join(ROOT, "multi_task_breast_cancer_b200")
+    banned_calls = {"conv2d", "conv_transpose2d", "instance_norm", "batch_norm", "max_pool2d", "leaky_relu",
+                    "interpolate", "adaptive_avg_pool2d", "linear"}
+    for fn in sorted(os.listdir(pkg)):
+        if not fn.endswith(".py"):
+            continue
+        tree = ast.parse(open(os.path.join(pkg, fn)).read())
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Import):
+                assert not any(a.name.split(".")[0] == "oracle" for a in node.names), fn
+            if isinstance(node, ast.ImportFrom):
+                assert (node.module or "").split(".")[0] != "oracle", fn
+                assert (node.module or "") != "torch.nn.functional", fn
+            if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute):
+                assert node.func.attr not in banned_calls, (fn, node.func.attr, node.lineno)
