@@ -28,6 +28,14 @@ MODEL_NAMES = {"unetpp": "MTUNetPlusPlus(deep_supervision=True)", "nnunet": "MTn
 TRAIN_GFLOP = {("unetpp", 256): 128.29, ("unetpp", 512): 513.16, ("nnunet", 256): 68.90, ("nnunet", 128): 17.23, ("bts", 128): 15.29}
 
 
+def config_of(arch: str, batch: int, size: int, world: int) -> dict:
+    """`config` of the JSON line -- the SAME dictionary for both arms (the reference arm times the reference's CPU
+    loop 'on our arm's config'; what it actually sampled is in its cpu_baseline.sample)."""
+    return {"workload": workload(arch, batch, size), "arch": arch, "batch_per_gpu": batch, "global_batch": world * batch,
+            "size": size, "parallelism": f"dp{world}", "l2": "per-step working set (GBs of activations) >> 126 MB L2",
+            "cuda_graph": True}
+
+
 def workload(arch: str, batch: int, size: int) -> str:
     """The default (unetpp, 32, 256) is BASELINE.json configs[1]; --arch nnunet is configs[2], --size 512 configs[4]."""
     return (f"{MODEL_NAMES[arch]} training step, batch {batch}/GPU, 1x{size}x{size}, 3 classes, Dice+focal, "
@@ -46,9 +54,14 @@ def parse():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--arch", default="unetpp", choices=["unetpp", "nnunet", "bts"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-batch", type=int, default=4)
-    ap.add_argument("--cpu-steps", type=int, default=3)
-    return ap.parse_args()
+    ap.add_argument("--no-library-baseline", action="store_true")
+    ap.add_argument("--cpu-batch", type=int, default=0, help="batch of the CPU arm (0: the workload's own batch at "
+                    "<= 256x256, 8 at 512x512 where one CPU step of 32 images takes ~25 s)")
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    a = ap.parse_args()
+    if a.cpu_batch <= 0:
+        a.cpu_batch = a.batch if a.size <= 256 else min(a.batch, 8)
+    return a
 
 
 def measured_peaks():
@@ -132,18 +145,76 @@ def cpu_reference_loop(arch, B, size, steps, warmup):
             "cores": cores, "batch": B, "steps": steps}
 
 
+def library_baseline(arch, B, size, steps, warmup, dev):
+    """'The Blackwell kernel to beat' (SURVEY 2.2 / 8d): the reference's modules (oracle restatement, pinned bit-exactly
+    against /root/reference) under plain torch eager on the SAME GPU, same batch, same step (forward + Dice/focal +
+    backward + Adam(eps 1e-4)), i.e. cuDNN / cuBLAS / ATen kernels -- once in fp32 with TF32 tensor cores allowed, once
+    under bf16 autocast with channels_last.  cudnn.benchmark is on (the library gets to pick its fastest algorithm).
+    Checker leg: runs after, and outside, every timed region of our arm; nothing of it is on the product path."""
+    import torch
+    from oracle import torch_oracle as O
+    out = {"what": "reference modules under torch eager on this GPU (cuDNN/cuBLAS/ATen), same step and batch",
+           "torch": torch.__version__, "cudnn": torch.backends.cudnn.version(), "batch": B, "steps": steps}
+    mk = {"unetpp": lambda: O.MTUNetPlusPlus(in_channels=1, out_channels=1, n_classes=3, deep_supervision=True),
+          "nnunet": lambda: O.MTnnUNet(1, 1, 3), "bts": lambda: O.Multi_BTS_UNet(1, 1, 3, 32, True)}[arch]
+    img, mask, onehot, _ = O.synthetic_batch(B, size, size, device=dev)
+    dice, focal = O.DiceLoss(), O.FocalLoss(alpha=1, gamma=2)
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    try:
+        for key, autocast in (("tf32", False), ("bf16_autocast_channels_last", True)):
+            torch.manual_seed(1993)
+            torch.backends.cudnn.allow_tf32 = True
+            torch.backends.cuda.matmul.allow_tf32 = True
+            torch.backends.cudnn.benchmark = True
+            model = mk().to(dev)
+            x = img
+            if autocast:
+                model = model.to(memory_format=torch.channels_last)
+                x = img.contiguous(memory_format=torch.channels_last)
+            opt = O.make_optimizer(model, 1e-4)
+
+            def step():
+                opt.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                    logits, outs = model(x)
+                    seg, cls = O.multitask_criterion(dice, mask, outs, focal, onehot, logits, True)
+                    total = 0.35 * seg + 0.65 * cls
+                total.backward()
+                opt.step()
+                return total
+            for _ in range(max(3, warmup)):
+                step()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / steps
+            out[key + "_img_s"] = B / (ms * 1e-3)
+            out[key + "_ms_per_step"] = ms
+            del model, opt
+            torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001 - a baseline that cannot run is reported, it never fails our arm
+        out["error"] = f"{type(e).__name__}: {e}"[:300]
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     B = args.cpu_batch
-    r = cpu_reference_loop(args.arch, B, args.size, max(1, min(args.steps, 5)), max(1, min(args.warmup, 1)))
-    sample = f"{r['steps']} timed steps of batch {B} (of the 32/GPU workload) after 1 warm-up, median"
+    r = cpu_reference_loop(args.arch, B, args.size, max(1, min(args.steps, 3)), max(1, min(args.warmup, 1)))
+    sample = f"{r['steps']} timed steps of batch {B} (the workload's batch is {args.batch}/GPU) after 1 warm-up, median"
     out = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
            "steps": r["steps"], "warmup": 1, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": workload(args.arch, args.batch, args.size), "arch": args.arch, "size": args.size, "batch_per_step": B,
-                      "note": "reference CPU training loop (oracle port of the reference modules, fp32, all host threads)"},
+           "config": config_of(args.arch, args.batch, args.size, args.gpus),
+           "note": f"reference CPU training loop (oracle port of the reference modules, fp32, all host threads), batch {B} per step",
            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _emit(out)
@@ -261,14 +332,21 @@ def run_ours(args):
         tc_fl = sum(agg[k]["flops"] for k in tc_kinds)
         achieved = agg[top]["flops"] / (agg[top]["ms"] * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
-        traffic = None
+        traffic, traffic_note = None, "profiles/traffic.json absent"
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
-            t = json.load(open(tp)).get("by_kind", {}).get(top)
-            if t and agg[top]["n"]:
+            from multi_task_breast_cancer_b200 import build as _build
+            tj = json.load(open(tp))
+            t = tj.get("by_kind", {}).get(top)
+            # the ncu pass is a separate run: only quote it when it profiled THIS build of the kernels
+            if tj.get("build_digest") != _build.lib_digest():
+                traffic_note = f"profiles/traffic.json ({tj.get('tag')}) was captured on another build: not quoted"
+            elif t and agg[top]["n"]:
                 traffic = t["dram_bytes_per_step"] / agg[top]["n"]  # mean DRAM bytes per launch (ncu, profiles/)
+                traffic_note = f"ncu launch list {tj.get('tag')} of this build (digest {str(tj.get('build_digest'))[:12]})"
         roofline = {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": traffic, "peak_source": peaks["source"] + " sustained",
+                    "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note,
+                    "peak_source": peaks["source"] + " sustained",
                     "launches_per_step": agg[top]["n"], "kernel_ms_per_step": agg[top]["ms"],
                     "share_of_step": agg[top]["ms"] / tot_ms,
                     "all_tensor_kernels": {"achieved": tc_fl / (tc_ms * 1e-3) / 1e12, "frac": tc_fl / (tc_ms * 1e-3) / 1e12 / peak,
@@ -280,18 +358,24 @@ def run_ours(args):
             cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                    "sample": f"{r['steps']} timed steps of batch {r['batch']} of the same workload on the host CPU after 1 warm-up "
                              f"(median {r['ms_per_step']:.0f} ms/step)"}
+        lib = None
+        if not args.no_library_baseline and world == 1:
+            lib = library_baseline(args.arch, B, S, 10, 3, dev)
+            if lib.get("bf16_autocast_channels_last_img_s"):
+                lib["ours_over_bf16"] = (B / (ms_dev * 1e-3)) / lib["bf16_autocast_channels_last_img_s"]
+            if lib.get("tf32_img_s"):
+                lib["ours_over_tf32"] = (B / (ms_dev * 1e-3)) / lib["tf32_img_s"]
         h2d = (h_img.numel() + h_mask.numel() + h_onehot.numel()) * 4
         n_launch = (ts.n_launches + 2) * args.steps   # + the two extra device launches behind the refinement entry point
         out = {"metric": METRIC, "value": world * B / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-               "config": {"workload": workload(args.arch, B, S), "arch": args.arch, "batch_per_gpu": B, "global_batch": world * B,
-                          "size": S, "parallelism": f"dp{world}", "l2": "per-step working set (GBs of activations) >> 126 MB L2",
-                          "cuda_graph": True},
+               "config": config_of(args.arch, B, S, world),
                "tflops_true": world * B * TRAIN_GFLOP[(args.arch, S)] / ms_dev if (args.arch, S) in TRAIN_GFLOP else None,
                "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
                        "ms_per_step": ms_e2e},
-               "gpu_launches": n_launch, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+               "gpu_launches": n_launch, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+               "library_baseline": lib}
         _emit(out)
     if world > 1:
         dist.barrier()

@@ -28,6 +28,9 @@ enum mtbc_status {
 const char* mtbc_last_error(void);
 /* Library ABI version (bumped on any struct change). */
 int mtbc_abi_version(void);
+/* SHA-256 (hex) of the sources and compiler flags this binary was built from; the host binding refuses to run a
+ * library whose digest differs from the sources next to it (a stale .so after a checkout). */
+const char* mtbc_build_digest(void);
 /* 0 if the current device is sm_100 and the tensor-map driver entry point resolves. */
 int mtbc_device_check(void);
 

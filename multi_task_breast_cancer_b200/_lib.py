@@ -129,7 +129,8 @@ _SIGS = {
 }
 _RESTYPES = {"mtbc_op_destroy": None, "mtbc_op_flops": c_f64}
 
-EXPORTED_SYMBOLS = sorted(list(_SIGS) + ["mtbc_last_error"])
+EXPORTED_SYMBOLS = sorted(list(_SIGS) + ["mtbc_last_error", "mtbc_build_digest"])
+ABI_VERSION = 3
 
 
 class MtbcError(RuntimeError):
@@ -144,10 +145,19 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    from . import build as _b
+    if _b.lib_digest() != _b._digest():
+        # stale or missing binary: rebuild from the sources next to it when a compiler is there, else fail loudly
+        try:
+            _b.build()
+        except Exception as e:  # noqa: BLE001 - reported as the loader's error below
+            if LIB_PATH.exists():
+                raise MtbcError(f"{LIB_PATH} was built from other sources and could not be rebuilt: {e}") from e
     if not LIB_PATH.exists():
         raise MtbcError(f"{LIB_PATH} not found: build it with `python -m multi_task_breast_cancer_b200.build` "
                         "(or __graft_entry__.build()); there is no fallback path")
     lib = C.CDLL(str(LIB_PATH))
+    _verify(lib)
     for name, args in _SIGS.items():
         fn = getattr(lib, name)
         fn.argtypes = args
@@ -156,6 +166,27 @@ def load():
     lib.mtbc_last_error.restype = C.c_char_p
     _lib = lib
     return lib
+
+
+def _verify(lib):
+    """Refuse a stale binary: the digest compiled into the library must equal the digest of the sources on disk, and
+    the ABI version must be the one these ctypes signatures were written for.  (A stamp file next to the .so could not
+    tell: the .so is git-ignored, so a checkout changes the sources but not the binary.)"""
+    try:
+        fn = lib.mtbc_build_digest
+    except AttributeError:
+        raise MtbcError(f"{LIB_PATH} predates mtbc_build_digest: rebuild it (python -m multi_task_breast_cancer_b200.build)")
+    fn.restype, fn.argtypes = C.c_char_p, []
+    have = fn().decode()
+    lib.mtbc_abi_version.restype, lib.mtbc_abi_version.argtypes = c_i32, []
+    if lib.mtbc_abi_version() != ABI_VERSION:
+        raise MtbcError(f"{LIB_PATH}: ABI version {lib.mtbc_abi_version()}, this binding needs {ABI_VERSION}: rebuild")
+    from . import build as _b
+    if (_b.CSRC / "api.cu").exists():          # sources present (always, in-tree): compare
+        want = _b._digest()
+        if have != want:
+            raise MtbcError(f"{LIB_PATH} was built from other sources (digest {have[:12]}.. != {want[:12]}..): "
+                            "rebuild it with `python -m multi_task_breast_cancer_b200.build`")
 
 
 def check(rc: int, what: str = ""):

@@ -14,7 +14,6 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libmtbc.so"
-STAMP = PKG_DIR / ".libmtbc.stamp"
 
 SOURCES = ["api.cu", "conv_gemm.cu", "conv_halo.cu", "pack.cu", "stream_ops.cu", "stream_pipe.cu", "heads.cu", "loss.cu", "augment.cu"]
 NVCC_FLAGS = [
@@ -43,10 +42,26 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def lib_digest(path: Path = LIB_PATH):
+    """Source digest compiled into an existing libmtbc.so (`mtbc_build_digest`), or None if it cannot be read."""
+    if not path.exists():
+        return None
+    import ctypes
+    try:
+        lib = ctypes.CDLL(str(path))
+        fn = lib.mtbc_build_digest
+    except (OSError, AttributeError):
+        return None
+    fn.restype = ctypes.c_char_p
+    fn.argtypes = []
+    return fn().decode()
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every CUDA source for sm_100a into libmtbc.so (skipped when sources are unchanged)."""
+    """Compile every CUDA source for sm_100a into libmtbc.so.  Skipped only when the digest COMPILED INTO the library
+    on disk equals the digest of the sources on disk (no side-car stamp file that could outlive a checkout)."""
     digest = _digest()
-    if not force and LIB_PATH.exists() and STAMP.exists() and STAMP.read_text().strip() == digest:
+    if not force and lib_digest() == digest:
         return LIB_PATH
     objs = []
     build_dir = PKG_DIR / "build"
@@ -55,6 +70,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     for src in SOURCES:
         obj = build_dir / (src + ".o")
         cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        if src == "api.cu":
+            cmd.insert(1, f'-DMTBC_BUILD_DIGEST="{digest}"')
         procs.append((src, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(str(obj))
     log = []
@@ -71,8 +88,10 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if verbose:
         print("\n".join(log))
     link = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB_PATH), *objs]
+    tmp = LIB_PATH.with_suffix(".so.tmp")
+    link[link.index(str(LIB_PATH))] = str(tmp)
     subprocess.run(link, check=True)
-    STAMP.write_text(digest)
+    os.replace(tmp, LIB_PATH)   # a process that already mapped the old file keeps its inode
     return LIB_PATH
 
 

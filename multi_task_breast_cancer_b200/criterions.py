@@ -31,8 +31,29 @@ def _require_cuda(*ts):
             raise _lib.MtbcError("criteria run on CUDA sm_100a only (no CPU fallback)")
 
 
+def _on_device_of(fn):
+    """Run `fn` with the first tensor argument's device current: allocations and `torch.cuda.current_stream()` (the
+    launch stream, `_st()`) then belong to the device that holds the data, whichever device is current outside."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kw):
+        dev = next((a.device for a in args if torch.is_tensor(a) and a.is_cuda), None)
+        if dev is None:
+            for a in args:   # lists of heads (deep supervision)
+                if isinstance(a, (list, tuple)) and a and torch.is_tensor(a[-1]) and a[-1].is_cuda:
+                    dev = a[-1].device
+                    break
+        if dev is None:
+            return fn(*args, **kw)
+        with torch.cuda.device(dev):
+            return fn(*args, **kw)
+    return wrapped
+
+
 class _DiceFn(torch.autograd.Function):
     @staticmethod
+    @_on_device_of
     def forward(ctx, logits, target):
         _require_cuda(logits, target)
         logits = logits.contiguous().float()
@@ -50,6 +71,7 @@ class _DiceFn(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @_on_device_of
     def backward(ctx, g):
         logits, target, sums = ctx.saved_tensors
         B, Cc = logits.shape[0], logits.shape[1]
@@ -80,6 +102,7 @@ class DiceLoss(torch.nn.Module):
 
 class _FocalFn(torch.autograd.Function):
     @staticmethod
+    @_on_device_of
     def forward(ctx, logits, target, alpha, gamma):
         _require_cuda(logits, target)
         logits = logits.contiguous().float()
@@ -92,6 +115,7 @@ class _FocalFn(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @_on_device_of
     def backward(ctx, g):
         logits, target = ctx.saved_tensors
         N, K = logits.shape
@@ -148,15 +172,17 @@ def init_criterion_classification(n_classes: int = 2, classes_weighted=None, cla
     raise NotImplementedError("only the 3-class FocalLoss(alpha=1, gamma=2) criterion is on the accelerated hot path")
 
 
+@_on_device_of
 def refine_predictions(mask_logits: torch.Tensor, class_logits: torch.Tensor, normal_id: int = 2,
                        overlap_seg_based_on_class: bool = True, overlap_class_based_on_seg: bool = True,
                        threshold: int = 0):
     """Batched prediction-refining module: returns (uint8 mask (B,1,H,W), int32 class (B,), int32 pixel count (B,))."""
-    _require_cuda(mask_logits, class_logits)
-    if isinstance(mask_logits, list):
+    # the models return lists under deep supervision (utils/models.py:313,360-361): last head, mean of the class logits
+    if isinstance(mask_logits, (list, tuple)):
         mask_logits = mask_logits[-1]
-    if isinstance(class_logits, list):
-        class_logits = torch.mean(torch.stack(class_logits, dim=0), dim=0)
+    if isinstance(class_logits, (list, tuple)):
+        class_logits = torch.mean(torch.stack(list(class_logits), dim=0), dim=0)
+    _require_cuda(mask_logits, class_logits)
     mask_logits = mask_logits.contiguous().float()
     class_logits = class_logits.contiguous().float()
     B = mask_logits.shape[0]
@@ -171,6 +197,7 @@ def refine_predictions(mask_logits: torch.Tensor, class_logits: torch.Tensor, no
     return mask, cls, cnt
 
 
+@_on_device_of
 def hard_dice_counts(mask_logits: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     """tp/fp/fn of (logit > 0) vs target over the whole batch (training_multitask.py:65-71 without the host sync)."""
     _require_cuda(mask_logits, target)

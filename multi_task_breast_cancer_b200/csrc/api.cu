@@ -30,7 +30,12 @@ struct mtbc_op {
 extern "C" {
 
 const char* mtbc_last_error(void) { return mtbc::g_err; }
-int mtbc_abi_version(void) { return 2; }
+int mtbc_abi_version(void) { return 3; }
+#ifndef MTBC_BUILD_DIGEST
+#define MTBC_BUILD_DIGEST "unstamped"
+#endif
+// SHA-256 of the sources + flags this binary was compiled from (build.py:_digest); _lib.load() refuses a mismatch.
+const char* mtbc_build_digest(void) { return MTBC_BUILD_DIGEST; }
 
 int mtbc_device_check(void) {
   int dev = 0;

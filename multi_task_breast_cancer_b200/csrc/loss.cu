@@ -13,7 +13,10 @@ __global__ void __launch_bounds__(256) dice_sums_kernel(const float* __restrict_
   const int n = blockIdx.y;
   const float4* x4 = reinterpret_cast<const float4*>(logits + static_cast<int64_t>(n) * HW);
   const float4* t4 = reinterpret_cast<const float4*>(target + static_cast<int64_t>(n) * HW);
-  const int64_t nv = HW / 4;
+  // 128-bit loads only when every sample's base address is 16-byte aligned (HW % 4 == 0 and aligned tensors); e.g.
+  // 125 x 125 masks take the scalar loop below for the whole plane instead of faulting on a misaligned float4
+  const bool vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(target)) & 15) == 0;
+  const int64_t nv = vec ? HW / 4 : 0;
   float sI = 0.f, sG = 0.f, sP = 0.f;
   for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < nv; i += gridDim.x * 256ll) {
     const float4 x = x4[i], t = t4[i];
@@ -22,8 +25,8 @@ __global__ void __launch_bounds__(256) dice_sums_kernel(const float* __restrict_
     sG += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
     sP += p0 * p0 + p1 * p1 + p2 * p2 + p3 * p3;
   }
-  if (blockIdx.x == 0) {  // tail (HW % 4)
-    for (int64_t i = nv * 4 + threadIdx.x; i < HW; i += 256) {
+  if (!vec) {  // scalar path, grid-strided like the vector one
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < HW; i += gridDim.x * 256ll) {
       const float x = logits[static_cast<int64_t>(n) * HW + i], t = target[static_cast<int64_t>(n) * HW + i];
       const float p = sigmoidf_(x);
       sI += t * p; sG += t * t; sP += p * p;

@@ -55,19 +55,31 @@ def deterministic_oversampling_indices(classes: Sequence) -> List[int]:
 
 def shard_indices(indices: Sequence[int], rank: int, world: int, batch: int, drop_last: bool = True) -> List[List[int]]:
     """Per-rank batches of an epoch: global batch g takes indices[g*world*batch : (g+1)*world*batch] and rank r the
-    r-th slice of `batch` of it (rank r gets samples [r*B, (r+1)*B) of the global batch)."""
+    r-th slice of `batch` of it (rank r gets samples [r*B, (r+1)*B) of the global batch).
+
+    Every rank gets the SAME number of batches and every batch has exactly `batch` samples -- the data-parallel step
+    issues one bucketed all-reduce sequence per step and averages per-rank means with 1/world, so unequal step counts
+    would deadlock NCCL and unequal batch sizes would bias the mean.  With drop_last=False the tail (fewer than
+    world*batch samples) is therefore completed to one more full global batch by wrapping around to the head of the
+    epoch's index list (the convention of torch's DistributedSampler(drop_last=False)).  On ONE rank nothing has to line
+    up, so the tail batch stays ragged: the reference trains on it (BUSI_dataloader.py:146-148 has no drop_last)."""
+    indices = list(indices)
     per_global = world * batch
     n_full = len(indices) // per_global
     out = []
     for g in range(n_full):
         a = g * per_global + rank * batch
-        out.append(list(indices[a:a + batch]))
-    if not drop_last and len(indices) % per_global:
-        tail = list(indices[n_full * per_global:])
-        share = math.ceil(len(tail) / world)
-        mine = tail[rank * share:(rank + 1) * share]
-        if mine:
-            out.append(mine)
+        out.append(indices[a:a + batch])
+    rest = len(indices) - n_full * per_global
+    if not drop_last and rest:
+        tail = indices[n_full * per_global:]
+        if world == 1:
+            out.append(tail)                     # ragged last batch, exactly the reference's
+        else:
+            need = per_global - rest
+            pad = (indices * (need // max(1, len(indices)) + 1))[:need]
+            full = tail + pad
+            out.append(full[rank * batch:(rank + 1) * batch])
     return out
 
 

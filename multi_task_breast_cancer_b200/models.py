@@ -37,12 +37,22 @@ class _PlanFunction(torch.autograd.Function):
         plan.run_pack()
         plan.run_forward()
         ctx.module, ctx.plan = module, plan
+        # The plan owns ONE set of activation buffers: a later forward through the same plan overwrites what this
+        # forward's backward needs.  Remember which forward this is so that backward can refuse a stale one.
+        plan.generation = getattr(plan, "generation", 0) + 1
+        ctx.generation = plan.generation
         # fresh tensor objects aliasing the plan's static output buffers (no copy)
         return tuple(t.detach() for t in plan.outputs_cls) + tuple(t.detach() for t in plan.outputs_seg)
 
     @staticmethod
     def backward(ctx, *grads):
         plan: Plan = ctx.plan
+        if ctx.generation != plan.generation:
+            raise RuntimeError(
+                "backward() through a forward whose activations are gone: this module keeps one static activation set "
+                f"per input shape and forward #{plan.generation} has overwritten those of forward #{ctx.generation}. "
+                "Call backward() before the next forward of the same shape (gradient accumulation as "
+                "forward; backward; forward; backward works), or run the extra forward under torch.no_grad().")
         ncls = len(plan.outputs_cls)
         for buf, g in zip(plan.g_cls, grads[:ncls]):
             if g is None:

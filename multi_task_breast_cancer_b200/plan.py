@@ -77,6 +77,14 @@ def _mk(name: str, *args) -> Callable[[C.c_void_p], None]:
     return launch
 
 
+def _annot(l: Callable, desc: str, true_bytes: float) -> Callable:
+    """Label a launch for the per-layer roofline table: `true_bytes` = ALGORITHMIC bytes (each tensor read once and
+    written once in its stored dtype, true channel counts -- SURVEY 8d), not what the kernel happens to move."""
+    l.desc = desc
+    l.true_bytes = float(true_bytes)
+    return l
+
+
 class JobTable:
     """Parameter-side jobs (padded vector copies, weight packs, weight-gradient unpacks) run as ONE launch."""
 
@@ -110,7 +118,7 @@ class JobTable:
         return [_mk_op(op, 0.0, f"{len(jobs)} parameter jobs")]
 
 
-def _mk_op(op: ops.Op, true_flops: float = 0.0, desc: str = "") -> Callable:
+def _mk_op(op: ops.Op, true_flops: float = 0.0, desc: str = "", true_bytes: float = 0.0) -> Callable:
     """Bind a tensor-core op launch; `true_flops` = algorithmic 2*M*N*K with unpadded channels (roofline numerator)."""
     lib = _lib.load()
     h = op.handle
@@ -122,6 +130,7 @@ def _mk_op(op: ops.Op, true_flops: float = 0.0, desc: str = "") -> Callable:
     launch.kind = op.kind
     launch.op = op
     launch.true_flops = true_flops
+    launch.true_bytes = float(true_bytes)
     launch.desc = desc
     return launch
 
@@ -240,8 +249,11 @@ class Plan:
         bvec = None if b is None else self.P(b)
         xs = torch.zeros(N, Cin * 9, dtype=torch.float32, device=self.device)  # shifted plane sums (mean removal)
         self._keep.append(xs)
-        self.fwd.append(_mk("mtbc_conv_first_fwd", ptr(x_in), N, Cin, H, Wd, ptr(Wt), ptr(bvec), Cout, ptr(y.feat.t),
-                            y.feat.Cp, ptr(ssum), ptr(ssq), ptr(xs)))
+        npx = N * H * Wd
+        self.fwd.append(_annot(_mk("mtbc_conv_first_fwd", ptr(x_in), N, Cin, H, Wd, ptr(Wt), ptr(bvec), Cout,
+                                   ptr(y.feat.t), y.feat.Cp, ptr(ssum), ptr(ssq), ptr(xs)),
+                               f"{name} first conv fwd {N}x{H}x{Wd} {Cin}->{Cout}", npx * (4 * Cin + 2 * Cout)))
+        self.fwd[-1].true_flops = 2.0 * npx * Cout * Cin * 9
         a, p, aux = self._norm_act(y, ssum, ssq, gamma, beta, slope, pool, name)
 
         def backward():
@@ -249,8 +261,11 @@ class Plan:
             dy = self._norm_act_bwd(blk, y, a, p, aux, gamma, beta, slope)
             if dy is None:
                 return blk
-            blk.append(self._side(_mk("mtbc_conv_first_wgrad", ptr(x_in), N, Cin, H, Wd, ptr(dy.t), dy.Cp, Cout,
-                                      ptr(self.grad_view[w])), dy))
+            l = _annot(_mk("mtbc_conv_first_wgrad", ptr(x_in), N, Cin, H, Wd, ptr(dy.t), dy.Cp, Cout,
+                           ptr(self.grad_view[w])), f"{name} first conv wgrad {N}x{H}x{Wd} {Cin}x{Cout}",
+                       npx * (4 * Cin + 2 * Cout))
+            l.true_flops = 2.0 * npx * Cout * Cin * 9
+            blk.append(self._side(l, dy))
             self._mark_grad(w, b)  # bias grad of a conv followed by InstanceNorm is identically zero
             return blk
         self._bwd_blocks.append(backward)
@@ -279,10 +294,14 @@ class Plan:
         op = ops.conv3x3_fwd_op(feats, pk["wf"], y.feat, bias=bias, stat_sum=ssum if fused else None,
                                 stat_sq=ssq if fused else None)
         self.tc_flops_fwd += op.flops
+        npx = N * H * Wd
+        wbytes = 2.0 * 9 * Cin * Cout
         self.fwd.append(_mk_op(op, 2.0 * N * H * Wd * Cout * Cin * 9,
-                               f"{name} fwd {N}x{H}x{Wd} {[f.C for f in feats]}->{Cout}"))
+                               f"{name} fwd {N}x{H}x{Wd} {[f.C for f in feats]}->{Cout}",
+                               2.0 * npx * (Cin + Cout) + wbytes))
         if not fused:
-            self.fwd.append(_mk("mtbc_in_stats", ptr(y.feat.t), N, H * Wd, Cp, ptr(ssum), ptr(ssq)))
+            self.fwd.append(_annot(_mk("mtbc_in_stats", ptr(y.feat.t), N, H * Wd, Cp, ptr(ssum), ptr(ssq)),
+                                   f"{name} in_stats {N}x{H}x{Wd}x{Cout}", 2.0 * npx * Cout))
         a, p, aux = self._norm_act(y, ssum, ssq, gamma, beta, slope, pool, name)
         self._wg_pending[w] = self._wg_pending.get(w, 0) + 1
 
@@ -302,13 +321,15 @@ class Plan:
             if o is not None:
                 self.tc_flops_bwd += o.flops
                 blk.append(self._side(_mk_op(o, 2.0 * N * H * Wd * Cout * Cin * 9,
-                                             f"{name} wgrad {N}x{H}x{Wd} {[f.C for f in feats]}x{Cout} fused"), dy))
+                                             f"{name} wgrad {N}x{H}x{Wd} {[f.C for f in feats]}x{Cout} fused",
+                                             2.0 * npx * (Cin + Cout) + 2 * wbytes), dy))
             else:
                 for f, off in zip(feats, pk["offs"]):
                     o = ops.conv3x3_wgrad_op(f, dy, acc, off)
                     self.tc_flops_bwd += o.flops
                     blk.append(self._side(_mk_op(o, 2.0 * N * H * Wd * Cout * f.C * 9,
-                                                 f"{name} wgrad {N}x{H}x{Wd} {f.C}x{Cout}"), dy))
+                                                 f"{name} wgrad {N}x{H}x{Wd} {f.C}x{Cout}",
+                                                 2.0 * npx * (f.C + Cout) + 4.0 * 9 * f.C * Cout), dy))
             self._mark_grad(w, b)
             self._emit_dgrad(blk, srcs, dy, w, pk, name, Cout)
             return blk
@@ -379,7 +400,8 @@ class Plan:
                 self.tc_flops_bwd += o.flops
                 cin = sum(s.feat.C for s in srcs)
                 blk.append(_mk_op(o, 2.0 * N * H * Wd * Cout * cin * 9,
-                                  f"{name} dgrad {N}x{H}x{Wd} {[s.feat.C for s in srcs]}<-{Cout} fused"))
+                                  f"{name} dgrad {N}x{H}x{Wd} {[s.feat.C for s in srcs]}<-{Cout} fused",
+                                  2.0 * N * H * Wd * (cin + Cout) + 2.0 * 9 * cin * Cout))
                 for s in srcs:
                     s.g_init = True
                 return
@@ -388,7 +410,8 @@ class Plan:
             o = ops.conv3x3_dgrad_op(dy, wd, g, accumulate=s.g_init)
             self.tc_flops_bwd += o.flops
             blk.append(_mk_op(o, 2.0 * N * H * Wd * Cout * s.feat.C * 9,
-                              f"{name} dgrad {N}x{H}x{Wd} {s.feat.C}<-{Cout} acc={int(s.g_init)}"))
+                              f"{name} dgrad {N}x{H}x{Wd} {s.feat.C}<-{Cout} acc={int(s.g_init)}",
+                              2.0 * N * H * Wd * (s.feat.C + Cout) + 2.0 * 9 * s.feat.C * Cout))
             s.g_init = True
 
     def _wg_accum(self, w: str, pk: dict) -> torch.Tensor:
@@ -411,9 +434,11 @@ class Plan:
         rstd = torch.zeros(N, Cp, dtype=torch.float32, device=self.device)
         gv = self._padded_vec(gamma, y.feat.Ck)
         bv = self._padded_vec(beta, y.feat.Ck)
-        self.fwd.append(_mk("mtbc_in_apply", ptr(y.feat.t), N, H, Wd, Cp, ptr(ssum), ptr(ssq), ptr(gv), ptr(bv), Cc,
-                            C.c_float(EPS), C.c_float(slope), ptr(a.feat.t), None if p is None else ptr(p.feat.t),
-                            ptr(mean), ptr(rstd)))
+        self.fwd.append(_annot(_mk("mtbc_in_apply", ptr(y.feat.t), N, H, Wd, Cp, ptr(ssum), ptr(ssq), ptr(gv), ptr(bv),
+                                   Cc, C.c_float(EPS), C.c_float(slope), ptr(a.feat.t),
+                                   None if p is None else ptr(p.feat.t), ptr(mean), ptr(rstd)),
+                               f"{name} in_apply{'+pool' if pool else ''} {N}x{H}x{Wd}x{Cc}",
+                               2.0 * N * H * Wd * Cc * (2.25 if pool else 2.0)))
         return a, p, (mean, rstd, gv, bv)
 
     def _norm_act_bwd(self, blk, y: PTensor, a: PTensor, p: Optional[PTensor], aux, gamma, beta, slope):
@@ -422,7 +447,9 @@ class Plan:
         N, H, Wd, Cp, Cc = y.feat.N, y.feat.H, y.feat.W, y.feat.Cp, y.feat.C
         if p is not None and p.g_init:
             g = a.grad()
-            blk.append(_mk("mtbc_maxpool2_bwd", ptr(a.feat.t), ptr(p.g.t), N, H, Wd, Cp, ptr(g.t), int(a.g_init)))
+            blk.append(_annot(_mk("mtbc_maxpool2_bwd", ptr(a.feat.t), ptr(p.g.t), N, H, Wd, Cp, ptr(g.t),
+                                  int(a.g_init)), f"{a.name} maxpool2_bwd {N}x{H}x{Wd}x{Cc}",
+                              2.0 * N * H * Wd * Cc * 2.25))
             a.g_init = True
         if not a.g_init:
             return None
@@ -436,6 +463,8 @@ class Plan:
         db = self.grad_view[beta] if beta else None
         l = _mk("mtbc_in_bwd", ptr(a.g.t), ptr(y.feat.t), N, H * Wd, Cp, ptr(mean), ptr(rstd), ptr(gv), ptr(bv),
                 C.c_float(slope), ptr(s1), ptr(s2), ptr(dy.t), ptr(dg), ptr(db), Cc, ptr(cnt))
+        # algorithmic: read g, read y, write dy once each (the two-pass kernel reads g and y twice: 10 B/elem moved)
+        _annot(l, f"{a.name} in_bwd {N}x{H}x{Wd}x{Cc}", 6.0 * N * H * Wd * Cc)
         l.wait_side = self._slot_readers.pop(self._cur_slot, [])   # weight gradients still reading this dy buffer
         self._dy_slot_of[id(dy.t)] = self._cur_slot
         blk.append(l)
@@ -458,7 +487,8 @@ class Plan:
         op = ops.convT_fwd_op(f, wf, out.feat, k, bias)
         self.tc_flops_fwd += op.flops
         t_flops = 2.0 * f.N * f.H * f.W * Cin * Cout * k * k
-        self.fwd.append(_mk_op(op, t_flops, f"{name} convT fwd {f.N}x{f.H}x{f.W} {Cin}->{Cout}"))
+        t_bytes = 2.0 * f.N * f.H * f.W * (Cin + k * k * Cout) + 2.0 * Cin * Cout * k * k
+        self.fwd.append(_mk_op(op, t_flops, f"{name} convT fwd {f.N}x{f.H}x{f.W} {Cin}->{Cout}", t_bytes))
 
         def backward():
             blk: List[Callable] = []
@@ -467,18 +497,19 @@ class Plan:
             acc = self.bwd_arena.alloc(k * k, cp, f.Ck)
             o = ops.convT_wgrad_op(f, out.g, acc, k)
             self.tc_flops_bwd += o.flops
-            blk.append(self._side(_mk_op(o, t_flops, f"{name} convT wgrad {f.N}x{f.H}x{f.W} {Cin}->{Cout}")))
+            blk.append(self._side(_mk_op(o, t_flops, f"{name} convT wgrad {f.N}x{f.H}x{f.W} {Cin}->{Cout}", t_bytes)))
             self.unpack_jobs.add(_lib.JOB_UNPACK_CONVT, [k * k * cp, f.Ck, Cin, Cout, k, 0], acc, self.grad_view[w],
                                  owner=w)
             self._late_unpacked.append(w)
             if b is not None:
-                blk.append(_mk("mtbc_channel_sum", ptr(out.g.t), out.g.N * out.g.H * out.g.W, out.g.Cp, Cout,
-                               ptr(self.grad_view[b]), 1))
+                blk.append(_annot(_mk("mtbc_channel_sum", ptr(out.g.t), out.g.N * out.g.H * out.g.W, out.g.Cp, Cout,
+                                      ptr(self.grad_view[b]), 1), f"{name} convT bias grad",
+                                  2.0 * out.g.N * out.g.H * out.g.W * Cout))
             self._mark_grad(w, b)
             g = x.grad()
             o = ops.convT_dgrad_op(out.g, wd, g, k, accumulate=x.g_init)
             self.tc_flops_bwd += o.flops
-            blk.append(_mk_op(o, t_flops, f"{name} convT dgrad {f.N}x{f.H}x{f.W} {Cin}<-{Cout}"))
+            blk.append(_mk_op(o, t_flops, f"{name} convT dgrad {f.N}x{f.H}x{f.W} {Cin}<-{Cout}", t_bytes))
             x.g_init = True
             return blk
         self._bwd_blocks.append(backward)
@@ -488,13 +519,15 @@ class Plan:
         """nn.Upsample(scale_factor=2, mode='nearest') (Multi_BTS_UNet.py:100)."""
         f = x.feat
         out = self.new(f.N, f.H * 2, f.W * 2, f.C, name)
-        self.fwd.append(_mk("mtbc_upsample2_fwd", ptr(f.t), f.N, f.H, f.W, f.Cp, ptr(out.feat.t)))
+        self.fwd.append(_annot(_mk("mtbc_upsample2_fwd", ptr(f.t), f.N, f.H, f.W, f.Cp, ptr(out.feat.t)),
+                               f"{name} upsample2 fwd", 2.0 * f.N * f.H * f.W * f.C * 5))
 
         def backward():
             if not out.g_init:
                 return []
             g = x.grad()
-            blk = [_mk("mtbc_upsample2_bwd", ptr(out.g.t), f.N, f.H, f.W, f.Cp, ptr(g.t), int(x.g_init))]
+            blk = [_annot(_mk("mtbc_upsample2_bwd", ptr(out.g.t), f.N, f.H, f.W, f.Cp, ptr(g.t), int(x.g_init)),
+                          f"{name} upsample2 bwd", 2.0 * f.N * f.H * f.W * f.C * 5)]
             x.g_init = True
             return blk
         self._bwd_blocks.append(backward)
@@ -509,7 +542,8 @@ class Plan:
         logits = torch.zeros(f.N, 1, f.H, f.W, dtype=torch.float32, device=self.device)
         dlog = torch.zeros_like(logits)
         npix = f.N * f.H * f.W
-        self.fwd.append(_mk("mtbc_head1x1_fwd", ptr(f.t), npix, f.Cp, f.C, ptr(self.P(w)), ptr(self.P(b)), ptr(logits)))
+        self.fwd.append(_annot(_mk("mtbc_head1x1_fwd", ptr(f.t), npix, f.Cp, f.C, ptr(self.P(w)), ptr(self.P(b)),
+                                   ptr(logits)), f"{a.name} head1x1 fwd", npix * (2.0 * f.C + 4)))
         idx = len(self.outputs_seg)
         self.outputs_seg.append(logits)
         self.g_seg.append(dlog)
@@ -518,8 +552,9 @@ class Plan:
             if not self.seg_grad_active[idx]:
                 return []
             g = a.grad()
-            blk = [_mk("mtbc_head1x1_bwd", ptr(f.t), ptr(dlog), npix, f.Cp, f.C, ptr(self.P(w)), ptr(g.t),
-                       int(a.g_init), ptr(self.grad_view[w]), ptr(self.grad_view[b]))]
+            blk = [_annot(_mk("mtbc_head1x1_bwd", ptr(f.t), ptr(dlog), npix, f.Cp, f.C, ptr(self.P(w)), ptr(g.t),
+                              int(a.g_init), ptr(self.grad_view[w]), ptr(self.grad_view[b])),
+                          f"{a.name} head1x1 bwd", npix * (4.0 * f.C + 4))]
             a.g_init = True
             self._mark_grad(w, b)
             return blk
@@ -537,7 +572,8 @@ class Plan:
         dlog = torch.zeros_like(logits)
         self.pack.append(_mk("mtbc_dshead_compose", ptr(self.P(wt)), ptr(self.P(bt)), ptr(self.P(w1)), ptr(self.P(b1)),
                              Cc, k, ptr(wc), ptr(bc)))
-        self.fwd.append(_mk("mtbc_dshead_fwd", ptr(f.t), f.N, f.H, f.W, f.Cp, Cc, k, ptr(wc), ptr(bc), ptr(logits)))
+        self.fwd.append(_annot(_mk("mtbc_dshead_fwd", ptr(f.t), f.N, f.H, f.W, f.Cp, Cc, k, ptr(wc), ptr(bc),
+                                   ptr(logits)), f"{a.name} dshead k{k} fwd", f.N * f.H * f.W * (2.0 * Cc + 4 * kk)))
         idx = len(self.outputs_seg)
         self.outputs_seg.append(logits)
         self.g_seg.append(dlog)
@@ -548,8 +584,9 @@ class Plan:
             dwc = self.bwd_arena.alloc(Cc, kk)
             dbc = self.bwd_arena.alloc(1)
             g = a.grad()
-            blk = [_mk("mtbc_dshead_bwd", ptr(f.t), ptr(dlog), f.N, f.H, f.W, f.Cp, Cc, k, ptr(wc), ptr(g.t),
-                       int(a.g_init), ptr(dwc), ptr(dbc)),
+            blk = [_annot(_mk("mtbc_dshead_bwd", ptr(f.t), ptr(dlog), f.N, f.H, f.W, f.Cp, Cc, k, ptr(wc), ptr(g.t),
+                              int(a.g_init), ptr(dwc), ptr(dbc)), f"{a.name} dshead k{k} bwd",
+                          f.N * f.H * f.W * (4.0 * Cc + 4 * kk)),
                    _mk("mtbc_dshead_decompose", ptr(dwc), ptr(dbc), ptr(self.P(wt)), ptr(self.P(bt)), ptr(self.P(w1)),
                        Cc, k, ptr(self.grad_view[wt]), ptr(self.grad_view[bt]), ptr(self.grad_view[w1]),
                        ptr(self.grad_view[b1]))]
@@ -569,16 +606,18 @@ class Plan:
         logits = torch.zeros(f.N, K, dtype=torch.float32, device=self.device)
         dlog = torch.zeros_like(logits)
         dgap = torch.zeros_like(gap)
-        self.fwd.append(_mk("mtbc_gap_fc_fwd", ptr(f.t), f.N, f.H * f.W, f.Cp, Fdim, ptr(self.P(w1)), ptr(self.P(b1)),
-                            Hd, ptr(self.P(w2)), ptr(self.P(b2)), K, ptr(gap), ptr(hid), ptr(logits)))
+        self.fwd.append(_annot(_mk("mtbc_gap_fc_fwd", ptr(f.t), f.N, f.H * f.W, f.Cp, Fdim, ptr(self.P(w1)),
+                                   ptr(self.P(b1)), Hd, ptr(self.P(w2)), ptr(self.P(b2)), K, ptr(gap), ptr(hid),
+                                   ptr(logits)), f"{a.name} gap_fc fwd", 2.0 * f.N * f.H * f.W * Fdim + 4.0 * Fdim * Hd))
         self.outputs_cls.append(logits)
         self.g_cls.append(dlog)
 
         def backward():
             g = a.grad()
-            blk = [_mk("mtbc_gap_fc_bwd", ptr(dlog), f.N, f.H * f.W, f.Cp, Fdim, ptr(self.P(w1)), Hd, ptr(self.P(w2)),
-                       K, ptr(gap), ptr(hid), ptr(g.t), int(a.g_init), ptr(self.grad_view[w1]), ptr(self.grad_view[b1]),
-                       ptr(self.grad_view[w2]), ptr(self.grad_view[b2]), ptr(dgap))]
+            blk = [_annot(_mk("mtbc_gap_fc_bwd", ptr(dlog), f.N, f.H * f.W, f.Cp, Fdim, ptr(self.P(w1)), Hd,
+                              ptr(self.P(w2)), K, ptr(gap), ptr(hid), ptr(g.t), int(a.g_init), ptr(self.grad_view[w1]),
+                              ptr(self.grad_view[b1]), ptr(self.grad_view[w2]), ptr(self.grad_view[b2]), ptr(dgap)),
+                          f"{a.name} gap_fc bwd", 2.0 * f.N * f.H * f.W * Fdim + 8.0 * Fdim * Hd)]
             a.g_init = True
             self._mark_grad(w1, b1, w2, b2)
             return blk
@@ -594,16 +633,19 @@ class Plan:
         dh = torch.zeros(f.N, Hd, dtype=torch.float32, device=self.device)
         logits = torch.zeros(f.N, K, dtype=torch.float32, device=self.device)
         dlog = torch.zeros_like(logits)
-        self.fwd.append(_mk("mtbc_flat_fc_fwd", ptr(f.t), f.N, f.H * f.W, f.Cp, f.C, ptr(self.P(w1)), ptr(self.P(b1)),
-                            Hd, ptr(self.P(w2)), ptr(self.P(b2)), K, ptr(hid), ptr(logits)))
+        nfeat = f.C * f.H * f.W
+        self.fwd.append(_annot(_mk("mtbc_flat_fc_fwd", ptr(f.t), f.N, f.H * f.W, f.Cp, f.C, ptr(self.P(w1)),
+                                   ptr(self.P(b1)), Hd, ptr(self.P(w2)), ptr(self.P(b2)), K, ptr(hid), ptr(logits)),
+                               f"{a.name} flat_fc fwd", 2.0 * f.N * nfeat + 4.0 * nfeat * Hd))
         self.outputs_cls.append(logits)
         self.g_cls.append(dlog)
 
         def backward():
             g = a.grad()
-            blk = [_mk("mtbc_flat_fc_bwd", ptr(f.t), ptr(dlog), f.N, f.H * f.W, f.Cp, f.C, ptr(self.P(w1)), Hd,
-                       ptr(self.P(w2)), K, ptr(hid), ptr(g.t), int(a.g_init), ptr(self.grad_view[w1]),
-                       ptr(self.grad_view[b1]), ptr(self.grad_view[w2]), ptr(self.grad_view[b2]), ptr(dh))]
+            blk = [_annot(_mk("mtbc_flat_fc_bwd", ptr(f.t), ptr(dlog), f.N, f.H * f.W, f.Cp, f.C, ptr(self.P(w1)), Hd,
+                              ptr(self.P(w2)), K, ptr(hid), ptr(g.t), int(a.g_init), ptr(self.grad_view[w1]),
+                              ptr(self.grad_view[b1]), ptr(self.grad_view[w2]), ptr(self.grad_view[b2]), ptr(dh)),
+                          f"{a.name} flat_fc bwd", 4.0 * f.N * nfeat + 8.0 * nfeat * Hd)]
             a.g_init = True
             self._mark_grad(w1, b1, w2, b2)
             return blk

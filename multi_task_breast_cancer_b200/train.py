@@ -34,9 +34,14 @@ class TrainStep:
     def __init__(self, model: torch.nn.Module, batch_shape: Sequence[int], lr: float = 1e-4, betas=(0.9, 0.999),
                  eps: float = 1e-4, alpha: float = 0.35, inversely_weighted: bool = True, focal_alpha: float = 1.0,
                  focal_gamma: float = 2.0, process_group=None, use_graph: bool = True, device=None,
-                 refine: bool = False, refine_flags=(True, True, 0), normal_id: int = 2):
+                 refine: bool = False, refine_flags=(True, True, 0), normal_id: int = 2,
+                 share_state_with: Optional["TrainStep"] = None, external_cotangent: bool = False):
         """`model` is one of models.{MTUNetPlusPlus, MTnnUNet, Multi_BTS_UNet} already on its CUDA device.
-        Hyper-parameters keep the meaning of src/config.yaml (optimizer.lr, training.alpha, loss.inversely_weighted)."""
+        Hyper-parameters keep the meaning of src/config.yaml (optimizer.lr, training.alpha, loss.inversely_weighted).
+
+        `share_state_with`: a TrainStep of the SAME model planned for another batch shape (the loader's ragged last
+        batch, BUSI_dataloader.py:146-148: no drop_last).  The new step gets its own plan / activations / graph but
+        updates the very same flat parameter buffer, Adam moments, step counter and learning-rate scalar."""
         self.model = model
         self.device = device or next(model.parameters()).device
         if self.device.type != "cuda":
@@ -56,8 +61,17 @@ class TrainStep:
         # Any eager launch between two graph replays exposes ~0.35 ms of graph start-up per step (tools/diag_e2e.py),
         # which is why it lives in the graph and not in the caller's loop.
         self.refine, self.refine_flags, self.normal_id = bool(refine), tuple(refine_flags), int(normal_id)
+        # external_cotangent=True (gradient-wiring / data-parallel checks): the fused objective is left out and the
+        # caller fills plan.g_cls / plan.g_seg itself, i.e. the step back-propagates sum(out * g) for fixed g
+        self.external_cotangent = bool(external_cotangent)
+        self._shared = share_state_with
+        if share_state_with is not None and share_state_with.model is not model:
+            raise ValueError("share_state_with: the other TrainStep drives a different model")
         with torch.cuda.device(self.device):
-            self._flatten_params()
+            if share_state_with is None:
+                self._flatten_params()
+            else:
+                self.flat_p, self.param_ranges = share_state_with.flat_p, share_state_with.param_ranges
             x = torch.zeros(self.B, self.Cin, self.H, self.W, dtype=torch.float32, device=self.device)
             self.plan: Plan = model._get_plan(x, True)
             self.x = self.plan.x_in
@@ -72,10 +86,15 @@ class TrainStep:
             self.focal_loss = torch.zeros(1, dtype=torch.float32, device=self.device)
             self.loss_out = torch.zeros(4, dtype=torch.float32, device=self.device)  # total, seg, cls, nan flag
             self.lr = float(lr)   # host copy (exact double) of the device scalar the captured Adam launch reads
-            self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=self.device)
-            self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
-            self.exp_avg = torch.zeros_like(self.flat_p)
-            self.exp_avg_sq = torch.zeros_like(self.flat_p)
+            if share_state_with is None:
+                self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=self.device)
+                self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+                self.exp_avg = torch.zeros_like(self.flat_p)
+                self.exp_avg_sq = torch.zeros_like(self.flat_p)
+            else:
+                o = share_state_with
+                self.lr, self.lr_dev, self.step_dev = o.lr, o.lr_dev, o.step_dev
+                self.exp_avg, self.exp_avg_sq = o.exp_avg, o.exp_avg_sq
             if self.refine:
                 self.refined_mask = torch.zeros(self.B, 1, self.H, self.W, dtype=torch.uint8, device=self.device)
                 self.refined_class = torch.zeros(self.B, dtype=torch.int32, device=self.device)
@@ -117,6 +136,11 @@ class TrainStep:
         L: List = []
         L += plan.pack
         L += plan.fwd
+        if self.external_cotangent:
+            L += plan.bwd
+            self.launches_fb = L
+            self._build_opt_launches()
+            return
         # ---- fused objective (criterions.py:52-76 + training_multitask.py:98)
         L.append(_mk("mtbc_zero_bytes", ptr(self.dice_sums), self.dice_sums.numel() * 4))
         for i, logits in enumerate(plan.outputs_seg):
@@ -143,6 +167,10 @@ class TrainStep:
                      ptr(plan.g_cls[0])))
         L += plan.bwd
         self.launches_fb = L
+        self._build_opt_launches()
+
+    def _build_opt_launches(self):
+        plan = self.plan
         # ---- optimizer (after the all-reduce when data parallel)
         self.launches_opt = [
             _mk("mtbc_increment_i32", ptr(self.step_dev)),
@@ -399,6 +427,8 @@ class TrainStep:
     def set_lr(self, lr: float):
         self.lr = float(lr)
         self.lr_dev.fill_(float(lr))
+        if self._shared is not None:
+            self._shared.lr = self.lr
 
     def losses(self) -> torch.Tensor:
         """Device tensor [total, seg, cls, nan_flag] of the last step (reading it synchronises)."""

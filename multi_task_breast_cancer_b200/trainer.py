@@ -244,8 +244,11 @@ class _Accumulators:
 class EpochRunner:
     """train_one_epoch / validate_one_epoch of src/training_multitask.py on top of a TrainStep.
 
-    Batches must have the shape the TrainStep was planned for (static CUDA graph); a loader's ragged last batch is
-    rejected with a clear error rather than silently padded (use drop_last=True, or a second runner for the tail)."""
+    The TrainStep is a static CUDA graph for one batch shape.  The reference's loaders have no `drop_last`
+    (BUSI_dataloader.py:146-148) and `train_one_epoch` trains on the ragged last batch (training_multitask.py:79), so a
+    batch with FEWER samples than planned gets a second plan + graph keyed on its size (`TrainStep(share_state_with=)`:
+    same parameters, Adam moments and step counter) instead of an error; any other shape mismatch is rejected.  Data
+    parallel runs must hand every rank full batches (data.shard_indices pads the tail by wrapping around)."""
 
     def __init__(self, train_step, num_classes: int = 3):
         self.ts = train_step
@@ -255,7 +258,8 @@ class EpochRunner:
         self.dev = train_step.device
         self.optimizer = FlatAdam(train_step)
         self._acc = _Accumulators(self.K, self.dev)
-        self._eval = None
+        self._eval = {}     # batch size -> EvalStep
+        self._tail = {}     # batch size -> TrainStep sharing the optimizer state (ragged last batch)
 
     # -------------------------------------------------------------------------------------------------- training
     def train_one_epoch(self, loader: Iterable) -> Tuple[float, float, float, float]:
@@ -268,7 +272,7 @@ class EpochRunner:
         with torch.cuda.device(self.dev):
             for data in loader:
                 img, mask, onehot = _batch_of(data, self.K)
-                self._check_shape(img)
+                ts = self._step_for(img)
                 ts.load_batch(img if img.is_cuda or img.is_pinned() else img.pin_memory(),
                               mask if mask.is_cuda or mask.is_pinned() else mask.pin_memory(),
                               onehot if onehot.is_cuda or onehot.is_pinned() else onehot.pin_memory())
@@ -286,17 +290,33 @@ class EpochRunner:
         return acc[0] / n, acc[4] / n, accuracy, f1w
 
     # -------------------------------------------------------------------------------------------------- validation
-    def _eval_step(self):
-        if self._eval is None:
-            self._eval = EvalStep(self.ts.model, (self.ts.B, self.ts.Cin, self.ts.H, self.ts.W), alpha=self.ts.alpha,
-                                  inversely_weighted=self.ts.inv_w, focal_alpha=self.ts.focal_alpha,
-                                  focal_gamma=self.ts.focal_gamma)
-        return self._eval
+    def _eval_step(self, B: Optional[int] = None):
+        B = self.ts.B if B is None else int(B)
+        if B not in self._eval:
+            self._eval[B] = EvalStep(self.ts.model, (B, self.ts.Cin, self.ts.H, self.ts.W), alpha=self.ts.alpha,
+                                     inversely_weighted=self.ts.inv_w, focal_alpha=self.ts.focal_alpha,
+                                     focal_gamma=self.ts.focal_gamma)
+        return self._eval[B]
+
+    def _step_for(self, img):
+        """The TrainStep for this batch: the planned one, or a sibling for a ragged (smaller) last batch."""
+        self._check_shape(img)
+        B = int(img.shape[0])
+        if B == self.ts.B:
+            return self.ts
+        if self.ts.world > 1:
+            raise ValueError("data-parallel steps need full batches on every rank (equal step counts and unbiased "
+                             "1/world averaging): shard the epoch with data.shard_indices")
+        if B not in self._tail:
+            t = self.ts
+            self._tail[B] = type(t)(t.model, (B, t.Cin, t.H, t.W), lr=t.lr, betas=t.betas, eps=t.eps, alpha=t.alpha,
+                                    inversely_weighted=t.inv_w, focal_alpha=t.focal_alpha, focal_gamma=t.focal_gamma,
+                                    use_graph=t.use_graph, device=t.device, share_state_with=t)
+        return self._tail[B]
 
     def validate_one_epoch(self, loader: Iterable) -> Tuple[float, float, float, float, float, float]:
         """-> (avg_val_loss, avg_val_dice, val_acc, val_f1, avg_seg_val_loss, avg_cls_val_loss),
         training_multitask.py:119-159 (forward + objective only, no gradients)."""
-        ev = self._eval_step()
         self.ts.model.train(False)
         self._acc.reset()
         n = 0
@@ -304,6 +324,7 @@ class EpochRunner:
             for data in loader:
                 img, mask, onehot = _batch_of(data, self.K)
                 self._check_shape(img)
+                ev = self._eval_step(img.shape[0])
                 ev.run(img, mask, onehot)
                 self._acc.add_step(ev.loss_out, ev.plan.outputs_seg[-1], ev.mask, ev.plan.outputs_cls[0], ev.onehot)
                 n += 1
@@ -315,8 +336,9 @@ class EpochRunner:
 
     def _check_shape(self, img):
         want = (self.ts.B, self.ts.Cin, self.ts.H, self.ts.W)
-        if tuple(img.shape) != want:
-            raise ValueError(f"batch of shape {tuple(img.shape)} handed to a step planned for {want}")
+        if img.dim() != 4 or tuple(img.shape[1:]) != want[1:] or not 0 < img.shape[0] <= want[0]:
+            raise ValueError(f"batch of shape {tuple(img.shape)} handed to a step planned for {want} (only the batch "
+                             "dimension may be smaller: the loader's last batch)")
 
 
 class EvalStep:

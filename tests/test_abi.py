@@ -21,17 +21,34 @@ def test_header_symbols_exported(lib):
 def test_ctypes_signatures_match_header(lib):
     from multi_task_breast_cancer_b200 import _lib
     decls = dict(_decls())
-    assert set(_lib._SIGS) | {"mtbc_last_error"} == set(decls), set(decls) ^ (set(_lib._SIGS) | {"mtbc_last_error"})
+    special = {"mtbc_last_error", "mtbc_build_digest"}
+    assert set(_lib._SIGS) | special == set(decls), set(decls) ^ (set(_lib._SIGS) | special)
     for name, args in decls.items():
-        if name == "mtbc_last_error":
+        if name in special:
             continue
         n = 0 if args.strip() in ("", "void") else len(args.split(","))
         assert n == len(_lib._SIGS[name]), (name, n, len(_lib._SIGS[name]))
 
 
 def test_abi_version_and_error_string(lib):
-    assert lib.mtbc_abi_version() == 2
+    from multi_task_breast_cancer_b200 import _lib, build
+    assert lib.mtbc_abi_version() == _lib.ABI_VERSION == 3
     assert isinstance(lib.mtbc_last_error(), bytes)
+    # the digest compiled into the binary is the digest of the sources on disk (no side-car stamp file)
+    assert build.lib_digest() == build._digest()
+
+
+def test_stale_library_is_refused(tmp_path, monkeypatch):
+    """A libmtbc.so built from other sources must not be bound silently (tracked stamp vs ignored .so)."""
+    import pytest
+    from multi_task_breast_cancer_b200 import _lib, build
+    def no_compiler(*a, **k):
+        raise RuntimeError("nvcc not found")
+    monkeypatch.setattr(build, "_digest", lambda: "0" * 64)
+    monkeypatch.setattr(build, "build", no_compiler)     # with a compiler the loader rebuilds instead (build.build)
+    monkeypatch.setattr(_lib, "_lib", None)
+    with pytest.raises(_lib.MtbcError, match="other sources"):
+        _lib.load()
 
 
 def test_no_library_fallback_symbols():

@@ -36,8 +36,19 @@ def test_shard_indices_partition_the_epoch():
             got = sum((per_rank[r][g] for r in range(world)), [])
             assert got == idx[g * world * batch:(g + 1) * world * batch]        # rank r = r-th slice of the global batch
         tail = [D.shard_indices(idx, r, world, batch, drop_last=False) for r in range(world)]
-        seen = sorted(sum((sum(t, []) for t in tail), []))
-        assert seen == idx                                                       # nothing lost, nothing duplicated
+        # data-parallel safety: same number of steps on every rank (else the per-bucket all-reduces
+        # deadlock) and -- for world > 1 -- only full batches (1/world averaging of per-rank means stays unbiased)
+        assert len({len(t) for t in tail}) == 1
+        seen = sum((sum(t, []) for t in tail), [])
+        assert set(seen) == set(idx)                                             # nothing lost
+        if world == 1:
+            assert sorted(seen) == idx and len(tail[0][-1]) == 103 % batch       # ragged tail, as the reference
+        else:
+            assert all(len(b) == batch for t in tail for b in t)
+            extra = len(seen) - len(idx)                                         # wrapped-around padding only
+            assert 0 <= extra < world * batch
+            last_global = sum((t[-1] for t in tail), [])
+            assert last_global[:103 - n_global * world * batch] == idx[n_global * world * batch:]
 
 
 def test_transform_draws_follow_torchvision_call_order():

@@ -78,12 +78,20 @@ def test_train_one_epoch_bookkeeping_is_exact_and_losses_match_oracle(use_graph)
 
 
 def test_validate_one_epoch_matches_oracle_and_leaves_weights_alone():
+    """Validation on TRAINED weights: at random init the class logits are O(0.05) apart and a bf16-level difference
+    flips argmax, which made the old accuracy / F1 tolerances (0.5 / 0.6) vacuous.  The oracle first trains 40 Adam
+    steps; then accuracy and weighted F1 must be IDENTICAL unless the oracle's own top-1 margin on some sample is below
+    the bf16 noise floor (then accuracy may move by exactly those samples)."""
     from oracle import torch_oracle as O
     from multi_task_breast_cancer_b200.train import TrainStep
     from multi_task_breast_cancer_b200.trainer import EpochRunner
     ref, new = _pair("unetpp")
     B, S, n = 2, 64, 3
     dev = _batches(n, B, S, device="cuda", seed=7)
+    opt = O.make_optimizer(ref, 1e-3)
+    for s in range(40):
+        O.train_step(ref, opt, *dev[s % n])
+    new.load_state_dict(ref.state_dict())
     ts = TrainStep(new, (B, 1, S, S))
     runner = EpochRunner(ts, 3)
     before = ts.flat_p.clone()
@@ -91,17 +99,65 @@ def test_validate_one_epoch_matches_oracle_and_leaves_weights_alone():
     out2 = runner.validate_one_epoch(iter(dev))          # graph replay path
     exp = O.validate_one_epoch(ref, dev)
     assert torch.equal(before, ts.flat_p) and int(ts.step_dev.item()) == 0
+    with torch.no_grad():
+        margins = []
+        for img, _, _ in dev:
+            top = torch.stack(ref(img)[0]).mean(0).topk(2, dim=1).values
+            margins += (top[:, 0] - top[:, 1]).tolist()
+    unstable = sum(m < 3e-2 for m in margins)
     names = ["val_loss", "val_dice", "val_acc", "val_f1", "seg_val_loss", "cls_val_loss"]
     for k, a, a2, b in zip(names, out, out2, exp):
-        tol = {"val_dice": 3e-2, "val_acc": 0.5, "val_f1": 0.6}.get(k)
-        if tol is None:
-            assert abs(a - b) < 1e-2 * abs(b), (k, a, b)
+        if k == "val_acc":
+            assert abs(a - b) <= unstable / (n * B) + 1e-12, (k, a, b, margins)
+        elif k == "val_f1":
+            assert unstable > 0 or abs(a - b) < 1e-12, (k, a, b, margins)
+        elif k == "val_dice":
+            assert abs(a - b) < 2e-2, (k, a, b)
         else:
-            assert abs(a - b) <= tol, (k, a, b)
+            assert abs(a - b) < 1e-2 * abs(b), (k, a, b)
         assert abs(a - a2) < 1e-3 * max(1.0, abs(a)), (k, a, a2)
+    assert unstable <= 1, margins      # the trained case is meant to be decisive: at most one borderline sample
     assert abs(out[0] - (0.35 * out[4] + 0.65 * out[5])) < 1e-5
     with pytest.raises(ValueError):
-        runner.validate_one_epoch(iter([tuple(t[:1] for t in dev[0])]))     # ragged batch: explicit error
+        runner.validate_one_epoch(iter([tuple(t[:, :, :32] if t.dim() == 4 else t for t in dev[0])]))  # other H: error
+
+
+def test_ragged_last_batch_trains_and_validates_like_the_reference():
+    """The reference loaders have no drop_last (BUSI_dataloader.py:146-148) and train_one_epoch trains on the tail batch
+    (training_multitask.py:79): batches of 3, 3, 2 go through two plans that share parameters and Adam state."""
+    from oracle import torch_oracle as O
+    from multi_task_breast_cancer_b200.train import TrainStep
+    from multi_task_breast_cancer_b200.trainer import EpochRunner
+    ref, new = _pair("nnunet")
+    S = 128
+    full = _batches(2, 3, S, device="cuda")
+    tail = tuple(t[:2].contiguous() for t in _batches(1, 3, S, device="cuda", seed=77)[0])
+    data = full + [tail]
+    ts = TrainStep(new, (3, 1, S, S), lr=1e-4)
+    runner = EpochRunner(ts, 3)
+    p0 = ts.flat_p.clone()
+    loss, dice, acc, f1w = runner.train_one_epoch(iter(data))
+    assert int(ts.step_dev.item()) == 3 and 2 in runner._tail
+    t2 = runner._tail[2]
+    assert t2.flat_p.data_ptr() == ts.flat_p.data_ptr() and t2.exp_avg.data_ptr() == ts.exp_avg.data_ptr()
+    assert t2.step_dev.data_ptr() == ts.step_dev.data_ptr() and t2.plan is not ts.plan
+    # the tail step really updated the shared parameters: a third Adam step moves every weight again
+    opt = O.make_optimizer(ref, 1e-4)
+    rl, rd, ra, rf = O.train_one_epoch(ref, opt, data)
+    assert abs(loss - rl) < 1e-2 * abs(rl), (loss, rl)
+    assert abs(dice - rd) < 2e-2, (dice, rd)
+    ref_flat = torch.cat([p.detach().flatten() for p in ref.parameters()])
+    new_flat = torch.cat([p.detach().flatten() for p in new.parameters()])
+    moved = (new_flat - ref_flat).abs().max().item()
+    assert moved <= 6.2e-4, moved                 # three Adam steps of at most lr = 1e-4 each, on either side
+    assert not torch.equal(p0, ts.flat_p)
+    # second epoch: both graphs are replayed (no re-capture), still three more steps
+    runner.train_one_epoch(iter(data))
+    assert int(ts.step_dev.item()) == 6
+    v = runner.validate_one_epoch(iter(data))
+    e = O.validate_one_epoch(ref, data)
+    assert abs(v[0] - e[0]) < 2e-2 * abs(e[0]), (v, e)
+    assert set(runner._eval) == {3, 2}
 
 
 def test_checkpoint_round_trip_in_reference_format(tmp_path):

@@ -1,32 +1,148 @@
-"""2-rank check of the data-parallel step (torchrun --nproc-per-node 2 tools/dp_check.py MODE):
-MODE = eager | graph   with MTBC_DP_OVERLAP=0/1.  Prints the loss of each step and a parameter checksum on rank 0."""
-import os, sys
+"""Data-parallel correctness ON THE CUDA PATH ("R ranks x B/R samples == 1 rank x B samples").
+
+    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/dp_check.py [arch B S]
+
+Every rank drives a TrainStep over its slice of ONE global batch (rank r: samples [r*B/R, (r+1)*B/R)) with the bucketed,
+overlapped NCCL all-reduce of train.py; rank 0 also runs the same global batch through a single-GPU TrainStep.  Compared:
+
+  1. random-cotangent objective (sum(out * g), g ~ randn fixed per sample: no InstanceNorm cancellation, so the
+     comparison is sensitive): the all-reduced flat gradient of the R ranks against the full-batch gradient, per
+     parameter (relative L2) and as a whole (cosine);
+  2. the real objective (Dice + focal, alpha mix): mean over ranks of the per-rank loss against the full-batch loss, the
+     all-reduced gradient x 1/R against the full-batch gradient, and the parameters after 3 Adam steps (every rank
+     must hold identical parameters; they must match the single-GPU run within the Adam step bound).
+No operation couples samples, so the two sides differ only by fp32 summation order / bf16 rounding flips.
+Modes: graph replay with overlapped buckets (default), MTBC_DP_OVERLAP=0, and eager -- all three are run.
+"""
+import os
+import sys
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import torch, torch.distributed as dist
-from oracle import torch_oracle as O
+import torch
+import torch.distributed as dist
+from oracle import torch_oracle as O   # synthetic batch generator only
 from multi_task_breast_cancer_b200 import models as M
 from multi_task_breast_cancer_b200.train import TrainStep
-mode = sys.argv[1] if len(sys.argv) > 1 else "graph"
-rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+
+arch = sys.argv[1] if len(sys.argv) > 1 else "unetpp"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+S = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-torch.manual_seed(1993)
-model = M.MTnnUNet(1, 1, 3).to(dev)
-ts = TrainStep(model, (2, 1, 64, 64), process_group=dist.group.WORLD, use_graph=(mode == "graph"))
-img, mask, onehot, _ = O.synthetic_batch(2, 64, 64, seed=1993 + rank)
-ts.load_batch(img.to(dev), mask.to(dev), onehot.to(dev))
-out = []
-for i in range(4):
-    ts.step()
+b = B // world
+assert b * world == B
+mk = {"unetpp": lambda: M.MTUNetPlusPlus(deep_supervision=True), "nnunet": lambda: M.MTnnUNet(1, 1, 3),
+      "bts": lambda: M.Multi_BTS_UNet(1, 1, 3, 32, True)}[arch]
+img, mask, onehot, _ = O.synthetic_batch(B, S, S, seed=1993)
+img, mask, onehot = img.to(dev), mask.to(dev), onehot.to(dev)
+sl = slice(rank * b, (rank + 1) * b)
+ok = True
+
+
+def rel(a, c):
+    return ((a - c).norm() / (c.norm() + 1e-30)).item()
+
+
+def fill_cotangents(ts, lo, hi):
+    g = torch.Generator(device="cpu").manual_seed(7)
+    for buf in ts.plan.g_cls:
+        full = torch.randn((B,) + tuple(buf.shape[1:]), generator=g)
+        buf.copy_(full[lo:hi])
+    for i, buf in enumerate(ts.plan.g_seg):
+        full = torch.randn((B,) + tuple(buf.shape[1:]), generator=g)
+        if ts.plan.seg_grad_active[i]:
+            buf.copy_(full[lo:hi])
+
+
+def per_param(ts, flat_a, flat_b, tag, tol):
+    global ok
+    worst = (0.0, "")
+    for n, (a, c) in ts.param_ranges.items():
+        if not ts.plan.has_grad.get(n):
+            continue
+        ref = flat_b[a:c]
+        if ref.norm().item() < 1e-12:
+            continue
+        e = rel(flat_a[a:c], ref)
+        if e > worst[0]:
+            worst = (e, n)
+    cos = torch.nn.functional.cosine_similarity(flat_a, flat_b, dim=0).item()
+    good = worst[0] <= tol
+    ok &= good
+    print(f"  {tag}: worst per-parameter rel-L2 {worst[0]:.2e} ({worst[1]}), whole-vector rel {rel(flat_a, flat_b):.2e}, "
+          f"cos {cos:.6f}  [{'ok' if good else 'FAIL'} tol {tol}]", flush=True)
+
+
+for mode, overlap in (("graph", "1"), ("graph", "0"), ("eager", "1")):
+    os.environ["MTBC_DP_OVERLAP"] = overlap
+    # ---------------------------------------------------------------- 1. random cotangent
+    torch.manual_seed(1993)
+    model = mk().to(dev)
+    ts = TrainStep(model, (b, 1, S, S), process_group=dist.group.WORLD, use_graph=(mode == "graph"),
+                   external_cotangent=True, lr=0.0)
+    ts.load_batch(img[sl], mask[sl], onehot[sl])
+    fill_cotangents(ts, rank * b, (rank + 1) * b)
+    ts.step(); ts.step()
     torch.cuda.synchronize()
-    out.append(ts.losses()[0].item())
-chk = ts.flat_p.double().abs().sum().item()
-allc = [None, None]
-dist.all_gather_object(allc, chk)
+    g_dp = ts.plan.grad_flat.clone()
+    if rank == 0:
+        print(f"== {arch} global batch {B} @{S}x{S}: {world} ranks x {b}  vs  1 rank x {B}; mode {mode}, overlap {overlap}", flush=True)
+        torch.manual_seed(1993)
+        full = mk().to(dev)
+        tf = TrainStep(full, (B, 1, S, S), use_graph=False, external_cotangent=True, lr=0.0)
+        tf.load_batch(img, mask, onehot)
+        fill_cotangents(tf, 0, B)
+        tf.step()
+        torch.cuda.synchronize()
+        per_param(ts, g_dp, tf.plan.grad_flat, "random cotangent, all-reduced gradient vs full batch", 2e-2)
+        del tf, full
+    del ts, model
+    # ---------------------------------------------------------------- 2. real objective, 3 Adam steps
+    torch.manual_seed(1993)
+    model = mk().to(dev)
+    ts = TrainStep(model, (b, 1, S, S), process_group=dist.group.WORLD, use_graph=(mode == "graph"), lr=1e-4)
+    ts.load_batch(img[sl], mask[sl], onehot[sl])
+    losses = []
+    for i in range(3):
+        ts.step()
+        torch.cuda.synchronize()
+        l = ts.losses()[:3].clone()
+        dist.all_reduce(l)            # logging only: mean over ranks of the per-rank means == full-batch mean
+        losses.append((l / world).tolist())
+    chk = [None] * world
+    dist.all_gather_object(chk, ts.flat_p.double().sum().item())
+    same = all(c == chk[0] for c in chk)
+    ok &= same
+    if rank == 0:
+        torch.manual_seed(1993)
+        full = mk().to(dev)
+        tf = TrainStep(full, (B, 1, S, S), use_graph=False, lr=1e-4)
+        tf.load_batch(img, mask, onehot)
+        for i in range(3):
+            tf.step()
+            torch.cuda.synchronize()
+            lf = tf.losses()[:3].tolist()
+            d = max(abs(x - y) / abs(y) for x, y in zip(losses[i], lf))
+            good = d < 2e-3
+            ok &= good
+            print(f"  real objective step {i}: DP mean loss {losses[i][0]:.6f} vs full batch {lf[0]:.6f} (worst rel of "
+                  f"total/seg/cls {d:.2e}) [{'ok' if good else 'FAIL'}]", flush=True)
+        dp = (ts.flat_p - tf.flat_p).abs().max().item()
+        good = dp <= 3 * 2.05e-4
+        ok &= good
+        print(f"  parameters after 3 Adam steps: identical on all ranks: {same}; max |DP - single| = {dp:.2e} "
+              f"(bound 3 lr = 3e-4 each way) [{'ok' if good and same else 'FAIL'}]", flush=True)
+        del tf, full
+    del ts, model
+    torch.cuda.empty_cache()
+    dist.barrier()
+flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print(f"mode {mode} overlap {os.environ.get('MTBC_DP_OVERLAP', '1')}: losses {['%.5f' % v for v in out]} param checksum per rank {allc} "
-          f"(ranks identical: {abs(allc[0] - allc[1]) < 1e-9 * abs(allc[0])})", flush=True)
+    print("DP CHECK", "PASSED" if flag.item() == 1.0 else "FAILED", flush=True)
 dist.barrier()
 dist.destroy_process_group()
+sys.exit(0 if flag.item() == 1.0 else 1)

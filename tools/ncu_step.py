@@ -46,5 +46,6 @@ rt.cudaProfilerStop()
 meta = [{"kind": l.kind, "desc": getattr(l, "desc", ""), "flops": getattr(l, "true_flops", 0.0),
          "nk": getattr(l, "n_kernels", 1)} for l in launches]
 if out != "/dev/null":
-    json.dump({"arch": arch, "B": B, "S": S, "launches": meta}, open(out, "w"))
+    from multi_task_breast_cancer_b200 import build as _b
+    json.dump({"arch": arch, "B": B, "S": S, "build_digest": _b.lib_digest(), "launches": meta}, open(out, "w"))
 print(f"ncu_step: {len(launches)} plan launches")

@@ -12,6 +12,9 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 src, tag = sys.argv[1], sys.argv[2]
+# the plain (un-profiled) run of tools/ncu_step.py that precedes the ncu pass records which build it was
+_meta_path = src.replace("_launches.csv", "_step_launches.json")
+build_digest = json.load(open(_meta_path)).get("build_digest") if os.path.exists(_meta_path) else None
 rows = list(csv.reader(l for l in open(src) if l.startswith('"')))
 h = rows[0]
 ki, mi, vi, ii, ui = (h.index(c) for c in ("Kernel Name", "Metric Name", "Metric Value", "ID", "Metric Unit"))
@@ -51,5 +54,5 @@ for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
 open(os.path.join(ROOT, "profiles", f"{tag}_launches.md"), "w").write("\n".join(lines) + "\n")
 traffic = {k: {"dram_bytes_per_step": a["rd"] + a["wr"], "kernels": a["n"], "us": a["us"]} for k, a in agg.items()}
-json.dump({"tag": tag, "by_kind": traffic}, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+json.dump({"tag": tag, "build_digest": build_digest, "by_kind": traffic}, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 print("\n".join(lines))
