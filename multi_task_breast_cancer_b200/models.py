@@ -53,6 +53,12 @@ class _PlanFunction(torch.autograd.Function):
                 f"per input shape and forward #{plan.generation} has overwritten those of forward #{ctx.generation}. "
                 "Call backward() before the next forward of the same shape (gradient accumulation as "
                 "forward; backward; forward; backward works), or run the extra forward under torch.no_grad().")
+        # Gradient accumulation (backward without zero_grad in between): a `.grad` delivered by an earlier backward IS a
+        # view of the plan's gradient buffer, which this backward is about to overwrite.  Move such gradients to memory
+        # of their own first; _deliver_grads then adds the new gradient to them (torch's `.grad +=` semantics).
+        for name, p in plan.params.items():
+            if p.grad is not None and p.grad.data_ptr() == plan.grad_view[name].data_ptr():
+                p.grad = p.grad.clone()
         ncls = len(plan.outputs_cls)
         for buf, g in zip(plan.g_cls, grads[:ncls]):
             if g is None:
@@ -124,9 +130,9 @@ class _PlanModule(nn.Module):
             if not plan.has_grad[name] or not p.requires_grad:
                 continue
             g = plan.grad_view[name]
-            if p.grad is None or p.grad.data_ptr() == g.data_ptr():
-                p.grad = g
-            else:
+            if p.grad is None:
+                p.grad = g          # no copy: the optimizer reads the plan's buffer (valid until the next backward)
+            elif p.grad.data_ptr() != g.data_ptr():
                 p.grad.add_(g)
 
     def _run(self, x: torch.Tensor):

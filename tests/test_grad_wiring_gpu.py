@@ -1,18 +1,24 @@
-"""Reverse-mode WIRING of the static plans (plan.py) against the fp32 oracle, parameter by parameter.
+"""Reverse-mode WIRING of the static plans (plan.py), parameter by parameter, on the B200.
 
-Why a random cotangent.  With the real objective at random init the Dice gradient is nearly uniform over the plane, each
-InstanceNorm backward subtracts the plane mean from it, and what is left is a small difference of large numbers: the
-fp32 oracle's own gradient moves by 20 % (median over parameters, up to 60 %) when nothing but its WEIGHTS are rounded to
-bf16 (tools/emulate_bf16.py, EMU=w; rounding the gradient tensors instead, EMU=ga,gy, moves it by 0.4-0.6 %).  A
-whole-network check under that objective therefore cannot tell a missing contribution from rounding (round 1 asserted
-cos > 0.6).  Filling every output's gradient with randn removes the cancellation: a bf16 forward perturbation of 1e-2
-then moves a parameter gradient by O(1e-2), while a dropped consumer of a multi-consumer tensor, a shared module that
-only counts one of its two applications, or a wrong K offset of one concat source moves it by O(1)
-(`test_tolerance_would_catch_a_dropped_consumer` shows the margin on the oracle itself).
+Objective: a RANDOM COTANGENT on every output (sum(out * g), g ~ randn) instead of the Dice + focal loss, so that no
+near-uniform loss gradient is cancelled by the InstanceNorm backward.
 
-Asserted per parameter (relative L2 against the oracle's fp32 gradient): conv / InstanceNorm-affine / transposed-conv
-parameters and the class FC layers <= 5e-2, mask-head parameters <= 1e-2 (bf16 activations, fp32 head arithmetic);
-parameters the reference leaves without gradient must have none here either."""
+Checker: the fp32 oracle WITH THE SAME STORAGE PRECISION (oracle/emulation.py: conv outputs, activations, their
+gradients and the conv weights rounded to bf16, everything else fp32).  Against the PLAIN fp32 oracle no bf16
+implementation can be tight, whatever its kernels: a forward rounding error eps moves a fraction ~0.8*eps of the
+LeakyReLU units across 0, each of those takes the other slope in the backward pass, and the per-parameter gradient moves
+by ~0.9*sqrt(0.8*eps) ~ 8 % per layer at eps = 1e-2, growing with depth -- measured on the oracle against itself with
+nothing but storage rounding switched on (tools/emulate_bf16.py with OBJ=random: 10 % one layer below the head, 20-57 %
+in the encoder and the class branch, where the global-average-pool hands every InstanceNorm a plane-constant gradient;
+tests/test_host_logic.py::test_bf16_storage_alone_moves_gradients pins that on the CPU).  With the rounding emulated on
+the checker's side those flips are common mode; what is left is fp32 summation order.  A dropped consumer of a
+multi-consumer tensor, a shared module counted once or a wrong K offset of one concat source is O(1) either way
+(`test_tolerance_would_catch_a_dropped_consumer`).
+
+Asserted per parameter (relative L2 against the storage-emulating oracle): conv / InstanceNorm-affine / transposed-conv
+parameters and the class FC layers <= 5e-2, mask-head parameters <= 1e-2; parameters the reference leaves without
+gradient must have none here either.  The same comparison against the plain fp32 oracle is printed and asserted only
+by direction (cosine), for the record."""
 import pytest
 import torch
 
@@ -71,7 +77,6 @@ def backward_random(model, img, gc=None, gs=None):
 
 
 MASK_HEADS = ("final_conv_", "output")                              # 1x1 / composed deep-supervision mask heads
-CLASS_FC = ("classifier.1.", "classifier.3.", "classifier.5.")        # Linear layers behind GAP / Flatten
 # parameters whose gradient only comes out right if the explicit reverse-mode bookkeeping is right
 MUST_CHECK = {
     "unetpp": [
@@ -104,46 +109,56 @@ MUST_CHECK = {
                                          ("bts", True, 2, 128), ("bts", False, 2, 128), ("unetpp", True, 3, 64)])
 def test_random_cotangent_gradients_match_oracle_per_parameter(arch, ds, B, S):
     from oracle import torch_oracle as O
+    from oracle.emulation import named_grads, with_bf16_storage
     ref, new = pair(arch, ds)
+    emu = with_bf16_storage(ref)
     img, *_ = O.synthetic_batch(B, S, S, device="cuda")
     gc, gs = backward_random(ref, img)
+    backward_random(emu, img, gc, gs)
     backward_random(new, img, gc, gs)
     torch.cuda.synchronize()
-    pr, pn = dict(ref.named_parameters()), dict(new.named_parameters())
-    scale = max(p.grad.norm().item() / p.numel() ** 0.5 for p in pr.values() if p.grad is not None)
+    g_ref, g_emu, pn = named_grads(ref), named_grads(emu), dict(new.named_parameters())
+    scale = max(g.norm().item() / g.numel() ** 0.5 for g in g_emu.values() if g is not None)
     rows, bad = [], []
     for n, p in pn.items():
-        r = pr[n]
-        assert (p.grad is None) == (r.grad is None), f"{n}: gradient presence differs from the reference"
-        if r.grad is None:
+        r = g_emu[n]
+        assert (p.grad is None) == (r is None) == (g_ref[n] is None), f"{n}: gradient presence differs from the reference"
+        if r is None:
             continue
         assert p.grad.shape == p.shape and p.grad.dtype == torch.float32 and torch.isfinite(p.grad).all(), n
-        rms = r.grad.norm().item() / r.grad.numel() ** 0.5
+        rms = r.norm().item() / r.numel() ** 0.5
         if rms < 1e-6 * scale:
             # conv bias in front of an InstanceNorm: identically zero here, ~1e-9 noise in the reference
             assert p.grad.abs().max().item() <= 1e-5 * scale, (n, p.grad.abs().max().item())
             continue
-        e = rel(p.grad, r.grad)
-        # mask heads: fp32 arithmetic on bf16 activations -> 1e-2; the class FC layers sit behind the whole encoder (their
-        # input carries its accumulated bf16 error, and hidden ReLU units near 0 may flip) -> the conv-stack bound
+        e = rel(p.grad, r)
+        # mask heads: fp32 arithmetic on bf16 activations -> 1e-2; the class FC layers sit behind the whole encoder (a
+        # hidden ReLU unit at 0 may still differ by summation order) -> the conv-stack bound
         tol = 1e-2 if n.startswith(MASK_HEADS) else 5e-2
-        rows.append((e, n, tol))
+        rows.append((e, n, tol, rel(p.grad, g_ref[n]), rel(r, g_ref[n])))
         if e > tol:
-            bad.append((n, e, tol))
+            bad.append((n, round(e, 4), tol))
     rows.sort(reverse=True)
-    print(f"\n{arch} ds={ds} B={B} {S}x{S}: {len(rows)} parameters checked, worst:")
-    for e, n, tol in rows[:8]:
-        print(f"   {n:55s} rel {e:.4f} (tol {tol})")
-    checked = {n for _, n, _ in rows}
+    print(f"\n{arch} ds={ds} B={B} {S}x{S}: {len(rows)} parameters; rel-L2 of the CUDA gradient vs the bf16-storage oracle "
+          f"| CUDA vs plain fp32 oracle | bf16-storage oracle vs plain fp32 oracle (the storage format's own price):")
+    for e, n, tol, e32, emu32 in rows[:10]:
+        print(f"   {n:55s} {e:.4f} (tol {tol}) | {e32:.4f} | {emu32:.4f}")
+    med = sorted(r[0] for r in rows)[len(rows) // 2]
+    med32 = sorted(r[3] for r in rows)[len(rows) // 2]
+    print(f"   median {med:.4f} | {med32:.4f} | {sorted(r[4] for r in rows)[len(rows) // 2]:.4f}")
+    checked = {r[1] for r in rows}
     for n in MUST_CHECK[arch]:
-        if n in pn and pr[n].grad is not None:
+        if n in pn and g_emu[n] is not None:
             assert n in checked, f"{n} was not compared"
     assert not bad, bad
-    # whole-vector agreement follows from the per-parameter bound; assert it anyway (round 1 asserted > 0.6)
-    a = torch.cat([pn[n].grad.flatten() for _, n, _ in rows])
-    b = torch.cat([pr[n].grad.flatten() for _, n, _ in rows])
+    a = torch.cat([pn[r[1]].grad.flatten() for r in rows])
+    b = torch.cat([g_emu[r[1]].flatten() for r in rows])
+    c = torch.cat([g_ref[r[1]].flatten() for r in rows])
     cos = torch.nn.functional.cosine_similarity(a, b, dim=0).item()
+    cos32 = torch.nn.functional.cosine_similarity(a, c, dim=0).item()
+    print(f"   flat gradient: cos vs bf16-storage oracle {cos:.5f}, vs plain fp32 oracle {cos32:.5f}")
     assert cos > 0.999, cos
+    assert cos32 > 0.9, cos32      # for the record: round 1 asserted > 0.6 (with the real loss)
 
 
 def test_tolerance_would_catch_a_dropped_consumer():

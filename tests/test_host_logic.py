@@ -171,3 +171,43 @@ def test_step_segments_split_at_bucket_markers():
     assert [[l.kind for l in ls] for ls, _ in segs] == [["a", "b"], ["c"], [], ["d", "e"], []]
     assert [k for _, k in segs] == [0, 1, 2, 3, None]
     assert sum(len(ls) for ls, _ in segs) == sum(l.kind != "bucket_ready" for l in fb)
+
+
+def test_bf16_storage_alone_moves_gradients():
+    """No kernel involved: the fp32 oracle against itself with nothing but the B200 path's STORAGE rounding switched on
+    (oracle/emulation.py).  With a random cotangent on every output (no Dice / InstanceNorm cancellation) the forward
+    moves by ~1e-2, yet per-parameter gradients move by 10 % and more: LeakyReLU units whose pre-activation lies within
+    the rounding error of 0 take the other slope.  This is why tests/test_grad_wiring_gpu.py checks the CUDA path
+    against the storage-emulating oracle (and why round 1's check against the plain oracle could only assert a
+    direction)."""
+    from oracle.emulation import named_grads, with_bf16_storage
+    torch.manual_seed(1993)
+    ref = O.MTUNetPlusPlus(in_channels=1, out_channels=1, n_classes=3, deep_supervision=True)
+    emu = with_bf16_storage(ref)
+    img, *_ = O.synthetic_batch(1, 64, 64)
+    outs = []
+    for m in (ref, emu):
+        g = torch.Generator().manual_seed(11)
+        logits, segs = m(img)
+        sum((t * torch.randn(t.shape, generator=g)).sum() for t in list(logits) + list(segs)).backward()
+        outs.append(segs[-1].detach())
+    fwd = ((outs[1] - outs[0]).norm() / outs[0].norm()).item()
+    gr, ge = named_grads(ref), named_grads(emu)
+
+    def rel(n):
+        return ((ge[n] - gr[n]).norm() / gr[n].norm()).item()
+    assert 2e-3 < fwd < 5e-2, fwd                                   # the forward moves by ~1e-2 ...
+    assert rel("final_conv_0_4.weight") < 5e-2                      # ... the head's own gradient likewise ...
+    assert rel("upcat_0_4.convs.conv_0.conv.weight") > 5e-2         # ... one TwoConv below it: already beyond 5e-2 ...
+    assert rel("conv_2_0.convs.conv_0.conv.weight") > 0.1           # ... and the encoder far beyond
+    # rounding only the gradient tensors (forward untouched) costs two orders of magnitude less
+    emu_g = with_bf16_storage(ref, what=("gy", "ga"))
+    ref.zero_grad(set_to_none=True)
+    for m in (ref, emu_g):
+        g = torch.Generator().manual_seed(11)
+        logits, segs = m(img)
+        sum((t * torch.randn(t.shape, generator=g)).sum() for t in list(logits) + list(segs)).backward()
+    gr, gg = named_grads(ref), named_grads(emu_g)
+    e = ((gg["conv_2_0.convs.conv_0.conv.weight"] - gr["conv_2_0.convs.conv_0.conv.weight"]).norm()
+         / gr["conv_2_0.convs.conv_0.conv.weight"].norm()).item()
+    assert e < 2e-2, e

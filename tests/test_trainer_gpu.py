@@ -154,9 +154,13 @@ def test_ragged_last_batch_trains_and_validates_like_the_reference():
     # second epoch: both graphs are replayed (no re-capture), still three more steps
     runner.train_one_epoch(iter(data))
     assert int(ts.step_dev.item()) == 6
+    # validation on the ragged loader, against the oracle carrying OUR weights (six bf16 / fp32 Adam steps apart the
+    # two trainings have drifted by a few percent in the class loss; that is not what is checked here)
+    ref.load_state_dict(new.state_dict())
     v = runner.validate_one_epoch(iter(data))
     e = O.validate_one_epoch(ref, data)
-    assert abs(v[0] - e[0]) < 2e-2 * abs(e[0]), (v, e)
+    assert abs(v[0] - e[0]) < 1e-2 * abs(e[0]), (v, e)
+    assert abs(v[4] - e[4]) < 5e-3 * abs(e[4]) and abs(v[5] - e[5]) < 2e-2 * abs(e[5]), (v, e)
     assert set(runner._eval) == {3, 2}
 
 

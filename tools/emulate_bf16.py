@@ -22,22 +22,6 @@ from oracle import torch_oracle as O
 MODE = set(os.environ.get("EMU", "y,a,gy,ga,w").split(","))
 
 
-def make_round(fwd, bwd):
-    class R(torch.autograd.Function):
-        @staticmethod
-        def forward(ctx, x):
-            return x.to(torch.bfloat16).float() if fwd else x.clone()
-
-        @staticmethod
-        def backward(ctx, g):
-            return g.to(torch.bfloat16).float() if bwd else g
-    return R
-
-
-RoundY = make_round("y" in MODE, "gy" in MODE)
-RoundA = make_round("a" in MODE, "ga" in MODE)
-
-
 def rel(a, b):
     return ((a - b).norm() / (b.norm() + 1e-20)).item()
 
@@ -53,6 +37,17 @@ def build(arch):
 def run(model, img, mask, onehot):
     model.zero_grad(set_to_none=True)
     logits, outs = model(img)
+    if os.environ.get("OBJ") == "random_seg":
+        g = torch.Generator().manual_seed(11)
+        obj = sum((t * torch.randn(t.shape, generator=g)).sum() for t in list(outs)) + 0.0 * sum(t.sum() for t in logits)
+        obj.backward()
+        return logits, outs
+    if os.environ.get("OBJ") == "random":
+        # random cotangent on every output (tests/test_grad_wiring_gpu.py): no Dice / InstanceNorm cancellation
+        g = torch.Generator().manual_seed(11)
+        obj = sum((t * torch.randn(t.shape, generator=g)).sum() for t in list(logits) + list(outs))
+        obj.backward()
+        return logits, outs
     seg, cls = O.multitask_criterion(O.DiceLoss(), mask, outs, O.FocalLoss(), onehot, logits, True)
     (0.35 * seg + 0.65 * cls).backward()
     return logits, outs
@@ -63,17 +58,9 @@ def main():
     B, H, W = (int(v) for v in sys.argv[2:5])
     torch.manual_seed(1993)
     ref = build(arch)
-    emu = copy.deepcopy(ref)
+    from oracle.emulation import named_grads, with_bf16_storage
+    emu = with_bf16_storage(ref, MODE)
     img, mask, onehot, _ = O.synthetic_batch(B, H, W)
-    for n, m in emu.named_modules():
-        is_ds_head = n.startswith("output") or n.startswith("final_conv")
-        if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)) and not is_ds_head:
-            if "w" in MODE:
-                with torch.no_grad():
-                    m.weight.copy_(m.weight.to(torch.bfloat16).float())
-            m.register_forward_hook(lambda mod, i, o: RoundY.apply(o))
-        if isinstance(m, nn.LeakyReLU):
-            m.register_forward_hook(lambda mod, i, o: RoundA.apply(o))
     rl, ro = run(ref, img, mask, onehot)
     el, eo = run(emu, img, mask, onehot)
     print(f"== {arch} B{B} {H}x{W}: bf16-storage emulation {sorted(MODE)} vs fp32")
@@ -83,12 +70,12 @@ def main():
         print(f"  class logits rel {rel(a, b):.4g}")
     for a, b in zip(eo, ro):
         print(f"  mask logits rel {rel(a, b):.4g}")
-    pr = dict(ref.named_parameters())
+    pr, pe = named_grads(ref), named_grads(emu)
     rows = []
-    for n, p in emu.named_parameters():
-        if p.grad is None or pr[n].grad is None:
+    for n, g in pe.items():
+        if g is None or pr[n] is None:
             continue
-        rows.append((rel(p.grad, pr[n].grad), n, pr[n].grad.norm().item()))
+        rows.append((rel(g, pr[n]), n, pr[n].norm().item()))
     med = sorted(r[0] for r in rows)[len(rows) // 2]
     print(f"  grads: median rel {med:.4g}; max {max(r[0] for r in rows if r[2] > 1e-6):.4g}")
     for e, n, s in rows[::-1]:
