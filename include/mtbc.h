@@ -34,6 +34,21 @@ const char* mtbc_build_digest(void);
 /* 0 if the current device is sm_100 and the tensor-map driver entry point resolves. */
 int mtbc_device_check(void);
 
+/* Execution mode of the calling thread for the element-type generic entry points below (every function that takes an
+ * NHWC activation as `const void*` / `void*`).  Default 0 = the product path: bf16 activations.
+ *   MTBC_MODE_ACT_FP32      the activation pointers hold fp32 (TF32 parity mode, north_star "1e-3 (TF32 mode)": fp32
+ *                           storage, tcgen05.mma kind::tf32 through mtbc_conv_gemm_desc.dtype = 1 or 3)
+ *   MTBC_MODE_DETERMINISTIC reductions whose order would depend on block scheduling take an order-independent path
+ * A launch list is built under one mode and must be launched under the same mode (plan.py sets it around each call;
+ * a CUDA graph bakes the choice in at capture). */
+#define MTBC_MODE_ACT_FP32 1
+#define MTBC_MODE_DETERMINISTIC 2
+int mtbc_set_mode(int32_t flags);
+int mtbc_get_mode(void);
+/* Scratch an entry point needs beyond the buffers in its signature, in bytes (0 for every entry point but the ones
+ * named here; -1 for bad arguments).  op = "in_stats_det": N samples, HW pixels per plane, channel pitch Cp. */
+int64_t mtbc_query_workspace_bytes(const char* op, int32_t N, int64_t HW, int32_t Cp);
+
 /* ------------------------------------------------------------------------------------------------------------- */
 /* Strided NHWC view of a bf16 activation (channel stride 1).  Strides in elements.                               */
 typedef struct {
@@ -93,6 +108,12 @@ typedef struct {
    * bias/statistics): columns are routed to outs[]; creation fails with MTBC_ERR_INVALID if the shape is not eligible. */
   int32_t nouts;
   mtbc_out_slice outs[MTBC_MAX_VIEWS];
+  /* Element type of views / wpack / out.  0: bf16 operands, tcgen05.mma kind::f16 (the product path).
+   * 1: fp32 storage, tcgen05.mma kind::tf32 (the TF32 parity mode of north_star; wpack holds TF32-rounded values).
+   * 3: fp32 storage, 3xTF32: wpack_lo holds the TF32 rounding of (w - tf32(w)), the kernel splits the activations
+   *    the same way in shared memory and issues a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (fp32-grade products). */
+  int32_t dtype;
+  const void* wpack_lo;
 } mtbc_conv_gemm_desc;
 
 /* One tap of a weight-gradient GEMM: dW[tap][co][k0 + ci] += sum_pixels A[a_view][pixel + (a_dh,a_dw)][ci] *
@@ -208,6 +229,11 @@ int mtbc_conv_first_wgrad(const float* x, int32_t N, int32_t Cin, int32_t H, int
 
 /* Per-(n,c) sum / sum of squares of a bf16 NHWC tensor (used when the producing GEMM could not fuse them). */
 int mtbc_in_stats(const void* y, int32_t N, int32_t HW, int32_t Cp, float* stat_sum, float* stat_sq, void* stream);
+/* Same result, bit-identical from run to run: no floating-point atomics (block partials in `workspace`, added in block
+ * order by the last block to arrive).  stat_sum / stat_sq are STORED, not accumulated.  workspace:
+ * mtbc_query_workspace_bytes("in_stats_det", N, HW, Cp) bytes, zeroed once by the caller (the kernel re-arms it). */
+int mtbc_in_stats_det(const void* y, int32_t N, int32_t HW, int32_t Cp, float* stat_sum, float* stat_sq,
+                      void* workspace, void* stream);
 /* a = lrelu(((y-mean)*rstd)*gamma+beta); mean/rstd (fp32 [N][Cp]) are written for the backward pass.
  * gamma/beta may be NULL (affine=False).  pooled (bf16 [N][H/2][W/2][Cp]) optional. */
 int mtbc_in_apply(const void* y, int32_t N, int32_t H, int32_t W, int32_t Cp, const float* stat_sum,

@@ -35,7 +35,8 @@ class ConvGemmDesc(C.Structure):
                 ("wpack", c_vp), ("w_ntaps", c_i32), ("w_ktot", c_i32), ("ncols", c_i32),
                 ("W", c_i32), ("H", c_i32), ("N", c_i32), ("epi_mode", c_i32), ("out", c_vp), ("out_C", c_i32),
                 ("up_k", c_i32), ("up_cp", c_i32), ("bias", c_vp), ("stat_sum", c_vp), ("stat_sq", c_vp),
-                ("stat_C", c_i32), ("accumulate", c_i32), ("nouts", c_i32), ("outs", OutSlice * MAX_VIEWS)]
+                ("stat_C", c_i32), ("accumulate", c_i32), ("nouts", c_i32), ("outs", OutSlice * MAX_VIEWS),
+                ("dtype", c_i32), ("wpack_lo", c_vp)]
 
 
 class WgradTap(C.Structure):
@@ -64,6 +65,10 @@ JOB_COPY_F32, JOB_PACK_CONV, JOB_PACK_CONVT, JOB_UNPACK_CONV, JOB_UNPACK_CONVT =
 _SIGS = {
     "mtbc_abi_version": [],
     "mtbc_device_check": [],
+    "mtbc_set_mode": [c_i32],
+    "mtbc_get_mode": [],
+    "mtbc_query_workspace_bytes": [C.c_char_p, c_i32, c_i64, c_i32],
+    "mtbc_in_stats_det": [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp],
     "mtbc_conv_gemm_create": [C.POINTER(ConvGemmDesc), C.POINTER(c_vp)],
     "mtbc_wgrad_create": [C.POINTER(WgradDesc), C.POINTER(c_vp)],
     "mtbc_wgrad_multi_create": [C.POINTER(WgradMultiDesc), C.POINTER(c_vp)],
@@ -127,7 +132,8 @@ _SIGS = {
     "mtbc_f32_to_bf16_nhwc": [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp],
     "mtbc_bf16_nhwc_to_f32": [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp],
 }
-_RESTYPES = {"mtbc_op_destroy": None, "mtbc_op_flops": c_f64}
+_RESTYPES = {"mtbc_op_destroy": None, "mtbc_op_flops": c_f64, "mtbc_query_workspace_bytes": c_i64}
+MODE_ACT_FP32, MODE_DETERMINISTIC = 1, 2
 
 EXPORTED_SYMBOLS = sorted(list(_SIGS) + ["mtbc_last_error", "mtbc_build_digest"])
 ABI_VERSION = 3

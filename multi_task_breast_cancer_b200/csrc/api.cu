@@ -15,6 +15,9 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
+static thread_local int g_mode = 0;
+int current_mode() { return g_mode; }
+
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(MTBC_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
@@ -36,6 +39,13 @@ int mtbc_abi_version(void) { return 3; }
 #endif
 // SHA-256 of the sources + flags this binary was compiled from (build.py:_digest); _lib.load() refuses a mismatch.
 const char* mtbc_build_digest(void) { return MTBC_BUILD_DIGEST; }
+
+int mtbc_set_mode(int32_t flags) {
+  if (flags & ~(mtbc::MODE_ACT_FP32 | mtbc::MODE_DETERMINISTIC)) return mtbc::set_error(MTBC_ERR_INVALID, "set_mode: unknown flag bits 0x%x", flags);
+  mtbc::g_mode = flags;
+  return 0;
+}
+int mtbc_get_mode(void) { return mtbc::g_mode; }
 
 int mtbc_device_check(void) {
   int dev = 0;

@@ -8,10 +8,12 @@
 //    same NHWC boxes; accumulators for up to 9 taps live side by side in TMEM; split over pixel ranges with fp32 atomics.
 #include "ptx.cuh"
 #include "internal.h"
+#include "act_io.cuh"
 #include <cuda.h>
 #include <vector>
 #include <algorithm>
 #include <string.h>
+#include <type_traits>
 #include <stdlib.h>
 
 namespace mtbc {
@@ -26,13 +28,14 @@ struct SegDev {
 struct ConvGemmParams {
   CUtensorMap amap[MTBC_MAX_VIEWS];
   CUtensorMap wmap[2];  // [0]: 32-channel boxes / 64B swizzle, [1]: 64-channel boxes / 128B swizzle
+                        // (fp32 operands: [0] = the 32-float / 128B-swizzle box of wpack, [1] = the same of wpack_lo)
   SegDev seg[MTBC_MAX_SEGS];
   int32_t nseg;
   int32_t TW, TH, TN, tiles_w, tiles_h, n_mtiles, n_ntiles;
   int32_t W, H, N;
   int32_t BN, tmem_cols, stages, a_stage_bytes, stage_bytes;
   int32_t epi_mode, out_C, up_k, up_cp, accumulate, stat_C, bias_len;
-  __nv_bfloat16* out;
+  void* out;
   const float* bias;
   float* stat_sum;
   float* stat_sq;
@@ -45,9 +48,19 @@ constexpr int kMaxBias = 1024;
 // warp % 4).  Two TMEM accumulators: the epilogue of work item i (TMEM -> registers -> bf16 global stores, the
 // dominant cost of the transposed convolutions, whose GEMM is a single K block) overlaps the loads and MMAs of item
 // i+1.  Work item = (pixel tile, N tile), N tile fastest so neighbouring CTAs share the A tile in L2.
-__global__ void __launch_bounds__(320) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+//
+// PREC 0: bf16 operands (kind::f16).  PREC 1: fp32 operands read as TF32 (kind::tf32): a 32-channel chunk is a
+// 128-byte row (the geometry of the bf16 64-channel chunk), four K = 8 instructions per chunk.  PREC 3: 3xTF32 -- the
+// four extra warps 10..13 split every landed A tile in place into its TF32 rounding and, in a second buffer, the
+// remainder; weights arrive pre-split (wpack, wpack_lo); three products per K step give fp32-grade results.
+template <int PREC>
+__global__ void __launch_bounds__(PREC == 3 ? 448 : 320) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  using OutT = typename std::conditional<PREC == 0, __nv_bfloat16, float>::type;
+  constexpr int ES = PREC == 0 ? 2 : 4;          // operand element size
+  constexpr int NT = PREC == 3 ? 448 : 320;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t s_full[kMaxStages];
+  __shared__ uint64_t s_split[kMaxStages];       // PREC 3: "A tile of this stage has been split"
   __shared__ uint64_t s_empty[kMaxStages];
   __shared__ uint64_t s_accfull[2], s_accempty[2];
   __shared__ uint32_t s_tmem;
@@ -59,13 +72,14 @@ __global__ void __launch_bounds__(320) conv_gemm_kernel(const __grid_constant__ 
   const int BN = p.BN;
   const int n_items = p.n_mtiles * p.n_ntiles;
 
-  for (int i = tid; i < 512; i += 320) (&s_stat[0][0])[i] = 0.f;
+  for (int i = tid; i < 512; i += NT) (&s_stat[0][0])[i] = 0.f;
   if (p.bias != nullptr)
-    for (int i = tid; i < p.bias_len; i += 320) s_bias[i] = p.bias[i];
+    for (int i = tid; i < p.bias_len; i += NT) s_bias[i] = p.bias[i];
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&s_full[s], 1);
       mbar_init(&s_empty[s], 1);
+      mbar_init(&s_split[s], 4);
     }
     for (int b = 0; b < 2; ++b) { mbar_init(&s_accfull[b], 1); mbar_init(&s_accempty[b], 8); }
     fence_mbar_init();
@@ -92,15 +106,17 @@ __global__ void __launch_bounds__(320) conv_gemm_kernel(const __grid_constant__ 
         for (int s = 0; s < p.nseg; ++s) {
           const SegDev sg = p.seg[s];
           const CUtensorMap* am = &p.amap[sg.view];
-          const CUtensorMap* wm = &p.wmap[sg.kc == 64 ? 1 : 0];
-          const uint32_t bytes = static_cast<uint32_t>((128 + BN) * sg.kc * 2);
+          const CUtensorMap* wm = &p.wmap[(PREC == 0 && sg.kc == 64) ? 1 : 0];
+          const uint32_t bytes = static_cast<uint32_t>((128 + (PREC == 3 ? 2 : 1) * BN) * sg.kc * ES);
           for (int ch = 0; ch < sg.nchunk; ++ch) {
             mbar_wait(&s_empty[stage], phase ^ 1u);
             uint8_t* a_dst = smem + stage * p.stage_bytes;
-            uint8_t* b_dst = a_dst + p.a_stage_bytes;
+            uint8_t* b_dst = a_dst + (PREC == 3 ? 2 : 1) * p.a_stage_bytes;
             mbar_arrive_expect_tx(&s_full[stage], bytes);
             tma_load_4d(a_dst, am, &s_full[stage], ch * sg.kc, w0 + sg.dw, h0 + sg.dh, n0);
             tma_load_3d(b_dst, wm, &s_full[stage], sg.wk0 + ch * sg.kc, ntile * BN, sg.wtap);
+            if (PREC == 3)
+              tma_load_3d(b_dst + BN * sg.kc * ES, &p.wmap[1], &s_full[stage], sg.wk0 + ch * sg.kc, ntile * BN, sg.wtap);
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -109,7 +125,7 @@ __global__ void __launch_bounds__(320) conv_gemm_kernel(const __grid_constant__ 
   } else if (warp == 1) {
     if (elect_one()) {
       // -------------------------------------------------------------- MMA issuer (one thread)
-      const uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      const uint32_t idesc = PREC == 0 ? umma_idesc_bf16(128, BN, 0, 0) : umma_idesc_tf32(128, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -122,18 +138,35 @@ __global__ void __launch_bounds__(320) conv_gemm_kernel(const __grid_constant__ 
         uint32_t accumulate = 0;
         for (int s = 0; s < p.nseg; ++s) {
           const SegDev sg = p.seg[s];
-          const uint32_t hi = umma_desc_hi(8u * sg.kc * 2u, sg.kc == 64 ? 2u : 4u);
+          const uint32_t hi = umma_desc_hi(8u * sg.kc * ES, sg.kc * ES == 128 ? 2u : 4u);
           for (int ch = 0; ch < sg.nchunk; ++ch) {
-            mbar_wait(&s_full[stage], phase);
+            mbar_wait(PREC == 3 ? &s_split[stage] : &s_full[stage], phase);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(smem + stage * p.stage_bytes);
-            const uint32_t a_lo = umma_desc_lo(a_addr, 16), b_lo = umma_desc_lo(a_addr + p.a_stage_bytes, 16);
+            const uint32_t a_lo = umma_desc_lo(a_addr, 16);
+            const uint32_t b_lo = umma_desc_lo(a_addr + (PREC == 3 ? 2 : 1) * p.a_stage_bytes, 16);
             // low descriptor words advance by compile-time steps: keeps the issuing lane at the tensor pipe's floor
-            umma_bf16_lohi(d_addr, a_lo, hi, b_lo, hi, idesc, accumulate);
-            umma_bf16_lohi(d_addr, a_lo + 2, hi, b_lo + 2, hi, idesc, 1u);
-            if (sg.kc == 64) {
-              umma_bf16_lohi(d_addr, a_lo + 4, hi, b_lo + 4, hi, idesc, 1u);
-              umma_bf16_lohi(d_addr, a_lo + 6, hi, b_lo + 6, hi, idesc, 1u);
+            if (PREC == 0) {
+              umma_bf16_lohi(d_addr, a_lo, hi, b_lo, hi, idesc, accumulate);
+              umma_bf16_lohi(d_addr, a_lo + 2, hi, b_lo + 2, hi, idesc, 1u);
+              if (sg.kc == 64) {
+                umma_bf16_lohi(d_addr, a_lo + 4, hi, b_lo + 4, hi, idesc, 1u);
+                umma_bf16_lohi(d_addr, a_lo + 6, hi, b_lo + 6, hi, idesc, 1u);
+              }
+            } else {
+              // 32 fp32 channels = one 128-byte row = four K = 8 steps of 32 bytes
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_tf32_lohi(d_addr, a_lo + 2 * k, hi, b_lo + 2 * k, hi, idesc, (k == 0) ? accumulate : 1u);
+              if (PREC == 3) {
+                // remainder terms: a_lo * w_hi and a_hi * w_lo (a_lo * w_lo is below fp32 resolution)
+                const uint32_t a2 = umma_desc_lo(a_addr + p.a_stage_bytes, 16);
+                const uint32_t b2 = umma_desc_lo(a_addr + 2 * p.a_stage_bytes + BN * sg.kc * ES, 16);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_tf32_lohi(d_addr, a2 + 2 * k, hi, b_lo + 2 * k, hi, idesc, 1u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_tf32_lohi(d_addr, a_lo + 2 * k, hi, b2 + 2 * k, hi, idesc, 1u);
+              }
             }
             accumulate = 1;
             umma_commit(&s_empty[stage]);
@@ -143,7 +176,40 @@ __global__ void __launch_bounds__(320) conv_gemm_kernel(const __grid_constant__ 
         umma_commit(&s_accfull[buf]);
       }
     }
-  } else {
+  } else if (PREC == 3 && warp >= 10) {
+    // ---------------------------------------------------------------- 3xTF32 splitter: 4 warps, 128 threads.  In place
+    // a -> tf32_rn(a); remainder a - tf32_rn(a) (itself exactly representable in fp32) into the second A buffer at
+    // the same (swizzled) offset; then make the generic-proxy writes visible to the tensor core's async proxy.
+    int stage = 0;
+    uint32_t phase = 0;
+    const int st = tid - 320;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      for (int s = 0; s < p.nseg; ++s) {
+        const int nchunk = p.seg[s].nchunk;
+        for (int ch = 0; ch < nchunk; ++ch) {
+          mbar_wait(&s_full[stage], phase);
+          float4* a_hi = reinterpret_cast<float4*>(smem + stage * p.stage_bytes);
+          float4* a_lo = reinterpret_cast<float4*>(smem + stage * p.stage_bytes + p.a_stage_bytes);
+          const int n4 = p.a_stage_bytes >> 4;
+          for (int i = st; i < n4; i += 128) {
+            const float4 v = a_hi[i];
+            float4 h, l;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(*reinterpret_cast<uint32_t*>(&h.x)) : "f"(v.x));
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(*reinterpret_cast<uint32_t*>(&h.y)) : "f"(v.y));
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(*reinterpret_cast<uint32_t*>(&h.z)) : "f"(v.z));
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(*reinterpret_cast<uint32_t*>(&h.w)) : "f"(v.w));
+            l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+            a_hi[i] = h;
+            a_lo[i] = l;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_split[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 2 && warp < 10) {
     // ---------------------------------------------------------------- epilogue: 8 warps, two per TMEM lane quarter,
     // each pair splitting the N tile's 16-column chunks in halves.  Short dependent chain per chunk (these warps are
     // alone on their schedulers): running output pointers instead of divisions, bias from shared memory, TMEM loads
@@ -161,7 +227,7 @@ __global__ void __launch_bounds__(320) conv_gemm_kernel(const __grid_constant__ 
     const int epi_mode = p.epi_mode, up_k = p.up_k, up_cp = p.up_cp, out_C = p.out_C;
     const int H = p.H, W = p.W, N = p.N;
     const int64_t Wo = static_cast<int64_t>(W) * up_k;
-    __nv_bfloat16* const out = p.out;
+    OutT* const out = static_cast<OutT*>(p.out);
     const int nchunks = BN >> 4;
     const int k_begin = half ? (nchunks + 1) >> 1 : 0;
     const int k_end = half ? nchunks : (nchunks + 1) >> 1;
@@ -177,7 +243,7 @@ __global__ void __launch_bounds__(320) conv_gemm_kernel(const __grid_constant__ 
       const bool valid = (n < N) && (h < H) && (w < W);
       // destination of this thread's first chunk, then running (q, bcol) for the pixel shuffle
       const int col0 = ntile * BN + k_begin * 16;
-      __nv_bfloat16* pixbase;
+      OutT* pixbase;
       int bcol, qi = 0, qj = 0;
       if (epi_mode == 0) {
         pixbase = out + ((static_cast<int64_t>(n) * H + h) * W + w) * out_C;
@@ -222,7 +288,7 @@ __global__ void __launch_bounds__(320) conv_gemm_kernel(const __grid_constant__ 
         }
         if (valid) {
           const int left = out_C - bcol;   // columns of this chunk that exist in the (possibly dense) destination
-          emit_bf16x16_n(pixbase + (static_cast<int64_t>(qi) * Wo + qj) * out_C + bcol, v, acc,
+          emit16_n<OutT>(pixbase + (static_cast<int64_t>(qi) * Wo + qj) * out_C + bcol, v, acc,
                          left >= 16 ? 16 : (left >= 8 ? 8 : 0), wide);
         }
         bcol += 16;
@@ -463,30 +529,34 @@ static PFN_tmapEncodeTiled get_encode() {
 bool tensor_map_available() { return get_encode() != nullptr; }
 
 // bf16 NHWC view -> 4D tensor map with box (kc, TW, TH, TN)
-int encode_act(CUtensorMap* m, const mtbc_act_view& v, int kc, int TW, int TH, int TN) {
+int encode_act(CUtensorMap* m, const mtbc_act_view& v, int kc, int TW, int TH, int TN, int fp32) {
   PFN_tmapEncodeTiled enc = get_encode();
   if (!enc) return set_error(MTBC_ERR_NO_DEVICE, "cuTensorMapEncodeTiled not available");
   if (v.C % 8 != 0 || (reinterpret_cast<uintptr_t>(v.ptr) & 15) != 0)
     return set_error(MTBC_ERR_INVALID, "activation view: C %% 8 != 0 or pointer not 16B aligned");
+  const cuuint64_t es = fp32 ? 4 : 2;
   cuuint64_t gdim[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N};
-  cuuint64_t gstr[3] = {(cuuint64_t)v.sW * 2, (cuuint64_t)v.sH * 2, (cuuint64_t)v.sN * 2};
+  cuuint64_t gstr[3] = {(cuuint64_t)v.sW * es, (cuuint64_t)v.sH * es, (cuuint64_t)v.sN * es};
   cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(v.ptr), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+  CUresult r = enc(m, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                   const_cast<void*>(v.ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   kc * es == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(MTBC_ERR_CUDA, "cuTensorMapEncodeTiled(act) failed: %d", (int)r);
   return 0;
 }
-int encode_w(CUtensorMap* m, const void* w, int ktot, int nrows, int ntaps, int kc, int BN) {
+int encode_w(CUtensorMap* m, const void* w, int ktot, int nrows, int ntaps, int kc, int BN, int fp32) {
   PFN_tmapEncodeTiled enc = get_encode();
   if (!enc) return set_error(MTBC_ERR_NO_DEVICE, "cuTensorMapEncodeTiled not available");
+  const cuuint64_t es = fp32 ? 4 : 2;
   cuuint64_t gdim[3] = {(cuuint64_t)ktot, (cuuint64_t)nrows, (cuuint64_t)ntaps};
-  cuuint64_t gstr[2] = {(cuuint64_t)ktot * 2, (cuuint64_t)ktot * 2 * nrows};
+  cuuint64_t gstr[2] = {(cuuint64_t)ktot * es, (cuuint64_t)ktot * es * nrows};
   cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)BN, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+  CUresult r = enc(m, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                   const_cast<void*>(w), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   kc * es == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(MTBC_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
   return 0;
@@ -513,9 +583,12 @@ struct ConvGemmOp : public OpBase {
   ConvGemmParams p;
   dim3 grid;
   int smem_bytes;
+  int prec = 0;
   double flops;
   int launch(cudaStream_t st) override {
-    conv_gemm_kernel<<<grid, 320, smem_bytes, st>>>(p);
+    if (prec == 0) conv_gemm_kernel<0><<<grid, 320, smem_bytes, st>>>(p);
+    else if (prec == 1) conv_gemm_kernel<1><<<grid, 320, smem_bytes, st>>>(p);
+    else conv_gemm_kernel<3><<<grid, 448, smem_bytes, st>>>(p);
     return check_launch("conv_gemm_kernel");
   }
   double op_flops() const override { return flops; }
@@ -535,7 +608,10 @@ struct WgradOp : public OpBase {
 
 int conv_gemm_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   if (!d || !out) return set_error(MTBC_ERR_INVALID, "null argument");
-  {
+  if (d->dtype != 0 && d->dtype != 1 && d->dtype != 3) return set_error(MTBC_ERR_INVALID, "conv_gemm: dtype %d", d->dtype);
+  const int fp32 = d->dtype != 0, es = fp32 ? 4 : 2, x3 = d->dtype == 3;
+  if (x3 && !d->wpack_lo) return set_error(MTBC_ERR_INVALID, "conv_gemm: 3xTF32 needs wpack_lo");
+  if (!fp32) {
     int rc = conv_halo_try_create(d, out);  // halo-tile kernel for 3x3 convs on large planes (conv_halo.cu)
     if (rc <= 0) return rc;                  // 0 = created, < 0 = error, > 0 = not eligible -> generic kernel below
   }
@@ -558,7 +634,7 @@ int conv_gemm_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   // 128 leave TMEM and shared memory for two CTAs per SM, i.e. 16 epilogue warps instead of 8 (MTBC_CONVT_BN=256 restores
   // the single 256-wide tile).
   const char* bn_env = getenv("MTBC_CONVT_BN");
-  const int bn_cap = (d->epi_mode == 1 && !(bn_env && atoi(bn_env) == 256)) ? 128 : 256;
+  const int bn_cap = ((d->epi_mode == 1 && !(bn_env && atoi(bn_env) == 256)) || x3) ? 128 : 256;
   const int BN = pick_bn(d->ncols, bn_cap, 16);
   if (BN == 0) { delete op; return set_error(MTBC_ERR_INVALID, "conv_gemm: no N tile for ncols=%d", d->ncols); }
   p.BN = BN;
@@ -568,9 +644,9 @@ int conv_gemm_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   for (int i = 0; i < d->nviews; ++i) {
     const mtbc_act_view& v = d->views[i];
     if (v.W != d->W || v.H != d->H || v.N != d->N) { delete op; return set_error(MTBC_ERR_INVALID, "conv_gemm: view %d geometry mismatch", i); }
-    kc_of_view[i] = (((v.C + 31) & ~31) % 64 == 0) ? 64 : 32;
+    kc_of_view[i] = (!fp32 && ((v.C + 31) & ~31) % 64 == 0) ? 64 : 32;   // 128-byte rows either way
     if (kc_of_view[i] > kcmax) kcmax = kc_of_view[i];
-    int rc = encode_act(&p.amap[i], v, kc_of_view[i], TW, TH, TN);
+    int rc = encode_act(&p.amap[i], v, kc_of_view[i], TW, TH, TN, fp32);
     if (rc) { delete op; return rc; }
   }
   bool use32 = false, use64 = false;
@@ -588,10 +664,12 @@ int conv_gemm_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
     ksum += C;
   }
   p.nseg = d->nseg;
-  if (use32) { int rc = encode_w(&p.wmap[0], d->wpack, d->w_ktot, d->ncols, d->w_ntaps, 32, BN); if (rc) { delete op; return rc; } }
-  if (use64) { int rc = encode_w(&p.wmap[1], d->wpack, d->w_ktot, d->ncols, d->w_ntaps, 64, BN); if (rc) { delete op; return rc; } }
-  p.a_stage_bytes = 128 * kcmax * 2;
-  p.stage_bytes = (128 + BN) * kcmax * 2;
+  if (use32) { int rc = encode_w(&p.wmap[0], d->wpack, d->w_ktot, d->ncols, d->w_ntaps, 32, BN, fp32); if (rc) { delete op; return rc; } }
+  if (use64) { int rc = encode_w(&p.wmap[1], d->wpack, d->w_ktot, d->ncols, d->w_ntaps, 64, BN, 0); if (rc) { delete op; return rc; } }
+  if (x3) { int rc = encode_w(&p.wmap[1], d->wpack_lo, d->w_ktot, d->ncols, d->w_ntaps, 32, BN, 1); if (rc) { delete op; return rc; } }
+  op->prec = d->dtype;
+  p.a_stage_bytes = 128 * kcmax * es;
+  p.stage_bytes = (x3 ? 2 : 1) * (128 + BN) * kcmax * es;
   p.stage_bytes = (p.stage_bytes + 1023) & ~1023;
   // small stages and <= 256 TMEM columns: two persistent CTAs per SM (they hide each other's pipeline bubbles)
   const bool two = (p.stage_bytes * 3 <= 100 * 1024) && (2 * p.tmem_cols <= 512);
@@ -603,7 +681,7 @@ int conv_gemm_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   op->smem_bytes = stages * p.stage_bytes + 1024;
   p.epi_mode = d->epi_mode; p.out_C = d->out_C; p.up_k = d->up_k > 0 ? d->up_k : 1; p.up_cp = d->up_cp > 0 ? d->up_cp : d->ncols;
   p.accumulate = d->accumulate; p.stat_C = d->stat_C;
-  p.out = reinterpret_cast<__nv_bfloat16*>(d->out);
+  p.out = d->out;
   p.bias = d->bias; p.stat_sum = d->stat_sum; p.stat_sq = d->stat_sq;
   p.bias_len = d->epi_mode == 1 ? p.up_cp : d->ncols;
   if (d->bias && p.bias_len > kMaxBias) { delete op; return set_error(MTBC_ERR_INVALID, "conv_gemm: bias longer than %d", kMaxBias); }
@@ -621,7 +699,9 @@ int conv_gemm_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
     op->grid = dim3(gx, 1, 1);
   }
   op->flops = 2.0 * double(d->N) * d->H * d->W * double(d->ncols) * ksum;
-  cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  cudaError_t e = d->dtype == 0 ? cudaFuncSetAttribute(conv_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)
+                  : d->dtype == 1 ? cudaFuncSetAttribute(conv_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)
+                                  : cudaFuncSetAttribute(conv_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   if (e != cudaSuccess) { delete op; return set_error(MTBC_ERR_CUDA, "cudaFuncSetAttribute(conv_gemm): %s", cudaGetErrorString(e)); }
   *out = op;
   return 0;
@@ -660,8 +740,8 @@ int wgrad_create(const mtbc_wgrad_desc* d, OpBase** out) {
   for (int t = 1; t <= d->ntaps; ++t) if (d->ntaps % t == 0 && t * BN <= 512) T = t;
   p.T = T; p.ntaps = d->ntaps;
   p.tmem_cols = tmem_cols_for(T * BN);
-  for (int i = 0; i < d->a_nviews; ++i) { int rc = encode_act(&p.amap[i], d->a_views[i], p.a_kc, TW, TH, TN); if (rc) { delete op; return rc; } }
-  for (int i = 0; i < d->b_nviews; ++i) { int rc = encode_act(&p.bmap[i], d->b_views[i], p.b_kc, TW, TH, TN); if (rc) { delete op; return rc; } }
+  for (int i = 0; i < d->a_nviews; ++i) { int rc = encode_act(&p.amap[i], d->a_views[i], p.a_kc, TW, TH, TN, 0); if (rc) { delete op; return rc; } }
+  for (int i = 0; i < d->b_nviews; ++i) { int rc = encode_act(&p.bmap[i], d->b_views[i], p.b_kc, TW, TH, TN, 0); if (rc) { delete op; return rc; } }
   for (int t = 0; t < d->ntaps; ++t) {
     const mtbc_wgrad_tap& tp = d->taps[t];
     if (tp.a_view < 0 || tp.a_view >= d->a_nviews || tp.b_view < 0 || tp.b_view >= d->b_nviews) { delete op; return set_error(MTBC_ERR_INVALID, "wgrad: tap %d view out of range", t); }

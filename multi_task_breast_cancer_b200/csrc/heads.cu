@@ -3,11 +3,13 @@
 // projections are pure HBM streams.
 #include "ptx.cuh"
 #include "internal.h"
+#include "act_io.cuh"
 
 namespace mtbc {
 
 // ------------------------------------------------------------------------------------------------ 1x1 head
-__global__ void __launch_bounds__(256) head1x1_fwd_kernel(const __nv_bfloat16* __restrict__ a, int64_t npix, int Cp,
+template <typename T>
+__global__ void __launch_bounds__(256) head1x1_fwd_kernel(const T* __restrict__ a, int64_t npix, int Cp,
                                                           int C, const float* __restrict__ w,
                                                           const float* __restrict__ b, float* __restrict__ logits) {
   extern __shared__ float s_w[];  // [Cp]
@@ -16,17 +18,12 @@ __global__ void __launch_bounds__(256) head1x1_fwd_kernel(const __nv_bfloat16* _
   const float bias = b ? b[0] : 0.f;
   const int cvec = Cp / 8;
   for (int64_t pix = blockIdx.x * 256ll + threadIdx.x; pix < npix; pix += gridDim.x * 256ll) {
-    const uint4* src = reinterpret_cast<const uint4*>(a + pix * Cp);
+    const T* src = a + pix * Cp;
     float acc = bias;
     for (int v = 0; v < cvec; ++v) {
-      const uint4 u = src[v];
-      const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+      const V8 u = load8<T>(src + v * 8);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = unpack_bf16x2(uu[k]);
-        acc = fmaf(f.x, s_w[v * 8 + 2 * k], acc);
-        acc = fmaf(f.y, s_w[v * 8 + 2 * k + 1], acc);
-      }
+      for (int k = 0; k < 8; ++k) acc = fmaf(u.f[k], s_w[v * 8 + k], acc);
     }
     logits[pix] = acc;
   }
@@ -35,9 +32,10 @@ __global__ void __launch_bounds__(256) head1x1_fwd_kernel(const __nv_bfloat16* _
 // dA[pix][c] (+)= dl[pix]*w[c];  dw[c] += sum_pix dl[pix]*a[pix][c];  db += sum_pix dl[pix]
 // Four independent 16-byte vectors per thread and iteration (loads issued before use), block reduction through a
 // parked-partials table instead of contended shared-memory atomics (see stream_pipe.cu).
-__global__ void __launch_bounds__(256) head1x1_bwd_kernel(const __nv_bfloat16* __restrict__ a,
+template <typename T>
+__global__ void __launch_bounds__(256) head1x1_bwd_kernel(const T* __restrict__ a,
                                                           const float* __restrict__ dl, int64_t npix, int Cp, int C,
-                                                          const float* __restrict__ w, __nv_bfloat16* __restrict__ dA,
+                                                          const float* __restrict__ w, T* __restrict__ dA,
                                                           int accumulate, float* __restrict__ dw,
                                                           float* __restrict__ db) {
   __shared__ float s_stage[9 * 256];   // [k][thread]: 8 channel partials + the bias partial
@@ -51,43 +49,29 @@ __global__ void __launch_bounds__(256) head1x1_bwd_kernel(const __nv_bfloat16* _
   for (int k = 0; k < 8; ++k) wv[k] = (v * 8 + k) < C ? w[v * 8 + k] : 0.f;
   constexpr int U = 4;
   for (int64_t i0 = start; i0 < total; i0 += U * stride) {
-    uint4 u[U], q[U];
+    V8 u[U], q[U];
     float g[U];
 #pragma unroll
     for (int j = 0; j < U; ++j) {
       const int64_t i = i0 + j * stride;
       if (i < total) {
-        u[j] = *reinterpret_cast<const uint4*>(a + i * 8);
+        u[j] = load8<T>(a + i * 8);
         g[j] = dl[i / cvec];
-        if (accumulate) q[j] = *reinterpret_cast<const uint4*>(dA + i * 8);
+        if (accumulate) q[j] = load8<T>(dA + i * 8);
       }
     }
 #pragma unroll
     for (int j = 0; j < U; ++j) {
       const int64_t i = i0 + j * stride;
       if (i >= total) break;
-      const uint32_t uu[4] = {u[j].x, u[j].y, u[j].z, u[j].w};
-      float o[8];
+      V8 o;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = unpack_bf16x2(uu[k]);
-        acc[2 * k] = fmaf(g[j], f.x, acc[2 * k]);
-        acc[2 * k + 1] = fmaf(g[j], f.y, acc[2 * k + 1]);
+      for (int k = 0; k < 8; ++k) {
+        acc[k] = fmaf(g[j], u[j].f[k], acc[k]);
+        o.f[k] = g[j] * wv[k];
+        if (accumulate) o.f[k] += q[j].f[k];
       }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = g[j] * wv[k];
-      if (accumulate) {
-        const uint32_t qq[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 f = unpack_bf16x2(qq[k]);
-          o[2 * k] += f.x;
-          o[2 * k + 1] += f.y;
-        }
-      }
-      uint4 r;
-      r.x = pack_bf16x2(o[0], o[1]); r.y = pack_bf16x2(o[2], o[3]); r.z = pack_bf16x2(o[4], o[5]); r.w = pack_bf16x2(o[6], o[7]);
-      *reinterpret_cast<uint4*>(dA + i * 8) = r;
+      store8<T>(dA + i * 8, o);
       if (v == 0) accb += g[j];
     }
   }
@@ -128,7 +112,8 @@ __global__ void dshead_compose_kernel(const float* __restrict__ wt, const float*
 }
 
 // logits[n, k*h+i, k*w+j] = sum_ci a[n,h,w,ci]*wc[ci][q] + bc ; block = 256 threads = (256/kk pixels) x kk outputs
-__global__ void __launch_bounds__(256) dshead_fwd_kernel(const __nv_bfloat16* __restrict__ a, int N, int H, int W,
+template <typename T>
+__global__ void __launch_bounds__(256) dshead_fwd_kernel(const T* __restrict__ a, int N, int H, int W,
                                                          int Cp, int C, int k, const float* __restrict__ wc,
                                                          const float* __restrict__ bc, float* __restrict__ logits) {
   extern __shared__ float sm[];
@@ -145,7 +130,7 @@ __global__ void __launch_bounds__(256) dshead_fwd_kernel(const __nv_bfloat16* __
     __syncthreads();
     for (int i = threadIdx.x; i < PB * C; i += 256) {
       const int64_t pix = p0 + i / C;
-      s_a[i] = pix < npix ? __bfloat162float(a[pix * Cp + (i % C)]) : 0.f;
+      s_a[i] = pix < npix ? ld1<T>(a + pix * Cp + (i % C)) : 0.f;
     }
     __syncthreads();
     const int64_t pix = p0 + pl;
@@ -161,10 +146,11 @@ __global__ void __launch_bounds__(256) dshead_fwd_kernel(const __nv_bfloat16* __
   }
 }
 
-__global__ void __launch_bounds__(256) dshead_bwd_kernel(const __nv_bfloat16* __restrict__ a,
+template <typename T>
+__global__ void __launch_bounds__(256) dshead_bwd_kernel(const T* __restrict__ a,
                                                          const float* __restrict__ dl, int N, int H, int W, int Cp,
                                                          int C, int k, const float* __restrict__ wc,
-                                                         __nv_bfloat16* __restrict__ dA, int accumulate,
+                                                         T* __restrict__ dA, int accumulate,
                                                          float* __restrict__ dwc, float* __restrict__ dbc) {
   extern __shared__ float sm[];
   const int kk = k * k;
@@ -186,7 +172,7 @@ __global__ void __launch_bounds__(256) dshead_bwd_kernel(const __nv_bfloat16* __
     __syncthreads();
     for (int i = threadIdx.x; i < PB * C; i += 256) {
       const int64_t pix = p0 + i / C;
-      s_a[i] = pix < npix ? __bfloat162float(a[pix * Cp + (i % C)]) : 0.f;
+      s_a[i] = pix < npix ? ld1<T>(a + pix * Cp + (i % C)) : 0.f;
     }
     {
       const int pl = threadIdx.x / kk;
@@ -225,9 +211,9 @@ __global__ void __launch_bounds__(256) dshead_bwd_kernel(const __nv_bfloat16* __
           const float* gr = s_dl + pl * kk;
           for (int qq = 0; qq < kk; ++qq) s = fmaf(gr[qq], wr[qq], s);
         }
-        __nv_bfloat16* d = dA + pix * Cp + ci;
-        if (accumulate) s += __bfloat162float(*d);
-        *d = __float2bfloat16(s);
+        T* d = dA + pix * Cp + ci;
+        if (accumulate) s += ld1<T>(d);
+        st1<T>(d, s);
       }
     }
   }
@@ -272,23 +258,19 @@ __global__ void dshead_decompose_kernel(const float* __restrict__ dwc, const flo
 
 // ------------------------------------------------------------------------------------------------ GAP + FC head
 // gap[n][c] = mean over the plane.  grid (N, ceil(Cp / 64)): 8 channel vectors (16 B each) x 32 pixel lanes per block.
-__global__ void __launch_bounds__(256) gap_kernel(const __nv_bfloat16* __restrict__ a, int HW, int Cp, int F,
+template <typename T>
+__global__ void __launch_bounds__(256) gap_kernel(const T* __restrict__ a, int HW, int Cp, int F,
                                                   float* __restrict__ gap) {
   __shared__ float s_red[32][65];
   const int n = blockIdx.x, vec = threadIdx.x & 7, pl = threadIdx.x >> 3;
   const int c0 = blockIdx.y * 64 + vec * 8;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (c0 < Cp) {
-    const __nv_bfloat16* src = a + static_cast<int64_t>(n) * HW * Cp + c0;
+    const T* src = a + static_cast<int64_t>(n) * HW * Cp + c0;
     for (int p = pl; p < HW; p += 32) {
-      const uint4 u = *reinterpret_cast<const uint4*>(src + static_cast<int64_t>(p) * Cp);
-      const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+      const V8 u = load8<T>(src + static_cast<int64_t>(p) * Cp);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = unpack_bf16x2(uu[k]);
-        acc[2 * k] += f.x;
-        acc[2 * k + 1] += f.y;
-      }
+      for (int k = 0; k < 8; ++k) acc[k] += u.f[k];
     }
   }
 #pragma unroll
@@ -379,29 +361,22 @@ __global__ void __launch_bounds__(256) gap_fc_bwd_sample_kernel(const float* __r
 }
 
 // dA[n][p][c] (+)= dgap[n][c] for every pixel: one 16-byte vector per thread, whole grid
+template <typename T>
 __global__ void __launch_bounds__(256) gap_bcast_kernel(const float* __restrict__ dgap, int HW, int Cp, int F,
-                                                        __nv_bfloat16* __restrict__ dA, int accumulate, int64_t total) {
+                                                        T* __restrict__ dA, int accumulate, int64_t total) {
   const int cvec = Cp / 8;
   for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
     const int v = static_cast<int>(i % cvec);
     const int64_t n = i / (static_cast<int64_t>(cvec) * HW);
-    float o[8];
+    V8 o;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = (v * 8 + k) < F ? dgap[n * F + v * 8 + k] : 0.f;
-    uint4* dst = reinterpret_cast<uint4*>(dA + i * 8);
+    for (int k = 0; k < 8; ++k) o.f[k] = (v * 8 + k) < F ? dgap[n * F + v * 8 + k] : 0.f;
     if (accumulate) {
-      const uint4 q = *dst;
-      const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+      const V8 q = load8<T>(dA + i * 8);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = unpack_bf16x2(qq[k]);
-        o[2 * k] += f.x;
-        o[2 * k + 1] += f.y;
-      }
+      for (int k = 0; k < 8; ++k) o.f[k] += q.f[k];
     }
-    uint4 r;
-    r.x = pack_bf16x2(o[0], o[1]); r.y = pack_bf16x2(o[2], o[3]); r.z = pack_bf16x2(o[4], o[5]); r.w = pack_bf16x2(o[6], o[7]);
-    *dst = r;
+    store8<T>(dA + i * 8, o);
   }
 }
 // dw1[j][c] += sum_n dh[n][j]*gap[n][c] ; db1[j] += sum_n dh[n][j]
@@ -424,7 +399,8 @@ __global__ void __launch_bounds__(256) fc1_wgrad_kernel(const float* __restrict_
 
 // ------------------------------------------------------------------------------------------------ flatten + FC head
 // hidden_pre[n][j] += sum_{k in slice} w1[j][k]*a[n][k]   with k = c*HW + hw (NCHW flatten order of the reference)
-__global__ void __launch_bounds__(256) flat_fc1_kernel(const __nv_bfloat16* __restrict__ a, int N, int HW, int Cp,
+template <typename T>
+__global__ void __launch_bounds__(256) flat_fc1_kernel(const T* __restrict__ a, int N, int HW, int Cp,
                                                        int C, const float* __restrict__ w1, int Hd, int slices,
                                                        float* __restrict__ hidden_pre) {
   const int j = blockIdx.x, sl = blockIdx.y;
@@ -438,7 +414,7 @@ __global__ void __launch_bounds__(256) flat_fc1_kernel(const __nv_bfloat16* __re
       const int c = static_cast<int>(k / HW), hw = static_cast<int>(k % HW);
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        if (n0 + i < N) acc[i] = fmaf(wv, __bfloat162float(a[(static_cast<int64_t>(n0 + i) * HW + hw) * Cp + c]), acc[i]);
+        if (n0 + i < N) acc[i] = fmaf(wv, ld1<T>(a + (static_cast<int64_t>(n0 + i) * HW + hw) * Cp + c), acc[i]);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -502,10 +478,11 @@ __global__ void flat_fc_bwd_small_kernel(const float* __restrict__ dl, int N, in
   }
 }
 // one thread per flattened column k: single pass over w1 (read) and dw1 (write)
-__global__ void __launch_bounds__(256) flat_fc_bwd_big_kernel(const __nv_bfloat16* __restrict__ a, int N, int HW,
+template <typename T>
+__global__ void __launch_bounds__(256) flat_fc_bwd_big_kernel(const T* __restrict__ a, int N, int HW,
                                                               int Cp, int C, const float* __restrict__ w1, int Hd,
                                                               const float* __restrict__ dh,
-                                                              __nv_bfloat16* __restrict__ dA, int accumulate,
+                                                              T* __restrict__ dA, int accumulate,
                                                               float* __restrict__ dw1) {
   extern __shared__ float s_dh[];  // [N][Hd]
   for (int i = threadIdx.x; i < N * Hd; i += 256) s_dh[i] = dh[i];
@@ -518,7 +495,7 @@ __global__ void __launch_bounds__(256) flat_fc_bwd_big_kernel(const __nv_bfloat1
     float av[8], da[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      av[i] = (n0 + i < N) ? __bfloat162float(a[(static_cast<int64_t>(n0 + i) * HW + hw) * Cp + c]) : 0.f;
+      av[i] = (n0 + i < N) ? ld1<T>(a + (static_cast<int64_t>(n0 + i) * HW + hw) * Cp + c) : 0.f;
       da[i] = 0.f;
     }
     for (int j = 0; j < Hd; ++j) {
@@ -537,10 +514,10 @@ __global__ void __launch_bounds__(256) flat_fc_bwd_big_kernel(const __nv_bfloat1
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if (n0 + i < N) {
-        __nv_bfloat16* d = dA + (static_cast<int64_t>(n0 + i) * HW + hw) * Cp + c;
+        T* d = dA + (static_cast<int64_t>(n0 + i) * HW + hw) * Cp + c;
         float o = da[i];
-        if (accumulate) o += __bfloat162float(*d);
-        *d = __float2bfloat16(o);
+        if (accumulate) o += ld1<T>(d);
+        st1<T>(d, o);
       }
     }
   }
@@ -583,15 +560,15 @@ __global__ void __launch_bounds__(128) softmax_rows_bwd_kernel(const float* __re
 
 using namespace mtbc;
 #define ST(s) static_cast<cudaStream_t>(s)
-#define BF(p) static_cast<__nv_bfloat16*>(p)
-#define CBF(p) static_cast<const __nv_bfloat16*>(p)
+#define TP(p) static_cast<T*>(p)
+#define CTP(p) static_cast<const T*>(p)
 
 extern "C" {
 
 int mtbc_head1x1_fwd(const void* a, int64_t npix, int32_t Cp, int32_t C, const float* w, const float* b,
                      float* logits, void* stream) {
   int g = cdiv(npix, 256); if (g > 148 * 8) g = 148 * 8;
-  head1x1_fwd_kernel<<<g, 256, Cp * sizeof(float), ST(stream)>>>(CBF(a), npix, Cp, C, w, b, logits);
+  MTBC_DISPATCH_ACT((head1x1_fwd_kernel<T><<<g, 256, Cp * sizeof(float), ST(stream)>>>(CTP(a), npix, Cp, C, w, b, logits)));
   return check_launch("head1x1_fwd");
 }
 int mtbc_head1x1_bwd(const void* a, const float* dlogits, int64_t npix, int32_t Cp, int32_t C, const float* w,
@@ -600,8 +577,7 @@ int mtbc_head1x1_bwd(const void* a, const float* dlogits, int64_t npix, int32_t 
   if (Cp % 8 != 0 || cvec > 256) return set_error(MTBC_ERR_INVALID, "head1x1_bwd: Cp %% 8 != 0 or Cp > 2048");
   const int bd = (256 / cvec) * cvec;   // block size multiple of the channel-group count: a thread's group is invariant
   int g = cdiv(npix * cvec, bd * 8); if (g > 148 * 8) g = 148 * 8; if (g < 1) g = 1;
-  head1x1_bwd_kernel<<<g, bd, 0, ST(stream)>>>(CBF(a), dlogits, npix, Cp, C, w, BF(dA),
-                                                                      accumulate, dw, db);
+  MTBC_DISPATCH_ACT((head1x1_bwd_kernel<T><<<g, bd, 0, ST(stream)>>>(CTP(a), dlogits, npix, Cp, C, w, TP(dA), accumulate, dw, db)));
   return check_launch("head1x1_bwd");
 }
 int mtbc_dshead_compose(const float* wt, const float* bt, const float* w1, const float* b1, int32_t C, int32_t k,
@@ -618,8 +594,11 @@ int mtbc_dshead_fwd(const void* a, int32_t N, int32_t H, int32_t W, int32_t Cp, 
   const int64_t npix = static_cast<int64_t>(N) * H * W;
   int g = cdiv(npix, PB); if (g > 148 * 8) g = 148 * 8;
   const size_t smem = (static_cast<size_t>(C) * kk + static_cast<size_t>(PB) * C) * sizeof(float);
-  { static bool done = false; if (smem > 48 * 1024 && !done) { cudaFuncSetAttribute(dshead_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); done = true; } }
-  dshead_fwd_kernel<<<g, 256, smem, ST(stream)>>>(CBF(a), N, H, W, Cp, C, k, wc, bc, logits);
+  if (smem > 48 * 1024) {
+    cudaFuncSetAttribute(dshead_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(dshead_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  }
+  MTBC_DISPATCH_ACT((dshead_fwd_kernel<T><<<g, 256, smem, ST(stream)>>>(CTP(a), N, H, W, Cp, C, k, wc, bc, logits)));
   return check_launch("dshead_fwd");
 }
 int mtbc_dshead_bwd(const void* a, const float* dlogits, int32_t N, int32_t H, int32_t W, int32_t Cp, int32_t C,
@@ -631,8 +610,11 @@ int mtbc_dshead_bwd(const void* a, const float* dlogits, int32_t N, int32_t H, i
   const int64_t npix = static_cast<int64_t>(N) * H * W;
   int g = cdiv(npix, PB * 8); if (g > 148 * 2) g = 148 * 2; if (g < 1) g = 1;
   const size_t smem = (static_cast<size_t>(C) * kk + static_cast<size_t>(PB) * C + static_cast<size_t>(PB) * kk) * sizeof(float);
-  { static bool done = false; if (smem > 48 * 1024 && !done) { cudaFuncSetAttribute(dshead_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); done = true; } }
-  dshead_bwd_kernel<<<g, 256, smem, ST(stream)>>>(CBF(a), dlogits, N, H, W, Cp, C, k, wc, BF(dA), accumulate, dwc, dbc);
+  if (smem > 48 * 1024) {
+    cudaFuncSetAttribute(dshead_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(dshead_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  }
+  MTBC_DISPATCH_ACT((dshead_bwd_kernel<T><<<g, 256, smem, ST(stream)>>>(CTP(a), dlogits, N, H, W, Cp, C, k, wc, TP(dA), accumulate, dwc, dbc)));
   return check_launch("dshead_bwd");
 }
 int mtbc_dshead_decompose(const float* dwc, const float* dbc, const float* wt, const float* bt, const float* w1,
@@ -648,7 +630,7 @@ int mtbc_gap_fc_fwd(const void* a, int32_t N, int32_t HW, int32_t Cp, int32_t F,
                     int32_t Hd, const float* w2, const float* b2, int32_t K, float* gap, float* hidden, float* logits,
                     void* stream) {
   if (Cp % 8 != 0 || F > Cp) return set_error(MTBC_ERR_INVALID, "gap_fc_fwd: Cp %% 8 != 0 or F > Cp");
-  gap_kernel<<<dim3(N, cdiv(Cp, 64)), 256, 0, ST(stream)>>>(CBF(a), HW, Cp, F, gap);
+  MTBC_DISPATCH_ACT((gap_kernel<T><<<dim3(N, cdiv(Cp, 64)), 256, 0, ST(stream)>>>(CTP(a), HW, Cp, F, gap)));
   int rc = check_launch("gap");
   if (rc) return rc;
   if (F % 4 != 0) return set_error(MTBC_ERR_INVALID, "gap_fc_fwd: F %% 4 != 0");
@@ -672,7 +654,7 @@ int mtbc_gap_fc_bwd(const float* dlogits, int32_t N, int32_t HW, int32_t Cp, int
   if (rc) return rc;
   const int64_t total = static_cast<int64_t>(N) * HW * (Cp / 8);
   int gb = cdiv(total, 256); if (gb > 148 * 8) gb = 148 * 8;
-  gap_bcast_kernel<<<gb, 256, 0, ST(stream)>>>(dgap, HW, Cp, F, BF(dA), accumulate, total);
+  MTBC_DISPATCH_ACT((gap_bcast_kernel<T><<<gb, 256, 0, ST(stream)>>>(dgap, HW, Cp, F, TP(dA), accumulate, total)));
   return check_launch("gap_bcast");
 }
 
@@ -682,7 +664,7 @@ int mtbc_flat_fc_fwd(const void* a, int32_t N, int32_t HW, int32_t Cp, int32_t C
   cudaError_t e = cudaMemsetAsync(hidden, 0, static_cast<size_t>(N) * Hd * sizeof(float), ST(stream));
   if (e != cudaSuccess) return set_error(MTBC_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
   const int slices = 4;
-  flat_fc1_kernel<<<dim3(Hd, slices), 256, 0, ST(stream)>>>(CBF(a), N, HW, Cp, C, w1, Hd, slices, hidden);
+  MTBC_DISPATCH_ACT((flat_fc1_kernel<T><<<dim3(Hd, slices), 256, 0, ST(stream)>>>(CTP(a), N, HW, Cp, C, w1, Hd, slices, hidden)));
   int rc = check_launch("flat_fc1");
   if (rc) return rc;
   flat_fc2_kernel<<<N, 128, Hd * sizeof(float), ST(stream)>>>(hidden, b1, N, Hd, w2, b2, K, logits);
@@ -697,9 +679,12 @@ int mtbc_flat_fc_bwd(const void* a, const float* dlogits, int32_t N, int32_t HW,
   if (rc) return rc;
   const int64_t F = static_cast<int64_t>(C) * HW;
   const size_t smem = static_cast<size_t>(N) * Hd * sizeof(float);
-  { static bool done = false; if (smem > 48 * 1024 && !done) { cudaFuncSetAttribute(flat_fc_bwd_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); done = true; } }
-  flat_fc_bwd_big_kernel<<<cdiv(F, 256), 256, smem, ST(stream)>>>(CBF(a), N, HW, Cp, C, w1, Hd, scratch, BF(dA),
-                                                                 accumulate, dw1);
+  if (smem > 48 * 1024) {
+    cudaFuncSetAttribute(flat_fc_bwd_big_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(flat_fc_bwd_big_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  }
+  MTBC_DISPATCH_ACT((flat_fc_bwd_big_kernel<T><<<cdiv(F, 256), 256, smem, ST(stream)>>>(CTP(a), N, HW, Cp, C, w1, Hd, scratch, TP(dA),
+                                                                                         accumulate, dw1)));
   return check_launch("flat_fc_bwd_big");
 }
 

@@ -11,6 +11,11 @@ int set_error(int code, const char* fmt, ...);
 // cudaGetLastError() after a launch -> MTBC status (never synchronises).
 int check_launch(const char* what);
 
+// Per-thread execution mode of the element-type generic entry points (mtbc_set_mode): which dtype the NHWC activation
+// pointers they receive hold, and whether reductions must be order independent.
+enum { MODE_ACT_FP32 = 1, MODE_DETERMINISTIC = 2 };
+int current_mode();
+
 struct OpBase {
   virtual ~OpBase() {}
   virtual int launch(cudaStream_t st) = 0;
@@ -26,8 +31,8 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out);
 int wgrad_halo_try_create(const mtbc_wgrad_desc* d, OpBase** out);
 int wgrad_halo_multi_create(const mtbc_wgrad_multi_desc* d, OpBase** out);
 // tensor-map encoders (conv_gemm.cu): bf16 NHWC view with box (kc, bw, bh, bn); packed weights with box (kc, BN, 1)
-int encode_act(CUtensorMap* m, const mtbc_act_view& v, int kc, int bw, int bh, int bn);
-int encode_w(CUtensorMap* m, const void* w, int ktot, int nrows, int ntaps, int kc, int BN);
+int encode_act(CUtensorMap* m, const mtbc_act_view& v, int kc, int bw, int bh, int bn, int fp32 = 0);
+int encode_w(CUtensorMap* m, const void* w, int ktot, int nrows, int ntaps, int kc, int BN, int fp32 = 0);
 
 // bulk-copy pipelined streaming kernels (stream_pipe.cu) for large tensors
 bool pipe_eligible(int64_t N, int64_t HW, int Cp);

@@ -2,6 +2,7 @@
 // utilities.  All memory bound / tiny.
 #include "ptx.cuh"
 #include "internal.h"
+#include "act_io.cuh"
 #include <vector>
 
 namespace mtbc {
@@ -86,18 +87,36 @@ struct ParamJobDev {
   void* dst1;
 };
 
+// Packed-operand element types: bf16 (product path), or fp32 holding TF32 values (parity mode): part 1 = the weight
+// rounded to nearest TF32 (cvt.rna), part 2 = the TF32 rounding of what that left over (second term of the 3xTF32 split).
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+template <typename WT>
+__device__ __forceinline__ void put_w(WT* p, float v, int part);
+template <>
+__device__ __forceinline__ void put_w<__nv_bfloat16>(__nv_bfloat16* p, float v, int) { *p = __float2bfloat16(v); }
+template <>
+__device__ __forceinline__ void put_w<float>(float* p, float v, int part) {
+  const float hi = tf32_rn(v);
+  *p = part == 2 ? tf32_rn(v - hi) : hi;
+}
+
 // 32 (co) x 32 (ci) x TAPS weight tile through shared memory.  TAPS is a compile-time constant (1 or 9 on this path)
 // so the index divisions become multiply-shifts: with run-time `taps` the two divisions per element made the 15 M
 // parameter pack an instruction-bound 134 us launch (0.9 TB/s).
-template <int TAPS>
+template <int TAPS, typename WT>
 __device__ __forceinline__ void pack_conv_tile(const ParamJobDev& j, int local, float (*s_tile)[32 * 9 + 1]) {
   const int Cout = j.i[0], Cin = j.i[1], c_begin = j.i[3], c_count = j.i[4];
   const int tiles_cl = (c_count + 31) >> 5;
   const int co0 = (local / tiles_cl) << 5, cl0 = (local % tiles_cl) << 5;
   constexpr int roww = 32 * TAPS;
   const float* w = static_cast<const float*>(j.src);
-  __nv_bfloat16* wf = static_cast<__nv_bfloat16*>(j.dst0);
-  __nv_bfloat16* wd = static_cast<__nv_bfloat16*>(j.dst1);
+  WT* wf = static_cast<WT*>(j.dst0);
+  WT* wd = static_cast<WT*>(j.dst1);
+  const int part = j.i[10];
   for (int idx = threadIdx.x; idx < 32 * roww; idx += 256) {
     const int r = idx / roww, off = idx - r * roww;
     const int co = co0 + r, cl = cl0 + off / TAPS;
@@ -110,12 +129,12 @@ __device__ __forceinline__ void pack_conv_tile(const ParamJobDev& j, int local, 
     if (wf) {   // lanes run over ci
       const int cl = cl0 + lo, co = co0 + mid;
       if (cl < c_count && co < Cout)
-        wf[(static_cast<int64_t>(tap) * j.i[5] + co) * j.i[6] + j.i[7] + cl] = __float2bfloat16(s_tile[mid][lo * TAPS + tap]);
+        put_w<WT>(wf + (static_cast<int64_t>(tap) * j.i[5] + co) * j.i[6] + j.i[7] + cl, s_tile[mid][lo * TAPS + tap], part);
     }
     if (wd) {   // lanes run over co
       const int co = co0 + lo, cl = cl0 + mid;
       if (cl < c_count && co < Cout)
-        wd[(static_cast<int64_t>(TAPS - 1 - tap) * j.i[8] + cl) * j.i[9] + co] = __float2bfloat16(s_tile[lo][mid * TAPS + tap]);
+        put_w<WT>(wd + (static_cast<int64_t>(TAPS - 1 - tap) * j.i[8] + cl) * j.i[9] + co, s_tile[lo][mid * TAPS + tap], part);
     }
   }
 }
@@ -163,25 +182,37 @@ __global__ void __launch_bounds__(256) param_jobs_kernel(const ParamJobDev* __re
     // floats, wf is written in runs of 32 ci (64 B) and wd in runs of 32 co (64 B).  (Element-wise, the wd writes were
     // 2-byte scatters with a stride of a whole weight row: 0.27 ms per step for 15 M parameters.)
     const int local = blockIdx.x - chunk_first[blockIdx.x];
-    switch (j.i[2]) {
-      case 1: pack_conv_tile<1>(j, local, s_tile); break;
-      case 2: pack_conv_tile<4>(j, local, s_tile); break;
-      default: pack_conv_tile<9>(j, local, s_tile); break;
+    if (j.i[10] == 0) {
+      switch (j.i[2]) {
+        case 1: pack_conv_tile<1, __nv_bfloat16>(j, local, s_tile); break;
+        case 2: pack_conv_tile<4, __nv_bfloat16>(j, local, s_tile); break;
+        default: pack_conv_tile<9, __nv_bfloat16>(j, local, s_tile); break;
+      }
+    } else {   // fp32 operands holding TF32 values (i[10] = 1: rounded weight, 2: rounded remainder)
+      switch (j.i[2]) {
+        case 1: pack_conv_tile<1, float>(j, local, s_tile); break;
+        case 2: pack_conv_tile<4, float>(j, local, s_tile); break;
+        default: pack_conv_tile<9, float>(j, local, s_tile); break;
+      }
     }
   } else if (j.kind == MTBC_JOB_PACK_CONVT) {
     // i: Cin, Cout, k, cp, wf_ld, wd_rows, wd_ld ; element order = parameter order (ci, co, q)
     const int Cout = j.i[1], kk = j.i[2] * j.i[2], cp = j.i[3];
     const int64_t total = static_cast<int64_t>(j.i[0]) * Cout * kk;
     const float* w = static_cast<const float*>(j.src);
-    __nv_bfloat16* wf = static_cast<__nv_bfloat16*>(j.dst0);
-    __nv_bfloat16* wd = static_cast<__nv_bfloat16*>(j.dst1);
+    const int part = j.i[10];
     for (int64_t e = begin + threadIdx.x; e < begin + kChunk && e < total; e += 256) {
       const int q = static_cast<int>(e % kk);
       const int co = static_cast<int>((e / kk) % Cout);
       const int ci = static_cast<int>(e / (static_cast<int64_t>(kk) * Cout));
-      const __nv_bfloat16 b = __float2bfloat16(w[e]);
-      if (wf) wf[(static_cast<int64_t>(q) * cp + co) * j.i[4] + ci] = b;
-      if (wd) wd[(static_cast<int64_t>(q) * j.i[5] + ci) * j.i[6] + co] = b;
+      const int64_t of = (static_cast<int64_t>(q) * cp + co) * j.i[4] + ci, od = (static_cast<int64_t>(q) * j.i[5] + ci) * j.i[6] + co;
+      if (part == 0) {
+        if (j.dst0) put_w<__nv_bfloat16>(static_cast<__nv_bfloat16*>(j.dst0) + of, w[e], 0);
+        if (j.dst1) put_w<__nv_bfloat16>(static_cast<__nv_bfloat16*>(j.dst1) + od, w[e], 0);
+      } else {
+        if (j.dst0) put_w<float>(static_cast<float*>(j.dst0) + of, w[e], part);
+        if (j.dst1) put_w<float>(static_cast<float*>(j.dst1) + od, w[e], part);
+      }
     }
   } else if (j.kind == MTBC_JOB_UNPACK_CONV) {
     // i: rows, ld, k0, Cout, Cin, ksz, c_begin, c_count, add.  Same 32 x 32 x taps tile, the other way round.
@@ -349,10 +380,10 @@ __global__ void conv_first_shift_finish_kernel(const float* __restrict__ x, int 
 // stay in registers over the PPT pixels and are combined once (16 shuffles per 16 columns and quantity), not per pixel:
 // at one pixel per thread the 64 shuffles + shared-memory atomics per pixel, not the 100 MB store, bounded the kernel
 // (105 us at 32 x 256 x 256 x 24 against a 26 us write floor).  NCH = 16-column chunks (Cs / 16) when PPT > 1.
-template <int CIN, int NCH = 0, int PPT = 1>
+template <typename T, int CIN, int NCH = 0, int PPT = 1>
 __global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __restrict__ x, int N, int H, int W,
                                                              const float* __restrict__ w, const float* __restrict__ bias,
-                                                             int Cout, __nv_bfloat16* __restrict__ y, int Cp,
+                                                             int Cout, T* __restrict__ y, int Cp,
                                                              float* __restrict__ stat_sum, float* __restrict__ stat_sq,
                                                              const float* __restrict__ xs) {
   extern __shared__ __align__(16) float sm[];
@@ -407,7 +438,7 @@ __global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __rest
           xin[ci * 9 + r * 3 + s] =
               (hh >= 0 && hh < H && wc >= 0 && wc < W) ? __ldg(x + (static_cast<int64_t>(n) * CIN + ci) * HW + hh * W + wc) : 0.f;
         }
-    __nv_bfloat16* dst = y + pix * Cp;
+    T* dst = y + pix * Cp;
     auto chunk = [&](int c0, float (&v)[16]) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -433,7 +464,7 @@ __global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __rest
 #pragma unroll
         for (int i = 0; i < 16; ++i) { ps[c * 16 + i] += v[i]; pq[c * 16 + i] = fmaf(v[i], v[i], pq[c * 16 + i]); }
         const int left = Cp - c * 16;
-        emit_bf16x16_n(dst + c * 16, v, false, left >= 16 ? 16 : 8, wide);
+        emit16_n<T>(dst + c * 16, v, false, left >= 16 ? 16 : 8, wide);
       }
     } else {
       for (int c0 = 0; c0 < Cs; c0 += 16) {
@@ -452,7 +483,7 @@ __global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __rest
           }
         }
         const int left = Cp - c0;
-        emit_bf16x16_n(dst + c0, v, false, left >= 16 ? 16 : 8, wide);
+        emit16_n<T>(dst + c0, v, false, left >= 16 ? 16 : 8, wide);
       }
     }
   }
@@ -645,6 +676,7 @@ int mtbc_conv_first_fwd(const float* x, int32_t N, int32_t Cin, int32_t H, int32
     cudaError_t e = cudaMemsetAsync(center_scratch, 0, static_cast<size_t>(N) * Cin * 9 * sizeof(float), st0);
     if (e != cudaSuccess) return set_error(MTBC_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
     int slices = static_cast<int>(HW / 4096); if (slices < 1) slices = 1; if (slices > 32) slices = 32;
+    if (current_mode() & MODE_DETERMINISTIC) slices = 1;   // one block per plane: no cross-block float atomics
     conv_first_shift_sums_kernel<<<dim3(N * Cin, slices), 256, 0, st0>>>(x, H, W, center_scratch);
     int rc = check_launch("conv_first_shift_sums");
     if (rc) return rc;
@@ -655,20 +687,30 @@ int mtbc_conv_first_fwd(const float* x, int32_t N, int32_t Cin, int32_t H, int32
   const int Cs = (Cp + 15) & ~15;
   const int smem = (Cs * Cin * 9 + 3 * Cs) * sizeof(float);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = static_cast<int>(N * HW / 128);
+  if (current_mode() & MODE_ACT_FP32) {   // TF32 parity mode: fp32 output tensor, generic kernel (speed is not its point)
+    float* yf = static_cast<float*>(y);
+    switch (Cin) {
+      case 1: conv_first_fwd_kernel<float, 1><<<grid, 128, smem, st>>>(x, N, H, W, w, bias, Cout, yf, Cp, stat_sum, stat_sq, center_scratch); break;
+      case 2: conv_first_fwd_kernel<float, 2><<<grid, 128, smem, st>>>(x, N, H, W, w, bias, Cout, yf, Cp, stat_sum, stat_sq, center_scratch); break;
+      case 3: conv_first_fwd_kernel<float, 3><<<grid, 128, smem, st>>>(x, N, H, W, w, bias, Cout, yf, Cp, stat_sum, stat_sq, center_scratch); break;
+      default: conv_first_fwd_kernel<float, 4><<<grid, 128, smem, st>>>(x, N, H, W, w, bias, Cout, yf, Cp, stat_sum, stat_sq, center_scratch); break;
+    }
+    return check_launch("conv_first_fwd");
+  }
   __nv_bfloat16* yb = static_cast<__nv_bfloat16*>(y);
   // single-channel images on planes of whole 1024-pixel blocks (every benchmark shape): 8 pixels per thread
   if (Cin == 1 && Cs <= 32 && HW % 1024 == 0 && !getenv("MTBC_FIRST_PPT1")) {
     const int g8 = static_cast<int>(N * HW / 1024);
-    if (Cs == 16) conv_first_fwd_kernel<1, 1, 8><<<g8, 128, smem, st>>>(x, N, H, W, w, bias, Cout, yb, Cp, stat_sum, stat_sq, center_scratch);
-    else conv_first_fwd_kernel<1, 2, 8><<<g8, 128, smem, st>>>(x, N, H, W, w, bias, Cout, yb, Cp, stat_sum, stat_sq, center_scratch);
+    if (Cs == 16) conv_first_fwd_kernel<__nv_bfloat16, 1, 1, 8><<<g8, 128, smem, st>>>(x, N, H, W, w, bias, Cout, yb, Cp, stat_sum, stat_sq, center_scratch);
+    else conv_first_fwd_kernel<__nv_bfloat16, 1, 2, 8><<<g8, 128, smem, st>>>(x, N, H, W, w, bias, Cout, yb, Cp, stat_sum, stat_sq, center_scratch);
     return check_launch("conv_first_fwd");
   }
-  const int grid = static_cast<int>(N * HW / 128);
   switch (Cin) {
-    case 1: conv_first_fwd_kernel<1><<<grid, 128, smem, st>>>(x, N, H, W, w, bias, Cout, yb, Cp, stat_sum, stat_sq, center_scratch); break;
-    case 2: conv_first_fwd_kernel<2><<<grid, 128, smem, st>>>(x, N, H, W, w, bias, Cout, yb, Cp, stat_sum, stat_sq, center_scratch); break;
-    case 3: conv_first_fwd_kernel<3><<<grid, 128, smem, st>>>(x, N, H, W, w, bias, Cout, yb, Cp, stat_sum, stat_sq, center_scratch); break;
-    default: conv_first_fwd_kernel<4><<<grid, 128, smem, st>>>(x, N, H, W, w, bias, Cout, yb, Cp, stat_sum, stat_sq, center_scratch); break;
+    case 1: conv_first_fwd_kernel<__nv_bfloat16, 1><<<grid, 128, smem, st>>>(x, N, H, W, w, bias, Cout, yb, Cp, stat_sum, stat_sq, center_scratch); break;
+    case 2: conv_first_fwd_kernel<__nv_bfloat16, 2><<<grid, 128, smem, st>>>(x, N, H, W, w, bias, Cout, yb, Cp, stat_sum, stat_sq, center_scratch); break;
+    case 3: conv_first_fwd_kernel<__nv_bfloat16, 3><<<grid, 128, smem, st>>>(x, N, H, W, w, bias, Cout, yb, Cp, stat_sum, stat_sq, center_scratch); break;
+    default: conv_first_fwd_kernel<__nv_bfloat16, 4><<<grid, 128, smem, st>>>(x, N, H, W, w, bias, Cout, yb, Cp, stat_sum, stat_sq, center_scratch); break;
   }
   return check_launch("conv_first_fwd");
 }

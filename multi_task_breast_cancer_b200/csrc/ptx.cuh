@@ -133,6 +133,18 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, u
       ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::tf32: fp32 operands in shared memory, the tensor core reads the TF32 part (sign, 8 exponent, 10 mantissa bits).
+__device__ __forceinline__ void umma_tf32_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                               uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
   return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
 }
@@ -213,6 +225,17 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t M, uint32_
   d |= 1u << 10;
   d |= (a_mn_major & 1u) << 15;
   d |= (b_mn_major & 1u) << 16;
+  d |= ((N >> 3) & 0x3Fu) << 17;
+  d |= ((M >> 4) & 0x1Fu) << 24;
+  return d;
+}
+
+// Instruction descriptor for kind::tf32 (a/b format 2 = TF32), fp32 accumulate, M = 128, both operands K-major.
+__host__ __device__ __forceinline__ uint32_t umma_idesc_tf32(uint32_t M, uint32_t N) {
+  uint32_t d = 0;
+  d |= 1u << 4;
+  d |= 2u << 7;
+  d |= 2u << 10;
   d |= ((N >> 3) & 0x3Fu) << 17;
   d |= ((M >> 4) & 0x1Fu) << 24;
   return d;

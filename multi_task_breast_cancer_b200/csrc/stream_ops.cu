@@ -4,25 +4,10 @@
 // over its grid-stride loop so per-channel constants live in registers.
 #include "ptx.cuh"
 #include "internal.h"
+#include "act_io.cuh"
+#include <string>
 
 namespace mtbc {
-
-struct V8 {
-  float f[8];
-};
-__device__ __forceinline__ V8 load8(const __nv_bfloat16* p) {
-  const uint4 u = *reinterpret_cast<const uint4*>(p);
-  V8 r;
-  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-  r.f[0] = a.x; r.f[1] = a.y; r.f[2] = b.x; r.f[3] = b.y; r.f[4] = c.x; r.f[5] = c.y; r.f[6] = d.x; r.f[7] = d.y;
-  return r;
-}
-__device__ __forceinline__ void store8(__nv_bfloat16* p, const V8& v) {
-  uint4 u;
-  u.x = pack_bf16x2(v.f[0], v.f[1]); u.y = pack_bf16x2(v.f[2], v.f[3]);
-  u.z = pack_bf16x2(v.f[4], v.f[5]); u.w = pack_bf16x2(v.f[6], v.f[7]);
-  *reinterpret_cast<uint4*>(p) = u;
-}
 
 static int gcd_i(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
 // grid.x such that (grid.x * block) % cvec == 0 (channel group invariant per thread) and ~target blocks overall.
@@ -37,7 +22,8 @@ static int pick_gx(int64_t work_items, int block, int cvec, int n_outer, int per
 }
 
 // ------------------------------------------------------------------------------------------------ statistics
-__global__ void __launch_bounds__(256) in_stats_kernel(const __nv_bfloat16* __restrict__ y, int64_t HW, int Cp,
+template <typename T>
+__global__ void __launch_bounds__(256) in_stats_kernel(const T* __restrict__ y, int64_t HW, int Cp,
                                                        float* __restrict__ ssum, float* __restrict__ ssq) {
   extern __shared__ float s_acc[];  // [2][Cp]
   const int n = blockIdx.y, cvec = Cp / 8;
@@ -47,9 +33,9 @@ __global__ void __launch_bounds__(256) in_stats_kernel(const __nv_bfloat16* __re
   const int64_t start = blockIdx.x * 256ll + threadIdx.x, stride = gridDim.x * 256ll;
   const int v = static_cast<int>(start % cvec);
   float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const __nv_bfloat16* base = y + static_cast<int64_t>(n) * HW * Cp;
+  const T* base = y + static_cast<int64_t>(n) * HW * Cp;
   for (int64_t i = start; i < total; i += stride) {
-    const V8 x = load8(base + i * 8);
+    const V8 x = load8<T>(base + i * 8);
 #pragma unroll
     for (int k = 0; k < 8; ++k) { a[k] += x.f[k]; q[k] = fmaf(x.f[k], x.f[k], q[k]); }
   }
@@ -62,6 +48,61 @@ __global__ void __launch_bounds__(256) in_stats_kernel(const __nv_bfloat16* __re
     atomicAdd(ssum + static_cast<int64_t>(n) * Cp + i, s_acc[i]);
     atomicAdd(ssq + static_cast<int64_t>(n) * Cp + i, s_acc[Cp + i]);
   }
+}
+
+
+// Order-independent variant (MODE_DETERMINISTIC): no floating-point atomics anywhere.  Every thread's partial is parked
+// in a [k][thread] table, one thread per channel adds its rows in a fixed order, the block's sums go to
+// partial[n][block][2][Cp], and the LAST block of a sample to arrive (integer ticket) adds the blocks' partials in block
+// order.  Which block is last varies from run to run; the order of the additions does not, so the statistics -- and with
+// them every bf16 rounding downstream -- are bit-identical across runs.  blockDim.x is a multiple of Cp / 8.
+template <typename T>
+__global__ void __launch_bounds__(256) in_stats_det_kernel(const T* __restrict__ y, int64_t HW, int Cp,
+                                                           float* __restrict__ partial, int* __restrict__ ticket,
+                                                           float* __restrict__ ssum, float* __restrict__ ssq) {
+  __shared__ float s_tab[16 * 256];
+  __shared__ int s_last;
+  const int n = blockIdx.y, cvec = Cp / 8, bd = blockDim.x;
+  const int64_t total = HW * cvec;
+  const int64_t start = static_cast<int64_t>(blockIdx.x) * bd + threadIdx.x, stride = static_cast<int64_t>(gridDim.x) * bd;
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const T* base = y + static_cast<int64_t>(n) * HW * Cp;
+  for (int64_t i = start; i < total; i += stride) {
+    const V8 x = load8<T>(base + i * 8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a[k] += x.f[k]; q[k] = fmaf(x.f[k], x.f[k], q[k]); }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { s_tab[k * 256 + threadIdx.x] = a[k]; s_tab[(8 + k) * 256 + threadIdx.x] = q[k]; }
+  __syncthreads();
+  float* mine = partial + (static_cast<int64_t>(n) * gridDim.x + blockIdx.x) * 2 * Cp;
+  for (int ch = threadIdx.x; ch < Cp; ch += bd) {   // thread t's channel group is t % cvec (bd % cvec == 0)
+    float s0 = 0.f, s1 = 0.f;
+    for (int r = ch >> 3; r < bd; r += cvec) { s0 += s_tab[(ch & 7) * 256 + r]; s1 += s_tab[(8 + (ch & 7)) * 256 + r]; }
+    mine[ch] = s0;
+    mine[Cp + ch] = s1;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket + n, 1) == static_cast<int>(gridDim.x) - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* all = partial + static_cast<int64_t>(n) * gridDim.x * 2 * Cp;
+  for (int ch = threadIdx.x; ch < Cp; ch += bd) {
+    float s0 = 0.f, s1 = 0.f;
+    for (unsigned b = 0; b < gridDim.x; ++b) { s0 += all[static_cast<int64_t>(b) * 2 * Cp + ch]; s1 += all[static_cast<int64_t>(b) * 2 * Cp + Cp + ch]; }
+    ssum[static_cast<int64_t>(n) * Cp + ch] = s0;
+    ssq[static_cast<int64_t>(n) * Cp + ch] = s1;
+  }
+  if (threadIdx.x == 0) ticket[n] = 0;   // ready for the next launch (CUDA-graph replay)
+}
+static int stats_det_blocks(int64_t HW, int cvec, int N) {
+  int64_t want = (HW * cvec + 256 * 16 - 1) / (256 * 16);
+  const int64_t cap = (148 * 4 + N - 1) / N;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return static_cast<int>(want);
 }
 
 // ------------------------------------------------------------------------------------------------ forward apply
@@ -88,10 +129,11 @@ __device__ __forceinline__ NormConst norm_consts(const float* ssum, const float*
   return c;
 }
 
-__global__ void __launch_bounds__(256) in_apply_kernel(const __nv_bfloat16* __restrict__ y, int64_t HW, int Cp,
+template <typename T>
+__global__ void __launch_bounds__(256) in_apply_kernel(const T* __restrict__ y, int64_t HW, int Cp,
                                                        const float* __restrict__ ssum, const float* __restrict__ ssq,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       float eps, float slope, __nv_bfloat16* __restrict__ a,
+                                                       float eps, float slope, T* __restrict__ a,
                                                        float* __restrict__ mean, float* __restrict__ rstd) {
   const int n = blockIdx.y, cvec = Cp / 8;
   const int64_t total = HW * cvec;
@@ -99,39 +141,40 @@ __global__ void __launch_bounds__(256) in_apply_kernel(const __nv_bfloat16* __re
   const int v = static_cast<int>(start % cvec);
   const NormConst c = norm_consts(ssum, ssq, gamma, beta, n, Cp, v, 1.f / static_cast<float>(HW), eps, mean, rstd,
                                   start < cvec);
-  const __nv_bfloat16* src = y + static_cast<int64_t>(n) * HW * Cp;
-  __nv_bfloat16* dst = a + static_cast<int64_t>(n) * HW * Cp;
+  const T* src = y + static_cast<int64_t>(n) * HW * Cp;
+  T* dst = a + static_cast<int64_t>(n) * HW * Cp;
   for (int64_t i = start; i < total; i += 2 * stride) {
     const bool two = (i + stride) < total;
-    const V8 x0 = load8(src + i * 8);
+    const V8 x0 = load8<T>(src + i * 8);
     V8 x1;
-    if (two) x1 = load8(src + (i + stride) * 8);
+    if (two) x1 = load8<T>(src + (i + stride) * 8);
     V8 o0, o1;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float z0 = fmaf(x0.f[k], c.sc[k], c.sh[k]);
       o0.f[k] = z0 > 0.f ? z0 : z0 * slope;
     }
-    store8(dst + i * 8, o0);
+    store8<T>(dst + i * 8, o0);
     if (two) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const float z1 = fmaf(x1.f[k], c.sc[k], c.sh[k]);
         o1.f[k] = z1 > 0.f ? z1 : z1 * slope;
       }
-      store8(dst + (i + stride) * 8, o1);
+      store8<T>(dst + (i + stride) * 8, o1);
     }
   }
 }
 
 // Same, plus the 2x2/2 max-pooled tensor; one work item = one pooled pixel x 8 channels.
-__global__ void __launch_bounds__(256) in_apply_pool_kernel(const __nv_bfloat16* __restrict__ y, int H, int W, int Cp,
+template <typename T>
+__global__ void __launch_bounds__(256) in_apply_pool_kernel(const T* __restrict__ y, int H, int W, int Cp,
                                                             const float* __restrict__ ssum,
                                                             const float* __restrict__ ssq,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float eps, float slope,
-                                                            __nv_bfloat16* __restrict__ a,
-                                                            __nv_bfloat16* __restrict__ pooled,
+                                                            T* __restrict__ a,
+                                                            T* __restrict__ pooled,
                                                             float* __restrict__ mean, float* __restrict__ rstd) {
   const int n = blockIdx.y, cvec = Cp / 8;
   const int Hp = H / 2, Wp = W / 2;
@@ -141,9 +184,9 @@ __global__ void __launch_bounds__(256) in_apply_pool_kernel(const __nv_bfloat16*
   const int v = static_cast<int>(start % cvec);
   const NormConst c = norm_consts(ssum, ssq, gamma, beta, n, Cp, v, 1.f / static_cast<float>(HW), eps, mean, rstd,
                                   start < cvec);
-  const __nv_bfloat16* src = y + static_cast<int64_t>(n) * HW * Cp + v * 8;
-  __nv_bfloat16* dst = a + static_cast<int64_t>(n) * HW * Cp + v * 8;
-  __nv_bfloat16* pdst = pooled + static_cast<int64_t>(n) * Hp * Wp * Cp + v * 8;
+  const T* src = y + static_cast<int64_t>(n) * HW * Cp + v * 8;
+  T* dst = a + static_cast<int64_t>(n) * HW * Cp + v * 8;
+  T* pdst = pooled + static_cast<int64_t>(n) * Hp * Wp * Cp + v * 8;
   for (int64_t i = start; i < total; i += stride) {
     const int64_t pp = i / cvec;
     const int ph = static_cast<int>(pp / Wp), pw = static_cast<int>(pp - static_cast<int64_t>(ph) * Wp);
@@ -151,21 +194,21 @@ __global__ void __launch_bounds__(256) in_apply_pool_kernel(const __nv_bfloat16*
     const int64_t offs[4] = {o00, o00 + Cp, o00 + static_cast<int64_t>(W) * Cp, o00 + static_cast<int64_t>(W) * Cp + Cp};
     V8 x[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) x[j] = load8(src + offs[j]);
+    for (int j = 0; j < 4; ++j) x[j] = load8<T>(src + offs[j]);
     V8 mx;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const float z = fmaf(x[j].f[k], c.sc[k], c.sh[k]);
-        // round through bf16 so the pooled value equals the stored activation bit for bit
-        const float o = __bfloat162float(__float2bfloat16(z > 0.f ? z : z * slope));
+        // as it reads back from storage, so the pooled value equals the stored activation bit for bit
+        const float o = as_stored<T>(z > 0.f ? z : z * slope);
         x[j].f[k] = o;
         mx.f[k] = (j == 0) ? o : fmaxf(mx.f[k], o);
       }
-      store8(dst + offs[j], x[j]);
+      store8<T>(dst + offs[j], x[j]);
     }
-    store8(pdst + pp * Cp, mx);
+    store8<T>(pdst + pp * Cp, mx);
   }
 }
 
@@ -187,8 +230,9 @@ __device__ __forceinline__ BwdConst bwd_consts(const float* mean, const float* r
   return c;
 }
 
-__global__ void __launch_bounds__(256) in_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA,
-                                                            const __nv_bfloat16* __restrict__ y, int64_t HW, int Cp,
+template <typename T>
+__global__ void __launch_bounds__(256) in_bwd_reduce_kernel(const T* __restrict__ dA,
+                                                            const T* __restrict__ y, int64_t HW, int Cp,
                                                             const float* __restrict__ mean,
                                                             const float* __restrict__ rstd,
                                                             const float* __restrict__ gamma,
@@ -203,11 +247,11 @@ __global__ void __launch_bounds__(256) in_bwd_reduce_kernel(const __nv_bfloat16*
   const int v = static_cast<int>(start % cvec);
   const BwdConst c = bwd_consts(mean, rstd, gamma, beta, n, Cp, v);
   float a1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const __nv_bfloat16* gsrc = dA + static_cast<int64_t>(n) * HW * Cp;
-  const __nv_bfloat16* ysrc = y + static_cast<int64_t>(n) * HW * Cp;
+  const T* gsrc = dA + static_cast<int64_t>(n) * HW * Cp;
+  const T* ysrc = y + static_cast<int64_t>(n) * HW * Cp;
   for (int64_t i = start; i < total; i += stride) {
-    const V8 g = load8(gsrc + i * 8);
-    const V8 x = load8(ysrc + i * 8);
+    const V8 g = load8<T>(gsrc + i * 8);
+    const V8 x = load8<T>(ysrc + i * 8);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float xh = (x.f[k] - c.mean[k]) * c.rstd[k];
@@ -241,14 +285,15 @@ __global__ void __launch_bounds__(256) in_bwd_reduce_kernel(const __nv_bfloat16*
   }
 }
 
-__global__ void __launch_bounds__(256) in_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA,
-                                                           const __nv_bfloat16* __restrict__ y, int64_t HW, int Cp,
+template <typename T>
+__global__ void __launch_bounds__(256) in_bwd_apply_kernel(const T* __restrict__ dA,
+                                                           const T* __restrict__ y, int64_t HW, int Cp,
                                                            const float* __restrict__ mean,
                                                            const float* __restrict__ rstd,
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float slope,
                                                            const float* __restrict__ s1, const float* __restrict__ s2,
-                                                           __nv_bfloat16* __restrict__ dy) {
+                                                           T* __restrict__ dy) {
   const int n = blockIdx.y, cvec = Cp / 8;
   const int64_t total = HW * cvec;
   const int64_t start = blockIdx.x * 256ll + threadIdx.x, stride = gridDim.x * 256ll;
@@ -262,12 +307,12 @@ __global__ void __launch_bounds__(256) in_bwd_apply_kernel(const __nv_bfloat16* 
     m2[k] = s2[static_cast<int64_t>(n) * Cp + v * 8 + k] * inv_hw;
     rg[k] = c.rstd[k] * c.g[k];
   }
-  const __nv_bfloat16* gsrc = dA + static_cast<int64_t>(n) * HW * Cp;
-  const __nv_bfloat16* ysrc = y + static_cast<int64_t>(n) * HW * Cp;
-  __nv_bfloat16* dst = dy + static_cast<int64_t>(n) * HW * Cp;
+  const T* gsrc = dA + static_cast<int64_t>(n) * HW * Cp;
+  const T* ysrc = y + static_cast<int64_t>(n) * HW * Cp;
+  T* dst = dy + static_cast<int64_t>(n) * HW * Cp;
   for (int64_t i = start; i < total; i += stride) {
-    const V8 g = load8(gsrc + i * 8);
-    const V8 x = load8(ysrc + i * 8);
+    const V8 g = load8<T>(gsrc + i * 8);
+    const V8 x = load8<T>(ysrc + i * 8);
     V8 o;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -276,7 +321,7 @@ __global__ void __launch_bounds__(256) in_bwd_apply_kernel(const __nv_bfloat16* 
       const float gg = z > 0.f ? g.f[k] : g.f[k] * slope;
       o.f[k] = rg[k] * (gg - m1[k] - xh * m2[k]);
     }
-    store8(dst + i * 8, o);
+    store8<T>(dst + i * 8, o);
   }
 }
 
@@ -292,9 +337,10 @@ __global__ void in_affine_grad_kernel(const float* __restrict__ s1, const float*
 }
 
 // ------------------------------------------------------------------------------------------------ pooling / upsample
-__global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ a,
-                                                           const __nv_bfloat16* __restrict__ dP, int H, int W, int Cp,
-                                                           __nv_bfloat16* __restrict__ dA, int accumulate,
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const T* __restrict__ a,
+                                                           const T* __restrict__ dP, int H, int W, int Cp,
+                                                           T* __restrict__ dA, int accumulate,
                                                            int64_t total) {
   const int cvec = Cp / 8, Hp = H / 2, Wp = W / 2;
   for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
@@ -307,8 +353,8 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const __nv_bfloat16* 
     const int64_t offs[4] = {o00, o00 + Cp, o00 + static_cast<int64_t>(W) * Cp, o00 + static_cast<int64_t>(W) * Cp + Cp};
     V8 x[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) x[j] = load8(a + offs[j]);
-    const V8 g = load8(dP + pp * Cp + v * 8);
+    for (int j = 0; j < 4; ++j) x[j] = load8<T>(a + offs[j]);
+    const V8 g = load8<T>(dP + pp * Cp + v * 8);
     V8 o[4];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -323,17 +369,18 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const __nv_bfloat16* 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (accumulate) {
-        const V8 old = load8(dA + offs[j]);
+        const V8 old = load8<T>(dA + offs[j]);
 #pragma unroll
         for (int k = 0; k < 8; ++k) o[j].f[k] += old.f[k];
       }
-      store8(dA + offs[j], o[j]);
+      store8<T>(dA + offs[j], o[j]);
     }
   }
 }
 
-__global__ void __launch_bounds__(256) upsample2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int H, int W, int Cp,
-                                                            __nv_bfloat16* __restrict__ y, int64_t total) {
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2_fwd_kernel(const T* __restrict__ x, int H, int W, int Cp,
+                                                            T* __restrict__ y, int64_t total) {
   const int cvec = Cp / 8;
   for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
     const int v = static_cast<int>(i % cvec);
@@ -341,16 +388,17 @@ __global__ void __launch_bounds__(256) upsample2_fwd_kernel(const __nv_bfloat16*
     const int w = static_cast<int>(pp % W);
     const int h = static_cast<int>((pp / W) % H);
     const int64_t n = pp / (static_cast<int64_t>(W) * H);
-    const uint4 u = *reinterpret_cast<const uint4*>(x + pp * Cp + v * 8);
+    const V8 u = load8<T>(x + pp * Cp + v * 8);
     const int64_t o00 = ((n * 2 * H + 2 * h) * (2 * W) + 2 * w) * Cp + v * 8;
-    *reinterpret_cast<uint4*>(y + o00) = u;
-    *reinterpret_cast<uint4*>(y + o00 + Cp) = u;
-    *reinterpret_cast<uint4*>(y + o00 + static_cast<int64_t>(2 * W) * Cp) = u;
-    *reinterpret_cast<uint4*>(y + o00 + static_cast<int64_t>(2 * W) * Cp + Cp) = u;
+    store8<T>(y + o00, u);
+    store8<T>(y + o00 + Cp, u);
+    store8<T>(y + o00 + static_cast<int64_t>(2 * W) * Cp, u);
+    store8<T>(y + o00 + static_cast<int64_t>(2 * W) * Cp + Cp, u);
   }
 }
-__global__ void __launch_bounds__(256) upsample2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int H, int W, int Cp,
-                                                            __nv_bfloat16* __restrict__ dx, int accumulate,
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2_bwd_kernel(const T* __restrict__ dy, int H, int W, int Cp,
+                                                            T* __restrict__ dx, int accumulate,
                                                             int64_t total) {
   const int cvec = Cp / 8;
   for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
@@ -360,21 +408,22 @@ __global__ void __launch_bounds__(256) upsample2_bwd_kernel(const __nv_bfloat16*
     const int h = static_cast<int>((pp / W) % H);
     const int64_t n = pp / (static_cast<int64_t>(W) * H);
     const int64_t o00 = ((n * 2 * H + 2 * h) * (2 * W) + 2 * w) * Cp + v * 8;
-    const V8 a = load8(dy + o00), b = load8(dy + o00 + Cp), c = load8(dy + o00 + static_cast<int64_t>(2 * W) * Cp),
-             d = load8(dy + o00 + static_cast<int64_t>(2 * W) * Cp + Cp);
+    const V8 a = load8<T>(dy + o00), b = load8<T>(dy + o00 + Cp), c = load8<T>(dy + o00 + static_cast<int64_t>(2 * W) * Cp),
+             d = load8<T>(dy + o00 + static_cast<int64_t>(2 * W) * Cp + Cp);
     V8 o;
 #pragma unroll
     for (int k = 0; k < 8; ++k) o.f[k] = (a.f[k] + b.f[k]) + (c.f[k] + d.f[k]);
     if (accumulate) {
-      const V8 old = load8(dx + pp * Cp + v * 8);
+      const V8 old = load8<T>(dx + pp * Cp + v * 8);
 #pragma unroll
       for (int k = 0; k < 8; ++k) o.f[k] += old.f[k];
     }
-    store8(dx + pp * Cp + v * 8, o);
+    store8<T>(dx + pp * Cp + v * 8, o);
   }
 }
 
-__global__ void __launch_bounds__(256) channel_sum_kernel(const __nv_bfloat16* __restrict__ t, int64_t npix, int Cp,
+template <typename T>
+__global__ void __launch_bounds__(256) channel_sum_kernel(const T* __restrict__ t, int64_t npix, int Cp,
                                                           int C_true, float* __restrict__ out) {
   extern __shared__ float s_acc[];  // [Cp]
   const int cvec = Cp / 8;
@@ -385,7 +434,7 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const __nv_bfloat16* _
   const int v = static_cast<int>(start % cvec);
   float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int64_t i = start; i < total; i += stride) {
-    const V8 x = load8(t + i * 8);
+    const V8 x = load8<T>(t + i * 8);
 #pragma unroll
     for (int k = 0; k < 8; ++k) a[k] += x.f[k];
   }
@@ -402,8 +451,12 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const __nv_bfloat16* _
 using namespace mtbc;
 
 #define ST(s) static_cast<cudaStream_t>(s)
-#define BF(p) static_cast<__nv_bfloat16*>(p)
-#define CBF(p) static_cast<const __nv_bfloat16*>(p)
+#define TP(p) static_cast<T*>(p)
+#define CTP(p) static_cast<const T*>(p)
+// bf16 only: the bulk-copy pipelined kernels of stream_pipe.cu serve the product path's large tensors
+static inline bool use_pipe(int64_t N, int64_t HW, int Cp) {
+  return !(current_mode() & MODE_ACT_FP32) && pipe_eligible(N, HW, Cp);
+}
 
 extern "C" {
 
@@ -411,8 +464,32 @@ int mtbc_in_stats(const void* y, int32_t N, int32_t HW, int32_t Cp, float* stat_
   if (Cp % 8) return set_error(MTBC_ERR_INVALID, "in_stats: Cp %% 8");
   const int cvec = Cp / 8;
   const int gx = pick_gx(static_cast<int64_t>(HW) * cvec, 256, cvec, N, 8);
-  in_stats_kernel<<<dim3(gx, N), 256, 2 * Cp * sizeof(float), ST(stream)>>>(CBF(y), HW, Cp, stat_sum, stat_sq);
+  MTBC_DISPATCH_ACT((in_stats_kernel<T><<<dim3(gx, N), 256, 2 * Cp * sizeof(float), ST(stream)>>>(CTP(y), HW, Cp, stat_sum, stat_sq)));
   return check_launch("in_stats");
+}
+
+int64_t mtbc_query_workspace_bytes(const char* op, int32_t N, int64_t HW, int32_t Cp) {
+  if (op == nullptr) return -1;
+  const std::string name(op);
+  if (name == "in_stats_det") {
+    if (Cp % 8 || Cp <= 0 || N <= 0) return -1;
+    const int gx = stats_det_blocks(HW, Cp / 8, N);
+    return static_cast<int64_t>(N) * gx * 2 * Cp * sizeof(float) + static_cast<int64_t>(N) * sizeof(int) + 256;
+  }
+  return 0;   // every other entry point works in the buffers it is handed
+}
+
+int mtbc_in_stats_det(const void* y, int32_t N, int32_t HW, int32_t Cp, float* stat_sum, float* stat_sq,
+                      void* workspace, void* stream) {
+  if (Cp % 8 || Cp / 8 > 256) return set_error(MTBC_ERR_INVALID, "in_stats_det: Cp %% 8 != 0 or Cp > 2048");
+  if (!workspace) return set_error(MTBC_ERR_INVALID, "in_stats_det: workspace of mtbc_query_workspace_bytes(\"in_stats_det\") bytes, zeroed once, is required");
+  const int cvec = Cp / 8;
+  const int bd = (256 / cvec) * cvec;
+  const int gx = stats_det_blocks(HW, cvec, N);
+  int* ticket = static_cast<int*>(workspace);                       // [N], zero between launches
+  float* partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + ((static_cast<size_t>(N) * sizeof(int) + 255) & ~size_t(255)));
+  MTBC_DISPATCH_ACT((in_stats_det_kernel<T><<<dim3(gx, N), bd, 0, ST(stream)>>>(CTP(y), HW, Cp, partial, ticket, stat_sum, stat_sq)));
+  return check_launch("in_stats_det");
 }
 
 int mtbc_in_apply(const void* y, int32_t N, int32_t H, int32_t W, int32_t Cp, const float* stat_sum,
@@ -425,14 +502,14 @@ int mtbc_in_apply(const void* y, int32_t N, int32_t H, int32_t W, int32_t Cp, co
   if (pooled) {
     if ((H & 1) || (W & 1)) return set_error(MTBC_ERR_INVALID, "in_apply: pooled output needs even H, W");
     const int gx = pick_gx(HW / 4 * cvec, 256, cvec, N, 2);
-    in_apply_pool_kernel<<<dim3(gx, N), 256, 0, ST(stream)>>>(CBF(y), H, W, Cp, stat_sum, stat_sq, gamma, beta, eps,
-                                                             slope, BF(a), BF(pooled), mean, rstd);
+    MTBC_DISPATCH_ACT((in_apply_pool_kernel<T><<<dim3(gx, N), 256, 0, ST(stream)>>>(CTP(y), H, W, Cp, stat_sum, stat_sq, gamma, beta, eps,
+                                                                                     slope, TP(a), TP(pooled), mean, rstd)));
   } else {
-    if (pipe_eligible(N, HW, Cp))
+    if (use_pipe(N, HW, Cp))
       return in_apply_pipe(y, N, HW, Cp, stat_sum, stat_sq, gamma, beta, eps, slope, a, mean, rstd, ST(stream));
     const int gx = pick_gx(HW * cvec, 256, cvec, N, 4);
-    in_apply_kernel<<<dim3(gx, N), 256, 0, ST(stream)>>>(CBF(y), HW, Cp, stat_sum, stat_sq, gamma, beta, eps, slope,
-                                                        BF(a), mean, rstd);
+    MTBC_DISPATCH_ACT((in_apply_kernel<T><<<dim3(gx, N), 256, 0, ST(stream)>>>(CTP(y), HW, Cp, stat_sum, stat_sq, gamma, beta, eps, slope,
+                                                                                TP(a), mean, rstd)));
   }
   return check_launch("in_apply");
 }
@@ -440,25 +517,25 @@ int mtbc_in_apply(const void* y, int32_t N, int32_t H, int32_t W, int32_t Cp, co
 int mtbc_in_bwd_reduce(const void* dA, const void* y, int32_t N, int32_t HW, int32_t Cp, const float* mean,
                        const float* rstd, const float* gamma, const float* beta, float slope, float* s1, float* s2,
                        void* stream) {
-  if (pipe_eligible(N, HW, Cp))
+  if (use_pipe(N, HW, Cp))
     return in_bwd_reduce_pipe(dA, y, N, HW, Cp, mean, rstd, gamma, beta, slope, s1, s2, ST(stream));
   const int cvec = Cp / 8;
   const int gx = pick_gx(static_cast<int64_t>(HW) * cvec, 256, cvec, N, 8);
-  in_bwd_reduce_kernel<<<dim3(gx, N), 256, 2 * Cp * sizeof(float), ST(stream)>>>(CBF(dA), CBF(y), HW, Cp, mean, rstd,
-                                                                                 gamma, beta, slope, s1, s2);
+  MTBC_DISPATCH_ACT((in_bwd_reduce_kernel<T><<<dim3(gx, N), 256, 2 * Cp * sizeof(float), ST(stream)>>>(CTP(dA), CTP(y), HW, Cp, mean, rstd,
+                                                                                                         gamma, beta, slope, s1, s2)));
   return check_launch("in_bwd_reduce");
 }
 
 int mtbc_in_bwd_apply(const void* dA, const void* y, int32_t N, int32_t HW, int32_t Cp, const float* mean,
                       const float* rstd, const float* gamma, const float* beta, float slope, const float* s1,
                       const float* s2, void* dy, float* dgamma, float* dbeta, int32_t C_true, void* stream) {
-  if (pipe_eligible(N, HW, Cp))
+  if (use_pipe(N, HW, Cp))
     return in_bwd_apply_pipe(dA, y, N, HW, Cp, mean, rstd, gamma, beta, slope, s1, s2, dy, dgamma, dbeta, C_true,
                              ST(stream));
   const int cvec = Cp / 8;
   const int gx = pick_gx(static_cast<int64_t>(HW) * cvec, 256, cvec, N, 4);
-  in_bwd_apply_kernel<<<dim3(gx, N), 256, 0, ST(stream)>>>(CBF(dA), CBF(y), HW, Cp, mean, rstd, gamma, beta, slope, s1,
-                                                          s2, BF(dy));
+  MTBC_DISPATCH_ACT((in_bwd_apply_kernel<T><<<dim3(gx, N), 256, 0, ST(stream)>>>(CTP(dA), CTP(y), HW, Cp, mean, rstd, gamma, beta, slope, s1,
+                                                                                  s2, TP(dy))));
   int rc = check_launch("in_bwd_apply");
   if (rc) return rc;
   if (dgamma && dbeta) {
@@ -471,7 +548,7 @@ int mtbc_in_bwd_apply(const void* dA, const void* y, int32_t N, int32_t HW, int3
 int mtbc_in_bwd(const void* dA, const void* y, int32_t N, int32_t HW, int32_t Cp, const float* mean, const float* rstd,
                 const float* gamma, const float* beta, float slope, float* s1, float* s2, void* dy, float* dgamma,
                 float* dbeta, int32_t C_true, int32_t* counters, void* stream) {
-  if (counters != nullptr && in_bwd_fused_eligible(N, HW, Cp))
+  if (counters != nullptr && !(current_mode() & MODE_ACT_FP32) && in_bwd_fused_eligible(N, HW, Cp))
     return in_bwd_fused(dA, y, N, HW, Cp, mean, rstd, gamma, beta, slope, s1, s2, dy, dgamma, dbeta, C_true, counters,
                         ST(stream));
   int rc = mtbc_in_bwd_reduce(dA, y, N, HW, Cp, mean, rstd, gamma, beta, slope, s1, s2, stream);
@@ -483,20 +560,20 @@ int mtbc_maxpool2_bwd(const void* a, const void* dP, int32_t N, int32_t H, int32
                       int32_t accumulate, void* stream) {
   const int64_t total = static_cast<int64_t>(N) * (H / 2) * (W / 2) * (Cp / 8);
   int g = cdiv(total, 256); if (g > 148 * 8) g = 148 * 8;
-  maxpool2_bwd_kernel<<<g, 256, 0, ST(stream)>>>(CBF(a), CBF(dP), H, W, Cp, BF(dA), accumulate, total);
+  MTBC_DISPATCH_ACT((maxpool2_bwd_kernel<T><<<g, 256, 0, ST(stream)>>>(CTP(a), CTP(dP), H, W, Cp, TP(dA), accumulate, total)));
   return check_launch("maxpool2_bwd");
 }
 int mtbc_upsample2_fwd(const void* x, int32_t N, int32_t H, int32_t W, int32_t Cp, void* y, void* stream) {
   const int64_t total = static_cast<int64_t>(N) * H * W * (Cp / 8);
   int g = cdiv(total, 256); if (g > 148 * 8) g = 148 * 8;
-  upsample2_fwd_kernel<<<g, 256, 0, ST(stream)>>>(CBF(x), H, W, Cp, BF(y), total);
+  MTBC_DISPATCH_ACT((upsample2_fwd_kernel<T><<<g, 256, 0, ST(stream)>>>(CTP(x), H, W, Cp, TP(y), total)));
   return check_launch("upsample2_fwd");
 }
 int mtbc_upsample2_bwd(const void* dy, int32_t N, int32_t H, int32_t W, int32_t Cp, void* dx, int32_t accumulate,
                        void* stream) {
   const int64_t total = static_cast<int64_t>(N) * H * W * (Cp / 8);
   int g = cdiv(total, 256); if (g > 148 * 8) g = 148 * 8;
-  upsample2_bwd_kernel<<<g, 256, 0, ST(stream)>>>(CBF(dy), H, W, Cp, BF(dx), accumulate, total);
+  MTBC_DISPATCH_ACT((upsample2_bwd_kernel<T><<<g, 256, 0, ST(stream)>>>(CTP(dy), H, W, Cp, TP(dx), accumulate, total)));
   return check_launch("upsample2_bwd");
 }
 int mtbc_channel_sum(const void* t, int64_t npix, int32_t Cp, int32_t C_true, float* out, int32_t add, void* stream) {
@@ -504,10 +581,10 @@ int mtbc_channel_sum(const void* t, int64_t npix, int32_t Cp, int32_t C_true, fl
     cudaError_t e = cudaMemsetAsync(out, 0, C_true * sizeof(float), ST(stream));
     if (e != cudaSuccess) return set_error(MTBC_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
   }
-  if (pipe_eligible(1, npix, Cp)) return channel_sum_pipe(t, npix, Cp, C_true, out, ST(stream));
+  if (use_pipe(1, npix, Cp)) return channel_sum_pipe(t, npix, Cp, C_true, out, ST(stream));
   const int cvec = Cp / 8;
   const int gx = pick_gx(npix * cvec, 256, cvec, 1, 16);
-  channel_sum_kernel<<<gx, 256, Cp * sizeof(float), ST(stream)>>>(CBF(t), npix, Cp, C_true, out);
+  MTBC_DISPATCH_ACT((channel_sum_kernel<T><<<gx, 256, Cp * sizeof(float), ST(stream)>>>(CTP(t), npix, Cp, C_true, out)));
   return check_launch("channel_sum");
 }
 

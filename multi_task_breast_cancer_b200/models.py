@@ -83,7 +83,26 @@ class _PlanModule(nn.Module):
     _slope: float = 0.01
 
     def _init_runtime(self):
+        import os
         self._plans: Dict[Tuple, Plan] = {}
+        # Arithmetic mode (not part of the reference's constructor: set the attribute, call set_precision(), or export
+        # MTBC_PRECISION / MTBC_DETERMINISTIC before building the model).  "bf16" is the product path; "tf32" and
+        # "tf32x3" are the forward-only parity modes of north_star ("1e-3 (TF32 mode)").
+        self.precision = os.environ.get("MTBC_PRECISION", "bf16")
+        self.deterministic = os.environ.get("MTBC_DETERMINISTIC", "0") not in ("", "0")
+
+    def set_precision(self, precision: str = "bf16", deterministic: Optional[bool] = None):
+        """"bf16" (default, training + inference), "tf32" (fp32 storage, tcgen05 kind::tf32, inference only) or
+        "tf32x3" (same with the three-product split: fp32-grade results).  deterministic=True makes the forward pass
+        bit-reproducible (order-independent InstanceNorm statistics) at the price of one more read of every conv
+        output."""
+        from .plan import PRECISIONS
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {PRECISIONS}")
+        self.precision = precision
+        if deterministic is not None:
+            self.deterministic = bool(deterministic)
+        return self
 
     # nn.Module.__setstate__/deepcopy safety
     def __getstate__(self):
@@ -108,7 +127,7 @@ class _PlanModule(nn.Module):
             raise ValueError("expected a float32 (B, C, H, W) image batch")
         params = self._named_params()
         sig = tuple(p.data_ptr() for p in params.values())
-        key = (tuple(x.shape), x.device.index, need_grad, sig)
+        key = (tuple(x.shape), x.device.index, need_grad, sig, self.precision, self.deterministic)
         plan = self._plans.get(key)
         if plan is None:
             # drop plans built for stale parameter storage (e.g. after .to())
@@ -118,7 +137,8 @@ class _PlanModule(nn.Module):
             _lib.check(lib.mtbc_device_check(), "device check")
             B, Cin, H, W = x.shape
             with torch.cuda.device(x.device):
-                plan = Plan(B, H, W, x.device, params, training=need_grad)
+                plan = Plan(B, H, W, x.device, params, training=need_grad, precision=self.precision,
+                            deterministic=self.deterministic)
                 plan.x_in = torch.zeros(B, Cin, H, W, dtype=torch.float32, device=x.device)
                 self._build_graph(plan, plan.x_in)
                 plan.finalize(self._seg_heads_active())
@@ -137,6 +157,9 @@ class _PlanModule(nn.Module):
 
     def _run(self, x: torch.Tensor):
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if need_grad and self.precision != "bf16":
+            raise NotImplementedError(f"precision={self.precision!r} is a forward-only parity mode: call the model under "
+                                      "torch.no_grad() (training runs in bf16)")
         plan = self._get_plan(x, need_grad)
         with torch.cuda.device(x.device):
             if need_grad:

@@ -54,9 +54,13 @@ def ptr(t: Optional[torch.Tensor]):
 
 @dataclass
 class Feat:
-    """bf16 NHWC activation.  Cp = channel pitch of the tensor (multiple of 8), Ck = its GEMM extent (multiple of 32)."""
-    t: torch.Tensor  # [N, H, W, Cp] bf16
+    """NHWC activation: bf16 on the product path, fp32 in the TF32 parity mode.  Cp = channel pitch of the tensor
+    (multiple of 8), Ck = its GEMM extent (multiple of 32)."""
+    t: torch.Tensor  # [N, H, W, Cp] bf16 | fp32
     C: int           # true channels
+
+    @property
+    def fp32(self): return self.t.dtype == torch.float32
 
     @property
     def N(self): return self.t.shape[0]
@@ -70,9 +74,9 @@ class Feat:
     def Ck(self): return pad32(self.t.shape[3])
 
     @staticmethod
-    def empty(N, H, W, C, device="cuda", zero=True) -> "Feat":
+    def empty(N, H, W, C, device="cuda", zero=True, dtype=torch.bfloat16) -> "Feat":
         f = torch.zeros if zero else torch.empty
-        return Feat(f((N, H, W, pitch_of(C)), dtype=torch.bfloat16, device=device), C)
+        return Feat(f((N, H, W, pitch_of(C)), dtype=dtype, device=device), C)
 
     @staticmethod
     def from_nchw(x: torch.Tensor) -> "Feat":
@@ -96,7 +100,7 @@ def _view(f: Feat) -> ActView:
 def _strided_view(f: Feat, k: int, i: int, j: int) -> ActView:
     """View of every k-th pixel of f starting at (i, j): the (i, j) sub-lattice of a k-times upsampled map."""
     v = ActView()
-    v.ptr = f.t.data_ptr() + 2 * ((i * f.W + j) * f.Cp)
+    v.ptr = f.t.data_ptr() + f.t.element_size() * ((i * f.W + j) * f.Cp)
     v.C, v.W, v.H, v.N = f.Cp, f.W // k, f.H // k, f.N
     v.sW, v.sH, v.sN = k * f.Cp, k * f.W * f.Cp, f.H * f.W * f.Cp
     return v
@@ -141,13 +145,23 @@ def _create_gemm(d: ConvGemmDesc, keep, kind) -> Op:
     return Op(h, keep, kind)
 
 
+def _set_dtype(d: ConvGemmDesc, feats: Sequence[Feat], wpack: torch.Tensor, wpack_lo: Optional[torch.Tensor]):
+    """dtype 0: bf16 / kind::f16; 1: fp32 storage / kind::tf32; 3: 3xTF32 (wpack_lo = TF32 remainder of the weights)."""
+    fp32 = wpack.dtype == torch.float32
+    assert all(f.fp32 == fp32 for f in feats), "activations and packed weights must share the precision mode"
+    d.dtype = 0 if not fp32 else (3 if wpack_lo is not None else 1)
+    d.wpack_lo = None if wpack_lo is None else wpack_lo.data_ptr()
+
+
 def conv3x3_fwd_op(srcs: Sequence[Feat], wpack: torch.Tensor, out: Feat, bias: Optional[torch.Tensor] = None,
                    stat_sum: Optional[torch.Tensor] = None, stat_sq: Optional[torch.Tensor] = None,
-                   accumulate: bool = False, ksz: int = 3, kind: str = "conv3x3_fwd") -> Op:
-    """wpack: bf16 [ksz*ksz][out.Ck][Ktot] laid out by `k_offsets(srcs)`."""
+                   accumulate: bool = False, ksz: int = 3, kind: str = "conv3x3_fwd",
+                   wpack_lo: Optional[torch.Tensor] = None) -> Op:
+    """wpack: bf16 (or fp32 holding TF32 values) [ksz*ksz][out.Ck][Ktot] laid out by `k_offsets(srcs)`."""
     offs, ktot = k_offsets(srcs)
     assert wpack.shape == (ksz * ksz, out.Ck, ktot), (wpack.shape, (ksz * ksz, out.Ck, ktot))
     d = ConvGemmDesc()
+    _set_dtype(d, [*srcs, out], wpack, wpack_lo)
     d.nviews = len(srcs)
     for i, s in enumerate(srcs):
         d.views[i] = _view(s)
@@ -168,7 +182,7 @@ def conv3x3_fwd_op(srcs: Sequence[Feat], wpack: torch.Tensor, out: Feat, bias: O
     d.stat_C = out.Cp
     d.accumulate = int(accumulate)
     d.nouts = 0
-    return _create_gemm(d, [*(s.t for s in srcs), wpack, out.t, bias, stat_sum, stat_sq], kind)
+    return _create_gemm(d, [*(s.t for s in srcs), wpack, wpack_lo, out.t, bias, stat_sum, stat_sq], kind)
 
 
 def conv3x3_dgrad_op(dy: Feat, wd: torch.Tensor, dx: Feat, accumulate: bool, ksz: int = 3) -> Op:
@@ -204,10 +218,12 @@ def conv3x3_dgrad_multi_op(dy: Feat, wd_all: torch.Tensor, dxs: Sequence[Feat], 
     return _create_gemm(d, [dy.t, wd_all, *(f.t for f in dxs)], "conv3x3_dgrad")
 
 
-def convT_fwd_op(x: Feat, wf: torch.Tensor, out: Feat, k: int, bias: Optional[torch.Tensor]) -> Op:
-    """wf: bf16 [1][k*k*out.Ck][x.Ck]; out spatial = k * x spatial."""
+def convT_fwd_op(x: Feat, wf: torch.Tensor, out: Feat, k: int, bias: Optional[torch.Tensor],
+                 wf_lo: Optional[torch.Tensor] = None) -> Op:
+    """wf: bf16 (or fp32 / TF32 values) [1][k*k*out.Ck][x.Ck]; out spatial = k * x spatial."""
     assert wf.shape == (1, k * k * out.Ck, x.Ck)
     d = ConvGemmDesc()
+    _set_dtype(d, [x, out], wf, wf_lo)
     d.nviews = 1; d.views[0] = _view(x)
     d.nseg = 1; d.seg[0] = GemmSeg(0, 0, 0, 0, 0)
     d.wpack = wf.data_ptr(); d.w_ntaps = 1; d.w_ktot = x.Ck; d.ncols = k * k * out.Ck
@@ -215,7 +231,7 @@ def convT_fwd_op(x: Feat, wf: torch.Tensor, out: Feat, k: int, bias: Optional[to
     d.epi_mode = 1; d.out = out.t.data_ptr(); d.out_C = out.Cp; d.up_k = k; d.up_cp = out.Ck
     d.bias = None if bias is None else bias.data_ptr()
     d.stat_sum = None; d.stat_sq = None; d.stat_C = 0; d.accumulate = 0
-    return _create_gemm(d, [x.t, wf, out.t, bias], "convT_fwd")
+    return _create_gemm(d, [x.t, wf, wf_lo, out.t, bias], "convT_fwd")
 
 
 def convT_dgrad_op(dout: Feat, wd: torch.Tensor, dx: Feat, k: int, accumulate: bool) -> Op:

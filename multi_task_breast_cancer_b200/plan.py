@@ -21,6 +21,13 @@ from .ops import Feat, pad32, pitch_of, ptr
 EPS = 1e-5
 
 
+PRECISIONS = ("bf16", "tf32", "tf32x3")
+
+# Mode flags (mtbc_set_mode) of the plan being built: `_mk` binds them into every launch closure it creates.  Set by
+# Plan.__init__, cleared by Plan.finalize -- a plan is built in one go (models._PlanModule._get_plan).
+_build_mode = 0
+
+
 class PTensor:
     """A bf16 NHWC activation of the plan plus its (lazily allocated) gradient."""
 
@@ -32,7 +39,8 @@ class PTensor:
 
     def grad(self) -> Feat:
         if self.g is None:
-            self.g = Feat.empty(self.feat.N, self.feat.H, self.feat.W, self.feat.C, device=self.feat.t.device)
+            self.g = Feat.empty(self.feat.N, self.feat.H, self.feat.W, self.feat.C, device=self.feat.t.device,
+                                dtype=self.feat.t.dtype)
         return self.g
 
 
@@ -67,12 +75,26 @@ class Arena:
 
 def _mk(name: str, *args) -> Callable[[C.c_void_p], None]:
     """Bind a C-ABI call; the stream is supplied at launch time."""
-    fn = getattr(_lib.load(), name)
+    lib = _lib.load()
+    fn = getattr(lib, name)
+    mode = _build_mode
 
-    def launch(stream):
-        rc = fn(*args, stream)
-        if rc != 0:
-            _lib.check(rc, name)
+    if mode == 0:
+        def launch(stream):
+            rc = fn(*args, stream)
+            if rc != 0:
+                _lib.check(rc, name)
+    else:
+        # element-type generic entry points read the calling thread's mode (fp32 activations / deterministic
+        # reductions); the product path (mode 0) pays nothing for it
+        def launch(stream):
+            lib.mtbc_set_mode(mode)
+            try:
+                rc = fn(*args, stream)
+            finally:
+                lib.mtbc_set_mode(0)
+            if rc != 0:
+                _lib.check(rc, name)
     launch.kind = name
     return launch
 
@@ -138,10 +160,26 @@ def _mk_op(op: ops.Op, true_flops: float = 0.0, desc: str = "", true_bytes: floa
 class Plan:
     """Builder + executor.  Model files call the layer methods in forward order; `finalize()` emits the backward."""
 
-    def __init__(self, B: int, H: int, W: int, device, params: Dict[str, torch.nn.Parameter], training: bool = True):
+    def __init__(self, B: int, H: int, W: int, device, params: Dict[str, torch.nn.Parameter], training: bool = True,
+                 precision: str = "bf16", deterministic: bool = False):
+        """precision: "bf16" = the product path (bf16 storage, tcgen05 kind::f16).  "tf32" / "tf32x3" = the parity modes
+        north_star names ("1e-3 (TF32 mode)"): fp32 storage everywhere, tcgen05 kind::tf32 convolutions through the
+        generic implicit-GEMM kernel, single pass or with the 3xTF32 split (fp32-grade products); forward only.
+        deterministic: InstanceNorm statistics come from an order-independent reduction (mtbc_in_stats_det) instead of
+        the conv epilogues' fp32 atomics, so the forward pass is bit-identical from run to run."""
+        global _build_mode
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {PRECISIONS}")
+        if precision != "bf16" and training:
+            raise NotImplementedError("the TF32 parity modes are forward-only: run the model under torch.no_grad()")
         self.B, self.H, self.W, self.device = B, H, W, device
         self.params = params
         self.training = training
+        self.precision, self.deterministic = precision, bool(deterministic)
+        self.fp32 = precision != "bf16"
+        self.act_dtype = torch.float32 if self.fp32 else torch.bfloat16
+        self.mode_flags = (_lib.MODE_ACT_FP32 if self.fp32 else 0) | (_lib.MODE_DETERMINISTIC if deterministic else 0)
+        _build_mode = self.mode_flags
         self.pack: List[Callable] = []
         self.pack_jobs = JobTable()     # vector copies + weight packs, one launch at the head of `pack`
         self.unpack_jobs = JobTable()   # weight-gradient unpacks, one launch at the tail of `bwd`
@@ -186,7 +224,7 @@ class Plan:
         return self.params[name]
 
     def new(self, N, H, W, Cc, name) -> PTensor:
-        t = PTensor(Feat.empty(N, H, W, Cc, device=self.device), name)
+        t = PTensor(Feat.empty(N, H, W, Cc, device=self.device, dtype=self.act_dtype), name)
         self.tensors[name] = t
         return t
 
@@ -203,7 +241,7 @@ class Plan:
         turn = self._scratch_turn.get(key, 0)
         self._scratch_turn[key] = turn + 1
         if len(ring) < nbuf:
-            ring.append(Feat.empty(N, H, W, Cc, device=self.device))
+            ring.append(Feat.empty(N, H, W, Cc, device=self.device, dtype=self.act_dtype))
         idx = turn % len(ring) if len(ring) == nbuf else len(ring) - 1
         f = ring[idx]
         self._cur_slot = (key, idx)
@@ -250,10 +288,14 @@ class Plan:
         xs = torch.zeros(N, Cin * 9, dtype=torch.float32, device=self.device)  # shifted plane sums (mean removal)
         self._keep.append(xs)
         npx = N * H * Wd
+        det = self.deterministic
         self.fwd.append(_annot(_mk("mtbc_conv_first_fwd", ptr(x_in), N, Cin, H, Wd, ptr(Wt), ptr(bvec), Cout,
-                                   ptr(y.feat.t), y.feat.Cp, ptr(ssum), ptr(ssq), ptr(xs)),
+                                   ptr(y.feat.t), y.feat.Cp, None if det else ptr(ssum), None if det else ptr(ssq),
+                                   ptr(xs)),
                                f"{name} first conv fwd {N}x{H}x{Wd} {Cin}->{Cout}", npx * (4 * Cin + 2 * Cout)))
         self.fwd[-1].true_flops = 2.0 * npx * Cout * Cin * 9
+        if det:
+            self.fwd.append(self._stats_launch(y, ssum, ssq, name))
         a, p, aux = self._norm_act(y, ssum, ssq, gamma, beta, slope, pool, name)
 
         def backward():
@@ -285,14 +327,14 @@ class Plan:
         pk = self._pack_conv(w, feats, y.feat.Ck)
         ssum = self.fwd_arena.alloc(N, Cp)
         ssq = self.fwd_arena.alloc(N, Cp)
-        fused = H * Wd >= 128
+        fused = H * Wd >= 128 and not self.deterministic
         # The conv bias (MONAI Convolution has bias=True, MTUNetPlusPlus.py:24) is NOT added: InstanceNorm follows
         # immediately and is invariant to a per-channel shift of its input, so `a` is unchanged in exact arithmetic, the
         # bias gradient is identically zero (see backward below), and y is stored closer to zero-mean (fewer bf16
         # mantissa bits spent on a DC level).  It also takes 16 adds per chunk out of the epilogue's critical path.
         bias = None
         op = ops.conv3x3_fwd_op(feats, pk["wf"], y.feat, bias=bias, stat_sum=ssum if fused else None,
-                                stat_sq=ssq if fused else None)
+                                stat_sq=ssq if fused else None, wpack_lo=pk.get("wf_lo"))
         self.tc_flops_fwd += op.flops
         npx = N * H * Wd
         wbytes = 2.0 * 9 * Cin * Cout
@@ -300,8 +342,7 @@ class Plan:
                                f"{name} fwd {N}x{H}x{Wd} {[f.C for f in feats]}->{Cout}",
                                2.0 * npx * (Cin + Cout) + wbytes))
         if not fused:
-            self.fwd.append(_annot(_mk("mtbc_in_stats", ptr(y.feat.t), N, H * Wd, Cp, ptr(ssum), ptr(ssq)),
-                                   f"{name} in_stats {N}x{H}x{Wd}x{Cout}", 2.0 * npx * Cout))
+            self.fwd.append(self._stats_launch(y, ssum, ssq, name))
         a, p, aux = self._norm_act(y, ssum, ssq, gamma, beta, slope, pool, name)
         self._wg_pending[w] = self._wg_pending.get(w, 0) + 1
 
@@ -336,6 +377,22 @@ class Plan:
         self._bwd_blocks.append(backward)
         return a, p
 
+    def _stats_launch(self, y: PTensor, ssum, ssq, name: str) -> Callable:
+        """Separate InstanceNorm statistics pass over a stored conv output (planes too small for the fused epilogue
+        statistics, or deterministic mode)."""
+        f = y.feat
+        nbytes = 2.0 * f.N * f.H * f.W * f.C * (2 if self.fp32 else 1)
+        if not self.deterministic:
+            return _annot(_mk("mtbc_in_stats", ptr(f.t), f.N, f.H * f.W, f.Cp, ptr(ssum), ptr(ssq)),
+                          f"{name} in_stats {f.N}x{f.H}x{f.W}x{f.C}", nbytes)
+        need = int(_lib.load().mtbc_query_workspace_bytes(b"in_stats_det", f.N, f.H * f.W, f.Cp))
+        if need <= 0:
+            raise _lib.MtbcError(f"in_stats_det: no workspace size for N={f.N} HW={f.H * f.W} Cp={f.Cp}")
+        ws = torch.zeros((need + 3) // 4, dtype=torch.int32, device=self.device)
+        self._keep.append(ws)
+        return _annot(_mk("mtbc_in_stats_det", ptr(f.t), f.N, f.H * f.W, f.Cp, ptr(ssum), ptr(ssq), ptr(ws)),
+                      f"{name} in_stats_det {f.N}x{f.H}x{f.W}x{f.C}", nbytes)
+
     def _pack_conv(self, w: str, feats: Sequence[Feat], Cp: int) -> dict:
         """bf16 forward / data-gradient operands of a conv weight (shared modules are packed once per step)."""
         key = w
@@ -345,14 +402,20 @@ class Plan:
             return pk
         Wt = self.P(w)
         offs, ktot = ops.k_offsets(feats)
-        wf = torch.zeros(9, Cp, ktot, dtype=torch.bfloat16, device=self.device)
+        # bf16 operands, or fp32 operands holding TF32 values (part 1 = rounded weight, part 2 = rounded remainder)
+        wf = torch.zeros(9, Cp, ktot, dtype=torch.float32 if self.fp32 else torch.bfloat16, device=self.device)
+        wf_lo = torch.zeros_like(wf) if self.precision == "tf32x3" else None
         st_c = [f.C for f in feats]
         c0 = 0
         for cs, off in zip(st_c, offs):
-            self.pack_jobs.add(_lib.JOB_PACK_CONV, [Wt.shape[0], Wt.shape[1], 3, c0, cs, wf.shape[1], wf.shape[2], off,
-                                                    0, 0], Wt, wf, None)
+            for part, dst in ((1 if self.fp32 else 0, wf), (2, wf_lo)):
+                if dst is not None:
+                    self.pack_jobs.add(_lib.JOB_PACK_CONV, [Wt.shape[0], Wt.shape[1], 3, c0, cs, wf.shape[1],
+                                                            wf.shape[2], off, 0, 0, part], Wt, dst, None)
             c0 += cs
         pk = {"wf": wf, "offs": offs, "ktot": ktot, "src_cp": [f.Ck for f in feats], "src_c": st_c, "Cp": Cp}
+        if wf_lo is not None:
+            pk["wf_lo"] = wf_lo
         self._packed[key] = pk
         return pk
 
@@ -479,12 +542,15 @@ class Plan:
         assert f.C == Cin
         out = self.new(f.N, f.H * k, f.W * k, Cout, name)
         cp = out.feat.Ck                    # GEMM columns per sub-pixel (the tensor itself may be denser: out.feat.Cp)
-        wf = torch.zeros(1, k * k * cp, f.Ck, dtype=torch.bfloat16, device=self.device)
+        wf = torch.zeros(1, k * k * cp, f.Ck, dtype=torch.float32 if self.fp32 else torch.bfloat16, device=self.device)
         wd = torch.zeros(k * k, f.Ck, cp, dtype=torch.bfloat16, device=self.device) if self.training else None
-        self.pack_jobs.add(_lib.JOB_PACK_CONVT, [Cin, Cout, k, cp, wf.shape[2], 0 if wd is None else wd.shape[1],
-                                                 0 if wd is None else wd.shape[2]], Wt, wf, wd)
+        wf_lo = torch.zeros_like(wf) if self.precision == "tf32x3" else None
+        for part, dst, dst1 in ((1 if self.fp32 else 0, wf, wd), (2, wf_lo, None)):
+            if dst is not None:
+                self.pack_jobs.add(_lib.JOB_PACK_CONVT, [Cin, Cout, k, cp, wf.shape[2], 0 if dst1 is None else wd.shape[1],
+                                                         0 if dst1 is None else wd.shape[2], 0, 0, 0, part], Wt, dst, dst1)
         bias = self._padded_vec(b, cp)
-        op = ops.convT_fwd_op(f, wf, out.feat, k, bias)
+        op = ops.convT_fwd_op(f, wf, out.feat, k, bias, wf_lo)
         self.tc_flops_fwd += op.flops
         t_flops = 2.0 * f.N * f.H * f.W * Cin * Cout * k * k
         t_bytes = 2.0 * f.N * f.H * f.W * (Cin + k * k * Cout) + 2.0 * Cin * Cout * k * k
@@ -691,6 +757,8 @@ class Plan:
         self.fwd = self.fwd_arena.zero_launches() + self.fwd
         self._bwd_blocks = []
         self.finalized = True
+        global _build_mode
+        _build_mode = 0
 
     def _bucketize(self, body: List[Callable]) -> List[Callable]:
         """Split the flat gradient buffer into `n_buckets` contiguous ranges of about equal size and make each range

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _decls():
     src = open(os.path.join(ROOT, "include", "mtbc.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return re.findall(r"\b(?:int|void|double|const char\*)\s+(mtbc_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S)
+    return re.findall(r"\b(?:int64_t|int|void|double|const char\*)\s+(mtbc_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S)
 
 
 def test_header_symbols_exported(lib):

@@ -88,6 +88,38 @@ def test_forward_and_loss_parity(arch, B, S):
     assert abs(cls_n.item() - cls_r.item()) < 1e-2 * cls_r.item()
 
 
+@pytest.mark.parametrize("arch,B,S", [("unetpp", 4, 128), ("nnunet", 4, 128), ("bts", 4, 128), ("unetpp", 32, 256),
+                                      ("nnunet", 32, 256)])
+def test_forward_matches_the_storage_emulating_oracle(arch, B, S):
+    """Where the 1-6e-2 of test_forward_and_loss_parity comes from.  The same forward pass against the fp32 oracle with
+    nothing but the B200 path's bf16 STORAGE switched on (oracle/emulation.py: conv outputs, activations and weights
+    rounded to bf16, all arithmetic fp32): the kernels then agree with the checker an order of magnitude more closely
+    than the checker agrees with its own fp32 self, on every head -- the distance to the plain oracle is the price of
+    the storage format, not of the kernels.  The last two cases are BASELINE.json configs[1] / configs[2] at their real
+    shape (B = 32 @ 256 x 256); the oracle runs on the GPU as checker."""
+    from oracle import torch_oracle as O
+    from oracle.emulation import with_bf16_storage
+    ref, new = pair(arch)
+    emu = with_bf16_storage(ref, what=("y", "a", "w"))
+    img, *_ = O.synthetic_batch(B, S, S, device="cuda")
+    with torch.no_grad():
+        rl, ro = ref(img)
+        el, eo = emu(img)
+        nl, no = new(img)
+    worst = 0.0
+    for i, (a, e, r) in enumerate(zip(list(nl) + list(no), list(el) + list(eo), list(rl) + list(ro))):
+        d_emu, d_ref, floor = rel(a, e), rel(a, r), rel(e, r)
+        print(f"{arch} B{B} {S}: output {i}: CUDA vs bf16-storage oracle {d_emu:.2e} | CUDA vs fp32 oracle {d_ref:.2e} | "
+              f"bf16-storage oracle vs fp32 oracle {floor:.2e}")
+        worst = max(worst, d_emu)
+        assert d_emu < 1e-2, (i, d_emu)            # north_star's bf16 bar, against the checker that stores like we do
+        assert d_emu < 0.6 * max(floor, 2e-3) or d_emu < 3e-3, (i, d_emu, floor)
+    for a, e in zip(no, eo):
+        assert ((a > 0) == (e > 0)).float().mean().item() >= 0.999
+    for a, e in zip(nl, el):
+        assert torch.equal(a.argmax(1), e.argmax(1))
+
+
 @pytest.mark.parametrize("arch", ["unetpp", "nnunet", "bts"])
 def test_against_reference_golden_fixture(arch):
     """Same seed -> same init as the reference; outputs compared with what the reference modules themselves produced."""
