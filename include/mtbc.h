@@ -138,6 +138,9 @@ typedef struct {
   int32_t ld_k;   /* row length of dw_acc                   */
   int32_t k0;     /* column offset of this source           */
   int32_t splits; /* 0 = auto */
+  /* 0: bf16 views, tcgen05 kind::f16.  1: fp32 views (TF32 parity modes): the reduction runs in plain fp32 on the CUDA
+   * cores (exact products, fp32 accumulation) -- a checker-grade path, not a fast one. */
+  int32_t dtype;
 } mtbc_wgrad_desc;
 
 /* Weight gradient of a 3x3 Conv2d over a folded concatenation, ALL sources in one launch: dy is read once per pixel

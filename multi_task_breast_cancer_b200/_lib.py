@@ -46,7 +46,8 @@ class WgradTap(C.Structure):
 class WgradDesc(C.Structure):
     _fields_ = [("a_nviews", c_i32), ("a_views", ActView * 4), ("b_nviews", c_i32), ("b_views", ActView * 4),
                 ("ntaps", c_i32), ("taps", WgradTap * 9), ("W", c_i32), ("H", c_i32), ("N", c_i32),
-                ("dw_acc", c_vp), ("n_rows", c_i32), ("ld_k", c_i32), ("k0", c_i32), ("splits", c_i32)]
+                ("dw_acc", c_vp), ("n_rows", c_i32), ("ld_k", c_i32), ("k0", c_i32), ("splits", c_i32),
+                ("dtype", c_i32)]
 
 
 class WgradMultiDesc(C.Structure):

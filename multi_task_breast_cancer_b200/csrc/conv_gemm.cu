@@ -508,6 +508,115 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const __grid_constant__ Wgra
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ fp32 weight gradient
+// TF32 parity modes: dW[tap][co][k0 + ci] += sum_pixels A[pixel + (dh, dw)][ci] * B[pixel][co] in plain fp32 on the CUDA
+// cores (exact products).  32 (ci) x 32 (co) tile per block, 32 pixels per shared-memory step, 2 x 2 outputs per
+// thread, the pixel range split over blockIdx.z with fp32 atomics at the end.  Not a fast kernel: a checker-grade one.
+struct WgradF32Params {
+  const float* a[4];
+  const float* b[4];
+  int64_t a_sW[4], a_sH[4], a_sN[4], b_sW[4], b_sH[4], b_sN[4];
+  int16_t t_aview[9], t_adh[9], t_adw[9], t_bview[9];
+  int32_t ntaps, splits, aC, bC, W, H, N, n_rows, ld_k, k0;
+  float* dw;
+};
+
+__global__ void __launch_bounds__(256) wgrad_f32_kernel(const __grid_constant__ WgradF32Params p) {
+  __shared__ float xs[32][33], ds[32][33];
+  const int tap = blockIdx.z % p.ntaps, split = blockIdx.z / p.ntaps;
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  const int64_t P = static_cast<int64_t>(p.N) * p.H * p.W;
+  int64_t per = (P + p.splits - 1) / p.splits;
+  per = (per + 31) / 32 * 32;
+  const int64_t p_begin = split * per, p_end = p_begin + per < P ? p_begin + per : P;
+  const float* A = p.a[p.t_aview[tap]];
+  const float* B = p.b[p.t_bview[tap]];
+  const int av = p.t_aview[tap], bv = p.t_bview[tap], dh = p.t_adh[tap], dw_ = p.t_adw[tap];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int64_t p0 = p_begin; p0 < p_end; p0 += 32) {
+    for (int e = threadIdx.x; e < 1024; e += 256) {
+      const int px = e >> 5, c = e & 31;
+      const int64_t pp = p0 + px;
+      float xv = 0.f, dv = 0.f;
+      if (pp < p_end) {
+        const int w = static_cast<int>(pp % p.W);
+        const int h = static_cast<int>((pp / p.W) % p.H);
+        const int64_t n = pp / (static_cast<int64_t>(p.W) * p.H);
+        const int ha = h + dh, wa = w + dw_;
+        if (ha >= 0 && ha < p.H && wa >= 0 && wa < p.W && ci0 + c < p.aC)
+          xv = A[n * p.a_sN[av] + ha * p.a_sH[av] + wa * p.a_sW[av] + ci0 + c];
+        if (co0 + c < p.bC) dv = B[n * p.b_sN[bv] + h * p.b_sH[bv] + w * p.b_sW[bv] + co0 + c];
+      }
+      xs[px][c] = xv;
+      ds[px][c] = dv;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int q = 0; q < 32; ++q) {
+      const float x0 = xs[q][2 * tx], x1 = xs[q][2 * tx + 1], d0 = ds[q][2 * ty], d1 = ds[q][2 * ty + 1];
+      acc[0][0] = fmaf(x0, d0, acc[0][0]); acc[0][1] = fmaf(x0, d1, acc[0][1]);
+      acc[1][0] = fmaf(x1, d0, acc[1][0]); acc[1][1] = fmaf(x1, d1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int ci = ci0 + 2 * tx + i, co = co0 + 2 * ty + j;
+      if (ci < p.aC && co < p.bC)
+        atomicAdd(p.dw + (static_cast<int64_t>(tap) * p.n_rows + co) * p.ld_k + p.k0 + ci, acc[i][j]);
+    }
+}
+
+struct WgradF32Op : public OpBase {
+  WgradF32Params p;
+  dim3 grid;
+  double flops;
+  int launch(cudaStream_t st) override {
+    wgrad_f32_kernel<<<grid, 256, 0, st>>>(p);
+    return check_launch("wgrad_f32_kernel");
+  }
+  double op_flops() const override { return flops; }
+};
+
+static int wgrad_f32_create(const mtbc_wgrad_desc* d, OpBase** out) {
+  if (d->a_nviews < 1 || d->a_nviews > 4 || d->b_nviews < 1 || d->b_nviews > 4 || d->ntaps < 1 || d->ntaps > 9)
+    return set_error(MTBC_ERR_INVALID, "wgrad(fp32): bad view/tap counts");
+  WgradF32Op* op = new WgradF32Op();
+  WgradF32Params& p = op->p;
+  memset(&p, 0, sizeof(p));
+  for (int i = 0; i < d->a_nviews; ++i) {
+    p.a[i] = static_cast<const float*>(d->a_views[i].ptr);
+    p.a_sW[i] = d->a_views[i].sW; p.a_sH[i] = d->a_views[i].sH; p.a_sN[i] = d->a_views[i].sN;
+  }
+  for (int i = 0; i < d->b_nviews; ++i) {
+    p.b[i] = static_cast<const float*>(d->b_views[i].ptr);
+    p.b_sW[i] = d->b_views[i].sW; p.b_sH[i] = d->b_views[i].sH; p.b_sN[i] = d->b_views[i].sN;
+  }
+  for (int t = 0; t < d->ntaps; ++t) {
+    const mtbc_wgrad_tap& tp = d->taps[t];
+    if (tp.a_view < 0 || tp.a_view >= d->a_nviews || tp.b_view < 0 || tp.b_view >= d->b_nviews) { delete op; return set_error(MTBC_ERR_INVALID, "wgrad(fp32): tap %d view out of range", t); }
+    p.t_aview[t] = (int16_t)tp.a_view; p.t_adh[t] = (int16_t)tp.a_dh; p.t_adw[t] = (int16_t)tp.a_dw; p.t_bview[t] = (int16_t)tp.b_view;
+  }
+  p.ntaps = d->ntaps; p.aC = d->a_views[0].C; p.bC = d->b_views[0].C;
+  p.W = d->W; p.H = d->H; p.N = d->N; p.n_rows = d->n_rows; p.ld_k = d->ld_k; p.k0 = d->k0; p.dw = d->dw_acc;
+  const int tiles = ((p.aC + 31) / 32) * ((p.bC + 31) / 32) * d->ntaps;
+  const int64_t P = static_cast<int64_t>(d->N) * d->H * d->W;
+  int splits = d->splits > 0 ? d->splits : (148 * 4 + tiles - 1) / tiles;
+  const int64_t maxs = (P + 255) / 256;
+  if (splits > maxs) splits = static_cast<int>(maxs);
+  if (splits < 1) splits = 1;
+  if (static_cast<int64_t>(splits) * d->ntaps > 65535) splits = 65535 / d->ntaps;
+  p.splits = splits;
+  op->grid = dim3((p.aC + 31) / 32, (p.bC + 31) / 32, d->ntaps * splits);
+  op->flops = 2.0 * double(P) * double(p.aC) * double(p.bC) * d->ntaps;
+  *out = op;
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -709,6 +818,8 @@ int conv_gemm_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
 
 int wgrad_create(const mtbc_wgrad_desc* d, OpBase** out) {
   if (!d || !out) return set_error(MTBC_ERR_INVALID, "null argument");
+  if (d->dtype == 1) return wgrad_f32_create(d, out);
+  if (d->dtype != 0) return set_error(MTBC_ERR_INVALID, "wgrad: dtype %d", d->dtype);
   {
     int rc = wgrad_halo_try_create(d, out);
     if (rc <= 0) return rc;

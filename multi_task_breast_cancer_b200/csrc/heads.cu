@@ -49,27 +49,32 @@ __global__ void __launch_bounds__(256) head1x1_bwd_kernel(const T* __restrict__ 
   for (int k = 0; k < 8; ++k) wv[k] = (v * 8 + k) < C ? w[v * 8 + k] : 0.f;
   constexpr int U = 4;
   for (int64_t i0 = start; i0 < total; i0 += U * stride) {
-    V8 u[U], q[U];
+    Raw8<T> u[U], q[U];
     float g[U];
 #pragma unroll
     for (int j = 0; j < U; ++j) {
       const int64_t i = i0 + j * stride;
       if (i < total) {
-        u[j] = load8<T>(a + i * 8);
+        u[j].load(a + i * 8);
         g[j] = dl[i / cvec];
-        if (accumulate) q[j] = load8<T>(dA + i * 8);
+        if (accumulate) q[j].load(dA + i * 8);
       }
     }
 #pragma unroll
     for (int j = 0; j < U; ++j) {
       const int64_t i = i0 + j * stride;
       if (i >= total) break;
+      const V8 uv = u[j].unpack();
       V8 o;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        acc[k] = fmaf(g[j], u[j].f[k], acc[k]);
+        acc[k] = fmaf(g[j], uv.f[k], acc[k]);
         o.f[k] = g[j] * wv[k];
-        if (accumulate) o.f[k] += q[j].f[k];
+      }
+      if (accumulate) {
+        const V8 qv = q[j].unpack();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.f[k] += qv.f[k];
       }
       store8<T>(dA + i * 8, o);
       if (v == 0) accb += g[j];

@@ -519,9 +519,9 @@ __global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __rest
 // 8-channel groups OUTSIDE the pixel loop and fetched every 32-byte sector of the dense 48-byte rows up to three
 // times: 289 MB of DRAM traffic for a 100 MB tensor, 139 us).  The nine taps x 8 channels accumulate in registers over
 // the whole pixel range and are combined once: xor shuffles across the lanes of equal group, then shared-memory atomics.
-template <int G>
+template <int G, typename T>
 __global__ void __launch_bounds__(256) conv_first_wgrad_kernel(const float* __restrict__ x, int N, int Cin, int H,
-                                                               int W, const __nv_bfloat16* __restrict__ dy, int Cp,
+                                                               int W, const T* __restrict__ dy, int Cp,
                                                                int Cout, float* __restrict__ dw) {
   __shared__ float s_acc[9][64];
   const int ci = blockIdx.y;
@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(256) conv_first_wgrad_kernel(const float* __re
       const int hw = static_cast<int>(p32 - static_cast<uint32_t>(n) * hw32);
       const int h = hw / W, ww = hw - h * W;
       const float* xp = x + (static_cast<int64_t>(n) * Cin + ci) * HW;
-      const uint4 d0 = *reinterpret_cast<const uint4*>(dy + pix * Cp + g * 8);
+      const V8 d0 = load8<T>(dy + pix * Cp + g * 8);
       float xs[9];
 #pragma unroll
       for (int r = 0; r < 3; ++r)
@@ -557,15 +557,10 @@ __global__ void __launch_bounds__(256) conv_first_wgrad_kernel(const float* __re
           const int hh = h + r - 1, wc = ww + s - 1;
           xs[r * 3 + s] = (hh >= 0 && hh < H && wc >= 0 && wc < W) ? __ldg(xp + hh * W + wc) : 0.f;
         }
-      const uint32_t du[4] = {d0.x, d0.y, d0.z, d0.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = unpack_bf16x2(du[i]);
+      for (int i = 0; i < 8; ++i) {
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          acc[t][2 * i] = fmaf(xs[t], f.x, acc[t][2 * i]);
-          acc[t][2 * i + 1] = fmaf(xs[t], f.y, acc[t][2 * i + 1]);
-        }
+        for (int t = 0; t < 9; ++t) acc[t][i] = fmaf(xs[t], d0.f[i], acc[t][i]);
       }
     }
   }
@@ -723,12 +718,11 @@ int mtbc_conv_first_wgrad(const float* x, int32_t N, int32_t Cin, int32_t H, int
   int gx = static_cast<int>((total + (256 / G) * 16 - 1) / ((256 / G) * 16));
   if (gx > 148 * 4) gx = 148 * 4;
   if (gx < 1) gx = 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (G == 4)
-    conv_first_wgrad_kernel<4><<<dim3(gx, Cin), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, N, Cin, H, W, static_cast<const __nv_bfloat16*>(dy), Cp, Cout, dw);
+    MTBC_DISPATCH_ACT((conv_first_wgrad_kernel<4, T><<<dim3(gx, Cin), 256, 0, st>>>(x, N, Cin, H, W, static_cast<const T*>(dy), Cp, Cout, dw)));
   else
-    conv_first_wgrad_kernel<8><<<dim3(gx, Cin), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, N, Cin, H, W, static_cast<const __nv_bfloat16*>(dy), Cp, Cout, dw);
+    MTBC_DISPATCH_ACT((conv_first_wgrad_kernel<8, T><<<dim3(gx, Cin), 256, 0, st>>>(x, N, Cin, H, W, static_cast<const T*>(dy), Cp, Cout, dw)));
   return check_launch("conv_first_wgrad");
 }
 

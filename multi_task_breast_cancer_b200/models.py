@@ -87,13 +87,13 @@ class _PlanModule(nn.Module):
         self._plans: Dict[Tuple, Plan] = {}
         # Arithmetic mode (not part of the reference's constructor: set the attribute, call set_precision(), or export
         # MTBC_PRECISION / MTBC_DETERMINISTIC before building the model).  "bf16" is the product path; "tf32" and
-        # "tf32x3" are the forward-only parity modes of north_star ("1e-3 (TF32 mode)").
+        # "tf32x3" are the parity modes of north_star ("1e-3 (TF32 mode)"): correct forward + backward, not fast.
         self.precision = os.environ.get("MTBC_PRECISION", "bf16")
         self.deterministic = os.environ.get("MTBC_DETERMINISTIC", "0") not in ("", "0")
 
     def set_precision(self, precision: str = "bf16", deterministic: Optional[bool] = None):
-        """"bf16" (default, training + inference), "tf32" (fp32 storage, tcgen05 kind::tf32, inference only) or
-        "tf32x3" (same with the three-product split: fp32-grade results).  deterministic=True makes the forward pass
+        """"bf16" (default: the product path), "tf32" (fp32 storage, tcgen05 kind::tf32 convolutions) or "tf32x3" (same
+        with the three-product split: fp32-grade results; the mode the parity tests separate wiring from precision with).  deterministic=True makes the forward pass
         bit-reproducible (order-independent InstanceNorm statistics) at the price of one more read of every conv
         output."""
         from .plan import PRECISIONS
@@ -157,9 +157,6 @@ class _PlanModule(nn.Module):
 
     def _run(self, x: torch.Tensor):
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        if need_grad and self.precision != "bf16":
-            raise NotImplementedError(f"precision={self.precision!r} is a forward-only parity mode: call the model under "
-                                      "torch.no_grad() (training runs in bf16)")
         plan = self._get_plan(x, need_grad)
         with torch.cuda.device(x.device):
             if need_grad:

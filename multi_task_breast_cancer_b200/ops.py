@@ -185,9 +185,10 @@ def conv3x3_fwd_op(srcs: Sequence[Feat], wpack: torch.Tensor, out: Feat, bias: O
     return _create_gemm(d, [*(s.t for s in srcs), wpack, wpack_lo, out.t, bias, stat_sum, stat_sq], kind)
 
 
-def conv3x3_dgrad_op(dy: Feat, wd: torch.Tensor, dx: Feat, accumulate: bool, ksz: int = 3) -> Op:
+def conv3x3_dgrad_op(dy: Feat, wd: torch.Tensor, dx: Feat, accumulate: bool, ksz: int = 3,
+                     wd_lo: Optional[torch.Tensor] = None) -> Op:
     """wd: bf16 [ksz*ksz][dx.Ck][dy.Ck] (flipped taps, transposed channels) -> dx (+)= conv(dy, wd)."""
-    return conv3x3_fwd_op([dy], wd, dx, accumulate=accumulate, ksz=ksz, kind="conv3x3_dgrad")
+    return conv3x3_fwd_op([dy], wd, dx, accumulate=accumulate, ksz=ksz, kind="conv3x3_dgrad", wpack_lo=wd_lo)
 
 
 def conv3x3_dgrad_multi_op(dy: Feat, wd_all: torch.Tensor, dxs: Sequence[Feat], accumulates: Sequence[bool]) -> Op:
@@ -234,10 +235,12 @@ def convT_fwd_op(x: Feat, wf: torch.Tensor, out: Feat, k: int, bias: Optional[to
     return _create_gemm(d, [x.t, wf, wf_lo, out.t, bias], "convT_fwd")
 
 
-def convT_dgrad_op(dout: Feat, wd: torch.Tensor, dx: Feat, k: int, accumulate: bool) -> Op:
+def convT_dgrad_op(dout: Feat, wd: torch.Tensor, dx: Feat, k: int, accumulate: bool,
+                   wd_lo: Optional[torch.Tensor] = None) -> Op:
     """wd: bf16 [k*k][dx.Ck][dout.Ck]; dx (+)= sum_q dout_q * wd[q]."""
     assert wd.shape == (k * k, dx.Ck, dout.Ck)
     d = ConvGemmDesc()
+    _set_dtype(d, [dout, dx], wd, wd_lo)
     d.nviews = k * k
     for q in range(k * k):
         d.views[q] = _strided_view(dout, k, q // k, q % k)
@@ -247,7 +250,7 @@ def convT_dgrad_op(dout: Feat, wd: torch.Tensor, dx: Feat, k: int, accumulate: b
     d.W, d.H, d.N = dx.W, dx.H, dx.N
     d.epi_mode = 0; d.out = dx.t.data_ptr(); d.out_C = dx.Cp; d.up_k = 1; d.up_cp = dx.Ck
     d.bias = None; d.stat_sum = None; d.stat_sq = None; d.stat_C = 0; d.accumulate = int(accumulate)
-    return _create_gemm(d, [dout.t, wd, dx.t], "convT_dgrad")
+    return _create_gemm(d, [dout.t, wd, wd_lo, dx.t], "convT_dgrad")
 
 
 def conv3x3_wgrad_op(x: Feat, dy: Feat, dw_acc: torch.Tensor, k0: int, ksz: int = 3, splits: int = 0) -> Op:
@@ -265,6 +268,8 @@ def conv3x3_wgrad_op(x: Feat, dy: Feat, dw_acc: torch.Tensor, k0: int, ksz: int 
     d.ntaps = n
     d.W, d.H, d.N = dy.W, dy.H, dy.N
     d.dw_acc = dw_acc.data_ptr(); d.n_rows = dw_acc.shape[1]; d.ld_k = dw_acc.shape[2]; d.k0 = k0; d.splits = splits
+    assert x.fp32 == dy.fp32
+    d.dtype = 1 if x.fp32 else 0     # fp32 views: exact fp32 reduction on the CUDA cores (parity modes)
     h = C.c_void_p()
     _lib.check(_lib.load().mtbc_wgrad_create(C.byref(d), C.byref(h)), "conv3x3_wgrad")
     return Op(h, [x.t, dy.t, dw_acc], "conv3x3_wgrad")
@@ -301,6 +306,8 @@ def convT_wgrad_op(x: Feat, dout: Feat, dw_acc: torch.Tensor, k: int, splits: in
     d.ntaps = k * k
     d.W, d.H, d.N = x.W, x.H, x.N
     d.dw_acc = dw_acc.data_ptr(); d.n_rows = dw_acc.shape[1]; d.ld_k = dw_acc.shape[2]; d.k0 = 0; d.splits = splits
+    assert x.fp32 == dout.fp32
+    d.dtype = 1 if x.fp32 else 0
     h = C.c_void_p()
     _lib.check(_lib.load().mtbc_wgrad_create(C.byref(d), C.byref(h)), "convT_wgrad")
     return Op(h, [x.t, dout.t, dw_acc], "convT_wgrad")

@@ -163,15 +163,14 @@ class Plan:
     def __init__(self, B: int, H: int, W: int, device, params: Dict[str, torch.nn.Parameter], training: bool = True,
                  precision: str = "bf16", deterministic: bool = False):
         """precision: "bf16" = the product path (bf16 storage, tcgen05 kind::f16).  "tf32" / "tf32x3" = the parity modes
-        north_star names ("1e-3 (TF32 mode)"): fp32 storage everywhere, tcgen05 kind::tf32 convolutions through the
-        generic implicit-GEMM kernel, single pass or with the 3xTF32 split (fp32-grade products); forward only.
+        north_star names ("1e-3 (TF32 mode)"): fp32 storage everywhere, tcgen05 kind::tf32 convolutions and data
+        gradients through the generic implicit-GEMM kernel, single pass or with the 3xTF32 split (fp32-grade products),
+        weight gradients as exact fp32 reductions on the CUDA cores.  Checker-grade paths: correct, not fast.
         deterministic: InstanceNorm statistics come from an order-independent reduction (mtbc_in_stats_det) instead of
         the conv epilogues' fp32 atomics, so the forward pass is bit-identical from run to run."""
         global _build_mode
         if precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {PRECISIONS}")
-        if precision != "bf16" and training:
-            raise NotImplementedError("the TF32 parity modes are forward-only: run the model under torch.no_grad()")
         self.B, self.H, self.W, self.device = B, H, W, device
         self.params = params
         self.training = training
@@ -354,7 +353,7 @@ class Plan:
                 return blk
             acc = self._wg_accum(w, pk)
             o = None
-            if H % 16 == 0 and Wd % 8 == 0 and not os.environ.get("MTBC_NO_FUSED_WGRAD"):
+            if H % 16 == 0 and Wd % 8 == 0 and not self.fp32 and not os.environ.get("MTBC_NO_FUSED_WGRAD"):
                 try:   # one launch over every concat source: dy is read once per pixel tile
                     o = ops.conv3x3_wgrad_multi_op(feats, dy, acc, pk["offs"])
                 except _lib.MtbcError:
@@ -443,17 +442,20 @@ class Plan:
             wds = []
             c0 = 0
             for cs, cp in zip(pk["src_c"], pk["src_cp"]):
-                wd = torch.zeros(9, cp, Cp, dtype=torch.bfloat16, device=self.device)
-                self.pack_jobs.add(_lib.JOB_PACK_CONV, [Wt.shape[0], Wt.shape[1], 3, c0, cs, 0, 0, 0, cp, Cp],
-                                   Wt, None, wd)
+                wd = torch.zeros(9, cp, Cp, dtype=torch.float32 if self.fp32 else torch.bfloat16, device=self.device)
+                wd_lo = torch.zeros_like(wd) if self.precision == "tf32x3" else None
+                for part, dst in ((1 if self.fp32 else 0, wd), (2, wd_lo)):
+                    if dst is not None:
+                        self.pack_jobs.add(_lib.JOB_PACK_CONV, [Wt.shape[0], Wt.shape[1], 3, c0, cs, 0, 0, 0, cp, Cp,
+                                                                part], Wt, None, dst)
                 c0 += cs
-                wds.append(wd)
+                wds.append((wd, wd_lo) if self.fp32 else wd)
             pk[key] = wds
         return pk[key]
 
     def _emit_dgrad(self, blk, srcs, dy: Feat, w: str, pk: dict, name: str, Cout: int):
         N, H, Wd = dy.N, dy.H, dy.W
-        if len(srcs) > 1 and H % 16 == 0 and Wd % 8 == 0 and not os.environ.get("MTBC_NO_FUSED_DGRAD"):
+        if len(srcs) > 1 and H % 16 == 0 and Wd % 8 == 0 and not self.fp32 and not os.environ.get("MTBC_NO_FUSED_DGRAD"):
             grads = [s.grad() for s in srcs]
             try:
                 o = ops.conv3x3_dgrad_multi_op(dy, self._dgrad_pack(w, pk, True), grads, [s.g_init for s in srcs])
@@ -470,7 +472,8 @@ class Plan:
                 return
         for s, wd in zip(srcs, self._dgrad_pack(w, pk, False)):
             g = s.grad()
-            o = ops.conv3x3_dgrad_op(dy, wd, g, accumulate=s.g_init)
+            wd, wd_lo = wd if isinstance(wd, tuple) else (wd, None)
+            o = ops.conv3x3_dgrad_op(dy, wd, g, accumulate=s.g_init, wd_lo=wd_lo)
             self.tc_flops_bwd += o.flops
             blk.append(_mk_op(o, 2.0 * N * H * Wd * Cout * s.feat.C * 9,
                               f"{name} dgrad {N}x{H}x{Wd} {s.feat.C}<-{Cout} acc={int(s.g_init)}",
@@ -543,9 +546,11 @@ class Plan:
         out = self.new(f.N, f.H * k, f.W * k, Cout, name)
         cp = out.feat.Ck                    # GEMM columns per sub-pixel (the tensor itself may be denser: out.feat.Cp)
         wf = torch.zeros(1, k * k * cp, f.Ck, dtype=torch.float32 if self.fp32 else torch.bfloat16, device=self.device)
-        wd = torch.zeros(k * k, f.Ck, cp, dtype=torch.bfloat16, device=self.device) if self.training else None
-        wf_lo = torch.zeros_like(wf) if self.precision == "tf32x3" else None
-        for part, dst, dst1 in ((1 if self.fp32 else 0, wf, wd), (2, wf_lo, None)):
+        wd = torch.zeros(k * k, f.Ck, cp, dtype=wf.dtype, device=self.device) if self.training else None
+        x3 = self.precision == "tf32x3"
+        wf_lo = torch.zeros_like(wf) if x3 else None
+        wd_lo = torch.zeros_like(wd) if (x3 and wd is not None) else None
+        for part, dst, dst1 in ((1 if self.fp32 else 0, wf, wd), (2, wf_lo, wd_lo)):
             if dst is not None:
                 self.pack_jobs.add(_lib.JOB_PACK_CONVT, [Cin, Cout, k, cp, wf.shape[2], 0 if dst1 is None else wd.shape[1],
                                                          0 if dst1 is None else wd.shape[2], 0, 0, 0, part], Wt, dst, dst1)
@@ -573,7 +578,7 @@ class Plan:
                                   2.0 * out.g.N * out.g.H * out.g.W * Cout))
             self._mark_grad(w, b)
             g = x.grad()
-            o = ops.convT_dgrad_op(out.g, wd, g, k, accumulate=x.g_init)
+            o = ops.convT_dgrad_op(out.g, wd, g, k, accumulate=x.g_init, wd_lo=wd_lo)
             self.tc_flops_bwd += o.flops
             blk.append(_mk_op(o, t_flops, f"{name} convT dgrad {f.N}x{f.H}x{f.W} {Cin}<-{Cout}", t_bytes))
             x.g_init = True

