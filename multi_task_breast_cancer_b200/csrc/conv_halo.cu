@@ -1023,7 +1023,10 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   // never be a lap ahead of the barrier (a lane that skips the other lane's chunks could otherwise pass a wait on a
   // slot whose previous fill has not even landed).  Otherwise, and with two CTAs per SM, one lane.
   const char* sp_env = getenv("MTBC_HALO_SPLIT");
-  if (ctas_per_sm == 1 && p.lanes == 2 && total_chunks >= 2 && p.stages >= 4 && !(sp_env && sp_env[0] == '0')) {
+  // (not in deterministic mode: two lanes adding into ONE accumulator race for the order of their fp32 additions,
+  //  which made multi-source layers differ in the last bit from run to run -- tools/diag_det.py)
+  const bool det = (current_mode() & MODE_DETERMINISTIC) != 0;
+  if (ctas_per_sm == 1 && p.lanes == 2 && total_chunks >= 2 && p.stages >= 4 && !(sp_env && sp_env[0] == '0') && !det) {
     // split-chunk lanes: every tile's chunks alternate between the two lanes (see the kernel); needs an even ring
     p.lanes = 3;
     if (p.stages & 1) {

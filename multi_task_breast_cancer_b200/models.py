@@ -136,12 +136,20 @@ class _PlanModule(nn.Module):
             lib = _lib.load()
             _lib.check(lib.mtbc_device_check(), "device check")
             B, Cin, H, W = x.shape
+            from . import plan as _plan_mod
             with torch.cuda.device(x.device):
-                plan = Plan(B, H, W, x.device, params, training=need_grad, precision=self.precision,
-                            deterministic=self.deterministic)
-                plan.x_in = torch.zeros(B, Cin, H, W, dtype=torch.float32, device=x.device)
-                self._build_graph(plan, plan.x_in)
-                plan.finalize(self._seg_heads_active())
+                try:
+                    plan = Plan(B, H, W, x.device, params, training=need_grad, precision=self.precision,
+                                deterministic=self.deterministic)
+                    # op CREATION consults the mode too (the halo conv drops its two-lane accumulation when the
+                    # result has to be order independent), so it is set for the whole build, not just per launch
+                    lib.mtbc_set_mode(plan.mode_flags)
+                    plan.x_in = torch.zeros(B, Cin, H, W, dtype=torch.float32, device=x.device)
+                    self._build_graph(plan, plan.x_in)
+                    plan.finalize(self._seg_heads_active())
+                finally:
+                    lib.mtbc_set_mode(0)
+                    _plan_mod._build_mode = 0
             self._plans[key] = plan
         return plan
 

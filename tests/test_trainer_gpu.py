@@ -68,7 +68,10 @@ def test_train_one_epoch_bookkeeping_is_exact_and_losses_match_oracle(use_graph)
         gt, pr = O.class_lists([seen[i][2]], host[i][2].cuda(), gt, pr)
     exp_acc, exp_f1 = O.classification_scores(gt, pr)
     assert abs(loss - exp_loss) < 1e-6 * abs(exp_loss)
-    assert abs(dice - exp_dice) < 1e-12 and abs(acc - exp_acc) < 1e-12 and abs(f1w - exp_f1) < 1e-12
+    # hard Dice: the kernel thresholds logit > 0, the reference sigmoid(logit) > .5 -- the same set except for logits in
+    # (0, ~1.2e-7], where fp32 sigmoid rounds to exactly 0.5 (seen once: one pixel of 245 760); integer-exactness of the
+    # counts against `logit > 0` is asserted in test_models_gpu.py::test_prediction_refinement_bit_exact
+    assert abs(dice - exp_dice) < 2e-5 and abs(acc - exp_acc) < 1e-12 and abs(f1w - exp_f1) < 1e-12
     # against the fp32 oracle running the reference loop on the same data
     opt = O.make_optimizer(ref, 1e-4)
     rl, rd, ra, rf = O.train_one_epoch(ref, opt, [tuple(t.cuda() for t in b) for b in host])
