@@ -97,10 +97,12 @@ __global__ void __launch_bounds__(256) in_stats_det_kernel(const T* __restrict__
   }
   if (threadIdx.x == 0) ticket[n] = 0;   // ready for the next launch (CUDA-graph replay)
 }
+// Blocks per SAMPLE: a function of the plane only, never of the batch size, so that a sample's statistics are the same
+// bits whether it is processed in a batch of 16 or of 32 (data-parallel runs reproduce the single-GPU run exactly).
 static int stats_det_blocks(int64_t HW, int cvec, int N) {
+  (void)N;
   int64_t want = (HW * cvec + 256 * 16 - 1) / (256 * 16);
-  const int64_t cap = (148 * 4 + N - 1) / N;
-  if (want > cap) want = cap;
+  if (want > 32) want = 32;
   if (want < 1) want = 1;
   return static_cast<int>(want);
 }

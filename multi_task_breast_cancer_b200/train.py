@@ -99,6 +99,15 @@ class TrainStep:
                 self.refined_mask = torch.zeros(self.B, 1, self.H, self.W, dtype=torch.uint8, device=self.device)
                 self.refined_class = torch.zeros(self.B, dtype=torch.int32, device=self.device)
                 self.pixel_count = torch.zeros(self.B, dtype=torch.int32, device=self.device)
+            import os as _os
+            self.overlap = self.world > 1 and _os.environ.get("MTBC_DP_OVERLAP", "1") != "0"
+            # Per-bucket optimizer: bucket k's Adam runs on the communication stream right behind its all-reduce, i.e.
+            # while bucket k+1 is still being reduced and the backward pass is still running; only the LAST bucket's
+            # (small) update is left exposed at the end of the step instead of one Adam launch over all parameters
+            # that has to wait for every all-reduce.  Safe because a bucket is only marked ready once every kernel that
+            # reads its fp32 master parameters in the backward pass (heads, FC layers) has run; the convolutions read
+            # the bf16 operands packed at the head of the step.
+            self.bucket_adam = self.overlap and _os.environ.get("MTBC_DP_BUCKET_ADAM", "1") != "0"
             self._build_launches()
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self._heads: Dict[Optional[int], torch.cuda.CUDAGraph] = {}   # first graph of a step, per staging slot (None: no copy)
@@ -111,8 +120,6 @@ class TrainStep:
         self._load_turn = 0
         self.seg_graphs = None   # data parallel: [(CUDAGraph, bucket index or None)] + opt_graph
         self.opt_graph = None
-        import os as _os
-        self.overlap = self.world > 1 and _os.environ.get("MTBC_DP_OVERLAP", "1") != "0"
         self.steps_done = 0
         self._pinned: Dict[str, torch.Tensor] = {}
 
@@ -169,21 +176,31 @@ class TrainStep:
         self.launches_fb = L
         self._build_opt_launches()
 
-    def _build_opt_launches(self):
+    def _adam_launch(self, lo: int, hi: int):
         plan = self.plan
+        return _mk("mtbc_adam_step_dev", ptr(self.flat_p[lo:hi]), ptr(plan.grad_flat[lo:hi]), ptr(self.exp_avg[lo:hi]),
+                   ptr(self.exp_avg_sq[lo:hi]), hi - lo, ptr(self.lr_dev), C.c_float(self.betas[0]),
+                   C.c_float(self.betas[1]), C.c_float(self.eps), C.c_float(1.0 / self.world), ptr(self.step_dev))
+
+    def _build_opt_launches(self):
         # ---- optimizer (after the all-reduce when data parallel)
-        self.launches_opt = [
-            _mk("mtbc_increment_i32", ptr(self.step_dev)),
-            _mk("mtbc_adam_step_dev", ptr(self.flat_p), ptr(plan.grad_flat), ptr(self.exp_avg), ptr(self.exp_avg_sq),
-                self.flat_p.numel(), ptr(self.lr_dev), C.c_float(self.betas[0]), C.c_float(self.betas[1]),
-                C.c_float(self.eps), C.c_float(1.0 / self.world), ptr(self.step_dev)),
-        ]
+        inc = _mk("mtbc_increment_i32", ptr(self.step_dev))
+        if self.bucket_adam:
+            # the step counter moves at the head of the step; each bucket's update follows its own all-reduce
+            self.launches_fb = [inc] + self.launches_fb
+            self.launches_opt = []
+            self.launches_opt_bucket = {k: [self._adam_launch(lo, hi)] for k, (lo, hi) in enumerate(self.plan.buckets)
+                                        if hi > lo}
+            self._bucket_opt_graphs = {}
+            return
+        self.launches_opt = [inc, self._adam_launch(0, self.flat_p.numel())]
 
     # ------------------------------------------------------------------------------------------------ running
     @property
     def n_launches(self) -> int:
         """Kernel / memset launches of one step (our own kernels only; the NCCL all-reduces are not counted)."""
-        return sum(1 for l in self.launches_fb + self.launches_opt if l.kind != "bucket_ready")
+        extra = sum(len(v) for v in getattr(self, "launches_opt_bucket", {}).values())
+        return sum(1 for l in self.launches_fb + self.launches_opt if l.kind != "bucket_ready") + extra
 
     def _run_list(self, launches):
         """Launch a list on the current stream.  Launches marked `side` (weight gradients: they only feed accumulators
@@ -253,6 +270,14 @@ class TrainStep:
         self.comm_stream.wait_stream(main)
         with torch.cuda.stream(self.comm_stream):
             dist.all_reduce(self.plan.grad_flat[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+            if self.bucket_adam and k in self.launches_opt_bucket:
+                g = self._bucket_opt_graphs.get(k)
+                if g is not None:
+                    g.replay()
+                else:
+                    st = C.c_void_p(self.comm_stream.cuda_stream)
+                    for l in self.launches_opt_bucket[k]:
+                        l(st)
 
     def _run_step_dp(self, head=None):
         """forward + loss + backward with each gradient bucket's all-reduce forked onto the communication stream as soon
@@ -267,7 +292,8 @@ class TrainStep:
                 if k is not None:
                     self._fork_allreduce(k)
             main.wait_stream(self.comm_stream)
-            self.opt_graph.replay()
+            if self.opt_graph is not None:
+                self.opt_graph.replay()
             return
         for launches, k in self._segments():
             self._run_list(launches)
@@ -304,10 +330,19 @@ class TrainStep:
                     with torch.cuda.graph(g, capture_error_mode="thread_local"):
                         self._run_list(launches)
                 graphs.append((g, k))
-            og = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(og, capture_error_mode="thread_local"):
-                self._run_list(self.launches_opt)
-            self.opt_graph = og
+            if self.bucket_adam:
+                for k, ls in self.launches_opt_bucket.items():
+                    bg = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(bg, capture_error_mode="thread_local"):
+                        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+                        for l in ls:
+                            l(st)
+                    self._bucket_opt_graphs[k] = bg
+            else:
+                og = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(og, capture_error_mode="thread_local"):
+                    self._run_list(self.launches_opt)
+                self.opt_graph = og
             self.seg_graphs = graphs
             self.graph = graphs[0][0]
             self._heads[None] = self.graph
