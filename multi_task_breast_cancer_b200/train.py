@@ -101,13 +101,16 @@ class TrainStep:
                 self.pixel_count = torch.zeros(self.B, dtype=torch.int32, device=self.device)
             import os as _os
             self.overlap = self.world > 1 and _os.environ.get("MTBC_DP_OVERLAP", "1") != "0"
-            # Per-bucket optimizer: bucket k's Adam runs on the communication stream right behind its all-reduce, i.e.
-            # while bucket k+1 is still being reduced and the backward pass is still running; only the LAST bucket's
-            # (small) update is left exposed at the end of the step instead of one Adam launch over all parameters
-            # that has to wait for every all-reduce.  Safe because a bucket is only marked ready once every kernel that
-            # reads its fp32 master parameters in the backward pass (heads, FC layers) has run; the convolutions read
-            # the bf16 operands packed at the head of the step.
-            self.bucket_adam = self.overlap and _os.environ.get("MTBC_DP_BUCKET_ADAM", "1") != "0"
+            # Per-bucket optimizer (MTBC_DP_BUCKET_ADAM=1, off by default): bucket k's Adam runs on the communication
+            # stream right behind its all-reduce, i.e. while bucket k+1 is still being reduced and the backward pass is
+            # still running; only the last bucket's update is left exposed instead of one Adam launch over all
+            # parameters that waits for every all-reduce.  Safe because a bucket is only marked ready once every kernel
+            # that reads its fp32 master parameters in the backward pass (heads, FC layers) has run; the convolutions
+            # read the bf16 operands packed at the head of the step.  MEASURED, same 8 x B200 box, back to back
+            # (profiles/r02g_bench_n8*.json): 11.96 ms/step with it, 11.87 ms without -- the four small Adam launches
+            # compete with the backward kernels for HBM and sit between the all-reduces on the communication stream,
+            # which costs more than the ~0.05 ms of exposed tail it removes.  Kept as a switch, not as the default.
+            self.bucket_adam = self.overlap and _os.environ.get("MTBC_DP_BUCKET_ADAM", "0") == "1"
             self._build_launches()
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self._heads: Dict[Optional[int], torch.cuda.CUDAGraph] = {}   # first graph of a step, per staging slot (None: no copy)
