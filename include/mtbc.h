@@ -213,6 +213,33 @@ typedef struct {
 int mtbc_param_jobs_create(const mtbc_param_job* jobs, int32_t n, mtbc_op** out);
 
 /* ------------------------------------------------------------------------------------------------------------- */
+/* Sibling backbone ResidualUNet (src/models/segmentation/ResidualUNet.py): BatchNorm2d, residual add, F.dropout,    */
+/* stride-2 3x3 convolutions.  Element-type generic (mtbc_set_mode), memory bound.                                  */
+
+/* out = a + b over n elements (n % 8 == 0): `path + residual` (ResidualUNet.py:69,155). */
+int mtbc_add(const void* a, const void* b, void* out, int64_t n, void* stream);
+/* dst = src (accumulate == 0) or dst += src: hands a gradient to a tensor that may already hold one. */
+int mtbc_accumulate(const void* src, void* dst, int64_t n, int32_t accumulate, void* stream);
+/* F.dropout(x, p) (ResidualUNet.py:61,139,145; called with the default training=True, i.e. active in eval mode too):
+ * out = x * keep / (1 - p).  keep (one byte per element) is drawn from a counter-based generator keyed on (seed,
+ * counter[0], layer, element) and written to `mask`; external_mask != 0 reads `mask` instead (parity tests). */
+int mtbc_dropout_fwd(const void* x, void* out, uint8_t* mask, int64_t n, float p, uint64_t seed, const int32_t* counter,
+                     int32_t layer, int32_t external_mask, void* stream);
+int mtbc_dropout_bwd(const void* g, const uint8_t* mask, void* out, int64_t n, float p, int32_t accumulate, void* stream);
+/* out (N, 2H, 2W, Cp) = dy on the even lattice, zero elsewhere: the data gradient of a stride-2 3x3 convolution
+ * (ResidualUNet.py:115-131) is the stride-1 data gradient of this tensor. */
+int mtbc_zero_stuff2(const void* dy, int32_t N, int32_t H, int32_t W, int32_t Cp, void* out, void* stream);
+/* nn.BatchNorm2d (eps 1e-5, momentum 0.1) on top of the InstanceNorm passes: pools the per-(sample, channel) sums over
+ * the batch in place (training: batch average + running-statistics update with the unbiased variance +
+ * num_batches_tracked; eval: rows synthesised from the running statistics), after which mtbc_in_apply normalises with
+ * the batch / running statistics.  Backward: mtbc_in_bwd_reduce, mtbc_bn_pool_bwd (adds dgamma / dbeta from the
+ * un-pooled totals, then pools; eval: zeroes the sums), mtbc_in_bwd_apply with dgamma = dbeta = NULL. */
+int mtbc_bn_pool_fwd(float* stat_sum, float* stat_sq, int32_t N, int32_t Cp, int32_t C, int64_t HW, int32_t training,
+                     float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked, void* stream);
+int mtbc_bn_pool_bwd(float* s1, float* s2, int32_t N, int32_t Cp, int32_t C, int32_t training, float* dgamma,
+                     float* dbeta, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------- */
 /* First layer: Conv2d 3x3 with Cin <= 4 on the fp32 NCHW input image (K = 9*Cin is too small for a tensor tile).  */
 /* Replaces conv_0_0.conv_0 / encoder1.ConvInNormLRelu1.Conv forward + weight gradient (no data gradient: the image
  * needs none, training_multitask.py:82-90).

@@ -85,6 +85,13 @@ _SIGS = {
     "mtbc_unpack_convT_wgrad": [c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp],
     "mtbc_conv_first_fwd": [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp],
     "mtbc_conv_first_wgrad": [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp],
+    "mtbc_add": [c_vp, c_vp, c_vp, c_i64, c_vp],
+    "mtbc_accumulate": [c_vp, c_vp, c_i64, c_i32, c_vp],
+    "mtbc_dropout_fwd": [c_vp, c_vp, c_vp, c_i64, c_f32, C.c_uint64, c_vp, c_i32, c_i32, c_vp],
+    "mtbc_dropout_bwd": [c_vp, c_vp, c_vp, c_i64, c_f32, c_i32, c_vp],
+    "mtbc_zero_stuff2": [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp],
+    "mtbc_bn_pool_fwd": [c_vp, c_vp, c_i32, c_i32, c_i32, c_i64, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp],
+    "mtbc_bn_pool_bwd": [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp],
     "mtbc_in_stats": [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp],
     "mtbc_in_apply": [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_f32, c_f32, c_vp, c_vp,
                       c_vp, c_vp, c_vp],

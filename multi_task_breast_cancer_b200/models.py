@@ -119,6 +119,10 @@ class _PlanModule(nn.Module):
     def _seg_heads_active(self) -> Optional[List[bool]]:
         return None
 
+    def _plan_key_extra(self) -> Tuple:
+        """Anything else a plan bakes in (ResidualUNet: BatchNorm2d train / eval mode)."""
+        return ()
+
     def _get_plan(self, x: torch.Tensor, need_grad: bool) -> Plan:
         if not x.is_cuda:
             raise _lib.MtbcError("multi_task_breast_cancer_b200 runs on CUDA sm_100a only: move the model and the input to "
@@ -127,7 +131,7 @@ class _PlanModule(nn.Module):
             raise ValueError("expected a float32 (B, C, H, W) image batch")
         params = self._named_params()
         sig = tuple(p.data_ptr() for p in params.values())
-        key = (tuple(x.shape), x.device.index, need_grad, sig, self.precision, self.deterministic)
+        key = (tuple(x.shape), x.device.index, need_grad, sig, self.precision, self.deterministic) + self._plan_key_extra()
         plan = self._plans.get(key)
         if plan is None:
             # drop plans built for stale parameter storage (e.g. after .to())
@@ -667,6 +671,138 @@ class BTSUNet(_PlainUNetBase):
         return seg if self.deep_supervision else seg[-1]
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+class _RUInBlock(nn.Module):
+    """Parameter container of ResidualUNet.py:14-71 (registration order = the reference's, so that one seed gives one
+    initialisation)."""
+
+    def __init__(self, channel_in, channel_out):
+        super().__init__()
+        self.conv1 = nn.Conv2d(channel_in, channel_out, kernel_size=3, padding=1)
+        self.bn1 = nn.BatchNorm2d(channel_out)
+        self.conv2 = nn.Conv2d(channel_out, channel_out, kernel_size=3, padding=1)
+        self.conv3 = nn.Conv2d(channel_in, channel_out, kernel_size=3, padding=1)
+        self.bn3 = nn.BatchNorm2d(channel_out)
+
+
+class _RUResBlock(nn.Module):
+    """ResidualUNet.py:74-157: bn1 -> lrelu -> dropout -> conv1 (stride 2 when downsampling) -> bn2 -> lrelu -> dropout
+    -> conv2, plus the residual conv3 -> bn3."""
+
+    def __init__(self, channel_in, downsample=False):
+        super().__init__()
+        cout, st = (2 * channel_in, 2) if downsample else (channel_in, 1)
+        self.stride = st
+        self.bn1 = nn.BatchNorm2d(channel_in)
+        self.conv1 = nn.Conv2d(channel_in, cout, kernel_size=3, stride=st, padding=1)
+        self.bn2 = nn.BatchNorm2d(cout)
+        self.conv2 = nn.Conv2d(cout, cout, kernel_size=3, padding=1)
+        self.conv3 = nn.Conv2d(channel_in, cout, kernel_size=3, stride=st, padding=1)
+        self.bn3 = nn.BatchNorm2d(cout)
+
+
+class _RUEncoder(nn.Module):
+    def __init__(self, bf):
+        super().__init__()
+        self.down_block2 = _RUResBlock(bf, True)
+        self.down_block3 = _RUResBlock(bf * 2, True)
+        self.down_block4 = _RUResBlock(bf * 4, True)
+
+
+class _RUDecoder(nn.Module):
+    """ResidualUNet.py:195-269.  The 1x1 convs conv3 / conv2 / conv1 belong to the skip-connected variant (`seg_path`,
+    :298-339); ResidualUNet.forward (:356-362) never calls them, so they exist in the state_dict and get no gradient."""
+
+    def __init__(self, bf):
+        super().__init__()
+        self.upsample3 = nn.ConvTranspose2d(bf * 8, bf * 4, kernel_size=2, stride=2)
+        self.conv3 = nn.Conv2d(bf * 8, bf * 4, kernel_size=1)
+        self.up_block3 = _RUResBlock(bf * 4)
+        self.upsample2 = nn.ConvTranspose2d(bf * 4, bf * 2, kernel_size=2, stride=2)
+        self.conv2 = nn.Conv2d(bf * 4, bf * 2, kernel_size=1)
+        self.up_block2 = _RUResBlock(bf * 2)
+        self.upsample1 = nn.ConvTranspose2d(bf * 2, bf, kernel_size=2, stride=2)
+        self.conv1 = nn.Conv2d(bf * 2, bf, kernel_size=1)
+        self.up_block1 = _RUResBlock(bf)
+
+
+class _RUOut(nn.Module):
+    def __init__(self, bf, n_classes):
+        super().__init__()
+        self.conv = nn.Conv2d(bf, n_classes, kernel_size=1)
+
+
+class ResidualUNet(_PlanModule):
+    """Residual U-Net (reference src/models/segmentation/ResidualUNet.py:342-362): in_block -> three stride-2 residual
+    blocks -> three (ConvTranspose2d k2 s2 -> residual block) stages WITHOUT skip connections -> 1x1 conv.  The only
+    model of the repo with BatchNorm2d (batch statistics + running statistics in training, running statistics in eval),
+    stride-2 3x3 convs and F.dropout(p=0.2) -- which the reference calls with its default training=True, so the masks
+    are drawn in eval mode as well.  Returns the mask logits (B, regions, H, W)."""
+
+    name = "Residual UNet"
+    _slope = 0.01          # F.leaky_relu default
+    _p_drop = 0.2
+
+    def __init__(self, sequences=1, regions=1, width=24):
+        super().__init__()
+        if regions != 1:
+            raise NotImplementedError("mask heads project to one region (reference: regions=1)")
+        if width % 8:
+            raise NotImplementedError("width must be a multiple of 8 (16-byte channel vectors)")
+        self.in_block = _RUInBlock(sequences, width)
+        self.encoder = _RUEncoder(width)
+        self.decoder = _RUDecoder(width)
+        self.out_block = _RUOut(width, regions)
+        self._external_dropout = False      # parity tests: masks are handed in (plan.dropout_masks) instead of drawn
+        self._init_runtime()
+
+    def _plan_key_extra(self):
+        return (bool(self.training), bool(self._external_dropout))
+
+    def _bn(self, plan, x, mod, prefix, slope, p, name, stats=None):
+        return plan.bn_act(x, mod, prefix, slope, p, name, stats=stats, training=self.training)
+
+    def _res_block(self, plan, x, blk: _RUResBlock, prefix):
+        a = self._bn(plan, x, blk.bn1, prefix + ".bn1", self._slope, self._p_drop, prefix + ".a1")
+        y, s, q = plan.conv_plain([a], prefix + ".conv1.weight", prefix + ".conv1.bias", prefix + ".conv1",
+                                  stride=blk.stride, stats=True)
+        b = self._bn(plan, y, blk.bn2, prefix + ".bn2", self._slope, self._p_drop, prefix + ".a2", stats=(s, q))
+        path, _, _ = plan.conv_plain([b], prefix + ".conv2.weight", prefix + ".conv2.bias", prefix + ".conv2")
+        y3, s3, q3 = plan.conv_plain([x], prefix + ".conv3.weight", prefix + ".conv3.bias", prefix + ".conv3",
+                                     stride=blk.stride, stats=True)
+        res = self._bn(plan, y3, blk.bn3, prefix + ".bn3", 1.0, 0.0, prefix + ".res", stats=(s3, q3))
+        return plan.add(path, res, prefix + ".out")
+
+    def _build_graph(self, plan: Plan, x_in: torch.Tensor):
+        B, Cin, H, W = x_in.shape
+        if H % 128 or W % 16 or Cin > 4:
+            raise ValueError("ResidualUNet on sm_100a needs H % 128 == 0, W % 16 == 0 and at most 4 input channels")
+        plan.dropout_external = bool(self._external_dropout)
+        ib = self.in_block
+        y1, s1, q1 = plan.conv_plain(None, "in_block.conv1.weight", "in_block.conv1.bias", "in_block.conv1", stats=True,
+                                     first_input=x_in)
+        a1 = self._bn(plan, y1, ib.bn1, "in_block.bn1", self._slope, self._p_drop, "in_block.a1", stats=(s1, q1))
+        path, _, _ = plan.conv_plain([a1], "in_block.conv2.weight", "in_block.conv2.bias", "in_block.conv2")
+        y3, s3, q3 = plan.conv_plain(None, "in_block.conv3.weight", "in_block.conv3.bias", "in_block.conv3", stats=True,
+                                     first_input=x_in)
+        res = self._bn(plan, y3, ib.bn3, "in_block.bn3", 1.0, 0.0, "in_block.res", stats=(s3, q3))
+        l1 = plan.add(path, res, "down_level1")
+        l2 = self._res_block(plan, l1, self.encoder.down_block2, "encoder.down_block2")
+        l3 = self._res_block(plan, l2, self.encoder.down_block3, "encoder.down_block3")
+        codes = self._res_block(plan, l3, self.encoder.down_block4, "encoder.down_block4")
+        up3 = plan.convT(codes, "decoder.upsample3.weight", "decoder.upsample3.bias", 2, "up3")
+        u3 = self._res_block(plan, up3, self.decoder.up_block3, "decoder.up_block3")
+        up2 = plan.convT(u3, "decoder.upsample2.weight", "decoder.upsample2.bias", 2, "up2")
+        u2 = self._res_block(plan, up2, self.decoder.up_block2, "decoder.up_block2")
+        up1 = plan.convT(u2, "decoder.upsample1.weight", "decoder.upsample1.bias", 2, "up1")
+        u1 = self._res_block(plan, up1, self.decoder.up_block1, "decoder.up_block1")
+        plan.head1x1(u1, "out_block.conv.weight", "out_block.conv.bias")
+
+    def forward(self, x):
+        _, seg = self._run(x)
+        return seg[-1]
+
+
 # ======================================================================================================================
 # single-task siblings (SURVEY 8f row f4): classification-only graphs (encoder + class branch of the multi-task parents)
 # ======================================================================================================================
@@ -854,13 +990,16 @@ def init_classification_model(architecture: str, sequences: int = 1, n_classes: 
 
 def init_segmentation_model(architecture: str, sequences: int = 1, regions: int = 1, width: int = 48, save_folder=None,
                             deep_supervision: bool = False) -> nn.Module:
-    """The two branches of src/utils/experiment_init.py:26-92 whose graphs are subsets of the multi-task ones."""
+    """The reference-local branches of src/utils/experiment_init.py:26-92 (the MONAI networks of that factory are
+    third-party models outside this repo's path)."""
     if architecture == "BTSUNet":
         return BTSUNet(sequences=sequences, regions=regions, width=width, deep_supervision=deep_supervision)
     if architecture == "nnUNet":
         return nnUNet2021(sequences=sequences, regions=regions)
+    if architecture == "ResidualUNet":
+        return ResidualUNet(sequences=sequences, regions=regions, width=width)
     raise NotImplementedError(f"segmentation architecture {architecture!r} is outside the accelerated path "
-                              "(MONAI UNet / AttentionUnet / SwinUNETR / SegResNet, ResidualUNet)")
+                              "(MONAI UNet / AttentionUnet / SwinUNETR / SegResNet)")
 
 
 def init_multitask_model(architecture: str, sequences: int = 1, regions: int = 1, n_classes: int = 2, width: int = 48,

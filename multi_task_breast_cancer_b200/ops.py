@@ -185,6 +185,68 @@ def conv3x3_fwd_op(srcs: Sequence[Feat], wpack: torch.Tensor, out: Feat, bias: O
     return _create_gemm(d, [*(s.t for s in srcs), wpack, wpack_lo, out.t, bias, stat_sum, stat_sq], kind)
 
 
+# stride-2 3x3 convolution (ResidualUNet.py:115-131): tap row r reads input row 2h + r - 1, i.e. the odd sub-lattice
+# shifted by -1 (r = 0), the even one (r = 1) or the odd one (r = 2); likewise for columns.  Four strided views of the
+# input and nine (view, shift) segments turn it into the generic implicit GEMM, zero padding included (TMA zero fill).
+_S2 = {0: (1, -1), 1: (0, 0), 2: (1, 0)}
+
+
+def conv3x3_s2_fwd_op(x: Feat, wpack: torch.Tensor, out: Feat, bias: Optional[torch.Tensor] = None,
+                      stat_sum: Optional[torch.Tensor] = None, stat_sq: Optional[torch.Tensor] = None,
+                      wpack_lo: Optional[torch.Tensor] = None) -> Op:
+    """out (N, H/2, W/2) = conv3x3(x, stride 2, padding 1).  wpack: [9][out.Ck][x.Ck] as for the stride-1 conv."""
+    assert x.H % 2 == 0 and x.W % 2 == 0 and (out.H, out.W) == (x.H // 2, x.W // 2)
+    assert wpack.shape == (9, out.Ck, x.Ck), (wpack.shape, (9, out.Ck, x.Ck))
+    d = ConvGemmDesc()
+    _set_dtype(d, [x, out], wpack, wpack_lo)
+    d.nviews = 4
+    for i in range(2):
+        for j in range(2):
+            d.views[i * 2 + j] = _strided_view(x, 2, i, j)
+    n = 0
+    for r in range(3):
+        for c in range(3):
+            (i, dh), (j, dw) = _S2[r], _S2[c]
+            d.seg[n] = GemmSeg(i * 2 + j, dh, dw, 0, r * 3 + c)
+            n += 1
+    d.nseg = n
+    d.wpack = wpack.data_ptr(); d.w_ntaps = 9; d.w_ktot = x.Ck; d.ncols = out.Ck
+    d.W, d.H, d.N = out.W, out.H, out.N
+    d.epi_mode = 0; d.out = out.t.data_ptr(); d.out_C = out.Cp; d.up_k = 1; d.up_cp = out.Ck
+    d.bias = None if bias is None else bias.data_ptr()
+    d.stat_sum = None if stat_sum is None else stat_sum.data_ptr()
+    d.stat_sq = None if stat_sq is None else stat_sq.data_ptr()
+    d.stat_C = out.Cp
+    d.accumulate = 0
+    d.nouts = 0
+    return _create_gemm(d, [x.t, wpack, wpack_lo, out.t, bias, stat_sum, stat_sq], "conv3x3_s2_fwd")
+
+
+def conv3x3_s2_wgrad_op(x: Feat, dy: Feat, dw_acc: torch.Tensor, splits: int = 0) -> Op:
+    """Weight gradient of the stride-2 conv: dw_acc fp32 [9][dy.Ck][x.Ck]; the reduction runs over dy's pixel grid."""
+    assert dw_acc.dtype == torch.float32 and dw_acc.shape == (9, dy.Ck, x.Ck)
+    d = WgradDesc()
+    d.a_nviews = 4
+    for i in range(2):
+        for j in range(2):
+            d.a_views[i * 2 + j] = _strided_view(x, 2, i, j)
+    d.b_nviews = 1; d.b_views[0] = _view(dy)
+    n = 0
+    for r in range(3):
+        for c in range(3):
+            (i, dh), (j, dw) = _S2[r], _S2[c]
+            d.taps[n] = WgradTap(i * 2 + j, dh, dw, 0)
+            n += 1
+    d.ntaps = n
+    d.W, d.H, d.N = dy.W, dy.H, dy.N
+    d.dw_acc = dw_acc.data_ptr(); d.n_rows = dw_acc.shape[1]; d.ld_k = dw_acc.shape[2]; d.k0 = 0; d.splits = splits
+    assert x.fp32 == dy.fp32
+    d.dtype = 1 if x.fp32 else 0
+    h = C.c_void_p()
+    _lib.check(_lib.load().mtbc_wgrad_create(C.byref(d), C.byref(h)), "conv3x3_s2_wgrad")
+    return Op(h, [x.t, dy.t, dw_acc], "conv3x3_s2_wgrad")
+
+
 def conv3x3_dgrad_op(dy: Feat, wd: torch.Tensor, dx: Feat, accumulate: bool, ksz: int = 3,
                      wd_lo: Optional[torch.Tensor] = None) -> Op:
     """wd: bf16 [ksz*ksz][dx.Ck][dy.Ck] (flipped taps, transposed channels) -> dx (+)= conv(dy, wd)."""

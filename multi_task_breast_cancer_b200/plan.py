@@ -217,6 +217,11 @@ class Plan:
         self.tensors: Dict[str, PTensor] = {}  # name -> activation (debug / tests)
         self.debug: Dict[str, Feat] = {}
         self.param_done_at: Dict[str, int] = {}  # index into self.bwd after which the param's grad is final
+        # F.dropout of the ResidualUNet sibling: masks (uint8, forward order), generator seed, test hook
+        self.dropout_masks: List[torch.Tensor] = []
+        self.dropout_seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+        self.dropout_external = False
+        self._drop_ctr: Optional[torch.Tensor] = None
 
     # ------------------------------------------------------------------------------------------------ helpers
     def P(self, name: str) -> torch.nn.Parameter:
@@ -738,6 +743,185 @@ class Plan:
             return [_mk("mtbc_softmax_rows_bwd", ptr(probs), ptr(dprobs), N, K, ptr(dlog))]
         self._bwd_blocks.append(backward)
         return probs
+
+
+    # ------------------------------------------------------------------------------------------------ ResidualUNet
+    # BatchNorm / residual / dropout sibling backbone (reference src/models/segmentation/ResidualUNet.py).  The tensor
+    # kernels are the multi-task path's; BatchNorm2d is the InstanceNorm passes over batch-pooled sums (residual.cu).
+    def conv_plain(self, srcs: Optional[Sequence[PTensor]], w: str, b: Optional[str], name: str, stride: int = 1,
+                   stats: bool = False, first_input: Optional[torch.Tensor] = None):
+        """Conv2d 3x3 (stride 1 or 2, padding 1, bias ADDED) whose output is used as is (a BatchNorm2d or a residual add
+        follows, ResidualUNet.py:35-58,113-131).  Returns (y, stat_sum, stat_sq); the per-(sample, channel) sums are
+        None unless `stats`."""
+        Wt = self.P(w)
+        Cout, Cin = Wt.shape[0], Wt.shape[1]
+        if first_input is not None:
+            N, H, Wd = self.B, self.H, self.W
+            feats, x0 = None, None
+        else:
+            feats = [t.feat for t in srcs]
+            assert sum(f.C for f in feats) == Cin and (stride == 1 or len(feats) == 1)
+            x0 = srcs[0]
+            N, H, Wd = feats[0].N, feats[0].H // stride, feats[0].W // stride
+        y = self.new(N, H, Wd, Cout, name + ".y")
+        Cp, npx = y.feat.Cp, N * H * Wd
+        ssum = self.fwd_arena.alloc(N, Cp) if stats else None
+        ssq = self.fwd_arena.alloc(N, Cp) if stats else None
+        fused = stats and H * Wd >= 128 and not self.deterministic
+        pk = None
+        if first_input is not None:
+            bvec = None if b is None else self.P(b)
+            l = _annot(_mk("mtbc_conv_first_fwd", ptr(first_input), N, Cin, H, Wd, ptr(Wt), ptr(bvec), Cout,
+                           ptr(y.feat.t), Cp, ptr(ssum) if fused else None, ptr(ssq) if fused else None, None),
+                       f"{name} first conv fwd {N}x{H}x{Wd} {Cin}->{Cout}", npx * (4 * Cin + 2 * Cout))
+            l.true_flops = 2.0 * npx * Cout * Cin * 9
+            self.fwd.append(l)
+        else:
+            pk = self._pack_conv(w, feats, y.feat.Ck)
+            bias = self._padded_vec(b, y.feat.Ck)
+            kw = dict(bias=bias, stat_sum=ssum if fused else None, stat_sq=ssq if fused else None,
+                      wpack_lo=pk.get("wf_lo"))
+            op = (ops.conv3x3_fwd_op(feats, pk["wf"], y.feat, **kw) if stride == 1 else
+                  ops.conv3x3_s2_fwd_op(feats[0], pk["wf"], y.feat, **kw))
+            self.tc_flops_fwd += op.flops
+            self.fwd.append(_mk_op(op, 2.0 * npx * Cout * Cin * 9,
+                                   f"{name} fwd s{stride} {N}x{H}x{Wd} {[f.C for f in feats]}->{Cout}",
+                                   2.0 * npx * (Cin * stride * stride + Cout) + 18.0 * Cin * Cout))
+        if stats and not fused:
+            self.fwd.append(self._stats_launch(y, ssum, ssq, name))
+
+        def backward():
+            blk: List[Callable] = []
+            if not y.g_init:
+                return blk
+            dy = y.g
+            if first_input is not None:
+                blk.append(self._side(_annot(_mk("mtbc_conv_first_wgrad", ptr(first_input), N, Cin, H, Wd, ptr(dy.t),
+                                                 dy.Cp, Cout, ptr(self.grad_view[w])),
+                                             f"{name} first conv wgrad", npx * (4 * Cin + 2 * Cout))))
+            elif stride == 2:
+                acc = self._wg_accum(w, pk)
+                o = ops.conv3x3_s2_wgrad_op(feats[0], dy, acc)
+                self.tc_flops_bwd += o.flops
+                blk.append(self._side(_mk_op(o, 2.0 * npx * Cout * Cin * 9, f"{name} wgrad s2 {Cin}x{Cout}")))
+            else:
+                acc = self._wg_accum(w, pk)
+                for f, off in zip(feats, pk["offs"]):
+                    o = ops.conv3x3_wgrad_op(f, dy, acc, off)
+                    self.tc_flops_bwd += o.flops
+                    blk.append(self._side(_mk_op(o, 2.0 * npx * Cout * f.C * 9, f"{name} wgrad {f.C}x{Cout}")))
+            if b is not None:
+                blk.append(_annot(_mk("mtbc_channel_sum", ptr(dy.t), npx, dy.Cp, Cout, ptr(self.grad_view[b]), 1),
+                                  f"{name} bias grad", 2.0 * npx * Cout))
+            self._mark_grad(w, b)
+            if first_input is not None:
+                return blk                      # the image needs no gradient
+            if stride == 2:
+                up = self._keep_feat(N, 2 * H, 2 * Wd, Cout)
+                blk.append(_annot(_mk("mtbc_zero_stuff2", ptr(dy.t), N, H, Wd, dy.Cp, ptr(up.t)),
+                                  f"{name} zero-stuff dy", 2.0 * npx * Cout * 5))
+                self._emit_dgrad(blk, [x0], up, w, pk, name, Cout)
+            else:
+                self._emit_dgrad(blk, srcs, dy, w, pk, name, Cout)
+            return blk
+        self._bwd_blocks.append(backward)
+        return y, ssum, ssq
+
+    def _keep_feat(self, N, H, W, Cc) -> Feat:
+        f = Feat.empty(N, H, W, Cc, device=self.device, dtype=self.act_dtype)
+        self._keep.append(f.t)
+        return f
+
+    def bn_act(self, x: PTensor, bn: torch.nn.Module, prefix: str, slope: float, p_drop: float, name: str,
+               stats=None, training: bool = True) -> PTensor:
+        """nn.BatchNorm2d (eps 1e-5, momentum 0.1, affine) -> leaky_relu(slope; slope 1 = no activation) ->
+        F.dropout(p) on tensor x (ResidualUNet.py:58-61,137-145).  `stats` = (sum, sum of squares) per (sample, channel)
+        when the producing conv delivered them, else they are reduced here."""
+        f = x.feat
+        N, H, Wd, Cp, Cc = f.N, f.H, f.W, f.Cp, f.C
+        gamma, beta = prefix + ".weight", prefix + ".bias"
+        if stats is None or stats[0] is None:
+            ssum, ssq = self.fwd_arena.alloc(N, Cp), self.fwd_arena.alloc(N, Cp)
+            self.fwd.append(self._stats_launch(x, ssum, ssq, name))
+        else:
+            ssum, ssq = stats
+        self.fwd.append(_mk("mtbc_bn_pool_fwd", ptr(ssum), ptr(ssq), N, Cp, Cc, H * Wd, int(training),
+                            C.c_float(float(bn.momentum if bn.momentum is not None else 0.1)), ptr(bn.running_mean),
+                            ptr(bn.running_var), ptr(bn.num_batches_tracked)))
+        a = self.new(N, H, Wd, Cc, name)
+        mean = torch.zeros(N, Cp, dtype=torch.float32, device=self.device)
+        rstd = torch.zeros(N, Cp, dtype=torch.float32, device=self.device)
+        gv, bv = self._padded_vec(gamma, f.Ck), self._padded_vec(beta, f.Ck)
+        nbytes = 2.0 * N * H * Wd * Cc * (2 if self.fp32 else 1)
+        self.fwd.append(_annot(_mk("mtbc_in_apply", ptr(f.t), N, H, Wd, Cp, ptr(ssum), ptr(ssq), ptr(gv), ptr(bv), Cc,
+                                   C.c_float(float(bn.eps)), C.c_float(slope), ptr(a.feat.t), None, ptr(mean),
+                                   ptr(rstd)), f"{name} bn_apply {N}x{H}x{Wd}x{Cc}", 2 * nbytes))
+        out, mask = a, None
+        nel = N * H * Wd * Cp
+        if p_drop > 0.0:
+            out = self.new(N, H, Wd, Cc, name + ".drop")
+            mask = torch.zeros(nel, dtype=torch.uint8, device=self.device)
+            self.dropout_masks.append(mask)
+            self.fwd.append(_annot(_mk("mtbc_dropout_fwd", ptr(a.feat.t), ptr(out.feat.t), ptr(mask), nel,
+                                       C.c_float(p_drop), C.c_uint64(self.dropout_seed), ptr(self._drop_counter()),
+                                       len(self.dropout_masks), int(self.dropout_external)),
+                                   f"{name} dropout", 2 * nbytes))
+
+        def backward():
+            blk: List[Callable] = []
+            if not out.g_init:
+                return blk
+            if mask is not None:
+                g = a.grad()
+                blk.append(_mk("mtbc_dropout_bwd", ptr(out.g.t), ptr(mask), ptr(g.t), nel, C.c_float(p_drop), 0))
+                a.g_init = True
+            s1, s2 = self.bwd_arena.alloc(N, Cp), self.bwd_arena.alloc(N, Cp)
+            dx = self.scratch(N, H, Wd, Cc)
+            blk.append(_mk("mtbc_in_bwd_reduce", ptr(a.g.t), ptr(f.t), N, H * Wd, Cp, ptr(mean), ptr(rstd), ptr(gv),
+                           ptr(bv), C.c_float(slope), ptr(s1), ptr(s2)))
+            blk.append(_mk("mtbc_bn_pool_bwd", ptr(s1), ptr(s2), N, Cp, Cc, int(training), ptr(self.grad_view[gamma]),
+                           ptr(self.grad_view[beta])))
+            l = _annot(_mk("mtbc_in_bwd_apply", ptr(a.g.t), ptr(f.t), N, H * Wd, Cp, ptr(mean), ptr(rstd), ptr(gv),
+                           ptr(bv), C.c_float(slope), ptr(s1), ptr(s2), ptr(dx.t), None, None, Cc),
+                       f"{name} bn_bwd", 3 * nbytes)
+            l.wait_side = self._slot_readers.pop(self._cur_slot, [])
+            blk.append(l)
+            g = x.grad()
+            blk.append(_mk("mtbc_accumulate", ptr(dx.t), ptr(g.t), nel, int(x.g_init)))
+            x.g_init = True
+            self._mark_grad(gamma, beta)
+            return blk
+        self._bwd_blocks.append(backward)
+        return out
+
+    def _drop_counter(self) -> torch.Tensor:
+        """Device-side draw counter of this plan's dropout masks: advanced once at the head of every forward (also
+        under CUDA-graph replay), so every step draws fresh masks."""
+        if self._drop_ctr is None:
+            self._drop_ctr = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self.fwd.insert(0, _mk("mtbc_increment_i32", ptr(self._drop_ctr)))
+        return self._drop_ctr
+
+    def add(self, a: PTensor, b: PTensor, name: str) -> PTensor:
+        """`path + residual` (ResidualUNet.py:69,155)."""
+        fa, fb = a.feat, b.feat
+        assert fa.t.shape == fb.t.shape
+        out = self.new(fa.N, fa.H, fa.W, fa.C, name)
+        nel = fa.t.numel()
+        self.fwd.append(_annot(_mk("mtbc_add", ptr(fa.t), ptr(fb.t), ptr(out.feat.t), nel), f"{name} add",
+                               3.0 * nel * fa.t.element_size()))
+
+        def backward():
+            blk: List[Callable] = []
+            if not out.g_init:
+                return blk
+            for t in (a, b):
+                g = t.grad()
+                blk.append(_mk("mtbc_accumulate", ptr(out.g.t), ptr(g.t), nel, int(t.g_init)))
+                t.g_init = True
+            return blk
+        self._bwd_blocks.append(backward)
+        return out
 
     # ------------------------------------------------------------------------------------------------ finalize / run
     def finalize(self, seg_grad_active: Optional[Sequence[bool]] = None):

@@ -373,6 +373,90 @@ class BTSUNet(nn.Module):
         return self.output1(d1)
 
 
+class _RUInBlock(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, kernel_size=3, padding=1)
+        self.bn1 = nn.BatchNorm2d(cout)
+        self.conv2 = nn.Conv2d(cout, cout, kernel_size=3, padding=1)
+        self.conv3 = nn.Conv2d(cin, cout, kernel_size=3, padding=1)
+        self.bn3 = nn.BatchNorm2d(cout)
+
+
+class _RUResBlock(nn.Module):
+    def __init__(self, cin, downsample=False):
+        super().__init__()
+        cout, st = (2 * cin, 2) if downsample else (cin, 1)
+        self.bn1 = nn.BatchNorm2d(cin)
+        self.conv1 = nn.Conv2d(cin, cout, kernel_size=3, stride=st, padding=1)
+        self.bn2 = nn.BatchNorm2d(cout)
+        self.conv2 = nn.Conv2d(cout, cout, kernel_size=3, padding=1)
+        self.conv3 = nn.Conv2d(cin, cout, kernel_size=3, stride=st, padding=1)
+        self.bn3 = nn.BatchNorm2d(cout)
+
+
+class _RUEncoder(nn.Module):
+    def __init__(self, bf):
+        super().__init__()
+        self.down_block2 = _RUResBlock(bf, True)
+        self.down_block3 = _RUResBlock(bf * 2, True)
+        self.down_block4 = _RUResBlock(bf * 4, True)
+
+
+class _RUDecoder(nn.Module):
+    def __init__(self, bf):
+        super().__init__()
+        self.upsample3 = nn.ConvTranspose2d(bf * 8, bf * 4, kernel_size=2, stride=2)
+        self.conv3 = nn.Conv2d(bf * 8, bf * 4, kernel_size=1)      # skip-variant only: never called (ResidualUNet.py:356-362)
+        self.up_block3 = _RUResBlock(bf * 4)
+        self.upsample2 = nn.ConvTranspose2d(bf * 4, bf * 2, kernel_size=2, stride=2)
+        self.conv2 = nn.Conv2d(bf * 4, bf * 2, kernel_size=1)
+        self.up_block2 = _RUResBlock(bf * 2)
+        self.upsample1 = nn.ConvTranspose2d(bf * 2, bf, kernel_size=2, stride=2)
+        self.conv1 = nn.Conv2d(bf * 2, bf, kernel_size=1)
+        self.up_block1 = _RUResBlock(bf)
+
+
+class _RUOut(nn.Module):
+    def __init__(self, bf, n_classes):
+        super().__init__()
+        self.conv = nn.Conv2d(bf, n_classes, kernel_size=1)
+
+
+class ResidualUNet(nn.Module):
+    """Restates src/models/segmentation/ResidualUNet.py:342-362 (ResidualUNet.forward: in_block -> encoder -> decoder
+    -> out_block, i.e. the variant WITHOUT skip connections; `seg_path` :298-339 is not what the factory builds).
+    BatchNorm2d with running statistics, stride-2 3x3 convs, F.leaky_relu (slope 0.01) and F.dropout(p=0.2) called
+    with its default training=True (:61,139,145: active in eval mode too).  `dropout` is the hook parity tests use to
+    substitute fixed masks for torch's generator; by default it IS F.dropout, drawn in the reference's call order."""
+
+    def __init__(self, sequences=1, regions=1, width=24):
+        super().__init__()
+        self.in_block = _RUInBlock(sequences, width)
+        self.encoder = _RUEncoder(width)
+        self.decoder = _RUDecoder(width)
+        self.out_block = _RUOut(width, regions)
+        self.dropout = lambda t: F.dropout(t, p=0.2)
+
+    def _res(self, blk, x):
+        path = self.dropout(F.leaky_relu(blk.bn1(x)))
+        path = self.dropout(F.leaky_relu(blk.bn2(blk.conv1(path))))
+        path = blk.conv2(path)
+        return path + blk.bn3(blk.conv3(x))
+
+    def forward(self, x):
+        ib = self.in_block
+        path = ib.conv2(self.dropout(F.leaky_relu(ib.bn1(ib.conv1(x)))))
+        x = path + ib.bn3(ib.conv3(x))
+        for blk in (self.encoder.down_block2, self.encoder.down_block3, self.encoder.down_block4):
+            x = self._res(blk, x)
+        d = self.decoder
+        x = self._res(d.up_block3, d.upsample3(x))
+        x = self._res(d.up_block2, d.upsample2(x))
+        x = self._res(d.up_block1, d.upsample1(x))
+        return self.out_block.conv(x)
+
+
 class UNetPlusPlusClassifier(nn.Module):
     """Restates src/models/classification/UnetPlusPlus_Classifier.py:20-147: encoder + upcat_3_1 + class branch of
     MTUNetPlusPlus; raw class logits (the softmax is commented out in the reference, :142-143)."""

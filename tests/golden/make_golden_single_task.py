@@ -16,6 +16,7 @@ sys.path.insert(0, "/root/reference")
 from oracle import torch_oracle as O  # noqa: E402
 from src.models.segmentation.nnUNet import nnUNet2021 as RefNN  # noqa: E402
 from src.models.segmentation.BTS_UNet import BTSUNet as RefBTS  # noqa: E402
+from src.models.segmentation.ResidualUNet import ResidualUNet as RefRes  # noqa: E402
 
 SEED = 1993
 CASES = {
@@ -24,6 +25,10 @@ CASES = {
                        ora=lambda: O.BTSUNet(1, 1, 32, True)),
     "btsunet": dict(B=2, S=48, ref=lambda: RefBTS(sequences=1, regions=1, width=16, deep_supervision=False),
                     ora=lambda: O.BTSUNet(1, 1, 16, False)),
+    # BatchNorm2d (training mode: batch statistics + running-statistics update) + F.dropout: both sides draw their masks
+    # from torch's generator in the same call order, so one seed in front of each forward gives identical outputs
+    "residualunet": dict(B=2, S=64, ref=lambda: RefRes(sequences=1, regions=1, width=24),
+                         ora=lambda: O.ResidualUNet(1, 1, 24), reseed=True),
 }
 
 
@@ -45,16 +50,24 @@ for name, c in CASES.items():
     res = []
     for m in (ref, ora):
         m.zero_grad(set_to_none=True)
+        if c.get("reseed"):
+            torch.manual_seed(SEED + 1)       # same dropout draws on both sides
         outs = m(img)
         lst = outs if isinstance(outs, list) else [outs]
         loss = sum(dice(o, mask) / (n + 1) for n, o in enumerate(reversed(lst)))
         loss.backward()
-        res.append((lst, loss.item(), torch.cat([p.grad.flatten() for p in m.parameters()]).norm().item()))
+        res.append((lst, loss.item(), torch.cat([p.grad.flatten() for p in m.parameters() if p.grad is not None]).norm().item()))
     for a, b in zip(res[0][0], res[1][0]):
         assert torch.equal(a, b), name
     assert res[0][1] == res[1][1] and res[0][2] == res[1][2], name
-    out[name] = {"seed": SEED, "B": c["B"], "S": c["S"], "state_digest": digest(ref.state_dict()),
+    assert digest(ref.state_dict()) == digest(ora.state_dict()), name      # BatchNorm running statistics moved alike
+    gr, go = dict(ref.named_parameters()), dict(ora.named_parameters())
+    assert all((gr[k].grad is None) == (go[k].grad is None) for k in gr), name
+    torch.manual_seed(SEED); fresh = c["ref"]()
+    out[name] = {"seed": SEED, "B": c["B"], "S": c["S"], "state_digest": digest(fresh.state_dict()),
+                 "state_digest_after_step": digest(ref.state_dict()),
+                 "no_grad_params": sorted(k for k, p in ref.named_parameters() if p.grad is None),
                  "outputs": [o.detach().clone() for o in res[0][0]], "loss": res[0][1], "grad_norm": res[0][2],
-                 "n_params": sum(p.numel() for p in ref.parameters())}
+                 "n_params": sum(p.numel() for p in ref.parameters()), "reseed": bool(c.get("reseed"))}
     print(name, "ok", out[name]["n_params"], out[name]["loss"])
 torch.save(out, os.path.join(HERE, "single_task.pt"))
