@@ -151,14 +151,25 @@ def test_gradients_match_oracle_per_parameter(lib):
     (ref(img) * g).sum().backward()
     (new(img) * g).sum().backward()
     torch.cuda.synchronize()
-    pr, rows = dict(ref.named_parameters()), []
+    pr, rows, cancelled = dict(ref.named_parameters()), [], []
+    rms = lambda t: t.norm().item() / t.numel() ** 0.5
+    scale = max(rms(p.grad) for p in pr.values() if p.grad is not None)
     for k, p in new.named_parameters():
         assert (p.grad is None) == (pr[k].grad is None), k
-        if p.grad is not None:
-            rows.append((rel(p.grad, pr[k].grad), k))
+        if p.grad is None:
+            continue
+        if rms(pr[k].grad) < 1e-5 * scale:
+            # bias of a conv in front of a BatchNorm2d: the batch-mean subtraction cancels it, its true gradient is 0 and
+            # both sides hold rounding noise (reference ~1e-7 of the scale)
+            assert k.endswith((".conv1.bias", ".conv3.bias")), k
+            assert rms(p.grad) < 1e-4 * scale, (k, rms(p.grad), scale)
+            cancelled.append(k)
+            continue
+        rows.append((rel(p.grad, pr[k].grad), k))
     rows.sort(reverse=True)
-    print("\nResidualUNet [tf32x3] per-parameter gradient rel-L2, worst:", [(k, f"{e:.2e}") for e, k in rows[:5]])
-    assert len(rows) == len(pr) - 6          # every parameter but the six of the never-called 1x1 convs
+    print("\nResidualUNet [tf32x3] per-parameter gradient rel-L2, worst:", [(k, f"{e:.2e}") for e, k in rows[:5]],
+          f"; {len(cancelled)} BatchNorm-cancelled conv biases ~0 on both sides")
+    assert len(rows) + len(cancelled) == len(pr) - 6     # every parameter but the six of the never-called 1x1 convs
     assert rows[0][0] < 5e-2, rows[:5]
     unused = [k for k, p in new.named_parameters() if p.grad is None]
     assert sorted(unused) == sorted(f"decoder.conv{i}.{w}" for i in (1, 2, 3) for w in ("weight", "bias"))

@@ -35,14 +35,25 @@ for _ in range(3):
         l(st)
 torch.cuda.synchronize()
 rt = torch.cuda.cudart()
-rt.cudaProfilerStart()
+only = os.environ.get("ONLY")          # profile just the launches whose "kind|desc" label contains this substring
+if only is None:
+    rt.cudaProfilerStart()
 for i, l in enumerate(launches):
     # NVTX range = label of the plan launch; `ncu --nvtx --print-nvtx-rename kernel` renames the kernels with it
-    torch.cuda.nvtx.range_push(f"{i}|{l.kind}|{getattr(l, 'desc', '')}")
+    label = f"{i}|{l.kind}|{getattr(l, 'desc', '')}"
+    hit = only is not None and only in label
+    if hit:
+        torch.cuda.synchronize()
+        rt.cudaProfilerStart()
+    torch.cuda.nvtx.range_push(label)
     l(st)
     torch.cuda.nvtx.range_pop()
+    if hit:
+        torch.cuda.synchronize()
+        rt.cudaProfilerStop()
 torch.cuda.synchronize()
-rt.cudaProfilerStop()
+if only is None:
+    rt.cudaProfilerStop()
 meta = [{"kind": l.kind, "desc": getattr(l, "desc", ""), "flops": getattr(l, "true_flops", 0.0),
          "nk": getattr(l, "n_kernels", 1)} for l in launches]
 if out != "/dev/null":
