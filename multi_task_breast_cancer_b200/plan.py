@@ -578,9 +578,12 @@ class Plan:
                                  owner=w)
             self._late_unpacked.append(w)
             if b is not None:
-                blk.append(_annot(_mk("mtbc_channel_sum", ptr(out.g.t), out.g.N * out.g.H * out.g.W, out.g.Cp, Cout,
-                                      ptr(self.grad_view[b]), 1), f"{name} convT bias grad",
-                                  2.0 * out.g.N * out.g.H * out.g.W * Cout))
+                l = _annot(_mk("mtbc_channel_sum", ptr(out.g.t), out.g.N * out.g.H * out.g.W, out.g.Cp, Cout,
+                               ptr(self.grad_view[b]), 1), f"{name} convT bias grad",
+                           2.0 * out.g.N * out.g.H * out.g.W * Cout)
+                # like the weight gradients it only feeds the parameter-gradient buffer: side stream, next to the
+                # weight gradient that reads the same tensor (MTBC_SIDE_BIAS=0 keeps it on the main stream)
+                blk.append(self._side(l) if os.environ.get("MTBC_SIDE_BIAS", "1") != "0" else l)
             self._mark_grad(w, b)
             g = x.grad()
             o = ops.convT_dgrad_op(out.g, wd, g, k, accumulate=x.g_init, wd_lo=wd_lo)
@@ -942,7 +945,20 @@ class Plan:
             n_pre = len(self.bwd)
             self.bwd += body
             self.param_done_at = {n: i + n_pre for n, i in self.param_done_at.items()}
-        self.pack = self.pack_jobs.launch() + self.pack
+        pack_jobs = self.pack_jobs.launch()
+        if pack_jobs and os.environ.get("MTBC_SIDE_PACK", "1") != "0":
+            # The parameter pack (one launch, latency bound: ~0.1 ms for 15 M parameters; bf16 conv operands and the padded
+            # gamma / beta / bias vectors) is not needed by the first layer's conv, which reads the fp32 image and the
+            # fp32 master weights on the CUDA cores.  TrainStep forks the pack onto the side stream; the first forward
+            # launch that may read packed data (anything after the first-layer conv) waits for it.
+            free = ("mtbc_zero_bytes", "mtbc_conv_first_fwd", "mtbc_increment_i32")
+            waiter = next((l for l in self.fwd if l.kind not in free), None)
+            if waiter is not None and getattr(waiter, "wait_side", None) is None and self.fwd and \
+                    any(l.kind == "mtbc_conv_first_fwd" for l in self.fwd):
+                for l in pack_jobs:
+                    l.side = True
+                waiter.wait_side = list(pack_jobs)
+        self.pack = pack_jobs + self.pack
         self.fwd = self.fwd_arena.zero_launches() + self.fwd
         self._bwd_blocks = []
         self.finalized = True
