@@ -258,6 +258,15 @@ def run_ours(args):
             raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
+    if world > 1 and os.environ.get("MTBC_NUMA_BIND", "1") != "0":
+        # every rank stages 16.8 MB of pinned host memory per step: keep it on its own GPU's socket
+        from multi_task_breast_cancer_b200.train import bind_to_gpu_numa
+        try:   # NVML numbers the physical devices; CUDA_VISIBLE_DEVICES may remap the local rank
+            gpu = int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local])
+        except (KeyError, ValueError, IndexError):
+            gpu = local
+        numa = bind_to_gpu_numa(gpu)
     pg = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -374,6 +383,7 @@ def run_ours(args):
                "tflops_true": world * B * TRAIN_GFLOP[(args.arch, S)] / ms_dev if (args.arch, S) in TRAIN_GFLOP else None,
                "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
                        "ms_per_step": ms_e2e},
+               "host_cores_bound": None if numa is None else len(numa),
                "gpu_launches": n_launch, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                "library_baseline": lib}
         _emit(out)

@@ -30,6 +30,27 @@ from .ops import ptr, stream_ptr
 from .plan import Plan, _mk, flat_layout
 
 
+def bind_to_gpu_numa(device_index: int) -> Optional[List[int]]:
+    """Pin the calling process to the host cores NVML reports as local to GPU `device_index` (call before allocating
+    pinned batches: first touch then places them on the GPU's NUMA node).  One process per GPU, all started by torchrun
+    on whatever cores the launcher ran on, otherwise stage every rank's batch through the same socket.  Returns the
+    core list, or None when NVML or the affinity call is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cores = [64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1]
+        cores = [c for c in cores if c in os.sched_getaffinity(0)] or cores
+        if cores:
+            os.sched_setaffinity(0, cores)
+        return cores
+    except Exception:  # noqa: BLE001 - best effort: an unbound process is still correct
+        return None
+
+
 class TrainStep:
     def __init__(self, model: torch.nn.Module, batch_shape: Sequence[int], lr: float = 1e-4, betas=(0.9, 0.999),
                  eps: float = 1e-4, alpha: float = 0.35, inversely_weighted: bool = True, focal_alpha: float = 1.0,

@@ -85,6 +85,23 @@ def test_conv3x3_wgrad_fused_over_concat_sources(D, args):
     _run(D, D.conv_wgrad_multi_case, *args)
 
 
+@pytest.mark.parametrize("which", ["fwd", "dgrad", "wgrad", "fwd48", "wgrad48"])
+def test_conv3x3_at_the_benchmark_shape(D, which):
+    """The level-0 / level-1 multi-source layers of U-Net++ at BASELINE configs[1]'s real extent (B = 32, 256 x 256 /
+    128 x 128): many tiles per persistent CTA, G = 2 row stacking, two MMA lanes, the fused multi-source data / weight
+    gradients with their splits, two CTAs per SM -- the paths the small cases above only touch with a few tiles."""
+    if which == "fwd":
+        _run(D, D.conv_fwd_case, 32, 256, 256, [24, 24, 24, 24, 48], 24)
+    elif which == "dgrad":
+        _run(D, D.conv_dgrad_multi_case, 32, 256, 256, [24, 24, 24, 24, 48], 24)
+    elif which == "wgrad":
+        _run(D, D.conv_wgrad_multi_case, 32, 256, 256, [24, 24, 24, 24, 48], 24)
+    elif which == "fwd48":
+        _run(D, D.conv_fwd_case, 32, 128, 128, [48, 48, 48, 48], 48)
+    else:
+        _run(D, D.conv_wgrad_multi_case, 32, 128, 128, [48, 48, 48, 48], 48)
+
+
 @pytest.mark.parametrize("args", [(2, 16, 16, 64, 32), (2, 16, 16, 48, 48), (2, 8, 8, 384, 192), (4, 8, 8, 320, 320),
                                   # several pixel tiles per CTA: the weight-gradient operand rings wrap around
                                   (8, 128, 128, 48, 48), (6, 64, 64, 96, 48)])
