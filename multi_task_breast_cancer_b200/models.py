@@ -775,8 +775,14 @@ class ResidualUNet(_PlanModule):
 
     def _build_graph(self, plan: Plan, x_in: torch.Tensor):
         B, Cin, H, W = x_in.shape
-        if H % 128 or W % 16 or Cin > 4:
-            raise ValueError("ResidualUNet on sm_100a needs H % 128 == 0, W % 16 == 0 and at most 4 input channels")
+        if H % 8 or W % 8 or (H * W) % 128 or Cin > 4:
+            raise ValueError("ResidualUNet needs H and W divisible by 8 (three stride-2 convs), H * W a multiple of 128 "
+                             "and at most 4 input channels")
+        for k in range(4):   # plane extents the conv kernels tile: multiples of 16, or 1 / 2 / 4 / 8
+            for v in (H >> k, W >> k):
+                if not (v % 16 == 0 or v in (1, 2, 4, 8)):
+                    raise ValueError(f"ResidualUNet on sm_100a: the {v}-pixel planes of a {H}x{W} input are not tileable "
+                                     "(every level's extent must be a multiple of 16, or 8 / 4 / 2 / 1)")
         plan.dropout_external = bool(self._external_dropout)
         ib = self.in_block
         y1, s1, q1 = plan.conv_plain(None, "in_block.conv1.weight", "in_block.conv1.bias", "in_block.conv1", stats=True,

@@ -174,6 +174,7 @@ class TrainStep:
             return
         # ---- fused objective (criterions.py:52-76 + training_multitask.py:98)
         L.append(_mk("mtbc_zero_bytes", ptr(self.dice_sums), self.dice_sums.numel() * 4))
+        L[-1].wait_side = "all"     # the mask heads' forward launches run on the side stream (plan._side_fwd)
         for i, logits in enumerate(plan.outputs_seg):
             j = nh - 1 - i  # reversed list: the last head (full decoder) gets weight 1
             L.append(_mk("mtbc_dice_sums", ptr(logits), ptr(self.mask), B, HW, ptr(self.dice_sums[i])))

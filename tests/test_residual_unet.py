@@ -114,6 +114,25 @@ def test_forward_parity_train_mode_and_running_statistics(lib, precision, tol):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("B,H,W", [(2, 64, 64), (3, 128, 256), (2, 256, 256)])
+def test_other_input_extents(lib, B, H, W):
+    """The reference accepts any extent divisible by 8; the kernels need the planes tileable (H, W % 16 == 0): small
+    planes (8 x 8 at the bottom of a 64 x 64 input), a non-square input, and 256 x 256."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs CUDA")
+    ref, new = _pair("tf32x3")
+    img = O.synthetic_batch(B, max(H, W), max(H, W), device="cuda")[0][:, :, :H, :W].contiguous()
+    _share_masks(ref, new, img, need_grad=False)
+    with torch.no_grad():
+        r = ref(img)
+        n = new(img)
+    assert n.shape == r.shape == (B, 1, H, W) and rel(n, r) < 1e-3, rel(n, r)
+    if (H, W) == (64, 64):
+        with pytest.raises(ValueError, match="not tileable"):      # 192 / 8 = 24-pixel rows at the bottom level
+            new(torch.zeros(1, 1, 128, 192, device="cuda"))
+
+
+@pytest.mark.gpu
 def test_eval_mode_uses_running_statistics(lib):
     if not torch.cuda.is_available():
         pytest.skip("needs CUDA")
