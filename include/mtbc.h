@@ -307,12 +307,17 @@ int mtbc_dshead_compose(const float* wt, const float* bt, const float* w1, const
                         float* wc, float* bc, void* stream);
 int mtbc_dshead_fwd(const void* a, int32_t N, int32_t H, int32_t W, int32_t Cp, int32_t C, int32_t k, const float* wc,
                     const float* bc, float* logits, void* stream);
-/* dA (+)= ..., dwc[ci][q] += ..., dbc += ...  (dwc/dbc zeroed by caller). */
+/* dA (+)= dlogits . Wc^T.  The weight-gradient partials of block r go to row r of dwc_part ([nparts + 1][C*k*k]) and
+ * dbc_part ([nparts + 1]) -- no atomics, no zeroing by the caller; nparts = mtbc_dshead_bwd_parts(N, H, W). */
+int mtbc_dshead_bwd_parts(int32_t N, int32_t H, int32_t W);
 int mtbc_dshead_bwd(const void* a, const float* dlogits, int32_t N, int32_t H, int32_t W, int32_t Cp, int32_t C,
-                    int32_t k, const float* wc, void* dA, int32_t accumulate, float* dwc, float* dbc, void* stream);
-/* Chain rule back to the two original parameter sets (state_dict layout stays the reference's). */
-int mtbc_dshead_decompose(const float* dwc, const float* dbc, const float* wt, const float* bt, const float* w1,
-                          int32_t C, int32_t k, float* dwt, float* dbt, float* dw1, float* db1, void* stream);
+                    int32_t k, const float* wc, void* dA, int32_t accumulate, float* dwc_part, float* dbc_part,
+                    int32_t nparts, void* stream);
+/* Adds the partial rows (into row nparts of both buffers), then the chain rule back to the two original parameter sets
+ * (state_dict layout stays the reference's); dwt/dbt/dw1/db1 accumulate. */
+int mtbc_dshead_decompose(float* dwc_part, float* dbc_part, int32_t nparts, const float* wt, const float* bt,
+                          const float* w1, int32_t C, int32_t k, float* dwt, float* dbt, float* dw1, float* db1,
+                          void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------- */
 /* Classification head: AdaptiveAvgPool2d(1) -> Flatten -> Linear(F,Hd) -> ReLU -> Linear(Hd,K)

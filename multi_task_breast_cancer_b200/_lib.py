@@ -108,8 +108,9 @@ _SIGS = {
     "mtbc_head1x1_bwd": [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp],
     "mtbc_dshead_compose": [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp],
     "mtbc_dshead_fwd": [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp],
-    "mtbc_dshead_bwd": [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp],
-    "mtbc_dshead_decompose": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "mtbc_dshead_bwd_parts": [c_i32, c_i32, c_i32],
+    "mtbc_dshead_bwd": [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp],
+    "mtbc_dshead_decompose": [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp],
     "mtbc_gap_fc_fwd": [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp,
                         c_vp],
     "mtbc_gap_fc_bwd": [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp,
@@ -144,7 +145,7 @@ _RESTYPES = {"mtbc_op_destroy": None, "mtbc_op_flops": c_f64, "mtbc_query_worksp
 MODE_ACT_FP32, MODE_DETERMINISTIC = 1, 2
 
 EXPORTED_SYMBOLS = sorted(list(_SIGS) + ["mtbc_last_error", "mtbc_build_digest"])
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class MtbcError(RuntimeError):

@@ -1,5 +1,6 @@
 // C-ABI glue: error reporting, opaque op handles, device check.
 #include "internal.h"
+#include <stdlib.h>
 #include <stdarg.h>
 #include <stdio.h>
 
@@ -18,6 +19,12 @@ int set_error(int code, const char* fmt, ...) {
 static thread_local int g_mode = 0;
 int current_mode() { return g_mode; }
 
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MTBC_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(MTBC_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
@@ -33,7 +40,7 @@ struct mtbc_op {
 extern "C" {
 
 const char* mtbc_last_error(void) { return mtbc::g_err; }
-int mtbc_abi_version(void) { return 3; }
+int mtbc_abi_version(void) { return 4; }
 #ifndef MTBC_BUILD_DIGEST
 #define MTBC_BUILD_DIGEST "unstamped"
 #endif

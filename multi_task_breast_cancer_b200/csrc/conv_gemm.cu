@@ -73,8 +73,6 @@ __global__ void __launch_bounds__(PREC == 3 ? 448 : 320) conv_gemm_kernel(const 
   const int n_items = p.n_mtiles * p.n_ntiles;
 
   for (int i = tid; i < 512; i += NT) (&s_stat[0][0])[i] = 0.f;
-  if (p.bias != nullptr)
-    for (int i = tid; i < p.bias_len; i += NT) s_bias[i] = p.bias[i];
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&s_full[s], 1);
@@ -92,6 +90,13 @@ __global__ void __launch_bounds__(PREC == 3 ? 448 : 320) conv_gemm_kernel(const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
+  // programmatic dependent launch: nothing above read global memory (ptx.cuh: pdl_wait)
+  pdl_trigger();
+  pdl_wait();
+  if (p.bias != nullptr) {   // uniform
+    for (int i = tid; i < p.bias_len; i += NT) s_bias[i] = p.bias[i];
+    __syncthreads();
+  }
 
   if (warp == 0) {
     if (elect_one()) {
@@ -396,6 +401,8 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const __grid_constant__ Wgra
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
+  pdl_trigger();
+  pdl_wait();
 
   // number of A boxes that actually exist for this M block
   const int a_c0 = mblk * 128;
@@ -695,9 +702,9 @@ struct ConvGemmOp : public OpBase {
   int prec = 0;
   double flops;
   int launch(cudaStream_t st) override {
-    if (prec == 0) conv_gemm_kernel<0><<<grid, 320, smem_bytes, st>>>(p);
-    else if (prec == 1) conv_gemm_kernel<1><<<grid, 320, smem_bytes, st>>>(p);
-    else conv_gemm_kernel<3><<<grid, 448, smem_bytes, st>>>(p);
+    if (prec == 0) launch_pdl(conv_gemm_kernel<0>, grid, dim3(320), smem_bytes, st, p);
+    else if (prec == 1) launch_pdl(conv_gemm_kernel<1>, grid, dim3(320), smem_bytes, st, p);
+    else launch_pdl(conv_gemm_kernel<3>, grid, dim3(448), smem_bytes, st, p);
     return check_launch("conv_gemm_kernel");
   }
   double op_flops() const override { return flops; }
@@ -709,7 +716,7 @@ struct WgradOp : public OpBase {
   int smem_bytes;
   double flops;
   int launch(cudaStream_t st) override {
-    wgrad_kernel<<<grid, 128, smem_bytes, st>>>(p);
+    launch_pdl(wgrad_kernel, grid, dim3(128), smem_bytes, st, p);
     return check_launch("wgrad_kernel");
   }
   double op_flops() const override { return flops; }

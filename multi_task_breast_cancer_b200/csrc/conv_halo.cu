@@ -335,8 +335,6 @@ __global__ void __launch_bounds__((MINB == 2 ? 64 : 96) + 128 * P, MINB) conv_ha
   const int t_end = static_cast<int>(static_cast<int64_t>(p.n_mtiles) * (blockIdx.x + 1) / gridDim.x);
 
   const int bn1 = p.bn1;
-  for (int i = tid; i < 256; i += blockDim.x)
-    s_bias[i] = (p.bias != nullptr && i < BN) ? p.bias[ntile * bn1 + (i % bn1)] : 0.f;
   if (tid < (BN >> 4)) {
     const int lc = tid * 16;                      // column inside the accumulator
     const int prow = lc / bn1;                    // G = 2: 0 = upper pixel, 1 = lower pixel
@@ -368,6 +366,13 @@ __global__ void __launch_bounds__((MINB == 2 ? 64 : 96) + 128 * P, MINB) conv_ha
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
+  // everything above touched kernel parameters and shared memory only: the previous kernel may still be running
+  pdl_trigger();
+  pdl_wait();
+  if (p.bias != nullptr) {   // (uniform) the bias vector comes out of the parameter pack of this step
+    for (int i = tid; i < 256; i += blockDim.x) s_bias[i] = i < BN ? p.bias[ntile * bn1 + (i % bn1)] : 0.f;
+    __syncthreads();
+  }
 
   if (warp == 0) {
     if (elect_one()) {
@@ -630,6 +635,8 @@ __global__ void __launch_bounds__(128) wgrad_halo_kernel(const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
+  pdl_trigger();
+  pdl_wait();
 
   if (pt_end > pt_begin) {
     if (warp == 0 && elect_one()) {
@@ -749,6 +756,8 @@ __global__ void __launch_bounds__(128) wgrad_halo_multi_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
+  pdl_trigger();
+  pdl_wait();
 
   if (pt_end > pt_begin && nck > 0) {
     if (warp != 1 && elect_one()) {
@@ -852,9 +861,9 @@ struct ConvHaloOp : public OpBase {
   int epi_parts = 2;
   int launch(cudaStream_t st) override {
     // two CTAs per SM: the other CTA's MMA lane already feeds the pipe, one lane each (and no extra warp: registers)
-    if (epi_parts == 4) conv_halo_kernel<1, 4><<<grid, 96 + 512, smem_bytes, st>>>(p);
-    else if (ctas_per_sm == 2) conv_halo_kernel<2, 2><<<grid, 64 + 256, smem_bytes, st>>>(p);
-    else conv_halo_kernel<1, 2><<<grid, 96 + 256, smem_bytes, st>>>(p);
+    if (epi_parts == 4) launch_pdl(conv_halo_kernel<1, 4>, grid, dim3(96 + 512), smem_bytes, st, p);
+    else if (ctas_per_sm == 2) launch_pdl(conv_halo_kernel<2, 2>, grid, dim3(64 + 256), smem_bytes, st, p);
+    else launch_pdl(conv_halo_kernel<1, 2>, grid, dim3(96 + 256), smem_bytes, st, p);
     return check_launch("conv_halo_kernel");
   }
   double op_flops() const override { return flops; }
@@ -866,7 +875,7 @@ struct WgradHaloOp : public OpBase {
   int smem_bytes;
   double flops;
   int launch(cudaStream_t st) override {
-    wgrad_halo_kernel<<<grid, 128, smem_bytes, st>>>(p);
+    launch_pdl(wgrad_halo_kernel, grid, dim3(128), smem_bytes, st, p);
     return check_launch("wgrad_halo_kernel");
   }
   double op_flops() const override { return flops; }
@@ -918,7 +927,8 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
     const int wbytes = 9 * bn * kused * 2;
     // single-output layers keep the historical 120 KB cap (more halo stages); routed outputs (fused data gradients)
     // prefer wide N tiles: the dy halo is then read once per tile instead of once per source
-    const int cap = d->nouts > 0 ? 200 * 1024 - 2 * a_stage : 120 * 1024;
+    const char* cap_env = getenv("MTBC_HALO_WCAP_KB");
+    const int cap = d->nouts > 0 ? 200 * 1024 - 2 * a_stage : (cap_env ? atoi(cap_env) : 120) * 1024;
     if (wbytes <= cap) BN = bn;
   }
   if (BN < 32 && BN != d->ncols) return 1;
@@ -927,7 +937,9 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   {
     const char* w_env = getenv("MTBC_HALO_WIDE_NCOLS");
     const int wide = w_env ? atoi(w_env) : 96;
-    if (d->ncols >= wide && BN < 64 && d->nouts == 0) return 1;
+    const char* wb_env = getenv("MTBC_HALO_WIDE_BN");
+    const int wide_bn = wb_env ? atoi(wb_env) : 64;
+    if (d->ncols >= wide && BN < wide_bn && d->nouts == 0) return 1;
     if (d->ncols >= wide && BN < 64 && d->nouts > 0) return set_error(MTBC_ERR_INVALID, "conv_gemm: fused data gradient would need N tiles of %d columns", BN);
   }
 
@@ -994,7 +1006,10 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   const char* c_env = getenv("MTBC_HALO_CTAS");
   // forward G = 2 layers keep 64 statistics accumulators per epilogue thread: the 2-CTA variant (96 registers) spills
   // them, one CTA per SM with a deeper halo ring measured 4 % faster (3.24 -> 3.11 ms over the 35 forward convs)
-  const bool one_cta = (c_env && c_env[0] == '1') || (G == 2 && d->stat_sum != nullptr && !(c_env && c_env[0] == '2'));
+  // The same holds for G = 1 layers with 64 statistics columns: conv_1_0.conv_0 ([24] -> 48 @128^2) ran 69 us as two CTAs
+  // per SM and 34 us as one (tools/profile_plan.py with MTBC_HALO_CTAS=1, round 2).
+  const bool stats_heavy = d->stat_sum != nullptr && G * BN >= 64 && !getenv("MTBC_HALO_STATS2CTA");
+  const bool one_cta = (c_env && c_env[0] == '1') || ((G == 2 || stats_heavy) && d->stat_sum != nullptr && !(c_env && c_env[0] == '2'));
   if (one_cta && ctas_per_sm == 2) {
     ctas_per_sm = 1;
     int st1 = (200 * 1024 - p.b_total_bytes) / p.a_stage_bytes;
@@ -1130,7 +1145,7 @@ struct WgradMultiOp : public OpBase {
   int smem_bytes;
   double flops;
   int launch(cudaStream_t st) override {
-    wgrad_halo_multi_kernel<<<grid, 128, smem_bytes, st>>>(p);
+    launch_pdl(wgrad_halo_multi_kernel, grid, dim3(128), smem_bytes, st, p);
     return check_launch("wgrad_halo_multi_kernel");
   }
   double op_flops() const override { return flops; }

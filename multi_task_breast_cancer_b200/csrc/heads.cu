@@ -116,130 +116,205 @@ __global__ void dshead_compose_kernel(const float* __restrict__ wt, const float*
   }
 }
 
-// logits[n, k*h+i, k*w+j] = sum_ci a[n,h,w,ci]*wc[ci][q] + bc ; block = 256 threads = (256/kk pixels) x kk outputs
+// Composed deep-supervision head, round-2 kernels.  Tiles of 64 pixels per block step, activations / dl / the composed
+// weights in shared memory (fp32), 4 threads per pixel.  Round 1 processed 256 / k^2 pixels per step (4 at k = 8) and
+// funnelled every block's C * k^2 weight-gradient partials through fp32 atomics on the same 8 192 addresses: 1.19 ms for
+// the k = 8 head of nnU-Net at B = 32 @256^2 against ~0.03 ms of CUDA-core work (tools/profile_plan.py nnunet).  Now
+// every block keeps its weight-gradient partials in registers over all of its tiles and writes them ONCE to its own row
+// of a partials buffer; mtbc_dshead_decompose adds the rows.
+constexpr int kDsTP = 64;      // pixels per tile
+
+__device__ __forceinline__ int ds_logit_index(int64_t pix, int q, int H, int W, int k, int64_t* out) {
+  const int w = static_cast<int>(pix % W);
+  const int h = static_cast<int>((pix / W) % H);
+  const int64_t n = pix / (static_cast<int64_t>(W) * H);
+  *out = (n * H * k + static_cast<int64_t>(h) * k + q / k) * (static_cast<int64_t>(W) * k) + static_cast<int64_t>(w) * k + q % k;
+  return 0;
+}
+
 template <typename T>
-__global__ void __launch_bounds__(256) dshead_fwd_kernel(const T* __restrict__ a, int N, int H, int W,
-                                                         int Cp, int C, int k, const float* __restrict__ wc,
+__device__ __forceinline__ void ds_load_tile(const T* __restrict__ a, int64_t pix0, int64_t npix, int Cp, int C, int CA,
+                                             float* __restrict__ s_a) {
+  const int cvec = C >> 3;
+  for (int i = threadIdx.x; i < kDsTP * cvec; i += 256) {
+    const int px = i / cvec, v = i - px * cvec;
+    const int64_t pix = pix0 + px;
+    V8 x;
+    if (pix < npix) x = load8<T>(a + pix * Cp + v * 8);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x.f[j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_a[px * CA + v * 8 + j] = x.f[j];
+  }
+}
+
+// logits[n, k*h+i, k*w+j] = sum_ci a[n,h,w,ci]*wc[ci][q] + bc.  Thread (pixel p = tid / 4, part = tid % 4) owns the
+// outputs q = part + 4 j: its reads of the weight row are conflict free and the four threads of a pixel together write
+// whole k-float output rows.
+template <typename T, int KK>
+__global__ void __launch_bounds__(256) dshead_fwd_kernel(const T* __restrict__ a, int N, int H, int W, int Cp, int C,
+                                                         int k, const float* __restrict__ wc,
                                                          const float* __restrict__ bc, float* __restrict__ logits) {
   extern __shared__ float sm[];
-  const int kk = k * k;
-  const int PB = 256 / kk;
-  float* s_wc = sm;            // [C][kk]
-  float* s_a = sm + C * kk;    // [PB][C]
-  for (int i = threadIdx.x; i < C * kk; i += 256) s_wc[i] = wc[i];
+  constexpr int PQ = KK >= 4 ? KK / 4 : 1;
+  const int CA = C + 1;
+  float* s_wc = sm;             // [C][KK]
+  float* s_a = sm + C * KK;     // [64][C + 1]
+  for (int i = threadIdx.x; i < C * KK; i += 256) s_wc[i] = wc[i];
   const float bias = bc[0];
   const int64_t npix = static_cast<int64_t>(N) * H * W;
-  const int pl = threadIdx.x / kk, q = threadIdx.x % kk;
-  const int qi = q / k, qj = q % k;
-  for (int64_t p0 = blockIdx.x * static_cast<int64_t>(PB); p0 < npix; p0 += static_cast<int64_t>(gridDim.x) * PB) {
+  const int64_t ntiles = (npix + kDsTP - 1) / kDsTP;
+  const int p = threadIdx.x >> 2, part = threadIdx.x & 3;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     __syncthreads();
-    for (int i = threadIdx.x; i < PB * C; i += 256) {
-      const int64_t pix = p0 + i / C;
-      s_a[i] = pix < npix ? ld1<T>(a + pix * Cp + (i % C)) : 0.f;
+    ds_load_tile<T>(a, tile * kDsTP, npix, Cp, C, CA, s_a);
+    __syncthreads();
+    float acc[PQ];
+#pragma unroll
+    for (int j = 0; j < PQ; ++j) acc[j] = bias;
+    const float* ar = s_a + p * CA;
+    for (int ci = 0; ci < C; ++ci) {
+      const float av = ar[ci];
+      const float* wr = s_wc + ci * KK + part;
+#pragma unroll
+      for (int j = 0; j < PQ; ++j) acc[j] = fmaf(av, wr[4 * j], acc[j]);
     }
-    __syncthreads();
-    const int64_t pix = p0 + pl;
-    if (pl < PB && pix < npix) {
-      float acc = bias;
-      const float* ar = s_a + pl * C;
-      for (int ci = 0; ci < C; ++ci) acc = fmaf(ar[ci], s_wc[ci * kk + q], acc);
-      const int w = static_cast<int>(pix % W);
-      const int h = static_cast<int>((pix / W) % H);
-      const int64_t n = pix / (static_cast<int64_t>(W) * H);
-      logits[(n * H * k + static_cast<int64_t>(h) * k + qi) * (static_cast<int64_t>(W) * k) + static_cast<int64_t>(w) * k + qj] = acc;
+    const int64_t pix = tile * kDsTP + p;
+    if (pix < npix) {
+#pragma unroll
+      for (int j = 0; j < PQ; ++j) {
+        const int q = part + 4 * j;
+        if (q < KK) {
+          int64_t o;
+          ds_logit_index(pix, q, H, W, k, &o);
+          logits[o] = acc[j];
+        }
+      }
     }
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) dshead_bwd_kernel(const T* __restrict__ a,
-                                                         const float* __restrict__ dl, int N, int H, int W, int Cp,
-                                                         int C, int k, const float* __restrict__ wc,
-                                                         T* __restrict__ dA, int accumulate,
-                                                         float* __restrict__ dwc, float* __restrict__ dbc) {
+// dA[pix][ci] (+)= sum_q dl[pix][q] * wc[ci][q];  partial weight gradient of this block: dwc_part[block][ci][q] =
+// sum over the block's pixels of a[pix][ci] * dl[pix][q];  dbc_part[block] = sum of dl.
+template <typename T, int KK>
+__global__ void __launch_bounds__(256) dshead_bwd_kernel(const T* __restrict__ a, const float* __restrict__ dl, int N,
+                                                         int H, int W, int Cp, int C, int k,
+                                                         const float* __restrict__ wc, T* __restrict__ dA,
+                                                         int accumulate, float* __restrict__ dwc_part,
+                                                         float* __restrict__ dbc_part) {
   extern __shared__ float sm[];
-  const int kk = k * k;
-  const int PB = 256 / kk;
-  float* s_wc = sm;                 // [C][kk]
-  float* s_a = s_wc + C * kk;       // [PB][C]
-  float* s_dl = s_a + PB * C;       // [PB][kk]
-  __shared__ float s_db;
-  for (int i = threadIdx.x; i < C * kk; i += 256) s_wc[i] = wc[i];
-  if (threadIdx.x == 0) s_db = 0.f;
+  constexpr int KP = KK + 1, KW = KK + 4;
+  const int CA = C + 1, cvec = C >> 3, cpvec = Cp >> 3;
+  float* s_wc = sm;                        // [C][KK + 4]: the row of channel ci starts (ci / 8) % 4 words late
+  float* s_a = s_wc + C * KW;              // [64][C + 1]
+  float* s_dl = s_a + kDsTP * CA;          // [64][KK + 1]
+  __shared__ float s_red[8];
+  for (int i = threadIdx.x; i < C * KK; i += 256) {
+    const int ci = i / KK, q = i - ci * KK;
+    s_wc[ci * KW + q + ((ci >> 3) & 3)] = wc[i];
+  }
   const int64_t npix = static_cast<int64_t>(N) * H * W;
-  const int q = threadIdx.x % kk, cl = threadIdx.x / kk;  // this thread owns dwc[(cl + j*PB)][q]
-  const int nacc = (C + PB - 1) / PB;                      // <= 32
+  const int64_t ntiles = (npix + kDsTP - 1) / kDsTP;
+  const int p = threadIdx.x >> 2, part = threadIdx.x & 3;
+  const int nout = C * KK;
+  const int q_w = threadIdx.x % KK;        // 256 % KK == 0: the thread's weight-gradient column is fixed
   float acc[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) acc[j] = 0.f;
   float accb = 0.f;
-  for (int64_t p0 = blockIdx.x * static_cast<int64_t>(PB); p0 < npix; p0 += static_cast<int64_t>(gridDim.x) * PB) {
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     __syncthreads();
-    for (int i = threadIdx.x; i < PB * C; i += 256) {
-      const int64_t pix = p0 + i / C;
-      s_a[i] = pix < npix ? ld1<T>(a + pix * Cp + (i % C)) : 0.f;
-    }
-    {
-      const int pl = threadIdx.x / kk;
-      const int64_t pix = p0 + pl;
+    ds_load_tile<T>(a, tile * kDsTP, npix, Cp, C, CA, s_a);
+    for (int i = threadIdx.x; i < kDsTP * KK; i += 256) {
+      const int px = i / KK, q = i - px * KK;
+      const int64_t pix = tile * kDsTP + px;
       float g = 0.f;
-      if (pl < PB && pix < npix) {
-        const int w = static_cast<int>(pix % W);
-        const int h = static_cast<int>((pix / W) % H);
-        const int64_t n = pix / (static_cast<int64_t>(W) * H);
-        g = dl[(n * H * k + static_cast<int64_t>(h) * k + q / k) * (static_cast<int64_t>(W) * k) + static_cast<int64_t>(w) * k + q % k];
+      if (pix < npix) {
+        int64_t o;
+        ds_logit_index(pix, q, H, W, k, &o);
+        g = dl[o];
       }
-      if (pl < PB) s_dl[pl * kk + q] = g;
+      s_dl[px * KP + q] = g;
       accb += g;
     }
     __syncthreads();
-    // weight gradient partials
+    // ---- data gradient: thread (pixel p, channel vectors v = part, part + 4, ...), 8 channels at a time; the skew
+    // puts the four threads of a pixel on banks q + 0 / 1 / 2 / 3, threads of other pixels read the same words
+    const int64_t pix = tile * kDsTP + p;
+    const float* dr = s_dl + p * KP;
+    for (int v = part; v < cpvec; v += 4) {
+      V8 g;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (j < nacc) {
-        const int ci = cl + j * PB;
-        if (ci < C) {
-          float s = acc[j];
-          for (int pl = 0; pl < PB; ++pl) s = fmaf(s_a[pl * C + ci], s_dl[pl * kk + q], s);
-          acc[j] = s;
+      for (int j = 0; j < 8; ++j) g.f[j] = 0.f;
+      if (v < cvec) {
+        const float* wr = s_wc + v * 8 * KW + part;
+        for (int q = 0; q < KK; ++q) {
+          const float dv = dr[q];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g.f[j] = fmaf(dv, wr[j * KW + q], g.f[j]);
         }
       }
-    }
-    // data gradient: PB*Cp outputs
-    for (int i = threadIdx.x; i < PB * Cp; i += 256) {
-      const int pl = i / Cp, ci = i % Cp;
-      const int64_t pix = p0 + pl;
       if (pix < npix) {
-        float s = 0.f;
-        if (ci < C) {
-          const float* wr = s_wc + ci * kk;
-          const float* gr = s_dl + pl * kk;
-          for (int qq = 0; qq < kk; ++qq) s = fmaf(gr[qq], wr[qq], s);
+        T* dst = dA + pix * Cp + v * 8;
+        if (accumulate) {
+          const V8 old = load8<T>(dst);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g.f[j] += old.f[j];
         }
-        T* d = dA + pix * Cp + ci;
-        if (accumulate) s += ld1<T>(d);
-        st1<T>(d, s);
+        store8<T>(dst, g);
+      }
+    }
+    // ---- weight gradient partials: output o = tid + 256 j  ->  (ci = o / KK, q = q_w)
+    // (pixel loop outside: the dl value is read once for all of the thread's channels; ci = tid / KK + (256 / KK) j)
+    {
+      const float* ap = s_a + threadIdx.x / KK;
+#pragma unroll 2
+      for (int px = 0; px < kDsTP; ++px) {
+        const float d = s_dl[px * KP + q_w];
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (threadIdx.x + 256 * j < nout) acc[j] = fmaf(ap[px * CA + (256 / KK) * j], d, acc[j]);
       }
     }
   }
+  float* mine = dwc_part + static_cast<int64_t>(blockIdx.x) * nout;
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
-    if (j < nacc) {
-      const int ci = cl + j * PB;
-      if (ci < C && cl < PB) atomicAdd(dwc + ci * kk + q, acc[j]);
-    }
+    const int o = threadIdx.x + 256 * j;
+    if (o < nout) mine[o] = acc[j];
   }
   accb = warp_sum(accb);
-  if ((threadIdx.x & 31) == 0) atomicAdd(&s_db, accb);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = accb;
   __syncthreads();
-  if (threadIdx.x == 0) atomicAdd(dbc, s_db);
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += s_red[w];
+    dbc_part[blockIdx.x] = t;
+  }
 }
 
-__global__ void dshead_decompose_kernel(const float* __restrict__ dwc, const float* __restrict__ dbc,
-                                        const float* __restrict__ wt, const float* __restrict__ bt,
-                                        const float* __restrict__ w1, int C, int kk, float* __restrict__ dwt,
-                                        float* __restrict__ dbt, float* __restrict__ dw1, float* __restrict__ db1) {
-  // grid-stride over dwt entries; block 0 additionally does the small vectors
+// dwc_red[e] = sum over the blocks' partial rows; dbc_red = sum of the blocks' bias partials
+__global__ void __launch_bounds__(256) dshead_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bpart,
+                                                            int nparts, int n, float* __restrict__ red,
+                                                            float* __restrict__ bred) {
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e < n) {
+    float s = 0.f;
+    for (int r = 0; r < nparts; ++r) s += part[static_cast<int64_t>(r) * n + e];
+    red[e] = s;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    float b = 0.f;
+    for (int r = 0; r < nparts; ++r) b += bpart[r];
+    bred[0] = b;
+  }
+}
+
+// dwt[ci][co][q] += dwc[ci][q] * w1[co]
+__global__ void dshead_dwt_kernel(const float* __restrict__ dwc, const float* __restrict__ w1, int C, int kk,
+                                  float* __restrict__ dwt) {
   const int64_t total = static_cast<int64_t>(C) * C * kk;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -248,16 +323,31 @@ __global__ void dshead_decompose_kernel(const float* __restrict__ dwc, const flo
     const int ci = static_cast<int>(i / (static_cast<int64_t>(kk) * C));
     dwt[i] += dwc[ci * kk + q] * w1[co];
   }
-  if (blockIdx.x == 0) {
+}
+// one block per output channel co of the transposed conv:
+// dw1[co] += gb * bt[co] + sum_{ci,q} dwc[ci][q] * wt[ci][co][q];  dbt[co] += gb * w1[co];  db1 += gb
+__global__ void __launch_bounds__(256) dshead_dw1_kernel(const float* __restrict__ dwc, const float* __restrict__ dbc,
+                                                         const float* __restrict__ wt, const float* __restrict__ bt,
+                                                         const float* __restrict__ w1, int C, int kk,
+                                                         float* __restrict__ dbt, float* __restrict__ dw1,
+                                                         float* __restrict__ db1) {
+  __shared__ float s_red[8];
+  const int co = blockIdx.x;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < C * kk; i += 256) {
+    const int ci = i / kk, q = i - ci * kk;
+    s = fmaf(dwc[i], wt[(static_cast<int64_t>(ci) * C + co) * kk + q], s);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += s_red[w];
     const float gb = dbc[0];
-    for (int co = threadIdx.x; co < C; co += blockDim.x) {
-      float s = gb * bt[co];
-      for (int ci = 0; ci < C; ++ci)
-        for (int q = 0; q < kk; ++q) s = fmaf(dwc[ci * kk + q], wt[(static_cast<int64_t>(ci) * C + co) * kk + q], s);
-      dw1[co] += s;
-      dbt[co] += gb * w1[co];
-    }
-    if (threadIdx.x == 0) db1[0] += gb;
+    dw1[co] += t + gb * bt[co];
+    dbt[co] += gb * w1[co];
+    if (co == 0) db1[0] += gb;
   }
 }
 
@@ -564,6 +654,45 @@ __global__ void __launch_bounds__(128) softmax_rows_bwd_kernel(const float* __re
 }  // namespace mtbc
 
 using namespace mtbc;
+// k*k = 4 / 16 / 64 (k = 2 / 4 / 8) are compiled; C a multiple of 8 with C * k * k <= 8192 (32 accumulators per thread)
+template <typename T, int KK>
+static void dshead_fwd_launch(int g, size_t smem, cudaStream_t st, const void* a, int N, int H, int W, int Cp, int C, int k,
+                              const float* wc, const float* bc, float* logits) {
+  if (smem > 48 * 1024) cudaFuncSetAttribute(dshead_fwd_kernel<T, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  dshead_fwd_kernel<T, KK><<<g, 256, smem, st>>>(static_cast<const T*>(a), N, H, W, Cp, C, k, wc, bc, logits);
+}
+template <typename T, int KK>
+static void dshead_bwd_launch(int g, size_t smem, cudaStream_t st, const void* a, const float* dl, int N, int H, int W,
+                              int Cp, int C, int k, const float* wc, void* dA, int accumulate, float* dwc_part,
+                              float* dbc_part) {
+  if (smem > 48 * 1024) cudaFuncSetAttribute(dshead_bwd_kernel<T, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  dshead_bwd_kernel<T, KK><<<g, 256, smem, st>>>(static_cast<const T*>(a), dl, N, H, W, Cp, C, k, wc, static_cast<T*>(dA),
+                                                 accumulate, dwc_part, dbc_part);
+}
+#define MTBC_DISPATCH_KK(kk, fn, ...)                                   \
+  do {                                                                  \
+    if (mtbc::current_mode() & mtbc::MODE_ACT_FP32) {                   \
+      if ((kk) == 4) fn<float, 4>(__VA_ARGS__);                         \
+      else if ((kk) == 16) fn<float, 16>(__VA_ARGS__);                  \
+      else fn<float, 64>(__VA_ARGS__);                                  \
+    } else {                                                            \
+      if ((kk) == 4) fn<__nv_bfloat16, 4>(__VA_ARGS__);                 \
+      else if ((kk) == 16) fn<__nv_bfloat16, 16>(__VA_ARGS__);          \
+      else fn<__nv_bfloat16, 64>(__VA_ARGS__);                          \
+    }                                                                   \
+  } while (0)
+
+static int dshead_check(int32_t Cp, int32_t C, int32_t k) {
+  const int kk = k * k;
+  if (kk != 4 && kk != 16 && kk != 64) return set_error(MTBC_ERR_INVALID, "dshead: k must be 2, 4 or 8");
+  if (C % 8 != 0 || Cp % 8 != 0 || C > Cp) return set_error(MTBC_ERR_INVALID, "dshead: C %% 8 != 0 or C > Cp");
+  if (C * kk > 8192) return set_error(MTBC_ERR_INVALID, "dshead: C * k * k > 8192");
+  return MTBC_OK;
+}
+static int dshead_grid(int32_t N, int32_t H, int32_t W) {
+  const int64_t ntiles = cdiv(static_cast<int64_t>(N) * H * W, kDsTP);
+  return static_cast<int>(ntiles < 148 * 2 ? (ntiles < 1 ? 1 : ntiles) : 148 * 2);
+}
 #define ST(s) static_cast<cudaStream_t>(s)
 #define TP(p) static_cast<T*>(p)
 #define CTP(p) static_cast<const T*>(p)
@@ -593,41 +722,39 @@ int mtbc_dshead_compose(const float* wt, const float* bt, const float* w1, const
 }
 int mtbc_dshead_fwd(const void* a, int32_t N, int32_t H, int32_t W, int32_t Cp, int32_t C, int32_t k, const float* wc,
                     const float* bc, float* logits, void* stream) {
+  if (int rc = dshead_check(Cp, C, k)) return rc;
   const int kk = k * k;
-  if (kk > 256 || 256 % kk) return set_error(MTBC_ERR_INVALID, "dshead: k*k must divide 256");
-  const int PB = 256 / kk;
-  const int64_t npix = static_cast<int64_t>(N) * H * W;
-  int g = cdiv(npix, PB); if (g > 148 * 8) g = 148 * 8;
-  const size_t smem = (static_cast<size_t>(C) * kk + static_cast<size_t>(PB) * C) * sizeof(float);
-  if (smem > 48 * 1024) {
-    cudaFuncSetAttribute(dshead_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(dshead_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  }
-  MTBC_DISPATCH_ACT((dshead_fwd_kernel<T><<<g, 256, smem, ST(stream)>>>(CTP(a), N, H, W, Cp, C, k, wc, bc, logits)));
+  const int64_t ntiles = cdiv(static_cast<int64_t>(N) * H * W, kDsTP);
+  const int g = static_cast<int>(ntiles < 148 * 4 ? (ntiles < 1 ? 1 : ntiles) : 148 * 4);
+  const size_t smem = (static_cast<size_t>(C) * kk + static_cast<size_t>(kDsTP) * (C + 1)) * sizeof(float);
+  MTBC_DISPATCH_KK(kk, dshead_fwd_launch, g, smem, ST(stream), a, N, H, W, Cp, C, k, wc, bc, logits);
   return check_launch("dshead_fwd");
 }
+int mtbc_dshead_bwd_parts(int32_t N, int32_t H, int32_t W) { return dshead_grid(N, H, W); }
 int mtbc_dshead_bwd(const void* a, const float* dlogits, int32_t N, int32_t H, int32_t W, int32_t Cp, int32_t C,
-                    int32_t k, const float* wc, void* dA, int32_t accumulate, float* dwc, float* dbc, void* stream) {
+                    int32_t k, const float* wc, void* dA, int32_t accumulate, float* dwc_part, float* dbc_part,
+                    int32_t nparts, void* stream) {
+  if (int rc = dshead_check(Cp, C, k)) return rc;
   const int kk = k * k;
-  if (kk > 256 || 256 % kk) return set_error(MTBC_ERR_INVALID, "dshead: k*k must divide 256");
-  const int PB = 256 / kk;
-  if ((C + PB - 1) / PB > 32) return set_error(MTBC_ERR_INVALID, "dshead_bwd: C*k*k too large");
-  const int64_t npix = static_cast<int64_t>(N) * H * W;
-  int g = cdiv(npix, PB * 8); if (g > 148 * 2) g = 148 * 2; if (g < 1) g = 1;
-  const size_t smem = (static_cast<size_t>(C) * kk + static_cast<size_t>(PB) * C + static_cast<size_t>(PB) * kk) * sizeof(float);
-  if (smem > 48 * 1024) {
-    cudaFuncSetAttribute(dshead_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(dshead_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  }
-  MTBC_DISPATCH_ACT((dshead_bwd_kernel<T><<<g, 256, smem, ST(stream)>>>(CTP(a), dlogits, N, H, W, Cp, C, k, wc, TP(dA), accumulate, dwc, dbc)));
+  const int g = dshead_grid(N, H, W);
+  if (nparts != g) return set_error(MTBC_ERR_INVALID, "dshead_bwd: nparts %d != mtbc_dshead_bwd_parts() = %d", nparts, g);
+  const size_t smem = (static_cast<size_t>(C) * (kk + 4) + static_cast<size_t>(kDsTP) * (C + 1) +
+                       static_cast<size_t>(kDsTP) * (kk + 1)) * sizeof(float);
+  MTBC_DISPATCH_KK(kk, dshead_bwd_launch, g, smem, ST(stream), a, dlogits, N, H, W, Cp, C, k, wc, dA, accumulate, dwc_part,
+                   dbc_part);
   return check_launch("dshead_bwd");
 }
-int mtbc_dshead_decompose(const float* dwc, const float* dbc, const float* wt, const float* bt, const float* w1,
-                          int32_t C, int32_t k, float* dwt, float* dbt, float* dw1, float* db1, void* stream) {
-  const int kk = k * k;
-  const int64_t total = static_cast<int64_t>(C) * C * kk;
+int mtbc_dshead_decompose(float* dwc_part, float* dbc_part, int32_t nparts, const float* wt, const float* bt,
+                          const float* w1, int32_t C, int32_t k, float* dwt, float* dbt, float* dw1, float* db1,
+                          void* stream) {
+  const int kk = k * k, n = C * kk;
+  float* dwc = dwc_part + static_cast<int64_t>(nparts) * n;   // row nparts of both buffers receives the totals
+  float* dbc = dbc_part + nparts;
+  dshead_reduce_kernel<<<cdiv(n, 256), 256, 0, ST(stream)>>>(dwc_part, dbc_part, nparts, n, dwc, dbc);
+  const int64_t total = static_cast<int64_t>(C) * n;
   int g = cdiv(total, 256); if (g > 148 * 4) g = 148 * 4;
-  dshead_decompose_kernel<<<g, 256, 0, ST(stream)>>>(dwc, dbc, wt, bt, w1, C, kk, dwt, dbt, dw1, db1);
+  dshead_dwt_kernel<<<g, 256, 0, ST(stream)>>>(dwc, w1, C, kk, dwt);
+  dshead_dw1_kernel<<<C, 256, 0, ST(stream)>>>(dwc, dbc, wt, bt, w1, C, kk, dbt, dw1, db1);
   return check_launch("dshead_decompose");
 }
 

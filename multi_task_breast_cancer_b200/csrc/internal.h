@@ -49,6 +49,24 @@ int in_bwd_fused(const void* dA, const void* y, int N, int64_t HW, int Cp, const
                  float* dbeta, int C_true, int* counters, cudaStream_t st);
 int channel_sum_pipe(const void* t, int64_t npix, int Cp, int C_true, float* out, cudaStream_t st);
 
+// Launch with programmatic stream serialization (the kernel MUST call pdl_wait() before it touches anything another
+// kernel wrote).  MTBC_PDL=0 turns the attribute off (plain stream order).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
 }  // namespace mtbc

@@ -20,6 +20,15 @@ __device__ __forceinline__ bool elect_one() {
   return p != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization (internal.h: launch_pdl) may start while the
+// previous kernel of its stream is still draining: pdl_wait() blocks until that kernel (and, transitively, everything
+// before it) has completed and its writes are visible -- nothing produced by another kernel may be touched before it;
+// pdl_trigger() lets the NEXT kernel of the stream begin its own prologue (it is called after tcgen05.alloc, so a
+// dependent CTA can never take TMEM columns a CTA of this grid still has to allocate).  Both are no-ops in a plain launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

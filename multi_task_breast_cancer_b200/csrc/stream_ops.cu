@@ -137,6 +137,8 @@ __global__ void __launch_bounds__(256) in_apply_kernel(const T* __restrict__ y, 
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        float eps, float slope, T* __restrict__ a,
                                                        float* __restrict__ mean, float* __restrict__ rstd) {
+  pdl_trigger();   // programmatic dependent launch (ptx.cuh): wait before the first global access
+  pdl_wait();
   const int n = blockIdx.y, cvec = Cp / 8;
   const int64_t total = HW * cvec;
   const int64_t start = blockIdx.x * 256ll + threadIdx.x, stride = gridDim.x * 256ll;
@@ -178,6 +180,8 @@ __global__ void __launch_bounds__(256) in_apply_pool_kernel(const T* __restrict_
                                                             T* __restrict__ a,
                                                             T* __restrict__ pooled,
                                                             float* __restrict__ mean, float* __restrict__ rstd) {
+  pdl_trigger();   // programmatic dependent launch (ptx.cuh): wait before the first global access
+  pdl_wait();
   const int n = blockIdx.y, cvec = Cp / 8;
   const int Hp = H / 2, Wp = W / 2;
   const int64_t HW = static_cast<int64_t>(H) * W;
@@ -240,6 +244,8 @@ __global__ void __launch_bounds__(256) in_bwd_reduce_kernel(const T* __restrict_
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float slope,
                                                             float* __restrict__ s1, float* __restrict__ s2) {
+  pdl_trigger();   // programmatic dependent launch (ptx.cuh): wait before the first global access
+  pdl_wait();
   extern __shared__ float s_acc[];  // [2][Cp]
   const int n = blockIdx.y, cvec = Cp / 8;
   for (int i = threadIdx.x; i < 2 * Cp; i += 256) s_acc[i] = 0.f;
@@ -296,6 +302,8 @@ __global__ void __launch_bounds__(256) in_bwd_apply_kernel(const T* __restrict__
                                                            const float* __restrict__ beta, float slope,
                                                            const float* __restrict__ s1, const float* __restrict__ s2,
                                                            T* __restrict__ dy) {
+  pdl_trigger();   // programmatic dependent launch (ptx.cuh): wait before the first global access
+  pdl_wait();
   const int n = blockIdx.y, cvec = Cp / 8;
   const int64_t total = HW * cvec;
   const int64_t start = blockIdx.x * 256ll + threadIdx.x, stride = gridDim.x * 256ll;
@@ -344,6 +352,8 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const T* __restrict__
                                                            const T* __restrict__ dP, int H, int W, int Cp,
                                                            T* __restrict__ dA, int accumulate,
                                                            int64_t total) {
+  pdl_trigger();   // programmatic dependent launch (ptx.cuh): wait before the first global access
+  pdl_wait();
   const int cvec = Cp / 8, Hp = H / 2, Wp = W / 2;
   for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
     const int v = static_cast<int>(i % cvec);
@@ -504,13 +514,13 @@ int mtbc_in_apply(const void* y, int32_t N, int32_t H, int32_t W, int32_t Cp, co
   if (pooled) {
     if ((H & 1) || (W & 1)) return set_error(MTBC_ERR_INVALID, "in_apply: pooled output needs even H, W");
     const int gx = pick_gx(HW / 4 * cvec, 256, cvec, N, 2);
-    MTBC_DISPATCH_ACT((in_apply_pool_kernel<T><<<dim3(gx, N), 256, 0, ST(stream)>>>(CTP(y), H, W, Cp, stat_sum, stat_sq, gamma, beta, eps,
+    MTBC_DISPATCH_ACT((launch_pdl(in_apply_pool_kernel<T>, dim3(gx, N), dim3(256), 0, ST(stream), CTP(y), H, W, Cp, stat_sum, stat_sq, gamma, beta, eps,
                                                                                      slope, TP(a), TP(pooled), mean, rstd)));
   } else {
     if (use_pipe(N, HW, Cp))
       return in_apply_pipe(y, N, HW, Cp, stat_sum, stat_sq, gamma, beta, eps, slope, a, mean, rstd, ST(stream));
     const int gx = pick_gx(HW * cvec, 256, cvec, N, 4);
-    MTBC_DISPATCH_ACT((in_apply_kernel<T><<<dim3(gx, N), 256, 0, ST(stream)>>>(CTP(y), HW, Cp, stat_sum, stat_sq, gamma, beta, eps, slope,
+    MTBC_DISPATCH_ACT((launch_pdl(in_apply_kernel<T>, dim3(gx, N), dim3(256), 0, ST(stream), CTP(y), HW, Cp, stat_sum, stat_sq, gamma, beta, eps, slope,
                                                                                 TP(a), mean, rstd)));
   }
   return check_launch("in_apply");
@@ -523,7 +533,7 @@ int mtbc_in_bwd_reduce(const void* dA, const void* y, int32_t N, int32_t HW, int
     return in_bwd_reduce_pipe(dA, y, N, HW, Cp, mean, rstd, gamma, beta, slope, s1, s2, ST(stream));
   const int cvec = Cp / 8;
   const int gx = pick_gx(static_cast<int64_t>(HW) * cvec, 256, cvec, N, 8);
-  MTBC_DISPATCH_ACT((in_bwd_reduce_kernel<T><<<dim3(gx, N), 256, 2 * Cp * sizeof(float), ST(stream)>>>(CTP(dA), CTP(y), HW, Cp, mean, rstd,
+  MTBC_DISPATCH_ACT((launch_pdl(in_bwd_reduce_kernel<T>, dim3(gx, N), dim3(256), 2 * Cp * sizeof(float), ST(stream), CTP(dA), CTP(y), HW, Cp, mean, rstd,
                                                                                                          gamma, beta, slope, s1, s2)));
   return check_launch("in_bwd_reduce");
 }
@@ -536,7 +546,7 @@ int mtbc_in_bwd_apply(const void* dA, const void* y, int32_t N, int32_t HW, int3
                              ST(stream));
   const int cvec = Cp / 8;
   const int gx = pick_gx(static_cast<int64_t>(HW) * cvec, 256, cvec, N, 4);
-  MTBC_DISPATCH_ACT((in_bwd_apply_kernel<T><<<dim3(gx, N), 256, 0, ST(stream)>>>(CTP(dA), CTP(y), HW, Cp, mean, rstd, gamma, beta, slope, s1,
+  MTBC_DISPATCH_ACT((launch_pdl(in_bwd_apply_kernel<T>, dim3(gx, N), dim3(256), 0, ST(stream), CTP(dA), CTP(y), HW, Cp, mean, rstd, gamma, beta, slope, s1,
                                                                                   s2, TP(dy))));
   int rc = check_launch("in_bwd_apply");
   if (rc) return rc;
@@ -562,7 +572,7 @@ int mtbc_maxpool2_bwd(const void* a, const void* dP, int32_t N, int32_t H, int32
                       int32_t accumulate, void* stream) {
   const int64_t total = static_cast<int64_t>(N) * (H / 2) * (W / 2) * (Cp / 8);
   int g = cdiv(total, 256); if (g > 148 * 8) g = 148 * 8;
-  MTBC_DISPATCH_ACT((maxpool2_bwd_kernel<T><<<g, 256, 0, ST(stream)>>>(CTP(a), CTP(dP), H, W, Cp, TP(dA), accumulate, total)));
+  MTBC_DISPATCH_ACT((launch_pdl(maxpool2_bwd_kernel<T>, dim3(g), dim3(256), 0, ST(stream), CTP(a), CTP(dP), H, W, Cp, TP(dA), accumulate, total)));
   return check_launch("maxpool2_bwd");
 }
 int mtbc_upsample2_fwd(const void* x, int32_t N, int32_t H, int32_t W, int32_t Cp, void* y, void* stream) {

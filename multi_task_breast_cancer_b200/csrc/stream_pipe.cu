@@ -236,6 +236,8 @@ in_apply_pipe_kernel(PipeGeom g, const __nv_bfloat16* __restrict__ y, const floa
                      const float* __restrict__ ssq, const float* __restrict__ gamma, const float* __restrict__ beta,
                      float inv_hw, float eps, float slope, __nv_bfloat16* __restrict__ a, float* __restrict__ mean,
                      float* __restrict__ rstd) {
+  pdl_trigger();   // programmatic dependent launch (ptx.cuh): wait before the first global access
+  pdl_wait();
   extern __shared__ __align__(128) uint8_t pipe_smem[];
   __shared__ uint64_t s_full[kPipeMaxStages], s_empty[kPipeMaxStages];
   ApplyBody b;
@@ -321,6 +323,8 @@ in_bwd_reduce_pipe_kernel(PipeGeom g, const __nv_bfloat16* __restrict__ dA, cons
                           const float* __restrict__ mean, const float* __restrict__ rstd,
                           const float* __restrict__ gamma, const float* __restrict__ beta, float slope,
                           float* __restrict__ s1, float* __restrict__ s2) {
+  pdl_trigger();   // programmatic dependent launch (ptx.cuh): wait before the first global access
+  pdl_wait();
   extern __shared__ __align__(128) uint8_t pipe_smem[];
   __shared__ uint64_t s_full[kPipeMaxStages], s_empty[kPipeMaxStages];
   __shared__ float s_stage[16 * kPipeMaxThreads];
@@ -386,6 +390,8 @@ in_bwd_apply_pipe_kernel(PipeGeom g, const __nv_bfloat16* __restrict__ dA, const
                          const float* __restrict__ gamma, const float* __restrict__ beta, float slope, float inv_hw,
                          const float* __restrict__ s1, const float* __restrict__ s2, __nv_bfloat16* __restrict__ dy,
                          float* __restrict__ dgamma, float* __restrict__ dbeta, int N, int C_true) {
+  pdl_trigger();   // programmatic dependent launch (ptx.cuh): wait before the first global access
+  pdl_wait();
   extern __shared__ __align__(128) uint8_t pipe_smem[];
   __shared__ uint64_t s_full[kPipeMaxStages], s_empty[kPipeMaxStages];
   // affine gradients (dgamma[c] += sum_n s2[n][c], dbeta[c] += sum_n s1[n][c]): the statistics are final before this
@@ -636,6 +642,8 @@ struct ChanSumBody {
 
 __global__ void __launch_bounds__(kPipeMaxThreads + 32, 2)
 channel_sum_pipe_kernel(PipeGeom g, const __nv_bfloat16* __restrict__ t, int C_true, float* __restrict__ out) {
+  pdl_trigger();   // programmatic dependent launch (ptx.cuh): wait before the first global access
+  pdl_wait();
   extern __shared__ __align__(128) uint8_t pipe_smem[];
   __shared__ uint64_t s_full[kPipeMaxStages], s_empty[kPipeMaxStages];
   __shared__ float s_stage[8 * kPipeMaxThreads];
@@ -722,7 +730,7 @@ int in_apply_pipe(const void* y, int N, int64_t HW, int Cp, const float* ssum, c
   const PipeLaunch L = pipe_plan(N, HW, Cp, 1, true);
   static bool attr = false;
   if (!attr) { int rc = pipe_attr(in_apply_pipe_kernel, 200 * 1024); if (rc) return rc; attr = true; }
-  in_apply_pipe_kernel<<<L.grid, L.launch_threads, L.smem_in1, st>>>(
+  launch_pdl(in_apply_pipe_kernel, dim3(L.grid), dim3(L.launch_threads), L.smem_in1, st, 
       L.g, static_cast<const __nv_bfloat16*>(y), ssum, ssq, gamma, beta, 1.f / static_cast<float>(HW), eps, slope,
       static_cast<__nv_bfloat16*>(a), mean, rstd);
   return check_launch("in_apply_pipe");
@@ -733,7 +741,7 @@ int in_bwd_reduce_pipe(const void* dA, const void* y, int N, int64_t HW, int Cp,
   const PipeLaunch L = pipe_plan(N, HW, Cp, 2, false);
   static bool attr = false;
   if (!attr) { int rc = pipe_attr(in_bwd_reduce_pipe_kernel, 200 * 1024); if (rc) return rc; attr = true; }
-  in_bwd_reduce_pipe_kernel<<<L.grid, L.launch_threads, L.smem_in1, st>>>(
+  launch_pdl(in_bwd_reduce_pipe_kernel, dim3(L.grid), dim3(L.launch_threads), L.smem_in1, st, 
       L.g, static_cast<const __nv_bfloat16*>(dA), static_cast<const __nv_bfloat16*>(y), mean, rstd, gamma, beta, slope,
       s1, s2);
   return check_launch("in_bwd_reduce_pipe");
@@ -745,7 +753,7 @@ int in_bwd_apply_pipe(const void* dA, const void* y, int N, int64_t HW, int Cp, 
   const PipeLaunch L = pipe_plan(N, HW, Cp, 2, true);
   static bool attr = false;
   if (!attr) { int rc = pipe_attr(in_bwd_apply_pipe_kernel, 200 * 1024); if (rc) return rc; attr = true; }
-  in_bwd_apply_pipe_kernel<<<L.grid, L.launch_threads, L.smem_in1, st>>>(
+  launch_pdl(in_bwd_apply_pipe_kernel, dim3(L.grid), dim3(L.launch_threads), L.smem_in1, st, 
       L.g, static_cast<const __nv_bfloat16*>(dA), static_cast<const __nv_bfloat16*>(y), mean, rstd, gamma, beta, slope,
       1.f / static_cast<float>(HW), s1, s2, static_cast<__nv_bfloat16*>(dy), (dgamma && dbeta) ? dgamma : nullptr, dbeta,
       N, C_true);
@@ -756,7 +764,7 @@ int channel_sum_pipe(const void* t, int64_t npix, int Cp, int C_true, float* out
   const PipeLaunch L = pipe_plan(1, npix, Cp, 1, false);
   static bool attr = false;
   if (!attr) { int rc = pipe_attr(channel_sum_pipe_kernel, 200 * 1024); if (rc) return rc; attr = true; }
-  channel_sum_pipe_kernel<<<L.grid, L.launch_threads, L.smem_in1, st>>>(L.g, static_cast<const __nv_bfloat16*>(t), C_true, out);
+  launch_pdl(channel_sum_pipe_kernel, dim3(L.grid), dim3(L.launch_threads), L.smem_in1, st, L.g, static_cast<const __nv_bfloat16*>(t), C_true, out);
   return check_launch("channel_sum_pipe");
 }
 

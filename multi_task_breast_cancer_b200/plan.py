@@ -672,14 +672,17 @@ class Plan:
         def backward():
             if not self.seg_grad_active[idx]:
                 return []
-            dwc = self.bwd_arena.alloc(Cc, kk)
-            dbc = self.bwd_arena.alloc(1)
+            # per-block partial rows (+ one row of totals), written whole by the kernel: not in the zeroed arena
+            nparts = int(_lib.load().mtbc_dshead_bwd_parts(f.N, f.H, f.W))
+            dwc = torch.empty(nparts + 1, Cc * kk, dtype=torch.float32, device=self.device)
+            dbc = torch.empty(nparts + 1, dtype=torch.float32, device=self.device)
+            self._keep.extend((dwc, dbc))
             g = a.grad()
             blk = [_annot(_mk("mtbc_dshead_bwd", ptr(f.t), ptr(dlog), f.N, f.H, f.W, f.Cp, Cc, k, ptr(wc), ptr(g.t),
-                              int(a.g_init), ptr(dwc), ptr(dbc)), f"{a.name} dshead k{k} bwd",
+                              int(a.g_init), ptr(dwc), ptr(dbc), nparts), f"{a.name} dshead k{k} bwd",
                           f.N * f.H * f.W * (4.0 * Cc + 4 * kk)),
-                   _mk("mtbc_dshead_decompose", ptr(dwc), ptr(dbc), ptr(self.P(wt)), ptr(self.P(bt)), ptr(self.P(w1)),
-                       Cc, k, ptr(self.grad_view[wt]), ptr(self.grad_view[bt]), ptr(self.grad_view[w1]),
+                   _mk("mtbc_dshead_decompose", ptr(dwc), ptr(dbc), nparts, ptr(self.P(wt)), ptr(self.P(bt)),
+                       ptr(self.P(w1)), Cc, k, ptr(self.grad_view[wt]), ptr(self.grad_view[bt]), ptr(self.grad_view[w1]),
                        ptr(self.grad_view[b1]))]
             a.g_init = True
             self._mark_grad(wt, bt, w1, b1)

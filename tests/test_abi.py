@@ -32,7 +32,7 @@ def test_ctypes_signatures_match_header(lib):
 
 def test_abi_version_and_error_string(lib):
     from multi_task_breast_cancer_b200 import _lib, build
-    assert lib.mtbc_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.mtbc_abi_version() == _lib.ABI_VERSION == 4
     assert isinstance(lib.mtbc_last_error(), bytes)
     # the digest compiled into the binary is the digest of the sources on disk (no side-car stamp file)
     assert build.lib_digest() == build._digest()

@@ -151,7 +151,8 @@ def test_head1x1(D, args):
     _run(D, D.head1x1_case, *args)
 
 
-@pytest.mark.parametrize("args", [(2, 8, 8, 128, 8), (2, 16, 16, 64, 4), (3, 16, 16, 32, 2)])
+@pytest.mark.parametrize("args", [(2, 8, 8, 128, 8), (2, 16, 16, 64, 4), (3, 16, 16, 32, 2), (2, 24, 40, 24, 2), (3, 32, 32, 48, 4),
+                                  (32, 32, 32, 128, 8)])
 def test_composed_deep_supervision_head(D, args):
     _run(D, D.dshead_case, *args)
 

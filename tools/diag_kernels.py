@@ -473,11 +473,13 @@ def dshead_case(N, H, W, C, k):
         dl = rnd(N, 1, H * k, W * k)
         ref.backward(dl)
         dA = Feat.empty(N, H, W, C)
-        dwc = torch.zeros(C, k * k, device=dev); dbc = torch.zeros(1, device=dev)
+        nparts = int(_lib.load().mtbc_dshead_bwd_parts(N, H, W))
+        # partial rows are written whole by the kernel: poison them to prove nothing relies on a zeroed buffer
+        dwc = torch.full((nparts + 1, C * k * k), float("nan"), device=dev); dbc = torch.full((nparts + 1,), float("nan"), device=dev)
         _lib.call("mtbc_dshead_bwd", ops.ptr(af.t), ops.ptr(dl), N, H, W, af.Cp, C, k, ops.ptr(wc), ops.ptr(dA.t), 0,
-                  ops.ptr(dwc), ops.ptr(dbc), None)
+                  ops.ptr(dwc), ops.ptr(dbc), nparts, None)
         g = [torch.zeros_like(t) for t in (wt, bt, w1, b1)]
-        _lib.call("mtbc_dshead_decompose", ops.ptr(dwc), ops.ptr(dbc), ops.ptr(wt), ops.ptr(bt), ops.ptr(w1), C, k,
+        _lib.call("mtbc_dshead_decompose", ops.ptr(dwc), ops.ptr(dbc), nparts, ops.ptr(wt), ops.ptr(bt), ops.ptr(w1), C, k,
                   ops.ptr(g[0]), ops.ptr(g[1]), ops.ptr(g[2]), ops.ptr(g[3]), None)
         report(name + " dA", dA.to_nchw(), ps[0].grad, tol=1e-2)
         for nm, mine, r in zip(("dwt", "dbt", "dw1", "db1"), g, ps[1:]):
@@ -625,6 +627,8 @@ def run_group(group):
         dshead_case(2, 8, 8, 128, 8)
         dshead_case(2, 16, 16, 64, 4)
         dshead_case(3, 16, 16, 32, 2)
+        dshead_case(2, 24, 40, 24, 2)
+        dshead_case(3, 32, 32, 48, 4)
         gap_fc_case(3, 4, 4, 512)
         flat_fc_case(3, 16, 16, 256)
     elif group == "loss":
