@@ -114,6 +114,22 @@ typedef struct {
    *    the same way in shared memory and issues a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (fp32-grade products). */
   int32_t dtype;
   const void* wpack_lo;
+  /* Fused InstanceNorm + LeakyReLU backward statistics (dtype 0, single-output non-accumulating 3x3 data gradient on a
+   * halo-eligible shape with at most 64 GEMM columns per N tile; creation fails with MTBC_ERR_INVALID otherwise and the
+   * caller keeps mtbc_in_bwd_reduce).  With bwd_y != NULL the GEMM result D is the gradient of a = LeakyReLU(IN(y))
+   * (training_multitask.py:100 `loss.backward()` through MTnnUNet.py:35-36 / MONAI ADN): the epilogue reads y (bf16 NHWC,
+   * the geometry of `out`), forms gg = z > 0 ? D : bwd_slope * D with z = gamma * (y - mean) * rstd + beta from the fp32
+   * accumulator, stores gg in `out` instead of D, and adds sum(gg) to stat_sum[n][c] and sum(gg * (y - mean) * rstd) to
+   * stat_sq[n][c] -- exactly what mtbc_in_bwd_reduce leaves in s1 / s2, so only mtbc_in_bwd_apply (called with
+   * slope = 1, its input already carries the LeakyReLU factor) remains: 6 instead of 10 bytes per element for the
+   * normalisation backward of a single-consumer tensor.  bwd_mean / bwd_rstd: fp32 [N][stat_C]; bwd_gamma / bwd_beta:
+   * fp32 [>= stat_C] or NULL. */
+  const void* bwd_y;
+  const float* bwd_mean;
+  const float* bwd_rstd;
+  const float* bwd_gamma;
+  const float* bwd_beta;
+  float bwd_slope;
 } mtbc_conv_gemm_desc;
 
 /* One tap of a weight-gradient GEMM: dW[tap][co][k0 + ci] += sum_pixels A[a_view][pixel + (a_dh,a_dw)][ci] *

@@ -36,7 +36,9 @@ class ConvGemmDesc(C.Structure):
                 ("W", c_i32), ("H", c_i32), ("N", c_i32), ("epi_mode", c_i32), ("out", c_vp), ("out_C", c_i32),
                 ("up_k", c_i32), ("up_cp", c_i32), ("bias", c_vp), ("stat_sum", c_vp), ("stat_sq", c_vp),
                 ("stat_C", c_i32), ("accumulate", c_i32), ("nouts", c_i32), ("outs", OutSlice * MAX_VIEWS),
-                ("dtype", c_i32), ("wpack_lo", c_vp)]
+                ("dtype", c_i32), ("wpack_lo", c_vp),
+                ("bwd_y", c_vp), ("bwd_mean", c_vp), ("bwd_rstd", c_vp), ("bwd_gamma", c_vp), ("bwd_beta", c_vp),
+                ("bwd_slope", c_f32)]
 
 
 class WgradTap(C.Structure):

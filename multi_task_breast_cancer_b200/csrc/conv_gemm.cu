@@ -662,6 +662,24 @@ int encode_act(CUtensorMap* m, const mtbc_act_view& v, int kc, int TW, int TH, i
   if (r != CUDA_SUCCESS) return set_error(MTBC_ERR_CUDA, "cuTensorMapEncodeTiled(act) failed: %d", (int)r);
   return 0;
 }
+// Dense bf16 NHWC tensor seen as whole image-row segments: dims (W * C / 2 words, H, N), box (box_w * C / 2 words, box_h,
+// 1), no swizzle -- one TMA row per image row of the box instead of one per pixel, for tiles that are read back with
+// ordinary shared-memory loads (pixel pitch C * 2 bytes inside the tile).
+int encode_rows(CUtensorMap* m, const void* ptr, int C, int W, int H, int N, int box_w, int box_h) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  if (!enc) return set_error(MTBC_ERR_NO_DEVICE, "cuTensorMapEncodeTiled not available");
+  if (C % 8 != 0 || (reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || box_w * C / 2 > 256 || box_h > 256)
+    return set_error(MTBC_ERR_INVALID, "row view: C %% 8 != 0, pointer not 16B aligned or box too large");
+  cuuint64_t gdim[3] = {(cuuint64_t)W * C / 2, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t gstr[2] = {(cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[3] = {(cuuint32_t)(box_w * C / 2), (cuuint32_t)box_h, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(MTBC_ERR_CUDA, "cuTensorMapEncodeTiled(rows) failed: %d", (int)r);
+  return 0;
+}
 int encode_w(CUtensorMap* m, const void* w, int ktot, int nrows, int ntaps, int kc, int BN, int fp32) {
   PFN_tmapEncodeTiled enc = get_encode();
   if (!enc) return set_error(MTBC_ERR_NO_DEVICE, "cuTensorMapEncodeTiled not available");
@@ -731,6 +749,8 @@ int conv_gemm_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
     int rc = conv_halo_try_create(d, out);  // halo-tile kernel for 3x3 convs on large planes (conv_halo.cu)
     if (rc <= 0) return rc;                  // 0 = created, < 0 = error, > 0 = not eligible -> generic kernel below
   }
+  if (d->bwd_y != nullptr)
+    return set_error(MTBC_ERR_INVALID, "conv_gemm: fused InstanceNorm backward statistics need a halo-eligible 3x3 shape");
   if (d->nouts > 0) return set_error(MTBC_ERR_INVALID, "conv_gemm: routed outputs need a halo-eligible 3x3 shape");
   if (d->nviews < 1 || d->nviews > MTBC_MAX_VIEWS || d->nseg < 1 || d->nseg > MTBC_MAX_SEGS)
     return set_error(MTBC_ERR_INVALID, "conv_gemm: bad nviews/nseg (%d, %d)", d->nviews, d->nseg);

@@ -41,6 +41,7 @@ struct HaloOut {
 struct ConvHaloParams {
   CUtensorMap amap[MTBC_MAX_VIEWS];
   CUtensorMap wmap[2];
+  CUtensorMap ymap;     // fused InstanceNorm backward: the y tile of an output tile as 16 G image-row segments of 8 pixels
   HaloSrc src[MTBC_MAX_VIEWS];
   HaloOut outs[MTBC_MAX_VIEWS];  // column ranges of the GEMM output -> destination tensors (>= 1 entry)
   int32_t nsrc, nouts;
@@ -54,6 +55,13 @@ struct ConvHaloParams {
   const float* bias;
   float* stat_sum;
   float* stat_sq;
+  // Fused InstanceNorm + LeakyReLU backward statistics (mtbc_conv_gemm_desc.bwd_y): the accumulator is the gradient of
+  // a = LeakyReLU(IN(y)); the epilogue reads the y tile (same geometry as the output), turns the result into
+  // gg = z > 0 ? D : slope * D, stores gg and keeps sum(gg), sum(gg * (y - mean)) in its statistics registers.
+  const __nv_bfloat16* bwd_y;
+  const float *bwd_mean, *bwd_rstd, *bwd_gamma, *bwd_beta;
+  float bwd_slope;
+  int32_t y_stages, y_stage_bytes, y_rowb;   // y tile ring behind the halo ring (dense: pixel pitch y_rowb = 2 * out_C bytes)
 };
 
 constexpr int kHaloMaxStages = 8;
@@ -145,11 +153,12 @@ template <int V> struct IntC { static constexpr int value = V; };
 // P = column parts per TMEM lane quarter: 4 * P epilogue warps.  P = 2 everywhere except the 64-column G = 2 layers,
 // whose epilogue is a per-warp dependent chain (TMEM load -> statistics -> pack -> store, ~2600 cycles per tile
 // against ~1100 cycles of MMAs, profiles/r01f): with P = 4 every warp owns one 16-column chunk and the chain halves.
-template <int RACC, int P>
+template <int RACC, int P, bool BWD = false>
 __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t tmem_base, int t_begin, int t_end,
                                               int ntile, int warp, int lane, const float* s_bias,
                                               float (*s_part)[2][256], const HaloChunk* s_chunk,
-                                              uint64_t* s_accfull, uint64_t* s_accempty) {
+                                              uint64_t* s_accfull, uint64_t* s_accempty, float (*s_bw)[64],
+                                              const uint8_t* smem_y, uint64_t* s_yfull, uint64_t* s_yempty) {
   constexpr int kEpiWarps = 4 * P;
   constexpr int kEpiThreads = kEpiWarps * 32;
   const int q = warp & 3;                  // TMEM lane quarter this warp may read
@@ -169,6 +178,9 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
   float* const stat_sum = p.stat_sum;
   float* const stat_sq = p.stat_sq;
   constexpr int NR = RACC > 0 ? RACC / P : 1;   // columns of this warp's part
+  constexpr bool bwd = BWD && RACC > 0;   // fused InstanceNorm backward statistics (its own instantiation)
+  const float bwd_slope = p.bwd_slope;
+  const __nv_bfloat16* const out0 = p.outs[0].ptr;
   float rs[NR], rq[NR];
 #pragma unroll
   for (int i = 0; i < NR; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
@@ -180,8 +192,11 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
     for (int i = etid; i < BN; i += kEpiThreads) {
       if (ntile * bn1 + (i % bn1) >= stat_C) continue;   // GEMM pad column of a dense tensor: no such channel
       const int64_t o = static_cast<int64_t>(n) * stat_C + ntile * bn1 + (i % bn1);   // G = 2: both rows -> one channel
-      atomicAdd(stat_sum + o, s_part[0][0][i] + s_part[1][0][i] + s_part[2][0][i] + s_part[3][0][i]);
-      atomicAdd(stat_sq + o, s_part[0][1][i] + s_part[1][1][i] + s_part[2][1][i] + s_part[3][1][i]);
+      const float t0 = s_part[0][0][i] + s_part[1][0][i] + s_part[2][0][i] + s_part[3][0][i];
+      float t1 = s_part[0][1][i] + s_part[1][1][i] + s_part[2][1][i] + s_part[3][1][i];
+      if (bwd) t1 *= p.bwd_rstd[o];   // sum gg * (y - mean)  ->  sum gg * xhat
+      atomicAdd(stat_sum + o, t0);
+      atomicAdd(stat_sq + o, t1);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
   };
@@ -204,12 +219,46 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
     }
   };
 
+  // fused InstanceNorm backward: per accumulator column [0] mean, [1] gamma * rstd, [2] beta of sample n
+  auto load_consts = [&](int n) {
+    for (int i = etid; i < BN; i += kEpiThreads) {
+      const int c = ntile * bn1 + (i % bn1);
+      float mu = 0.f, zc = 0.f, zb = 1.f;   // GEMM pad column: accumulator is exactly 0, any branch will do
+      if (c < stat_C) {
+        const int64_t o = static_cast<int64_t>(n) * stat_C + c;
+        mu = p.bwd_mean[o];
+        zc = (p.bwd_gamma ? p.bwd_gamma[c] : 1.f) * p.bwd_rstd[o];
+        zb = p.bwd_beta ? p.bwd_beta[c] : 0.f;
+      }
+      s_bw[0][i] = mu; s_bw[1][i] = zc; s_bw[2][i] = zb;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+  };
+
   // one 16-column chunk: bias, statistics, bf16 store / accumulate
-  auto do_chunk = [&](int k, auto jc, uint32_t (&r)[16], int64_t pix, const HaloChunk& hc) {
+  auto do_chunk = [&](int k, auto jc, uint32_t (&r)[16], int64_t pix, const HaloChunk& hc, const uint4 (&yq)[2]) {
     constexpr int J = decltype(jc)::value;   // position of the chunk inside this warp's half (RACC > 0 only)
     float v[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+    if constexpr (bwd) {
+      const uint32_t yw[8] = {yq[0].x, yq[0].y, yq[0].z, yq[0].w, yq[1].x, yq[1].y, yq[1].z, yq[1].w};
+      const float* mu = s_bw[0] + k * 16;
+      const float* zc = s_bw[1] + k * 16;
+      const float* zb = s_bw[2] + k * 16;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float yv = __uint_as_float((i & 1) ? (yw[i >> 1] & 0xffff0000u) : (yw[i >> 1] << 16));
+        const float yc = yv - mu[i];
+        const float z = fmaf(yc, zc[i], zb[i]);
+        const float gg = z > 0.f ? v[i] : v[i] * bwd_slope;
+        v[i] = gg;
+        rs[J * 16 + i] += gg;
+        rq[J * 16 + i] = fmaf(gg, yc, rq[J * 16 + i]);
+      }
+      emit_bf16x16_n(hc.base + pix * hc.out_C, v, false, hc.nvalid, hc.wide != 0);
+      return;
+    }
     if (has_bias) {
       const float4* b4 = reinterpret_cast<const float4*>(s_bias + k * 16);
 #pragma unroll
@@ -247,13 +296,30 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
   }
   // statistics path: this warp's one or two chunk descriptors live in registers
   HaloChunk hc0 = s_chunk[k_begin], hc1 = s_chunk[(NR > 16) ? k_begin + 1 : k_begin];
+  // fused InstanceNorm backward: the producer lane streams the y tile of every output tile into a ring behind the halo
+  // ring (TMA, swizzled rows of y_rowb bytes); this thread's two 16-byte pieces per chunk sit at tile-invariant offsets
+  constexpr int NC = NR > 16 ? 2 : 1;
+  int yoff[NC][2];
+  int ys = 0;
+  uint32_t yph = 0;
+  if constexpr (bwd) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int col = (k_begin + c) * 16;
+      const int prow = col / bn1, ch0 = col - prow * bn1;
+      const int r = G == 2 ? (2 * th + prow) * 8 + tw : row;   // pixel inside the tile, image-row major
+      yoff[c][0] = r * p.y_rowb + ch0 * 2;
+      yoff[c][1] = yoff[c][0] + 16;
+    }
+    if (t_begin < t_end) load_consts(cur_n);
+  }
   int it = 0;
   for (int t = t_begin; t < t_end; ++t, ++it) {
     const int buf = it & 1;
     const uint32_t acc_phase = (it >> 1) & 1;
     const int w = tc * 8 + tw;
     const int h = (tr * 16 + th) * G;   // G = 2: row of the upper pixel; the lower one is folded into s_chunk[k].base
-    if (RACC > 0 && n != cur_n) { flush_regs(cur_n); cur_n = n; }
+    if (RACC > 0 && n != cur_n) { flush_regs(cur_n); cur_n = n; if (bwd) load_consts(n); }
     const int64_t pix = (static_cast<int64_t>(n) * H + h) * W + w;
     mbar_wait(&s_accfull[buf], acc_phase);
     tc_fence_after();
@@ -275,10 +341,26 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
       tc_fence_before();
       __syncwarp();
       if (lane == 0 && !p.late_release) mbar_arrive(&s_accempty[buf]);
-      do_chunk(k_begin, IntC<0>{}, r[0], pix, hc0);
-      if constexpr (NR > 16) do_chunk(k_begin + 1, IntC<1>{}, r[1], pix, hc1);
+      uint4 yq[NC][2];
+      if constexpr (bwd) {
+        mbar_wait(&s_yfull[ys], yph);
+        const uint8_t* yb = smem_y + ys * p.y_stage_bytes;
+        // (channels the dense tensor lacks read as 0: their accumulator columns are exactly 0 anyway)
+        yq[0][0] = hc0.nvalid >= 8 ? *reinterpret_cast<const uint4*>(yb + yoff[0][0]) : make_uint4(0, 0, 0, 0);
+        yq[0][1] = hc0.nvalid >= 16 ? *reinterpret_cast<const uint4*>(yb + yoff[0][1]) : make_uint4(0, 0, 0, 0);
+        if constexpr (NC > 1) {
+          yq[NC - 1][0] = hc1.nvalid >= 8 ? *reinterpret_cast<const uint4*>(yb + yoff[NC - 1][0]) : make_uint4(0, 0, 0, 0);
+          yq[NC - 1][1] = hc1.nvalid >= 16 ? *reinterpret_cast<const uint4*>(yb + yoff[NC - 1][1]) : make_uint4(0, 0, 0, 0);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_yempty[ys]);   // values are in registers: hand the slot back
+        if (++ys == p.y_stages) { ys = 0; yph ^= 1u; }
+      }
+      do_chunk(k_begin, IntC<0>{}, r[0], pix, hc0, yq[0]);
+      if constexpr (NR > 16) do_chunk(k_begin + 1, IntC<1>{}, r[1], pix, hc1, yq[NC - 1]);
       if (p.late_release) { __syncwarp(); if (lane == 0) mbar_arrive(&s_accempty[buf]); }
     } else {
+      const uint4 ynone[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
 #pragma unroll 1
       for (int k = k_begin; k < k_end; k += 2) {
         const bool two = (k + 1 < k_end);   // warp uniform
@@ -293,7 +375,7 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u)
-          if (u == 0 || two) do_chunk(k + u, IntC<0>{}, r[u], pix, s_chunk[k + u]);
+          if (u == 0 || two) do_chunk(k + u, IntC<0>{}, r[u], pix, s_chunk[k + u], ynone);
       }
       if (k_begin >= k_end || p.late_release) {   // (no chunk for this warp: still one arrival per warp and tile)
         tc_fence_before();
@@ -309,7 +391,9 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
 
 // MINB = resident CTAs per SM the register budget is compiled for: 2 for the narrow layers (small resident weights, two
 // CTAs overlap each other's pipeline bubbles), 1 for wide N tiles (no spills, one CTA owns the SM).
-template <int MINB, int P>
+// BWD = the fused InstanceNorm-backward-statistics epilogue (its own kernels, so the forward / plain data-gradient kernels'
+// register allocation does not depend on it)
+template <int MINB, int P, bool BWD = false>
 __global__ void __launch_bounds__((MINB == 2 ? 64 : 96) + 128 * P, MINB) conv_halo_kernel(const __grid_constant__ ConvHaloParams p) {
   constexpr int kEpiWarps = 4 * P;
   constexpr int kEpiThreads = kEpiWarps * 32;
@@ -322,11 +406,14 @@ __global__ void __launch_bounds__((MINB == 2 ? 64 : 96) + 128 * P, MINB) conv_ha
   __shared__ float s_part[4][2][256];  // [lane quarter][sum|sumsq][col]: per-warp column partials at a flush
   __shared__ HaloChunk s_chunk[16];    // destination of every 16-column chunk of this CTA's N tile
   __shared__ uint32_t s_cb[2][64];     // MMA lanes' chunk schedule: weight-block descriptor (low word) | 64-wide flag
+  __shared__ float s_bw[3][64];        // fused InstanceNorm backward: per accumulator column mean, gamma * rstd, beta
+  __shared__ uint64_t s_yfull[4], s_yempty[4];   // ... and the y tile ring
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_b = smem;                       // resident weights: [9 taps][source][chunk][BN x kc]
   uint8_t* smem_a = smem + p.b_total_bytes;     // halo ring
+  uint8_t* smem_y = smem_a + p.stages * p.a_stage_bytes;   // y tile ring (fused InstanceNorm backward only)
   const int ntile = blockIdx.y;
   const int BN = p.BN;
   // contiguous tile range per CTA: neighbouring tiles share halo rows in L2 and mostly belong to one sample, so the
@@ -351,6 +438,7 @@ __global__ void __launch_bounds__((MINB == 2 ? 64 : 96) + 128 * P, MINB) conv_ha
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&s_afull[s], 1); mbar_init(&s_aempty[s], 1); }
     mbar_init(&s_bfull, 1);
+    for (int s = 0; s < p.y_stages; ++s) { mbar_init(&s_yfull[s], 1); mbar_init(&s_yempty[s], kEpiWarps); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&s_accfull[b], p.lanes == 3 ? 2 : 1);   // split-chunk mode: both lanes commit every tile
       mbar_init(&s_accempty[b], kEpiWarps);
@@ -392,10 +480,19 @@ __global__ void __launch_bounds__((MINB == 2 ? 64 : 96) + 128 * P, MINB) conv_ha
         }
       int stage = 0;
       uint32_t phase = 0;
+      int ystage = 0;
+      uint32_t yphase = 0;
+      const uint32_t ybytes = static_cast<uint32_t>(p.y_stage_bytes);
       for (int t = t_begin; t < t_end; ++t) {
         const int w0 = (t % p.tiles_w) * 8;
         const int h0 = ((t / p.tiles_w) % p.tiles_h) * 16 * p.G;
         const int n = t / (p.tiles_w * p.tiles_h);
+        if (p.y_stages > 0) {
+          mbar_wait(&s_yempty[ystage], yphase ^ 1u);
+          mbar_arrive_expect_tx(&s_yfull[ystage], ybytes);
+          tma_load_3d(smem_y + ystage * p.y_stage_bytes, &p.ymap, &s_yfull[ystage], w0 * (p.y_rowb >> 2), h0, n);
+          if (++ystage == p.y_stages) { ystage = 0; yphase ^= 1u; }
+        }
         for (int s = 0; s < p.nsrc; ++s) {
           const HaloSrc sc = p.src[s];
           const uint32_t bytes = static_cast<uint32_t>(kHaloW * (16 * p.G + 2) * sc.kc * 2);
@@ -570,13 +667,20 @@ __global__ void __launch_bounds__((MINB == 2 ? 64 : 96) + 128 * P, MINB) conv_ha
     }
   } else {
     // -------------------------------------------------------------- epilogue warps 2..9 (TMEM lane quarter = warp % 4)
-    if constexpr (P == 2) {
-      if (p.stat_sum != nullptr && BN == 32) halo_epilogue<32, 2>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_chunk, s_accfull, s_accempty);
-      else if (p.stat_sum != nullptr && BN == 64) halo_epilogue<64, 2>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_chunk, s_accfull, s_accempty);
-      else halo_epilogue<0, 2>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_chunk, s_accfull, s_accempty);
+    if constexpr (BWD) {   // host guarantees statistics, BN = 32 / 64 and one CTA per SM
+      if constexpr (P == 2) {
+        if (BN == 32) halo_epilogue<32, 2, true>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_chunk, s_accfull, s_accempty, s_bw, smem_y, s_yfull, s_yempty);
+        else halo_epilogue<64, 2, true>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_chunk, s_accfull, s_accempty, s_bw, smem_y, s_yfull, s_yempty);
+      } else {
+        halo_epilogue<64, 4, true>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_chunk, s_accfull, s_accempty, s_bw, smem_y, s_yfull, s_yempty);
+      }
+    } else if constexpr (P == 2) {
+      if (p.stat_sum != nullptr && BN == 32) halo_epilogue<32, 2>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_chunk, s_accfull, s_accempty, s_bw, smem_y, s_yfull, s_yempty);
+      else if (p.stat_sum != nullptr && BN == 64) halo_epilogue<64, 2>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_chunk, s_accfull, s_accempty, s_bw, smem_y, s_yfull, s_yempty);
+      else halo_epilogue<0, 2>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_chunk, s_accfull, s_accempty, s_bw, smem_y, s_yfull, s_yempty);
     } else {
-      if (p.stat_sum != nullptr && BN == 64) halo_epilogue<64, 4>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_chunk, s_accfull, s_accempty);
-      else halo_epilogue<0, 4>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_chunk, s_accfull, s_accempty);
+      if (p.stat_sum != nullptr && BN == 64) halo_epilogue<64, 4>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_chunk, s_accfull, s_accempty, s_bw, smem_y, s_yfull, s_yempty);
+      else halo_epilogue<0, 4>(p, tmem_base, t_begin, t_end, ntile, warp, lane, s_bias, s_part, s_chunk, s_accfull, s_accempty, s_bw, smem_y, s_yfull, s_yempty);
     }
   }
 
@@ -861,7 +965,10 @@ struct ConvHaloOp : public OpBase {
   int epi_parts = 2;
   int launch(cudaStream_t st) override {
     // two CTAs per SM: the other CTA's MMA lane already feeds the pipe, one lane each (and no extra warp: registers)
-    if (epi_parts == 4) launch_pdl(conv_halo_kernel<1, 4>, grid, dim3(96 + 512), smem_bytes, st, p);
+    if (p.bwd_y != nullptr) {
+      if (epi_parts == 4) launch_pdl(conv_halo_kernel<1, 4, true>, grid, dim3(96 + 512), smem_bytes, st, p);
+      else launch_pdl(conv_halo_kernel<1, 2, true>, grid, dim3(96 + 256), smem_bytes, st, p);
+    } else if (epi_parts == 4) launch_pdl(conv_halo_kernel<1, 4>, grid, dim3(96 + 512), smem_bytes, st, p);
     else if (ctas_per_sm == 2) launch_pdl(conv_halo_kernel<2, 2>, grid, dim3(64 + 256), smem_bytes, st, p);
     else launch_pdl(conv_halo_kernel<1, 2>, grid, dim3(96 + 256), smem_bytes, st, p);
     return check_launch("conv_halo_kernel");
@@ -1009,7 +1116,9 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   // The same holds for G = 1 layers with 64 statistics columns: conv_1_0.conv_0 ([24] -> 48 @128^2) ran 69 us as two CTAs
   // per SM and 34 us as one (tools/profile_plan.py with MTBC_HALO_CTAS=1, round 2).
   const bool stats_heavy = d->stat_sum != nullptr && G * BN >= 64 && !getenv("MTBC_HALO_STATS2CTA");
-  const bool one_cta = (c_env && c_env[0] == '1') || ((G == 2 || stats_heavy) && d->stat_sum != nullptr && !(c_env && c_env[0] == '2'));
+  // (fused InstanceNorm backward statistics always run one CTA per SM: the 96-register variant spills their epilogue)
+  const bool one_cta = (c_env && c_env[0] == '1') || d->bwd_y != nullptr ||
+                       ((G == 2 || stats_heavy) && d->stat_sum != nullptr && !(c_env && c_env[0] == '2'));
   if (one_cta && ctas_per_sm == 2) {
     ctas_per_sm = 1;
     int st1 = (200 * 1024 - p.b_total_bytes) / p.a_stage_bytes;
@@ -1076,11 +1185,47 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
     p.outs[0].out_C = d->out_C; p.outs[0].col0 = 0; p.outs[0].col_end = d->ncols; p.outs[0].accumulate = d->accumulate;
   }
   p.bias = d->bias; p.stat_sum = d->stat_sum; p.stat_sq = d->stat_sq;
+  if (d->bwd_y != nullptr) {
+    // fused InstanceNorm backward statistics: served by the register-resident statistics epilogue only
+    if (d->nouts != 0 || d->accumulate || d->bias || !d->stat_sum || !d->stat_sq || !d->bwd_mean || !d->bwd_rstd ||
+        (p.BN != 32 && p.BN != 64) || d->stat_C != d->out_C) {
+      delete op;
+      return set_error(MTBC_ERR_INVALID, "conv_gemm: fused InstanceNorm backward statistics need a single-output, "
+                       "non-accumulating data gradient with N tiles of 32 or 64 columns (got %d)", p.BN);
+    }
+    p.bwd_y = reinterpret_cast<const __nv_bfloat16*>(d->bwd_y);
+    p.bwd_mean = d->bwd_mean; p.bwd_rstd = d->bwd_rstd; p.bwd_gamma = d->bwd_gamma; p.bwd_beta = d->bwd_beta;
+    p.bwd_slope = d->bwd_slope;
+    // y tile ring: three tiles of 8 x 16 G pixels x bn1 channels behind the halo ring (the halo ring gives up stages
+    // two at a time, which keeps every lane-parity rule above intact)
+    // (dense tile, pixel pitch 2 * out_C bytes: 16-byte shared-memory reads of 8 neighbouring pixels are conflict free
+    //  for 24 / 40 / 56 channels, two-way for 48, 4- / 8-way for 32 / 64.  Measured at B = 32 (tools/diag_fused_dgrad.py):
+    //  24 channels @256^2 66 -> 89 us for a 40 us reduction pass saved; 48 channels @128^2 34 -> 57 us for 21 us saved:
+    //  only the conflict-free pitches are served)
+    if ((d->out_C / 8) % 2 == 0 || d->ncols != BN) {
+      delete op;
+      return set_error(MTBC_ERR_INVALID, "conv_gemm: fused InstanceNorm backward statistics: channel pitch %d not served", d->out_C);
+    }
+    p.y_rowb = d->out_C * 2;
+    p.y_stage_bytes = (8 * 16 * G * p.y_rowb + 127) & ~127;
+    p.y_stages = 3;
+    const int ybytes = p.y_stages * p.y_stage_bytes;
+    while (p.stages > 2 && p.b_total_bytes + p.stages * p.a_stage_bytes + ybytes + 1024 > 212 * 1024) p.stages -= 2;
+    if (p.b_total_bytes + p.stages * p.a_stage_bytes + ybytes + 1024 > 212 * 1024 || total_chunks != 1) {
+      delete op;
+      return set_error(MTBC_ERR_INVALID, "conv_gemm: fused InstanceNorm backward statistics: no room for the y ring");
+    }
+    op->smem_bytes = p.b_total_bytes + p.stages * p.a_stage_bytes + ybytes + 1024;
+    int rc = encode_rows(&p.ymap, d->bwd_y, d->out_C, d->W, d->H, d->N, 8, 16 * G);
+    if (rc) { delete op; return rc; }
+  }
   op->grid = dim3(gx, d->ncols / BN, 1);
   op->flops = 2.0 * double(d->N) * d->H * d->W * double(d->ncols) * kused * 9.0;
   cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_halo_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_halo_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
+  if (e == cudaSuccess && d->bwd_y) e = cudaFuncSetAttribute(conv_halo_kernel<1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
+  if (e == cudaSuccess && d->bwd_y) e = cudaFuncSetAttribute(conv_halo_kernel<1, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
   if (e != cudaSuccess) { delete op; return set_error(MTBC_ERR_CUDA, "cudaFuncSetAttribute(conv_halo): %s", cudaGetErrorString(e)); }
   *out = op;
   return 0;

@@ -33,6 +33,7 @@ int wgrad_halo_multi_create(const mtbc_wgrad_multi_desc* d, OpBase** out);
 // tensor-map encoders (conv_gemm.cu): bf16 NHWC view with box (kc, bw, bh, bn); packed weights with box (kc, BN, 1)
 int encode_act(CUtensorMap* m, const mtbc_act_view& v, int kc, int bw, int bh, int bn, int fp32 = 0);
 int encode_w(CUtensorMap* m, const void* w, int ktot, int nrows, int ntaps, int kc, int BN, int fp32 = 0);
+int encode_rows(CUtensorMap* m, const void* ptr, int C, int W, int H, int N, int box_w, int box_h);
 
 // bulk-copy pipelined streaming kernels (stream_pipe.cu) for large tensors
 bool pipe_eligible(int64_t N, int64_t HW, int Cp);

@@ -41,30 +41,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return u;
 }
 
-// Packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 on sm_100): these streaming kernels need about half of the SM's issue
-// slots at HBM speed, so halving the FMA / MUL / ADD instruction count is bandwidth (tools/bench_stream.py).
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-  unsigned long long d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
-      "l"(*reinterpret_cast<unsigned long long*>(&b)), "l"(*reinterpret_cast<unsigned long long*>(&c)));
-  return *reinterpret_cast<float2*>(&d);
-}
-__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
-  unsigned long long d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
-      "l"(*reinterpret_cast<unsigned long long*>(&b)));
-  return *reinterpret_cast<float2*>(&d);
-}
-__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
-  unsigned long long d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
-      "l"(*reinterpret_cast<unsigned long long*>(&b)));
-  return *reinterpret_cast<float2*>(&d);
-}
-// bf16x2 word -> two fp32 (a bf16 is the upper half of an fp32: one shift, one mask)
-__device__ __forceinline__ float2 bf2_to_f2(uint32_t u) {
-  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
-}
+// (packed fp32x2 arithmetic and bf2_to_f2: ptx.cuh)
 
 struct PipeGeom {
   int64_t sample_vecs;      // HW * cvec: 16-byte vectors per sample

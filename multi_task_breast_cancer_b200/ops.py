@@ -156,8 +156,10 @@ def _set_dtype(d: ConvGemmDesc, feats: Sequence[Feat], wpack: torch.Tensor, wpac
 def conv3x3_fwd_op(srcs: Sequence[Feat], wpack: torch.Tensor, out: Feat, bias: Optional[torch.Tensor] = None,
                    stat_sum: Optional[torch.Tensor] = None, stat_sq: Optional[torch.Tensor] = None,
                    accumulate: bool = False, ksz: int = 3, kind: str = "conv3x3_fwd",
-                   wpack_lo: Optional[torch.Tensor] = None) -> Op:
-    """wpack: bf16 (or fp32 holding TF32 values) [ksz*ksz][out.Ck][Ktot] laid out by `k_offsets(srcs)`."""
+                   wpack_lo: Optional[torch.Tensor] = None, bwd_fuse=None) -> Op:
+    """wpack: bf16 (or fp32 holding TF32 values) [ksz*ksz][out.Ck][Ktot] laid out by `k_offsets(srcs)`.
+    bwd_fuse = (y Feat, mean, rstd, gamma | None, beta | None, slope): fused InstanceNorm + LeakyReLU backward statistics
+    (mtbc_conv_gemm_desc.bwd_y); stat_sum / stat_sq then receive s1 / s2.  Raises MtbcError when the shape is not served."""
     offs, ktot = k_offsets(srcs)
     assert wpack.shape == (ksz * ksz, out.Ck, ktot), (wpack.shape, (ksz * ksz, out.Ck, ktot))
     d = ConvGemmDesc()
@@ -182,7 +184,17 @@ def conv3x3_fwd_op(srcs: Sequence[Feat], wpack: torch.Tensor, out: Feat, bias: O
     d.stat_C = out.Cp
     d.accumulate = int(accumulate)
     d.nouts = 0
-    return _create_gemm(d, [*(s.t for s in srcs), wpack, wpack_lo, out.t, bias, stat_sum, stat_sq], kind)
+    keep = [*(s.t for s in srcs), wpack, wpack_lo, out.t, bias, stat_sum, stat_sq]
+    if bwd_fuse is not None:
+        yf, mean, rstd, gamma, beta, slope = bwd_fuse
+        assert (yf.N, yf.H, yf.W, yf.Cp) == (out.N, out.H, out.W, out.Cp) and not yf.fp32
+        assert mean.shape == (out.N, out.Cp) and rstd.shape == mean.shape and stat_sum is not None and stat_sq is not None
+        d.bwd_y = yf.t.data_ptr(); d.bwd_mean = mean.data_ptr(); d.bwd_rstd = rstd.data_ptr()
+        d.bwd_gamma = None if gamma is None else gamma.data_ptr()
+        d.bwd_beta = None if beta is None else beta.data_ptr()
+        d.bwd_slope = float(slope)
+        keep += [yf.t, mean, rstd, gamma, beta]
+    return _create_gemm(d, keep, kind)
 
 
 # stride-2 3x3 convolution (ResidualUNet.py:115-131): tap row r reads input row 2h + r - 1, i.e. the odd sub-lattice
@@ -248,9 +260,13 @@ def conv3x3_s2_wgrad_op(x: Feat, dy: Feat, dw_acc: torch.Tensor, splits: int = 0
 
 
 def conv3x3_dgrad_op(dy: Feat, wd: torch.Tensor, dx: Feat, accumulate: bool, ksz: int = 3,
-                     wd_lo: Optional[torch.Tensor] = None) -> Op:
-    """wd: bf16 [ksz*ksz][dx.Ck][dy.Ck] (flipped taps, transposed channels) -> dx (+)= conv(dy, wd)."""
-    return conv3x3_fwd_op([dy], wd, dx, accumulate=accumulate, ksz=ksz, kind="conv3x3_dgrad", wpack_lo=wd_lo)
+                     wd_lo: Optional[torch.Tensor] = None, bwd_fuse=None, s1: Optional[torch.Tensor] = None,
+                     s2: Optional[torch.Tensor] = None) -> Op:
+    """wd: bf16 [ksz*ksz][dx.Ck][dy.Ck] (flipped taps, transposed channels) -> dx (+)= conv(dy, wd).
+    bwd_fuse (see conv3x3_fwd_op): dx is the gradient of a = LeakyReLU(IN(y)); the launch stores gg instead and adds the
+    two plane sums of the InstanceNorm backward to s1 / s2."""
+    return conv3x3_fwd_op([dy], wd, dx, accumulate=accumulate, ksz=ksz, kind="conv3x3_dgrad", wpack_lo=wd_lo,
+                          bwd_fuse=bwd_fuse, stat_sum=s1, stat_sq=s2)
 
 
 def conv3x3_dgrad_multi_op(dy: Feat, wd_all: torch.Tensor, dxs: Sequence[Feat], accumulates: Sequence[bool]) -> Op:

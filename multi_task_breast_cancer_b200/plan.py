@@ -35,7 +35,20 @@ class PTensor:
         self.feat = feat
         self.name = name
         self.g: Optional[Feat] = None
-        self.g_init = False  # set during backward emission once some consumer has written the gradient
+        self._g_init = False
+        self.g_writes = 0       # launches that have written / accumulated into the gradient so far (backward emission)
+        self.fuse_cand = None   # the single-source conv data gradient that wrote it first (see Plan._emit_dgrad)
+
+    @property
+    def g_init(self) -> bool:
+        """Set during backward emission once some consumer has written the gradient."""
+        return self._g_init
+
+    @g_init.setter
+    def g_init(self, v: bool):
+        if v:
+            self.g_writes += 1
+        self._g_init = bool(v)
 
     def grad(self) -> Feat:
         if self.g is None:
@@ -143,12 +156,17 @@ class JobTable:
 def _mk_op(op: ops.Op, true_flops: float = 0.0, desc: str = "", true_bytes: float = 0.0) -> Callable:
     """Bind a tensor-core op launch; `true_flops` = algorithmic 2*M*N*K with unpadded channels (roofline numerator)."""
     lib = _lib.load()
-    h = op.handle
+    cell = [op]
 
     def launch(stream):
-        rc = lib.mtbc_op_launch(h, stream)
+        rc = lib.mtbc_op_launch(cell[0].handle, stream)
         if rc != 0:
             _lib.check(rc, op.kind)
+
+    def swap(new_op):   # replace the op behind an already emitted launch (fused InstanceNorm backward statistics)
+        cell[0] = new_op
+        launch.op = new_op
+    launch.swap = swap
     launch.kind = op.kind
     launch.op = op
     launch.true_flops = true_flops
@@ -490,9 +508,14 @@ class Plan:
             wd, wd_lo = wd if isinstance(wd, tuple) else (wd, None)
             o = ops.conv3x3_dgrad_op(dy, wd, g, accumulate=s.g_init, wd_lo=wd_lo)
             self.tc_flops_bwd += o.flops
-            blk.append(_mk_op(o, 2.0 * N * H * Wd * Cout * s.feat.C * 9,
-                              f"{name} dgrad {N}x{H}x{Wd} {s.feat.C}<-{Cout} acc={int(s.g_init)}",
-                              2.0 * N * H * Wd * (s.feat.C + Cout) + 2.0 * 9 * s.feat.C * Cout))
+            l = _mk_op(o, 2.0 * N * H * Wd * Cout * s.feat.C * 9,
+                       f"{name} dgrad {N}x{H}x{Wd} {s.feat.C}<-{Cout} acc={int(s.g_init)}",
+                       2.0 * N * H * Wd * (s.feat.C + Cout) + 2.0 * 9 * s.feat.C * Cout)
+            blk.append(l)
+            if not s.g_init and not self.fp32 and not self.deterministic:
+                # first writer of this gradient: if it stays the only one, the producer's InstanceNorm backward takes
+                # its two plane sums from this launch's epilogue (_norm_act_bwd swaps the op)
+                s.fuse_cand = {"launch": l, "dy": dy, "wd": wd}
             s.g_init = True
 
     def _wg_accum(self, w: str, pk: dict) -> torch.Tensor:
@@ -542,10 +565,31 @@ class Plan:
         self.debug[a.name + ".aux"] = (mean, rstd, gv, bv, s1, s2)
         dg = self.grad_view[gamma] if gamma else None
         db = self.grad_view[beta] if beta else None
-        l = _mk("mtbc_in_bwd", ptr(a.g.t), ptr(y.feat.t), N, H * Wd, Cp, ptr(mean), ptr(rstd), ptr(gv), ptr(bv),
-                C.c_float(slope), ptr(s1), ptr(s2), ptr(dy.t), ptr(dg), ptr(db), Cc, ptr(cnt))
-        # algorithmic: read g, read y, write dy once each (the two-pass kernel reads g and y twice: 10 B/elem moved)
-        _annot(l, f"{a.name} in_bwd {N}x{H}x{Wd}x{Cc}", 6.0 * N * H * Wd * Cc)
+        fused = None
+        cand = a.fuse_cand
+        # (MTBC_FUSE_INBWD=0 keeps the two-pass backward everywhere; the kernel serves the channel pitches for which the
+        #  trade pays: 24 channels @256^2, B = 32: reduction pass -40 us, data gradient +22 us -- DESIGN 9)
+        if cand is not None and a.g_writes == 1 and os.environ.get("MTBC_FUSE_INBWD", "1") != "0":
+            # `a` has ONE consumer, a 3x3 conv whose data gradient wrote a.g: that launch's epilogue already holds the
+            # gradient in fp32, so it applies the LeakyReLU factor, stores gg and leaves sum(gg), sum(gg * xhat) in
+            # s1 / s2 -- the reduction pass over (g, y) disappears (10 -> 6 B/elem + 2 B/elem read in the epilogue).
+            try:
+                fused = ops.conv3x3_dgrad_op(cand["dy"], cand["wd"], a.g, accumulate=False,
+                                             bwd_fuse=(y.feat, mean, rstd, gv, bv, slope), s1=s1, s2=s2)
+            except _lib.MtbcError:
+                fused = None   # shape not served by the halo kernel's statistics epilogue: two-pass backward below
+        if fused is not None:
+            cand["launch"].swap(fused)
+            cand["launch"].desc += " +in_bwd sums"
+            l = _mk("mtbc_in_bwd_apply", ptr(a.g.t), ptr(y.feat.t), N, H * Wd, Cp, ptr(mean), ptr(rstd), ptr(gv), ptr(bv),
+                    C.c_float(1.0), ptr(s1), ptr(s2), ptr(dy.t), ptr(dg), ptr(db), Cc)
+            l.kind = "mtbc_in_bwd"   # same row of the per-kernel tables as the two-pass launches
+            _annot(l, f"{a.name} in_bwd(apply) {N}x{H}x{Wd}x{Cc}", 6.0 * N * H * Wd * Cc)
+        else:
+            l = _mk("mtbc_in_bwd", ptr(a.g.t), ptr(y.feat.t), N, H * Wd, Cp, ptr(mean), ptr(rstd), ptr(gv), ptr(bv),
+                    C.c_float(slope), ptr(s1), ptr(s2), ptr(dy.t), ptr(dg), ptr(db), Cc, ptr(cnt))
+            # algorithmic: read g, read y, write dy once each (the two-pass kernel reads g and y twice: 10 B/elem moved)
+            _annot(l, f"{a.name} in_bwd {N}x{H}x{Wd}x{Cc}", 6.0 * N * H * Wd * Cc)
         l.wait_side = self._slot_readers.pop(self._cur_slot, [])   # weight gradients still reading this dy buffer
         self._dy_slot_of[id(dy.t)] = self._cur_slot
         blk.append(l)

@@ -45,6 +45,30 @@ def test_conv3x3_forward(D, N, H, W, src, cout, kw):
     _run(D, D.conv_fwd_case, N, H, W, src, cout, **kw)
 
 
+# fused InstanceNorm + LeakyReLU backward statistics in the data-gradient epilogue: G = 2 (24 / 32 channels on planes with
+# H % 32 == 0), G = 1 with 32 columns (H % 32 != 0), 64 columns, two samples per CTA range (sample change mid-range), and
+# the benchmark's level-0 / level-1 shapes
+@pytest.mark.parametrize("args", [(2, 32, 32, 24, 24, False), (2, 64, 64, 24, 24, True), (3, 48, 40, 24, 24, True),
+                                  (2, 32, 32, 40, 40, True), (2, 64, 64, 40, 40, False), (5, 32, 64, 56, 56, True),
+                                  (32, 256, 256, 24, 24, True), (8, 128, 128, 56, 56, True)])
+def test_conv3x3_data_gradient_with_fused_norm_backward_sums(D, args):
+    _run(D, D.conv_dgrad_inbwd_case, *args)
+
+
+def test_fused_norm_backward_sums_refuse_unserved_shapes(D):
+    """Channel pitches whose dense y tile would be read with shared-memory bank conflicts (32 / 48 / 64 channels) and planes
+    the halo kernel does not take are refused at creation: plan.py then keeps the two-pass InstanceNorm backward."""
+    import torch
+    from multi_task_breast_cancer_b200 import _lib, ops
+    from multi_task_breast_cancer_b200.ops import Feat
+    for (N, H, W, Cc) in [(2, 32, 32, 32), (2, 32, 32, 48), (2, 32, 32, 64), (2, 8, 8, 24)]:
+        y = Feat.empty(N, H, W, Cc); dy = Feat.empty(N, H, W, Cc); ga = Feat.empty(N, H, W, Cc)
+        wd = torch.zeros(9, ga.Ck, dy.Ck, dtype=torch.bfloat16, device="cuda")
+        st = [torch.zeros(N, y.Cp, device="cuda") for _ in range(4)]
+        with pytest.raises(_lib.MtbcError):
+            ops.conv3x3_dgrad_op(dy, wd, ga, False, bwd_fuse=(y, st[0], st[1], None, None, 0.1), s1=st[2], s2=st[3])
+
+
 @pytest.mark.parametrize("args", [(2, 16, 16, 64, 64, False), (2, 32, 32, 24, 48, True), (2, 16, 16, 192, 96, False),
                                   (4, 64, 64, 24, 24, False, 1e-5), (4, 4, 4, 512, 512, False, 1e-3)])
 def test_conv3x3_dgrad(D, args):

@@ -117,6 +117,64 @@ def conv_dgrad_case(N, H, W, Cin, Cout, accumulate, dyscale=1.0):
     run_case(fn, name)
 
 
+def conv_dgrad_inbwd_case(N, H, W, C, Cout, affine, slope=0.1):
+    """Data gradient of conv_1 with the InstanceNorm + LeakyReLU backward sums of its input's producer fused into the
+    epilogue (mtbc_conv_gemm_desc.bwd_y), followed by the apply pass with slope = 1: dy of the whole
+    conv -> IN -> LeakyReLU chain against torch autograd, and s1 / s2 against their definitions."""
+    name = f"conv3x3_dgrad+in_bwd N{N} {H}x{W} {C}<-{Cout} affine={affine}"
+
+    def fn():
+        y = (rnd(N, C, H, W, scale=2.0) + 0.7).to(torch.bfloat16).float()     # stored pre-norm conv output of layer 0
+        yf = Feat.from_nchw(y)
+        Cp = yf.Cp
+        g = b = gp = bp = None
+        if affine:
+            g = torch.rand(C, device=dev) + 0.5
+            b = torch.randn(C, device=dev) * 0.3
+            gp = torch.zeros(yf.Ck, device=dev); gp[:C] = g
+            bp = torch.zeros(yf.Ck, device=dev); bp[:C] = b
+        ssum = torch.zeros(N, Cp, device=dev); ssq = torch.zeros(N, Cp, device=dev)
+        _lib.call("mtbc_in_stats", ops.ptr(yf.t), N, H * W, Cp, ops.ptr(ssum), ops.ptr(ssq), None)
+        a = Feat.empty(N, H, W, C)
+        mean = torch.zeros(N, Cp, device=dev); rstd = torch.zeros(N, Cp, device=dev)
+        _lib.call("mtbc_in_apply", ops.ptr(yf.t), N, H, W, Cp, ops.ptr(ssum), ops.ptr(ssq), ops.ptr(gp), ops.ptr(bp), C,
+                  1e-5, slope, ops.ptr(a.t), None, ops.ptr(mean), ops.ptr(rstd), None)
+        w = rnd(Cout, C, 3, 3, scale=0.1)
+        dy1 = rnd(N, Cout, H, W)
+        dyf = Feat.from_nchw(dy1)
+        ga = Feat.empty(N, H, W, C)
+        wd = torch.zeros(9, ga.Ck, dyf.Ck, dtype=torch.bfloat16, device=dev)
+        wf = torch.zeros(9, dyf.Ck, ga.Ck, dtype=torch.bfloat16, device=dev)
+        ops.pack_conv_weight(w, [C], [0], wf, [wd])
+        s1 = torch.zeros(N, Cp, device=dev); s2 = torch.zeros(N, Cp, device=dev)
+        op = ops.conv3x3_dgrad_op(dyf, wd, ga, False, bwd_fuse=(yf, mean, rstd, gp, bp, slope), s1=s1, s2=s2)
+        op.launch()
+        dy0 = Feat.empty(N, H, W, C)
+        dg = torch.zeros(C, device=dev) if affine else None
+        db = torch.zeros(C, device=dev) if affine else None
+        _lib.call("mtbc_in_bwd_apply", ops.ptr(ga.t), ops.ptr(yf.t), N, H * W, Cp, ops.ptr(mean), ops.ptr(rstd),
+                  ops.ptr(gp), ops.ptr(bp), 1.0, ops.ptr(s1), ops.ptr(s2), ops.ptr(dy0.t), ops.ptr(dg), ops.ptr(db), C, None)
+        torch.cuda.synchronize()
+        # reference: autograd through IN -> LeakyReLU -> conv with the cotangent dy1
+        yr = y.clone().requires_grad_(True)
+        ar = F.leaky_relu(F.instance_norm(yr, weight=g, bias=b, eps=1e-5), slope)
+        out = F.conv2d(ar, w, padding=1)
+        out.backward(dy1)
+        D = F.conv_transpose2d(dy1, w, padding=1)
+        xh = (y - y.mean((2, 3), keepdim=True)) * torch.rsqrt(y.var((2, 3), unbiased=False, keepdim=True) + 1e-5)
+        z = xh if not affine else xh * g.view(1, -1, 1, 1) + b.view(1, -1, 1, 1)
+        gg = torch.where(z > 0, D, slope * D)
+        report(name + " gg", ga.to_nchw(), gg, tol=2e-2)
+        report(name + " s1", s1[:, :C], gg.sum((2, 3)), tol=2e-3)
+        report(name + " s2", s2[:, :C], (gg * xh).sum((2, 3)), tol=2e-3)
+        report(name + " dy", dy0.to_nchw(), yr.grad, tol=3e-2)
+        if affine:
+            report(name + " dgamma", dg, (gg * xh).sum((0, 2, 3)), tol=2e-3)
+            report(name + " dbeta", db, gg.sum((0, 2, 3)), tol=2e-3)
+
+    run_case(fn, name)
+
+
 def conv_dgrad_multi_case(N, H, W, src_C, Cout, acc_flags=None):
     """Fused data gradient: one launch writes the gradient of every concat source (some accumulating)."""
     name = f"conv3x3_dgrad_multi N{N} {H}x{W} {src_C}<-{Cout}"
