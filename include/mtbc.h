@@ -175,11 +175,32 @@ typedef struct {
   int32_t splits; /* 0 = auto */
 } mtbc_wgrad_multi_desc;
 
+/* Fused backward of nn.ConvTranspose2d(kernel = stride = 2) (MTnnUNet.py:96-100; MONAI UpCat via
+ * MTUNetPlusPlus.py:107-118): ONE pass over the output gradient produces the data gradient dx (+)= sum_q dy_q . wd[q],
+ * the weight gradient dw_acc[q][co][ci] += sum_pixels x[.][ci] * dy_q[.][co] and the bias gradient dbias[co] += sum dy --
+ * what aten::convolution_backward returns for the transposed conv, and what mtbc_conv_gemm (data gradient) +
+ * mtbc_wgrad + mtbc_channel_sum compute in three passes.  dy[q], q = 2 i + j, is the sub-lattice dy[n, 2h+i, 2w+j, :] as
+ * a strided view on the input's pixel grid.  Shapes served: Cin % 8 == 0 and Cin < 64, Cout % 8 == 0 and Cout <= 64,
+ * W % 16 == 0, H % 8 == 0, bf16; anything else fails with MTBC_ERR_INVALID (the caller keeps the three launches). */
+typedef struct {
+  mtbc_act_view x;       /* input of the transposed conv: bf16 NHWC (N, H, W, Cin)                              */
+  mtbc_act_view dy[4];   /* sub-lattices of the output gradient (N, H, W, Cout), strided                         */
+  const void* wd;        /* bf16 [4][wd_rows][wd_ld]: data-gradient pack of mtbc_pack_convT_weight               */
+  int32_t wd_rows, wd_ld;
+  float* dw_acc;         /* fp32 [4][n_rows][ld_k], zeroed by the caller (layout of mtbc_wgrad_desc)             */
+  int32_t n_rows, ld_k;
+  float* dbias;          /* fp32 [Cout], accumulated into; NULL: no bias                                         */
+  void* dx;              /* bf16 NHWC (N, H, W, dx_C)                                                            */
+  int32_t dx_C, accumulate;
+  int32_t Cout;
+} mtbc_convT_bwd_desc;
+
 typedef struct mtbc_op mtbc_op; /* opaque: encoded tensor maps + launch geometry */
 
 int mtbc_conv_gemm_create(const mtbc_conv_gemm_desc* d, mtbc_op** out);
 int mtbc_wgrad_create(const mtbc_wgrad_desc* d, mtbc_op** out);
 int mtbc_wgrad_multi_create(const mtbc_wgrad_multi_desc* d, mtbc_op** out);
+int mtbc_convT_bwd_create(const mtbc_convT_bwd_desc* d, mtbc_op** out);
 int mtbc_op_launch(mtbc_op* op, void* stream);
 int mtbc_ops_launch(mtbc_op* const* ops, int32_t n, void* stream);
 void mtbc_op_destroy(mtbc_op* op);

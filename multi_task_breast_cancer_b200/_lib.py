@@ -57,6 +57,12 @@ class WgradMultiDesc(C.Structure):
                 ("N", c_i32), ("dw_acc", c_vp), ("n_rows", c_i32), ("ld_k", c_i32), ("splits", c_i32)]
 
 
+class ConvTBwdDesc(C.Structure):
+    _fields_ = [("x", ActView), ("dy", ActView * 4), ("wd", c_vp), ("wd_rows", c_i32), ("wd_ld", c_i32),
+                ("dw_acc", c_vp), ("n_rows", c_i32), ("ld_k", c_i32), ("dbias", c_vp), ("dx", c_vp), ("dx_C", c_i32),
+                ("accumulate", c_i32), ("Cout", c_i32)]
+
+
 class ParamJob(C.Structure):
     _fields_ = [("kind", c_i32), ("i", c_i32 * 11), ("src", c_vp), ("dst0", c_vp), ("dst1", c_vp)]
 
@@ -75,6 +81,7 @@ _SIGS = {
     "mtbc_conv_gemm_create": [C.POINTER(ConvGemmDesc), C.POINTER(c_vp)],
     "mtbc_wgrad_create": [C.POINTER(WgradDesc), C.POINTER(c_vp)],
     "mtbc_wgrad_multi_create": [C.POINTER(WgradMultiDesc), C.POINTER(c_vp)],
+    "mtbc_convT_bwd_create": [C.POINTER(ConvTBwdDesc), C.POINTER(c_vp)],
     "mtbc_param_jobs_create": [C.POINTER(ParamJob), c_i32, C.POINTER(c_vp)],
     "mtbc_op_launch": [c_vp, c_vp],
     "mtbc_ops_launch": [C.POINTER(c_vp), c_i32, c_vp],

@@ -15,7 +15,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libmtbc.so"
 
-SOURCES = ["api.cu", "conv_gemm.cu", "conv_halo.cu", "pack.cu", "stream_ops.cu", "stream_pipe.cu", "heads.cu", "loss.cu", "augment.cu", "residual.cu"]
+SOURCES = ["api.cu", "conv_gemm.cu", "conv_halo.cu", "convt_bwd.cu", "pack.cu", "stream_ops.cu", "stream_pipe.cu", "heads.cu", "loss.cu", "augment.cu", "residual.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

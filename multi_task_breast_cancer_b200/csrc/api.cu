@@ -90,6 +90,14 @@ int mtbc_wgrad_multi_create(const mtbc_wgrad_multi_desc* d, mtbc_op** out) {
   *out = new mtbc_op{b};
   return 0;
 }
+int mtbc_convT_bwd_create(const mtbc_convT_bwd_desc* d, mtbc_op** out) {
+  if (!d || !out) return mtbc::set_error(MTBC_ERR_INVALID, "null argument");
+  mtbc::OpBase* b = nullptr;
+  int rc = mtbc::convT_bwd_create(d, &b);
+  if (rc) return rc;
+  *out = new mtbc_op{b};
+  return 0;
+}
 int mtbc_param_jobs_create(const mtbc_param_job* jobs, int32_t n, mtbc_op** out) {
   mtbc::OpBase* b = nullptr;
   int rc = mtbc::param_jobs_create(jobs, n, &b);

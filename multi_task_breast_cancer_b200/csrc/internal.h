@@ -30,6 +30,7 @@ bool tensor_map_available();
 int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out);
 int wgrad_halo_try_create(const mtbc_wgrad_desc* d, OpBase** out);
 int wgrad_halo_multi_create(const mtbc_wgrad_multi_desc* d, OpBase** out);
+int convT_bwd_create(const mtbc_convT_bwd_desc* d, OpBase** out);
 // tensor-map encoders (conv_gemm.cu): bf16 NHWC view with box (kc, bw, bh, bn); packed weights with box (kc, BN, 1)
 int encode_act(CUtensorMap* m, const mtbc_act_view& v, int kc, int bw, int bh, int bn, int fp32 = 0);
 int encode_w(CUtensorMap* m, const void* w, int ktot, int nrows, int ntaps, int kc, int BN, int fp32 = 0);

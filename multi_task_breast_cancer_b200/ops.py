@@ -15,7 +15,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import OutSlice, ActView, ConvGemmDesc, GemmSeg, WgradDesc, WgradMultiDesc, WgradTap
+from ._lib import OutSlice, ActView, ConvGemmDesc, ConvTBwdDesc, GemmSeg, WgradDesc, WgradMultiDesc, WgradTap
 
 
 def pad32(c: int) -> int:
@@ -389,6 +389,29 @@ def convT_wgrad_op(x: Feat, dout: Feat, dw_acc: torch.Tensor, k: int, splits: in
     h = C.c_void_p()
     _lib.check(_lib.load().mtbc_wgrad_create(C.byref(d), C.byref(h)), "convT_wgrad")
     return Op(h, [x.t, dout.t, dw_acc], "convT_wgrad")
+
+
+def convT_bwd_op(x: Feat, dout: Feat, wd: torch.Tensor, dw_acc: torch.Tensor, dbias: Optional[torch.Tensor], dx: Feat,
+                 accumulate: bool) -> Op:
+    """Fused backward of ConvTranspose2d(k = s = 2): dx (+)= data gradient, dw_acc fp32 [4][dout.Ck][x.Ck] += weight
+    gradient, dbias fp32 [Cout] += bias gradient, one pass over dout (mtbc_convT_bwd_desc).  Raises MtbcError for shapes
+    the kernel does not serve (the caller keeps convT_dgrad_op + convT_wgrad_op + mtbc_channel_sum)."""
+    assert wd.shape == (4, dx.Ck, dout.Ck) and dw_acc.shape == (4, dout.Ck, x.Ck) and dw_acc.dtype == torch.float32
+    assert (dx.N, dx.H, dx.W, dx.C) == (x.N, x.H, x.W, x.C) and (dout.H, dout.W) == (2 * x.H, 2 * x.W)
+    if x.fp32 or dout.fp32:
+        raise _lib.MtbcError("convT_bwd: bf16 only")
+    d = ConvTBwdDesc()
+    d.x = _view(x)
+    for q in range(4):
+        d.dy[q] = _strided_view(dout, 2, q // 2, q % 2)
+    d.wd = wd.data_ptr(); d.wd_rows = wd.shape[1]; d.wd_ld = wd.shape[2]
+    d.dw_acc = dw_acc.data_ptr(); d.n_rows = dw_acc.shape[1]; d.ld_k = dw_acc.shape[2]
+    d.dbias = None if dbias is None else dbias.data_ptr()
+    d.dx = dx.t.data_ptr(); d.dx_C = dx.Cp; d.accumulate = int(accumulate)
+    d.Cout = dout.C
+    h = C.c_void_p()
+    _lib.check(_lib.load().mtbc_convT_bwd_create(C.byref(d), C.byref(h)), "convT_bwd")
+    return Op(h, [x.t, dout.t, wd, dw_acc, dbias, dx.t], "convT_bwd")
 
 
 # ----------------------------------------------------------------------------------------------------------------

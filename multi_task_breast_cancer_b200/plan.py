@@ -625,6 +625,25 @@ class Plan:
             if not out.g_init:
                 return blk
             acc = self.bwd_arena.alloc(k * k, cp, f.Ck)
+            if k == 2 and not self.fp32 and os.environ.get("MTBC_FUSE_CONVT_BWD", "1") != "0":
+                # data, weight and bias gradient from ONE pass over the (N, 2H, 2W, Cout) gradient (convt_bwd.cu) instead
+                # of three launches that each stream it from HBM; shapes the kernel does not serve keep the three below
+                g = x.grad()
+                try:
+                    o = ops.convT_bwd_op(f, out.g, wd, acc, None if b is None else self.grad_view[b], g,
+                                         accumulate=x.g_init)
+                except _lib.MtbcError:
+                    o = None
+                if o is not None:
+                    self.tc_flops_bwd += o.flops
+                    blk.append(_mk_op(o, 2.0 * t_flops, f"{name} convT bwd {f.N}x{f.H}x{f.W} {Cin}<-{Cout} fused",
+                                      2.0 * f.N * f.H * f.W * (2 * Cin + k * k * Cout) + 4.0 * Cin * Cout * k * k))
+                    self.unpack_jobs.add(_lib.JOB_UNPACK_CONVT, [k * k * cp, f.Ck, Cin, Cout, k, 0], acc,
+                                         self.grad_view[w], owner=w)
+                    self._late_unpacked.append(w)
+                    self._mark_grad(w, b)
+                    x.g_init = True
+                    return blk
             o = ops.convT_wgrad_op(f, out.g, acc, k)
             self.tc_flops_bwd += o.flops
             blk.append(self._side(_mk_op(o, t_flops, f"{name} convT wgrad {f.N}x{f.H}x{f.W} {Cin}->{Cout}", t_bytes)))

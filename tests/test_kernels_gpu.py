@@ -55,6 +55,27 @@ def test_conv3x3_data_gradient_with_fused_norm_backward_sums(D, args):
     _run(D, D.conv_dgrad_inbwd_case, *args)
 
 
+# fused transposed-conv backward (data + weight + bias gradient in one pass over dout): one tile, several tiles per CTA
+# with accumulation into dx, narrow / wide channel counts, the benchmark's level-0 shape
+@pytest.mark.parametrize("args", [(1, 8, 16, 48, 48, False), (2, 16, 16, 48, 48, False), (2, 32, 16, 24, 48, True),
+                                  (3, 24, 48, 40, 64, True), (2, 16, 32, 56, 24, False, False),
+                                  (32, 128, 128, 48, 48, True)])
+def test_transposed_conv_fused_backward(D, args):
+    _run(D, D.convT_bwd_case, *args)
+
+
+def test_transposed_conv_fused_backward_refuses_unserved_shapes(D):
+    import torch
+    from multi_task_breast_cancer_b200 import _lib, ops
+    from multi_task_breast_cancer_b200.ops import Feat
+    for (N, H, W, Cin, Cout) in [(2, 16, 16, 64, 48), (2, 16, 16, 96, 48), (2, 8, 8, 48, 96), (2, 4, 16, 48, 48)]:
+        x = Feat.empty(N, H, W, Cin); dout = Feat.empty(N, 2 * H, 2 * W, Cout); dx = Feat.empty(N, H, W, Cin)
+        wd = torch.zeros(4, x.Ck, dout.Ck, dtype=torch.bfloat16, device="cuda")
+        acc = torch.zeros(4, dout.Ck, x.Ck, device="cuda")
+        with pytest.raises(_lib.MtbcError):
+            ops.convT_bwd_op(x, dout, wd, acc, None, dx, False)
+
+
 def test_fused_norm_backward_sums_refuse_unserved_shapes(D):
     """Channel pitches whose dense y tile would be read with shared-memory bank conflicts (32 / 48 / 64 channels) and planes
     the halo kernel does not take are refused at creation: plan.py then keeps the two-pass InstanceNorm backward."""

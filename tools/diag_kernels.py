@@ -307,6 +307,48 @@ def convT_case(N, H, W, Cin, Cout, k=2):
     run_case(fn, name)
 
 
+def convT_bwd_case(N, H, W, Cin, Cout, accumulate, bias=True):
+    """Fused backward of ConvTranspose2d(k = s = 2): data, weight and bias gradient from one pass over dout."""
+    name = f"convT_bwd N{N} {H}x{W} {Cin}->{Cout} acc={accumulate} bias={bias}"
+
+    def fn():
+        k = 2
+        x = rnd(N, Cin, H, W)
+        w = rnd(Cin, Cout, k, k, scale=0.1)
+        xf = Feat.from_nchw(x)
+        dout = rnd(N, Cout, H * k, W * k)
+        df = Feat.from_nchw(dout)
+        wf = torch.zeros(1, k * k * df.Ck, xf.Ck, dtype=torch.bfloat16, device=dev)
+        wd = torch.zeros(k * k, xf.Ck, df.Ck, dtype=torch.bfloat16, device=dev)
+        ops.pack_convT_weight(w, df.Ck, wf, wd)
+        base = rnd(N, Cin, H, W)
+        dx = Feat.from_nchw(base) if accumulate else Feat.empty(N, H, W, Cin)
+        acc = torch.zeros(k * k, df.Ck, xf.Ck, device=dev)
+        dbias = torch.full((Cout,), 0.5, device=dev) if bias else None     # accumulated into
+        op = ops.convT_bwd_op(xf, df, wd, acc, dbias, dx, accumulate)
+        op.launch()
+        grad = torch.zeros(Cin, Cout, k, k, device=dev)
+        _lib.call("mtbc_unpack_convT_wgrad", ops.ptr(acc), acc.shape[0] * acc.shape[1], acc.shape[2], ops.ptr(grad), Cin,
+                  Cout, k, 0, None)
+        torch.cuda.synchronize()
+        refdx = F.conv2d(dout, w, stride=k)
+        if accumulate:
+            refdx = refdx + base
+        report(name + " dx", dx.to_nchw(), refdx)
+        wr = w.clone().requires_grad_(True)
+        F.conv_transpose2d(x, wr, None, stride=k).backward(dout)
+        report(name + " dw", grad, wr.grad, tol=2e-3)
+        if bias:
+            report(name + " dbias", dbias, dout.sum((0, 2, 3)) + 0.5, tol=1e-4)
+        # a second launch accumulates the parameter gradients (the accumulators are only zeroed by the caller)
+        op.launch()
+        torch.cuda.synchronize()
+        if bias:
+            report(name + " dbias twice", dbias, 2 * dout.sum((0, 2, 3)) + 0.5, tol=1e-4)
+
+    run_case(fn, name)
+
+
 def first_conv_case(N, H, W, Cout):
     name = f"conv_first N{N} {H}x{W} 1->{Cout}"
 
@@ -759,6 +801,8 @@ def wgrad_cases():
 
 
 def convT_cases():
+    convT_bwd_case(2, 16, 16, 48, 48, False)
+    convT_bwd_case(2, 32, 16, 24, 48, True)
     convT_case(2, 16, 16, 64, 32)
     convT_case(2, 16, 16, 48, 48)
     convT_case(2, 8, 8, 384, 192)
