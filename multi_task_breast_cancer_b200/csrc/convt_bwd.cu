@@ -12,6 +12,10 @@
 // channel `Cin` of every landed tile, so row Cin of D_q is sum_pixel dy_q -- the bias gradient costs no instruction.
 // D_q (4 x 64 TMEM columns) stays resident for the CTA's whole tile range and is added to the pack-layout accumulator
 // once; D' is double buffered and drained per tile by four epilogue warps (bf16 store, or red.add for accumulation).
+// Shared memory is a ring of 16 KB slots, five per tile in the order dy_0 .. dy_3, x -- the order in which the MMA lane
+// lets go of them (dy_q after the weight-gradient MMAs of tap q, x after tap 3) -- so the producer refills a slot as soon
+// as its last reader has been issued and ~11 loads stay in flight (two whole 80 KB stages left the loads of the next
+// tile waiting for the last MMA of the previous one: 100 us per 48 -> 48 @128^2 layer at B = 32).
 #include "ptx.cuh"
 #include "internal.h"
 #include <string.h>
@@ -25,7 +29,7 @@ struct ConvTBwdParams {
   int32_t W, H, N, TW, TH, tiles_w, tiles_h, n_tiles;
   int32_t ci, co, NW;     // true channel counts; NW = data-gradient GEMM columns (Cin rounded up to 16)
   int32_t kd;             // K steps of the data gradient: ceil(Cout / 16)
-  int32_t stages, stage_bytes, w_tap_bytes, w_bytes;
+  int32_t slots, w_tap_bytes, w_bytes;   // ring of 16 KB slots, then the resident data-gradient weights
   int32_t n_rows, ld_k;
   float* dw_acc;
   float* dbias;
@@ -34,25 +38,28 @@ struct ConvTBwdParams {
 };
 
 constexpr int kCtBox = 128 * 128;   // one 128-pixel x 64-channel bf16 tile
-constexpr int kCtMaxStages = 4;
+constexpr int kCtMaxSlots = 12;
 constexpr int kCtDCol = 256;        // first TMEM column of the data-gradient accumulators (after 4 x 64 of D_q)
 
 __global__ void __launch_bounds__(256, 1) convT_bwd_kernel(const __grid_constant__ ConvTBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t s_full[kCtMaxStages], s_fixed[kCtMaxStages], s_empty[kCtMaxStages];
+  __shared__ uint64_t s_full[kCtMaxSlots], s_fixed[kCtMaxSlots], s_empty[kCtMaxSlots];
   __shared__ uint64_t s_dfull[2], s_dempty[2], s_wfull, s_accum;
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_w = smem;                 // resident data-gradient weights: [4 taps][NW rows x 128 B]
-  uint8_t* smem_s = smem + p.w_bytes;     // stages: [x tile][dy_0][dy_1][dy_2][dy_3]
+  uint8_t* smem_s = smem;                            // slot ring
+  uint8_t* smem_w = smem + p.slots * kCtBox;         // resident data-gradient weights: [4 taps][NW rows x 128 B]
+  // (the weights come last: the M = 128 weight-gradient MMA reads a second, meaningless 64-channel box behind the x slot,
+  //  which must still be shared memory when x sits in the last slot)
+  const int S = p.slots;
   const int t_begin = static_cast<int>(static_cast<int64_t>(p.n_tiles) * blockIdx.x / gridDim.x);
   const int t_end = static_cast<int>(static_cast<int64_t>(p.n_tiles) * (blockIdx.x + 1) / gridDim.x);
   const int NW = p.NW;
 
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_fixed[s], 1); mbar_init(&s_empty[s], 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_fixed[s], 1); mbar_init(&s_empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&s_dfull[b], 1); mbar_init(&s_dempty[b], 4); }
     mbar_init(&s_wfull, 1);
     mbar_init(&s_accum, 1);
@@ -75,18 +82,18 @@ __global__ void __launch_bounds__(256, 1) convT_bwd_kernel(const __grid_constant
         // ---------------------------------------------------------------- producer
         mbar_arrive_expect_tx(&s_wfull, static_cast<uint32_t>(4 * NW * 128));
         for (int q = 0; q < 4; ++q) tma_load_3d(smem_w + q * p.w_tap_bytes, &p.wmap, &s_wfull, 0, 0, q);
-        int stage = 0;
+        int slot = 0;
         uint32_t phase = 0;
         for (int t = t_begin; t < t_end; ++t) {
           const int w0 = (t % p.tiles_w) * p.TW;
           const int h0 = ((t / p.tiles_w) % p.tiles_h) * p.TH;
           const int n = t / (p.tiles_w * p.tiles_h);
-          mbar_wait(&s_empty[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&s_full[stage], 5u * kCtBox);
-          uint8_t* dst = smem_s + stage * p.stage_bytes;
-          tma_load_4d(dst, &p.xmap, &s_full[stage], 0, w0, h0, n);
-          for (int q = 0; q < 4; ++q) tma_load_4d(dst + (1 + q) * kCtBox, &p.dymap[q], &s_full[stage], 0, w0, h0, n);
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          for (int j = 0; j < 5; ++j) {   // dy_0 .. dy_3, x
+            mbar_wait(&s_empty[slot], phase ^ 1u);
+            mbar_arrive_expect_tx(&s_full[slot], static_cast<uint32_t>(kCtBox));
+            tma_load_4d(smem_s + slot * kCtBox, j < 4 ? &p.dymap[j] : &p.xmap, &s_full[slot], 0, w0, h0, n);
+            if (++slot == S) { slot = 0; phase ^= 1u; }
+          }
         }
       }
     } else if (warp == 1) {
@@ -96,55 +103,68 @@ __global__ void __launch_bounds__(256, 1) convT_bwd_kernel(const __grid_constant
         const uint32_t idesc_d = umma_idesc_bf16(128, NW, 0, 0);   // D'[pixel][ci]: both operands K-major, K = co
         const uint32_t hi = umma_desc_hi(1024u, 2u);               // 8 rows of 128 bytes, 128-byte swizzle
         mbar_wait(&s_wfull, 0);
-        int stage = 0;
+        int slot = 0;
         uint32_t phase = 0;
         int it = 0;
         for (int t = t_begin; t < t_end; ++t, ++it) {
           const int buf = it & 1;
           const uint32_t acc_phase = (it >> 1) & 1;
-          mbar_wait(&s_fixed[stage], phase);          // tile landed and its ones channel is written
           mbar_wait(&s_dempty[buf], acc_phase ^ 1u);  // epilogue has drained this data-gradient accumulator
           tc_fence_after();
-          const uint32_t base = smem_u32(smem_s + stage * p.stage_bytes);
           const uint32_t d_dx = tmem_base + kCtDCol + static_cast<uint32_t>(buf * NW);
           // data gradient first: its epilogue (global stores) overlaps the weight-gradient MMAs of the same tile
+          int sq[4];
           for (int q = 0; q < 4; ++q) {
-            const uint32_t a_lo = umma_desc_lo(base + (1 + q) * kCtBox, 16);
+            sq[q] = slot;
+            mbar_wait(&s_fixed[slot], phase);   // landed (s_full) and passed on by the ones-channel warp
+            tc_fence_after();
+            const uint32_t a_lo = umma_desc_lo(smem_u32(smem_s + slot * kCtBox), 16);
             const uint32_t b_lo = umma_desc_lo(smem_u32(smem_w + q * p.w_tap_bytes), 16);
             for (int k = 0; k < p.kd; ++k)
               umma_bf16_lohi(d_dx, a_lo + 2 * k, hi, b_lo + 2 * k, hi, idesc_d, (q | k) ? 1u : 0u);
+            if (++slot == S) { slot = 0; phase ^= 1u; }
           }
           umma_commit(&s_dfull[buf]);
-          const uint32_t x_lo = umma_desc_lo(base, kCtBox);
+          const int sx = slot;
+          mbar_wait(&s_fixed[sx], phase);   // x tile landed and its ones channel is written
+          tc_fence_after();
+          if (++slot == S) { slot = 0; phase ^= 1u; }
+          const uint32_t x_lo = umma_desc_lo(smem_u32(smem_s + sx * kCtBox), kCtBox);
           for (int q = 0; q < 4; ++q) {
-            const uint32_t b_lo = umma_desc_lo(base + (1 + q) * kCtBox, kCtBox);
+            const uint32_t b_lo = umma_desc_lo(smem_u32(smem_s + sq[q] * kCtBox), kCtBox);
             const uint32_t d_w = tmem_base + static_cast<uint32_t>(q * 64);
 #pragma unroll
             for (int k = 0; k < 8; ++k)   // 128 pixels = 8 K steps of 16 rows (2048 bytes = 128 descriptor units)
               umma_bf16_lohi(d_w, x_lo + k * 128, hi, b_lo + k * 128, hi, idesc_w, (it > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&s_empty[sq[q]]);   // every MMA that reads dy_q has been issued
           }
-          umma_commit(&s_empty[stage]);
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          umma_commit(&s_empty[sx]);
         }
         umma_commit(&s_accum);
       }
     } else if (warp == 2) {
       // ------------------------------------------------------------------ ones channel of every landed x tile
+      // Every slot passes through this warp (s_full -> s_fixed), so that s_fixed completes once per lap of the ring like
+      // the other barriers and one phase bit serves them all; only the x slots (every fifth) are written to.
       const int chunk = p.ci >> 3, sub = p.ci & 7;
-      int stage = 0;
+      int slot = 0;
       uint32_t phase = 0;
       for (int t = t_begin; t < t_end; ++t) {
-        mbar_wait(&s_full[stage], phase);
-        uint8_t* xb = smem_s + stage * p.stage_bytes;
+        for (int j = 0; j < 5; ++j) {
+          mbar_wait(&s_full[slot], phase);
+          if (j == 4) {
+            uint8_t* xb = smem_s + slot * kCtBox;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int r = lane + 32 * j;
-          *reinterpret_cast<uint16_t*>(xb + r * 128 + ((chunk ^ (r & 7)) << 4) + sub * 2) = 0x3F80;   // bf16 1.0
+            for (int i = 0; i < 4; ++i) {
+              const int r = lane + 32 * i;
+              *reinterpret_cast<uint16_t*>(xb + r * 128 + ((chunk ^ (r & 7)) << 4) + sub * 2) = 0x3F80;   // bf16 1.0
+            }
+            fence_proxy_async_smem();
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_fixed[slot]);
+          if (++slot == S) { slot = 0; phase ^= 1u; }
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_fixed[stage]);
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     } else if (warp >= 4) {
       // ------------------------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4)
@@ -254,8 +274,9 @@ int convT_bwd_create(const mtbc_convT_bwd_desc* d, OpBase** out) {
   p.ci = ci; p.co = co; p.NW = (ci + 15) & ~15; p.kd = (co + 15) / 16;
   p.w_tap_bytes = (p.NW * 128 + 1023) & ~1023;
   p.w_bytes = 4 * p.w_tap_bytes;
-  p.stage_bytes = 5 * kCtBox;
-  p.stages = 2;
+  p.slots = (212 * 1024 - 1024 - p.w_bytes) / kCtBox;
+  if (p.slots > kCtMaxSlots) p.slots = kCtMaxSlots;
+  if (p.slots < 6) { delete op; return set_error(MTBC_ERR_INVALID, "convT_bwd: no room for the slot ring"); }
   p.n_rows = d->n_rows; p.ld_k = d->ld_k;
   p.dw_acc = d->dw_acc; p.dbias = d->dbias;
   p.dx = reinterpret_cast<__nv_bfloat16*>(d->dx); p.dx_C = d->dx_C; p.accumulate = d->accumulate;
@@ -264,7 +285,7 @@ int convT_bwd_create(const mtbc_convT_bwd_desc* d, OpBase** out) {
   for (int q = 0; q < 4 && !rc; ++q) rc = encode_act(&p.dymap[q], d->dy[q], 64, 16, 8, 1);
   if (!rc) rc = encode_w(&p.wmap, d->wd, d->wd_ld, d->wd_rows, 4, 64, p.NW);
   if (rc) { delete op; return rc; }
-  op->smem_bytes = p.w_bytes + p.stages * p.stage_bytes + 1024;
+  op->smem_bytes = p.w_bytes + p.slots * kCtBox + 1024;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

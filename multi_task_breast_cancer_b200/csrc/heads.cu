@@ -105,9 +105,20 @@ __global__ void dshead_compose_kernel(const float* __restrict__ wt, const float*
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < C * kk) {
     const int ci = i / kk, q = i % kk;
-    float a = 0.f;
-    for (int co = 0; co < C; ++co) a = fmaf(wt[(static_cast<int64_t>(ci) * C + co) * kk + q], w1[co], a);
-    wc[i] = a;
+    // four independent chains, eight loads in flight: a single chain of C dependent load + FMA steps made this 37 us
+    // for C = 128, k = 8 (latency, not bytes)
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const float* wp = wt + static_cast<int64_t>(ci) * C * kk + q;
+    int co = 0;
+#pragma unroll 2
+    for (; co + 4 <= C; co += 4) {
+      a0 = fmaf(wp[static_cast<int64_t>(co) * kk], w1[co], a0);
+      a1 = fmaf(wp[static_cast<int64_t>(co + 1) * kk], w1[co + 1], a1);
+      a2 = fmaf(wp[static_cast<int64_t>(co + 2) * kk], w1[co + 2], a2);
+      a3 = fmaf(wp[static_cast<int64_t>(co + 3) * kk], w1[co + 3], a3);
+    }
+    for (; co < C; ++co) a0 = fmaf(wp[static_cast<int64_t>(co) * kk], w1[co], a0);
+    wc[i] = (a0 + a1) + (a2 + a3);
   }
   if (i == 0) {
     float a = b1[0];
@@ -301,14 +312,24 @@ __global__ void __launch_bounds__(256) dshead_reduce_kernel(const float* __restr
                                                             float* __restrict__ bred) {
   const int e = blockIdx.x * 256 + threadIdx.x;
   if (e < n) {
-    float s = 0.f;
-    for (int r = 0; r < nparts; ++r) s += part[static_cast<int64_t>(r) * n + e];
-    red[e] = s;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // (independent chains: the loads of a row are what takes time)
+    int r = 0;
+#pragma unroll 2
+    for (; r + 4 <= nparts; r += 4) {
+      s0 += part[static_cast<int64_t>(r) * n + e];
+      s1 += part[static_cast<int64_t>(r + 1) * n + e];
+      s2 += part[static_cast<int64_t>(r + 2) * n + e];
+      s3 += part[static_cast<int64_t>(r + 3) * n + e];
+    }
+    for (; r < nparts; ++r) s0 += part[static_cast<int64_t>(r) * n + e];
+    red[e] = (s0 + s1) + (s2 + s3);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x >= 224) {   // last warp of the (partly idle) last block
+    const int lane = threadIdx.x & 31;
     float b = 0.f;
-    for (int r = 0; r < nparts; ++r) b += bpart[r];
-    bred[0] = b;
+    for (int r = lane; r < nparts; r += 32) b += bpart[r];
+    b = warp_sum(b);
+    if (lane == 0) bred[0] = b;
   }
 }
 
