@@ -581,6 +581,74 @@ __global__ void __launch_bounds__(256) conv_first_wgrad_kernel(const float* __re
   }
 }
 
+// Row-strip variant of the first-layer weight gradient (W % 64 == 0, H % 8 == 0, at most four 8-channel groups): the
+// launch sits alone at the very end of the backward pass (nothing left to overlap it), so its 125 us were step time.
+// A block owns 8 image rows of one sample: the 10 x rows it needs go to shared memory once, zero halo included (the
+// per-pixel version spent half of its instructions on nine predicated, L1-served x loads per thread, with a quarter of
+// the threads idle at 24 channels); thread (g = tid / 64, s = tid % 64) walks pixels s, s + 64, ... of every row with the
+// 8 channels of group g: one 16-byte dy load, nine shared-memory loads and 72 FMAs per pixel.  The partials of a block
+// are summed through shared memory (one pass, no shuffles, no contended atomics) and leave as 72 G global atomics.
+constexpr int kFirstRB = 8;
+template <typename T>
+__global__ void __launch_bounds__(256) conv_first_wgrad_rows_kernel(const float* __restrict__ x, int N, int Cin, int H, int W,
+                                                                    const T* __restrict__ dy, int Cp, int Cout,
+                                                                    float* __restrict__ dw) {
+  extern __shared__ float sm[];
+  const int nthr = blockDim.x, NG = nthr >> 6;
+  const int ci = blockIdx.y;
+  const int strips = H / kFirstRB;
+  const int n = blockIdx.x / strips, h0 = (blockIdx.x - n * strips) * kFirstRB;
+  const int WP = W + 2;
+  float* s_x = sm;                                   // [kFirstRB + 2][W + 2]
+  const float* plane = x + (static_cast<int64_t>(n) * Cin + ci) * H * W;
+  for (int i = threadIdx.x; i < (kFirstRB + 2) * WP; i += nthr) {
+    const int r = i / WP, c = i - r * WP;
+    const int hh = h0 - 1 + r, ww = c - 1;
+    s_x[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(plane + hh * W + ww) : 0.f;
+  }
+  __syncthreads();
+  const int g = threadIdx.x >> 6, sl = threadIdx.x & 63;
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
+  for (int r = 0; r < kFirstRB; ++r) {
+    const T* drow = dy + ((static_cast<int64_t>(n) * H + h0 + r) * W) * Cp + g * 8;
+    const float* xr = s_x + r * WP + sl;
+#pragma unroll 2
+    for (int w0 = 0; w0 < W; w0 += 64) {
+      const V8 d0 = load8<T>(drow + static_cast<int64_t>(w0 + sl) * Cp);
+      float xs[9];
+#pragma unroll
+      for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+        for (int ss = 0; ss < 3; ++ss) xs[rr * 3 + ss] = xr[rr * WP + w0 + ss];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[t][i] = fmaf(xs[t], d0.f[i], acc[t][i]);
+    }
+  }
+  __syncthreads();                                   // s_x is dead: reuse the memory for the partials
+  const int pitch = nthr + 1;
+  float* s_p = sm;                                   // [72][nthr + 1]
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_p[(t * 8 + i) * pitch + threadIdx.x] = acc[t][i];
+  __syncthreads();
+  for (int o = threadIdx.x; o < NG * 72; o += nthr) {
+    const int g2 = o / 72, ti = o - g2 * 72;
+    const int t = ti >> 3, co = g2 * 8 + (ti & 7);
+    const float* row = s_p + ti * pitch + g2 * 64;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < 64; k += 4) { a0 += row[k]; a1 += row[k + 1]; a2 += row[k + 2]; a3 += row[k + 3]; }
+    if (co < Cout) atomicAdd(dw + (static_cast<int64_t>(co) * Cin + ci) * 9 + t, (a0 + a1) + (a2 + a3));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ utilities
 __global__ void fill_f32_kernel(float* p, int64_t n, float v) {
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
@@ -714,6 +782,21 @@ int mtbc_conv_first_wgrad(const float* x, int32_t N, int32_t Cin, int32_t H, int
   if (Cin < 1 || Cin > 4 || Cout > 64 || Cp % 8 != 0) return set_error(MTBC_ERR_INVALID, "conv_first_wgrad: Cin 1..4, Cout <= 64");
   const int64_t total = static_cast<int64_t>(N) * H * W;
   if (total >= (1ll << 31)) return set_error(MTBC_ERR_INVALID, "conv_first_wgrad: N*H*W must be below 2^31");
+  cudaStream_t st_rows = static_cast<cudaStream_t>(stream);
+  if (W % 64 == 0 && H % kFirstRB == 0 && Cp <= 32 && !getenv("MTBC_FIRST_WGRAD_PIXELS")) {
+    const int NG = Cp / 8, nthr = NG * 64;
+    size_t smem = static_cast<size_t>(72) * (nthr + 1) * sizeof(float);
+    const size_t sx = static_cast<size_t>(kFirstRB + 2) * (W + 2) * sizeof(float);
+    if (sx > smem) smem = sx;
+    if (smem <= 200 * 1024) {
+      const dim3 grid(N * (H / kFirstRB), Cin);
+      MTBC_DISPATCH_ACT(({
+        if (smem > 48 * 1024) cudaFuncSetAttribute(conv_first_wgrad_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        conv_first_wgrad_rows_kernel<T><<<grid, nthr, smem, st_rows>>>(x, N, Cin, H, W, static_cast<const T*>(dy), Cp, Cout, dw);
+      }));
+      return check_launch("conv_first_wgrad_rows");
+    }
+  }
   const int G = Cp <= 32 ? 4 : 8;
   int gx = static_cast<int>((total + (256 / G) * 16 - 1) / ((256 / G) * 16));
   if (gx > 148 * 4) gx = 148 * 4;

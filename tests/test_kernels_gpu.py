@@ -159,10 +159,12 @@ def test_first_layer(D, cout):
     _run(D, D.first_conv_case, 2, 32, 32, cout)
 
 
-@pytest.mark.parametrize("args", [(3, 64, 64, 24), (2, 128, 128, 32), (2, 16, 24, 24), (5, 32, 32, 16)])
+@pytest.mark.parametrize("args", [(3, 64, 64, 24), (2, 128, 128, 32), (2, 16, 24, 24), (5, 32, 32, 16), (2, 64, 192, 24),
+                                  (32, 256, 256, 24), (3, 72, 128, 16)])
 def test_first_layer_shapes(D, args):
     """Whole 1024-pixel blocks (8 pixels per thread, register-resident statistics) and planes that are not (one pixel
-    per thread); the weight gradient's pixel loop wraps around the grid."""
+    per thread); the weight gradient's pixel loop wraps around the grid; W % 64 == 0 and H % 8 == 0 take the row-strip
+    weight gradient (one, two and four 64-pixel passes per row; the benchmark shape), the others the per-pixel one."""
     _run(D, D.first_conv_case, *args)
 
 
