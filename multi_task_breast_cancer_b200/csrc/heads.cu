@@ -12,6 +12,9 @@ template <typename T>
 __global__ void __launch_bounds__(256) head1x1_fwd_kernel(const T* __restrict__ a, int64_t npix, int Cp,
                                                           int C, const float* __restrict__ w,
                                                           const float* __restrict__ b, float* __restrict__ logits) {
+  pdl_trigger();   // programmatic dependent launch (ptx.cuh)
+  pdl_wait();
+
   extern __shared__ float s_w[];  // [Cp]
   for (int i = threadIdx.x; i < Cp; i += 256) s_w[i] = i < C ? w[i] : 0.f;
   __syncthreads();
@@ -38,6 +41,9 @@ __global__ void __launch_bounds__(256) head1x1_bwd_kernel(const T* __restrict__ 
                                                           const float* __restrict__ w, T* __restrict__ dA,
                                                           int accumulate, float* __restrict__ dw,
                                                           float* __restrict__ db) {
+  pdl_trigger();   // programmatic dependent launch (ptx.cuh)
+  pdl_wait();
+
   __shared__ float s_stage[9 * 256];   // [k][thread]: 8 channel partials + the bias partial
   const int cvec = Cp / 8;
   const int bd = blockDim.x;
@@ -740,7 +746,7 @@ extern "C" {
 int mtbc_head1x1_fwd(const void* a, int64_t npix, int32_t Cp, int32_t C, const float* w, const float* b,
                      float* logits, void* stream) {
   int g = cdiv(npix, 256); if (g > 148 * 8) g = 148 * 8;
-  MTBC_DISPATCH_ACT((head1x1_fwd_kernel<T><<<g, 256, Cp * sizeof(float), ST(stream)>>>(CTP(a), npix, Cp, C, w, b, logits)));
+  MTBC_DISPATCH_ACT((launch_pdl(head1x1_fwd_kernel<T>, dim3(g), dim3(256), Cp * sizeof(float), ST(stream), CTP(a), npix, Cp, C, w, b, logits)));
   return check_launch("head1x1_fwd");
 }
 int mtbc_head1x1_bwd(const void* a, const float* dlogits, int64_t npix, int32_t Cp, int32_t C, const float* w,
@@ -749,7 +755,7 @@ int mtbc_head1x1_bwd(const void* a, const float* dlogits, int64_t npix, int32_t 
   if (Cp % 8 != 0 || cvec > 256) return set_error(MTBC_ERR_INVALID, "head1x1_bwd: Cp %% 8 != 0 or Cp > 2048");
   const int bd = (256 / cvec) * cvec;   // block size multiple of the channel-group count: a thread's group is invariant
   int g = cdiv(npix * cvec, bd * 8); if (g > 148 * 8) g = 148 * 8; if (g < 1) g = 1;
-  MTBC_DISPATCH_ACT((head1x1_bwd_kernel<T><<<g, bd, 0, ST(stream)>>>(CTP(a), dlogits, npix, Cp, C, w, TP(dA), accumulate, dw, db)));
+  MTBC_DISPATCH_ACT((launch_pdl(head1x1_bwd_kernel<T>, dim3(g), dim3(bd), 0, ST(stream), CTP(a), dlogits, npix, Cp, C, w, TP(dA), accumulate, dw, db)));
   return check_launch("head1x1_bwd");
 }
 int mtbc_dshead_compose(const float* wt, const float* bt, const float* w1, const float* b1, int32_t C, int32_t k,

@@ -10,6 +10,9 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf
 __global__ void __launch_bounds__(256) dice_sums_kernel(const float* __restrict__ logits,
                                                         const float* __restrict__ target, int64_t HW,
                                                         float* __restrict__ sums) {
+  pdl_trigger();   // programmatic dependent launch (ptx.cuh)
+  pdl_wait();
+
   const int n = blockIdx.y;
   const float4* x4 = reinterpret_cast<const float4*>(logits + static_cast<int64_t>(n) * HW);
   const float4* t4 = reinterpret_cast<const float4*>(target + static_cast<int64_t>(n) * HW);
@@ -45,6 +48,9 @@ __global__ void __launch_bounds__(256) dice_sums_kernel(const float* __restrict_
 }
 
 __global__ void dice_finalize_kernel(const float* __restrict__ sums, int N, float* __restrict__ loss) {
+  pdl_trigger();   // programmatic dependent launch (ptx.cuh)
+  pdl_wait();
+
   float s = 0.f;
   for (int n = threadIdx.x; n < N; n += 32) {
     const float I = sums[n * 3], G = sums[n * 3 + 1], P = sums[n * 3 + 2];
@@ -58,6 +64,9 @@ __global__ void __launch_bounds__(256) dice_bwd_kernel(const float* __restrict__
                                                        const float* __restrict__ target, int64_t HW, int N,
                                                        const float* __restrict__ sums, const float* __restrict__ gscale,
                                                        float gmul, float* __restrict__ dlogits) {
+  pdl_trigger();   // programmatic dependent launch (ptx.cuh)
+  pdl_wait();
+
   const int n = blockIdx.y;
   const float I = sums[n * 3], G = sums[n * 3 + 1], P = sums[n * 3 + 2];
   const float D = G + P + 1.f, num = 2.f * I + 1.f;
@@ -96,6 +105,9 @@ __device__ __forceinline__ void focal_sample(const float* x, const float* t, int
 
 __global__ void focal_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ target, int N, int K,
                                  float alpha, float gamma, float* __restrict__ loss) {
+  pdl_trigger();   // programmatic dependent launch (ptx.cuh)
+  pdl_wait();
+
   float s = 0.f;
   for (int n = threadIdx.x; n < N; n += 32) {
     float fl, d, lse, ts;
@@ -109,6 +121,9 @@ __global__ void focal_fwd_kernel(const float* __restrict__ logits, const float* 
 __global__ void focal_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ target, int N, int K,
                                  float alpha, float gamma, const float* __restrict__ gscale, float gmul,
                                  float* __restrict__ dlogits) {
+  pdl_trigger();   // programmatic dependent launch (ptx.cuh)
+  pdl_wait();
+
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const float* x = logits + static_cast<int64_t>(n) * K;
@@ -124,6 +139,9 @@ __global__ void focal_bwd_kernel(const float* __restrict__ logits, const float* 
 
 __global__ void multitask_loss_kernel(const float* __restrict__ dice, int nheads, int inv_w,
                                       const float* __restrict__ focal, float alpha_mix, float* __restrict__ out) {
+  pdl_trigger();   // programmatic dependent launch (ptx.cuh)
+  pdl_wait();
+
   float seg = 0.f;
   for (int j = 0; j < nheads; ++j) seg += inv_w ? dice[j] / static_cast<float>(j + 1) : dice[j];
   const float cls = focal[0];
@@ -136,6 +154,9 @@ __global__ void multitask_loss_kernel(const float* __restrict__ dice, int nheads
 // ------------------------------------------------------------------------------------------------ refinement
 __global__ void __launch_bounds__(256) refine_count_kernel(const float* __restrict__ mask_logits, int64_t HW,
                                                            int32_t* __restrict__ count) {
+  pdl_trigger();   // programmatic dependent launch (ptx.cuh)
+  pdl_wait();
+
   const int n = blockIdx.y;
   const float* x = mask_logits + static_cast<int64_t>(n) * HW;
   int c = 0;
@@ -149,6 +170,9 @@ __global__ void __launch_bounds__(256) refine_apply_kernel(const float* __restri
                                                            int pixel_threshold, const int32_t* __restrict__ count,
                                                            uint8_t* __restrict__ mask_out,
                                                            int32_t* __restrict__ class_out) {
+  pdl_trigger();   // programmatic dependent launch (ptx.cuh)
+  pdl_wait();
+
   const int n = blockIdx.y;
   int cls = 0;
   float best = class_logits[static_cast<int64_t>(n) * K];
@@ -279,6 +303,9 @@ __global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ p, co
                                                        float* __restrict__ m, float* __restrict__ v, int64_t n,
                                                        const float* __restrict__ lr_dev, float b1, float b2, float eps,
                                                        float gscale, const int32_t* __restrict__ step_dev) {
+  pdl_trigger();   // programmatic dependent launch (ptx.cuh)
+  pdl_wait();
+
   const float step = static_cast<float>(step_dev[0]);
   const float bc1 = 1.f - powf(b1, step);
   const float bc2s = sqrtf(1.f - powf(b2, step));
@@ -363,32 +390,32 @@ extern "C" {
 
 int mtbc_dice_sums(const float* logits, const float* target, int32_t N, int64_t HW, float* sums, void* stream) {
   int gx = cdiv(HW / 4 + 1, 256 * 4); if (gx > (148 * 8) / N + 1) gx = (148 * 8) / N + 1; if (gx < 1) gx = 1;
-  dice_sums_kernel<<<dim3(gx, N), 256, 0, ST(stream)>>>(logits, target, HW, sums);
+  launch_pdl(dice_sums_kernel, dim3(gx, N), dim3(256), 0, ST(stream), logits, target, HW, sums);
   return check_launch("dice_sums");
 }
 int mtbc_dice_finalize(const float* sums, int32_t N, float* loss, void* stream) {
-  dice_finalize_kernel<<<1, 32, 0, ST(stream)>>>(sums, N, loss);
+  launch_pdl(dice_finalize_kernel, dim3(1), dim3(32), 0, ST(stream), sums, N, loss);
   return check_launch("dice_finalize");
 }
 int mtbc_dice_bwd(const float* logits, const float* target, int32_t N, int64_t HW, const float* sums,
                   const float* gscale, float gmul, float* dlogits, void* stream) {
   int gx = cdiv(HW, 256 * 4); if (gx > (148 * 8) / N + 1) gx = (148 * 8) / N + 1; if (gx < 1) gx = 1;
-  dice_bwd_kernel<<<dim3(gx, N), 256, 0, ST(stream)>>>(logits, target, HW, N, sums, gscale, gmul, dlogits);
+  launch_pdl(dice_bwd_kernel, dim3(gx, N), dim3(256), 0, ST(stream), logits, target, HW, N, sums, gscale, gmul, dlogits);
   return check_launch("dice_bwd");
 }
 int mtbc_focal_fwd(const float* logits, const float* target, int32_t N, int32_t K, float alpha, float gamma,
                    float* loss, void* stream) {
-  focal_fwd_kernel<<<1, 32, 0, ST(stream)>>>(logits, target, N, K, alpha, gamma, loss);
+  launch_pdl(focal_fwd_kernel, dim3(1), dim3(32), 0, ST(stream), logits, target, N, K, alpha, gamma, loss);
   return check_launch("focal_fwd");
 }
 int mtbc_focal_bwd(const float* logits, const float* target, int32_t N, int32_t K, float alpha, float gamma,
                    const float* gscale, float gmul, float* dlogits, void* stream) {
-  focal_bwd_kernel<<<cdiv(N, 64), 64, 0, ST(stream)>>>(logits, target, N, K, alpha, gamma, gscale, gmul, dlogits);
+  launch_pdl(focal_bwd_kernel, dim3(cdiv(N, 64)), dim3(64), 0, ST(stream), logits, target, N, K, alpha, gamma, gscale, gmul, dlogits);
   return check_launch("focal_bwd");
 }
 int mtbc_multitask_loss(const float* dice_losses, int32_t nheads, int32_t inversely_weighted, const float* focal,
                         float alpha_mix, float* out, void* stream) {
-  multitask_loss_kernel<<<1, 1, 0, ST(stream)>>>(dice_losses, nheads, inversely_weighted, focal, alpha_mix, out);
+  launch_pdl(multitask_loss_kernel, dim3(1), dim3(1), 0, ST(stream), dice_losses, nheads, inversely_weighted, focal, alpha_mix, out);
   return check_launch("multitask_loss");
 }
 
@@ -398,10 +425,10 @@ int mtbc_refine_predictions(const float* mask_logits, const float* class_logits,
   cudaError_t e = cudaMemsetAsync(count_out, 0, N * sizeof(int32_t), ST(stream));
   if (e != cudaSuccess) return set_error(MTBC_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
   int gx = cdiv(HW, 256 * 8); if (gx > (148 * 8) / N + 1) gx = (148 * 8) / N + 1; if (gx < 1) gx = 1;
-  refine_count_kernel<<<dim3(gx, N), 256, 0, ST(stream)>>>(mask_logits, HW, count_out);
+  launch_pdl(refine_count_kernel, dim3(gx, N), dim3(256), 0, ST(stream), mask_logits, HW, count_out);
   int rc = check_launch("refine_count");
   if (rc) return rc;
-  refine_apply_kernel<<<dim3(gx, N), 256, 0, ST(stream)>>>(mask_logits, class_logits, HW, K, normal_id, seg_by_class,
+  launch_pdl(refine_apply_kernel, dim3(gx, N), dim3(256), 0, ST(stream), mask_logits, class_logits, HW, K, normal_id, seg_by_class,
                                                           class_by_seg, pixel_threshold, count_out, mask_out, class_out);
   return check_launch("refine_apply");
 }
@@ -449,7 +476,7 @@ int mtbc_adam_step_dev(float* param, const float* grad, float* exp_avg, float* e
                        const int32_t* step_dev, void* stream) {
   if (n <= 0) return 0;
   int g = cdiv(n, 256 * 4); if (g > 148 * 8) g = 148 * 8;
-  adam_dev_kernel<<<g, 256, 0, ST(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr_dev, beta1, beta2, eps, grad_scale, step_dev);
+  launch_pdl(adam_dev_kernel, dim3(g), dim3(256), 0, ST(stream), param, grad, exp_avg, exp_avg_sq, n, lr_dev, beta1, beta2, eps, grad_scale, step_dev);
   return check_launch("adam_step_dev");
 }
 int mtbc_increment_i32(int32_t* p, void* stream) {
