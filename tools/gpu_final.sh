@@ -34,6 +34,7 @@ echo "ncu launches exit $?"
 i=0
 while IFS= read -r SEL; do
   [ -z "$SEL" ] && continue
+  [ -n "$SKIP_FULL" ] && continue
   i=$((i+1))
   ONLY="$SEL" timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on \
       -f -o $OUT/${TAG}_full_${i} python tools/ncu_step.py /dev/null > $OUT/${TAG}_ncu_full_${i}.log 2>&1
