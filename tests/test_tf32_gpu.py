@@ -222,3 +222,44 @@ def test_deterministic_mode_is_bit_reproducible(arch):
     with torch.no_grad():
         pl, po = plain(img)
     assert rel(po[-1], runs[0][0][-1]) < 2e-2
+
+
+def test_fused_transposed_conv_backward_matches_the_three_launch_path(monkeypatch):
+    """Plan level: the one-pass backward of the 48 -> 48 transposed convolutions (convt_bwd.cu: data + weight + bias
+    gradient) against the three launches it replaces (MTBC_FUSE_CONVT_BWD=0), in deterministic mode where two runs of
+    the same path agree to cos >= 0.999: same forward bits, same gradients up to summation order -- for the transposed
+    convolutions' own parameters and for everything upstream of their data gradient."""
+    from oracle import torch_oracle as O
+    from multi_task_breast_cancer_b200 import criterions as Cr
+    img, mask, onehot, _ = O.synthetic_batch(2, 128, 128, device="cuda")
+    grads, outs_all, kinds = [], [], []
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("MTBC_FUSE_CONVT_BWD", fuse)
+        _, new = pair("unetpp")
+        new.set_precision("bf16", deterministic=True)
+        logits, outs = new(img)
+        seg, cls = Cr.apply_criterion_multitask_segmentation_classification(
+            Cr.init_criterion_segmentation("DICE"), mask, outs, Cr.init_criterion_classification(3, None, "Focal"),
+            onehot, logits, True)
+        (0.35 * seg + 0.65 * cls).backward()
+        torch.cuda.synchronize()
+        grads.append({n: p.grad.detach().clone() for n, p in new.named_parameters() if p.grad is not None})
+        outs_all.append([t.detach().clone() for t in list(logits) + list(outs)])
+        plan = next(iter(new._plans.values()))
+        kinds.append({getattr(l, "kind", "") for l in plan.bwd})
+    assert "convT_bwd" in kinds[0] and "convT_bwd" not in kinds[1], kinds
+    for a, b in zip(outs_all[0], outs_all[1]):
+        assert torch.equal(a, b)
+    fa = torch.cat([g.flatten() for g in grads[0].values()])
+    fb = torch.cat([grads[1][n].flatten() for n in grads[0]])
+    cos = torch.nn.functional.cosine_similarity(fa, fb, dim=0).item()
+    # the fused layers' own weights (upcat_0_j: 48 -> 48 @ half resolution) and every transposed-conv parameter; bias
+    # gradients are plane sums with cancellation, and the deeper layers only see the fused layers through bf16 data
+    # gradients whose accumulation order differs (measured worst: 3.6e-2 on a bias two levels down)
+    own = max((rel(grads[0][n], grads[1][n]), n) for n in grads[0] if n.startswith("upcat_0_") and n.endswith("deconv.weight"))
+    worst = max((rel(grads[0][n], grads[1][n]), n) for n in grads[0] if "deconv" in n)
+    print(f"\nfused vs three-launch transposed-conv backward: flat gradient cos {cos:.6f}, fused layers' weights worst "
+          f"{own[1]} rel {own[0]:.2e}, all transposed-conv parameters worst {worst[1]} rel {worst[0]:.2e}")
+    assert cos >= 0.999, cos
+    assert own[0] < 2e-2, own
+    assert worst[0] < 1e-1, worst
