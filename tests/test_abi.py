@@ -87,3 +87,39 @@ def test_product_package_never_imports_the_oracle_or_aten_compute():
                 assert (node.module or "") != "torch.nn.functional", fn
             if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute):
                 assert node.func.attr not in banned_calls, (fn, node.func.attr, node.lineno)
+
+
+def test_descriptor_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors of the descriptor structs have the size and field offsets the C compiler gives include/mtbc.h
+    (a field appended on one side only would shift every later argument silently)."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    import pytest
+    from multi_task_breast_cancer_b200 import _lib as L
+    gcc = shutil.which("gcc") or shutil.which("cc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    pairs = [("mtbc_act_view", L.ActView, ["ptr", "sN"]), ("mtbc_gemm_seg", L.GemmSeg, ["wtap"]),
+             ("mtbc_out_slice", L.OutSlice, ["accumulate"]),
+             ("mtbc_conv_gemm_desc", L.ConvGemmDesc, ["seg", "wpack", "outs", "dtype", "wpack_lo", "bwd_y", "bwd_slope"]),
+             ("mtbc_wgrad_desc", L.WgradDesc, ["taps", "dw_acc", "dtype"]),
+             ("mtbc_wgrad_multi_desc", L.WgradMultiDesc, ["k0", "dy", "splits"]),
+             ("mtbc_convT_bwd_desc", L.ConvTBwdDesc, ["dy", "wd", "dw_acc", "dbias", "dx", "Cout"]),
+             ("mtbc_param_job", L.ParamJob, ["i", "src", "dst1"])]
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "mtbc.h"', "int main(void) {"]
+    for cname, _, fields in pairs:
+        lines.append(f'  printf("%zu", sizeof({cname}));')
+        for f in fields:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {f}));')
+        lines.append('  printf("\\n");')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    for (cname, ct, fields), line in zip(pairs, out):
+        want = [int(v) for v in line.split()]
+        have = [C.sizeof(ct)] + [getattr(ct, f).offset for f in fields]
+        assert have == want, (cname, fields, have, want)
