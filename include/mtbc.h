@@ -130,6 +130,13 @@ typedef struct {
   const float* bwd_gamma;
   const float* bwd_beta;
   float bwd_slope;
+  /* Pixel-pair view (stat_fold > 0; halo-eligible 3x3 forward convolutions only, no bwd_y): the caller describes a conv
+   * over the tensors viewed as (N, H, W/2, 2C) -- one TMA box row = two neighbouring pixels of a dense 24-channel tensor
+   * (96 bytes) instead of one (48) -- with the paired weights of MTBC_JOB_PACK_CONV_PAIR, so GEMM column c = op * C + co
+   * is output pixel 2q + op, channel co.  Statistics and bias are per CHANNEL: column c (< stat_C) adds into
+   * stat_sum[n][c % stat_fold] / stat_sq[n][c % stat_fold] (rows of stat_fold floats) and takes bias[c % stat_fold].
+   * Creation fails with MTBC_ERR_INVALID if the shape is not served by the halo kernel. */
+  int32_t stat_fold;
 } mtbc_conv_gemm_desc;
 
 /* One tap of a weight-gradient GEMM: dW[tap][co][k0 + ci] += sum_pixels A[a_view][pixel + (a_dh,a_dw)][ci] *
@@ -235,10 +242,17 @@ int mtbc_unpack_convT_wgrad(const float* acc, int32_t rows, int32_t ld, float* g
  *   PACK_CONVT    i = {Cin, Cout, k, cp, wf_ld, wd_rows, wd_ld}                      src=w dst0=wf dst1=wd|NULL
  *   UNPACK_CONV   i = {rows, ld, k0, Cout, Cin, ksz, c_begin, c_count, add}          src=acc dst0=grad
  *   UNPACK_CONVT  i = {rows, ld, Cin, Cout, k, add}                                  src=acc dst0=grad
+ *   PACK_CONV_PAIR i = {Cout, Cin, c_begin, c_count, rows, ld, k0, n0, Ks, Np, dgrad}  src=w dst0=wp (bf16, pre-zeroed)
+ *     3x3 Conv2d weight -> operand of the SAME convolution over pixel pairs (mtbc_conv_gemm_desc.stat_fold): with
+ *     E[dh][dw][k][n] the per-pixel operand (forward: k = ci - c_begin, n = co, E = w[co][ci][dh+1][dw+1]; dgrad != 0:
+ *     k = co, n = ci - c_begin, E = w[co][ci][1-dh][1-dw]) the pair operand is
+ *       wp[(dh+1)*3 + (dq+1)][n0 + op*Np + n][k0 + par*Ks + k] = E[dh][2*dq + par - op][k][n]   (|2*dq + par - op| <= 1)
+ *     for input pixel parity par and output pixel parity op (Ks / Np = channel pitch of the source / output tensor);
+ *     every other element of wp stays zero.
  * The table is copied to the device at creation; launch with mtbc_op_launch. */
 enum mtbc_job_kind {
   MTBC_JOB_COPY_F32 = 0, MTBC_JOB_PACK_CONV = 1, MTBC_JOB_PACK_CONVT = 2, MTBC_JOB_UNPACK_CONV = 3,
-  MTBC_JOB_UNPACK_CONVT = 4
+  MTBC_JOB_UNPACK_CONVT = 4, MTBC_JOB_PACK_CONV_PAIR = 5
 };
 typedef struct {
   int32_t kind;

@@ -38,7 +38,7 @@ class ConvGemmDesc(C.Structure):
                 ("stat_C", c_i32), ("accumulate", c_i32), ("nouts", c_i32), ("outs", OutSlice * MAX_VIEWS),
                 ("dtype", c_i32), ("wpack_lo", c_vp),
                 ("bwd_y", c_vp), ("bwd_mean", c_vp), ("bwd_rstd", c_vp), ("bwd_gamma", c_vp), ("bwd_beta", c_vp),
-                ("bwd_slope", c_f32)]
+                ("bwd_slope", c_f32), ("stat_fold", c_i32)]
 
 
 class WgradTap(C.Structure):
@@ -67,7 +67,7 @@ class ParamJob(C.Structure):
     _fields_ = [("kind", c_i32), ("i", c_i32 * 11), ("src", c_vp), ("dst0", c_vp), ("dst1", c_vp)]
 
 
-JOB_COPY_F32, JOB_PACK_CONV, JOB_PACK_CONVT, JOB_UNPACK_CONV, JOB_UNPACK_CONVT = range(5)
+JOB_COPY_F32, JOB_PACK_CONV, JOB_PACK_CONVT, JOB_UNPACK_CONV, JOB_UNPACK_CONVT, JOB_PACK_CONV_PAIR = range(6)
 
 
 # name -> argtypes (return type is int unless listed in _RESTYPES)

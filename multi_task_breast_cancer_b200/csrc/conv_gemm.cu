@@ -752,6 +752,7 @@ int conv_gemm_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   if (d->bwd_y != nullptr)
     return set_error(MTBC_ERR_INVALID, "conv_gemm: fused InstanceNorm backward statistics need a halo-eligible 3x3 shape");
   if (d->nouts > 0) return set_error(MTBC_ERR_INVALID, "conv_gemm: routed outputs need a halo-eligible 3x3 shape");
+  if (d->stat_fold != 0) return set_error(MTBC_ERR_INVALID, "conv_gemm: the pixel-pair view needs a halo-eligible 3x3 shape (bf16)");
   if (d->nviews < 1 || d->nviews > MTBC_MAX_VIEWS || d->nseg < 1 || d->nseg > MTBC_MAX_SEGS)
     return set_error(MTBC_ERR_INVALID, "conv_gemm: bad nviews/nseg (%d, %d)", d->nviews, d->nseg);
   if (d->ncols % 32 != 0) return set_error(MTBC_ERR_INVALID, "conv_gemm: ncols %% 32 != 0");

@@ -52,6 +52,9 @@ struct ConvHaloParams {
   int32_t late_release;   // debug (MTBC_HALO_LATE_RELEASE=1): hand the accumulator back after the stores, not before
   int32_t G, bn1;   // G = output rows stacked along N (1 or 2); bn1 = columns per output pixel; BN = G * bn1
   int32_t stat_C;
+  int32_t stat_fold;      // pixel-pair view (mtbc_conv_gemm_desc.stat_fold): column c -> channel c % stat_fold
+  int32_t pair24;         // ... of a 24 -> 24 layer: only the non-zero blocks of the pair operand are issued
+
   const float* bias;
   float* stat_sum;
   float* stat_sq;
@@ -131,6 +134,42 @@ __device__ __forceinline__ void halo_issue_chunk_g2(uint32_t d_addr, uint32_t a_
   }
 }
 
+// Pixel-pair view of a dense 24-channel source and 24-channel output (mtbc_conv_gemm_desc.stat_fold = 24, one 64-wide
+// chunk: K elements [0, 24) = pixel 2q, [24, 48) = pixel 2q+1; columns [0, 24) = output pixel 2q, [24, 48) = 2q+1).  Of the
+// nine (dh, dq) tap blocks only the three dq = 0 ones are dense; a dq = -1 block holds a single 24 x 24 sub-block
+// (input pixel 2q-1 -> output pixel 2q: K elements 24..47, columns 0..23) and a dq = +1 block the opposite corner
+// (input pixel 2q+2 -> output pixel 2q+1: K elements 0..23, columns 24..47).  Issued: dq = 0 as three K steps of N = 48,
+// dq = -1 as K steps 1, 2 with N = 32 (columns 0..31), dq = +1 as K steps 0, 1 with N = 32 on columns 16..47 (B rows and
+// accumulator columns shifted by 16): 21 instructions instead of 27, and everything skipped is exactly zero.
+__device__ __forceinline__ void halo_issue_chunk_pair24(uint32_t d_addr, uint32_t a_lo, uint32_t b_lo, uint32_t b_tap16,
+                                                        uint32_t idesc48, uint32_t idesc32, uint32_t accumulate) {
+  constexpr uint32_t rowb = 128u;
+  const uint32_t a_hi = umma_desc_hi(kHaloW * rowb, 2u);
+  const uint32_t b_hi = umma_desc_hi(8u * rowb, 2u);
+#pragma unroll
+  for (int dh = 0; dh < 3; ++dh) {   // dq = 0: initialises all 48 columns
+    const uint32_t a_t = a_lo + ((dh * kHaloW + 1) * rowb >> 4);
+    const uint32_t b_t = b_lo + (dh * 3 + 1) * b_tap16;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      umma_bf16_lohi(d_addr, a_t + 2 * k, a_hi, b_t + 2 * k, b_hi, idesc48, (dh | k) ? 1u : accumulate);
+  }
+#pragma unroll
+  for (int dh = 0; dh < 3; ++dh) {   // dq = -1
+    const uint32_t a_t = a_lo + ((dh * kHaloW) * rowb >> 4);
+    const uint32_t b_t = b_lo + (dh * 3) * b_tap16;
+#pragma unroll
+    for (int k = 1; k < 3; ++k) umma_bf16_lohi(d_addr, a_t + 2 * k, a_hi, b_t + 2 * k, b_hi, idesc32, 1u);
+  }
+#pragma unroll
+  for (int dh = 0; dh < 3; ++dh) {   // dq = +1
+    const uint32_t a_t = a_lo + ((dh * kHaloW + 2) * rowb >> 4);
+    const uint32_t b_t = b_lo + (dh * 3 + 2) * b_tap16 + (16u * rowb >> 4);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) umma_bf16_lohi(d_addr + 16u, a_t + 2 * k, a_hi, b_t + 2 * k, b_hi, idesc32, 1u);
+  }
+}
+
 // Epilogue of the halo kernel: 8 warps, two per TMEM lane quarter (thread <-> output pixel), each pair splitting the
 // tile's columns in halves.  The epilogue warps share their schedulers with nobody, so the loop is written for a short
 // dependent chain: destinations per 16-column chunk are precomputed in shared memory (s_chunk), TMEM loads are issued
@@ -175,6 +214,7 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
   const int tiles_w = p.tiles_w, tiles_per_n = p.tiles_w * p.tiles_h;
   const int H = p.H, W = p.W, stat_C = p.stat_C;
   const int G = p.G, bn1 = p.bn1;
+  const int fold = p.stat_fold;
   float* const stat_sum = p.stat_sum;
   float* const stat_sq = p.stat_sq;
   constexpr int NR = RACC > 0 ? RACC / P : 1;   // columns of this warp's part
@@ -190,8 +230,10 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
   auto flush_cols = [&](int n) {
     asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
     for (int i = etid; i < BN; i += kEpiThreads) {
-      if (ntile * bn1 + (i % bn1) >= stat_C) continue;   // GEMM pad column of a dense tensor: no such channel
-      const int64_t o = static_cast<int64_t>(n) * stat_C + ntile * bn1 + (i % bn1);   // G = 2: both rows -> one channel
+      const int gc = ntile * bn1 + (i % bn1);            // G = 2: both rows -> one channel
+      if (gc >= stat_C) continue;                        // GEMM pad column of a dense tensor: no such channel
+      // (pixel-pair view: the columns of both pixels of a pair belong to one channel)
+      const int64_t o = fold > 0 ? static_cast<int64_t>(n) * fold + gc % fold : static_cast<int64_t>(n) * stat_C + gc;
       const float t0 = s_part[0][0][i] + s_part[1][0][i] + s_part[2][0][i] + s_part[3][0][i];
       float t1 = s_part[0][1][i] + s_part[1][1][i] + s_part[2][1][i] + s_part[3][1][i];
       if (bwd) t1 *= p.bwd_rstd[o];   // sum gg * (y - mean)  ->  sum gg * xhat
@@ -458,7 +500,10 @@ __global__ void __launch_bounds__((MINB == 2 ? 64 : 96) + 128 * P, MINB) conv_ha
   pdl_trigger();
   pdl_wait();
   if (p.bias != nullptr) {   // (uniform) the bias vector comes out of the parameter pack of this step
-    for (int i = tid; i < 256; i += blockDim.x) s_bias[i] = i < BN ? p.bias[ntile * bn1 + (i % bn1)] : 0.f;
+    for (int i = tid; i < 256; i += blockDim.x) {
+      const int gc = ntile * bn1 + (i % bn1);
+      s_bias[i] = i >= BN ? 0.f : (p.stat_fold > 0 ? (gc < p.stat_C ? p.bias[gc % p.stat_fold] : 0.f) : p.bias[gc]);
+    }
     __syncthreads();
   }
 
@@ -588,6 +633,7 @@ __global__ void __launch_bounds__((MINB == 2 ? 64 : 96) + 128 * P, MINB) conv_ha
       }
     } else if (L < nlanes && elect_one()) {
       const uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      const uint32_t idesc_p48 = umma_idesc_bf16(128, 48, 0, 0), idesc_p32 = umma_idesc_bf16(128, 32, 0, 0);
       const uint32_t idesc1 = umma_idesc_bf16(128, bn1, 0, 0);
       const uint32_t b_tap16 = static_cast<uint32_t>(p.b_tap_bytes) >> 4;
       const bool g2 = p.G == 2;
@@ -637,6 +683,8 @@ __global__ void __launch_bounds__((MINB == 2 ? 64 : 96) + 128 * P, MINB) conv_ha
           const uint32_t kind = cb >> 30;   // 0: 32 wide, 1: 32 wide minus one K step, 2: 64 wide, 3: 64 wide minus one
           if (no_mma) {
             // debug: no MMAs
+          } else if (p.pair24) {
+            halo_issue_chunk_pair24(d_addr, a_lo, b_lo, b_tap16, idesc_p48, idesc_p32, accumulate);
           } else if (g2) {
             if (kind == 2) halo_issue_chunk_g2<64, 32>(d_addr, a_lo, b_lo, 3 * b_tap16, idesc1, idesc, accumulate);
             else if (kind == 0) halo_issue_chunk_g2<32, 32>(d_addr, a_lo, b_lo, 3 * b_tap16, idesc1, idesc, accumulate);
@@ -1005,6 +1053,8 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
     if (col != d->ncols) return set_error(MTBC_ERR_INVALID, "conv_gemm: output slices do not tile ncols");
   }
   if (d->H % 16 != 0 || d->W % 8 != 0 || d->w_ntaps != 9 || d->ncols % 32 != 0) return 1;
+  if (d->stat_fold != 0 && (d->stat_fold < 0 || d->nouts != 0 || d->bwd_y != nullptr || d->stat_C % d->stat_fold != 0))
+    return set_error(MTBC_ERR_INVALID, "conv_gemm: pixel-pair view: single output, no fused backward statistics, stat_C %% stat_fold == 0");
   // every view must appear with the full 3x3 stencil, tap index = (dh+1)*3 + (dw+1), one weight column offset
   int wk0[MTBC_MAX_VIEWS];
   int seen[MTBC_MAX_VIEWS];
@@ -1129,7 +1179,12 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
   op->ctas_per_sm = ctas_per_sm;
   {
     const char* e_env = getenv("MTBC_HALO_EPI");
-    const bool want4 = (G == 2 && p.BN == 64) && !(e_env && e_env[0] == '2');
+    // (pixel-pair view of a 24 -> 24 layer: G = 1, 64 columns with statistics: the 8-warp epilogue walks 32 columns
+    //  per warp and tile; MTBC_HALO_EPI4_G1=1 tries the same for every G = 1 statistics layer of 64 columns)
+    const char* e1_env = getenv("MTBC_HALO_EPI4_G1");
+    const bool g1_64 = G == 1 && p.BN == 64 && d->stat_sum != nullptr &&
+                       (d->stat_fold > 0 || (e1_env && e1_env[0] == '1'));
+    const bool want4 = ((G == 2 && p.BN == 64) || g1_64) && !(e_env && e_env[0] == '2');
     if (want4) {   // 16 epilogue warps, one CTA per SM (576 threads)
       if (ctas_per_sm == 2) {
         int st1 = (200 * 1024 - p.b_total_bytes) / p.a_stage_bytes;
@@ -1169,9 +1224,16 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
       p.lanes = 1;
     }
   }
+  {
+    // zero blocks of the pair operand are not issued (halo_issue_chunk_pair24); MTBC_PAIR_SKIP=0 issues all 27
+    const char* ps_env = getenv("MTBC_PAIR_SKIP");
+    p.pair24 = (d->stat_fold == 24 && d->nviews == 1 && d->views[0].C == 48 && d->ncols == 64 && BN == 64 && G == 1 &&
+                p.src[0].kc == 64 && p.src[0].nchunk == 1 && p.lanes != 3 && !(ps_env && ps_env[0] == '0')) ? 1 : 0;
+  }
   int gx = sm_count() * ctas_per_sm;
   if (gx > p.n_mtiles) gx = p.n_mtiles;
   p.stat_C = d->stat_C;
+  p.stat_fold = d->stat_fold;
   if (d->nouts > 0) {
     p.nouts = d->nouts;
     for (int i = 0; i < d->nouts; ++i) {

@@ -214,6 +214,29 @@ __global__ void __launch_bounds__(256) param_jobs_kernel(const ParamJobDev* __re
         if (j.dst1) put_w<float>(static_cast<float*>(j.dst1) + od, w[e], part);
       }
     }
+  } else if (j.kind == MTBC_JOB_PACK_CONV_PAIR) {
+    // i: Cout, Cin, c_begin, c_count, rows, ld, k0, n0, Ks, Np, dgrad (include/mtbc.h).  One element per
+    // (tap row, pair offset, input parity, output parity, co, ci): the non-zero elements of the pixel-pair operand.
+    const int Cout = j.i[0], Cin = j.i[1], c_begin = j.i[2], c_count = j.i[3], rows = j.i[4], ld = j.i[5], k0 = j.i[6],
+              n0 = j.i[7], Ks = j.i[8], Np = j.i[9], dgrad = j.i[10];
+    const int64_t per_tap = 4ll * Cout * c_count;
+    const int64_t total = 9 * per_tap;
+    const float* w = static_cast<const float*>(j.src);
+    __nv_bfloat16* wp = static_cast<__nv_bfloat16*>(j.dst0);
+    for (int64_t e = begin + threadIdx.x; e < begin + kChunk && e < total; e += 256) {
+      const int tapp = static_cast<int>(e / per_tap);
+      int r = static_cast<int>(e - tapp * per_tap);
+      const int ci = r % c_count; r /= c_count;
+      const int co = r % Cout; r /= Cout;
+      const int par = r & 1, op = r >> 1;
+      const int dh = tapp / 3 - 1, dq = tapp % 3 - 1;
+      const int dw = 2 * dq + par - op;
+      if (dw < -1 || dw > 1) continue;
+      const int kh = dgrad ? 1 - dh : dh + 1, kw = dgrad ? 1 - dw : dw + 1;
+      const float v = w[((static_cast<int64_t>(co) * Cin + c_begin + ci) * 3 + kh) * 3 + kw];
+      const int n = dgrad ? ci : co, k = dgrad ? co : ci;
+      wp[(static_cast<int64_t>(tapp) * rows + n0 + op * Np + n) * ld + k0 + par * Ks + k] = __float2bfloat16(v);
+    }
   } else if (j.kind == MTBC_JOB_UNPACK_CONV) {
     // i: rows, ld, k0, Cout, Cin, ksz, c_begin, c_count, add.  Same 32 x 32 x taps tile, the other way round.
     const int local = blockIdx.x - chunk_first[blockIdx.x];
@@ -263,6 +286,7 @@ static int64_t job_elems(const mtbc_param_job& j) {
     case MTBC_JOB_PACK_CONVT: return static_cast<int64_t>(j.i[0]) * j.i[1] * j.i[2] * j.i[2];
     case MTBC_JOB_UNPACK_CONV: return static_cast<int64_t>(j.i[3]) * j.i[7] * j.i[5] * j.i[5];
     case MTBC_JOB_UNPACK_CONVT: return static_cast<int64_t>(j.i[2]) * j.i[3] * j.i[4] * j.i[4];
+    case MTBC_JOB_PACK_CONV_PAIR: return 36ll * j.i[0] * j.i[3];
     default: return -1;
   }
 }
@@ -276,6 +300,13 @@ int param_jobs_create(const mtbc_param_job* jobs, int n, OpBase** out) {
     const bool is_pack = jobs[a].kind == MTBC_JOB_PACK_CONV || jobs[a].kind == MTBC_JOB_PACK_CONVT;
     if (e < 0 || !jobs[a].src || !(jobs[a].dst0 || (is_pack && jobs[a].dst1)))
       return set_error(MTBC_ERR_INVALID, "param_jobs: job %d is malformed", a);
+    if (jobs[a].kind == MTBC_JOB_PACK_CONV_PAIR) {
+      const int32_t* i = jobs[a].i;   // Cout, Cin, c_begin, c_count, rows, ld, k0, n0, Ks, Np, dgrad
+      const int nn = i[10] ? i[3] : i[0], kk = i[10] ? i[0] : i[3];
+      if (i[0] < 1 || i[3] < 1 || i[2] < 0 || i[2] + i[3] > i[1] || kk > i[8] || nn > i[9] || i[6] < 0 || i[7] < 0 ||
+          i[6] + i[8] + kk > i[5] || i[7] + i[9] + nn > i[4])
+        return set_error(MTBC_ERR_INVALID, "param_jobs: job %d: pair pack does not fit its operand", a);
+    }
     h[a].kind = jobs[a].kind;
     for (int k = 0; k < 11; ++k) h[a].i[k] = jobs[a].i[k];
     h[a].src = jobs[a].src; h[a].dst0 = jobs[a].dst0; h[a].dst1 = jobs[a].dst1;

@@ -89,6 +89,13 @@ class Feat:
         return self.t[..., : self.C].permute(0, 3, 1, 2).float().contiguous()
 
 
+def pair_view(f: Feat) -> Feat:
+    """The same memory as (N, H, W/2, 2*Cp): one row of the view = two neighbouring pixels (dense tensors only: the
+    channels that exist fill the pitch, so a pair is 2*C contiguous real channels)."""
+    assert f.C == f.Cp and f.W % 2 == 0 and f.t.is_contiguous(), (f.C, f.Cp, f.W)
+    return Feat(f.t.view(f.N, f.H, f.W // 2, 2 * f.Cp), 2 * f.C)
+
+
 def _view(f: Feat) -> ActView:
     v = ActView()
     v.ptr = f.t.data_ptr()
@@ -156,8 +163,10 @@ def _set_dtype(d: ConvGemmDesc, feats: Sequence[Feat], wpack: torch.Tensor, wpac
 def conv3x3_fwd_op(srcs: Sequence[Feat], wpack: torch.Tensor, out: Feat, bias: Optional[torch.Tensor] = None,
                    stat_sum: Optional[torch.Tensor] = None, stat_sq: Optional[torch.Tensor] = None,
                    accumulate: bool = False, ksz: int = 3, kind: str = "conv3x3_fwd",
-                   wpack_lo: Optional[torch.Tensor] = None, bwd_fuse=None) -> Op:
+                   wpack_lo: Optional[torch.Tensor] = None, bwd_fuse=None, stat_fold: int = 0) -> Op:
     """wpack: bf16 (or fp32 holding TF32 values) [ksz*ksz][out.Ck][Ktot] laid out by `k_offsets(srcs)`.
+    stat_fold > 0: `srcs` / `out` are pixel-pair views (`pair_view`) and wpack the paired operand (JOB_PACK_CONV_PAIR);
+    statistics / bias are indexed by column % stat_fold (mtbc_conv_gemm_desc.stat_fold).
     bwd_fuse = (y Feat, mean, rstd, gamma | None, beta | None, slope): fused InstanceNorm + LeakyReLU backward statistics
     (mtbc_conv_gemm_desc.bwd_y); stat_sum / stat_sq then receive s1 / s2.  Raises MtbcError when the shape is not served."""
     offs, ktot = k_offsets(srcs)
@@ -182,6 +191,7 @@ def conv3x3_fwd_op(srcs: Sequence[Feat], wpack: torch.Tensor, out: Feat, bias: O
     d.stat_sum = None if stat_sum is None else stat_sum.data_ptr()
     d.stat_sq = None if stat_sq is None else stat_sq.data_ptr()
     d.stat_C = out.Cp
+    d.stat_fold = int(stat_fold)
     d.accumulate = int(accumulate)
     d.nouts = 0
     keep = [*(s.t for s in srcs), wpack, wpack_lo, out.t, bias, stat_sum, stat_sq]

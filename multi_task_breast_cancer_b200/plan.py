@@ -365,8 +365,18 @@ class Plan:
         # bias gradient is identically zero (see backward below), and y is stored closer to zero-mean (fewer bf16
         # mantissa bits spent on a DC level).  It also takes 16 adds per chunk out of the epilogue's critical path.
         bias = None
-        op = ops.conv3x3_fwd_op(feats, pk["wf"], y.feat, bias=bias, stat_sum=ssum if fused else None,
-                                stat_sq=ssq if fused else None, wpack_lo=pk.get("wf_lo"))
+        op = None
+        if self._pair_ok(feats, y.feat, fused):
+            # pixel-pair view: the same convolution over (N, H, W/2, 2C) tensors -- one 96-byte TMA box row
+            # per two pixels of a dense 24-channel tensor instead of two 48-byte ones, K = 48 = three full K steps
+            try:
+                op = ops.conv3x3_fwd_op([ops.pair_view(feats[0])], self._pair_pack(w, pk, feats[0], y.feat),
+                                        ops.pair_view(y.feat), bias=bias, stat_sum=ssum, stat_sq=ssq, stat_fold=Cp)
+            except _lib.MtbcError:
+                op = None
+        if op is None:
+            op = ops.conv3x3_fwd_op(feats, pk["wf"], y.feat, bias=bias, stat_sum=ssum if fused else None,
+                                    stat_sq=ssq if fused else None, wpack_lo=pk.get("wf_lo"))
         self.tc_flops_fwd += op.flops
         npx = N * H * Wd
         wbytes = 2.0 * 9 * Cin * Cout
@@ -450,6 +460,27 @@ class Plan:
             pk["wf_lo"] = wf_lo
         self._packed[key] = pk
         return pk
+
+    def _pair_ok(self, feats: Sequence[Feat], y: Feat, fused: bool) -> bool:
+        """Single dense source and dense output whose pixel pairs fit one 128-byte row / 64 GEMM columns, planes the
+        halo kernel tiles in the pair view (MTBC_PAIR=0 switches the view off)."""
+        if os.environ.get("MTBC_PAIR", "0") != "1" or self.fp32 or not fused or len(feats) != 1:
+            return False
+        f = feats[0]
+        # 24-channel tensors: a pair is 48 channels = three full K = 16 steps and 48 of 64 columns; with 32 channels the
+        # pair operand would be half zeros at no saving in padding
+        return (f.C == f.Cp and y.C == y.Cp and 32 < 2 * f.Cp <= 48 and 32 < 2 * y.Cp <= 48
+                and y.H % 16 == 0 and y.W % 16 == 0)
+
+    def _pair_pack(self, w: str, pk: dict, f: Feat, y: Feat) -> torch.Tensor:
+        """Forward operand of the pixel-pair view: [9 = (dh, dq)][(op, co) -> 64][(par, ci) -> 64] (JOB_PACK_CONV_PAIR)."""
+        if "wfp" not in pk:
+            Wt = self.P(w)
+            wfp = torch.zeros(9, ops.pad32(2 * y.Cp), ops.pad32(2 * f.Cp), dtype=torch.bfloat16, device=self.device)
+            self.pack_jobs.add(_lib.JOB_PACK_CONV_PAIR, [Wt.shape[0], Wt.shape[1], 0, Wt.shape[1], wfp.shape[1],
+                                                         wfp.shape[2], 0, 0, f.Cp, y.Cp, 0], Wt, wfp)
+            pk["wfp"] = wfp
+        return pk["wfp"]
 
     def _dgrad_pack(self, w: str, pk: dict, fused: bool):
         """Data-gradient operand(s) of a conv weight, created when the backward is emitted: one tall pack

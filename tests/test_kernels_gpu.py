@@ -45,6 +45,27 @@ def test_conv3x3_forward(D, N, H, W, src, cout, kw):
     _run(D, D.conv_fwd_case, N, H, W, src, cout, **kw)
 
 
+# the same convolution over pixel pairs (96-byte TMA rows for dense 24-channel tensors): paired operand, result,
+# per-channel statistics folded over the two pixels of a pair; several samples per CTA range, bias, the benchmark shape
+@pytest.mark.parametrize("args", [(2, 16, 32, 24, 24), (3, 48, 64, 24, 24, True), (2, 64, 64, 24, 24),
+                                  (32, 256, 256, 24, 24)])
+def test_conv3x3_forward_through_the_pixel_pair_view(D, args):
+    _run(D, D.conv_fwd_pair_case, *args)
+
+
+def test_pixel_pair_view_refuses_what_it_cannot_serve(D):
+    """The generic (small-plane) kernel knows nothing about folded statistics: creation must fail, not mis-index."""
+    import torch
+    from multi_task_breast_cancer_b200 import _lib, ops
+    from multi_task_breast_cancer_b200.ops import Feat
+    x = Feat.empty(2, 8, 16, 24); y = Feat.empty(2, 8, 16, 24)     # H = 8: not a halo plane
+    xp, yp = ops.pair_view(x), ops.pair_view(y)
+    w = torch.zeros(9, yp.Ck, xp.Ck, dtype=torch.bfloat16, device="cuda")
+    st = [torch.zeros(2, 24, device="cuda") for _ in range(2)]
+    with pytest.raises(_lib.MtbcError):
+        ops.conv3x3_fwd_op([xp], w, yp, stat_sum=st[0], stat_sq=st[1], stat_fold=24)
+
+
 # fused InstanceNorm + LeakyReLU backward statistics in the data-gradient epilogue: G = 2 (24 / 32 channels on planes with
 # H % 32 == 0), G = 1 with 32 columns (H % 32 != 0), 64 columns, two samples per CTA range (sample change mid-range), and
 # the benchmark's level-0 / level-1 shapes

@@ -92,6 +92,78 @@ def conv_fwd_case(N, H, W, src_C, Cout, bias=True, stats=True, identity=False):
     run_case(fn, name)
 
 
+def pair_operand_ref(w, c_begin, c_count, rows, ld, k0, n0, Ks, Np, dgrad):
+    """Reference of MTBC_JOB_PACK_CONV_PAIR (include/mtbc.h): the 3x3 conv over pixel pairs, element by element."""
+    Cout = w.shape[0]
+    wp = torch.zeros(9, rows, ld, device=w.device)
+    for dh in (-1, 0, 1):
+        for dq in (-1, 0, 1):
+            for par in (0, 1):
+                for op in (0, 1):
+                    dw = 2 * dq + par - op
+                    if abs(dw) > 1:
+                        continue
+                    kh, kw = (1 - dh, 1 - dw) if dgrad else (dh + 1, dw + 1)
+                    blk = w[:, c_begin:c_begin + c_count, kh, kw]   # [co][ci]
+                    t = (dh + 1) * 3 + dq + 1
+                    if dgrad:   # rows = ci, columns = co
+                        wp[t, n0 + op * Np:n0 + op * Np + c_count, k0 + par * Ks:k0 + par * Ks + Cout] = blk.t()
+                    else:
+                        wp[t, n0 + op * Np:n0 + op * Np + Cout, k0 + par * Ks:k0 + par * Ks + c_count] = blk
+    return wp
+
+
+def conv_fwd_pair_case(N, H, W, C, Cout, bias=False):
+    """3x3 conv of a dense C-channel tensor through the pixel-pair view (mtbc_conv_gemm_desc.stat_fold): the paired
+    operand from the batched pack job against its element-wise definition, the result and the per-channel statistics
+    against torch fp32, and against the same conv through the per-pixel view of the same kernel."""
+    name = f"conv3x3_fwd PAIR N{N} {H}x{W} {C}->{Cout} bias={bias}"
+
+    def fn():
+        import ctypes as Ct
+        from multi_task_breast_cancer_b200 import plan as P
+        x = rnd(N, C, H, W)
+        w = rnd(Cout, C, 3, 3, scale=0.1)
+        b = rnd(Cout) if bias else None
+        src = Feat.from_nchw(x)
+        out = Feat.empty(N, H, W, Cout)
+        assert src.Cp == C and out.Cp == Cout, "pair view needs dense tensors"
+        sp, outp = ops.pair_view(src), ops.pair_view(out)
+        wfp = torch.zeros(9, outp.Ck, sp.Ck, dtype=torch.bfloat16, device=dev)
+        jt = P.JobTable()
+        jt.add(_lib.JOB_PACK_CONV_PAIR, [Cout, C, 0, C, wfp.shape[1], wfp.shape[2], 0, 0, src.Cp, out.Cp, 0], w, wfp)
+        st = Ct.c_void_p(ops.stream_ptr())
+        for l in jt.launch():
+            l(st)
+        torch.cuda.synchronize()
+        report(name + " [operand]", wfp, pair_operand_ref(w, 0, C, wfp.shape[1], wfp.shape[2], 0, 0, C, Cout, 0), tol=1e-6)
+        bp = None
+        if bias:
+            bp = torch.zeros(out.Ck, device=dev)
+            bp[:Cout] = b
+        ssum = torch.zeros(N, out.Cp, device=dev)
+        ssq = torch.zeros(N, out.Cp, device=dev)
+        op = ops.conv3x3_fwd_op([sp], wfp, outp, bias=bp, stat_sum=ssum, stat_sq=ssq, stat_fold=out.Cp)
+        op.launch()
+        torch.cuda.synchronize()
+        ref = F.conv2d(x, w, b, padding=1)
+        report(name, out.to_nchw(), ref)
+        report(name + " [sum]", ssum[:, :Cout], ref.sum((2, 3)), tol=1e-2)
+        report(name + " [sumsq]", ssq[:, :Cout], (ref * ref).sum((2, 3)), tol=1e-2)
+        # the per-pixel view of the same kernel: same products, other summation order inside the fp32 accumulator
+        out1 = Feat.empty(N, H, W, Cout)
+        offs, ktot = ops.k_offsets([src])
+        wf = torch.zeros(9, out1.Ck, ktot, dtype=torch.bfloat16, device=dev)
+        ops.pack_conv_weight(w, [C], offs, wf, [None])
+        s1 = torch.zeros(N, out1.Cp, device=dev); q1 = torch.zeros(N, out1.Cp, device=dev)
+        ops.conv3x3_fwd_op([src], wf, out1, bias=bp, stat_sum=s1, stat_sq=q1).launch()
+        torch.cuda.synchronize()
+        report(name + " [vs per-pixel view]", out.t, out1.t, tol=8e-3)
+        report(name + " [sumsq vs per-pixel view]", ssq, q1, tol=1e-4)
+
+    run_case(fn, name)
+
+
 def conv_dgrad_case(N, H, W, Cin, Cout, accumulate, dyscale=1.0):
     name = f"conv3x3_dgrad N{N} {H}x{W} {Cin}<-{Cout} acc={accumulate} dyscale={dyscale}"
 
