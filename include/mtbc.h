@@ -130,11 +130,12 @@ typedef struct {
   const float* bwd_gamma;
   const float* bwd_beta;
   float bwd_slope;
-  /* Pixel-pair view (stat_fold > 0; halo-eligible 3x3 forward convolutions only, no bwd_y): the caller describes a conv
+  /* Pixel-pair view (stat_fold > 0; halo-eligible 3x3 convolutions / data gradients, single output): the caller describes a conv
    * over the tensors viewed as (N, H, W/2, 2C) -- one TMA box row = two neighbouring pixels of a dense 24-channel tensor
    * (96 bytes) instead of one (48) -- with the paired weights of MTBC_JOB_PACK_CONV_PAIR, so GEMM column c = op * C + co
    * is output pixel 2q + op, channel co.  Statistics and bias are per CHANNEL: column c (< stat_C) adds into
-   * stat_sum[n][c % stat_fold] / stat_sq[n][c % stat_fold] (rows of stat_fold floats) and takes bias[c % stat_fold].
+   * stat_sum[n][c % stat_fold] / stat_sq[n][c % stat_fold] (rows of stat_fold floats) and takes bias[c % stat_fold];
+   * with bwd_y (the pair view of y) bwd_mean / bwd_rstd are [N][stat_fold] and bwd_gamma / bwd_beta indexed c % stat_fold.
    * Creation fails with MTBC_ERR_INVALID if the shape is not served by the halo kernel. */
   int32_t stat_fold;
 } mtbc_conv_gemm_desc;

@@ -264,10 +264,11 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
   // fused InstanceNorm backward: per accumulator column [0] mean, [1] gamma * rstd, [2] beta of sample n
   auto load_consts = [&](int n) {
     for (int i = etid; i < BN; i += kEpiThreads) {
-      const int c = ntile * bn1 + (i % bn1);
+      const int gc = ntile * bn1 + (i % bn1);
       float mu = 0.f, zc = 0.f, zb = 1.f;   // GEMM pad column: accumulator is exactly 0, any branch will do
-      if (c < stat_C) {
-        const int64_t o = static_cast<int64_t>(n) * stat_C + c;
+      if (gc < stat_C) {
+        const int c = fold > 0 ? gc % fold : gc;   // pixel-pair view: both pixels of a pair share the channel constants
+        const int64_t o = static_cast<int64_t>(n) * (fold > 0 ? fold : stat_C) + c;
         mu = p.bwd_mean[o];
         zc = (p.bwd_gamma ? p.bwd_gamma[c] : 1.f) * p.bwd_rstd[o];
         zb = p.bwd_beta ? p.bwd_beta[c] : 0.f;
@@ -1053,8 +1054,8 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
     if (col != d->ncols) return set_error(MTBC_ERR_INVALID, "conv_gemm: output slices do not tile ncols");
   }
   if (d->H % 16 != 0 || d->W % 8 != 0 || d->w_ntaps != 9 || d->ncols % 32 != 0) return 1;
-  if (d->stat_fold != 0 && (d->stat_fold < 0 || d->nouts != 0 || d->bwd_y != nullptr || d->stat_C % d->stat_fold != 0))
-    return set_error(MTBC_ERR_INVALID, "conv_gemm: pixel-pair view: single output, no fused backward statistics, stat_C %% stat_fold == 0");
+  if (d->stat_fold != 0 && (d->stat_fold < 0 || d->nouts != 0 || d->stat_C % d->stat_fold != 0))
+    return set_error(MTBC_ERR_INVALID, "conv_gemm: pixel-pair view: single output, stat_C %% stat_fold == 0");
   // every view must appear with the full 3x3 stencil, tap index = (dh+1)*3 + (dw+1), one weight column offset
   int wk0[MTBC_MAX_VIEWS];
   int seen[MTBC_MAX_VIEWS];
@@ -1264,13 +1265,14 @@ int conv_halo_try_create(const mtbc_conv_gemm_desc* d, OpBase** out) {
     //  for 24 / 40 / 56 channels, two-way for 48, 4- / 8-way for 32 / 64.  Measured at B = 32 (tools/diag_fused_dgrad.py):
     //  24 channels @256^2 66 -> 89 us for a 40 us reduction pass saved; 48 channels @128^2 34 -> 57 us for 21 us saved:
     //  only the conflict-free pitches are served)
-    if ((d->out_C / 8) % 2 == 0 || d->ncols != BN) {
+    // (pixel-pair view of a 24-channel tensor: 96-byte rows, two-way conflicts on the y reads, and half the halo rows)
+    if (((d->out_C / 8) % 2 == 0 && !(d->stat_fold > 0 && d->out_C == 48)) || d->ncols != BN) {
       delete op;
       return set_error(MTBC_ERR_INVALID, "conv_gemm: fused InstanceNorm backward statistics: channel pitch %d not served", d->out_C);
     }
     p.y_rowb = d->out_C * 2;
     p.y_stage_bytes = (8 * 16 * G * p.y_rowb + 127) & ~127;
-    p.y_stages = 3;
+    p.y_stages = d->stat_fold > 0 ? 2 : 3;   // (pair view: 72 KB of paired weights; two y slots leave four halo stages)
     const int ybytes = p.y_stages * p.y_stage_bytes;
     while (p.stages > 2 && p.b_total_bytes + p.stages * p.a_stage_bytes + ybytes + 1024 > 212 * 1024) p.stages -= 2;
     if (p.b_total_bytes + p.stages * p.a_stage_bytes + ybytes + 1024 > 212 * 1024 || total_chunks != 1) {

@@ -198,7 +198,8 @@ def conv3x3_fwd_op(srcs: Sequence[Feat], wpack: torch.Tensor, out: Feat, bias: O
     if bwd_fuse is not None:
         yf, mean, rstd, gamma, beta, slope = bwd_fuse
         assert (yf.N, yf.H, yf.W, yf.Cp) == (out.N, out.H, out.W, out.Cp) and not yf.fp32
-        assert mean.shape == (out.N, out.Cp) and rstd.shape == mean.shape and stat_sum is not None and stat_sq is not None
+        assert mean.shape == (out.N, stat_fold or out.Cp) and rstd.shape == mean.shape
+        assert stat_sum is not None and stat_sq is not None
         d.bwd_y = yf.t.data_ptr(); d.bwd_mean = mean.data_ptr(); d.bwd_rstd = rstd.data_ptr()
         d.bwd_gamma = None if gamma is None else gamma.data_ptr()
         d.bwd_beta = None if beta is None else beta.data_ptr()
@@ -271,12 +272,12 @@ def conv3x3_s2_wgrad_op(x: Feat, dy: Feat, dw_acc: torch.Tensor, splits: int = 0
 
 def conv3x3_dgrad_op(dy: Feat, wd: torch.Tensor, dx: Feat, accumulate: bool, ksz: int = 3,
                      wd_lo: Optional[torch.Tensor] = None, bwd_fuse=None, s1: Optional[torch.Tensor] = None,
-                     s2: Optional[torch.Tensor] = None) -> Op:
+                     s2: Optional[torch.Tensor] = None, stat_fold: int = 0) -> Op:
     """wd: bf16 [ksz*ksz][dx.Ck][dy.Ck] (flipped taps, transposed channels) -> dx (+)= conv(dy, wd).
     bwd_fuse (see conv3x3_fwd_op): dx is the gradient of a = LeakyReLU(IN(y)); the launch stores gg instead and adds the
     two plane sums of the InstanceNorm backward to s1 / s2."""
     return conv3x3_fwd_op([dy], wd, dx, accumulate=accumulate, ksz=ksz, kind="conv3x3_dgrad", wpack_lo=wd_lo,
-                          bwd_fuse=bwd_fuse, stat_sum=s1, stat_sq=s2)
+                          bwd_fuse=bwd_fuse, stat_sum=s1, stat_sq=s2, stat_fold=stat_fold)
 
 
 def conv3x3_dgrad_multi_op(dy: Feat, wd_all: torch.Tensor, dxs: Sequence[Feat], accumulates: Sequence[bool]) -> Op:

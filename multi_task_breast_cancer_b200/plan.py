@@ -464,7 +464,7 @@ class Plan:
     def _pair_ok(self, feats: Sequence[Feat], y: Feat, fused: bool) -> bool:
         """Single dense source and dense output whose pixel pairs fit one 128-byte row / 64 GEMM columns, planes the
         halo kernel tiles in the pair view (MTBC_PAIR=0 switches the view off)."""
-        if os.environ.get("MTBC_PAIR", "0") != "1" or self.fp32 or not fused or len(feats) != 1:
+        if os.environ.get("MTBC_PAIR", "1") == "0" or self.fp32 or not fused or len(feats) != 1:
             return False
         f = feats[0]
         # 24-channel tensors: a pair is 48 channels = three full K = 16 steps and 48 of 64 columns; with 32 channels the
@@ -481,6 +481,18 @@ class Plan:
                                                          wfp.shape[2], 0, 0, f.Cp, y.Cp, 0], Wt, wfp)
             pk["wfp"] = wfp
         return pk["wfp"]
+
+    def _pair_pack_dgrad(self, cand: dict, g: Feat) -> torch.Tensor:
+        """Data-gradient operand of the pixel-pair view for one concat source: [9][(op, ci) -> 64][(par, co) -> 64]."""
+        pk, key = cand["pk"], ("wdp", cand["c0"])
+        if key not in pk:
+            Wt = self.P(cand["w"])
+            dy = cand["dy"]
+            wdp = torch.zeros(9, ops.pad32(2 * g.Cp), ops.pad32(2 * dy.Cp), dtype=torch.bfloat16, device=self.device)
+            self.pack_jobs.add(_lib.JOB_PACK_CONV_PAIR, [Wt.shape[0], Wt.shape[1], cand["c0"], cand["cs"], wdp.shape[1],
+                                                         wdp.shape[2], 0, 0, dy.Cp, g.Cp, 1], Wt, wdp)
+            pk[key] = wdp
+        return pk[key]
 
     def _dgrad_pack(self, w: str, pk: dict, fused: bool):
         """Data-gradient operand(s) of a conv weight, created when the backward is emitted: one tall pack
@@ -534,6 +546,7 @@ class Plan:
                 for s in srcs:
                     s.g_init = True
                 return
+        c0 = 0
         for s, wd in zip(srcs, self._dgrad_pack(w, pk, False)):
             g = s.grad()
             wd, wd_lo = wd if isinstance(wd, tuple) else (wd, None)
@@ -546,8 +559,9 @@ class Plan:
             if not s.g_init and not self.fp32 and not self.deterministic:
                 # first writer of this gradient: if it stays the only one, the producer's InstanceNorm backward takes
                 # its two plane sums from this launch's epilogue (_norm_act_bwd swaps the op)
-                s.fuse_cand = {"launch": l, "dy": dy, "wd": wd}
+                s.fuse_cand = {"launch": l, "dy": dy, "wd": wd, "w": w, "pk": pk, "c0": c0, "cs": s.feat.C}
             s.g_init = True
+            c0 += s.feat.C
 
     def _wg_accum(self, w: str, pk: dict) -> torch.Tensor:
         if w not in self._wg_acc:
@@ -604,9 +618,22 @@ class Plan:
             # `a` has ONE consumer, a 3x3 conv whose data gradient wrote a.g: that launch's epilogue already holds the
             # gradient in fp32, so it applies the LeakyReLU factor, stores gg and leaves sum(gg), sum(gg * xhat) in
             # s1 / s2 -- the reduction pass over (g, y) disappears (10 -> 6 B/elem + 2 B/elem read in the epilogue).
+            # The same launch through the pixel-pair view (dy, gradient and y as (N, H, W/2, 48) tensors) is built and
+            # tested but off: with the y tile in the epilogue this launch follows its bytes, not its box rows or MMAs --
+            # 94 -> 98 us at 24 channels @256^2, B = 32 (gpurun_out/r04c, MTBC_PAIR_DGRAD=1 switches it on)
+            if (os.environ.get("MTBC_PAIR_DGRAD", "0") == "1" and "w" in cand
+                    and self._pair_ok([cand["dy"]], a.g, True) and y.feat.C == y.feat.Cp):
+                try:
+                    fused = ops.conv3x3_dgrad_op(ops.pair_view(cand["dy"]), self._pair_pack_dgrad(cand, a.g),
+                                                 ops.pair_view(a.g), accumulate=False,
+                                                 bwd_fuse=(ops.pair_view(y.feat), mean, rstd, gv, bv, slope),
+                                                 s1=s1, s2=s2, stat_fold=Cp)
+                except _lib.MtbcError:
+                    fused = None
             try:
-                fused = ops.conv3x3_dgrad_op(cand["dy"], cand["wd"], a.g, accumulate=False,
-                                             bwd_fuse=(y.feat, mean, rstd, gv, bv, slope), s1=s1, s2=s2)
+                if fused is None:
+                    fused = ops.conv3x3_dgrad_op(cand["dy"], cand["wd"], a.g, accumulate=False,
+                                                 bwd_fuse=(y.feat, mean, rstd, gv, bv, slope), s1=s1, s2=s2)
             except _lib.MtbcError:
                 fused = None   # shape not served by the halo kernel's statistics epilogue: two-pass backward below
         if fused is not None:

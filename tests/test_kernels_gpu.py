@@ -53,6 +53,13 @@ def test_conv3x3_forward_through_the_pixel_pair_view(D, args):
     _run(D, D.conv_fwd_pair_case, *args)
 
 
+# ... and the data gradient with the fused InstanceNorm backward sums through the pair view (affine on / off, a sample
+# change inside a CTA's tile range, the benchmark shape)
+@pytest.mark.parametrize("args", [(2, 32, 32, 24, 24, True), (3, 48, 64, 24, 24, False), (32, 256, 256, 24, 24, True)])
+def test_conv3x3_data_gradient_with_fused_norm_backward_sums_through_the_pixel_pair_view(D, args):
+    _run(D, D.conv_dgrad_inbwd_case, *args, pair=True)
+
+
 def test_pixel_pair_view_refuses_what_it_cannot_serve(D):
     """The generic (small-plane) kernel knows nothing about folded statistics: creation must fail, not mis-index."""
     import torch

@@ -189,11 +189,11 @@ def conv_dgrad_case(N, H, W, Cin, Cout, accumulate, dyscale=1.0):
     run_case(fn, name)
 
 
-def conv_dgrad_inbwd_case(N, H, W, C, Cout, affine, slope=0.1):
+def conv_dgrad_inbwd_case(N, H, W, C, Cout, affine, slope=0.1, pair=False):
     """Data gradient of conv_1 with the InstanceNorm + LeakyReLU backward sums of its input's producer fused into the
     epilogue (mtbc_conv_gemm_desc.bwd_y), followed by the apply pass with slope = 1: dy of the whole
     conv -> IN -> LeakyReLU chain against torch autograd, and s1 / s2 against their definitions."""
-    name = f"conv3x3_dgrad+in_bwd N{N} {H}x{W} {C}<-{Cout} affine={affine}"
+    name = f"conv3x3_dgrad+in_bwd N{N} {H}x{W} {C}<-{Cout} affine={affine}" + (" PAIR" if pair else "")
 
     def fn():
         y = (rnd(N, C, H, W, scale=2.0) + 0.7).to(torch.bfloat16).float()     # stored pre-norm conv output of layer 0
@@ -219,7 +219,21 @@ def conv_dgrad_inbwd_case(N, H, W, C, Cout, affine, slope=0.1):
         wf = torch.zeros(9, dyf.Ck, ga.Ck, dtype=torch.bfloat16, device=dev)
         ops.pack_conv_weight(w, [C], [0], wf, [wd])
         s1 = torch.zeros(N, Cp, device=dev); s2 = torch.zeros(N, Cp, device=dev)
-        op = ops.conv3x3_dgrad_op(dyf, wd, ga, False, bwd_fuse=(yf, mean, rstd, gp, bp, slope), s1=s1, s2=s2)
+        if pair:   # the same launch through the pixel-pair view (dy, the gradient and y as (N, H, W/2, 2C) tensors)
+            import ctypes as Ct
+            from multi_task_breast_cancer_b200 import plan as P
+            dyp, gap, yp = ops.pair_view(dyf), ops.pair_view(ga), ops.pair_view(yf)
+            wdp = torch.zeros(9, gap.Ck, dyp.Ck, dtype=torch.bfloat16, device=dev)
+            jt = P.JobTable()
+            jt.add(_lib.JOB_PACK_CONV_PAIR, [Cout, C, 0, C, wdp.shape[1], wdp.shape[2], 0, 0, dyf.Cp, ga.Cp, 1], w, wdp)
+            for l in jt.launch():
+                l(Ct.c_void_p(ops.stream_ptr()))
+            torch.cuda.synchronize()
+            report(name + " [operand]", wdp, pair_operand_ref(w, 0, C, wdp.shape[1], wdp.shape[2], 0, 0, dyf.Cp, ga.Cp, 1), tol=1e-6)
+            op = ops.conv3x3_dgrad_op(dyp, wdp, gap, False, bwd_fuse=(yp, mean, rstd, gp, bp, slope), s1=s1, s2=s2,
+                                      stat_fold=Cp)
+        else:
+            op = ops.conv3x3_dgrad_op(dyf, wd, ga, False, bwd_fuse=(yf, mean, rstd, gp, bp, slope), s1=s1, s2=s2)
         op.launch()
         dy0 = Feat.empty(N, H, W, C)
         dg = torch.zeros(C, device=dev) if affine else None
