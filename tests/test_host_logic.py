@@ -211,3 +211,41 @@ def test_bf16_storage_alone_moves_gradients():
     e = ((gg["conv_2_0.convs.conv_0.conv.weight"] - gr["conv_2_0.convs.conv_0.conv.weight"]).norm()
          / gr["conv_2_0.convs.conv_0.conv.weight"].norm()).item()
     assert e < 2e-2, e
+
+
+def test_pixel_pair_operand_is_the_same_convolution():
+    """The operand MTBC_JOB_PACK_CONV_PAIR is defined to write (include/mtbc.h; element-wise restatement in
+    tools/diag_kernels.py::pair_operand_ref, which the GPU test compares the pack job with) turns the 3x3 conv over pixels
+    into a 3x3 conv over pixel PAIRS of the tensors viewed as (N, H, W/2, 2C): checked here in fp32 on the CPU, forward
+    and data gradient, for a concat source that starts at channel 8 of a wider weight."""
+    import sys
+    import torch.nn.functional as F
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from diag_kernels import pair_operand_ref
+    torch.manual_seed(0)
+    N, C, Co, H, W, c0 = 2, 24, 24, 8, 12, 8
+    wfull = torch.randn(Co, c0 + C + 5, 3, 3, dtype=torch.float64)
+    w = wfull[:, c0:c0 + C]
+    x = torch.randn(N, C, H, W, dtype=torch.float64)
+
+    def pairs(t):      # NCHW -> NCHW of the pair view: channel = parity * C + c, width W/2
+        n, c, h, ww = t.shape
+        return t.permute(0, 2, 3, 1).reshape(n, h, ww // 2, 2 * c).permute(0, 3, 1, 2)
+
+    def unpairs(t, c):
+        n, _, h, w2 = t.shape
+        return t.permute(0, 2, 3, 1).reshape(n, h, 2 * w2, c).permute(0, 3, 1, 2)
+
+    wp = pair_operand_ref(wfull, c0, C, 64, 64, 0, 0, C, Co, 0).double()
+    assert (wp != 0).sum().item() == (wfull[:, c0:c0 + C] != 0).sum().item() * 2      # every tap appears for both output parities
+    y = F.conv2d(pairs(x), wp[:, :2 * Co, :2 * C].reshape(3, 3, 2 * Co, 2 * C).permute(2, 3, 0, 1), padding=1)
+    assert torch.allclose(unpairs(y, Co), F.conv2d(x, w, padding=1), atol=1e-6)
+    dy = torch.randn(N, Co, H, W, dtype=torch.float64)
+    wd = pair_operand_ref(wfull, c0, C, 64, 64, 0, 0, Co, C, 1).double()
+    dx = F.conv2d(pairs(dy), wd[:, :2 * C, :2 * Co].reshape(3, 3, 2 * C, 2 * Co).permute(2, 3, 0, 1), padding=1)
+    assert torch.allclose(unpairs(dx, C), F.conv_transpose2d(dy, w, padding=1), atol=1e-6)
+    # structure the kernel's issue sequence relies on (halo_issue_chunk_pair24): outside dq = 0 only one corner is non-zero
+    for dh in range(3):
+        left, right = wp[dh * 3 + 0], wp[dh * 3 + 2]
+        assert left[Co:, :].abs().sum() == 0 and left[:, :C].abs().sum() == 0      # rows 0..23 x columns 24..47 only
+        assert right[:Co, :].abs().sum() == 0 and right[:, C:].abs().sum() == 0     # rows 24..47 x columns 0..23 only
