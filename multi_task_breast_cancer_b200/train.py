@@ -135,9 +135,17 @@ class TrainStep:
             self._build_launches()
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self._heads: Dict[Optional[int], torch.cuda.CUDAGraph] = {}   # first graph of a step, per staging slot (None: no copy)
+        # read-back of the loss vector (losses_to_host): stream, two snapshots, completion events; with a prefetched host
+        # batch the snapshot is the last node of the step's head graph (MTBC_SNAP_IN_GRAPH=0: an eager copy after it)
+        self._read_stream: Optional[torch.cuda.Stream] = None
+        self._loss_snap: List[torch.Tensor] = []
+        self._read_done: List[Optional[torch.cuda.Event]] = [None, None]
+        self._read_turn = 0
+        self._snap_slot: Optional[int] = None
+        import os as _os2
+        self._snap_in_graph = _os2.environ.get("MTBC_SNAP_IN_GRAPH", "1") != "0"
         self.comm_stream: Optional[torch.cuda.Stream] = None
         self.side_stream: Optional[torch.cuda.Stream] = None
-        import os as _os2
         self.side_enabled = _os2.environ.get("MTBC_SIDE_WGRAD", "1") != "0"
         self._copy_stream: Optional[torch.cuda.Stream] = None
         self._pending = None
@@ -385,6 +393,9 @@ class TrainStep:
         device copies staging slot -> static inputs, so a prefetched host batch costs no eager launch between replays."""
         g = torch.cuda.CUDAGraph()
         kw = dict(capture_error_mode="thread_local") if self.overlap else {}
+        snap = slot is not None and self._snap_in_graph
+        if snap:
+            self._ensure_readback()
         with torch.cuda.graph(g, **kw):
             if slot is not None:
                 sx, sm, so = self._stage[slot]
@@ -392,6 +403,10 @@ class TrainStep:
                 self.mask.copy_(sm, non_blocking=True)
                 self.onehot.copy_(so, non_blocking=True)
             self._run_list(self._head_launches())
+            if snap:
+                # the loss vector of this step, parked for `losses_to_host` (the objective is part of every head graph):
+                # as an eager 16-byte copy between two replays it exposed the next graph's start-up
+                self._loss_snap[slot].copy_(self.loss_out, non_blocking=True)
         return g
 
     def load_batch(self, x: torch.Tensor, mask: torch.Tensor, onehot: torch.Tensor):
@@ -457,6 +472,10 @@ class TrainStep:
                 head = self._heads.get(slot)
                 if head is None:
                     head = self._heads[slot] = self._capture_head(slot)
+                self._snap_slot = slot if (slot is not None and self._snap_in_graph) else None
+                if self._snap_slot is not None and self._read_done[slot] is not None:
+                    # the host read of two steps ago must have left the snapshot this replay overwrites
+                    torch.cuda.current_stream(self.device).wait_event(self._read_done[slot])
                 if self.overlap:
                     self._run_step_dp(head)
                 else:
@@ -468,6 +487,7 @@ class TrainStep:
                 self.steps_done += 1
                 return
             self._consume_pending()
+            self._snap_slot = None
             if self.overlap:
                 self._run_step_dp()
             else:
@@ -500,16 +520,15 @@ class TrainStep:
         on a read-back stream from a snapshot taken on the compute stream, so the next step's launches never queue
         behind a copy engine that is busy with the next batch's host->device transfer."""
         main = torch.cuda.current_stream(self.device)
-        if getattr(self, "_read_stream", None) is None:
-            self._read_stream = torch.cuda.Stream(device=self.device)
-            self._loss_snap = [torch.zeros_like(self.loss_out) for _ in range(2)]
-            self._read_done = [None, None]
-            self._read_turn = 0
-        slot = self._read_turn & 1
-        self._read_turn += 1
-        if self._read_done[slot] is not None:
-            main.wait_event(self._read_done[slot])       # the read of two steps ago has left this snapshot
-        self._loss_snap[slot].copy_(self.loss_out, non_blocking=True)
+        self._ensure_readback()
+        if self._snap_slot is not None:
+            slot = self._snap_slot      # the step's graph has already parked the losses in this slot's snapshot
+        else:
+            slot = self._read_turn & 1
+            self._read_turn += 1
+            if self._read_done[slot] is not None:
+                main.wait_event(self._read_done[slot])       # the read of two steps ago has left this snapshot
+            self._loss_snap[slot].copy_(self.loss_out, non_blocking=True)
         ready = torch.cuda.Event()
         ready.record(main)
         rs = self._read_stream
@@ -520,6 +539,11 @@ class TrainStep:
             done.record(rs)
         self._read_done[slot] = done
         return done
+
+    def _ensure_readback(self):
+        if self._read_stream is None:
+            self._read_stream = torch.cuda.Stream(device=self.device)
+            self._loss_snap = [torch.zeros_like(self.loss_out) for _ in range(2)]
 
     def forward_backward_only(self):
         """Forward + loss + backward without the optimizer (parity tests)."""
