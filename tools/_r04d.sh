@@ -1,4 +1,6 @@
-# trajectory spread (nnU-Net) + micro-optimisations (32-bit index math, fused small-plane InstanceNorm backward)
+# trajectory spread (nnU-Net) + two micro-optimisations that were measured and NOT kept (32-bit index math in three
+# streaming kernels, cooperative InstanceNorm backward for small planes behind MTBC_FUSED_INBWD_SMALL: DESIGN 9); the
+# profile / bench legs below therefore only reproduce on the tree of that experiment
 mkdir -p gpurun_out
 O=gpurun_out
 timeout 200 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "instance_norm or head1x1 or pixel_pair" > $O/r04d_pytest_k.log 2>&1; echo "kernel pytest exit $?"; tail -3 $O/r04d_pytest_k.log
